@@ -1,0 +1,175 @@
+/*
+ * mgodpl_b200 — C ABI of the B200-native collision-query path.
+ *
+ * This is the drop-in boundary for ONE hot path of werner291/Multigoal-Orchard-Drone-Planning-Library ("the
+ * reference", paths below are relative to its checkout): RobotState -> forward kinematics -> box-vs-tree-mesh
+ * collision, i.e. check_link_collision / check_robot_collision / check_motion_collides / check_path_collides
+ * (src/planning/collision_detection.h:29-111), the goal sampler built on them (src/planning/goal_sampling.cpp:51-99)
+ * and the PRM edge-validation call sites (src/planning/tsp_over_prm.cpp:33-66).  The reference has no FFI of its
+ * own (single C++ process); these entry points are what a binding for this path would have to expose, and the C++
+ * facade in multigoal-orchard-drone-planning-library_b200/host/ re-creates the reference's signatures on top of them.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every function returns an int status (MGODPL_OK == 0) and never throws.
+ *    mgodpl_last_error() gives a thread-local message for the last non-OK status on the calling thread.
+ *  - a rigid transform is 7 doubles: translation x y z, then the unit quaternion x y z w
+ *    (src/math/Transform.h:20-23, src/math/Quaternion.h:25-27).
+ *  - a robot state is `stride` doubles: base transform (7) then `n_joint_values` joint values
+ *    (src/planning/RobotState.h:16-23).  n_joint_values may exceed the number of joint *variables*: the surplus is
+ *    ignored by FK but counts in the motion distance, exactly like the reference.
+ *  - result bitmasks: query i -> bit (i & 31) of word (i >> 5); tail bits are zero.  Bit set == collides.
+ *  - "_device" variants take device pointers and only enqueue work on `stream` (a cudaStream_t passed as void*);
+ *    the others take host pointers, copy in, run, copy out and synchronise `stream` before returning.
+ *  - handles are immutable after creation and may be used from several host threads at once.
+ *  - there is no CPU fallback: without a CUDA device every entry point returns MGODPL_E_NO_DEVICE.
+ */
+#ifndef MGODPL_B200_H
+#define MGODPL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mgodpl_scene mgodpl_scene; /* stands where fcl::CollisionObjectd stood (collision_detection.h:30) */
+typedef struct mgodpl_robot mgodpl_robot; /* device copy of robot_model::RobotModel (RobotModel.h:36-196)       */
+
+enum mgodpl_status {
+	MGODPL_OK = 0,
+	MGODPL_E_INVALID_ARGUMENT = 1,
+	MGODPL_E_UNSUPPORTED_SHAPE = 2, /* "Only boxes are implemented for collision geometry." collision_detection.cpp:50 */
+	MGODPL_E_LINK_NOT_FOUND = 3,    /* "Link not found: ..." RobotModel.cpp:119                                      */
+	MGODPL_E_UNKNOWN_JOINT_TYPE = 4,/* "Unknown joint type" RobotModel.h:104                                         */
+	MGODPL_E_CUDA = 5,
+	MGODPL_E_NO_DEVICE = 6,
+	MGODPL_E_OUT_OF_MEMORY = 7,
+	MGODPL_E_UNSUPPORTED_ROBOT = 8  /* more links / boxes / joint values than MGODPL_MAX_* */
+};
+
+#define MGODPL_MAX_LINKS 12
+#define MGODPL_MAX_BOXES 12
+#define MGODPL_MAX_JOINT_VALUES 16
+
+enum mgodpl_shape_type { MGODPL_SHAPE_BOX = 0, MGODPL_SHAPE_MESH = 1 };    /* shapes.h:24-29 */
+enum mgodpl_joint_type { MGODPL_JOINT_REVOLUTE = 0, MGODPL_JOINT_FIXED = 1 }; /* RobotModel.h:48-62 variant order */
+
+/* PositionedShape (positioned_shape.h:12-30) attached to a link; only boxes can be collided (collision_detection.cpp:21-22). */
+typedef struct mgodpl_shape_desc {
+	int32_t link;
+	int32_t shape_type;  /* mgodpl_shape_type */
+	double size[3];      /* Box::size, full extents, centred (shapes.h:20-22) */
+	double transform[7]; /* relative to the link frame */
+} mgodpl_shape_desc;
+
+/* RobotModel::Joint (RobotModel.h:67-84).  Joints must be listed in insertJoint order: the order decides the
+ * DFS expansion order of forwardKinematics and with it which joint value feeds which joint (RobotModel.cpp:53-69). */
+typedef struct mgodpl_joint_desc {
+	int32_t link_a, link_b;
+	int32_t joint_type; /* mgodpl_joint_type */
+	int32_t reserved;
+	double attachment_a[7], attachment_b[7];
+	double axis[3];                 /* revolute only */
+	double min_angle, max_angle;    /* revolute only */
+} mgodpl_joint_desc;
+
+typedef struct mgodpl_scene_opts {
+	uint32_t flags;          /* MGODPL_SCENE_* */
+	uint32_t max_leaf_size;  /* triangles per BVH leaf after collapsing, 0 = default */
+} mgodpl_scene_opts;
+#define MGODPL_SCENE_COUNTERS 1u   /* keep device-side work counters (states, nodes visited, leaf tests) */
+#define MGODPL_SCENE_NO_REFINE 2u  /* plain Morton LBVH, skip the SAH refinement passes */
+
+typedef struct mgodpl_scene_info {
+	uint64_t n_triangles, n_nodes, n_leaves, device_bytes;
+	double bounds_lo[3], bounds_hi[3];
+	double build_ms;       /* device time of the BVH build */
+	double sah_cost;       /* surface-area-heuristic cost of the final tree (C_node = 1, C_tri = 1) */
+	uint32_t max_depth, max_leaf_size;
+} mgodpl_scene_info;
+
+/* Deterministic cost counters: the reference's own observability hook on this path is an invocation counter
+ * (src/planning/functional_utils.cppm:27-32, approach_planning.cpp:505-533). */
+typedef struct mgodpl_counters {
+	uint64_t states_checked;   /* robot states that went through FK + collision */
+	uint64_t boxes_traversed;  /* boxes that survived the root cull and entered the BVH */
+	uint64_t nodes_visited;
+	uint64_t leaf_tests;       /* exact box/triangle tests */
+	uint64_t motions_checked;
+	uint64_t uncertain_steps;  /* motions whose step count sat within 1e-9 of an integer boundary (re-derived on host) */
+} mgodpl_counters;
+
+const char *mgodpl_last_error(void);
+int mgodpl_device_count(void);
+
+/* ---- scene: replaces meshToFclBVH(const Mesh&) / treeMeshesToFclCollisionObject (src/planning/fcl_utils.cpp:23-60) ----
+ * verts: nv x 3 doubles; tris: nt x 3 vertex indices.  Builds the linear BVH on the current CUDA device. */
+int mgodpl_scene_create(const double *verts, size_t nv, const uint32_t *tris, size_t nt, const mgodpl_scene_opts *opts,
+						mgodpl_scene **out);
+/* Same, with the reference's index type (Mesh::triangles is vector<array<size_t,3>>, src/planning/Mesh.h:19-22). */
+int mgodpl_scene_create_u64(const double *verts, size_t nv, const uint64_t *tris, size_t nt,
+							const mgodpl_scene_opts *opts, mgodpl_scene **out);
+int mgodpl_scene_destroy(mgodpl_scene *scene);
+int mgodpl_scene_get_info(const mgodpl_scene *scene, mgodpl_scene_info *info);
+int mgodpl_scene_get_counters(mgodpl_scene *scene, mgodpl_counters *out, int reset);
+
+/* ---- robot: flattened RobotModel (links in insertLink order, joints in insertJoint order) -------------------------
+ * root_link is what robot.findLinkByName("flying_base") returns (collision_detection.cpp:65); end_effector_link is
+ * findLinkByName("end_effector") or -1 when goal sampling is not needed. */
+int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_t n_shapes,
+						const mgodpl_joint_desc *joints, int32_t n_joints, int32_t root_link, int32_t end_effector_link,
+						mgodpl_robot **out);
+int mgodpl_robot_destroy(mgodpl_robot *robot);
+int mgodpl_robot_n_variables(const mgodpl_robot *robot); /* RobotModel::count_joint_variables, RobotModel.cpp:130-134 */
+
+/* ---- forwardKinematics (src/planning/RobotModel.cpp:17-90), batched: out_link_tfs is n x n_links x 7 doubles ---- */
+int mgodpl_forward_kinematics(const mgodpl_robot *robot, const double *states, size_t n, size_t stride,
+							  int32_t n_joint_values, double *out_link_tfs, void *stream);
+
+/* ---- check_link_collision (collision_detection.cpp:16-55) for explicit boxes: n x (world transform 7 + size 3) ---- */
+int mgodpl_check_boxes(mgodpl_scene *scene, const double *boxes, size_t n, uint32_t *hit_bits, void *stream);
+
+/* ---- check_robot_collision (collision_detection.cpp:57-80), N states ---------------------------------------------- */
+int mgodpl_check_states(mgodpl_scene *scene, const mgodpl_robot *robot, const double *states, size_t n, size_t stride,
+						int32_t n_joint_values, uint32_t *hit_bits, void *stream);
+int mgodpl_check_states_device(mgodpl_scene *scene, const mgodpl_robot *robot, const double *d_states, size_t n,
+							   size_t stride, int32_t n_joint_values, uint32_t *d_hit_bits, void *stream);
+
+/* ---- check_motion_collides (collision_detection.cpp:82-105), M motions a[i] -> b[i] --------------------------------
+ * max_step: the reference hard-codes 0.1 (collision_detection.cpp:90, collision_detection.cppm:61).
+ * toi (optional): first colliding interpolation parameter (NaN where the motion is free).
+ * n_steps_out (optional): the step count used for each motion.
+ * The host variant guarantees the reference's step count bit-for-bit: motions whose distance/max_step lands within
+ * 1e-9 of an integer are re-derived with the host libm and re-run if the count differs. */
+int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const double *a, const double *b, size_t m,
+						 size_t stride, int32_t n_joint_values, double max_step, uint32_t *hit_bits, double *toi,
+						 uint32_t *n_steps_out, void *stream);
+/* Device variant: d_n_steps_override (optional) forces the step count of motion i when its entry is not 0xFFFFFFFF;
+ * d_uncertain_bits (optional) receives one bit per motion whose step count is boundary-sensitive. */
+int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, const double *d_a, const double *d_b,
+								size_t m, size_t stride, int32_t n_joint_values, double max_step,
+								const uint32_t *d_n_steps_override, uint32_t *d_hit_bits, double *d_toi,
+								uint32_t *d_n_steps_out, uint32_t *d_uncertain_bits, void *stream);
+
+/* ---- check_path_collides (collision_detection.cpp:107-122): w waypoints, returns first colliding segment or -1 ---- */
+int mgodpl_check_path(mgodpl_scene *scene, const mgodpl_robot *robot, const double *states, size_t w, size_t stride,
+					  int32_t n_joint_values, double max_step, int64_t *first_colliding_segment, void *stream);
+
+/* ---- goal sampling: genGoalStateUniform + collision filter (goal_sampling.cpp:51-99,
+ *      goal_sample_success_rate.cpp:121-142) for F targets x S samples ------------------------------------------------
+ * draws: S x (1 + n_variables) doubles = the yaw and joint values genUprightState would draw (goal_sampling.cpp:13-49),
+ *        produced by the caller's std::mt19937 so sampled states match the reference bit for bit; shared by all targets
+ *        (the reference re-seeds per problem).  Pass NULL to draw on the device from a counter-based generator (`seed`).
+ * hit_bits: F x ceil(S/32) words; collisions: F counts; states_out (optional): F x S x (7 + n_variables) doubles. */
+int mgodpl_sample_goals(mgodpl_scene *scene, const mgodpl_robot *robot, const double *targets, size_t f,
+						const double *draws, size_t s, uint64_t seed, double distance_from_target, uint32_t *hit_bits,
+						uint32_t *collisions, double *states_out, void *stream);
+int mgodpl_sample_goals_device(mgodpl_scene *scene, const mgodpl_robot *robot, const double *d_targets, size_t f,
+							   const double *d_draws, size_t s, uint64_t seed, double distance_from_target,
+							   uint32_t *d_hit_bits, uint32_t *d_collisions, double *d_states_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGODPL_B200_H */

@@ -1,0 +1,647 @@
+// C ABI of the collision-query path (include/mgodpl_b200.h): handle management, robot flattening, host-buffer
+// staging, and the host-side fix-up that keeps motion step counts bit-identical to the reference's libm.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace mgodpl_b200;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+	g_last_error = msg;
+	return code;
+}
+int fail_cuda(cudaError_t e, const char *what) {
+	// sticky errors must not poison the next call's cudaGetLastError
+	cudaGetLastError();
+	return fail(e == cudaErrorMemoryAllocation ? MGODPL_E_OUT_OF_MEMORY : MGODPL_E_CUDA,
+				std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(x)                                    \
+	do {                                         \
+		cudaError_t e_ = (x);                    \
+		if (e_ != cudaSuccess) return fail_cuda(e_, #x); \
+	} while (0)
+
+int require_device() {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) {
+		cudaGetLastError();
+		return fail(MGODPL_E_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+	}
+	return MGODPL_OK;
+}
+
+/// A growable device + pinned-host staging area, one per in-flight host-buffer call.
+struct Workspace {
+	char *dev = nullptr, *host = nullptr;
+	size_t dev_cap = 0, host_cap = 0;
+	cudaError_t reserve(size_t dev_bytes, size_t host_bytes) {
+		if (dev_bytes > dev_cap) {
+			if (dev) cudaFree(dev);
+			dev = nullptr, dev_cap = 0;
+			size_t cap = dev_bytes + dev_bytes / 4 + 4096;
+			cudaError_t e = cudaMalloc((void **) &dev, cap);
+			if (e != cudaSuccess) return e;
+			dev_cap = cap;
+		}
+		if (host_bytes > host_cap) {
+			if (host) cudaFreeHost(host);
+			host = nullptr, host_cap = 0;
+			size_t cap = host_bytes + host_bytes / 4 + 4096;
+			cudaError_t e = cudaMallocHost((void **) &host, cap);
+			if (e != cudaSuccess) return e;
+			host_cap = cap;
+		}
+		return cudaSuccess;
+	}
+	~Workspace() {
+		if (dev) cudaFree(dev);
+		if (host) cudaFreeHost(host);
+	}
+};
+
+struct WorkspacePool {
+	std::mutex mu;
+	std::vector<std::unique_ptr<Workspace>> free_list;
+	std::unique_ptr<Workspace> acquire() {
+		std::lock_guard<std::mutex> g(mu);
+		if (free_list.empty()) return std::make_unique<Workspace>();
+		auto w = std::move(free_list.back());
+		free_list.pop_back();
+		return w;
+	}
+	void release(std::unique_ptr<Workspace> w) {
+		std::lock_guard<std::mutex> g(mu);
+		free_list.push_back(std::move(w));
+	}
+};
+struct Lease {
+	WorkspacePool &pool;
+	std::unique_ptr<Workspace> ws;
+	explicit Lease(WorkspacePool &p) : pool(p), ws(p.acquire()) {}
+	~Lease() { pool.release(std::move(ws)); }
+	Workspace *operator->() { return ws.get(); }
+};
+
+/// Carves aligned sub-buffers out of a workspace.
+struct Carver {
+	size_t off = 0;
+	size_t take(size_t bytes) {
+		size_t o = off;
+		off += (bytes + 255) & ~(size_t) 255;
+		return o;
+	}
+};
+
+}  // namespace
+
+struct mgodpl_scene {
+	SceneDev dev{};
+	BuiltScene built{};
+	mgodpl_scene_info info{};
+	unsigned long long *d_counters = nullptr;
+	// Work-distribution cursors for the motion kernel: a ring, so that asynchronous device-variant calls on several
+	// streams never share one (a slot is reused only after CURSOR_RING further launches).
+	static constexpr unsigned CURSOR_RING = 1024;
+	unsigned long long *d_cursors = nullptr;
+	std::atomic<unsigned> next_cursor{0};
+	WorkspacePool pool;
+	unsigned long long *cursor() { return d_cursors + (next_cursor.fetch_add(1) % CURSOR_RING); }
+};
+
+struct mgodpl_robot {
+	RobotDev dev{};
+	int n_joints = 0;
+	double *d_limits = nullptr;  // n_vars x (min, max)
+	std::vector<double> limits;
+};
+
+// =================================================================================================================
+extern "C" {
+
+const char *mgodpl_last_error(void) { return g_last_error.c_str(); }
+
+int mgodpl_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+// ---- scene ---------------------------------------------------------------------------------------------------------
+static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tris32, const uint64_t *tris64, size_t nt,
+							 const mgodpl_scene_opts *opts, mgodpl_scene **out) {
+	if (!out) return fail(MGODPL_E_INVALID_ARGUMENT, "out is null");
+	*out = nullptr;
+	if ((nv && !verts) || (nt && !tris32 && !tris64)) return fail(MGODPL_E_INVALID_ARGUMENT, "null mesh pointer");
+	if (nt > (1u << 27)) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^27 triangles");
+	if (int rc = require_device()) return rc;
+	// Validate indices and gather the bounds of the vertices the triangles actually use (host, one pass).
+	std::vector<uint32_t> idx(nt * 3);
+	double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+	for (size_t i = 0; i < nt * 3; ++i) {
+		uint64_t v = tris32 ? tris32[i] : tris64[i];
+		if (v >= nv) return fail(MGODPL_E_INVALID_ARGUMENT, "triangle index out of range");
+		idx[i] = (uint32_t) v;
+		for (int a = 0; a < 3; ++a) {
+			double c = verts[3 * v + a];
+			if (!std::isfinite(c)) return fail(MGODPL_E_INVALID_ARGUMENT, "non-finite vertex coordinate");
+			lo[a] = std::min(lo[a], c), hi[a] = std::max(hi[a], c);
+		}
+	}
+	if (!nt) lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0.0;
+	auto sc = std::make_unique<mgodpl_scene>();
+	double origin[3], max_abs = 0.0;
+	for (int a = 0; a < 3; ++a) {
+		origin[a] = 0.5 * (lo[a] + hi[a]);
+		max_abs = std::max(max_abs, 0.5 * (hi[a] - lo[a]));
+	}
+	cudaStream_t stream = nullptr;
+	double *d_verts = nullptr;
+	uint32_t *d_tris = nullptr;
+	unsigned leaf = opts && opts->max_leaf_size ? opts->max_leaf_size : 4;
+	bool refine = !(opts && (opts->flags & MGODPL_SCENE_NO_REFINE));
+	if (nt) {
+		CU(cudaMalloc((void **) &d_verts, nv * 3 * sizeof(double)));
+		cudaError_t e = cudaMalloc((void **) &d_tris, nt * 3 * sizeof(uint32_t));
+		if (e != cudaSuccess) {
+			cudaFree(d_verts);
+			return fail_cuda(e, "cudaMalloc(tris)");
+		}
+		e = cudaMemcpyAsync(d_verts, verts, nv * 3 * sizeof(double), cudaMemcpyHostToDevice, stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(d_tris, idx.data(), nt * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
+		if (e == cudaSuccess) e = build_scene(d_verts, nv, d_tris, nt, lo, hi, origin, leaf, refine, &sc->built, stream);
+		cudaStreamSynchronize(stream);
+		cudaFree(d_verts);
+		cudaFree(d_tris);
+		if (e != cudaSuccess) {
+			cudaFree(sc->built.nodes), cudaFree(sc->built.tris), cudaFree(sc->built.tri_ids);
+			return fail_cuda(e, "build_scene");
+		}
+	}
+	SceneDev &d = sc->dev;
+	d.nodes = sc->built.nodes;
+	d.tris = sc->built.tris;
+	d.n_nodes = sc->built.n_nodes;
+	d.n_tris = sc->built.n_tris;
+	for (int a = 0; a < 3; ++a) d.origin[a] = origin[a];
+	// fp32 cull tests carry ~1e-7 relative error on coordinates up to max_abs (plus robot reach): inflate every
+	// box by a margin two orders of magnitude above that.  Exactness is restored by the fp64 leaf test.
+	d.margin = (float) std::max(2e-5, 4e-6 * (max_abs + 2.0));
+	if (d.n_nodes) {
+		float4 root[2];
+		CU(cudaMemcpy(root, d.nodes, sizeof(root), cudaMemcpyDeviceToHost));
+		d.root_c[0] = root[0].x, d.root_c[1] = root[0].y, d.root_c[2] = root[0].z;
+		d.root_h[0] = root[1].x, d.root_h[1] = root[1].y, d.root_h[2] = root[1].z;
+	} else {
+		for (int a = 0; a < 3; ++a) d.root_c[a] = 0.f, d.root_h[a] = -1.f;  // nothing overlaps an empty scene
+	}
+	CU(cudaMalloc((void **) &sc->d_cursors, mgodpl_scene::CURSOR_RING * sizeof(unsigned long long)));
+	if (opts && (opts->flags & MGODPL_SCENE_COUNTERS)) {
+		CU(cudaMalloc((void **) &sc->d_counters, CNT_N * sizeof(unsigned long long)));
+		CU(cudaMemset(sc->d_counters, 0, CNT_N * sizeof(unsigned long long)));
+		d.counters = sc->d_counters;
+	}
+	mgodpl_scene_info &in = sc->info;
+	in.n_triangles = nt, in.n_nodes = d.n_nodes, in.n_leaves = sc->built.n_leaves;
+	in.device_bytes = sc->built.device_bytes;
+	for (int a = 0; a < 3; ++a) in.bounds_lo[a] = lo[a], in.bounds_hi[a] = hi[a];
+	in.build_ms = sc->built.build_ms, in.sah_cost = sc->built.sah_cost;
+	in.max_depth = sc->built.max_depth, in.max_leaf_size = sc->built.max_leaf;
+	*out = sc.release();
+	return MGODPL_OK;
+}
+
+int mgodpl_scene_create(const double *verts, size_t nv, const uint32_t *tris, size_t nt, const mgodpl_scene_opts *opts,
+						mgodpl_scene **out) {
+	return scene_create_impl(verts, nv, tris, nullptr, nt, opts, out);
+}
+int mgodpl_scene_create_u64(const double *verts, size_t nv, const uint64_t *tris, size_t nt, const mgodpl_scene_opts *opts,
+							mgodpl_scene **out) {
+	return scene_create_impl(verts, nv, nullptr, tris, nt, opts, out);
+}
+int mgodpl_scene_destroy(mgodpl_scene *s) {
+	if (!s) return MGODPL_OK;
+	cudaFree(s->built.nodes), cudaFree(s->built.tris), cudaFree(s->built.tri_ids), cudaFree(s->d_counters), cudaFree(s->d_cursors);
+	delete s;
+	return MGODPL_OK;
+}
+int mgodpl_scene_get_info(const mgodpl_scene *s, mgodpl_scene_info *info) {
+	if (!s || !info) return fail(MGODPL_E_INVALID_ARGUMENT, "null argument");
+	*info = s->info;
+	return MGODPL_OK;
+}
+int mgodpl_scene_get_counters(mgodpl_scene *s, mgodpl_counters *out, int reset) {
+	if (!s || !out) return fail(MGODPL_E_INVALID_ARGUMENT, "null argument");
+	memset(out, 0, sizeof(*out));
+	if (!s->d_counters) return fail(MGODPL_E_INVALID_ARGUMENT, "scene was created without MGODPL_SCENE_COUNTERS");
+	unsigned long long v[CNT_N];
+	CU(cudaMemcpy(v, s->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
+	out->states_checked = v[CNT_STATES], out->boxes_traversed = v[CNT_BOXES], out->nodes_visited = v[CNT_NODES];
+	out->leaf_tests = v[CNT_LEAF], out->motions_checked = v[CNT_MOTIONS], out->uncertain_steps = v[CNT_UNCERTAIN];
+	if (reset) CU(cudaMemset(s->d_counters, 0, sizeof(v)));
+	return MGODPL_OK;
+}
+
+// ---- robot -----------------------------------------------------------------------------------------------------------
+namespace {
+struct HTf {
+	double t[3], q[4];
+};
+HTf load_tf(const double *p) { return {{p[0], p[1], p[2]}, {p[3], p[4], p[5], p[6]}}; }
+void hq_mul(const double *a, const double *b, double *o) {
+	o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+	o[1] = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+	o[2] = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+	o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+}
+/// Transformd::inverse (Transform.h:52-58): conjugate, then rotate the negated translation by it.
+HTf inverse(const HTf &a) {
+	HTf r;
+	r.q[0] = -a.q[0], r.q[1] = -a.q[1], r.q[2] = -a.q[2], r.q[3] = a.q[3];
+	double v[4] = {-a.t[0], -a.t[1], -a.t[2], 0.0}, c[4] = {a.q[0], a.q[1], a.q[2], a.q[3]}, tmp[4], res[4];
+	hq_mul(r.q, v, tmp);
+	hq_mul(tmp, c, res);
+	r.t[0] = res[0], r.t[1] = res[1], r.t[2] = res[2];
+	return r;
+}
+bool rot_is_identity(const double *q) { return q[0] == 0.0 && q[1] == 0.0 && q[2] == 0.0 && q[3] == 1.0; }
+double vnorm(const double *t) { return std::sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]); }
+}  // namespace
+
+int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_t n_shapes, const mgodpl_joint_desc *joints,
+						int32_t n_joints, int32_t root_link, int32_t ee_link, mgodpl_robot **out) {
+	if (!out) return fail(MGODPL_E_INVALID_ARGUMENT, "out is null");
+	*out = nullptr;
+	if (n_links <= 0 || n_shapes < 0 || n_joints < 0 || (n_shapes && !shapes) || (n_joints && !joints))
+		return fail(MGODPL_E_INVALID_ARGUMENT, "bad robot description");
+	if (root_link < 0 || root_link >= n_links) return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: root link index out of range");
+	if (ee_link >= n_links) return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: end effector index out of range");
+	if (n_links > MGODPL_MAX_LINKS) return fail(MGODPL_E_UNSUPPORTED_ROBOT, "too many links");
+	if (n_shapes > MGODPL_MAX_BOXES) return fail(MGODPL_E_UNSUPPORTED_ROBOT, "too many collision shapes");
+	for (int i = 0; i < n_shapes; ++i) {
+		if (shapes[i].shape_type != MGODPL_SHAPE_BOX)
+			return fail(MGODPL_E_UNSUPPORTED_SHAPE, "Only boxes are implemented for collision geometry.");
+		if (shapes[i].link < 0 || shapes[i].link >= n_links) return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: shape link index");
+	}
+	for (int i = 0; i < n_joints; ++i) {
+		if (joints[i].joint_type != MGODPL_JOINT_REVOLUTE && joints[i].joint_type != MGODPL_JOINT_FIXED)
+			return fail(MGODPL_E_UNKNOWN_JOINT_TYPE, "Unknown joint type");
+		if (joints[i].link_a < 0 || joints[i].link_a >= n_links || joints[i].link_b < 0 || joints[i].link_b >= n_links)
+			return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: joint link index");
+	}
+	if (int rc = require_device()) return rc;
+
+	auto rb = std::make_unique<mgodpl_robot>();
+	RobotDev &d = rb->dev;
+	d.n_links = n_links, d.root = root_link, d.ee = ee_link, d.n_ops = 0, d.n_boxes = n_shapes;
+	rb->n_joints = n_joints;
+
+	// Back-links in insertJoint order (RobotModel.cpp:103-112).
+	std::vector<std::vector<int>> link_joints(n_links);
+	for (int j = 0; j < n_joints; ++j) {
+		link_joints[joints[j].link_a].push_back(j);
+		link_joints[joints[j].link_b].push_back(j);
+	}
+	// Replay forwardKinematics' explicit-stack DFS (RobotModel.cpp:17-90) symbolically.  An entry remembers which
+	// joint produced it and the variable cursor at expansion time; a link takes the transform of its first pop.
+	struct Entry {
+		int link, parent, joint, var;
+		bool from_a;
+	};
+	std::vector<Entry> stack{{root_link, -1, -1, -1, true}};
+	std::vector<char> visited(n_links, 0);
+	int var_cursor = 0;
+	std::vector<double> depth_reach(n_links, 0.0);  // bound on |link origin - root origin|
+	while (!stack.empty()) {
+		Entry e = stack.back();
+		stack.pop_back();
+		if (visited[e.link]) continue;
+		visited[e.link] = 1;
+		if (e.joint >= 0) {
+			const mgodpl_joint_desc &J = joints[e.joint];
+			FkOp &op = d.ops[d.n_ops++];
+			op.parent = e.parent, op.child = e.link, op.var = e.var, op.flags = 0;
+			HTf pre = load_tf(e.from_a ? J.attachment_a : J.attachment_b);
+			HTf post = inverse(load_tf(e.from_a ? J.attachment_b : J.attachment_a));
+			if (!e.from_a) op.flags |= FK_INVERT;  // joint crossed from linkB: variable transform inverted (RobotModel.cpp:66-67)
+			memcpy(op.pre_t, pre.t, sizeof(pre.t)), memcpy(op.pre_q, pre.q, sizeof(pre.q));
+			memcpy(op.post_t, post.t, sizeof(post.t)), memcpy(op.post_q, post.q, sizeof(post.q));
+			memcpy(op.axis, J.axis, sizeof(J.axis));
+			if (rot_is_identity(pre.q)) op.flags |= FK_PRE_ROT_ID;
+			if (rot_is_identity(post.q)) op.flags |= FK_POST_ROT_ID;
+			depth_reach[e.link] = depth_reach[e.parent] + vnorm(pre.t) + vnorm(post.t);
+		}
+		for (int ji: link_joints[e.link]) {
+			const mgodpl_joint_desc &J = joints[ji];
+			if (visited[J.link_b]) continue;  // the reference only looks at linkB here (RobotModel.cpp:56-57)
+			bool from_a = J.link_a == e.link;
+			int var = J.joint_type == MGODPL_JOINT_REVOLUTE ? var_cursor : -1;
+			var_cursor += J.joint_type == MGODPL_JOINT_REVOLUTE ? 1 : 0;
+			stack.push_back({from_a ? J.link_b : J.link_a, e.link, ji, var, from_a});
+		}
+	}
+	int n_vars = 0;
+	for (int j = 0; j < n_joints; ++j) n_vars += joints[j].joint_type == MGODPL_JOINT_REVOLUTE;
+	d.n_vars = n_vars;
+	if (n_vars > MGODPL_MAX_JOINT_VALUES) return fail(MGODPL_E_UNSUPPORTED_ROBOT, "too many joint variables");
+	if (ee_link >= 0 && !visited[ee_link]) return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: end effector unreachable from root");
+
+	// Boxes, the links FK must reach for collision, and the reach radius of the whole robot.
+	std::vector<char> needed(n_links, 0);
+	double reach = 0.0;
+	for (int i = 0; i < n_shapes; ++i) {
+		BoxDev &b = d.boxes[i];
+		b.link = shapes[i].link;
+		for (int a = 0; a < 3; ++a) b.half[a] = 0.5 * shapes[i].size[a];
+		HTf tf = load_tf(shapes[i].transform);
+		memcpy(b.t, tf.t, sizeof(tf.t)), memcpy(b.q, tf.q, sizeof(tf.q));
+		b.tf_identity = rot_is_identity(tf.q) && tf.t[0] == 0.0 && tf.t[1] == 0.0 && tf.t[2] == 0.0;
+		needed[b.link] = 1;
+		// unreachable links keep the root transform (RobotModel.cpp:23-24), so depth_reach 0 is right for them
+		reach = std::max(reach, depth_reach[b.link] + vnorm(tf.t) + vnorm(b.half));
+	}
+	d.reach = reach * (1.0 + 1e-9) + 1e-9;
+	for (int k = d.n_ops - 1; k >= 0; --k) {
+		if (needed[d.ops[k].child]) {
+			d.ops[k].flags |= FK_FOR_COLLISION;
+			needed[d.ops[k].parent] = 1;
+		}
+	}
+	// Joint limits for device-side goal sampling: one (min, max) per variable in variable order.
+	rb->limits.assign(2 * std::max(n_vars, 1), 0.0);
+	{
+		int v = 0;
+		for (int j = 0; j < n_joints; ++j)
+			if (joints[j].joint_type == MGODPL_JOINT_REVOLUTE) {
+				rb->limits[2 * v] = joints[j].min_angle, rb->limits[2 * v + 1] = joints[j].max_angle;
+				++v;
+			}
+	}
+	CU(cudaMalloc((void **) &rb->d_limits, rb->limits.size() * sizeof(double)));
+	CU(cudaMemcpy(rb->d_limits, rb->limits.data(), rb->limits.size() * sizeof(double), cudaMemcpyHostToDevice));
+	*out = rb.release();
+	return MGODPL_OK;
+}
+
+int mgodpl_robot_destroy(mgodpl_robot *r) {
+	if (!r) return MGODPL_OK;
+	cudaFree(r->d_limits);
+	delete r;
+	return MGODPL_OK;
+}
+int mgodpl_robot_n_variables(const mgodpl_robot *r) { return r ? r->dev.n_vars : -1; }
+
+// ---- argument checks shared by the query entry points ----------------------------------------------------------------
+static int check_state_args(const mgodpl_robot *robot, size_t stride, int32_t js) {
+	if (!robot) return fail(MGODPL_E_INVALID_ARGUMENT, "robot is null");
+	if (js < robot->dev.n_vars) return fail(MGODPL_E_INVALID_ARGUMENT, "fewer joint values per state than joint variables");
+	if (js > MGODPL_MAX_JOINT_VALUES) return fail(MGODPL_E_UNSUPPORTED_ROBOT, "too many joint values per state");
+	if (stride < (size_t) (7 + js)) return fail(MGODPL_E_INVALID_ARGUMENT, "stride smaller than 7 + n_joint_values");
+	if (stride > 7 + MGODPL_MAX_JOINT_VALUES) return fail(MGODPL_E_INVALID_ARGUMENT, "stride larger than 7 + MGODPL_MAX_JOINT_VALUES");
+	return MGODPL_OK;
+}
+
+// ---- forward kinematics ------------------------------------------------------------------------------------------------
+int mgodpl_forward_kinematics(const mgodpl_robot *robot, const double *states, size_t n, size_t stride, int32_t js,
+							  double *out, void *stream_) {
+	if (int rc = check_state_args(robot, stride, js)) return rc;
+	if (n && (!states || !out)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (int rc = require_device()) return rc;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	if (!n) return MGODPL_OK;
+	size_t in_b = n * stride * 8, out_b = n * robot->dev.n_links * 7 * 8;
+	double *d_in = nullptr, *d_out = nullptr;
+	CU(cudaMalloc((void **) &d_in, in_b));
+	cudaError_t e = cudaMalloc((void **) &d_out, out_b);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, states, in_b, cudaMemcpyHostToDevice, stream);
+	if (e == cudaSuccess) e = launch_forward_kinematics(robot->dev, d_in, n, stride, d_out, stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+	cudaFree(d_in), cudaFree(d_out);
+	if (e != cudaSuccess) return fail_cuda(e, "forward_kinematics");
+	return MGODPL_OK;
+}
+
+// ---- boxes ---------------------------------------------------------------------------------------------------------------
+int mgodpl_check_boxes(mgodpl_scene *scene, const double *boxes, size_t n, uint32_t *hit_bits, void *stream_) {
+	if (!scene) return fail(MGODPL_E_INVALID_ARGUMENT, "scene is null");
+	if (n && (!boxes || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (int rc = require_device()) return rc;
+	if (!n) return MGODPL_OK;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	Lease ws(scene->pool);
+	Carver c;
+	size_t o_in = c.take(n * 80), words = (n + 31) / 32, o_out = c.take(words * 4);
+	CU(ws->reserve(c.off, words * 4));
+	CU(cudaMemcpyAsync(ws->dev + o_in, boxes, n * 80, cudaMemcpyHostToDevice, stream));
+	CU(launch_check_boxes(scene->dev, (const double *) (ws->dev + o_in), n, (uint32_t *) (ws->dev + o_out), stream));
+	CU(cudaMemcpyAsync(ws->host, ws->dev + o_out, words * 4, cudaMemcpyDeviceToHost, stream));
+	CU(cudaStreamSynchronize(stream));
+	memcpy(hit_bits, ws->host, words * 4);
+	return MGODPL_OK;
+}
+
+// ---- states --------------------------------------------------------------------------------------------------------------
+int mgodpl_check_states_device(mgodpl_scene *scene, const mgodpl_robot *robot, const double *d_states, size_t n, size_t stride,
+							   int32_t js, uint32_t *d_hit_bits, void *stream_) {
+	if (!scene) return fail(MGODPL_E_INVALID_ARGUMENT, "scene is null");
+	if (int rc = check_state_args(robot, stride, js)) return rc;
+	if (n && (!d_states || !d_hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (int rc = require_device()) return rc;
+	CU(launch_check_states(scene->dev, robot->dev, d_states, n, stride, d_hit_bits, (cudaStream_t) stream_));
+	return MGODPL_OK;
+}
+
+int mgodpl_check_states(mgodpl_scene *scene, const mgodpl_robot *robot, const double *states, size_t n, size_t stride,
+						int32_t js, uint32_t *hit_bits, void *stream_) {
+	if (!scene) return fail(MGODPL_E_INVALID_ARGUMENT, "scene is null");
+	if (int rc = check_state_args(robot, stride, js)) return rc;
+	if (n && (!states || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (int rc = require_device()) return rc;
+	if (!n) return MGODPL_OK;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	Lease ws(scene->pool);
+	Carver c;
+	size_t in_b = n * stride * 8, words = (n + 31) / 32;
+	size_t o_in = c.take(in_b), o_out = c.take(words * 4);
+	CU(ws->reserve(c.off, words * 4));
+	// Caller memory goes straight to the device; only the (small) result is staged through pinned memory.
+	CU(cudaMemcpyAsync(ws->dev + o_in, states, in_b, cudaMemcpyHostToDevice, stream));
+	CU(launch_check_states(scene->dev, robot->dev, (const double *) (ws->dev + o_in), n, stride, (uint32_t *) (ws->dev + o_out), stream));
+	CU(cudaMemcpyAsync(ws->host, ws->dev + o_out, words * 4, cudaMemcpyDeviceToHost, stream));
+	CU(cudaStreamSynchronize(stream));
+	memcpy(hit_bits, ws->host, words * 4);
+	return MGODPL_OK;
+}
+
+// ---- motions ---------------------------------------------------------------------------------------------------------------
+int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, const double *d_a, const double *d_b, size_t m,
+								size_t stride, int32_t js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,
+								double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, void *stream_) {
+	if (!scene) return fail(MGODPL_E_INVALID_ARGUMENT, "scene is null");
+	if (int rc = check_state_args(robot, stride, js)) return rc;
+	if (!(max_step > 0.0)) return fail(MGODPL_E_INVALID_ARGUMENT, "max_step must be positive");
+	if (m && (!d_a || !d_b || !d_hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (int rc = require_device()) return rc;
+	if (!m) return MGODPL_OK;
+	CU(launch_check_motions(scene->dev, robot->dev, d_a, d_b, m, stride, js, max_step, d_override, d_hit_bits, d_toi, d_n_steps,
+							d_uncertain, scene->cursor(), (cudaStream_t) stream_));
+	return MGODPL_OK;
+}
+
+namespace {
+/// equal_weights_distance + ceil exactly as the reference computes them on the host (distance.cpp:17-25,
+/// Quaternion.h:78-85, collision_detection.cpp:88-92), with the host libm.
+uint32_t host_n_steps(const double *a, const double *b, int js, double max_step) {
+	double dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+	double d = std::sqrt(dx * dx + dy * dy + dz * dz);
+	double c = a[6] * b[6] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
+	c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
+	d += std::acos(2.0 * c * c - 1.0);
+	for (int i = 0; i < js; ++i) d += std::abs(a[7 + i] - b[7 + i]);
+	double n = std::ceil(d / max_step);
+	if (!(n >= 0.0 && n < 4.0e9)) return 0;
+	return (uint32_t) n;
+}
+}  // namespace
+
+int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const double *a, const double *b, size_t m, size_t stride,
+						 int32_t js, double max_step, uint32_t *hit_bits, double *toi, uint32_t *n_steps_out, void *stream_) {
+	if (!scene) return fail(MGODPL_E_INVALID_ARGUMENT, "scene is null");
+	if (int rc = check_state_args(robot, stride, js)) return rc;
+	if (!(max_step > 0.0)) return fail(MGODPL_E_INVALID_ARGUMENT, "max_step must be positive");
+	if (m && (!a || !b || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (int rc = require_device()) return rc;
+	if (!m) return MGODPL_OK;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	Lease ws(scene->pool);
+	Carver c;
+	const size_t in_b = m * stride * 8, words = (m + 31) / 32;
+	size_t o_a = c.take(in_b), o_b = c.take(in_b);
+	// outputs are contiguous so that one D2H copy brings them all back
+	size_t o_hit = c.take(words * 4), o_unc = c.take(words * 4), o_steps = c.take(m * 4), o_toi = c.take(toi ? m * 8 : 0);
+	size_t out_lo = o_hit, out_hi = c.off;
+	size_t o_ovr = c.take(m * 4);
+	CU(ws->reserve(c.off, c.off - out_lo));
+	char *D = ws->dev, *H = ws->host - out_lo;  // host staging mirrors the device layout from out_lo onwards
+	unsigned long long *cursor = scene->cursor();
+	CU(cudaMemcpyAsync(D + o_a, a, in_b, cudaMemcpyHostToDevice, stream));
+	CU(cudaMemcpyAsync(D + o_b, b, in_b, cudaMemcpyHostToDevice, stream));
+	CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a), (const double *) (D + o_b), m, stride, js, max_step,
+							nullptr, (uint32_t *) (D + o_hit), toi ? (double *) (D + o_toi) : nullptr, (uint32_t *) (D + o_steps),
+							(uint32_t *) (D + o_unc), cursor, stream));
+	CU(cudaMemcpyAsync(H + out_lo, D + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, stream));
+	CU(cudaStreamSynchronize(stream));
+	// Step-count fix-up: the device libm may differ from the host's by an ulp, which only matters when distance /
+	// max_step sits on an integer boundary.  Re-derive those on the host and re-run the ones that disagree.
+	uint32_t *h_unc = (uint32_t *) (H + o_unc), *h_steps = (uint32_t *) (H + o_steps), *h_ovr = (uint32_t *) (H + o_ovr);
+	size_t n_fix = 0;
+	for (size_t w = 0; w < words; ++w) {
+		uint32_t bits = h_unc[w];
+		while (bits) {
+			int k = __builtin_ctz(bits);
+			bits &= bits - 1;
+			size_t i = w * 32 + k;
+			uint32_t want = host_n_steps(a + i * stride, b + i * stride, js, max_step);
+			if (want != h_steps[i]) {
+				if (!n_fix) memset(h_ovr, 0xff, m * 4);
+				h_ovr[i] = want;
+				++n_fix;
+			}
+		}
+	}
+	if (n_fix) {
+		// Rare path: re-run the whole batch with the corrected counts pinned (kept simple; the boundary set is
+		// normally empty for sampled states).
+		CU(cudaMemcpyAsync(D + o_ovr, h_ovr, m * 4, cudaMemcpyHostToDevice, stream));
+		CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a), (const double *) (D + o_b), m, stride, js,
+								max_step, (const uint32_t *) (D + o_ovr), (uint32_t *) (D + o_hit),
+								toi ? (double *) (D + o_toi) : nullptr, (uint32_t *) (D + o_steps), nullptr,
+								cursor, stream));
+		CU(cudaMemcpyAsync(H + out_lo, D + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, stream));
+		CU(cudaStreamSynchronize(stream));
+	}
+	memcpy(hit_bits, H + o_hit, words * 4);
+	if (toi) memcpy(toi, H + o_toi, m * 8);
+	if (n_steps_out) memcpy(n_steps_out, h_steps, m * 4);
+	return MGODPL_OK;
+}
+
+int mgodpl_check_path(mgodpl_scene *scene, const mgodpl_robot *robot, const double *states, size_t w, size_t stride, int32_t js,
+					  double max_step, int64_t *first, void *stream) {
+	if (!first) return fail(MGODPL_E_INVALID_ARGUMENT, "first_colliding_segment is null");
+	*first = -1;
+	if (w < 2) return MGODPL_OK;
+	size_t m = w - 1;
+	std::vector<uint32_t> bits((m + 31) / 32);
+	// consecutive waypoint pairs: a = states[0..w-2], b = states[1..w-1] (collision_detection.cpp:111-113)
+	int rc = mgodpl_check_motions(scene, robot, states, states + stride, m, stride, js, max_step, bits.data(), nullptr, nullptr, stream);
+	if (rc) return rc;
+	for (size_t i = 0; i < bits.size(); ++i)
+		if (bits[i]) {
+			*first = (int64_t) (i * 32 + __builtin_ctz(bits[i]));
+			break;
+		}
+	return MGODPL_OK;
+}
+
+// ---- goal sampling -------------------------------------------------------------------------------------------------------------
+int mgodpl_sample_goals_device(mgodpl_scene *scene, const mgodpl_robot *robot, const double *d_targets, size_t f, const double *d_draws,
+							   size_t s, uint64_t seed, double dist, uint32_t *d_hit_bits, uint32_t *d_collisions, double *d_states_out,
+							   void *stream_) {
+	if (!scene || !robot) return fail(MGODPL_E_INVALID_ARGUMENT, "null handle");
+	if (robot->dev.ee < 0) return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: end_effector");
+	if (f && s && (!d_targets || !d_hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (int rc = require_device()) return rc;
+	CU(launch_sample_goals(scene->dev, robot->dev, d_targets, f, d_draws, robot->d_limits, s, seed, dist, d_hit_bits, d_collisions,
+						   d_states_out, (cudaStream_t) stream_));
+	return MGODPL_OK;
+}
+
+int mgodpl_sample_goals(mgodpl_scene *scene, const mgodpl_robot *robot, const double *targets, size_t f, const double *draws, size_t s,
+						uint64_t seed, double dist, uint32_t *hit_bits, uint32_t *collisions, double *states_out, void *stream_) {
+	if (!scene || !robot) return fail(MGODPL_E_INVALID_ARGUMENT, "null handle");
+	if (robot->dev.ee < 0) return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: end_effector");
+	if (f && s && (!targets || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (int rc = require_device()) return rc;
+	if (!f || !s) return MGODPL_OK;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	const int nv = robot->dev.n_vars;
+	Lease ws(scene->pool);
+	Carver c;
+	size_t wpr = (s + 31) / 32;
+	size_t o_t = c.take(f * 24), o_d = c.take(draws ? s * (1 + nv) * 8 : 0);
+	size_t o_hit = c.take(f * wpr * 4), o_cnt = c.take(f * 4);
+	size_t small_hi = c.off;
+	size_t o_st = c.take(states_out ? f * s * (7 + nv) * 8 : 0);
+	CU(ws->reserve(c.off, small_hi - o_hit));
+	char *D = ws->dev, *H = ws->host - o_hit;  // host staging mirrors the device layout of the two result arrays
+	CU(cudaMemcpyAsync(D + o_t, targets, f * 24, cudaMemcpyHostToDevice, stream));
+	if (draws) CU(cudaMemcpyAsync(D + o_d, draws, s * (1 + nv) * 8, cudaMemcpyHostToDevice, stream));
+	CU(launch_sample_goals(scene->dev, robot->dev, (const double *) (D + o_t), f, draws ? (const double *) (D + o_d) : nullptr,
+						   robot->d_limits, s, seed, dist, (uint32_t *) (D + o_hit), (uint32_t *) (D + o_cnt),
+						   states_out ? (double *) (D + o_st) : nullptr, stream));
+	CU(cudaMemcpyAsync(H + o_hit, D + o_hit, small_hi - o_hit, cudaMemcpyDeviceToHost, stream));
+	if (states_out) CU(cudaMemcpyAsync(states_out, D + o_st, f * s * (7 + nv) * 8, cudaMemcpyDeviceToHost, stream));
+	CU(cudaStreamSynchronize(stream));
+	memcpy(hit_bits, H + o_hit, f * wpr * 4);
+	if (collisions) memcpy(collisions, H + o_cnt, f * 4);
+	return MGODPL_OK;
+}
+
+}  // extern "C"

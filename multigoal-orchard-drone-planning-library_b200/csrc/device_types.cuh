@@ -1,0 +1,74 @@
+// Device-resident data layout of the collision-query path (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/mgodpl_b200.h"
+
+namespace mgodpl_b200 {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Scene BVH, flattened in depth-first preorder with skip links ("stackless" traversal: a visit either steps to
+// node+1 or jumps to node.skip).  One node = two float4 = 32 B, so a lane fetches a node with two LDG.128:
+//   a = (centre.x, centre.y, centre.z, as_float(skip))       coordinates are relative to SceneDev::origin
+//   b = (half.x,   half.y,   half.z,   as_float(leaf_info))  half extents are rounded outward
+// leaf_info < 0  : internal node
+// leaf_info >= 0 : leaf; (leaf_info >> 4) = first triangle slot, (leaf_info & 15) + 1 = triangle count
+// Triangles are stored in leaf (preorder) order as 9 fp64 world coordinates, so a leaf's triangles are contiguous.
+// ---------------------------------------------------------------------------------------------------------------
+struct SceneDev {
+	const float4 *nodes;     // 2 * n_nodes float4
+	const double *tris;      // 9 * n_tris doubles (v0 v1 v2), world frame, leaf order
+	uint32_t n_nodes;
+	uint32_t n_tris;
+	double origin[3];        // fp32 node coordinates are relative to this point (centre of the scene bounds)
+	float root_c[3], root_h[3]; // root bounds relative to origin (same as node 0)
+	float margin;            // conservative inflation applied to every fp32 cull test
+	unsigned long long *counters; // mgodpl_counters as 6 x u64, or nullptr
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Robot: the reference's explicit-stack DFS (RobotModel.cpp:17-90) only depends on the model, never on the state,
+// so the host unrolls it once into a list of ops executed in pop order:
+//     tf[child] = tf[parent] . pre . J(theta[var]) . post
+// with pre = this-side attachment, post = inverse(other-side attachment), J = axis-angle rotation (inverse when the
+// joint is crossed from linkB) or identity for fixed joints.
+// ---------------------------------------------------------------------------------------------------------------
+struct FkOp {
+	int32_t parent, child;
+	int32_t var;          // index into joint values, -1 = no variable (fixed joint)
+	int32_t flags;        // FK_*
+	double pre_t[3], pre_q[4];
+	double post_t[3], post_q[4];
+	double axis[3];
+};
+enum : int32_t {
+	FK_INVERT = 1,        // joint crossed from linkB: use the inverse rotation
+	FK_PRE_ROT_ID = 2,    // pre.q is exactly identity
+	FK_POST_ROT_ID = 4,   // post.q is exactly identity
+	FK_FOR_COLLISION = 8  // child (or something below it) carries collision geometry
+};
+
+struct BoxDev {
+	int32_t link;
+	int32_t tf_identity;  // shape transform is exactly identity
+	double half[3];
+	double t[3], q[4];    // shape transform relative to the link
+};
+
+struct RobotDev {
+	int32_t n_links, n_ops, n_boxes, n_vars;
+	int32_t root, ee;
+	double reach;         // radius around the root link origin that contains every box for every joint value
+	FkOp ops[MGODPL_MAX_LINKS];
+	BoxDev boxes[MGODPL_MAX_BOXES];
+};
+
+struct Tf64 {
+	double tx, ty, tz, qx, qy, qz, qw;
+};
+
+// Counter slots (mgodpl_counters order)
+enum { CNT_STATES = 0, CNT_BOXES, CNT_NODES, CNT_LEAF, CNT_MOTIONS, CNT_UNCERTAIN, CNT_N };
+
+}  // namespace mgodpl_b200

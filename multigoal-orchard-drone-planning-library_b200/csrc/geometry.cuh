@@ -1,0 +1,173 @@
+// fp64 rigid-body math, forward kinematics and the exact box/triangle test; fp32 conservative culling.
+//
+// Semantics follow the reference (paths relative to its checkout): src/math/Quaternion.h:25-85, Transform.h:20-78,
+// src/planning/RobotModel.cpp:17-90, RobotState.cpp:14-24.  The arithmetic is free to differ in the last bits
+// (rotate-by-cross-products instead of the sandwich product, fused multiply-adds): every boolean this path returns is
+// decided in fp64 with ~1e-15 m of slack, against a 1e-6 m parity band.
+#pragma once
+#include "device_types.cuh"
+
+namespace mgodpl_b200 {
+
+struct D3 {
+	double x, y, z;
+};
+struct Q4 {
+	double x, y, z, w;
+};
+
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ D3 operator*(D3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ D3 cross(D3 a, D3 b) {
+	return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+/// Hamilton product (Quaternion.h:36-44).
+__device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
+	return {a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x,
+			a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+}
+__device__ __forceinline__ Q4 qconj(Q4 q) { return {-q.x, -q.y, -q.z, q.w}; }
+/// q (v,0) q* for a unit quaternion (Quaternion.h:46-51), evaluated as v + 2w(u x v) + 2u x (u x v).
+__device__ __forceinline__ D3 qrot(Q4 q, D3 v) {
+	D3 u{q.x, q.y, q.z};
+	D3 t = cross(u, v);
+	t = t + t;
+	return v + t * q.w + cross(u, t);
+}
+/// Rotation matrix of a unit quaternion, world = R * local (what Eigen builds for fcl::Transform3d::rotate,
+/// collision_detection.cpp:29-30).  Row-major r[3*i+j].
+__device__ __forceinline__ void qmat(Q4 q, double *r) {
+	double x = q.x, y = q.y, z = q.z, w = q.w;
+	r[0] = 1 - 2 * (y * y + z * z), r[1] = 2 * (x * y - z * w), r[2] = 2 * (x * z + y * w);
+	r[3] = 2 * (x * y + z * w), r[4] = 1 - 2 * (x * x + z * z), r[5] = 2 * (y * z - x * w);
+	r[6] = 2 * (x * z - y * w), r[7] = 2 * (y * z + x * w), r[8] = 1 - 2 * (x * x + y * y);
+}
+
+struct Pose {
+	D3 t;
+	Q4 q;
+};
+/// Transformd::then (Transform.h:31-36).
+__device__ __forceinline__ Pose then(const Pose &a, D3 bt, Q4 bq, bool b_rot_identity) {
+	Pose r;
+	r.t = a.t + qrot(a.q, bt);
+	r.q = b_rot_identity ? a.q : qmul(a.q, bq);
+	return r;
+}
+
+/// One op of the host-unrolled forwardKinematics DFS: tf[child] = tf[parent] . pre . J(theta) . post.
+__device__ __forceinline__ Pose fk_apply(const FkOp &op, const Pose &parent, const double *joint_values) {
+	Pose p = then(parent, D3{op.pre_t[0], op.pre_t[1], op.pre_t[2]}, Q4{op.pre_q[0], op.pre_q[1], op.pre_q[2], op.pre_q[3]},
+				  op.flags & FK_PRE_ROT_ID);
+	if (op.var >= 0) {
+		// RobotModel::variableTransform (RobotModel.cpp:136-154) + Quaterniond::fromAxisAngle (Quaternion.h:53-62)
+		double s, c;
+		sincos(joint_values[op.var] / 2.0, &s, &c);
+		if (op.flags & FK_INVERT) s = -s;
+		p.q = qmul(p.q, Q4{op.axis[0] * s, op.axis[1] * s, op.axis[2] * s, c});
+	}
+	return then(p, D3{op.post_t[0], op.post_t[1], op.post_t[2]}, Q4{op.post_q[0], op.post_q[1], op.post_q[2], op.post_q[3]},
+				op.flags & FK_POST_ROT_ID);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 culling box: an oriented box expressed relative to SceneDev::origin, half extents already inflated by the
+// scene's conservative margin.  19 registers.
+// ---------------------------------------------------------------------------------------------------------------
+struct CullBox {
+	float cx, cy, cz;
+	float r[9];        // row-major, world = R * local
+	float hx, hy, hz;  // inflated half extents
+	float wx, wy, wz;  // half extents of the box's world-axis AABB (from the inflated h)
+};
+
+__device__ __forceinline__ CullBox make_cull_box(const SceneDev &sc, D3 c, Q4 q, const double *half) {
+	double R[9];
+	qmat(q, R);
+	CullBox b;
+	b.cx = (float) (c.x - sc.origin[0]), b.cy = (float) (c.y - sc.origin[1]), b.cz = (float) (c.z - sc.origin[2]);
+#pragma unroll
+	for (int i = 0; i < 9; ++i) b.r[i] = (float) R[i];
+	b.hx = (float) half[0] + sc.margin, b.hy = (float) half[1] + sc.margin, b.hz = (float) half[2] + sc.margin;
+	b.wx = fabsf(b.r[0]) * b.hx + fabsf(b.r[1]) * b.hy + fabsf(b.r[2]) * b.hz;
+	b.wy = fabsf(b.r[3]) * b.hx + fabsf(b.r[4]) * b.hy + fabsf(b.r[5]) * b.hz;
+	b.wz = fabsf(b.r[6]) * b.hx + fabsf(b.r[7]) * b.hy + fabsf(b.r[8]) * b.hz;
+	return b;
+}
+
+/// Conservative oriented-box vs AABB(centre, half) overlap: the 3 world axes and the 3 box axes of the
+/// separating-axis test (the 9 edge-edge axes are skipped, which can only report extra overlaps).
+__device__ __forceinline__ bool cull_overlap(const CullBox &b, float ncx, float ncy, float ncz, float nhx, float nhy,
+											 float nhz) {
+	float dx = ncx - b.cx, dy = ncy - b.cy, dz = ncz - b.cz;
+	bool sep = fabsf(dx) > nhx + b.wx;
+	sep |= fabsf(dy) > nhy + b.wy;
+	sep |= fabsf(dz) > nhz + b.wz;
+	float p0 = b.r[0] * dx + b.r[3] * dy + b.r[6] * dz;
+	float p1 = b.r[1] * dx + b.r[4] * dy + b.r[7] * dz;
+	float p2 = b.r[2] * dx + b.r[5] * dy + b.r[8] * dz;
+	float e0 = fabsf(b.r[0]) * nhx + fabsf(b.r[3]) * nhy + fabsf(b.r[6]) * nhz + b.hx;
+	float e1 = fabsf(b.r[1]) * nhx + fabsf(b.r[4]) * nhy + fabsf(b.r[7]) * nhz + b.hy;
+	float e2 = fabsf(b.r[2]) * nhx + fabsf(b.r[5]) * nhy + fabsf(b.r[8]) * nhz + b.hz;
+	sep |= fabsf(p0) > e0;
+	sep |= fabsf(p1) > e1;
+	sep |= fabsf(p2) > e2;
+	return !sep;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Exact narrow phase: closed oriented box vs closed triangle, 13-axis separating-axis test in the box frame, fp64.
+// Stands where FCL's box/triangle test stood behind fcl::collide (collision_detection.cpp:36-45); touching counts
+// as contact.  Axes that are numerically null (degenerate triangle, edge parallel to a box axis) carry no
+// information and are skipped — the remaining axes are complete for those configurations.
+// ---------------------------------------------------------------------------------------------------------------
+struct ExactBox {
+	double cx, cy, cz;
+	double r[9];
+	double hx, hy, hz;
+};
+
+__device__ __forceinline__ bool axis_separates(double ax, double ay, double az, double floor2, const ExactBox &b, D3 p0,
+											   D3 p1, D3 p2) {
+	double l2 = ax * ax + ay * ay + az * az;
+	double q0 = ax * p0.x + ay * p0.y + az * p0.z;
+	double q1 = ax * p1.x + ay * p1.y + az * p1.z;
+	double q2 = ax * p2.x + ay * p2.y + az * p2.z;
+	double lo = fmin(q0, fmin(q1, q2)), hi = fmax(q0, fmax(q1, q2));
+	double rad = b.hx * fabs(ax) + b.hy * fabs(ay) + b.hz * fabs(az);
+	return (l2 > floor2) && (fmax(lo - rad, -hi - rad) > 0.0);
+}
+
+static __device__ __noinline__ bool box_triangle_hit(const ExactBox &b, const double *__restrict__ tri) {
+	D3 p[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		double dx = __ldg(tri + 3 * k) - b.cx, dy = __ldg(tri + 3 * k + 1) - b.cy, dz = __ldg(tri + 3 * k + 2) - b.cz;
+		p[k] = {b.r[0] * dx + b.r[3] * dy + b.r[6] * dz, b.r[1] * dx + b.r[4] * dy + b.r[7] * dz,
+				b.r[2] * dx + b.r[5] * dy + b.r[8] * dz};
+	}
+	// box face normals
+	if (fmin(p[0].x, fmin(p[1].x, p[2].x)) > b.hx || fmax(p[0].x, fmax(p[1].x, p[2].x)) < -b.hx) return false;
+	if (fmin(p[0].y, fmin(p[1].y, p[2].y)) > b.hy || fmax(p[0].y, fmax(p[1].y, p[2].y)) < -b.hy) return false;
+	if (fmin(p[0].z, fmin(p[1].z, p[2].z)) > b.hz || fmax(p[0].z, fmax(p[1].z, p[2].z)) < -b.hz) return false;
+	D3 f0 = p[1] - p[0], f1 = p[2] - p[1], f2 = p[0] - p[2];
+	double s0 = dot(f0, f0), s1 = dot(f1, f1), s2 = dot(f2, f2);
+	double scale2 = fmax(s0, fmax(s1, s2));
+	D3 n = cross(f0, f1);
+	if (axis_separates(n.x, n.y, n.z, 1e-28 * scale2 * scale2, b, p[0], p[1], p[2])) return false;
+	const D3 f[3] = {f0, f1, f2};
+	const double fl[3] = {s0, s1, s2};
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		double fl2 = 1e-24 * fl[k];
+		if (axis_separates(0.0, -f[k].z, f[k].y, fl2, b, p[0], p[1], p[2])) return false;
+		if (axis_separates(f[k].z, 0.0, -f[k].x, fl2, b, p[0], p[1], p[2])) return false;
+		if (axis_separates(-f[k].y, f[k].x, 0.0, fl2, b, p[0], p[1], p[2])) return false;
+	}
+	return true;
+}
+
+}  // namespace mgodpl_b200

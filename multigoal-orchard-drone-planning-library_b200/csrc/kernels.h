@@ -1,0 +1,37 @@
+// Host-callable launchers of the device kernels (query_kernels.cu, scene_build.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_types.cuh"
+
+namespace mgodpl_b200 {
+
+cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const double *d_states, size_t n, size_t stride,
+								uint32_t *d_hit_bits, cudaStream_t stream);
+cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t n, uint32_t *d_hit_bits, cudaStream_t stream);
+cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const double *d_a, const double *d_b, size_t m,
+								 size_t stride, int js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,
+								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned long long *d_next_motion,
+								 cudaStream_t stream);
+cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const double *d_targets, size_t f,
+								const double *d_draws, const double *d_limits, size_t s, unsigned long long seed,
+								double distance_from_target, uint32_t *d_hit_bits, uint32_t *d_collisions,
+								double *d_states_out, cudaStream_t stream);
+cudaError_t launch_forward_kinematics(const RobotDev &rb, const double *d_states, size_t n, size_t stride, double *d_out,
+									  cudaStream_t stream);
+
+/// Result of the device BVH build: device buffers owned by the caller (cudaFree).
+struct BuiltScene {
+	float4 *nodes = nullptr;
+	double *tris = nullptr;
+	uint32_t *tri_ids = nullptr;  // original triangle index of every stored triangle slot
+	uint32_t n_nodes = 0, n_tris = 0, n_leaves = 0, max_depth = 0, max_leaf = 0;
+	double sah_cost = 0, build_ms = 0;
+	size_t device_bytes = 0;
+};
+/// d_verts: nv x 3 doubles, d_tris: nt x 3 uint32 (device).  lo/hi: scene bounds (host, from the vertices used).
+cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris, size_t nt, const double *lo,
+						const double *hi, const double *origin, unsigned max_leaf_size, bool refine, BuiltScene *out,
+						cudaStream_t stream);
+
+}  // namespace mgodpl_b200

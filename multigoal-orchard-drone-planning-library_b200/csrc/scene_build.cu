@@ -1,0 +1,293 @@
+// GPU scene builder: triangle soup -> linear BVH (Morton sort + Karras topology) -> bottom-up refit with leaf
+// collapsing -> depth-first preorder flattening with skip links.  Stands where meshToFclBVH stood
+// (src/planning/fcl_utils.cpp:23-56): same input (the Mesh's vertices and index triples, identity pose), a different
+// acceleration structure.  Runs once per scene; everything it produces stays resident in HBM.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "geometry.cuh"
+#include "kernels.h"
+
+namespace mgodpl_b200 {
+
+namespace {
+
+constexpr int TB = 256;
+
+struct BuildStats {
+	unsigned long long n_leaves;
+	unsigned max_depth, max_leaf;
+	double sah;
+};
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long v) {  // 21 bits -> every third bit
+	v &= 0x1fffffull;
+	v = (v | v << 32) & 0x1f00000000ffffull;
+	v = (v | v << 16) & 0x1f0000ff0000ffull;
+	v = (v | v << 8) & 0x100f00f00f00f00full;
+	v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+	v = (v | v << 2) & 0x1249249249249249ull;
+	return v;
+}
+
+/// Per triangle: fp32 bounds relative to `origin` (rounded outward) and the 63-bit Morton key of the bounds centre.
+__global__ void k_prepare(const double *__restrict__ verts, const uint32_t *__restrict__ tris, unsigned nt, D3 origin, D3 lo,
+						  D3 inv_extent, float4 *__restrict__ tlo, float4 *__restrict__ thi,
+						  unsigned long long *__restrict__ keys, uint32_t *__restrict__ ids) {
+	unsigned t = blockIdx.x * TB + threadIdx.x;
+	if (t >= nt) return;
+	double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+	for (int k = 0; k < 3; ++k) {
+		const double *v = verts + 3ull * tris[3ull * t + k];
+		for (int a = 0; a < 3; ++a) mn[a] = fmin(mn[a], v[a]), mx[a] = fmax(mx[a], v[a]);
+	}
+	tlo[t] = make_float4(__double2float_rd(mn[0] - origin.x), __double2float_rd(mn[1] - origin.y),
+						 __double2float_rd(mn[2] - origin.z), 0.f);
+	thi[t] = make_float4(__double2float_ru(mx[0] - origin.x), __double2float_ru(mx[1] - origin.y),
+						 __double2float_ru(mx[2] - origin.z), 0.f);
+	const double scale = 2097151.0;  // 2^21 - 1
+	double cx = fmin(fmax((0.5 * (mn[0] + mx[0]) - lo.x) * inv_extent.x, 0.0), 1.0);
+	double cy = fmin(fmax((0.5 * (mn[1] + mx[1]) - lo.y) * inv_extent.y, 0.0), 1.0);
+	double cz = fmin(fmax((0.5 * (mn[2] + mx[2]) - lo.z) * inv_extent.z, 0.0), 1.0);
+	keys[t] = spread21((unsigned long long) (cx * scale)) << 2 | spread21((unsigned long long) (cy * scale)) << 1 |
+			  spread21((unsigned long long) (cz * scale));
+	ids[t] = t;
+}
+
+// Node ids during construction: internal nodes 0 .. n-2, leaves n-1 .. 2n-2 (leaf j = sorted triangle j).
+__device__ __forceinline__ int delta(const unsigned long long *keys, int n, int i, int j) {
+	if (j < 0 || j >= n) return -1;
+	unsigned long long a = keys[i], b = keys[j];
+	return a == b ? 64 + __clz(i ^ j) : __clzll((long long) (a ^ b));
+}
+
+/// Karras 2012: one thread per internal node finds its key range and split.
+__global__ void k_topology(const unsigned long long *__restrict__ keys, int n, int *__restrict__ left, int *__restrict__ right,
+						   int *__restrict__ parent) {
+	int i = blockIdx.x * TB + threadIdx.x;
+	if (i >= n - 1) return;
+	int d = delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
+	int dmin = delta(keys, n, i, i - d);
+	int lmax = 2;
+	while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+	int l = 0;
+	for (int t = lmax >> 1; t; t >>= 1)
+		if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+	int j = i + l * d;
+	int dnode = delta(keys, n, i, j);
+	int s = 0;
+	for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+		if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+		if (t == 1) break;
+	}
+	int gamma = i + s * d + min(d, 0);
+	int lc = min(i, j) == gamma ? gamma + n - 1 : gamma;
+	int rc = max(i, j) == gamma + 1 ? gamma + 1 + n - 1 : gamma + 1;
+	left[i] = lc, right[i] = rc;
+	parent[lc] = i, parent[rc] = i;
+	if (i == 0) parent[0] = -1;
+}
+
+/// Bottom-up: bounds, triangle counts, first triangle slot, and — with leaves collapsed at `max_leaf` triangles —
+/// the number of nodes the flattened subtree will occupy.
+__global__ void k_refit(int n, const uint32_t *__restrict__ ids, const float4 *__restrict__ tlo, const float4 *__restrict__ thi,
+						const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ parent,
+						float4 *__restrict__ blo, float4 *__restrict__ bhi, unsigned *__restrict__ tri_count,
+						unsigned *__restrict__ first_slot, unsigned *__restrict__ eff_size, unsigned *__restrict__ flags,
+						unsigned max_leaf) {
+	int j = blockIdx.x * TB + threadIdx.x;
+	if (j >= n) return;
+	int node = j + n - 1;
+	uint32_t t = ids[j];
+	blo[node] = tlo[t], bhi[node] = thi[t];
+	tri_count[node] = 1, first_slot[node] = j, eff_size[node] = 1;
+	__threadfence();
+	int p = n > 1 ? parent[node] : -1;
+	while (p >= 0) {
+		if (atomicAdd(&flags[p], 1u) == 0) return;  // first child to arrive leaves; the second one merges
+		__threadfence();
+		int l = left[p], r = right[p];
+		float4 llo = __ldcg(blo + l), lhi = __ldcg(bhi + l), rlo = __ldcg(blo + r), rhi = __ldcg(bhi + r);
+		blo[p] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
+		bhi[p] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
+		unsigned cnt = __ldcg(tri_count + l) + __ldcg(tri_count + r);
+		tri_count[p] = cnt;
+		first_slot[p] = min(__ldcg(first_slot + l), __ldcg(first_slot + r));
+		eff_size[p] = cnt <= max_leaf ? 1u : 1u + __ldcg(eff_size + l) + __ldcg(eff_size + r);
+		__threadfence();
+		p = parent[p];
+	}
+}
+
+__device__ __forceinline__ float half_area(float4 lo, float4 hi) {
+	float x = hi.x - lo.x, y = hi.y - lo.y, z = hi.z - lo.z;
+	return x * y + y * z + z * x;
+}
+
+/// One thread per construction node: if the node survives collapsing, find its preorder slot by walking to the
+/// root, then emit the 32-byte traversal node (centre, skip | half extent, leaf info).
+__global__ void k_flatten(int n, const int *__restrict__ left, const int *__restrict__ parent, const float4 *__restrict__ blo,
+						  const float4 *__restrict__ bhi, const unsigned *__restrict__ tri_count,
+						  const unsigned *__restrict__ first_slot, const unsigned *__restrict__ eff_size, unsigned max_leaf,
+						  float4 *__restrict__ nodes, BuildStats *__restrict__ stats) {
+	int x = blockIdx.x * TB + threadIdx.x;
+	if (x >= 2 * n - 1) return;
+	const int root = 0;  // internal node 0, or — when n == 1 — the single leaf (id n-1 == 0)
+	int p = parent[x];   // -1 for the root
+	if (p >= 0 && tri_count[p] <= max_leaf) return;  // swallowed by a collapsed ancestor
+	unsigned pre = 0, depth = 0;
+	for (int c = x; p >= 0; c = p, p = parent[p]) {
+		int l = left[p];
+		pre += 1u + (c == l ? 0u : eff_size[l]);
+		++depth;
+	}
+	const unsigned cnt = tri_count[x];
+	const bool leaf = cnt <= max_leaf;
+	const float4 lo = blo[x], hi = bhi[x];
+	float c[3], h[3];
+	const float lo3[3] = {lo.x, lo.y, lo.z}, hi3[3] = {hi.x, hi.y, hi.z};
+	for (int a = 0; a < 3; ++a) {
+		double cd = 0.5 * ((double) lo3[a] + (double) hi3[a]);
+		c[a] = (float) cd;
+		h[a] = __double2float_ru(0.5 * ((double) hi3[a] - (double) lo3[a]) + fabs(cd - (double) c[a]));
+	}
+	const unsigned skip = pre + eff_size[x];
+	const int info = leaf ? (int) (first_slot[x] << 4 | (cnt - 1)) : -1;
+	nodes[2 * pre] = make_float4(c[0], c[1], c[2], __uint_as_float(skip));
+	nodes[2 * pre + 1] = make_float4(h[0], h[1], h[2], __int_as_float(info));
+	// statistics
+	const float root_area = half_area(blo[root], bhi[root]);
+	double cost = root_area > 0.f ? (double) half_area(lo, hi) / (double) root_area * (leaf ? (double) cnt : 1.0) : 0.0;
+	atomicAdd(&stats->sah, cost);
+	if (leaf) {
+		atomicAdd(&stats->n_leaves, 1ull);
+		atomicMax(&stats->max_leaf, cnt);
+		atomicMax(&stats->max_depth, depth);
+	}
+}
+
+/// Triangle payload in leaf (= Morton) order: 9 fp64 world coordinates per slot.
+__global__ void k_emit_tris(const double *__restrict__ verts, const uint32_t *__restrict__ tris, const uint32_t *__restrict__ ids,
+							unsigned nt, double *__restrict__ out) {
+	unsigned j = blockIdx.x * TB + threadIdx.x;
+	if (j >= nt) return;
+	uint32_t t = ids[j];
+	for (int k = 0; k < 3; ++k) {
+		const double *v = verts + 3ull * tris[3ull * t + k];
+		out[9ull * j + 3 * k] = v[0], out[9ull * j + 3 * k + 1] = v[1], out[9ull * j + 3 * k + 2] = v[2];
+	}
+}
+
+struct Scratch {
+	std::vector<void *> ptrs;
+	template<class T>
+	cudaError_t alloc(T **p, size_t n) {
+		cudaError_t e = cudaMalloc((void **) p, std::max<size_t>(n, 1) * sizeof(T));
+		if (e == cudaSuccess) ptrs.push_back(*p);
+		return e;
+	}
+	~Scratch() {
+		for (void *p: ptrs) cudaFree(p);
+	}
+};
+
+}  // namespace
+
+#define BS_CHECK(x)                       \
+	do {                                  \
+		cudaError_t e_ = (x);             \
+		if (e_ != cudaSuccess) return e_; \
+	} while (0)
+
+cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris, size_t nt, const double *lo, const double *hi,
+						const double *origin, unsigned max_leaf_size, bool refine, BuiltScene *out, cudaStream_t stream) {
+	(void) nv;
+	(void) refine;
+	*out = BuiltScene{};
+	if (nt == 0) return cudaSuccess;
+	if (max_leaf_size < 1) max_leaf_size = 1;
+	if (max_leaf_size > 16) max_leaf_size = 16;
+	const int n = (int) nt;
+	const unsigned gt = (unsigned) ((nt + TB - 1) / TB);
+	Scratch tmp;
+	float4 *tlo, *thi, *blo, *bhi;
+	unsigned long long *keys, *keys2;
+	uint32_t *ids, *ids2;
+	int *left, *right, *parent;
+	unsigned *tri_count, *first_slot, *eff_size, *flags;
+	BuildStats *d_stats;
+	BS_CHECK(tmp.alloc(&tlo, nt));
+	BS_CHECK(tmp.alloc(&thi, nt));
+	BS_CHECK(tmp.alloc(&keys, nt));
+	BS_CHECK(tmp.alloc(&keys2, nt));
+	BS_CHECK(tmp.alloc(&ids2, nt));
+	BS_CHECK(tmp.alloc(&left, nt));
+	BS_CHECK(tmp.alloc(&right, nt));
+	BS_CHECK(tmp.alloc(&parent, 2 * nt));
+	BS_CHECK(tmp.alloc(&blo, 2 * nt));
+	BS_CHECK(tmp.alloc(&bhi, 2 * nt));
+	BS_CHECK(tmp.alloc(&tri_count, 2 * nt));
+	BS_CHECK(tmp.alloc(&first_slot, 2 * nt));
+	BS_CHECK(tmp.alloc(&eff_size, 2 * nt));
+	BS_CHECK(tmp.alloc(&flags, nt));
+	BS_CHECK(tmp.alloc(&d_stats, 1));
+	BS_CHECK(cudaMalloc((void **) &ids, nt * sizeof(uint32_t)));  // kept: slot -> original triangle
+	out->tri_ids = ids;
+
+	cudaEvent_t ev0, ev1;
+	BS_CHECK(cudaEventCreate(&ev0));
+	BS_CHECK(cudaEventCreate(&ev1));
+	BS_CHECK(cudaEventRecord(ev0, stream));
+
+	D3 inv{hi[0] > lo[0] ? 1.0 / (hi[0] - lo[0]) : 0.0, hi[1] > lo[1] ? 1.0 / (hi[1] - lo[1]) : 0.0,
+		   hi[2] > lo[2] ? 1.0 / (hi[2] - lo[2]) : 0.0};
+	k_prepare<<<gt, TB, 0, stream>>>(d_verts, d_tris, (unsigned) nt, D3{origin[0], origin[1], origin[2]},
+									 D3{lo[0], lo[1], lo[2]}, inv, tlo, thi, keys, ids2);
+	BS_CHECK(cudaGetLastError());
+	{
+		size_t bytes = 0;
+		BS_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys2, ids2, ids, n, 0, 63, stream));
+		void *ws;
+		BS_CHECK(tmp.alloc((char **) &ws, bytes));
+		BS_CHECK(cub::DeviceRadixSort::SortPairs(ws, bytes, keys, keys2, ids2, ids, n, 0, 63, stream));
+	}
+	BS_CHECK(cudaMemsetAsync(flags, 0, nt * sizeof(unsigned), stream));
+	BS_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(BuildStats), stream));
+	BS_CHECK(cudaMemsetAsync(parent, 0xff, 2 * nt * sizeof(int), stream));
+	if (n > 1) {
+		k_topology<<<gt, TB, 0, stream>>>(keys2, n, left, right, parent);
+		BS_CHECK(cudaGetLastError());
+	}
+	k_refit<<<gt, TB, 0, stream>>>(n, ids, tlo, thi, left, right, parent, blo, bhi, tri_count, first_slot, eff_size, flags,
+								   max_leaf_size);
+	BS_CHECK(cudaGetLastError());
+	// The flattened size is the root's effective size; fetch it before allocating the node array.
+	unsigned n_nodes = 0;
+	BS_CHECK(cudaMemcpyAsync(&n_nodes, eff_size, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+	BS_CHECK(cudaStreamSynchronize(stream));
+	BS_CHECK(cudaMalloc((void **) &out->nodes, (size_t) n_nodes * 2 * sizeof(float4)));
+	BS_CHECK(cudaMalloc((void **) &out->tris, nt * 9 * sizeof(double)));
+	k_flatten<<<(unsigned) ((2 * nt - 1 + TB - 1) / TB), TB, 0, stream>>>(n, left, parent, blo, bhi, tri_count, first_slot,
+																		  eff_size, max_leaf_size, out->nodes, d_stats);
+	BS_CHECK(cudaGetLastError());
+	k_emit_tris<<<gt, TB, 0, stream>>>(d_verts, d_tris, ids, (unsigned) nt, out->tris);
+	BS_CHECK(cudaGetLastError());
+	BS_CHECK(cudaEventRecord(ev1, stream));
+	BuildStats st{};
+	BS_CHECK(cudaMemcpyAsync(&st, d_stats, sizeof(st), cudaMemcpyDeviceToHost, stream));
+	BS_CHECK(cudaStreamSynchronize(stream));
+	float ms = 0;
+	cudaEventElapsedTime(&ms, ev0, ev1);
+	cudaEventDestroy(ev0);
+	cudaEventDestroy(ev1);
+	out->n_nodes = n_nodes;
+	out->n_tris = (uint32_t) nt;
+	out->n_leaves = (uint32_t) st.n_leaves;
+	out->max_depth = st.max_depth;
+	out->max_leaf = st.max_leaf;
+	out->sah_cost = st.sah;
+	out->build_ms = ms;
+	out->device_bytes = (size_t) n_nodes * 32 + nt * 72 + nt * 4;
+	return cudaSuccess;
+}
+
+}  // namespace mgodpl_b200

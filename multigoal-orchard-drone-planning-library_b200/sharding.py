@@ -1,0 +1,47 @@
+"""Batch sharding for one-process-per-GPU runs.
+
+Every state / motion / goal sample is independent given the (replicated, read-only) scene, so a batch is split into
+contiguous index ranges whose boundaries are multiples of 32: result bitmask words then never straddle two ranks and
+the gathered mask is the plain concatenation of the per-rank words.  No collective is needed on the data path; only
+the packed result words are gathered.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n: int, rank: int, world_size: int, align: int = 32) -> tuple[int, int]:
+    """[lo, hi) of `rank`'s share of n queries; lo is a multiple of `align`, shares differ by at most `align`."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("bad rank / world_size")
+    blocks = (n + align - 1) // align
+    per, extra = divmod(blocks, world_size)
+    lo_b = rank * per + min(rank, extra)
+    hi_b = lo_b + per + (1 if rank < extra else 0)
+    return min(lo_b * align, n), min(hi_b * align, n)
+
+
+def words_for(n: int) -> int:
+    return (n + 31) // 32
+
+
+def gather_words(local_words, n: int, rank: int, world_size: int, group=None):
+    """All-gather the packed result words of every rank's shard into the full bitmask (torch.distributed; NCCL on
+    GPUs, gloo in the CPU tests).  `local_words` is a uint32/int32 torch tensor of this rank's shard."""
+    import torch
+    import torch.distributed as dist
+
+    sizes = [words_for(hi - lo) for lo, hi in (shard_range(n, r, world_size) for r in range(world_size))]
+    pad = max(sizes) if sizes else 0
+    buf = torch.zeros(pad, dtype=torch.int32, device=local_words.device)
+    buf[: local_words.numel()] = local_words.view(torch.int32)
+    out = [torch.empty_like(buf) for _ in range(world_size)]
+    dist.all_gather(out, buf, group=group)
+    return torch.cat([o[:s] for o, s in zip(out, sizes)])
+
+
+def concat_words(per_rank_words, n: int) -> np.ndarray:
+    """Host-side equivalent of gather_words for already-collected shards (used by tests)."""
+    out = np.concatenate([np.asarray(w, dtype=np.uint32) for w in per_rank_words]) if per_rank_words else np.zeros(0, np.uint32)
+    assert len(out) == words_for(n)
+    return out
