@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Benchmark of the collision-query hot path (BASELINE.json metric: collision-checked states/s and motions/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the hot path over one batch of synthetic input:
+  workload  BASELINE.json configs[1]: 100 000 straight-line motions between PRM-sampler states
+            (generateUniformRandomState, h=5, v=10; src/planning/tsp_over_prm.cpp:569-571) validated with
+            check_motion_collides at the reference's 0.1 step, early exit, toi reported, against the 200 k-triangle
+            synthetic tree (trunk + leaves), default 0.75 m one-joint arm.
+  value     collision-checked robot states per second, counted the way the reference would count them
+            (a motion that first collides at step k costs k+1 state checks, a free one n_steps+1), inputs resident in
+            HBM, device time from CUDA events on the launching stream, L2 flushed before every timed step.
+  e2e       the same metric through the host-buffer C ABI call (pinned host inputs, H2D + kernel + D2H inside).
+With N > 1 (torchrun) every rank holds a replica of the scene and validates its own 100 000 motions (weak scaling);
+the packed result words are all-gathered over NCCL inside the step.
+
+--impl reference times the reference's own CPU implementation of the same path (oracle/_ref: the reference's sources
+compiled unmodified over the FCL/Eigen shim; falls back to the oracle port) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_MOTIONS = 100_000
+ARM, JOINTS = 0.75, (0,)
+TREE = dict(seed=42, trunk_triangles=50_000, leaf_triangles=150_000, n_fruit=500)
+MAX_STEP = 0.1
+B_MOTION = 2 * 8 * (7 + 2) + 1 / 8 + 8 + 4  # two fp64 states in, 1 result bit + toi + step count out
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def make_inputs(mg, rank: int):
+    model = mg.robots.create_procedural_robot_model(ARM, JOINTS)
+    rng = mg.robots.Mt19937(42 + rank)
+    s = mg.robots.generate_uniform_random_states(model, rng, 2 * M_MOTIONS, 5.0, 10.0)
+    return model, s[:M_MOTIONS].copy(), s[M_MOTIONS:].copy()
+
+
+def ref_equivalent_states(hit, toi, n_steps):
+    """State checks the reference's sequential loop performs (collision_detection.cpp:94-103)."""
+    n = np.maximum(n_steps, 1)
+    first = np.rint(np.nan_to_num(toi) * n).astype(np.int64)
+    return np.where(hit, np.where(n_steps > 0, first + 1, 1), n_steps + 1)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import mgodpl_b200 as mg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    tree = mg.scenes.make_tree(**TREE)
+    mesh = tree.collision_mesh(True)
+    scene = mg.Scene.from_mesh(mesh)
+    info = scene.info()
+    model, a, b = make_inputs(mg, rank)
+    robot = model.to_device()
+    stride, js, m = a.shape[1], a.shape[1] - 7, len(a)
+    words = (m + 31) // 32
+
+    # device-resident inputs / outputs
+    d_a, d_b = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    d_hit = torch.zeros(words, dtype=torch.int32, device=dev)
+    d_toi = torch.zeros(m, dtype=torch.float64, device=dev)
+    d_steps = torch.zeros(m, dtype=torch.int32, device=dev)
+    d_unc = torch.zeros(words, dtype=torch.int32, device=dev)
+    gathered = [torch.empty_like(d_hit) for _ in range(world)] if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)  # 256 MiB > 126 MB of L2
+
+    def step():
+        mg.capi.check_motions_device(scene, robot, d_a, d_b, m, stride, js, d_hit, MAX_STEP, d_toi, d_steps, d_unc,
+                                     stream=stream)
+        if world > 1:
+            dist.all_gather(gathered, d_hit)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        flush.fill_(k)  # evict inputs and scene from L2 (outside the timed events)
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag.set()
+    sampler.join()
+    step_ms = [s.elapsed_time(e) for s, e in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+
+    hit = mg.capi.unpack_bits(d_hit.cpu().numpy().view(np.uint32), m)
+    toi, n_steps = d_toi.cpu().numpy(), d_steps.cpu().numpy().astype(np.int64)
+    states_per_batch = torch.tensor([float(ref_equivalent_states(hit, toi, n_steps).sum())], dtype=torch.float64, device=dev)
+    motions_total = torch.tensor([float(m)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(states_per_batch)
+        dist.all_reduce(motions_total)
+    states_all, motions_all = float(states_per_batch.item()), float(motions_total.item())
+    value = states_all * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host-buffer C ABI call, pinned inputs, H2D + kernel + D2H in the timed region -------------------------
+    pa, pb = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+    na, nb = pa.numpy(), pb.numpy()
+    for _ in range(2):
+        mg.capi.check_motions(scene, robot, na, nb, MAX_STEP, True, stream=stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = mg.capi.check_motions(scene, robot, na, nb, MAX_STEP, True, stream=stream)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    assert np.array_equal(res["hit"], hit), "host-buffer and device-buffer paths disagree"
+    e2e_value = states_all * e2e_steps / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_kind = peaks()
+    ms_per_step = total_ms / args.steps
+    b_scene = info.n_nodes * 32 + info.n_triangles * 72
+    algo_bytes = m * B_MOTION + b_scene
+    achieved = algo_bytes / (np.mean(step_ms) * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("k_check_motions_dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": "collision_checked_states_per_sec", "value": value, "unit": "states/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 100k straight-line motions/GPU, check_motion_collides @ step 0.1, early exit + toi, "
+                               "200k-triangle synthetic tree (trunk+leaves), 0.75 m 1-joint arm, PRM sampler h=5 v=10",
+                   "motions_per_gpu": m, "triangles": int(info.n_triangles), "bvh_nodes": int(info.n_nodes),
+                   "l2": "flushed before every timed step (256 MiB write)", "parallelism": f"replicated scene x{world}, batch sharded"},
+        "motions_per_sec": motions_all * args.steps / (total_ms * 1e-3),
+        "states_checked_per_motion": states_all / motions_all, "collision_rate": float(hit.mean()),
+        "e2e": {"value": e2e_value, "unit": "states/s", "h2d_bytes_per_step": int(2 * m * stride * 8),
+                "d2h_bytes_per_step": int(2 * words * 4 + m * 4 + m * 8), "steps": e2e_steps},
+        "gpu_launches": args.steps + e2e_steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_kind": peak_kind, "kernel": "k_check_motions",
+                     "algorithmic_bytes_per_launch": algo_bytes},
+        "clocks": sampler.summary(),
+        "scene": {"build_ms": info.build_ms, "sah_cost": info.sah_cost, "max_depth": int(info.max_depth),
+                  "device_bytes": int(info.device_bytes)},
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(mesh, a, b, use_ref=False)
+    if not args.no_extra:
+        line["extra"] = extra_workloads(mg, torch, scene, tree, dev, stream)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_workloads(mg, torch, scene, tree, dev, stream):
+    """Secondary numbers (not the headline): 10 M state checks and 500 x 1000 goal samples on the same tree."""
+    out = {}
+    model = mg.robots.create_procedural_robot_model(1.0, (0,))
+    robot = model.to_device()
+    n = 10_000_000
+    lo, hi = tree.trunk_mesh.aabb()
+    h = max(hi[0] - lo[0], hi[1] - lo[1]) / 2 + 2.0
+    gen = torch.Generator(device=dev).manual_seed(1)
+    u = torch.rand((n, 6), generator=gen, device=dev, dtype=torch.float64)
+    st = torch.zeros((n, 9), dtype=torch.float64, device=dev)
+    st[:, 0] = (u[:, 0] * 2 - 1) * 5.0
+    st[:, 1] = (u[:, 1] * 2 - 1) * 5.0
+    st[:, 2] = u[:, 2] * 10.0
+    yaw = u[:, 3] * (2 * np.pi)
+    st[:, 5], st[:, 6] = torch.sin(yaw / 2), torch.cos(yaw / 2)
+    st[:, 7] = (u[:, 4] * 2 - 1) * (np.pi / 2)
+    st[:, 8] = (u[:, 5] * 2 - 1) * (np.pi / 2)
+    d_hit = torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev)
+    for name, hh, vv in (("states_10M_prm_box_h5_v10", 5.0, 10.0), ("states_10M_config1_box", h, float(lo[2] + 1.0))):
+        st[:, 0] = (u[:, 0] * 2 - 1) * hh
+        st[:, 1] = (u[:, 1] * 2 - 1) * hh
+        st[:, 2] = u[:, 2] * vv
+        for _ in range(2):
+            mg.capi.check_states_device(scene, robot, st, n, 9, 2, d_hit, stream=stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            mg.capi.check_states_device(scene, robot, st, n, 9, 2, d_hit, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out[name] = {"states_per_sec": n / (ms * 1e-3), "ms": ms, "hbm_frac": n * 72.125 / (ms * 1e-3) / 1e9 / peaks()[0],
+                     "collision_rate": float(mg.capi.unpack_bits(d_hit.cpu().numpy().view(np.uint32), n).mean())}
+    # goal sampling: 500 fruit x 1000 samples, device-side draws
+    f, s = len(tree.fruit_centers), 1000
+    d_t = torch.from_numpy(tree.fruit_centers.copy()).to(dev)
+    d_gh = torch.zeros(f * ((s + 31) // 32), dtype=torch.int32, device=dev)
+    d_cnt = torch.zeros(f, dtype=torch.int32, device=dev)
+    for _ in range(2):
+        mg.capi.sample_goals_device(scene, robot, d_t, f, s, d_gh, d_collisions=d_cnt, stream=stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        mg.capi.sample_goals_device(scene, robot, d_t, f, s, d_gh, d_collisions=d_cnt, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    out["goal_sampling_500x1000"] = {"samples_per_sec": f * s / (ms * 1e-3), "ms": ms,
+                                     "collision_rate": float(d_cnt.cpu().numpy().sum() / (f * s))}
+    return out
+
+
+def cpu_baseline(mesh, a, b, use_ref: bool, budget_s: float = 20.0):
+    """The CPU implementation of the same step on the host cores (reported baseline, not the target)."""
+    from oracle import oracle as o
+    cores = os.cpu_count() or 1
+    m = len(a)
+    if use_ref and o.have_ref():
+        robot, scene = o.RefRobot(ARM, JOINTS), o.RefScene(mesh.vertices, mesh.triangles)
+
+        def run(lo, hi, out):
+            out.append(scene.check_motions(robot, a[lo:hi], b[lo:hi]))
+        kind = "reference"
+        what = ("reference's own collision_detection.cpp/RobotModel.cpp/... compiled unmodified (oracle/_ref); FCL is absent "
+                "offline, fcl::collide answered by the oracle's exact SAT over an AABB tree")
+    else:
+        robot, scene = o.Robot(ARM, JOINTS), o.Scene(mesh.vertices, mesh.triangles)
+
+        def run(lo, hi, out):
+            r = scene.check_motions(robot, a[lo:hi], b[lo:hi])
+            out.append((r["hit"], r["toi"]))
+        kind = "port"
+        what = "fp64 oracle port (FCL-equivalent CPU restatement; FCL not buildable offline)"
+    # calibrate on a small slice, then size the sample for ~budget_s of wall time
+    t0 = time.perf_counter()
+    run(0, min(m, 500), [])
+    per = (time.perf_counter() - t0) / min(m, 500)
+    sample = int(min(m, max(2000, budget_s * cores / max(per, 1e-9) * 0.5)))
+    chunks = np.linspace(0, sample, cores + 1).astype(int)
+    outs = [[] for _ in range(cores)]
+    threads = [threading.Thread(target=run, args=(chunks[i], chunks[i + 1], outs[i])) for i in range(cores) if chunks[i + 1] > chunks[i]]
+    t0 = time.perf_counter()
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    dt = time.perf_counter() - t0
+    hit = np.concatenate([x[0][0] for x in outs if x])
+    toi = np.concatenate([x[0][1] for x in outs if x])
+    # reference-equivalent state count of the sample, from the oracle's own step counts
+    res = o.Scene(mesh.vertices, mesh.triangles).check_motions(o.Robot(ARM, JOINTS), a[:sample], b[:sample], threads=cores)
+    states = int(res["states_checked"].sum())
+    assert np.array_equal(hit, res["hit"])
+    return {"value": states / dt, "unit": "states/s", "cores": cores, "kind": kind,
+            "sample": f"first {sample} of {m} motions of the same batch, {cores} host threads, {dt:.2f} s; {what}",
+            "motions_per_sec": sample / dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import mgodpl_b200 as mg
+    tree = mg.scenes.make_tree(**TREE)
+    mesh = tree.collision_mesh(True)
+    _, a, b = make_inputs(mg, 0)
+    steps = max(1, args.steps)
+    vals = []
+    for k in range(args.warmup + steps):
+        r = cpu_baseline(mesh, a, b, use_ref=True, budget_s=max(2.0, 60.0 / (args.warmup + steps)))
+        if k >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    mps = float(np.mean([r["motions_per_sec"] for r in vals]))
+    r = vals[-1]
+    sample_n = int(r["sample"].split()[1])
+    line = {"impl": "reference", "metric": "collision_checked_states_per_sec", "value": v, "unit": "states/s",
+            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sample_n / mps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: straight-line motions, check_motion_collides @ step 0.1, early exit + toi, "
+                                   "200k-triangle synthetic tree (trunk+leaves), 0.75 m 1-joint arm, PRM sampler h=5 v=10; "
+                                   "each step a bounded sample of the 100k-motion batch"},
+            "motions_per_sec": mps,
+            "cpu_baseline": {"value": v, "unit": "states/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": v, "unit": "states/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
