@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -112,13 +113,19 @@ struct mgodpl_scene {
 	BuiltScene built{};
 	mgodpl_scene_info info{};
 	unsigned long long *d_counters = nullptr;
-	// Work-distribution cursors for the motion kernel: a ring, so that asynchronous device-variant calls on several
-	// streams never share one (a slot is reused only after CURSOR_RING further launches).
-	static constexpr unsigned CURSOR_RING = 1024;
-	unsigned long long *d_cursors = nullptr;
-	std::atomic<unsigned> next_cursor{0};
-	WorkspacePool pool;
-	unsigned long long *cursor() { return d_cursors + (next_cursor.fetch_add(1) % CURSOR_RING); }
+	WorkspacePool pool;  // host-buffer calls: one exclusive workspace per call, held until the call has synchronised
+	// Device-buffer calls only enqueue work, so their scratch must outlive the call: one workspace per stream, reused in
+	// stream order (growing it frees the old block with cudaFree, which waits for the device first).
+	std::mutex stream_mu;
+	std::map<cudaStream_t, std::unique_ptr<Workspace>> stream_ws;
+	cudaError_t device_scratch(cudaStream_t stream, size_t bytes, char **out) {
+		std::lock_guard<std::mutex> g(stream_mu);
+		auto &w = stream_ws[stream];
+		if (!w) w = std::make_unique<Workspace>();
+		cudaError_t e = w->reserve(bytes, 0);
+		*out = w->dev;
+		return e;
+	}
 };
 
 struct mgodpl_robot {
@@ -210,7 +217,6 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 	} else {
 		for (int a = 0; a < 3; ++a) d.root_c[a] = 0.f, d.root_h[a] = -1.f;  // nothing overlaps an empty scene
 	}
-	CU(cudaMalloc((void **) &sc->d_cursors, mgodpl_scene::CURSOR_RING * sizeof(unsigned long long)));
 	if (opts && (opts->flags & MGODPL_SCENE_COUNTERS)) {
 		CU(cudaMalloc((void **) &sc->d_counters, CNT_N * sizeof(unsigned long long)));
 		CU(cudaMemset(sc->d_counters, 0, CNT_N * sizeof(unsigned long long)));
@@ -236,7 +242,7 @@ int mgodpl_scene_create_u64(const double *verts, size_t nv, const uint64_t *tris
 }
 int mgodpl_scene_destroy(mgodpl_scene *s) {
 	if (!s) return MGODPL_OK;
-	cudaFree(s->built.nodes), cudaFree(s->built.tris), cudaFree(s->built.tri_ids), cudaFree(s->d_counters), cudaFree(s->d_cursors);
+	cudaFree(s->built.nodes), cudaFree(s->built.tris), cudaFree(s->built.tri_ids), cudaFree(s->d_counters);
 	delete s;
 	return MGODPL_OK;
 }
@@ -441,15 +447,17 @@ int mgodpl_forward_kinematics(const mgodpl_robot *robot, const double *states, s
 int mgodpl_check_boxes(mgodpl_scene *scene, const double *boxes, size_t n, uint32_t *hit_bits, void *stream_) {
 	if (!scene) return fail(MGODPL_E_INVALID_ARGUMENT, "scene is null");
 	if (n && (!boxes || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (n >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^32-2 queries in one call");
 	if (int rc = require_device()) return rc;
 	if (!n) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Lease ws(scene->pool);
 	Carver c;
-	size_t o_in = c.take(n * 80), words = (n + 31) / 32, o_out = c.take(words * 4);
+	const size_t words = (n + 31) / 32, qb = query_scratch_bytes(n);
+	size_t o_in = c.take(n * 80), o_out = c.take(words * 4), o_q = c.take(qb);
 	CU(ws->reserve(c.off, words * 4));
 	CU(cudaMemcpyAsync(ws->dev + o_in, boxes, n * 80, cudaMemcpyHostToDevice, stream));
-	CU(launch_check_boxes(scene->dev, (const double *) (ws->dev + o_in), n, (uint32_t *) (ws->dev + o_out), stream));
+	CU(launch_check_boxes(scene->dev, (const double *) (ws->dev + o_in), n, (uint32_t *) (ws->dev + o_out), ws->dev + o_q, qb, stream));
 	CU(cudaMemcpyAsync(ws->host, ws->dev + o_out, words * 4, cudaMemcpyDeviceToHost, stream));
 	CU(cudaStreamSynchronize(stream));
 	memcpy(hit_bits, ws->host, words * 4);
@@ -462,8 +470,14 @@ int mgodpl_check_states_device(mgodpl_scene *scene, const mgodpl_robot *robot, c
 	if (!scene) return fail(MGODPL_E_INVALID_ARGUMENT, "scene is null");
 	if (int rc = check_state_args(robot, stride, js)) return rc;
 	if (n && (!d_states || !d_hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (n >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^32-2 queries in one call");
 	if (int rc = require_device()) return rc;
-	CU(launch_check_states(scene->dev, robot->dev, d_states, n, stride, d_hit_bits, (cudaStream_t) stream_));
+	if (!n) return MGODPL_OK;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	const size_t qb = query_scratch_bytes(n * (size_t) robot->dev.n_boxes);
+	char *scratch = nullptr;
+	CU(scene->device_scratch(stream, qb, &scratch));
+	CU(launch_check_states(scene->dev, robot->dev, d_states, n, stride, d_hit_bits, scratch, qb, stream));
 	return MGODPL_OK;
 }
 
@@ -472,17 +486,19 @@ int mgodpl_check_states(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	if (!scene) return fail(MGODPL_E_INVALID_ARGUMENT, "scene is null");
 	if (int rc = check_state_args(robot, stride, js)) return rc;
 	if (n && (!states || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (n >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^32-2 queries in one call");
 	if (int rc = require_device()) return rc;
 	if (!n) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Lease ws(scene->pool);
 	Carver c;
-	size_t in_b = n * stride * 8, words = (n + 31) / 32;
-	size_t o_in = c.take(in_b), o_out = c.take(words * 4);
+	const size_t in_b = n * stride * 8, words = (n + 31) / 32, qb = query_scratch_bytes(n * (size_t) robot->dev.n_boxes);
+	size_t o_in = c.take(in_b), o_out = c.take(words * 4), o_q = c.take(qb);
 	CU(ws->reserve(c.off, words * 4));
 	// Caller memory goes straight to the device; only the (small) result is staged through pinned memory.
 	CU(cudaMemcpyAsync(ws->dev + o_in, states, in_b, cudaMemcpyHostToDevice, stream));
-	CU(launch_check_states(scene->dev, robot->dev, (const double *) (ws->dev + o_in), n, stride, (uint32_t *) (ws->dev + o_out), stream));
+	CU(launch_check_states(scene->dev, robot->dev, (const double *) (ws->dev + o_in), n, stride, (uint32_t *) (ws->dev + o_out),
+						   ws->dev + o_q, qb, stream));
 	CU(cudaMemcpyAsync(ws->host, ws->dev + o_out, words * 4, cudaMemcpyDeviceToHost, stream));
 	CU(cudaStreamSynchronize(stream));
 	memcpy(hit_bits, ws->host, words * 4);
@@ -490,6 +506,10 @@ int mgodpl_check_states(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 }
 
 // ---- motions ---------------------------------------------------------------------------------------------------------------
+/// Queue sizing for motions: the step count is only known on the device, so assume ~128 steps per motion (the PRM
+/// sampler averages ~104) — a wrong guess only moves work between stage B and stage A's inline path.
+static size_t motion_scratch_bytes(size_t m, int n_boxes) { return query_scratch_bytes(m * 128 * (size_t) n_boxes); }
+
 int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, const double *d_a, const double *d_b, size_t m,
 								size_t stride, int32_t js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,
 								double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, void *stream_) {
@@ -497,10 +517,18 @@ int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, 
 	if (int rc = check_state_args(robot, stride, js)) return rc;
 	if (!(max_step > 0.0)) return fail(MGODPL_E_INVALID_ARGUMENT, "max_step must be positive");
 	if (m && (!d_a || !d_b || !d_hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (m >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^32-2 queries in one call");
 	if (int rc = require_device()) return rc;
 	if (!m) return MGODPL_OK;
-	CU(launch_check_motions(scene->dev, robot->dev, d_a, d_b, m, stride, js, max_step, d_override, d_hit_bits, d_toi, d_n_steps,
-							d_uncertain, scene->cursor(), (cudaStream_t) stream_));
+	cudaStream_t stream = (cudaStream_t) stream_;
+	Carver c;
+	const size_t qb = motion_scratch_bytes(m, robot->dev.n_boxes);
+	size_t o_first = c.take(m * 4), o_steps = c.take(d_n_steps ? 0 : m * 4), o_q = c.take(qb);
+	char *scratch = nullptr;
+	CU(scene->device_scratch(stream, c.off, &scratch));
+	CU(launch_check_motions(scene->dev, robot->dev, d_a, d_b, m, stride, js, max_step, d_override, d_hit_bits, d_toi,
+							d_n_steps ? d_n_steps : (uint32_t *) (scratch + o_steps), d_uncertain, (unsigned *) (scratch + o_first),
+							scratch + o_q, qb, stream));
 	return MGODPL_OK;
 }
 
@@ -515,7 +543,7 @@ uint32_t host_n_steps(const double *a, const double *b, int js, double max_step)
 	d += std::acos(2.0 * c * c - 1.0);
 	for (int i = 0; i < js; ++i) d += std::abs(a[7 + i] - b[7 + i]);
 	double n = std::ceil(d / max_step);
-	if (!(n >= 0.0 && n < 4.0e9)) return 0;
+	if (!(n >= 0.0 && n < 268435455.0)) return 0;
 	return (uint32_t) n;
 }
 }  // namespace
@@ -526,29 +554,31 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	if (int rc = check_state_args(robot, stride, js)) return rc;
 	if (!(max_step > 0.0)) return fail(MGODPL_E_INVALID_ARGUMENT, "max_step must be positive");
 	if (m && (!a || !b || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (m >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^32-2 queries in one call");
 	if (int rc = require_device()) return rc;
 	if (!m) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Lease ws(scene->pool);
 	Carver c;
-	const size_t in_b = m * stride * 8, words = (m + 31) / 32;
-	size_t o_a = c.take(in_b), o_b = c.take(in_b);
+	const size_t in_b = m * stride * 8, words = (m + 31) / 32, qb = motion_scratch_bytes(m, robot->dev.n_boxes);
+	size_t o_a = c.take(in_b), o_b = c.take(in_b), o_first = c.take(m * 4);
 	// outputs are contiguous so that one D2H copy brings them all back
 	size_t o_hit = c.take(words * 4), o_unc = c.take(words * 4), o_steps = c.take(m * 4), o_toi = c.take(toi ? m * 8 : 0);
-	size_t out_lo = o_hit, out_hi = c.off;
+	const size_t out_lo = o_hit, out_hi = c.off;
 	size_t o_ovr = c.take(m * 4);
-	CU(ws->reserve(c.off, c.off - out_lo));
+	const size_t host_hi = c.off;
+	size_t o_q = c.take(qb);
+	CU(ws->reserve(c.off, host_hi - out_lo));
 	char *D = ws->dev, *H = ws->host - out_lo;  // host staging mirrors the device layout from out_lo onwards
-	unsigned long long *cursor = scene->cursor();
 	CU(cudaMemcpyAsync(D + o_a, a, in_b, cudaMemcpyHostToDevice, stream));
 	CU(cudaMemcpyAsync(D + o_b, b, in_b, cudaMemcpyHostToDevice, stream));
 	CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a), (const double *) (D + o_b), m, stride, js, max_step,
 							nullptr, (uint32_t *) (D + o_hit), toi ? (double *) (D + o_toi) : nullptr, (uint32_t *) (D + o_steps),
-							(uint32_t *) (D + o_unc), cursor, stream));
+							(uint32_t *) (D + o_unc), (unsigned *) (D + o_first), D + o_q, qb, stream));
 	CU(cudaMemcpyAsync(H + out_lo, D + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, stream));
 	CU(cudaStreamSynchronize(stream));
 	// Step-count fix-up: the device libm may differ from the host's by an ulp, which only matters when distance /
-	// max_step sits on an integer boundary.  Re-derive those on the host and re-run the ones that disagree.
+	// max_step sits on an integer boundary.  Re-derive those on the host and re-run if any count disagrees.
 	uint32_t *h_unc = (uint32_t *) (H + o_unc), *h_steps = (uint32_t *) (H + o_steps), *h_ovr = (uint32_t *) (H + o_ovr);
 	size_t n_fix = 0;
 	for (size_t w = 0; w < words; ++w) {
@@ -566,13 +596,12 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		}
 	}
 	if (n_fix) {
-		// Rare path: re-run the whole batch with the corrected counts pinned (kept simple; the boundary set is
-		// normally empty for sampled states).
+		// Rare path (the boundary set is normally empty for sampled states): re-run with the corrected counts pinned.
 		CU(cudaMemcpyAsync(D + o_ovr, h_ovr, m * 4, cudaMemcpyHostToDevice, stream));
 		CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a), (const double *) (D + o_b), m, stride, js,
 								max_step, (const uint32_t *) (D + o_ovr), (uint32_t *) (D + o_hit),
 								toi ? (double *) (D + o_toi) : nullptr, (uint32_t *) (D + o_steps), nullptr,
-								cursor, stream));
+								(unsigned *) (D + o_first), D + o_q, qb, stream));
 		CU(cudaMemcpyAsync(H + out_lo, D + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, stream));
 		CU(cudaStreamSynchronize(stream));
 	}
@@ -601,22 +630,32 @@ int mgodpl_check_path(mgodpl_scene *scene, const mgodpl_robot *robot, const doub
 }
 
 // ---- goal sampling -------------------------------------------------------------------------------------------------------------
+static int check_goal_args(mgodpl_scene *scene, const mgodpl_robot *robot, size_t f, size_t s) {
+	if (!scene || !robot) return fail(MGODPL_E_INVALID_ARGUMENT, "null handle");
+	if (robot->dev.ee < 0) return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: end_effector");
+	if (f && s && f * (((s + 31) / 32) * 32) >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^32-2 samples in one call");
+	return MGODPL_OK;
+}
+
 int mgodpl_sample_goals_device(mgodpl_scene *scene, const mgodpl_robot *robot, const double *d_targets, size_t f, const double *d_draws,
 							   size_t s, uint64_t seed, double dist, uint32_t *d_hit_bits, uint32_t *d_collisions, double *d_states_out,
 							   void *stream_) {
-	if (!scene || !robot) return fail(MGODPL_E_INVALID_ARGUMENT, "null handle");
-	if (robot->dev.ee < 0) return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: end_effector");
+	if (int rc = check_goal_args(scene, robot, f, s)) return rc;
 	if (f && s && (!d_targets || !d_hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
 	if (int rc = require_device()) return rc;
+	if (!f || !s) return MGODPL_OK;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	const size_t qb = query_scratch_bytes(f * s * (size_t) robot->dev.n_boxes);
+	char *scratch = nullptr;
+	CU(scene->device_scratch(stream, qb, &scratch));
 	CU(launch_sample_goals(scene->dev, robot->dev, d_targets, f, d_draws, robot->d_limits, s, seed, dist, d_hit_bits, d_collisions,
-						   d_states_out, (cudaStream_t) stream_));
+						   d_states_out, scratch, qb, stream));
 	return MGODPL_OK;
 }
 
 int mgodpl_sample_goals(mgodpl_scene *scene, const mgodpl_robot *robot, const double *targets, size_t f, const double *draws, size_t s,
 						uint64_t seed, double dist, uint32_t *hit_bits, uint32_t *collisions, double *states_out, void *stream_) {
-	if (!scene || !robot) return fail(MGODPL_E_INVALID_ARGUMENT, "null handle");
-	if (robot->dev.ee < 0) return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: end_effector");
+	if (int rc = check_goal_args(scene, robot, f, s)) return rc;
 	if (f && s && (!targets || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
 	if (int rc = require_device()) return rc;
 	if (!f || !s) return MGODPL_OK;
@@ -624,18 +663,18 @@ int mgodpl_sample_goals(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	const int nv = robot->dev.n_vars;
 	Lease ws(scene->pool);
 	Carver c;
-	size_t wpr = (s + 31) / 32;
+	const size_t wpr = (s + 31) / 32, qb = query_scratch_bytes(f * s * (size_t) robot->dev.n_boxes);
 	size_t o_t = c.take(f * 24), o_d = c.take(draws ? s * (1 + nv) * 8 : 0);
 	size_t o_hit = c.take(f * wpr * 4), o_cnt = c.take(f * 4);
-	size_t small_hi = c.off;
-	size_t o_st = c.take(states_out ? f * s * (7 + nv) * 8 : 0);
+	const size_t small_hi = c.off;
+	size_t o_st = c.take(states_out ? f * s * (7 + nv) * 8 : 0), o_q = c.take(qb);
 	CU(ws->reserve(c.off, small_hi - o_hit));
 	char *D = ws->dev, *H = ws->host - o_hit;  // host staging mirrors the device layout of the two result arrays
 	CU(cudaMemcpyAsync(D + o_t, targets, f * 24, cudaMemcpyHostToDevice, stream));
 	if (draws) CU(cudaMemcpyAsync(D + o_d, draws, s * (1 + nv) * 8, cudaMemcpyHostToDevice, stream));
 	CU(launch_sample_goals(scene->dev, robot->dev, (const double *) (D + o_t), f, draws ? (const double *) (D + o_d) : nullptr,
 						   robot->d_limits, s, seed, dist, (uint32_t *) (D + o_hit), (uint32_t *) (D + o_cnt),
-						   states_out ? (double *) (D + o_st) : nullptr, stream));
+						   states_out ? (double *) (D + o_st) : nullptr, D + o_q, qb, stream));
 	CU(cudaMemcpyAsync(H + o_hit, D + o_hit, small_hi - o_hit, cudaMemcpyDeviceToHost, stream));
 	if (states_out) CU(cudaMemcpyAsync(states_out, D + o_st, f * s * (7 + nv) * 8, cudaMemcpyDeviceToHost, stream));
 	CU(cudaStreamSynchronize(stream));

@@ -6,17 +6,24 @@
 
 namespace mgodpl_b200 {
 
+/// Upper bound on queued boxes per launch (64 B each); beyond it stage A traverses inline.
+constexpr size_t QUEUE_MAX_ITEMS = 8u << 20;
+/// Bytes of device scratch a query launch wants for `worst_case_boxes` candidate boxes (queue header + items).
+size_t query_scratch_bytes(size_t worst_case_boxes);
+
 cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const double *d_states, size_t n, size_t stride,
-								uint32_t *d_hit_bits, cudaStream_t stream);
-cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t n, uint32_t *d_hit_bits, cudaStream_t stream);
+								uint32_t *d_hit_bits, void *scratch, size_t scratch_bytes, cudaStream_t stream);
+cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t n, uint32_t *d_hit_bits, void *scratch,
+							   size_t scratch_bytes, cudaStream_t stream);
+/// d_n_steps and d_first_step (m x u32 each) are mandatory work buffers; d_toi / d_uncertain / d_override optional.
 cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const double *d_a, const double *d_b, size_t m,
 								 size_t stride, int js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,
-								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned long long *d_next_motion,
-								 cudaStream_t stream);
+								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned *d_first_step,
+								 void *scratch, size_t scratch_bytes, cudaStream_t stream);
 cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const double *d_targets, size_t f,
 								const double *d_draws, const double *d_limits, size_t s, unsigned long long seed,
 								double distance_from_target, uint32_t *d_hit_bits, uint32_t *d_collisions,
-								double *d_states_out, cudaStream_t stream);
+								double *d_states_out, void *scratch, size_t scratch_bytes, cudaStream_t stream);
 cudaError_t launch_forward_kinematics(const RobotDev &rb, const double *d_states, size_t n, size_t stride, double *d_out,
 									  cudaStream_t stream);
 

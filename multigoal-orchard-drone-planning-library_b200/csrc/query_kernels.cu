@@ -1,31 +1,51 @@
 // The collision-query kernels: batched forward kinematics, box-vs-BVH traversal, motion validation, goal sampling.
 //
-// Shape of every query kernel (DESIGN.md "Kernels"):
-//   phase A  one thread per candidate robot state: load/generate the state, cull the whole robot against the scene
-//            bounds with its reach sphere, run FK in fp64, cull each link box against the scene bounds, and push the
-//            survivors (fp64 box pose + owner) into a block-wide queue in shared memory;
-//   phase B  the block's threads drain the queue, one box per thread: stackless skip-link traversal of the flattened
-//            BVH with fp32 conservative node tests, exact fp64 box/triangle tests at the leaves, first hit wins;
-//   phase C  hits are OR-ed into a per-block bitmask and written out as packed words.
-// Far-away states (the majority in PRM-style sampling) never leave phase A; the boxes that do need a tree descent are
-// compacted so that phase B runs with full warps instead of a few live lanes per warp.
+// Every query runs as a two-stage pipeline on one stream (DESIGN.md "Kernels"):
+//
+//   stage A  "expand"   one thread per candidate robot state (an explicit state, one interpolation step of a motion,
+//                       or one goal sample).  Cull the whole robot against the scene bounds with its reach sphere
+//                       (translation only), then — for the few that survive — interpolate / run FK in fp64, cull each
+//                       link box against the scene bounds and append the survivors (fp64 box pose + owner) to a
+//                       work queue in HBM, one warp-aggregated atomic per warp.
+//   stage B  "traverse" one thread per queued box, full warps: stackless skip-link traversal of the flattened BVH,
+//                       fp32 conservative node tests, exact fp64 box/triangle tests at the leaves, first hit wins.
+//                       Hits are reported with atomicOr (state bitmasks) or atomicMin (first colliding motion step).
+//   stage C  "finish"   motions only: first colliding step -> hit bit + toi.
+//
+// Far-away states (the majority under PRM-style sampling) cost a 24-byte read and a handful of flops in stage A;
+// boxes that do need a tree descent are compacted, so stage B runs converged and at full occupancy.  If the queue
+// would overflow, stage A traverses the box on the spot — capacity is a performance knob, never a correctness one.
+#include <cooperative_groups.h>
+
 #include "geometry.cuh"
 #include "kernels.h"
 
+namespace cg = cooperative_groups;
+
 namespace mgodpl_b200 {
 
-constexpr int BLOCK = 256;
-constexpr int WARPS = BLOCK / 32;
-constexpr int ROUND_BOXES = 2;            // link boxes pushed per state per round
-constexpr int QCAP = BLOCK * ROUND_BOXES;
+constexpr int BLOCK_A = 256;
+constexpr int BLOCK_B = 128;
+constexpr unsigned NO_HIT = 0xFFFFFFFFu;
+constexpr int ROW_MAX = 7 + MGODPL_MAX_JOINT_VALUES;
 
-struct Queue {
-	double c[3][QCAP];
-	double q[4][QCAP];
-	uint16_t owner[QCAP];
-	uint8_t box[QCAP];
-	unsigned count;
-	unsigned hitmask[WARPS];
+// ---------------------------------------------------------------------------------------------------------------
+// Work queue: 64-byte items = fp64 box pose (centre, quaternion) + owner + (step | box << 28).
+// ---------------------------------------------------------------------------------------------------------------
+struct __align__(16) Item {
+	double c[3];
+	double q[4];
+	unsigned owner;
+	unsigned step_box;
+};
+static_assert(sizeof(Item) == 64, "queue item must be 64 bytes");
+
+enum ResultMode : int { RESULT_BITS = 0, RESULT_FIRST_STEP = 1 };
+
+struct Results {
+	int mode;
+	uint32_t *hit_bits;      // RESULT_BITS: bit `owner`
+	unsigned *first_step;    // RESULT_FIRST_STEP: min colliding step of motion `owner`
 };
 
 struct LocalCounters {
@@ -43,10 +63,73 @@ __device__ __forceinline__ void flush_counters(const SceneDev &sc, const LocalCo
 	}
 }
 
-__device__ __forceinline__ bool finite7(const double *p) {
-	double s = p[0] + p[1] + p[2] + p[3] + p[4] + p[5] + p[6];
-	return isfinite(s);
+__device__ __forceinline__ bool already_decided(const Results &res, unsigned owner, unsigned step) {
+	if (res.mode == RESULT_BITS) return (__ldcg(res.hit_bits + (owner >> 5)) >> (owner & 31)) & 1u;
+	return __ldcg(res.first_step + owner) <= step;  // an earlier (or this) step already collides
 }
+__device__ __forceinline__ void report_hit(const Results &res, unsigned owner, unsigned step) {
+	if (res.mode == RESULT_BITS) atomicOr(res.hit_bits + (owner >> 5), 1u << (owner & 31));
+	else atomicMin(res.first_step + owner, step);
+}
+
+/// The traversal proper: does the box (c, q, half) touch any triangle of the scene?
+__device__ __forceinline__ bool box_hits_scene(const SceneDev &sc, D3 c, Q4 q, const double *half, LocalCounters &lc) {
+	const CullBox cb = make_cull_box(sc, c, q, half);
+	ExactBox eb;
+	eb.cx = c.x, eb.cy = c.y, eb.cz = c.z;
+	qmat(q, eb.r);
+	eb.hx = half[0], eb.hy = half[1], eb.hz = half[2];
+	const unsigned n_nodes = sc.n_nodes;
+	unsigned node = 0;
+	lc.boxes++;
+	while (node < n_nodes) {
+		const float4 a = __ldg(sc.nodes + 2 * node);
+		const float4 b = __ldg(sc.nodes + 2 * node + 1);
+		const bool ov = cull_overlap(cb, a.x, a.y, a.z, b.x, b.y, b.z);
+		const int leaf = __float_as_int(b.w);
+		lc.nodes++;
+		if (ov && leaf >= 0) {
+			const unsigned first = (unsigned) leaf >> 4, cnt = ((unsigned) leaf & 15u) + 1u;
+			for (unsigned k = 0; k < cnt; ++k) {
+				lc.leaf++;
+				if (box_triangle_hit(eb, sc.tris + 9ull * (first + k))) return true;
+			}
+		}
+		node = (ov && leaf < 0) ? node + 1 : __float_as_uint(a.w);
+	}
+	return false;
+}
+
+struct QueueDev {
+	Item *items;
+	unsigned *count;  // items appended so far (may exceed cap: the excess was traversed inline)
+	unsigned cap;
+};
+
+/// Stage A tail: cull one box against the scene bounds and hand it to stage B (or traverse it here on overflow).
+__device__ __forceinline__ void emit_box(const SceneDev &sc, const QueueDev &Q, const Results &res, D3 c, Q4 q,
+										 const double *half, unsigned owner, unsigned step, unsigned box, LocalCounters &lc) {
+	const CullBox cb = make_cull_box(sc, c, q, half);
+	if (!cull_overlap(cb, sc.root_c[0], sc.root_c[1], sc.root_c[2], sc.root_h[0], sc.root_h[1], sc.root_h[2])) return;
+	cg::coalesced_group g = cg::coalesced_threads();
+	unsigned base = 0;
+	if (g.thread_rank() == 0) base = atomicAdd(Q.count, g.size());
+	const unsigned pos = g.shfl(base, 0) + g.thread_rank();
+	if (pos < Q.cap) {
+		Item it;
+		it.c[0] = c.x, it.c[1] = c.y, it.c[2] = c.z;
+		it.q[0] = q.x, it.q[1] = q.y, it.q[2] = q.z, it.q[3] = q.w;
+		it.owner = owner, it.step_box = step | box << 28;
+		uint4 *dst = reinterpret_cast<uint4 *>(Q.items + pos);
+		const uint4 *src = reinterpret_cast<const uint4 *>(&it);
+#pragma unroll
+		for (int k = 0; k < 4; ++k) __stcg(dst + k, src[k]);
+	} else if (!already_decided(res, owner, step)) {
+		if (box_hits_scene(sc, c, q, half, lc)) report_hit(res, owner, step);
+	}
+}
+
+__device__ __forceinline__ bool finite7(const double *p) { return isfinite(p[0] + p[1] + p[2] + p[3] + p[4] + p[5] + p[6]); }
 
 /// Whole-robot cull: does the sphere (base origin, rb.reach) miss the scene bounds?
 __device__ __forceinline__ bool robot_out_of_reach(const SceneDev &sc, const RobotDev &rb, D3 t) {
@@ -54,88 +137,63 @@ __device__ __forceinline__ bool robot_out_of_reach(const SceneDev &sc, const Rob
 	double dy = fmax(fabs(t.y - (sc.origin[1] + (double) sc.root_c[1])) - (double) sc.root_h[1], 0.0);
 	double dz = fmax(fabs(t.z - (sc.origin[2] + (double) sc.root_c[2])) - (double) sc.root_h[2], 0.0);
 	double r = rb.reach + (double) sc.margin;
-	return dx * dx + dy * dy + dz * dz > r * r;
+	return !(dx * dx + dy * dy + dz * dz <= r * r);  // NaN counts as out of reach
 }
 
-__device__ __forceinline__ void push_item(Queue &Q, const SceneDev &sc, D3 c, Q4 q, const double *half, unsigned owner,
-										  unsigned box) {
-	CullBox cb = make_cull_box(sc, c, q, half);
-	if (!cull_overlap(cb, sc.root_c[0], sc.root_c[1], sc.root_c[2], sc.root_h[0], sc.root_h[1], sc.root_h[2])) return;
-	unsigned pos = atomicAdd(&Q.count, 1u);
-	Q.c[0][pos] = c.x, Q.c[1][pos] = c.y, Q.c[2][pos] = c.z;
-	Q.q[0][pos] = q.x, Q.q[1][pos] = q.y, Q.q[2][pos] = q.z, Q.q[3][pos] = q.w;
-	Q.owner[pos] = (uint16_t) owner;
-	Q.box[pos] = (uint8_t) box;
-}
-
-/// FK for the links that carry collision geometry (check_robot_collision, collision_detection.cpp:57-80).
-__device__ __forceinline__ void fk_collision_links(const RobotDev &rb, const Pose &base, const double *joints, Pose *link_tf) {
+/// FK for the links that carry collision geometry + one emit per box (check_robot_collision,
+/// collision_detection.cpp:57-80; check_link_collision :16-55).
+__device__ __forceinline__ void expand_state(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
+											 const Pose &base, const double *joints, unsigned owner, unsigned step,
+											 LocalCounters &lc) {
+	Pose link_tf[MGODPL_MAX_LINKS];
 	link_tf[rb.root] = base;
 	for (int i = 0; i < rb.n_ops; ++i) {
 		const FkOp &op = rb.ops[i];
 		if (op.flags & FK_FOR_COLLISION) link_tf[op.child] = fk_apply(op, link_tf[op.parent], joints);
 	}
-}
-
-/// Phase B: drain the block queue.  `half_of(item)` yields the fp64 half extents of a queued box.
-template<class HalfFn>
-__device__ __forceinline__ void traverse_queue(Queue &Q, const SceneDev &sc, LocalCounters &lc, HalfFn half_of) {
-	const unsigned n = Q.count;
-	for (unsigned i = threadIdx.x; i < n; i += BLOCK) {
-		const unsigned owner = Q.owner[i];
-		if ((((volatile unsigned *) Q.hitmask)[owner >> 5] >> (owner & 31)) & 1u) continue;  // another box already hit
-		D3 c{Q.c[0][i], Q.c[1][i], Q.c[2][i]};
-		Q4 q{Q.q[0][i], Q.q[1][i], Q.q[2][i], Q.q[3][i]};
-		const double *half = half_of(i, owner);
-		const CullBox cb = make_cull_box(sc, c, q, half);
-		ExactBox eb;
-		eb.cx = c.x, eb.cy = c.y, eb.cz = c.z;
-		qmat(q, eb.r);
-		eb.hx = half[0], eb.hy = half[1], eb.hz = half[2];
-		bool hit = false;
-		unsigned node = 0;
-		const unsigned n_nodes = sc.n_nodes;
-		lc.boxes++;
-		while (node < n_nodes) {
-			const float4 a = __ldg(sc.nodes + 2 * node);
-			const float4 b = __ldg(sc.nodes + 2 * node + 1);
-			const bool ov = cull_overlap(cb, a.x, a.y, a.z, b.x, b.y, b.z);
-			const int leaf = __float_as_int(b.w);
-			lc.nodes++;
-			if (ov && leaf >= 0) {
-				const unsigned first = (unsigned) leaf >> 4, cnt = ((unsigned) leaf & 15u) + 1u;
-				for (unsigned k = 0; k < cnt && !hit; ++k) {
-					lc.leaf++;
-					hit = box_triangle_hit(eb, sc.tris + 9ull * (first + k));
-				}
-				if (hit) break;
-			}
-			node = (ov && leaf < 0) ? node + 1 : __float_as_uint(a.w);
-		}
-		if (hit) atomicOr(&Q.hitmask[owner >> 5], 1u << (owner & 31));
+	for (int bi = 0; bi < rb.n_boxes; ++bi) {
+		const BoxDev &bx = rb.boxes[bi];
+		const Pose &l = link_tf[bx.link];
+		Pose w = bx.tf_identity ? l : then(l, D3{bx.t[0], bx.t[1], bx.t[2]}, Q4{bx.q[0], bx.q[1], bx.q[2], bx.q[3]}, false);
+		emit_box(sc, Q, res, w.t, w.q, bx.half, owner, step, (unsigned) bi, lc);
 	}
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// State sources for the tiled state kernel.  A tile is BLOCK consecutive samples of one row; tile -> (row, s0).
+// Stage A kernels
 // ---------------------------------------------------------------------------------------------------------------
-/// Explicit states (check_robot_collision over N states): rows = 1.
-struct ExplicitStates {
-	const double *states;
-	size_t stride;
-	__device__ __forceinline__ void stage(double *smem, size_t row, size_t s0, unsigned cnt) const {
-		const double *src = states + s0 * stride;
-		for (unsigned i = threadIdx.x; i < cnt * stride; i += BLOCK) smem[i] = __ldg(src + i);
+/// Explicit states: check_robot_collision over N states.
+__global__ void __launch_bounds__(BLOCK_A)
+k_expand_states(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ states,
+				size_t n, size_t stride, QueueDev Q, Results res) {
+	LocalCounters lc;
+	for (size_t i = (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < n; i += (size_t) gridDim.x * BLOCK_A) {
+		const double *r = states + i * stride;
+		lc.states++;
+		const D3 t{__ldg(r), __ldg(r + 1), __ldg(r + 2)};
+		if (robot_out_of_reach(sc, rb, t)) continue;
+		double row[ROW_MAX];
+		for (int k = 0; k < 4 + rb.n_vars; ++k) row[k] = __ldg(r + 3 + k);
+		if (!isfinite(row[0] + row[1] + row[2] + row[3])) continue;
+		expand_state(sc, rb, Q, res, Pose{t, Q4{row[0], row[1], row[2], row[3]}}, row + 4, (unsigned) i, 0u, lc);
 	}
-	__device__ __forceinline__ bool get(const double *smem, const RobotDev &, size_t, size_t, unsigned tid, Pose &base,
-										const double *&joints, double *) const {
-		const double *r = smem + tid * stride;
-		base.t = {r[0], r[1], r[2]};
-		base.q = {r[3], r[4], r[5], r[6]};
-		joints = r + 7;
-		return finite7(r);
+	flush_counters(sc, lc);
+}
+
+/// Explicit world-frame boxes: check_link_collision (collision_detection.cpp:16-55), n x (tf7, size3).
+__global__ void __launch_bounds__(BLOCK_A)
+k_expand_boxes(const __grid_constant__ SceneDev sc, const double *__restrict__ boxes, size_t n, QueueDev Q, Results res) {
+	LocalCounters lc;
+	for (size_t i = (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < n; i += (size_t) gridDim.x * BLOCK_A) {
+		double v[10];
+#pragma unroll
+		for (int k = 0; k < 10; ++k) v[k] = __ldg(boxes + i * 10 + k);
+		if (!finite7(v)) continue;
+		const double half[3] = {v[7] * 0.5, v[8] * 0.5, v[9] * 0.5};
+		emit_box(sc, Q, res, D3{v[0], v[1], v[2]}, Q4{v[3], v[4], v[5], v[6]}, half, (unsigned) i, 0u, 0u, lc);
 	}
-};
+	flush_counters(sc, lc);
+}
 
 __device__ __forceinline__ double u01_from_bits(unsigned long long x) { return (double) (x >> 11) * 0x1.0p-53; }
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // splitmix64 finaliser
@@ -145,172 +203,66 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // 
 	return z ^ (z >> 31);
 }
 
-/// genGoalStateUniform (goal_sampling.cpp:51-79): upright state from draws (yaw, joint values), FK to the end
-/// effector, base shifted so the end effector lands on the row's target.  rows = targets, per_row = samples.
-struct GoalStates {
-	const double *targets;   // rows x 3
-	const double *draws;     // per_row x (1 + n_vars), or nullptr -> counter-based generator
-	const double *limits;    // n_vars x (min, max), device copy, used only by the generator
-	unsigned long long seed;
-	double distance_from_target;
-	double *states_out;      // optional rows x per_row x (7 + n_vars)
-	size_t per_row;
-	__device__ __forceinline__ void stage(double *, size_t, size_t, unsigned) const {}
-	__device__ __forceinline__ bool get(const double *, const RobotDev &rb, size_t row, size_t s, unsigned, Pose &base,
-										const double *&joints, double *jv) const {
-		const int nv = rb.n_vars;
-		double yaw;
+/// Goal samples: genGoalStateUniform (goal_sampling.cpp:51-79) for `rows` targets x `per_row` samples.  The upright
+/// state comes from caller-supplied draws (yaw, joint values — goal_sampling.cpp:13-49) or from a counter-based
+/// generator; FK to the end effector; base shifted so the end effector lands on the target; then the collision filter.
+/// Result bit index = row * (32 * words_per_row) + sample.
+__global__ void __launch_bounds__(BLOCK_A)
+k_expand_goals(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ targets,
+			   size_t rows, size_t per_row, const double *__restrict__ draws, const double *__restrict__ limits,
+			   unsigned long long seed, double distance_from_target, double *__restrict__ states_out, QueueDev Q, Results res) {
+	LocalCounters lc;
+	const int nv = rb.n_vars;
+	const size_t total = rows * per_row, bits_per_row = ((per_row + 31) / 32) * 32;
+	for (size_t i = (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < total; i += (size_t) gridDim.x * BLOCK_A) {
+		const size_t row = i / per_row, s = i - row * per_row;
+		double jv[MGODPL_MAX_JOINT_VALUES], yaw;
 		if (draws) {
 			const double *d = draws + s * (size_t) (1 + nv);
 			yaw = __ldg(d);
 			for (int k = 0; k < nv; ++k) jv[k] = __ldg(d + 1 + k);
 		} else {
-			unsigned long long ctr = (row * per_row + s) * (unsigned long long) (1 + nv);
+			unsigned long long ctr = i * (unsigned long long) (1 + nv);
 			yaw = -M_PI + 2.0 * M_PI * u01_from_bits(mix64(seed ^ mix64(ctr)));
-			for (int k = 0; k < nv; ++k) {
-				double lo = limits[2 * k], hi = limits[2 * k + 1];
-				jv[k] = lo + (hi - lo) * u01_from_bits(mix64(seed ^ mix64(ctr + 1 + k)));
-			}
+			for (int k = 0; k < nv; ++k)
+				jv[k] = limits[2 * k] + (limits[2 * k + 1] - limits[2 * k]) * u01_from_bits(mix64(seed ^ mix64(ctr + 1 + k)));
 		}
-		// genUprightState (goal_sampling.cpp:13-49): base at the origin, rotation about z.
+		// genUprightState: base at the origin, rotation about z by yaw (Quaternion.h:53-62 with axis UnitZ)
 		double sy, cy;
 		sincos(yaw / 2.0, &sy, &cy);
 		Pose tf[MGODPL_MAX_LINKS];
 		tf[rb.root] = Pose{{0, 0, 0}, {0 * sy, 0 * sy, 1 * sy, cy}};
-		for (int i = 0; i < rb.n_ops; ++i) tf[rb.ops[i].child] = fk_apply(rb.ops[i], tf[rb.ops[i].parent], jv);
+		for (int k = 0; k < rb.n_ops; ++k) tf[rb.ops[k].child] = fk_apply(rb.ops[k], tf[rb.ops[k].parent], jv);
 		const Pose ee = tf[rb.ee];
-		D3 tgt{__ldg(targets + 3 * row), __ldg(targets + 3 * row + 1), __ldg(targets + 3 * row + 2)};
-		D3 delta = tgt - ee.t;
+		D3 delta = D3{__ldg(targets + 3 * row), __ldg(targets + 3 * row + 1), __ldg(targets + 3 * row + 2)} - ee.t;
 		if (distance_from_target > 0.0) delta = delta + qrot(ee.q, D3{0.0, -distance_from_target, 0.0});
-		base.q = tf[rb.root].q;
-		base.t = D3{0, 0, 0} + delta;
-		joints = jv;
+		const Pose base{D3{0, 0, 0} + delta, tf[rb.root].q};
 		if (states_out) {
-			double *o = states_out + (row * per_row + s) * (size_t) (7 + nv);
+			double *o = states_out + i * (size_t) (7 + nv);
 			o[0] = base.t.x, o[1] = base.t.y, o[2] = base.t.z;
 			o[3] = base.q.x, o[4] = base.q.y, o[5] = base.q.z, o[6] = base.q.w;
 			for (int k = 0; k < nv; ++k) o[7 + k] = jv[k];
 		}
-		return isfinite(base.t.x + base.t.y + base.t.z);
-	}
-};
-
-template<class Source>
-__global__ void __launch_bounds__(BLOCK)
-k_check_states(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const Source src, size_t rows,
-			   size_t per_row, uint32_t *__restrict__ hit_bits) {
-	__shared__ Queue Q;
-	extern __shared__ double s_rows[];
-	const unsigned tid = threadIdx.x;
-	const size_t tiles_per_row = (per_row + BLOCK - 1) / BLOCK;
-	const size_t words_per_row = (per_row + 31) / 32;
-	const size_t n_tiles = rows * tiles_per_row;
-	LocalCounters lc;
-	for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-		const size_t row = tile / tiles_per_row, s0 = (tile - row * tiles_per_row) * BLOCK;
-		const unsigned cnt = (unsigned) min((size_t) BLOCK, per_row - s0);
-		if (tid < WARPS) Q.hitmask[tid] = 0;
-		src.stage(s_rows, row, s0, cnt);
-		__syncthreads();
-		Pose link_tf[MGODPL_MAX_LINKS];
-		double jv[MGODPL_MAX_JOINT_VALUES];
-		const double *joints = nullptr;
-		bool active = false;
-		if (tid < cnt) {
-			Pose base;
-			active = src.get(s_rows, rb, row, s0 + tid, tid, base, joints, jv);
-			lc.states++;
-			active = active && !robot_out_of_reach(sc, rb, base.t);
-			if (active) fk_collision_links(rb, base, joints, link_tf);
-		}
-		for (int g = 0; g < rb.n_boxes; g += ROUND_BOXES) {
-			if (tid == 0) Q.count = 0;
-			__syncthreads();
-			if (active) {
-				const int e = min(g + ROUND_BOXES, rb.n_boxes);
-				for (int bi = g; bi < e; ++bi) {
-					const BoxDev &bx = rb.boxes[bi];
-					const Pose &l = link_tf[bx.link];
-					Pose w = bx.tf_identity ? l : then(l, D3{bx.t[0], bx.t[1], bx.t[2]}, Q4{bx.q[0], bx.q[1], bx.q[2], bx.q[3]}, false);
-					push_item(Q, sc, w.t, w.q, bx.half, tid, bi);
-				}
-			}
-			__syncthreads();
-			traverse_queue(Q, sc, lc, [&](unsigned i, unsigned) { return rb.boxes[Q.box[i]].half; });
-			__syncthreads();
-		}
-		if (tid < WARPS && s0 + 32u * tid < per_row) hit_bits[row * words_per_row + s0 / 32 + tid] = Q.hitmask[tid];
-		__syncthreads();
+		lc.states++;
+		if (robot_out_of_reach(sc, rb, base.t)) continue;
+		expand_state(sc, rb, Q, res, base, jv, (unsigned) (row * bits_per_row + s), 0u, lc);
 	}
 	flush_counters(sc, lc);
 }
 
-/// check_link_collision for explicit world-frame boxes (collision_detection.cpp:16-55): n x (tf7, size3).
-__global__ void __launch_bounds__(BLOCK)
-k_check_boxes(const __grid_constant__ SceneDev sc, const double *__restrict__ boxes, size_t n, uint32_t *__restrict__ hit_bits) {
-	__shared__ Queue Q;
-	__shared__ double s_half[BLOCK][3];
-	const unsigned tid = threadIdx.x;
-	const size_t n_tiles = (n + BLOCK - 1) / BLOCK;
-	LocalCounters lc;
-	for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-		if (tid < WARPS) Q.hitmask[tid] = 0;
-		if (tid == 0) Q.count = 0;
-		__syncthreads();
-		const size_t idx = tile * BLOCK + tid;
-		if (idx < n) {
-			const double *r = boxes + idx * 10;
-			double v[10];
-#pragma unroll
-			for (int k = 0; k < 10; ++k) v[k] = __ldg(r + k);
-			s_half[tid][0] = v[7] * 0.5, s_half[tid][1] = v[8] * 0.5, s_half[tid][2] = v[9] * 0.5;
-			if (finite7(v)) push_item(Q, sc, D3{v[0], v[1], v[2]}, Q4{v[3], v[4], v[5], v[6]}, s_half[tid], tid, 0);
-		}
-		__syncthreads();
-		traverse_queue(Q, sc, lc, [&](unsigned, unsigned owner) { return (const double *) s_half[owner]; });
-		__syncthreads();
-		if (tid < WARPS && tile * BLOCK + 32u * tid < n) hit_bits[tile * WARPS + tid] = Q.hitmask[tid];
-		__syncthreads();
-	}
-	flush_counters(sc, lc);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Motion validation: check_motion_collides (collision_detection.cpp:82-105).  One warp per motion, lanes = 32
-// consecutive interpolation steps; the block's 8 warps share the traversal queue; a motion stops at the first chunk
-// that contains a hit and reports the lowest colliding step as toi.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int ROW_MAX = 7 + MGODPL_MAX_JOINT_VALUES;
-
-struct MotionSetup {
-	unsigned n_steps;
-	bool linear;     // slerp falls back to linear weights
-	bool negate;     // quaternion dot < 0: second weight negated
-	double theta, sin_theta;
-};
-
-__global__ void __launch_bounds__(BLOCK)
-k_check_motions(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
-				const double *__restrict__ b, size_t m, size_t stride, int js, double max_step,
-				const uint32_t *__restrict__ n_steps_override, uint32_t *__restrict__ hit_bits, double *__restrict__ toi,
-				uint32_t *__restrict__ n_steps_out, uint32_t *__restrict__ uncertain_bits,
-				unsigned long long *__restrict__ next_motion) {
-	__shared__ Queue Q;
+/// Motions: check_motion_collides (collision_detection.cpp:82-105).  One warp per motion; lanes take 32 consecutive
+/// interpolation steps at a time.  Every step 0..n_steps is expanded; the first colliding one is found in stage B/C.
+__global__ void __launch_bounds__(BLOCK_A)
+k_expand_motions(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
+				 const double *__restrict__ b, size_t m, size_t stride, int js, double max_step,
+				 const uint32_t *__restrict__ n_steps_override, uint32_t *__restrict__ n_steps_out,
+				 uint32_t *__restrict__ uncertain_bits, QueueDev Q, Results res) {
+	constexpr int WARPS = BLOCK_A / 32;
 	__shared__ double s_a[WARPS][ROW_MAX], s_b[WARPS][ROW_MAX];
-	const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	LocalCounters lc;
-	unsigned long long motion = ~0ull;
-	unsigned chunk = 0;
-	MotionSetup ms{};
-	unsigned long long n_motions_done = 0, n_uncertain = 0;
-
-	auto fetch = [&]() {
-		unsigned long long mi = 0;
-		if (lane == 0) mi = atomicAdd(next_motion, 1ull);
-		mi = __shfl_sync(0xffffffffu, mi, 0);
-		motion = mi < m ? mi : ~0ull;
-		chunk = 0;
-		if (motion == ~0ull) return;
+	unsigned long long n_uncertain = 0, n_motions = 0;
+	for (size_t motion = (size_t) blockIdx.x * WARPS + warp; motion < m; motion += (size_t) gridDim.x * WARPS) {
 		__syncwarp();
 		if (lane < stride) {
 			s_a[warp][lane] = __ldg(a + motion * stride + lane);
@@ -318,123 +270,114 @@ k_check_motions(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 		}
 		__syncwarp();
 		const double *A = s_a[warp], *B = s_b[warp];
-		// equal_weights_distance (distance.cpp:17-25) in the reference's operand order
+		// equal_weights_distance (distance.cpp:17-25, Quaternion.h:78-85) in the reference's operand order
 		double dx = A[0] - B[0], dy = A[1] - B[1], dz = A[2] - B[2];
 		double d = sqrt(dx * dx + dy * dy + dz * dz);
 		double c = A[6] * B[6] + A[3] * B[3] + A[4] * B[4] + A[5] * B[5];
 		double cc = fmin(fmax(c, -1.0), 1.0);
 		d += acos(2.0 * cc * cc - 1.0);
 		for (int i = 0; i < js; ++i) d += fabs(A[7 + i] - B[7 + i]);
-		double x = d / max_step;
-		double n = ceil(x);
+		const double x = d / max_step;
+		double nd = ceil(x);
 		bool uncertain = fabs(x - rint(x)) < 1e-9 * fmax(1.0, x);
-		if (!(n >= 0.0 && n < 4.0e9)) n = 0.0;  // non-finite or absurd distances: single check of the start state
-		ms.n_steps = (unsigned) n;
+		if (!(nd >= 0.0 && nd < 268435455.0)) nd = 0.0;  // non-finite / absurd distances: one check of the start state
+		unsigned n_steps = (unsigned) nd;
 		if (n_steps_override) {
-			unsigned o = __ldg(n_steps_override + motion);
-			if (o != 0xFFFFFFFFu) {
-				ms.n_steps = o;
-				uncertain = false;
-			}
+			const unsigned o = __ldg(n_steps_override + motion);
+			if (o != NO_HIT) n_steps = o, uncertain = false;
 		}
-		// Eigen slerp rule (Quaternion.cpp:12-20): dot over (x,y,z,w)
-		double dq = A[3] * B[3] + A[4] * B[4] + A[5] * B[5] + A[6] * B[6];
-		double ad = fabs(dq);
-		ms.negate = dq < 0.0;
-		ms.linear = ad >= 1.0 - 2.220446049250313e-16;
-		ms.theta = ms.linear ? 0.0 : acos(ad);
-		ms.sin_theta = ms.linear ? 1.0 : sin(ms.theta);
 		if (lane == 0) {
-			if (n_steps_out) n_steps_out[motion] = ms.n_steps;
-			if (uncertain) {
-				if (uncertain_bits) atomicOr(uncertain_bits + (motion >> 5), 1u << (motion & 31));
-				n_uncertain++;
-			}
+			if (n_steps_out) n_steps_out[motion] = n_steps;
+			if (uncertain && uncertain_bits) atomicOr(uncertain_bits + (motion >> 5), 1u << (motion & 31));
+			n_uncertain += uncertain;
+			n_motions++;
 		}
-	};
-
-	fetch();
-	while (true) {
-		if (tid < WARPS) Q.hitmask[tid] = 0;
-		if (!__syncthreads_or(motion != ~0ull)) break;
-		// ---- phase A: interpolate + FK for this lane's step --------------------------------------------------
-		Pose link_tf[MGODPL_MAX_LINKS];
-		double jv[MGODPL_MAX_JOINT_VALUES];
-		bool active = false;
-		const unsigned long long step = (unsigned long long) chunk * 32ull + lane;
-		double t = 0.0;
-		if (motion != ~0ull && step <= ms.n_steps) {
-			const double *A = s_a[warp], *B = s_b[warp];
-			Pose base;
-			if (ms.n_steps == 0) {  // the reference evaluates 0/0 here; we check the start state once
-				base.t = {A[0], A[1], A[2]};
-				base.q = {A[3], A[4], A[5], A[6]};
-				for (int k = 0; k < rb.n_vars; ++k) jv[k] = A[7 + k];
-			} else {
-				t = (double) step / (double) ms.n_steps;
-				// Transform.h:69-78 (translation) and RobotState.cpp:19-21 (joints): two distinct lerp forms
-				base.t = {(1.0 - t) * A[0] + t * B[0], (1.0 - t) * A[1] + t * B[1], (1.0 - t) * A[2] + t * B[2]};
-				double w0, w1;
-				if (ms.linear) {
-					w0 = 1.0 - t, w1 = t;
-				} else {
-					w0 = sin((1.0 - t) * ms.theta) / ms.sin_theta;
-					w1 = sin(t * ms.theta) / ms.sin_theta;
-				}
-				if (ms.negate) w1 = -w1;
-				base.q = {w0 * A[3] + w1 * B[3], w0 * A[4] + w1 * B[4], w0 * A[5] + w1 * B[5], w0 * A[6] + w1 * B[6]};
-				for (int k = 0; k < rb.n_vars; ++k) jv[k] = A[7 + k] * (1 - t) + B[7 + k] * t;
-			}
+		// Eigen slerp rule (Quaternion.cpp:12-20): shortest arc, linear weights when |dot| >= 1 - eps
+		const double dq = A[3] * B[3] + A[4] * B[4] + A[5] * B[5] + A[6] * B[6];
+		const double ad = fabs(dq);
+		const bool linear = ad >= 1.0 - 2.220446049250313e-16;
+		const double theta = linear ? 0.0 : acos(ad);
+		const double inv_sin = linear ? 1.0 : 1.0 / sin(theta);
+		for (unsigned long long s0 = 0; s0 <= n_steps; s0 += 32) {
+			const unsigned long long step = s0 + lane;
+			if (step > n_steps) continue;
 			lc.states++;
-			active = isfinite(base.t.x + base.t.y + base.t.z + base.q.x + base.q.y + base.q.z + base.q.w) &&
-					 !robot_out_of_reach(sc, rb, base.t);
-			if (active) fk_collision_links(rb, base, jv, link_tf);
-		}
-		// ---- phase A2/B: per box group, push survivors and drain the shared queue ------------------------------
-		for (int g = 0; g < rb.n_boxes; g += ROUND_BOXES) {
-			if (tid == 0) Q.count = 0;
-			__syncthreads();
-			if (active) {
-				const int e = min(g + ROUND_BOXES, rb.n_boxes);
-				for (int bi = g; bi < e; ++bi) {
-					const BoxDev &bx = rb.boxes[bi];
-					const Pose &l = link_tf[bx.link];
-					Pose w = bx.tf_identity ? l : then(l, D3{bx.t[0], bx.t[1], bx.t[2]}, Q4{bx.q[0], bx.q[1], bx.q[2], bx.q[3]}, false);
-					push_item(Q, sc, w.t, w.q, bx.half, tid, bi);
-				}
-			}
-			__syncthreads();
-			traverse_queue(Q, sc, lc, [&](unsigned i, unsigned) { return rb.boxes[Q.box[i]].half; });
-			__syncthreads();
-		}
-		// ---- phase C: first colliding step of this chunk, early exit ---------------------------------------------
-		if (motion != ~0ull) {
-			const unsigned mask = Q.hitmask[warp];
-			bool done = false;
-			if (mask) {
-				const unsigned first = __ffs(mask) - 1;
-				if (lane == first) {
-					atomicOr(hit_bits + (motion >> 5), 1u << (motion & 31));
-					if (toi) toi[motion] = t;
-				}
-				done = true;
-			} else if ((unsigned long long) chunk * 32ull + 31ull >= ms.n_steps) {
-				if (lane == 0 && toi) toi[motion] = __longlong_as_double(0x7ff8000000000000ll);
-				done = true;
+			// for n_steps == 0 the reference evaluates t = 0/0; here the start state is checked once.
+			const double t = n_steps ? (double) step / (double) n_steps : 0.0;
+			// Transform.h:69-78 — translation lerp (1-t) a + t b
+			const D3 tr{(1.0 - t) * A[0] + t * B[0], (1.0 - t) * A[1] + t * B[1], (1.0 - t) * A[2] + t * B[2]};
+			if (robot_out_of_reach(sc, rb, tr)) continue;
+			double w0, w1;
+			if (linear) {
+				w0 = 1.0 - t, w1 = t;
 			} else {
-				chunk++;
+				w0 = sin((1.0 - t) * theta) * inv_sin;
+				w1 = sin(t * theta) * inv_sin;
 			}
-			if (done) {
-				n_motions_done += lane == 0;
-				fetch();
-			}
+			if (dq < 0.0) w1 = -w1;
+			Pose base{tr, Q4{w0 * A[3] + w1 * B[3], w0 * A[4] + w1 * B[4], w0 * A[5] + w1 * B[5], w0 * A[6] + w1 * B[6]}};
+			if (n_steps == 0) base.q = Q4{A[3], A[4], A[5], A[6]};
+			if (!isfinite(base.q.x + base.q.y + base.q.z + base.q.w)) continue;
+			double jv[MGODPL_MAX_JOINT_VALUES];
+			// RobotState.cpp:19-21 — joints lerp as a (1-t) + b t
+			for (int k = 0; k < rb.n_vars; ++k) jv[k] = n_steps ? A[7 + k] * (1 - t) + B[7 + k] * t : A[7 + k];
+			expand_state(sc, rb, Q, res, base, jv, (unsigned) motion, (unsigned) step, lc);
 		}
-		__syncthreads();  // hitmask is reset at the top of the loop
 	}
 	flush_counters(sc, lc);
 	if (sc.counters && lane == 0) {
-		if (n_motions_done) atomicAdd(sc.counters + CNT_MOTIONS, n_motions_done);
+		if (n_motions) atomicAdd(sc.counters + CNT_MOTIONS, n_motions);
 		if (n_uncertain) atomicAdd(sc.counters + CNT_UNCERTAIN, n_uncertain);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stage B: drain the queue, one box per thread.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK_B)
+k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ explicit_boxes,
+		   QueueDev Q, Results res) {
+	LocalCounters lc;
+	const unsigned n = min(__ldcg(Q.count), Q.cap);
+	for (unsigned i = blockIdx.x * BLOCK_B + threadIdx.x; i < n; i += gridDim.x * BLOCK_B) {
+		Item it;
+		const uint4 *src = reinterpret_cast<const uint4 *>(Q.items + i);
+		uint4 *dst = reinterpret_cast<uint4 *>(&it);
+#pragma unroll
+		for (int k = 0; k < 4; ++k) dst[k] = __ldcg(src + k);
+		const unsigned step = it.step_box & 0x0FFFFFFFu, box = it.step_box >> 28;
+		if (already_decided(res, it.owner, step)) continue;
+		double half_buf[3];
+		const double *half;
+		if (explicit_boxes) {
+			const double *bx = explicit_boxes + (size_t) it.owner * 10;
+			half_buf[0] = __ldg(bx + 7) * 0.5, half_buf[1] = __ldg(bx + 8) * 0.5, half_buf[2] = __ldg(bx + 9) * 0.5;
+			half = half_buf;
+		} else {
+			half = rb.boxes[box].half;
+		}
+		if (box_hits_scene(sc, D3{it.c[0], it.c[1], it.c[2]}, Q4{it.q[0], it.q[1], it.q[2], it.q[3]}, half, lc))
+			report_hit(res, it.owner, step);
+	}
+	flush_counters(sc, lc);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stage C (motions): first colliding step -> packed hit bit and toi = step / n_steps (collision_detection.cpp:95-101).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_finish_motions(const unsigned *__restrict__ first_step, const uint32_t *__restrict__ n_steps, size_t m,
+				 uint32_t *__restrict__ hit_bits, double *__restrict__ toi) {
+	const size_t i = (size_t) blockIdx.x * 256 + threadIdx.x;
+	const unsigned fs = i < m ? first_step[i] : NO_HIT;
+	const bool hit = fs != NO_HIT;
+	const unsigned word = __ballot_sync(0xffffffffu, hit);
+	if (i < m) {
+		if ((threadIdx.x & 31) == 0) hit_bits[i >> 5] = word;
+		if (toi) {
+			const unsigned n = n_steps[i];
+			toi[i] = hit ? (n ? (double) fs / (double) n : 0.0) : __longlong_as_double(0x7ff8000000000000ll);
+		}
 	}
 }
 
@@ -454,10 +397,10 @@ __global__ void k_count_rows(const uint32_t *__restrict__ bits, size_t rows, siz
 }
 
 /// Batched forwardKinematics (RobotModel.cpp:17-90): all link transforms of every state, n x n_links x 7 doubles.
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(256)
 k_forward_kinematics(const __grid_constant__ RobotDev rb, const double *__restrict__ states, size_t n, size_t stride,
 					 double *__restrict__ out) {
-	const size_t i = (size_t) blockIdx.x * BLOCK + threadIdx.x;
+	const size_t i = (size_t) blockIdx.x * 256 + threadIdx.x;
 	if (i >= n) return;
 	const double *r = states + i * stride;
 	double jv[MGODPL_MAX_JOINT_VALUES];
@@ -477,77 +420,117 @@ k_forward_kinematics(const __grid_constant__ RobotDev rb, const double *__restri
 // ---------------------------------------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------------------------------------
-static int g_sm_count = 0;
 static int sm_count() {
-	if (!g_sm_count) {
+	static int n = 0;
+	if (!n) {
 		int dev = 0;
 		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-		if (g_sm_count <= 0) g_sm_count = 148;
+		cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+		if (n <= 0) n = 148;
 	}
-	return g_sm_count;
+	return n;
 }
-/// Persistent-style grids: a multiple of the SM count (148 on B200), several resident blocks per SM.
-static unsigned grid_for(size_t tiles, int blocks_per_sm) {
-	size_t cap = (size_t) sm_count() * blocks_per_sm;
-	return (unsigned) (tiles < cap ? (tiles ? tiles : 1) : cap);
+/// Grids are a multiple of the SM count (148 on B200) times the resident blocks per SM, or smaller for small inputs.
+static unsigned grid_for(size_t work_items, int block, int blocks_per_sm) {
+	size_t blocks = (work_items + block - 1) / block, cap = (size_t) sm_count() * blocks_per_sm;
+	return (unsigned) (blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+size_t query_scratch_bytes(size_t worst_case_boxes) {
+	size_t cap = worst_case_boxes < QUEUE_MAX_ITEMS ? worst_case_boxes : QUEUE_MAX_ITEMS;
+	return 256 + (cap ? cap : 1) * sizeof(Item);
+}
+
+static QueueDev carve_queue(void *scratch, size_t scratch_bytes) {
+	QueueDev Q;
+	Q.count = reinterpret_cast<unsigned *>(scratch);
+	Q.items = reinterpret_cast<Item *>(reinterpret_cast<char *>(scratch) + 256);
+	size_t cap = scratch_bytes > 256 ? (scratch_bytes - 256) / sizeof(Item) : 0;
+	Q.cap = (unsigned) (cap < QUEUE_MAX_ITEMS ? cap : QUEUE_MAX_ITEMS);
+	return Q;
+}
+
+#define LQ_CHECK(x)                       \
+	do {                                  \
+		cudaError_t e_ = (x);             \
+		if (e_ != cudaSuccess) return e_; \
+	} while (0)
+
+static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const double *explicit_boxes, const QueueDev &Q,
+								const Results &res, size_t worst_case_items, cudaStream_t stream) {
+	size_t bound = worst_case_items < Q.cap ? worst_case_items : Q.cap;
+	k_traverse<<<grid_for(bound, BLOCK_B, 12), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res);
+	return cudaGetLastError();
 }
 
 cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const double *d_states, size_t n, size_t stride,
-								uint32_t *d_hit_bits, cudaStream_t stream) {
+								uint32_t *d_hit_bits, void *scratch, size_t scratch_bytes, cudaStream_t stream) {
 	if (!n) return cudaSuccess;
-	ExplicitStates src{d_states, stride};
-	size_t smem = (size_t) BLOCK * stride * sizeof(double);
-	static bool attr = false;
-	if (!attr) {
-		cudaFuncSetAttribute(k_check_states<ExplicitStates>, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK * ROW_MAX * 8);
-		attr = true;
-	}
-	k_check_states<ExplicitStates><<<grid_for((n + BLOCK - 1) / BLOCK, 6), BLOCK, smem, stream>>>(sc, rb, src, 1, n, d_hit_bits);
-	return cudaGetLastError();
+	QueueDev Q = carve_queue(scratch, scratch_bytes);
+	Results res{RESULT_BITS, d_hit_bits, nullptr};
+	LQ_CHECK(cudaMemsetAsync(Q.count, 0, sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
+	k_expand_states<<<grid_for(n, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_states, n, stride, Q, res);
+	LQ_CHECK(cudaGetLastError());
+	return run_traverse(sc, rb, nullptr, Q, res, n * (size_t) rb.n_boxes, stream);
 }
 
-cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t n, uint32_t *d_hit_bits, cudaStream_t stream) {
+cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t n, uint32_t *d_hit_bits, void *scratch,
+							   size_t scratch_bytes, cudaStream_t stream) {
 	if (!n) return cudaSuccess;
-	k_check_boxes<<<grid_for((n + BLOCK - 1) / BLOCK, 6), BLOCK, 0, stream>>>(sc, d_boxes, n, d_hit_bits);
-	return cudaGetLastError();
+	QueueDev Q = carve_queue(scratch, scratch_bytes);
+	Results res{RESULT_BITS, d_hit_bits, nullptr};
+	RobotDev none{};
+	LQ_CHECK(cudaMemsetAsync(Q.count, 0, sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
+	k_expand_boxes<<<grid_for(n, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, d_boxes, n, Q, res);
+	LQ_CHECK(cudaGetLastError());
+	return run_traverse(sc, none, d_boxes, Q, res, n, stream);
 }
 
 cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const double *d_a, const double *d_b, size_t m,
 								 size_t stride, int js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,
-								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned long long *d_next_motion,
-								 cudaStream_t stream) {
+								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned *d_first_step,
+								 void *scratch, size_t scratch_bytes, cudaStream_t stream) {
 	if (!m) return cudaSuccess;
-	cudaError_t e = cudaMemsetAsync(d_hit_bits, 0, ((m + 31) / 32) * 4, stream);
-	if (e != cudaSuccess) return e;
-	if (d_uncertain && (e = cudaMemsetAsync(d_uncertain, 0, ((m + 31) / 32) * 4, stream)) != cudaSuccess) return e;
-	if ((e = cudaMemsetAsync(d_next_motion, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
-	k_check_motions<<<grid_for((m + WARPS - 1) / WARPS, 6), BLOCK, 0, stream>>>(
-			sc, rb, d_a, d_b, m, stride, js, max_step, d_override, d_hit_bits, d_toi, d_n_steps, d_uncertain, d_next_motion);
+	QueueDev Q = carve_queue(scratch, scratch_bytes);
+	Results res{RESULT_FIRST_STEP, nullptr, d_first_step};
+	LQ_CHECK(cudaMemsetAsync(Q.count, 0, sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(d_first_step, 0xff, m * sizeof(unsigned), stream));
+	if (d_uncertain) LQ_CHECK(cudaMemsetAsync(d_uncertain, 0, ((m + 31) / 32) * 4, stream));
+	k_expand_motions<<<grid_for(m * 32, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
+																		   d_n_steps, d_uncertain, Q, res);
+	LQ_CHECK(cudaGetLastError());
+	LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (size_t) Q.cap, stream));
+	k_finish_motions<<<(unsigned) ((m + 255) / 256), 256, 0, stream>>>(d_first_step, d_n_steps, m, d_hit_bits, d_toi);
 	return cudaGetLastError();
 }
 
 cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const double *d_targets, size_t f,
 								const double *d_draws, const double *d_limits, size_t s, unsigned long long seed,
 								double distance_from_target, uint32_t *d_hit_bits, uint32_t *d_collisions,
-								double *d_states_out, cudaStream_t stream) {
+								double *d_states_out, void *scratch, size_t scratch_bytes, cudaStream_t stream) {
 	if (!f || !s) return cudaSuccess;
-	GoalStates src{d_targets, d_draws, d_limits, seed, distance_from_target, d_states_out, s};
-	size_t tiles = f * ((s + BLOCK - 1) / BLOCK);
-	k_check_states<GoalStates><<<grid_for(tiles, 6), BLOCK, 0, stream>>>(sc, rb, src, f, s, d_hit_bits);
-	cudaError_t e = cudaGetLastError();
-	if (e != cudaSuccess) return e;
+	QueueDev Q = carve_queue(scratch, scratch_bytes);
+	Results res{RESULT_BITS, d_hit_bits, nullptr};
+	const size_t wpr = (s + 31) / 32;
+	LQ_CHECK(cudaMemsetAsync(Q.count, 0, sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, f * wpr * 4, stream));
+	k_expand_goals<<<grid_for(f * s, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_targets, f, s, d_draws, d_limits, seed,
+																		distance_from_target, d_states_out, Q, res);
+	LQ_CHECK(cudaGetLastError());
+	LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, f * s * (size_t) rb.n_boxes, stream));
 	if (d_collisions) {
-		k_count_rows<<<(unsigned) f, 128, 0, stream>>>(d_hit_bits, f, (s + 31) / 32, d_collisions);
-		e = cudaGetLastError();
+		k_count_rows<<<(unsigned) f, 128, 0, stream>>>(d_hit_bits, f, wpr, d_collisions);
+		LQ_CHECK(cudaGetLastError());
 	}
-	return e;
+	return cudaSuccess;
 }
 
 cudaError_t launch_forward_kinematics(const RobotDev &rb, const double *d_states, size_t n, size_t stride, double *d_out,
 									  cudaStream_t stream) {
 	if (!n) return cudaSuccess;
-	k_forward_kinematics<<<(unsigned) ((n + BLOCK - 1) / BLOCK), BLOCK, 0, stream>>>(rb, d_states, n, stride, d_out);
+	k_forward_kinematics<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(rb, d_states, n, stride, d_out);
 	return cudaGetLastError();
 }
 
