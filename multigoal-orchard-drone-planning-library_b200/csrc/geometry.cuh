@@ -84,6 +84,14 @@ struct CullBox {
 	float wx, wy, wz;  // half extents of the box's world-axis AABB (from the inflated h)
 };
 
+/// Second half of make_cull_box: inflated half extents and the world-axis AABB, given centre and rotation.
+__device__ __forceinline__ void finish_cull_box(const SceneDev &sc, CullBox &b, float h0, float h1, float h2) {
+	b.hx = h0 + sc.margin, b.hy = h1 + sc.margin, b.hz = h2 + sc.margin;
+	b.wx = fabsf(b.r[0]) * b.hx + fabsf(b.r[1]) * b.hy + fabsf(b.r[2]) * b.hz;
+	b.wy = fabsf(b.r[3]) * b.hx + fabsf(b.r[4]) * b.hy + fabsf(b.r[5]) * b.hz;
+	b.wz = fabsf(b.r[6]) * b.hx + fabsf(b.r[7]) * b.hy + fabsf(b.r[8]) * b.hz;
+}
+
 __device__ __forceinline__ CullBox make_cull_box(const SceneDev &sc, D3 c, Q4 q, const double *half) {
 	double R[9];
 	qmat(q, R);
@@ -91,10 +99,7 @@ __device__ __forceinline__ CullBox make_cull_box(const SceneDev &sc, D3 c, Q4 q,
 	b.cx = (float) (c.x - sc.origin[0]), b.cy = (float) (c.y - sc.origin[1]), b.cz = (float) (c.z - sc.origin[2]);
 #pragma unroll
 	for (int i = 0; i < 9; ++i) b.r[i] = (float) R[i];
-	b.hx = (float) half[0] + sc.margin, b.hy = (float) half[1] + sc.margin, b.hz = (float) half[2] + sc.margin;
-	b.wx = fabsf(b.r[0]) * b.hx + fabsf(b.r[1]) * b.hy + fabsf(b.r[2]) * b.hz;
-	b.wy = fabsf(b.r[3]) * b.hx + fabsf(b.r[4]) * b.hy + fabsf(b.r[5]) * b.hz;
-	b.wz = fabsf(b.r[6]) * b.hx + fabsf(b.r[7]) * b.hy + fabsf(b.r[8]) * b.hz;
+	finish_cull_box(sc, b, (float) half[0], (float) half[1], (float) half[2]);
 	return b;
 }
 

@@ -30,15 +30,21 @@ constexpr unsigned NO_HIT = 0xFFFFFFFFu;
 constexpr int ROW_MAX = 7 + MGODPL_MAX_JOINT_VALUES;
 
 // ---------------------------------------------------------------------------------------------------------------
-// Work queue: 64-byte items = fp64 box pose (centre, quaternion) + owner + (step | box << 28).
+// Work queue: 128-byte items.  The fp32 culling box (centre relative to the scene origin + rotation) is what the
+// traversal keeps in registers; the fp64 pose is only re-read when a leaf needs the exact test.
 // ---------------------------------------------------------------------------------------------------------------
 struct __align__(16) Item {
+	float cull_c[3];
+	float cull_r[9];
+	unsigned owner;
+	unsigned step_box;  // step | box << 28
+	unsigned pad0[2];
 	double c[3];
 	double q[4];
-	unsigned owner;
-	unsigned step_box;
+	double pad1;
 };
-static_assert(sizeof(Item) == 64, "queue item must be 64 bytes");
+static_assert(sizeof(Item) == 128, "queue item must be 128 bytes");
+constexpr unsigned ITEM_EXACT_OFFSET = 64;  // byte offset of Item::c
 
 enum ResultMode : int { RESULT_BITS = 0, RESULT_FIRST_STEP = 1 };
 
@@ -72,13 +78,18 @@ __device__ __forceinline__ void report_hit(const Results &res, unsigned owner, u
 	else atomicMin(res.first_step + owner, step);
 }
 
-/// The traversal proper: does the box (c, q, half) touch any triangle of the scene?
-__device__ __forceinline__ bool box_hits_scene(const SceneDev &sc, D3 c, Q4 q, const double *half, LocalCounters &lc) {
-	const CullBox cb = make_cull_box(sc, c, q, half);
+__device__ __forceinline__ ExactBox make_exact_box(D3 c, Q4 q, const double *half) {
 	ExactBox eb;
 	eb.cx = c.x, eb.cy = c.y, eb.cz = c.z;
 	qmat(q, eb.r);
 	eb.hx = half[0], eb.hy = half[1], eb.hz = half[2];
+	return eb;
+}
+
+/// Plain one-thread traversal (stage A's queue-overflow path): does the box touch any triangle of the scene?
+__device__ __noinline__ bool box_hits_scene(const SceneDev &sc, const CullBox &cb, D3 c, Q4 q, const double *half,
+											LocalCounters &lc) {
+	const ExactBox eb = make_exact_box(c, q, half);
 	const unsigned n_nodes = sc.n_nodes;
 	unsigned node = 0;
 	lc.boxes++;
@@ -102,7 +113,8 @@ __device__ __forceinline__ bool box_hits_scene(const SceneDev &sc, D3 c, Q4 q, c
 
 struct QueueDev {
 	Item *items;
-	unsigned *count;  // items appended so far (may exceed cap: the excess was traversed inline)
+	unsigned *count;   // items appended so far (may exceed cap: the excess was traversed inline)
+	unsigned *cursor;  // stage B's chunk dispenser
 	unsigned cap;
 };
 
@@ -116,16 +128,18 @@ __device__ __forceinline__ void emit_box(const SceneDev &sc, const QueueDev &Q, 
 	if (g.thread_rank() == 0) base = atomicAdd(Q.count, g.size());
 	const unsigned pos = g.shfl(base, 0) + g.thread_rank();
 	if (pos < Q.cap) {
-		Item it;
-		it.c[0] = c.x, it.c[1] = c.y, it.c[2] = c.z;
-		it.q[0] = q.x, it.q[1] = q.y, it.q[2] = q.z, it.q[3] = q.w;
-		it.owner = owner, it.step_box = step | box << 28;
 		uint4 *dst = reinterpret_cast<uint4 *>(Q.items + pos);
-		const uint4 *src = reinterpret_cast<const uint4 *>(&it);
-#pragma unroll
-		for (int k = 0; k < 4; ++k) __stcg(dst + k, src[k]);
+		__stcg(dst + 0, make_uint4(__float_as_uint(cb.cx), __float_as_uint(cb.cy), __float_as_uint(cb.cz), __float_as_uint(cb.r[0])));
+		__stcg(dst + 1, make_uint4(__float_as_uint(cb.r[1]), __float_as_uint(cb.r[2]), __float_as_uint(cb.r[3]), __float_as_uint(cb.r[4])));
+		__stcg(dst + 2, make_uint4(__float_as_uint(cb.r[5]), __float_as_uint(cb.r[6]), __float_as_uint(cb.r[7]), __float_as_uint(cb.r[8])));
+		__stcg(dst + 3, make_uint4(owner, step | box << 28, 0u, 0u));
+		double2 *dd = reinterpret_cast<double2 *>(dst + 4);
+		__stcg(dd + 0, make_double2(c.x, c.y));
+		__stcg(dd + 1, make_double2(c.z, q.x));
+		__stcg(dd + 2, make_double2(q.y, q.z));
+		__stcg(dd + 3, make_double2(q.w, 0.0));
 	} else if (!already_decided(res, owner, step)) {
-		if (box_hits_scene(sc, c, q, half, lc)) report_hit(res, owner, step);
+		if (box_hits_scene(sc, cb, c, q, half, lc)) report_hit(res, owner, step);
 	}
 }
 
@@ -332,32 +346,123 @@ k_expand_motions(const __grid_constant__ SceneDev sc, const __grid_constant__ Ro
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Stage B: drain the queue, one box per thread.
+// Stage B: drain the queue.  Persistent warps, one box per lane, "while-while" with lane refill:
+//   refill   lanes whose box is finished take the next queued boxes (warp-local chunks of the queue, so neighbouring
+//            lanes hold neighbouring interpolation steps / samples and walk the tree together);
+//   descend  every lane steps through the skip-link BVH until it reaches an overlapping leaf or runs out of nodes;
+//            the warp leaves this loop once too few lanes are still descending;
+//   leaves   lanes parked on a leaf run the exact fp64 box/triangle test together.
+// Without refill a warp's time is its slowest lane (a few boxes deep in the canopy among many that die at the top
+// of the tree): measured 3.6 active threads per instruction; this loop keeps most lanes busy.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(BLOCK_B)
+constexpr unsigned QUEUE_CHUNK = 64;    // items a warp claims per cursor atomic
+constexpr int REFILL_MIN = 8;           // idle lanes that trigger a refill
+constexpr int DESCEND_MIN = 20;         // leave the descend loop when fewer lanes than this are still walking
+
+__global__ void __launch_bounds__(BLOCK_B, 4)
 k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ explicit_boxes,
 		   QueueDev Q, Results res) {
+	constexpr unsigned FULL = 0xffffffffu, END = 0xffffffffu;
+	const unsigned lane = threadIdx.x & 31;
+	const unsigned n_items = min(__ldcg(Q.count), Q.cap);
+	const unsigned n_nodes = sc.n_nodes;
 	LocalCounters lc;
-	const unsigned n = min(__ldcg(Q.count), Q.cap);
-	for (unsigned i = blockIdx.x * BLOCK_B + threadIdx.x; i < n; i += gridDim.x * BLOCK_B) {
-		Item it;
-		const uint4 *src = reinterpret_cast<const uint4 *>(Q.items + i);
-		uint4 *dst = reinterpret_cast<uint4 *>(&it);
-#pragma unroll
-		for (int k = 0; k < 4; ++k) dst[k] = __ldcg(src + k);
-		const unsigned step = it.step_box & 0x0FFFFFFFu, box = it.step_box >> 28;
-		if (already_decided(res, it.owner, step)) continue;
-		double half_buf[3];
-		const double *half;
-		if (explicit_boxes) {
-			const double *bx = explicit_boxes + (size_t) it.owner * 10;
-			half_buf[0] = __ldg(bx + 7) * 0.5, half_buf[1] = __ldg(bx + 8) * 0.5, half_buf[2] = __ldg(bx + 9) * 0.5;
-			half = half_buf;
-		} else {
-			half = rb.boxes[box].half;
+	unsigned chunk_lo = 0, chunk_hi = 0;  // warp-uniform: unclaimed part of this warp's chunk
+	bool exhausted = false;               // warp-uniform: the queue has nothing left to claim
+	// lane state
+	CullBox cb{};
+	unsigned node = END, owner = 0, step_box = 0, item = 0;
+	int pending = -1;  // leaf info of an overlapping leaf awaiting its exact test
+
+	for (;;) {
+		const bool idle = node >= n_nodes && pending < 0;
+		const unsigned idle_mask = __ballot_sync(FULL, idle);
+		if (idle_mask == FULL && exhausted) break;
+		// ---- refill ---------------------------------------------------------------------------------------------
+		if (!exhausted && (__popc(idle_mask) >= REFILL_MIN)) {
+			if (chunk_lo == chunk_hi) {
+				unsigned lo = 0;
+				if (lane == 0) lo = atomicAdd(Q.cursor, QUEUE_CHUNK);
+				lo = __shfl_sync(FULL, lo, 0);
+				chunk_lo = min(lo, n_items), chunk_hi = min(lo + QUEUE_CHUNK, n_items);
+				exhausted = chunk_lo >= n_items;
+			}
+			const unsigned avail = chunk_hi - chunk_lo, rank = __popc(idle_mask & ((1u << lane) - 1u));
+			if (idle && rank < avail) {
+				item = chunk_lo + rank;
+				const uint4 *src = reinterpret_cast<const uint4 *>(Q.items + item);
+				const uint4 v0 = __ldcg(src), v1 = __ldcg(src + 1), v2 = __ldcg(src + 2), v3 = __ldcg(src + 3);
+				owner = v3.x, step_box = v3.y;
+				if (!already_decided(res, owner, step_box & 0x0FFFFFFFu)) {
+					cb.cx = __uint_as_float(v0.x), cb.cy = __uint_as_float(v0.y), cb.cz = __uint_as_float(v0.z);
+					cb.r[0] = __uint_as_float(v0.w), cb.r[1] = __uint_as_float(v1.x), cb.r[2] = __uint_as_float(v1.y);
+					cb.r[3] = __uint_as_float(v1.z), cb.r[4] = __uint_as_float(v1.w), cb.r[5] = __uint_as_float(v2.x);
+					cb.r[6] = __uint_as_float(v2.y), cb.r[7] = __uint_as_float(v2.z), cb.r[8] = __uint_as_float(v2.w);
+					float h0, h1, h2;
+					if (explicit_boxes) {
+						const double *bx = explicit_boxes + (size_t) owner * 10;
+						h0 = (float) (__ldg(bx + 7) * 0.5), h1 = (float) (__ldg(bx + 8) * 0.5), h2 = (float) (__ldg(bx + 9) * 0.5);
+					} else {
+						const double *hh = rb.boxes[step_box >> 28].half;
+						h0 = (float) hh[0], h1 = (float) hh[1], h2 = (float) hh[2];
+					}
+					finish_cull_box(sc, cb, h0, h1, h2);
+					node = 0;
+					lc.boxes++;
+				}
+			}
+			chunk_lo += min(avail, (unsigned) __popc(idle_mask));
+			continue;  // re-evaluate who is idle (a refill may have come up short at a chunk boundary)
 		}
-		if (box_hits_scene(sc, D3{it.c[0], it.c[1], it.c[2]}, Q4{it.q[0], it.q[1], it.q[2], it.q[3]}, half, lc))
-			report_hit(res, it.owner, step);
+		// ---- descend ----------------------------------------------------------------------------------------------
+		bool run = node < n_nodes && pending < 0;
+		unsigned go = __ballot_sync(FULL, run);
+		const int low_water = exhausted ? 1 : DESCEND_MIN;
+		while (go) {
+			if (run) {
+				const float4 a = __ldg(sc.nodes + 2 * node);
+				const float4 b = __ldg(sc.nodes + 2 * node + 1);
+				const bool ov = cull_overlap(cb, a.x, a.y, a.z, b.x, b.y, b.z);
+				const int leaf = __float_as_int(b.w);
+				lc.nodes++;
+				if (ov && leaf >= 0) pending = leaf;
+				node = (ov && leaf < 0) ? node + 1 : __float_as_uint(a.w);
+				run = node < n_nodes && pending < 0;
+			}
+			go = __ballot_sync(FULL, run);
+			if (__popc(go) < low_water) break;
+		}
+		// ---- leaves -------------------------------------------------------------------------------------------------
+		if (pending >= 0) {
+			const unsigned first = (unsigned) pending >> 4, cnt = ((unsigned) pending & 15u) + 1u;
+			pending = -1;
+			const unsigned step = step_box & 0x0FFFFFFFu;
+			if (already_decided(res, owner, step)) {
+				node = END;
+			} else {
+				const double2 *ex = reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(Q.items + item) + ITEM_EXACT_OFFSET);
+				const double2 e0 = __ldcg(ex), e1 = __ldcg(ex + 1), e2 = __ldcg(ex + 2), e3 = __ldcg(ex + 3);
+				double half_buf[3];
+				const double *half;
+				if (explicit_boxes) {
+					const double *bx = explicit_boxes + (size_t) owner * 10;
+					half_buf[0] = __ldg(bx + 7) * 0.5, half_buf[1] = __ldg(bx + 8) * 0.5, half_buf[2] = __ldg(bx + 9) * 0.5;
+					half = half_buf;
+				} else {
+					half = rb.boxes[step_box >> 28].half;
+				}
+				const ExactBox eb = make_exact_box(D3{e0.x, e0.y, e1.x}, Q4{e1.y, e2.x, e2.y, e3.x}, half);
+				bool hit = false;
+				for (unsigned k = 0; k < cnt && !hit; ++k) {
+					lc.leaf++;
+					hit = box_triangle_hit(eb, sc.tris + 9ull * (first + k));
+				}
+				if (hit) {
+					report_hit(res, owner, step);
+					node = END;
+				}
+			}
+		}
 	}
 	flush_counters(sc, lc);
 }
@@ -444,6 +549,7 @@ size_t query_scratch_bytes(size_t worst_case_boxes) {
 static QueueDev carve_queue(void *scratch, size_t scratch_bytes) {
 	QueueDev Q;
 	Q.count = reinterpret_cast<unsigned *>(scratch);
+	Q.cursor = Q.count + 1;
 	Q.items = reinterpret_cast<Item *>(reinterpret_cast<char *>(scratch) + 256);
 	size_t cap = scratch_bytes > 256 ? (scratch_bytes - 256) / sizeof(Item) : 0;
 	Q.cap = (unsigned) (cap < QUEUE_MAX_ITEMS ? cap : QUEUE_MAX_ITEMS);
@@ -459,7 +565,7 @@ static QueueDev carve_queue(void *scratch, size_t scratch_bytes) {
 static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const double *explicit_boxes, const QueueDev &Q,
 								const Results &res, size_t worst_case_items, cudaStream_t stream) {
 	size_t bound = worst_case_items < Q.cap ? worst_case_items : Q.cap;
-	k_traverse<<<grid_for(bound, BLOCK_B, 12), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res);
+	k_traverse<<<grid_for(bound, BLOCK_B, 4), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res);
 	return cudaGetLastError();
 }
 
@@ -468,7 +574,7 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 	if (!n) return cudaSuccess;
 	QueueDev Q = carve_queue(scratch, scratch_bytes);
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
-	LQ_CHECK(cudaMemsetAsync(Q.count, 0, sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 2 * sizeof(unsigned), stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
 	k_expand_states<<<grid_for(n, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_states, n, stride, Q, res);
 	LQ_CHECK(cudaGetLastError());
@@ -481,7 +587,7 @@ cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t
 	QueueDev Q = carve_queue(scratch, scratch_bytes);
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	RobotDev none{};
-	LQ_CHECK(cudaMemsetAsync(Q.count, 0, sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 2 * sizeof(unsigned), stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
 	k_expand_boxes<<<grid_for(n, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, d_boxes, n, Q, res);
 	LQ_CHECK(cudaGetLastError());
@@ -495,7 +601,7 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	if (!m) return cudaSuccess;
 	QueueDev Q = carve_queue(scratch, scratch_bytes);
 	Results res{RESULT_FIRST_STEP, nullptr, d_first_step};
-	LQ_CHECK(cudaMemsetAsync(Q.count, 0, sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 2 * sizeof(unsigned), stream));
 	LQ_CHECK(cudaMemsetAsync(d_first_step, 0xff, m * sizeof(unsigned), stream));
 	if (d_uncertain) LQ_CHECK(cudaMemsetAsync(d_uncertain, 0, ((m + 31) / 32) * 4, stream));
 	k_expand_motions<<<grid_for(m * 32, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
@@ -514,7 +620,7 @@ cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const do
 	QueueDev Q = carve_queue(scratch, scratch_bytes);
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	const size_t wpr = (s + 31) / 32;
-	LQ_CHECK(cudaMemsetAsync(Q.count, 0, sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 2 * sizeof(unsigned), stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, f * wpr * 4, stream));
 	k_expand_goals<<<grid_for(f * s, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_targets, f, s, d_draws, d_limits, seed,
 																		distance_from_target, d_states_out, Q, res);
