@@ -447,7 +447,7 @@ int mgodpl_forward_kinematics(const mgodpl_robot *robot, const double *states, s
 int mgodpl_check_boxes(mgodpl_scene *scene, const double *boxes, size_t n, uint32_t *hit_bits, void *stream_) {
 	if (!scene) return fail(MGODPL_E_INVALID_ARGUMENT, "scene is null");
 	if (n && (!boxes || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
-	if (n >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^32-2 queries in one call");
+	if (n > SURVIVOR_MAX_ENTRIES) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^26 queries in one call: split the batch");
 	if (int rc = require_device()) return rc;
 	if (!n) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
@@ -470,11 +470,11 @@ int mgodpl_check_states_device(mgodpl_scene *scene, const mgodpl_robot *robot, c
 	if (!scene) return fail(MGODPL_E_INVALID_ARGUMENT, "scene is null");
 	if (int rc = check_state_args(robot, stride, js)) return rc;
 	if (n && (!d_states || !d_hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
-	if (n >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^32-2 queries in one call");
+	if (n > SURVIVOR_MAX_ENTRIES) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^26 queries in one call: split the batch");
 	if (int rc = require_device()) return rc;
 	if (!n) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
-	const size_t qb = query_scratch_bytes(n * (size_t) robot->dev.n_boxes);
+	const size_t qb = query_scratch_bytes(n * (size_t) robot->dev.n_boxes, n);
 	char *scratch = nullptr;
 	CU(scene->device_scratch(stream, qb, &scratch));
 	CU(launch_check_states(scene->dev, robot->dev, d_states, n, stride, d_hit_bits, scratch, qb, stream));
@@ -486,13 +486,13 @@ int mgodpl_check_states(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	if (!scene) return fail(MGODPL_E_INVALID_ARGUMENT, "scene is null");
 	if (int rc = check_state_args(robot, stride, js)) return rc;
 	if (n && (!states || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
-	if (n >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^32-2 queries in one call");
+	if (n > SURVIVOR_MAX_ENTRIES) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^26 queries in one call: split the batch");
 	if (int rc = require_device()) return rc;
 	if (!n) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Lease ws(scene->pool);
 	Carver c;
-	const size_t in_b = n * stride * 8, words = (n + 31) / 32, qb = query_scratch_bytes(n * (size_t) robot->dev.n_boxes);
+	const size_t in_b = n * stride * 8, words = (n + 31) / 32, qb = query_scratch_bytes(n * (size_t) robot->dev.n_boxes, n);
 	size_t o_in = c.take(in_b), o_out = c.take(words * 4), o_q = c.take(qb);
 	CU(ws->reserve(c.off, words * 4));
 	// Caller memory goes straight to the device; only the (small) result is staged through pinned memory.
@@ -508,7 +508,10 @@ int mgodpl_check_states(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 // ---- motions ---------------------------------------------------------------------------------------------------------------
 /// Queue sizing for motions: the step count is only known on the device, so assume ~128 steps per motion (the PRM
 /// sampler averages ~104) — a wrong guess only moves work between stage B and stage A's inline path.
-static size_t motion_scratch_bytes(size_t m, int n_boxes) { return query_scratch_bytes(m * 128 * (size_t) n_boxes); }
+static size_t motion_survivors(size_t m) { return m * 128; }
+static size_t motion_scratch_bytes(size_t m, int n_boxes) {
+	return query_scratch_bytes(m * 128 * (size_t) n_boxes, motion_survivors(m));
+}
 
 int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, const double *d_a, const double *d_b, size_t m,
 								size_t stride, int32_t js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,
@@ -528,7 +531,7 @@ int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, 
 	CU(scene->device_scratch(stream, c.off, &scratch));
 	CU(launch_check_motions(scene->dev, robot->dev, d_a, d_b, m, stride, js, max_step, d_override, d_hit_bits, d_toi,
 							d_n_steps ? d_n_steps : (uint32_t *) (scratch + o_steps), d_uncertain, (unsigned *) (scratch + o_first),
-							scratch + o_q, qb, stream));
+							scratch + o_q, qb, motion_survivors(m), stream));
 	return MGODPL_OK;
 }
 
@@ -574,7 +577,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	CU(cudaMemcpyAsync(D + o_b, b, in_b, cudaMemcpyHostToDevice, stream));
 	CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a), (const double *) (D + o_b), m, stride, js, max_step,
 							nullptr, (uint32_t *) (D + o_hit), toi ? (double *) (D + o_toi) : nullptr, (uint32_t *) (D + o_steps),
-							(uint32_t *) (D + o_unc), (unsigned *) (D + o_first), D + o_q, qb, stream));
+							(uint32_t *) (D + o_unc), (unsigned *) (D + o_first), D + o_q, qb, motion_survivors(m), stream));
 	CU(cudaMemcpyAsync(H + out_lo, D + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, stream));
 	CU(cudaStreamSynchronize(stream));
 	// Step-count fix-up: the device libm may differ from the host's by an ulp, which only matters when distance /
@@ -601,7 +604,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a), (const double *) (D + o_b), m, stride, js,
 								max_step, (const uint32_t *) (D + o_ovr), (uint32_t *) (D + o_hit),
 								toi ? (double *) (D + o_toi) : nullptr, (uint32_t *) (D + o_steps), nullptr,
-								(unsigned *) (D + o_first), D + o_q, qb, stream));
+								(unsigned *) (D + o_first), D + o_q, qb, motion_survivors(m), stream));
 		CU(cudaMemcpyAsync(H + out_lo, D + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, stream));
 		CU(cudaStreamSynchronize(stream));
 	}

@@ -9,7 +9,9 @@ namespace mgodpl_b200 {
 /// Upper bound on queued boxes per launch (64 B each); beyond it stage A traverses inline.
 constexpr size_t QUEUE_MAX_ITEMS = 8u << 20;
 /// Bytes of device scratch a query launch wants for `worst_case_boxes` candidate boxes (queue header + items).
-size_t query_scratch_bytes(size_t worst_case_boxes);
+/// Upper bound on survivor-list entries (8 B each) between the broad cull and FK expansion.
+constexpr size_t SURVIVOR_MAX_ENTRIES = 64u << 20;
+size_t query_scratch_bytes(size_t worst_case_boxes, size_t survivor_entries = 0);
 
 cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const double *d_states, size_t n, size_t stride,
 								uint32_t *d_hit_bits, void *scratch, size_t scratch_bytes, cudaStream_t stream);
@@ -19,7 +21,7 @@ cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t
 cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const double *d_a, const double *d_b, size_t m,
 								 size_t stride, int js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,
 								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned *d_first_step,
-								 void *scratch, size_t scratch_bytes, cudaStream_t stream);
+								 void *scratch, size_t scratch_bytes, size_t survivor_entries, cudaStream_t stream);
 cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const double *d_targets, size_t f,
 								const double *d_draws, const double *d_limits, size_t s, unsigned long long seed,
 								double distance_from_target, uint32_t *d_hit_bits, uint32_t *d_collisions,

@@ -16,6 +16,7 @@
 // boxes that do need a tree descent are compacted, so stage B runs converged and at full occupancy.  If the queue
 // would overflow, stage A traverses the box on the spot — capacity is a performance knob, never a correctness one.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "geometry.cuh"
 #include "kernels.h"
@@ -176,20 +177,48 @@ __device__ __forceinline__ void expand_state(const SceneDev &sc, const RobotDev 
 // ---------------------------------------------------------------------------------------------------------------
 // Stage A kernels
 // ---------------------------------------------------------------------------------------------------------------
-/// Explicit states: check_robot_collision over N states.
+/// Survivor list between the broad cull (A1) and FK expansion (A2): 8-byte entries (owner, step).
+struct SurvivorsDev {
+	uint2 *entries;
+	unsigned *count;  // entries appended (<= cap is guaranteed by the launchers' sizing or by inline expansion)
+	unsigned cap;
+};
+
+/// A1 for explicit states: read only the base translation (24 of the state's 72+ bytes) and keep the states whose
+/// reach sphere touches the scene bounds.
 __global__ void __launch_bounds__(BLOCK_A)
-k_expand_states(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ states,
-				size_t n, size_t stride, QueueDev Q, Results res) {
-	LocalCounters lc;
+k_cull_states(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ states,
+			  size_t n, size_t stride, SurvivorsDev S) {
+	unsigned n_states = 0;
 	for (size_t i = (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < n; i += (size_t) gridDim.x * BLOCK_A) {
 		const double *r = states + i * stride;
-		lc.states++;
+		n_states++;
 		const D3 t{__ldg(r), __ldg(r + 1), __ldg(r + 2)};
 		if (robot_out_of_reach(sc, rb, t)) continue;
+		cg::coalesced_group g = cg::coalesced_threads();
+		unsigned base = 0;
+		if (g.thread_rank() == 0) base = atomicAdd(S.count, g.size());
+		S.entries[g.shfl(base, 0) + g.thread_rank()] = make_uint2((unsigned) i, 0u);  // cap == n: cannot overflow
+	}
+	LocalCounters lc;
+	lc.states = n_states;
+	flush_counters(sc, lc);
+}
+
+/// A2 for explicit states: FK + per-box cull + queue append, one thread per surviving state
+/// (check_robot_collision, collision_detection.cpp:57-80).
+__global__ void __launch_bounds__(BLOCK_A)
+k_expand_states(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ states,
+				size_t stride, SurvivorsDev S, QueueDev Q, Results res) {
+	LocalCounters lc;
+	const unsigned n = min(__ldcg(S.count), S.cap);
+	for (unsigned k = blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
+		const unsigned i = __ldcg(&S.entries[k]).x;
+		const double *r = states + (size_t) i * stride;
 		double row[ROW_MAX];
-		for (int k = 0; k < 4 + rb.n_vars; ++k) row[k] = __ldg(r + 3 + k);
-		if (!isfinite(row[0] + row[1] + row[2] + row[3])) continue;
-		expand_state(sc, rb, Q, res, Pose{t, Q4{row[0], row[1], row[2], row[3]}}, row + 4, (unsigned) i, 0u, lc);
+		for (int j = 0; j < 7 + rb.n_vars; ++j) row[j] = __ldg(r + j);
+		if (!finite7(row)) continue;
+		expand_state(sc, rb, Q, res, Pose{D3{row[0], row[1], row[2]}, Q4{row[3], row[4], row[5], row[6]}}, row + 7, i, 0u, lc);
 	}
 	flush_counters(sc, lc);
 }
@@ -264,85 +293,143 @@ k_expand_goals(const __grid_constant__ SceneDev sc, const __grid_constant__ Robo
 	flush_counters(sc, lc);
 }
 
-/// Motions: check_motion_collides (collision_detection.cpp:82-105).  One warp per motion; lanes take 32 consecutive
-/// interpolation steps at a time.  Every step 0..n_steps is expanded; the first colliding one is found in stage B/C.
+/// One interpolation step of one motion: interpolate(a, b, t) (RobotState.cpp:14-24, Transform.h:69-78, Eigen slerp
+/// rule of Quaternion.cpp:12-20), exact reach cull, FK, box emit.  A/B point at the two endpoint rows.
+__device__ __forceinline__ void expand_motion_step(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
+												   const double *__restrict__ A, const double *__restrict__ B, unsigned n_steps,
+												   unsigned motion, unsigned step, LocalCounters &lc) {
+	double a[ROW_MAX], b[ROW_MAX];
+	for (int k = 0; k < 7 + rb.n_vars; ++k) a[k] = __ldg(A + k), b[k] = __ldg(B + k);
+	lc.states++;
+	// for n_steps == 0 the reference evaluates t = 0/0; here the start state is checked once.
+	const double t = n_steps ? (double) step / (double) n_steps : 0.0;
+	const D3 tr{(1.0 - t) * a[0] + t * b[0], (1.0 - t) * a[1] + t * b[1], (1.0 - t) * a[2] + t * b[2]};
+	if (robot_out_of_reach(sc, rb, tr)) return;
+	Pose base{tr, Q4{a[3], a[4], a[5], a[6]}};
+	double jv[MGODPL_MAX_JOINT_VALUES];
+	if (n_steps) {
+		const double dq = a[3] * b[3] + a[4] * b[4] + a[5] * b[5] + a[6] * b[6];
+		const double ad = fabs(dq);
+		double w0, w1;
+		if (ad >= 1.0 - 2.220446049250313e-16) {
+			w0 = 1.0 - t, w1 = t;
+		} else {
+			const double theta = acos(ad), st = sin(theta);
+			w0 = sin((1.0 - t) * theta) / st;
+			w1 = sin(t * theta) / st;
+		}
+		if (dq < 0.0) w1 = -w1;
+		base.q = Q4{w0 * a[3] + w1 * b[3], w0 * a[4] + w1 * b[4], w0 * a[5] + w1 * b[5], w0 * a[6] + w1 * b[6]};
+		for (int k = 0; k < rb.n_vars; ++k) jv[k] = a[7 + k] * (1 - t) + b[7 + k] * t;
+	} else {
+		for (int k = 0; k < rb.n_vars; ++k) jv[k] = a[7 + k];
+	}
+	if (!isfinite(base.q.x + base.q.y + base.q.z + base.q.w)) return;
+	expand_state(sc, rb, Q, res, base, jv, motion, step, lc);
+}
+
+/// A1 for motions, one thread per motion: the step count of check_motion_collides (collision_detection.cpp:88-92)
+/// and — instead of visiting every step — the contiguous range of steps whose base position can lie within the
+/// robot's reach of the scene bounds (slab clip of the translation segment, widened by one step either side).
+/// The surviving (motion, step) pairs go to the survivor list, written warp-cooperatively.
 __global__ void __launch_bounds__(BLOCK_A)
-k_expand_motions(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
-				 const double *__restrict__ b, size_t m, size_t stride, int js, double max_step,
-				 const uint32_t *__restrict__ n_steps_override, uint32_t *__restrict__ n_steps_out,
-				 uint32_t *__restrict__ uncertain_bits, QueueDev Q, Results res) {
-	constexpr int WARPS = BLOCK_A / 32;
-	__shared__ double s_a[WARPS][ROW_MAX], s_b[WARPS][ROW_MAX];
-	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
+				const double *__restrict__ b, size_t m, size_t stride, int js, double max_step,
+				const uint32_t *__restrict__ n_steps_override, uint32_t *__restrict__ n_steps_out,
+				uint32_t *__restrict__ uncertain_bits, SurvivorsDev S, QueueDev Q, Results res) {
+	const unsigned lane = threadIdx.x & 31;
 	LocalCounters lc;
 	unsigned long long n_uncertain = 0, n_motions = 0;
-	for (size_t motion = (size_t) blockIdx.x * WARPS + warp; motion < m; motion += (size_t) gridDim.x * WARPS) {
-		__syncwarp();
-		if (lane < stride) {
-			s_a[warp][lane] = __ldg(a + motion * stride + lane);
-			s_b[warp][lane] = __ldg(b + motion * stride + lane);
-		}
-		__syncwarp();
-		const double *A = s_a[warp], *B = s_b[warp];
-		// equal_weights_distance (distance.cpp:17-25, Quaternion.h:78-85) in the reference's operand order
-		double dx = A[0] - B[0], dy = A[1] - B[1], dz = A[2] - B[2];
-		double d = sqrt(dx * dx + dy * dy + dz * dz);
-		double c = A[6] * B[6] + A[3] * B[3] + A[4] * B[4] + A[5] * B[5];
-		double cc = fmin(fmax(c, -1.0), 1.0);
-		d += acos(2.0 * cc * cc - 1.0);
-		for (int i = 0; i < js; ++i) d += fabs(A[7 + i] - B[7 + i]);
-		const double x = d / max_step;
-		double nd = ceil(x);
-		bool uncertain = fabs(x - rint(x)) < 1e-9 * fmax(1.0, x);
-		if (!(nd >= 0.0 && nd < 268435455.0)) nd = 0.0;  // non-finite / absurd distances: one check of the start state
-		unsigned n_steps = (unsigned) nd;
-		if (n_steps_override) {
-			const unsigned o = __ldg(n_steps_override + motion);
-			if (o != NO_HIT) n_steps = o, uncertain = false;
-		}
-		if (lane == 0) {
-			if (n_steps_out) n_steps_out[motion] = n_steps;
-			if (uncertain && uncertain_bits) atomicOr(uncertain_bits + (motion >> 5), 1u << (motion & 31));
+	const size_t m_pad = (m + 31) & ~(size_t) 31;
+	for (size_t i = (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < m_pad; i += (size_t) gridDim.x * BLOCK_A) {
+		unsigned s_lo = 0, len = 0, n_steps = 0;
+		if (i < m) {
+			const double *A = a + i * stride, *B = b + i * stride;
+			double ar[7], br[7];
+#pragma unroll
+			for (int k = 0; k < 7; ++k) ar[k] = __ldg(A + k), br[k] = __ldg(B + k);
+			// equal_weights_distance (distance.cpp:17-25, Quaternion.h:78-85) in the reference's operand order
+			const double dx = ar[0] - br[0], dy = ar[1] - br[1], dz = ar[2] - br[2];
+			double d = sqrt(dx * dx + dy * dy + dz * dz);
+			const double c = ar[6] * br[6] + ar[3] * br[3] + ar[4] * br[4] + ar[5] * br[5];
+			const double cc = fmin(fmax(c, -1.0), 1.0);
+			d += acos(2.0 * cc * cc - 1.0);
+			for (int k = 0; k < js; ++k) d += fabs(__ldg(A + 7 + k) - __ldg(B + 7 + k));
+			const double x = d / max_step;
+			double nd = ceil(x);
+			bool uncertain = fabs(x - rint(x)) < 1e-9 * fmax(1.0, x);
+			if (!(nd >= 0.0 && nd < 268435455.0)) nd = 0.0;  // non-finite / absurd distances: one check of the start state
+			n_steps = (unsigned) nd;
+			if (n_steps_override) {
+				const unsigned o = __ldg(n_steps_override + i);
+				if (o != NO_HIT) n_steps = o, uncertain = false;
+			}
+			if (n_steps_out) n_steps_out[i] = n_steps;
+			if (uncertain && uncertain_bits) atomicOr(uncertain_bits + (i >> 5), 1u << (i & 31));
 			n_uncertain += uncertain;
 			n_motions++;
-		}
-		// Eigen slerp rule (Quaternion.cpp:12-20): shortest arc, linear weights when |dot| >= 1 - eps
-		const double dq = A[3] * B[3] + A[4] * B[4] + A[5] * B[5] + A[6] * B[6];
-		const double ad = fabs(dq);
-		const bool linear = ad >= 1.0 - 2.220446049250313e-16;
-		const double theta = linear ? 0.0 : acos(ad);
-		const double inv_sin = linear ? 1.0 : 1.0 / sin(theta);
-		for (unsigned long long s0 = 0; s0 <= n_steps; s0 += 32) {
-			const unsigned long long step = s0 + lane;
-			if (step > n_steps) continue;
-			lc.states++;
-			// for n_steps == 0 the reference evaluates t = 0/0; here the start state is checked once.
-			const double t = n_steps ? (double) step / (double) n_steps : 0.0;
-			// Transform.h:69-78 — translation lerp (1-t) a + t b
-			const D3 tr{(1.0 - t) * A[0] + t * B[0], (1.0 - t) * A[1] + t * B[1], (1.0 - t) * A[2] + t * B[2]};
-			if (robot_out_of_reach(sc, rb, tr)) continue;
-			double w0, w1;
-			if (linear) {
-				w0 = 1.0 - t, w1 = t;
-			} else {
-				w0 = sin((1.0 - t) * theta) * inv_sin;
-				w1 = sin(t * theta) * inv_sin;
+			// slab clip of P(t) = A + t (B - A), t in [0, 1], against the scene bounds grown by the reach
+			const double grow = rb.reach + (double) sc.margin + 1e-6;
+			double t0 = 0.0, t1 = 1.0;
+			bool empty = false;
+#pragma unroll
+			for (int k = 0; k < 3; ++k) {
+				const double p = ar[k] - (sc.origin[k] + (double) sc.root_c[k]);
+				const double e = (double) sc.root_h[k] + grow;
+				const double dl = n_steps ? br[k] - ar[k] : 0.0;
+				if (fabs(dl) < 1e-300) {
+					empty |= !(fabs(p) <= e);
+				} else {
+					double ta = (-e - p) / dl, tb = (e - p) / dl;
+					if (ta > tb) {
+						const double tmp = ta;
+						ta = tb, tb = tmp;
+					}
+					t0 = fmax(t0, ta), t1 = fmin(t1, tb);
+				}
 			}
-			if (dq < 0.0) w1 = -w1;
-			Pose base{tr, Q4{w0 * A[3] + w1 * B[3], w0 * A[4] + w1 * B[4], w0 * A[5] + w1 * B[5], w0 * A[6] + w1 * B[6]}};
-			if (n_steps == 0) base.q = Q4{A[3], A[4], A[5], A[6]};
-			if (!isfinite(base.q.x + base.q.y + base.q.z + base.q.w)) continue;
-			double jv[MGODPL_MAX_JOINT_VALUES];
-			// RobotState.cpp:19-21 — joints lerp as a (1-t) + b t
-			for (int k = 0; k < rb.n_vars; ++k) jv[k] = n_steps ? A[7 + k] * (1 - t) + B[7 + k] * t : A[7 + k];
-			expand_state(sc, rb, Q, res, base, jv, (unsigned) motion, (unsigned) step, lc);
+			if (!empty && t0 <= t1) {
+				const double lo = floor(t0 * (double) n_steps) - 1.0, hi = ceil(t1 * (double) n_steps) + 1.0;
+				s_lo = (unsigned) fmax(lo, 0.0);
+				const unsigned s_hi = (unsigned) fmin(hi, (double) n_steps);
+				len = s_hi - s_lo + 1;
+			}
+		}
+		// cooperative append: for every lane with a non-empty range, the whole warp writes its (motion, step) pairs
+		unsigned todo = __ballot_sync(0xffffffffu, len > 0);
+		while (todo) {
+			const int src = __ffs(todo) - 1;
+			todo &= todo - 1;
+			const unsigned l = __shfl_sync(0xffffffffu, len, src), lo = __shfl_sync(0xffffffffu, s_lo, src);
+			const unsigned mot = (unsigned) (i - lane + src), ns = __shfl_sync(0xffffffffu, n_steps, src);
+			unsigned base = 0;
+			if (lane == 0) base = atomicAdd(S.count, l);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			for (unsigned k = lane; k < l; k += 32) {
+				if (base + k < S.cap) S.entries[base + k] = make_uint2(mot, lo + k);
+				else expand_motion_step(sc, rb, Q, res, a + (size_t) mot * stride, b + (size_t) mot * stride, ns, mot, lo + k, lc);
+			}
 		}
 	}
 	flush_counters(sc, lc);
-	if (sc.counters && lane == 0) {
+	if (sc.counters) {
 		if (n_motions) atomicAdd(sc.counters + CNT_MOTIONS, n_motions);
 		if (n_uncertain) atomicAdd(sc.counters + CNT_UNCERTAIN, n_uncertain);
 	}
+}
+
+/// A2 for motions: one thread per surviving (motion, step).
+__global__ void __launch_bounds__(BLOCK_A)
+k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
+					  const double *__restrict__ b, size_t stride, const uint32_t *__restrict__ n_steps, SurvivorsDev S,
+					  QueueDev Q, Results res) {
+	LocalCounters lc;
+	const unsigned n = min(__ldcg(S.count), S.cap);
+	for (unsigned k = blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
+		const uint2 e = __ldcg(&S.entries[k]);
+		expand_motion_step(sc, rb, Q, res, a + (size_t) e.x * stride, b + (size_t) e.x * stride, __ldg(n_steps + e.x), e.x, e.y, lc);
+	}
+	flush_counters(sc, lc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -356,12 +443,16 @@ k_expand_motions(const __grid_constant__ SceneDev sc, const __grid_constant__ Ro
 // of the tree): measured 3.6 active threads per instruction; this loop keeps most lanes busy.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr unsigned QUEUE_CHUNK = 64;    // items a warp claims per cursor atomic
-constexpr int REFILL_MIN = 8;           // idle lanes that trigger a refill
-constexpr int DESCEND_MIN = 20;         // leave the descend loop when fewer lanes than this are still walking
+struct TraverseTuning {
+	int refill_min;   // idle lanes that trigger a refill
+	int descend_min;  // leave the descend loop when fewer lanes than this are still walking
+};
 
-__global__ void __launch_bounds__(BLOCK_B, 4)
+template<int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK_B, MIN_BLOCKS)
 k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ explicit_boxes,
-		   QueueDev Q, Results res) {
+		   QueueDev Q, Results res, TraverseTuning tune) {
+	const int REFILL_MIN = tune.refill_min, DESCEND_MIN = tune.descend_min;
 	constexpr unsigned FULL = 0xffffffffu, END = 0xffffffffu;
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned n_items = min(__ldcg(Q.count), Q.cap);
@@ -541,18 +632,31 @@ static unsigned grid_for(size_t work_items, int block, int blocks_per_sm) {
 	return (unsigned) (blocks < cap ? (blocks ? blocks : 1) : cap);
 }
 
-size_t query_scratch_bytes(size_t worst_case_boxes) {
+size_t query_scratch_bytes(size_t worst_case_boxes, size_t survivor_entries) {
 	size_t cap = worst_case_boxes < QUEUE_MAX_ITEMS ? worst_case_boxes : QUEUE_MAX_ITEMS;
-	return 256 + (cap ? cap : 1) * sizeof(Item);
+	size_t scap = survivor_entries < SURVIVOR_MAX_ENTRIES ? survivor_entries : SURVIVOR_MAX_ENTRIES;
+	return 256 + ((scap * sizeof(uint2) + 255) & ~(size_t) 255) + (cap ? cap : 1) * sizeof(Item);
 }
 
+/// Scratch layout: [256 B header: queue count, queue cursor, survivor count][survivor entries][queue items].
+static void carve(void *scratch, size_t scratch_bytes, size_t survivor_entries, SurvivorsDev *S, QueueDev *Q) {
+	char *p = reinterpret_cast<char *>(scratch);
+	Q->count = reinterpret_cast<unsigned *>(p);
+	Q->cursor = Q->count + 1;
+	size_t scap = survivor_entries < SURVIVOR_MAX_ENTRIES ? survivor_entries : SURVIVOR_MAX_ENTRIES;
+	size_t sbytes = (scap * sizeof(uint2) + 255) & ~(size_t) 255;
+	if (S) {
+		S->count = Q->count + 2;
+		S->entries = reinterpret_cast<uint2 *>(p + 256);
+		S->cap = (unsigned) scap;
+	}
+	Q->items = reinterpret_cast<Item *>(p + 256 + sbytes);
+	size_t cap = scratch_bytes > 256 + sbytes ? (scratch_bytes - 256 - sbytes) / sizeof(Item) : 0;
+	Q->cap = (unsigned) (cap < QUEUE_MAX_ITEMS ? cap : QUEUE_MAX_ITEMS);
+}
 static QueueDev carve_queue(void *scratch, size_t scratch_bytes) {
 	QueueDev Q;
-	Q.count = reinterpret_cast<unsigned *>(scratch);
-	Q.cursor = Q.count + 1;
-	Q.items = reinterpret_cast<Item *>(reinterpret_cast<char *>(scratch) + 256);
-	size_t cap = scratch_bytes > 256 ? (scratch_bytes - 256) / sizeof(Item) : 0;
-	Q.cap = (unsigned) (cap < QUEUE_MAX_ITEMS ? cap : QUEUE_MAX_ITEMS);
+	carve(scratch, scratch_bytes, 0, nullptr, &Q);
 	return Q;
 }
 
@@ -565,18 +669,36 @@ static QueueDev carve_queue(void *scratch, size_t scratch_bytes) {
 static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const double *explicit_boxes, const QueueDev &Q,
 								const Results &res, size_t worst_case_items, cudaStream_t stream) {
 	size_t bound = worst_case_items < Q.cap ? worst_case_items : Q.cap;
-	k_traverse<<<grid_for(bound, BLOCK_B, 4), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res);
+	static int min_blocks = 0;
+	static TraverseTuning tune{8, 20};
+	if (!min_blocks) {
+		const char *e = getenv("MGODPL_TRAVERSE_BLOCKS");
+		min_blocks = e ? atoi(e) : 4;
+		if ((e = getenv("MGODPL_REFILL_MIN"))) tune.refill_min = atoi(e);
+		if ((e = getenv("MGODPL_DESCEND_MIN"))) tune.descend_min = atoi(e);
+	}
+	switch (min_blocks) {
+		case 8: k_traverse<8><<<grid_for(bound, BLOCK_B, 8), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune); break;
+		case 6: k_traverse<6><<<grid_for(bound, BLOCK_B, 6), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune); break;
+		case 5: k_traverse<5><<<grid_for(bound, BLOCK_B, 5), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune); break;
+		default: k_traverse<4><<<grid_for(bound, BLOCK_B, 4), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune); break;
+	}
 	return cudaGetLastError();
 }
 
 cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const double *d_states, size_t n, size_t stride,
 								uint32_t *d_hit_bits, void *scratch, size_t scratch_bytes, cudaStream_t stream) {
 	if (!n) return cudaSuccess;
-	QueueDev Q = carve_queue(scratch, scratch_bytes);
+	SurvivorsDev S;
+	QueueDev Q;
+	carve(scratch, scratch_bytes, n, &S, &Q);
+	if (S.cap < n) return cudaErrorInvalidValue;  // callers split batches at SURVIVOR_MAX_ENTRIES
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
-	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 2 * sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 4 * sizeof(unsigned), stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
-	k_expand_states<<<grid_for(n, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_states, n, stride, Q, res);
+	k_cull_states<<<grid_for(n, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_states, n, stride, S);
+	LQ_CHECK(cudaGetLastError());
+	k_expand_states<<<grid_for(n, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_states, stride, S, Q, res);
 	LQ_CHECK(cudaGetLastError());
 	return run_traverse(sc, rb, nullptr, Q, res, n * (size_t) rb.n_boxes, stream);
 }
@@ -587,7 +709,7 @@ cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t
 	QueueDev Q = carve_queue(scratch, scratch_bytes);
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	RobotDev none{};
-	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 2 * sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 4 * sizeof(unsigned), stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
 	k_expand_boxes<<<grid_for(n, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, d_boxes, n, Q, res);
 	LQ_CHECK(cudaGetLastError());
@@ -597,15 +719,19 @@ cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t
 cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const double *d_a, const double *d_b, size_t m,
 								 size_t stride, int js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,
 								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned *d_first_step,
-								 void *scratch, size_t scratch_bytes, cudaStream_t stream) {
+								 void *scratch, size_t scratch_bytes, size_t survivor_entries, cudaStream_t stream) {
 	if (!m) return cudaSuccess;
-	QueueDev Q = carve_queue(scratch, scratch_bytes);
+	SurvivorsDev S;
+	QueueDev Q;
+	carve(scratch, scratch_bytes, survivor_entries, &S, &Q);
 	Results res{RESULT_FIRST_STEP, nullptr, d_first_step};
-	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 2 * sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 4 * sizeof(unsigned), stream));
 	LQ_CHECK(cudaMemsetAsync(d_first_step, 0xff, m * sizeof(unsigned), stream));
 	if (d_uncertain) LQ_CHECK(cudaMemsetAsync(d_uncertain, 0, ((m + 31) / 32) * 4, stream));
-	k_expand_motions<<<grid_for(m * 32, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
-																		   d_n_steps, d_uncertain, Q, res);
+	k_motion_ranges<<<grid_for(m, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
+																	  d_n_steps, d_uncertain, S, Q, res);
+	LQ_CHECK(cudaGetLastError());
+	k_expand_motion_steps<<<grid_for(S.cap, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, S, Q, res);
 	LQ_CHECK(cudaGetLastError());
 	LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (size_t) Q.cap, stream));
 	k_finish_motions<<<(unsigned) ((m + 255) / 256), 256, 0, stream>>>(d_first_step, d_n_steps, m, d_hit_bits, d_toi);
@@ -620,7 +746,7 @@ cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const do
 	QueueDev Q = carve_queue(scratch, scratch_bytes);
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	const size_t wpr = (s + 31) / 32;
-	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 2 * sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 4 * sizeof(unsigned), stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, f * wpr * 4, stream));
 	k_expand_goals<<<grid_for(f * s, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_targets, f, s, d_draws, d_limits, seed,
 																		distance_from_target, d_states_out, Q, res);
