@@ -156,7 +156,6 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 	*out = nullptr;
 	if ((nv && !verts) || (nt && !tris32 && !tris64)) return fail(MGODPL_E_INVALID_ARGUMENT, "null mesh pointer");
 	if (nt > (1u << 27)) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^27 triangles");
-	if (int rc = require_device()) return rc;
 	// Validate indices and gather the bounds of the vertices the triangles actually use (host, one pass).
 	std::vector<uint32_t> idx(nt * 3);
 	double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -171,6 +170,7 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 		}
 	}
 	if (!nt) lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0.0;
+	if (int rc = require_device()) return rc;
 	auto sc = std::make_unique<mgodpl_scene>();
 	double origin[3], max_abs = 0.0;
 	for (int a = 0; a < 3; ++a) {

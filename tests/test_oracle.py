@@ -1,0 +1,242 @@
+"""CPU tests of the oracle: known-answer vectors, the committed golden fixtures generated from
+the reference's own sources, and — when oracle/_ref is present — a live cross-check against those sources."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.json")
+
+
+def unhex(xs, shape=None):
+    a = np.array([float.fromhex(x) for x in xs])
+    return a.reshape(shape) if shape else a
+
+
+def yaw_q(yaw):
+    return [0.0, 0.0, np.sin(yaw / 2), np.cos(yaw / 2)]
+
+
+# ---- Appendix B known-answer vectors ------------------------------------------------------------------------------
+def test_kat_fk_default_robot(oracle):
+    r = oracle.Robot(0.75, (0,))
+    fk = r.fk([1, 2, 3, *yaw_q(0.5), 0.3])
+    want = np.array([[1, 2, 3, 0, 0, 0.24740395925452294, 0.9689124217106447],
+                     [0.732360125711425, 2.4899115037259008, 3.110820077498002, 0.14479246283091116,
+                      0.036971585637570345, 0.2446258794777393, 0.9580325796404553],
+                     [0.5606053591436905, 2.804306495073727, 3.2216401549960043, 0.14479246283091116,
+                      0.036971585637570345, 0.2446258794777393, 0.9580325796404553]])
+    assert np.abs(fk - want).max() < 1e-12
+
+
+def test_kat_fk_one_metre_arm(oracle):
+    r = oracle.Robot(1.0, (0,))
+    fk = r.fk([-0.5, 0.25, 1.5, *yaw_q(2.0), -0.7])
+    want_t = np.array([[-0.5, 0.25, 1.5], [-1.029594001777892, 0.007627304342453123, 1.1778911563811545],
+                       [-1.3773285181906476, -0.15151602400566527, 0.855782312762309]])
+    want_q = np.array([-0.18526847604530977, -0.28853855572800713, 0.7904548817813493, 0.5075452428210487])
+    assert np.abs(fk[:, :3] - want_t).max() < 1e-12
+    assert np.abs(fk[1, 3:] - want_q).max() < 1e-12 and np.abs(fk[2, 3:] - want_q).max() < 1e-12
+
+
+def test_kat_fk_closed_form(oracle):
+    """stick centre = base.t + Rz(yaw) [(0,0.2,0) + Rx(theta) (0, l/2, 0)]; EE the same with l."""
+    rng = np.random.default_rng(0)
+    for arm in (0.5, 0.75, 1.0):
+        r = oracle.Robot(arm, (0,))
+        for _ in range(20):
+            t, yaw, th = rng.uniform(-3, 3, 3), rng.uniform(-np.pi, np.pi), rng.uniform(-1.5, 1.5)
+            fk = r.fk([*t, *yaw_q(yaw), th])
+            Rz = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1]])
+            Rx = np.array([[1, 0, 0], [0, np.cos(th), -np.sin(th)], [0, np.sin(th), np.cos(th)]])
+            assert np.abs(fk[1, :3] - (t + Rz @ (np.array([0, 0.2, 0]) + Rx @ np.array([0, arm / 2, 0])))).max() < 1e-12
+            assert np.abs(fk[2, :3] - (t + Rz @ (np.array([0, 0.2, 0]) + Rx @ np.array([0, arm, 0])))).max() < 1e-12
+
+
+def test_kat_distance_and_steps(oracle):
+    a = [0, -3, 1, 0, 0, 0, 1, 0.1, 0.0]
+    b = [0.25, 3, 1.5, *yaw_q(1.03), -0.4, 0.2]
+    d = oracle.distance(a, b)
+    assert abs(d - 7.755985396596976) < 1e-12
+    assert oracle.motion_steps(d) == 78
+
+
+def test_kat_step_count_boundary(oracle):
+    """d / 0.1 == 77.0 exactly in fp64 — the step count must not tip over to 78."""
+    a = [0, 0, 0, 0, 0, 0, 1, 0.0, 0.0]
+    b = [6, 0, 0, *yaw_q(1.0), 0.5, 0.2]
+    assert oracle.angular_distance(a[3:7], b[3:7]) == 0.9999999999999999
+    assert oracle.motion_steps(oracle.distance(a, b)) == 77
+
+
+def test_kat_slerp(oracle):
+    q = oracle.slerp([0, 0, 0, 1], yaw_q(1.0), 0.25)
+    assert np.abs(q - np.array([0, 0, 0.12467473338522768, 0.992197667229329])).max() < 1e-12
+
+
+def test_transform_inverse_property(oracle):
+    """tf . tf^-1 ~ identity to 1e-6 on random transforms (the reference's test/math/Transform_test.cpp:16-65)."""
+    rng = np.random.default_rng(42)
+    for _ in range(100):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        tf = np.concatenate([rng.uniform(-10, 10, 3), q])
+        ident = oracle.tf_then(tf, oracle.tf_inverse(tf))
+        assert np.abs(ident[:3]).max() < 1e-6 and np.abs(np.abs(ident[6]) - 1) < 1e-6 and np.abs(ident[3:6]).max() < 1e-6
+
+
+# ---- narrow phase ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("gap", [1e-3, 1e-5, 1e-7, 0.0, -1e-7, -1e-5, -1e-3])
+def test_box_triangle_band_cases(oracle, gap):
+    """Axis-aligned unit box vs a triangle parallel to its +x face at signed distance `gap`."""
+    x = 0.5 + gap
+    hit, clearance = oracle.box_tri([0, 0, 0, 0, 0, 0, 1], [1, 1, 1], [x, -0.2, -0.2, x, 0.3, -0.1, x, 0.0, 0.25])
+    assert hit == (gap <= 0)
+    assert abs(clearance - gap) < 1e-12
+
+
+def test_box_triangle_clearance_vertex_and_edge_features(oracle):
+    # nearest features: box corner vs triangle vertex -> distance sqrt(3) * 0.1
+    hit, cl = oracle.box_tri([0, 0, 0, 0, 0, 0, 1], [1, 1, 1], [0.6, 0.6, 0.6, 1.6, 0.6, 0.6, 0.6, 1.6, 0.6])
+    assert not hit and abs(cl - np.sqrt(3) * 0.1) < 1e-12
+    # triangle piercing the box: overlapping, penetration depth positive
+    hit, cl = oracle.box_tri([0, 0, 0, 0, 0, 0, 1], [1, 1, 1], [-2, 0, 0, 2, 0.1, 0, 0, 0, 2])
+    assert hit and cl < 0
+    # degenerate (zero-area) triangle = a segment through the box
+    hit, _ = oracle.box_tri([0, 0, 0, 0, 0, 0, 1], [1, 1, 1], [-2, 0, 0, 2, 0, 0, 0, 0, 0])
+    assert hit
+
+
+def test_sat_against_brute_force_distance(oracle):
+    """SAT boolean vs an independent check: sampled points of the triangle inside the box => must report a hit."""
+    rng = np.random.default_rng(1)
+    for _ in range(300):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        tf = np.concatenate([rng.uniform(-1, 1, 3), q])
+        size = rng.uniform(0.05, 1.0, 3)
+        tri = rng.uniform(-1.5, 1.5, 9)
+        hit, cl = oracle.box_tri(tf, size, tri)
+        # sample barycentric points, transform into the box frame with the oracle's own transform inverse
+        inv = oracle.tf_inverse(tf)
+        w = rng.dirichlet([1, 1, 1], 400)
+        pts = w @ tri.reshape(3, 3)
+        local = np.array([oracle.tf_then(inv, np.concatenate([p, [0, 0, 0, 1]]))[:3] for p in pts[:40]])
+        inside = (np.abs(local) <= size / 2).all(axis=1).any()
+        if inside:
+            assert hit
+        assert (cl <= 0) == hit
+
+
+# ---- golden fixtures generated from the reference's own sources ------------------------------------------------------
+@pytest.fixture(scope="module")
+def golden():
+    with open(GOLDEN) as f:
+        return json.load(f)
+
+
+def test_golden_fk_distance_interpolate(oracle, golden):
+    for e in golden["robots"]:
+        r = oracle.Robot(e["arm_length"], tuple(e["joint_types"]))
+        assert (r.n_links, r.n_joints) == (e["n_links"], e["n_joints"])
+        states = unhex(e["states"], e["states_shape"])
+        # generateUniformRandomState with std::mt19937(42): bit for bit
+        assert np.array_equal(oracle.gen_uniform_states(r, len(states), seed=42), states)
+        fk = unhex(e["fk"], e["fk_shape"])
+        assert np.array_equal(np.stack([r.fk(s) for s in states]), fk)
+        a, b = states[:12], states[12:]
+        assert np.array_equal(np.array([oracle.distance(x, y) for x, y in zip(a, b)]), unhex(e["distance"]))
+        interp = unhex(e["interp"], e["interp_shape"])
+        got = np.stack([[oracle.interpolate(x, y, t) for t in e["interp_t"]] for x, y in zip(a, b)])
+        assert np.array_equal(got, interp)
+        assert np.array_equal(oracle.gen_goal_states(r, e["goal_target"], e["goal_shape"][0], seed=42),
+                              unhex(e["goal_states"], e["goal_shape"]))
+        assert np.array_equal(oracle.gen_goal_states(r, e["goal_target"], e["goal_dist_shape"][0], seed=7, distance_from_target=0.15),
+                              unhex(e["goal_states_dist"], e["goal_dist_shape"]))
+        if "ee_vec_in" in e:
+            pv = unhex(e["ee_vec_in"], (2, 6))
+            got = np.stack([oracle.from_ee_and_vector(r, x[:3], x[3:]) for x in pv])
+            assert np.array_equal(got, unhex(e["ee_vec_out"], (2, 8)))
+
+
+def test_golden_scene_checks(oracle, golden, mg):
+    g = golden["scene"]
+    tree = mg.scenes.make_tree(**g["tree"])
+    mesh = tree.trunk_mesh
+    assert mesh.n_triangles == g["n_triangles"] and float(mesh.vertices.sum()).hex() == g["mesh_checksum"], \
+        "synthetic tree generator changed: regenerate tests/golden with make_golden.py"
+    r = oracle.Robot(g["robot"][0], tuple(g["robot"][1]))
+    s = oracle.Scene(mesh.vertices, mesh.triangles)
+    st = oracle.gen_uniform_states(r, g["n_states"], seed=g["states_seed"], h_range=g["h_range"], v_range=g["v_range"])
+    hits = s.check_states(r, st)
+    assert "".join("1" if h else "0" for h in hits) == g["state_hits"]
+    res = s.check_motions(r, st[:100], st[100:200])
+    assert "".join("1" if h else "0" for h in res["hit"]) == g["motion_hits"]
+    toi = unhex(g["motion_toi"])
+    assert np.array_equal(np.nan_to_num(res["toi"], nan=-1.0), toi)
+    path = unhex(g["path"], g["path_shape"])
+    assert s.check_path(r, path) == g["path_first_colliding_segment"] == 2
+
+
+# ---- live cross-check against the reference's own sources (present in the build container and, prebuilt, on the box) --
+def test_oracle_matches_reference_sources_live(oracle, mg):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference); the committed golden fixtures cover this")
+    rng = np.random.default_rng(3)
+    for arm, jt in [(1.0, (0,)), (0.75, (1,)), (1.0, (0, 1)), (0.9, (1, 1, 0))]:
+        r, rr = oracle.Robot(arm, jt), oracle.RefRobot(arm, jt)
+        a = oracle.gen_uniform_states(r, 200, seed=9)
+        assert np.array_equal(a, oracle.ref_gen_uniform_states(rr, 200, seed=9))
+        for s in a[:50]:
+            assert np.array_equal(r.fk(s), rr.fk(s))
+        for x, y in zip(a[:100], a[100:]):
+            assert oracle.distance(x, y) == oracle.ref_distance(x, y)
+            t = rng.uniform()
+            assert np.array_equal(oracle.interpolate(x, y, t), oracle.ref_interpolate(x, y, t))
+    tree = mg.scenes.make_tree(seed=2, trunk_triangles=2000, leaf_triangles=1000, n_fruit=2)
+    mesh = tree.collision_mesh(True)
+    r, rr = oracle.Robot(1.0, (0,)), oracle.RefRobot(1.0, (0,))
+    s, rs = oracle.Scene(mesh.vertices, mesh.triangles), oracle.RefScene(mesh.vertices, mesh.triangles)
+    st = oracle.gen_uniform_states(r, 600, seed=1, h_range=2.0, v_range=3.0)
+    assert np.array_equal(s.check_states(r, st), rs.check_states(rr, st))
+    res = s.check_motions(r, st[:300], st[300:])
+    rh, rt = rs.check_motions(rr, st[:300], st[300:])
+    assert np.array_equal(res["hit"], rh)
+    assert np.array_equal(np.nan_to_num(res["toi"], nan=-1), np.nan_to_num(rt, nan=-1))
+
+
+# ---- properties inherited from the reference's legacy tests ------------------------------------------------------------
+def test_motion_check_symmetry(oracle, mg):
+    """check(s1, s2) == check(s2, s1) (src_old/test/collision_checking_test.cpp:30-57)."""
+    tree = mg.scenes.make_tree(seed=4, trunk_triangles=3000, leaf_triangles=0, n_fruit=2)
+    r = oracle.Robot(0.75, (0,))
+    s = oracle.Scene(tree.trunk_mesh.vertices, tree.trunk_mesh.triangles)
+    st = oracle.gen_uniform_states(r, 400, seed=5, h_range=2.5, v_range=3.0)
+    fwd = s.check_motions(r, st[:200], st[200:])["hit"]
+    bwd = s.check_motions(r, st[200:], st[:200])["hit"]
+    # sample positions differ between the two directions only by rounding; disagreement needs a grazing contact
+    assert (fwd != bwd).sum() <= 1
+
+
+def test_trunk_fly_through_hits_mid_segment(oracle, mg):
+    """Base from (0,-10,1) to (0,10,1) must collide around t = 0.5 (test/planning/MyCollisionEnvTest.cpp:24-76)."""
+    tree = mg.scenes.make_tree(seed=4, trunk_triangles=3000, leaf_triangles=0, n_fruit=2)
+    r = oracle.Robot(0.75, (0,))
+    s = oracle.Scene(tree.trunk_mesh.vertices, tree.trunk_mesh.triangles)
+    a = np.array([[0, -10, 1, 0, 0, 0, 1, 0, 0.0]])
+    b = np.array([[0, 10, 1, 0, 0, 0, 1, 0, 0.0]])
+    res = s.check_motions(r, a, b)
+    assert res["hit"][0] and abs(res["toi"][0] - 0.5) < 0.2
+    far = np.array([[0, -10, 1, 0, 0, 0, 1, 0, 0.0]])
+    assert not s.check_states(r, far)[0]
+    assert s.check_states(r, np.array([[0, 0, 1, 0, 0, 0, 1, 0, 0.0]]))[0]
+
+
+def test_degenerate_motion_checks_start_state_once(oracle, mg):
+    tree = mg.scenes.make_tree(seed=4, trunk_triangles=3000, leaf_triangles=0, n_fruit=2)
+    r = oracle.Robot(0.75, (0,))
+    s = oracle.Scene(tree.trunk_mesh.vertices, tree.trunk_mesh.triangles)
+    inside = np.array([[0, 0, 1, 0, 0, 0, 1, 0, 0.0]])
+    res = s.check_motions(r, inside, inside)
+    assert res["n_steps"][0] == 0 and res["states_checked"][0] == 1 and res["hit"][0] and res["toi"][0] == 0.0
