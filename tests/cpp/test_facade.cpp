@@ -1,0 +1,252 @@
+// C++ tests of the host-side facade (multigoal-orchard-drone-planning-library_b200/host/mgodpl.hpp): the reference's
+// planning-layer API running on the CUDA library, checked against the fp64 oracle (oracle/mgodpl_oracle.hpp — test
+// infrastructure).  Modelled on the reference's own test style: seeded randomised properties
+// (test/math/Transform_test.cpp:16-65) and the legacy collision tests (test/planning/MyCollisionEnvTest.cpp:13-78,
+// src_old/test/collision_checking_test.cpp:30-57).  Needs a CUDA device; run by tests/test_gpu_facade.py.
+#include <cstdio>
+#include <thread>
+
+#include "../../multigoal-orchard-drone-planning-library_b200/host/mgodpl.hpp"
+#include "../../oracle/mgodpl_oracle.hpp"
+
+using namespace mgodpl;
+
+static int g_failed = 0, g_checked = 0;
+#define CHECK(cond)                                                        \
+	do {                                                                   \
+		++g_checked;                                                       \
+		if (!(cond)) {                                                     \
+			++g_failed;                                                    \
+			std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+		}                                                                  \
+	} while (0)
+
+// ---- a small procedural tree: trunk + a few branches as triangulated tubes ---------------------------------------------
+static void add_tube(Mesh &m, math::Vec3d a, math::Vec3d b, double r0, double r1, int sides, int segs) {
+	math::Vec3d d = (b - a).normalized();
+	math::Vec3d u = std::fabs(d.x()) < 0.9 ? math::Vec3d{1, 0, 0} : math::Vec3d{0, 1, 0};
+	math::Vec3d e1{d.y() * u.z() - d.z() * u.y(), d.z() * u.x() - d.x() * u.z(), d.x() * u.y() - d.y() * u.x()};
+	e1 = e1.normalized();
+	math::Vec3d e2{d.y() * e1.z() - d.z() * e1.y(), d.z() * e1.x() - d.x() * e1.z(), d.x() * e1.y() - d.y() * e1.x()};
+	size_t base = m.vertices.size();
+	for (int s = 0; s <= segs; ++s) {
+		double t = (double) s / segs, r = r0 + (r1 - r0) * t;
+		math::Vec3d c = a + (b - a) * t;
+		for (int k = 0; k < sides; ++k) {
+			double ang = 2 * M_PI * k / sides;
+			m.vertices.push_back(c + e1 * (r * std::cos(ang)) + e2 * (r * std::sin(ang)));
+		}
+	}
+	for (int s = 0; s < segs; ++s)
+		for (int k = 0; k < sides; ++k) {
+			size_t i0 = base + s * sides + k, i1 = base + s * sides + (k + 1) % sides, j0 = i0 + sides, j1 = i1 + sides;
+			m.triangles.push_back({i0, i1, j0});
+			m.triangles.push_back({i1, j1, j0});
+		}
+}
+static Mesh make_tree() {
+	Mesh m;
+	add_tube(m, {0, 0, 0}, {0, 0, 1.6}, 0.12, 0.08, 10, 24);
+	random_numbers::RandomNumberGenerator rng(7);
+	for (int i = 0; i < 14; ++i) {
+		double az = rng.uniformReal(0, 2 * M_PI), el = rng.uniformReal(0.2, 1.1), len = rng.uniformReal(0.6, 1.3), z = rng.uniformReal(0.9, 1.6);
+		math::Vec3d dir{std::cos(az) * std::cos(el), std::sin(az) * std::cos(el), std::sin(el)};
+		add_tube(m, {0, 0, z}, math::Vec3d{0, 0, z} + dir * len, 0.05, 0.015, 6, 16);
+	}
+	return m;
+}
+
+// ---- oracle twins ---------------------------------------------------------------------------------------------------------
+static orc::State to_orc(const RobotState &s) {
+	orc::State o;
+	o.base = {{s.base_tf.translation.x(), s.base_tf.translation.y(), s.base_tf.translation.z()},
+			  {s.base_tf.orientation.x, s.base_tf.orientation.y, s.base_tf.orientation.z, s.base_tf.orientation.w}};
+	o.joints = s.joint_values;
+	return o;
+}
+static orc::Scene orc_scene(const Mesh &m) {
+	std::vector<double> v;
+	std::vector<uint32_t> t;
+	for (auto &p: m.vertices) v.insert(v.end(), {p.x(), p.y(), p.z()});
+	for (auto &tr: m.triangles) t.insert(t.end(), {(uint32_t) tr[0], (uint32_t) tr[1], (uint32_t) tr[2]});
+	return orc::Scene(v.data(), m.vertices.size(), t.data(), m.triangles.size());
+}
+static RobotState base_at(double x, double y, double z) { return {{{x, y, z}, {0, 0, 0, 1}}, {0.0, 0.0}}; }
+
+int main() {
+	if (mgodpl_device_count() <= 0) {
+		std::printf("no CUDA device: the facade has no CPU fallback\n");
+		return 2;
+	}
+	const Mesh tree = make_tree();
+	const gpu::Scene scene = gpu::meshToScene(tree);  // was: fcl_utils::meshToFclBVH(tree)
+	const orc::Scene oscene = orc_scene(tree);
+	const auto robot = experiments::createProceduralRobotModel();
+	const orc::Robot orobot = orc::procedural_robot(0.75, {0});
+	const auto flying_base = robot.findLinkByName("flying_base"), end_effector = robot.findLinkByName("end_effector");
+	CHECK(scene.info().n_triangles == tree.triangles.size());
+
+	// -- host FK of the facade equals the oracle's restatement bit for bit ------------------------------------------------
+	{
+		random_numbers::RandomNumberGenerator rng(42);
+		for (int i = 0; i < 100; ++i) {
+			RobotState s = generateUniformRandomState(robot, rng);
+			auto fk = robot_model::forwardKinematics(robot, s, flying_base);
+			orc::State os = to_orc(s);
+			auto ofk = orc::forward_kinematics(orobot, os.joints.data(), 0, os.base);
+			for (size_t l = 0; l < fk.link_transforms.size(); ++l)
+				CHECK(fk.link_transforms[l].translation.x() == ofk[l].t.x && fk.link_transforms[l].orientation.w == ofk[l].q.w);
+		}
+	}
+	// -- trunk fly-through (MyCollisionEnvTest.cpp:24-76) -------------------------------------------------------------------
+	{
+		CHECK(!check_robot_collision(robot, scene, base_at(0, -10, 1)));
+		CHECK(check_robot_collision(robot, scene, base_at(0, 0, 1)));
+		CHECK(!check_robot_collision(robot, scene, base_at(0, 10, 1)));
+		double toi = -1;
+		CHECK(check_motion_collides(robot, scene, base_at(0, -10, 1), base_at(0, 10, 1), toi));
+		CHECK(std::fabs(toi - 0.5) < 0.2);
+		CHECK(!check_motion_collides(robot, scene, base_at(5, -10, 1), base_at(5, 10, 1)));
+		RobotPath path;
+		for (double y: {-10.0, -6.0, -3.0, 3.0, 10.0}) path.append(base_at(0, y, 1));
+		PathPoint pt{};
+		CHECK(check_path_collides(robot, scene, path, pt) && pt.segment_i == 2);
+		RobotPath clear;
+		for (double y: {-10.0, -6.0, -3.0}) clear.append(base_at(4, y, 1));
+		CHECK(!check_path_collides(robot, scene, clear));
+	}
+	// -- randomised single + batched state checks against the oracle, with band accounting --------------------------------
+	{
+		random_numbers::RandomNumberGenerator rng(42);
+		std::vector<RobotState> states;
+		for (int i = 0; i < 20000; ++i) states.push_back(generateUniformRandomState(robot, rng, 2.0, 3.0));
+		auto bits = check_states(robot, scene, states);
+		size_t mismatch_outside = 0, in_band = 0, hits = 0;
+		for (size_t i = 0; i < states.size(); ++i) {
+			const orc::State os = to_orc(states[i]);
+			const bool want = orc::check_robot_collision(orobot, oscene, os);
+			hits += want;
+			if (bit(bits, i) != want) {
+				const double cl = orc::robot_clearance(orobot, oscene, os, 1e-3);
+				if (std::fabs(cl) > 1e-6) ++mismatch_outside;
+				else ++in_band;
+			}
+		}
+		std::printf("states: %zu / %zu collide, mismatches outside band %zu, inside %zu\n", hits, states.size(), mismatch_outside, in_band);
+		CHECK(mismatch_outside == 0);
+		CHECK(hits > 1000 && hits < 19000);
+		for (size_t i = 0; i < 200; ++i) CHECK(check_robot_collision(robot, scene, states[i]) == bit(bits, i));
+		// per-link entry point
+		auto fk = robot_model::forwardKinematics(robot, states[5], flying_base);
+		bool any = false;
+		for (size_t l = 0; l < fk.link_transforms.size(); ++l) any |= check_link_collision(robot.getLinks()[l], scene, fk.link_transforms[l]);
+		CHECK(any == bit(bits, 5));
+	}
+	// -- motions: boolean, toi and step count equal the oracle's loop -----------------------------------------------------
+	{
+		random_numbers::RandomNumberGenerator rng(43);
+		std::vector<RobotState> a, b;
+		for (int i = 0; i < 3000; ++i) a.push_back(generateUniformRandomState(robot, rng, 3.0, 4.0)), b.push_back(generateUniformRandomState(robot, rng, 3.0, 4.0));
+		MotionResults r = check_motions(robot, scene, a.data(), b.data(), a.size());
+		size_t bad = 0, hits = 0;
+		for (size_t i = 0; i < a.size(); ++i) {
+			orc::MotionResult want = orc::check_motion_collides(orobot, oscene, to_orc(a[i]), to_orc(b[i]));
+			hits += want.hit;
+			if (want.n_steps != r.n_steps[i]) ++bad;
+			if (want.hit != bit(r.hit_bits, i) || (want.hit && want.toi != r.toi[i])) ++bad;  // grazing cases would show up here
+		}
+		std::printf("motions: %zu / %zu collide, %zu disagreements\n", hits, a.size(), bad);
+		CHECK(bad == 0);
+		double toi = -1;
+		for (size_t i = 0; i < 50; ++i) {
+			bool h = check_motion_collides(robot, scene, a[i], b[i], toi);
+			CHECK(h == bit(r.hit_bits, i));
+			if (h) CHECK(toi == r.toi[i]);
+		}
+		// symmetry property (src_old/test/collision_checking_test.cpp:30-57)
+		MotionResults rev = check_motions(robot, scene, b.data(), a.data(), a.size());
+		size_t asym = 0;
+		for (size_t i = 0; i < a.size(); ++i) asym += bit(r.hit_bits, i) != bit(rev.hit_bits, i);
+		CHECK(asym <= 2);
+	}
+	// -- the functional plug API + counting decorators ----------------------------------------------------------------------
+	{
+		CollisionEnvironment env{robot, scene};
+		CollisionFunctions fns = collision_functions_in_environment(env);
+		calls_t n_state = 0, n_motion = 0;
+		CollisionFunctions counted = collision_functions_in_environment_counting(fns, {n_state, n_motion});
+		CHECK(counted.state_collides(base_at(0, 0, 1)));
+		CHECK(!counted.state_collides(base_at(0, 9, 1)));
+		CHECK(counted.motion_collides(base_at(0, -10, 1), base_at(0, 10, 1)));
+		CHECK(n_state == 2 && n_motion == 1);
+		auto sampled = motion_collision_check_fn_from_state_collision(fns.state_collides);
+		CHECK(sampled(base_at(0, -10, 1), base_at(0, 10, 1)) && !sampled(base_at(5, -10, 1), base_at(5, 10, 1)));
+	}
+	// -- goal sampling: same result and same generator state as the reference's sequential loop ---------------------------
+	{
+		const math::Vec3d target{0.45, 0.3, 1.7};
+		random_numbers::RandomNumberGenerator rng(42), twin(42);
+		auto got = findGoalStateByUniformSampling(target, robot, flying_base, end_effector, scene, rng, 1000);
+		std::optional<RobotState> want;
+		for (int i = 0; i < 1000 && !want; ++i) {  // goal_sampling.cpp:90-96 with the oracle as collision check
+			RobotState s = genGoalStateUniform(twin, target, robot, flying_base, end_effector);
+			if (!orc::check_robot_collision(orobot, oscene, to_orc(s))) want = s;
+		}
+		CHECK(got.has_value() == want.has_value());
+		if (got && want) CHECK(*got == *want);
+		CHECK(rng.uniformReal(0, 1) == twin.uniformReal(0, 1));  // both generators consumed the same number of draws
+		auto ee = robot_model::forwardKinematics(robot, *got, flying_base).forLink(end_effector).translation;
+		CHECK((ee - target).norm() < 1e-12);
+
+		std::vector<math::Vec3d> targets{{0.45, 0.3, 1.7}, {-0.6, 0.2, 1.9}, {0.1, -0.7, 1.4}, {3.0, 3.0, 2.0}};
+		GoalSamples gs = sample_goal_states(robot, scene, targets, 1000, 42, 0.0, true);
+		for (size_t f = 0; f < targets.size(); ++f) {
+			random_numbers::RandomNumberGenerator r2(42);  // goal_sample_success_rate.cpp:121: fresh rng(42) per problem
+			uint32_t collisions = 0;
+			for (size_t s = 0; s < 1000; ++s) {
+				RobotState st = genGoalStateUniform(r2, targets[f], robot, flying_base, end_effector);
+				if (s < 5) CHECK((st.base_tf.translation - gs.states[f * 1000 + s].base_tf.translation).norm() < 1e-12);
+				collisions += orc::check_robot_collision(orobot, oscene, to_orc(st));
+			}
+			std::printf("goal target %zu: %u collisions (oracle %u)\n", f, gs.collisions[f], collisions);
+			CHECK(gs.collisions[f] == collisions);
+		}
+		CHECK(gs.collisions[3] == 0);  // a target far from the tree is always reachable
+	}
+	// -- error vocabulary -------------------------------------------------------------------------------------------------------
+	{
+		robot_model::RobotModel bad;
+		bad.insertLink({"flying_base", {}, {PositionedShape::untransformed(Mesh{})}, {}});
+		bool threw = false;
+		try {
+			check_robot_collision(bad, scene, base_at(0, 0, 1));
+		} catch (const std::runtime_error &e) { threw = std::string(e.what()).find("Only boxes are implemented") != std::string::npos; }
+		CHECK(threw);
+		robot_model::RobotModel nameless;
+		nameless.insertLink(robot_model::RobotModel::Link::namedBox("base", {1, 1, 1}));
+		threw = false;
+		try {
+			check_robot_collision(nameless, scene, base_at(0, 0, 1));
+		} catch (const std::runtime_error &e) { threw = std::string(e.what()) == "Link not found: flying_base"; }
+		CHECK(threw);
+	}
+	// -- concurrent callers on one shared scene (the reference runs this path from TBB workers) ---------------------------
+	{
+		std::vector<std::thread> pool;
+		std::vector<int> ok(6, 0);
+		for (int t = 0; t < 6; ++t)
+			pool.emplace_back([&, t] {
+				random_numbers::RandomNumberGenerator rng(100 + t);
+				int good = 0;
+				for (int i = 0; i < 150; ++i) {
+					RobotState s = generateUniformRandomState(robot, rng, 2.0, 3.0);
+					good += check_robot_collision(robot, scene, s) == orc::check_robot_collision(orobot, oscene, to_orc(s));
+				}
+				ok[t] = good;
+			});
+		for (auto &th: pool) th.join();
+		for (int t = 0; t < 6; ++t) CHECK(ok[t] >= 149);
+	}
+	std::printf("%d checks, %d failed\n", g_checked, g_failed);
+	return g_failed ? 1 : 0;
+}
