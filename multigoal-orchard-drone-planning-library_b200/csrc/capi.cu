@@ -1,5 +1,6 @@
 // C ABI of the collision-query path (include/mgodpl_b200.h): handle management, robot flattening, host-buffer
 // staging, and the host-side fix-up that keeps motion step counts bit-identical to the reference's libm.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -367,18 +368,27 @@ int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_
 	if (n_vars > MGODPL_MAX_JOINT_VALUES) return fail(MGODPL_E_UNSUPPORTED_ROBOT, "too many joint variables");
 	if (ee_link >= 0 && !visited[ee_link]) return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: end effector unreachable from root");
 
-	// Boxes, the links FK must reach for collision, and the reach radius of the whole robot.
+	// Boxes (sorted by the op that reaches their link, root first), the links FK must reach for collision, and the
+	// reach radius of the whole robot.
+	std::vector<int> link_rank(n_links, 0);  // order in which FK produces each link
+	for (int k = 0; k < d.n_ops; ++k) link_rank[d.ops[k].child] = k + 1;
+	// links the DFS never reaches keep the root transform (RobotModel.cpp:23-24): their boxes ride on the root link
+	std::vector<int> box_link(n_shapes);
+	for (int i = 0; i < n_shapes; ++i) box_link[i] = visited[shapes[i].link] ? shapes[i].link : root_link;
+	std::vector<int> order(n_shapes);
+	for (int i = 0; i < n_shapes; ++i) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return link_rank[box_link[x]] < link_rank[box_link[y]]; });
 	std::vector<char> needed(n_links, 0);
 	double reach = 0.0;
 	for (int i = 0; i < n_shapes; ++i) {
+		const mgodpl_shape_desc &sh = shapes[order[i]];
 		BoxDev &b = d.boxes[i];
-		b.link = shapes[i].link;
-		for (int a = 0; a < 3; ++a) b.half[a] = 0.5 * shapes[i].size[a];
-		HTf tf = load_tf(shapes[i].transform);
+		b.link = box_link[order[i]];
+		for (int a = 0; a < 3; ++a) b.half[a] = 0.5 * sh.size[a];
+		HTf tf = load_tf(sh.transform);
 		memcpy(b.t, tf.t, sizeof(tf.t)), memcpy(b.q, tf.q, sizeof(tf.q));
 		b.tf_identity = rot_is_identity(tf.q) && tf.t[0] == 0.0 && tf.t[1] == 0.0 && tf.t[2] == 0.0;
 		needed[b.link] = 1;
-		// unreachable links keep the root transform (RobotModel.cpp:23-24), so depth_reach 0 is right for them
 		reach = std::max(reach, depth_reach[b.link] + vnorm(tf.t) + vnorm(b.half));
 	}
 	d.reach = reach * (1.0 + 1e-9) + 1e-9;
@@ -387,6 +397,31 @@ int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_
 			d.ops[k].flags |= FK_FOR_COLLISION;
 			needed[d.ops[k].parent] = 1;
 		}
+	}
+	// Contiguous box range of every link (boxes are sorted by link).
+	auto range_of = [&](int link, int32_t *lo, int32_t *hi) {
+		*lo = n_shapes, *hi = 0;
+		for (int i = 0; i < n_shapes; ++i)
+			if (d.boxes[i].link == link) *lo = std::min(*lo, i), *hi = std::max(*hi, i + 1);
+		if (*hi == 0) *lo = 0;
+	};
+	range_of(root_link, &d.root_box_begin, &d.root_box_end);
+	for (int k = 0; k < d.n_ops; ++k) range_of(d.ops[k].child, &d.ops[k].box_begin, &d.ops[k].box_end);
+	// Register-resident FK: mark ops whose parent is the previous collision op's child, and children that must be stored.
+	{
+		int prev_child = root_link;
+		std::vector<int> executed;
+		for (int k = 0; k < d.n_ops; ++k)
+			if (d.ops[k].flags & FK_FOR_COLLISION) executed.push_back(k);
+		for (size_t e = 0; e < executed.size(); ++e) {
+			FkOp &op = d.ops[executed[e]];
+			if (op.parent == prev_child) op.flags |= FK_PARENT_IS_PREV;
+			prev_child = op.child;
+		}
+		for (size_t e = 0; e < executed.size(); ++e)
+			for (size_t f = e + 1; f < executed.size(); ++f)
+				if (d.ops[executed[f]].parent == d.ops[executed[e]].child && !(d.ops[executed[f]].flags & FK_PARENT_IS_PREV))
+					d.ops[executed[e]].flags |= FK_STORE;
 	}
 	// Joint limits for device-side goal sampling: one (min, max) per variable in variable order.
 	rb->limits.assign(2 * std::max(n_vars, 1), 0.0);
@@ -526,12 +561,12 @@ int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, 
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Carver c;
 	const size_t qb = motion_scratch_bytes(m, robot->dev.n_boxes);
-	size_t o_first = c.take(m * 4), o_steps = c.take(d_n_steps ? 0 : m * 4), o_q = c.take(qb);
+	size_t o_first = c.take(m * 4), o_steps = c.take(d_n_steps ? 0 : m * 4), o_slerp = c.take(m * 16), o_q = c.take(qb);
 	char *scratch = nullptr;
 	CU(scene->device_scratch(stream, c.off, &scratch));
 	CU(launch_check_motions(scene->dev, robot->dev, d_a, d_b, m, stride, js, max_step, d_override, d_hit_bits, d_toi,
 							d_n_steps ? d_n_steps : (uint32_t *) (scratch + o_steps), d_uncertain, (unsigned *) (scratch + o_first),
-							scratch + o_q, qb, motion_survivors(m), stream));
+							scratch + o_slerp, scratch + o_q, qb, motion_survivors(m), stream));
 	return MGODPL_OK;
 }
 
@@ -564,7 +599,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	Lease ws(scene->pool);
 	Carver c;
 	const size_t in_b = m * stride * 8, words = (m + 31) / 32, qb = motion_scratch_bytes(m, robot->dev.n_boxes);
-	size_t o_a = c.take(in_b), o_b = c.take(in_b), o_first = c.take(m * 4);
+	size_t o_a = c.take(in_b), o_b = c.take(in_b), o_first = c.take(m * 4), o_slerp = c.take(m * 16);
 	// outputs are contiguous so that one D2H copy brings them all back
 	size_t o_hit = c.take(words * 4), o_unc = c.take(words * 4), o_steps = c.take(m * 4), o_toi = c.take(toi ? m * 8 : 0);
 	const size_t out_lo = o_hit, out_hi = c.off;
@@ -577,7 +612,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	CU(cudaMemcpyAsync(D + o_b, b, in_b, cudaMemcpyHostToDevice, stream));
 	CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a), (const double *) (D + o_b), m, stride, js, max_step,
 							nullptr, (uint32_t *) (D + o_hit), toi ? (double *) (D + o_toi) : nullptr, (uint32_t *) (D + o_steps),
-							(uint32_t *) (D + o_unc), (unsigned *) (D + o_first), D + o_q, qb, motion_survivors(m), stream));
+							(uint32_t *) (D + o_unc), (unsigned *) (D + o_first), D + o_slerp, D + o_q, qb, motion_survivors(m), stream));
 	CU(cudaMemcpyAsync(H + out_lo, D + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, stream));
 	CU(cudaStreamSynchronize(stream));
 	// Step-count fix-up: the device libm may differ from the host's by an ulp, which only matters when distance /
@@ -604,7 +639,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a), (const double *) (D + o_b), m, stride, js,
 								max_step, (const uint32_t *) (D + o_ovr), (uint32_t *) (D + o_hit),
 								toi ? (double *) (D + o_toi) : nullptr, (uint32_t *) (D + o_steps), nullptr,
-								(unsigned *) (D + o_first), D + o_q, qb, motion_survivors(m), stream));
+								(unsigned *) (D + o_first), D + o_slerp, D + o_q, qb, motion_survivors(m), stream));
 		CU(cudaMemcpyAsync(H + out_lo, D + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, stream));
 		CU(cudaStreamSynchronize(stream));
 	}

@@ -38,6 +38,7 @@ struct FkOp {
 	int32_t parent, child;
 	int32_t var;          // index into joint values, -1 = no variable (fixed joint)
 	int32_t flags;        // FK_*
+	int32_t box_begin, box_end;  // RobotDev::boxes[box_begin, box_end) hang off `child`
 	double pre_t[3], pre_q[4];
 	double post_t[3], post_q[4];
 	double axis[3];
@@ -46,7 +47,10 @@ enum : int32_t {
 	FK_INVERT = 1,        // joint crossed from linkB: use the inverse rotation
 	FK_PRE_ROT_ID = 2,    // pre.q is exactly identity
 	FK_POST_ROT_ID = 4,   // post.q is exactly identity
-	FK_FOR_COLLISION = 8  // child (or something below it) carries collision geometry
+	FK_FOR_COLLISION = 8, // child (or something below it) carries collision geometry
+	FK_PARENT_IS_PREV = 16, // among the collision ops, the parent is the previous op's child (or the root for the first):
+	                        // the running pose stays in registers, no link table access
+	FK_STORE = 32         // a later, non-adjacent collision op uses this child as its parent: keep it in the link table
 };
 
 struct BoxDev {
@@ -59,6 +63,7 @@ struct BoxDev {
 struct RobotDev {
 	int32_t n_links, n_ops, n_boxes, n_vars;
 	int32_t root, ee;
+	int32_t root_box_begin, root_box_end;  // boxes of the root link (boxes are sorted by the op that reaches their link)
 	double reach;         // radius around the root link origin that contains every box for every joint value
 	FkOp ops[MGODPL_MAX_LINKS];
 	BoxDev boxes[MGODPL_MAX_BOXES];

@@ -93,12 +93,14 @@ __device__ __forceinline__ void finish_cull_box(const SceneDev &sc, CullBox &b, 
 }
 
 __device__ __forceinline__ CullBox make_cull_box(const SceneDev &sc, D3 c, Q4 q, const double *half) {
-	double R[9];
-	qmat(q, R);
 	CullBox b;
 	b.cx = (float) (c.x - sc.origin[0]), b.cy = (float) (c.y - sc.origin[1]), b.cz = (float) (c.z - sc.origin[2]);
-#pragma unroll
-	for (int i = 0; i < 9; ++i) b.r[i] = (float) R[i];
+	// fp32 rotation from the rounded quaternion: entries are good to ~3e-7, i.e. ~3e-6 m over a 10 m lever — the
+	// scene margin (>= 2e-5 m, growing with the extent) absorbs it; the exact test never uses this matrix.
+	const float x = (float) q.x, y = (float) q.y, z = (float) q.z, w = (float) q.w;
+	b.r[0] = 1.f - 2.f * (y * y + z * z), b.r[1] = 2.f * (x * y - z * w), b.r[2] = 2.f * (x * z + y * w);
+	b.r[3] = 2.f * (x * y + z * w), b.r[4] = 1.f - 2.f * (x * x + z * z), b.r[5] = 2.f * (y * z - x * w);
+	b.r[6] = 2.f * (x * z - y * w), b.r[7] = 2.f * (y * z + x * w), b.r[8] = 1.f - 2.f * (x * x + y * y);
 	finish_cull_box(sc, b, (float) half[0], (float) half[1], (float) half[2]);
 	return b;
 }

@@ -17,10 +17,11 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 								uint32_t *d_hit_bits, void *scratch, size_t scratch_bytes, cudaStream_t stream);
 cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t n, uint32_t *d_hit_bits, void *scratch,
 							   size_t scratch_bytes, cudaStream_t stream);
-/// d_n_steps and d_first_step (m x u32 each) are mandatory work buffers; d_toi / d_uncertain / d_override optional.
+/// d_n_steps, d_first_step (m x u32 each) and d_slerp (m x 16 B) are mandatory work buffers; d_toi / d_uncertain /
+/// d_override are optional.
 cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const double *d_a, const double *d_b, size_t m,
 								 size_t stride, int js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,
-								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned *d_first_step,
+								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned *d_first_step, void *d_slerp,
 								 void *scratch, size_t scratch_bytes, size_t survivor_entries, cudaStream_t stream);
 cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const double *d_targets, size_t f,
 								const double *d_draws, const double *d_limits, size_t s, unsigned long long seed,

@@ -156,21 +156,29 @@ __device__ __forceinline__ bool robot_out_of_reach(const SceneDev &sc, const Rob
 }
 
 /// FK for the links that carry collision geometry + one emit per box (check_robot_collision,
-/// collision_detection.cpp:57-80; check_link_collision :16-55).
+/// collision_detection.cpp:57-80; check_link_collision :16-55).  Ops run in the reference's DFS pop order; for chain
+/// robots (every procedural drone) the running pose stays in registers and the link table is never touched.
+__device__ __forceinline__ void emit_link_boxes(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
+												const Pose &link, int lo, int hi, unsigned owner, unsigned step, LocalCounters &lc) {
+	for (int bi = lo; bi < hi; ++bi) {
+		const BoxDev &bx = rb.boxes[bi];
+		const Pose w = bx.tf_identity ? link : then(link, D3{bx.t[0], bx.t[1], bx.t[2]}, Q4{bx.q[0], bx.q[1], bx.q[2], bx.q[3]}, false);
+		emit_box(sc, Q, res, w.t, w.q, bx.half, owner, step, (unsigned) bi, lc);
+	}
+}
 __device__ __forceinline__ void expand_state(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
 											 const Pose &base, const double *joints, unsigned owner, unsigned step,
 											 LocalCounters &lc) {
 	Pose link_tf[MGODPL_MAX_LINKS];
 	link_tf[rb.root] = base;
+	emit_link_boxes(sc, rb, Q, res, base, rb.root_box_begin, rb.root_box_end, owner, step, lc);
+	Pose cur = base;
 	for (int i = 0; i < rb.n_ops; ++i) {
 		const FkOp &op = rb.ops[i];
-		if (op.flags & FK_FOR_COLLISION) link_tf[op.child] = fk_apply(op, link_tf[op.parent], joints);
-	}
-	for (int bi = 0; bi < rb.n_boxes; ++bi) {
-		const BoxDev &bx = rb.boxes[bi];
-		const Pose &l = link_tf[bx.link];
-		Pose w = bx.tf_identity ? l : then(l, D3{bx.t[0], bx.t[1], bx.t[2]}, Q4{bx.q[0], bx.q[1], bx.q[2], bx.q[3]}, false);
-		emit_box(sc, Q, res, w.t, w.q, bx.half, owner, step, (unsigned) bi, lc);
+		if (!(op.flags & FK_FOR_COLLISION)) continue;
+		cur = fk_apply(op, (op.flags & FK_PARENT_IS_PREV) ? cur : link_tf[op.parent], joints);
+		if (op.flags & FK_STORE) link_tf[op.child] = cur;
+		emit_link_boxes(sc, rb, Q, res, cur, op.box_begin, op.box_end, owner, step, lc);
 	}
 }
 
@@ -297,9 +305,10 @@ k_expand_goals(const __grid_constant__ SceneDev sc, const __grid_constant__ Robo
 /// rule of Quaternion.cpp:12-20), exact reach cull, FK, box emit.  A/B point at the two endpoint rows.
 __device__ __forceinline__ void expand_motion_step(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
 												   const double *__restrict__ A, const double *__restrict__ B, unsigned n_steps,
-												   unsigned motion, unsigned step, LocalCounters &lc) {
-	double a[ROW_MAX], b[ROW_MAX];
-	for (int k = 0; k < 7 + rb.n_vars; ++k) a[k] = __ldg(A + k), b[k] = __ldg(B + k);
+												   double2 slerp_k, unsigned motion, unsigned step, LocalCounters &lc) {
+	double a[7], b[7];
+#pragma unroll
+	for (int k = 0; k < 7; ++k) a[k] = __ldg(A + k), b[k] = __ldg(B + k);
 	lc.states++;
 	// for n_steps == 0 the reference evaluates t = 0/0; here the start state is checked once.
 	const double t = n_steps ? (double) step / (double) n_steps : 0.0;
@@ -308,21 +317,21 @@ __device__ __forceinline__ void expand_motion_step(const SceneDev &sc, const Rob
 	Pose base{tr, Q4{a[3], a[4], a[5], a[6]}};
 	double jv[MGODPL_MAX_JOINT_VALUES];
 	if (n_steps) {
-		const double dq = a[3] * b[3] + a[4] * b[4] + a[5] * b[5] + a[6] * b[6];
-		const double ad = fabs(dq);
+		// slerp_k = (theta, sin(theta)) of the motion, theta < 0 flags the linear-weights case, the sign of .y carries
+		// "dot < 0" (second weight negated) — all per-motion constants of the Eigen rule, computed once in stage A1.
 		double w0, w1;
-		if (ad >= 1.0 - 2.220446049250313e-16) {
+		if (slerp_k.x < 0.0) {
 			w0 = 1.0 - t, w1 = t;
 		} else {
-			const double theta = acos(ad), st = sin(theta);
-			w0 = sin((1.0 - t) * theta) / st;
-			w1 = sin(t * theta) / st;
+			const double st = fabs(slerp_k.y);
+			w0 = sin((1.0 - t) * slerp_k.x) / st;
+			w1 = sin(t * slerp_k.x) / st;
 		}
-		if (dq < 0.0) w1 = -w1;
+		if (signbit(slerp_k.y)) w1 = -w1;
 		base.q = Q4{w0 * a[3] + w1 * b[3], w0 * a[4] + w1 * b[4], w0 * a[5] + w1 * b[5], w0 * a[6] + w1 * b[6]};
-		for (int k = 0; k < rb.n_vars; ++k) jv[k] = a[7 + k] * (1 - t) + b[7 + k] * t;
+		for (int k = 0; k < rb.n_vars; ++k) jv[k] = __ldg(A + 7 + k) * (1 - t) + __ldg(B + 7 + k) * t;
 	} else {
-		for (int k = 0; k < rb.n_vars; ++k) jv[k] = a[7 + k];
+		for (int k = 0; k < rb.n_vars; ++k) jv[k] = __ldg(A + 7 + k);
 	}
 	if (!isfinite(base.q.x + base.q.y + base.q.z + base.q.w)) return;
 	expand_state(sc, rb, Q, res, base, jv, motion, step, lc);
@@ -336,7 +345,7 @@ __global__ void __launch_bounds__(BLOCK_A)
 k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
 				const double *__restrict__ b, size_t m, size_t stride, int js, double max_step,
 				const uint32_t *__restrict__ n_steps_override, uint32_t *__restrict__ n_steps_out,
-				uint32_t *__restrict__ uncertain_bits, SurvivorsDev S, QueueDev Q, Results res) {
+				uint32_t *__restrict__ uncertain_bits, double2 *__restrict__ slerp_out, SurvivorsDev S, QueueDev Q, Results res) {
 	const unsigned lane = threadIdx.x & 31;
 	LocalCounters lc;
 	unsigned long long n_uncertain = 0, n_motions = 0;
@@ -365,6 +374,19 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 				if (o != NO_HIT) n_steps = o, uncertain = false;
 			}
 			if (n_steps_out) n_steps_out[i] = n_steps;
+			{
+				// Eigen slerp rule (Quaternion.cpp:12-20): dot over (x, y, z, w); linear weights when |dot| >= 1 - eps
+				const double dq = ar[3] * br[3] + ar[4] * br[4] + ar[5] * br[5] + ar[6] * br[6];
+				const double ad = fabs(dq);
+				double2 k;
+				if (ad >= 1.0 - 2.220446049250313e-16) {
+					k.x = -1.0, k.y = 1.0;
+				} else {
+					k.x = acos(ad), k.y = sin(k.x);
+				}
+				if (dq < 0.0) k.y = -k.y;
+				slerp_out[i] = k;
+			}
 			if (uncertain && uncertain_bits) atomicOr(uncertain_bits + (i >> 5), 1u << (i & 31));
 			n_uncertain += uncertain;
 			n_motions++;
@@ -395,6 +417,7 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 				len = s_hi - s_lo + 1;
 			}
 		}
+		__syncwarp();  // slerp_out[] of this warp's motions is read by other lanes on the overflow path
 		// cooperative append: for every lane with a non-empty range, the whole warp writes its (motion, step) pairs
 		unsigned todo = __ballot_sync(0xffffffffu, len > 0);
 		while (todo) {
@@ -407,7 +430,7 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 			base = __shfl_sync(0xffffffffu, base, 0);
 			for (unsigned k = lane; k < l; k += 32) {
 				if (base + k < S.cap) S.entries[base + k] = make_uint2(mot, lo + k);
-				else expand_motion_step(sc, rb, Q, res, a + (size_t) mot * stride, b + (size_t) mot * stride, ns, mot, lo + k, lc);
+				else expand_motion_step(sc, rb, Q, res, a + (size_t) mot * stride, b + (size_t) mot * stride, ns, slerp_out[mot], mot, lo + k, lc);
 			}
 		}
 	}
@@ -421,13 +444,14 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 /// A2 for motions: one thread per surviving (motion, step).
 __global__ void __launch_bounds__(BLOCK_A)
 k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
-					  const double *__restrict__ b, size_t stride, const uint32_t *__restrict__ n_steps, SurvivorsDev S,
-					  QueueDev Q, Results res) {
+					  const double *__restrict__ b, size_t stride, const uint32_t *__restrict__ n_steps,
+					  const double2 *__restrict__ slerp_k, SurvivorsDev S, QueueDev Q, Results res) {
 	LocalCounters lc;
 	const unsigned n = min(__ldcg(S.count), S.cap);
 	for (unsigned k = blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
 		const uint2 e = __ldcg(&S.entries[k]);
-		expand_motion_step(sc, rb, Q, res, a + (size_t) e.x * stride, b + (size_t) e.x * stride, __ldg(n_steps + e.x), e.x, e.y, lc);
+		expand_motion_step(sc, rb, Q, res, a + (size_t) e.x * stride, b + (size_t) e.x * stride, __ldg(n_steps + e.x), __ldg(slerp_k + e.x),
+						   e.x, e.y, lc);
 	}
 	flush_counters(sc, lc);
 }
@@ -718,7 +742,7 @@ cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t
 
 cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const double *d_a, const double *d_b, size_t m,
 								 size_t stride, int js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,
-								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned *d_first_step,
+								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned *d_first_step, void *d_slerp,
 								 void *scratch, size_t scratch_bytes, size_t survivor_entries, cudaStream_t stream) {
 	if (!m) return cudaSuccess;
 	SurvivorsDev S;
@@ -729,9 +753,9 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	LQ_CHECK(cudaMemsetAsync(d_first_step, 0xff, m * sizeof(unsigned), stream));
 	if (d_uncertain) LQ_CHECK(cudaMemsetAsync(d_uncertain, 0, ((m + 31) / 32) * 4, stream));
 	k_motion_ranges<<<grid_for(m, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
-																	  d_n_steps, d_uncertain, S, Q, res);
+																	  d_n_steps, d_uncertain, (double2 *) d_slerp, S, Q, res);
 	LQ_CHECK(cudaGetLastError());
-	k_expand_motion_steps<<<grid_for(S.cap, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, S, Q, res);
+	k_expand_motion_steps<<<grid_for(S.cap, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const double2 *) d_slerp, S, Q, res);
 	LQ_CHECK(cudaGetLastError());
 	LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (size_t) Q.cap, stream));
 	k_finish_motions<<<(unsigned) ((m + 255) / 256), 256, 0, stream>>>(d_first_step, d_n_steps, m, d_hit_bits, d_toi);
