@@ -181,7 +181,7 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 	cudaStream_t stream = nullptr;
 	double *d_verts = nullptr;
 	uint32_t *d_tris = nullptr;
-	unsigned leaf = opts && opts->max_leaf_size ? opts->max_leaf_size : 4;
+	unsigned leaf = opts && opts->max_leaf_size ? opts->max_leaf_size : 2;
 	bool refine = !(opts && (opts->flags & MGODPL_SCENE_NO_REFINE));
 	if (nt) {
 		CU(cudaMalloc((void **) &d_verts, nv * 3 * sizeof(double)));

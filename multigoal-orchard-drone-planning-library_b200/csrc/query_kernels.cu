@@ -460,23 +460,24 @@ k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant
 // Stage B: drain the queue.  Persistent warps, one box per lane, "while-while" with lane refill:
 //   refill   lanes whose box is finished take the next queued boxes (warp-local chunks of the queue, so neighbouring
 //            lanes hold neighbouring interpolation steps / samples and walk the tree together);
-//   descend  every lane steps through the skip-link BVH until it reaches an overlapping leaf or runs out of nodes;
-//            the warp leaves this loop once too few lanes are still descending;
-//   leaves   lanes parked on a leaf run the exact fp64 box/triangle test together.
+//   descend  every lane steps through the skip-link BVH until it reaches an overlapping leaf (it parks there) or runs
+//            out of nodes (it goes idle); the warp leaves this loop once a refill or a leaf batch is worthwhile;
+//   leaves   lanes parked on a leaf run the exact fp64 box/triangle test together, in batches of >= leaf_min lanes
+//            (the test is ~400 instructions; running it for 3 lanes at a time cost as much as all descents).
 // Without refill a warp's time is its slowest lane (a few boxes deep in the canopy among many that die at the top
 // of the tree): measured 3.6 active threads per instruction; this loop keeps most lanes busy.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr unsigned QUEUE_CHUNK = 64;    // items a warp claims per cursor atomic
 struct TraverseTuning {
-	int refill_min;   // idle lanes that trigger a refill
-	int descend_min;  // leave the descend loop when fewer lanes than this are still walking
+	int refill_min;  // idle lanes that trigger a refill
+	int leaf_min;    // parked lanes (on an overlapping leaf) that trigger a batch of exact tests
 };
 
 template<int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK_B, MIN_BLOCKS)
 k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ explicit_boxes,
 		   QueueDev Q, Results res, TraverseTuning tune) {
-	const int REFILL_MIN = tune.refill_min, DESCEND_MIN = tune.descend_min;
+	const int REFILL_MIN = tune.refill_min, LEAF_MIN = tune.leaf_min;
 	constexpr unsigned FULL = 0xffffffffu, END = 0xffffffffu;
 	const unsigned lane = threadIdx.x & 31;
 	const unsigned n_items = min(__ldcg(Q.count), Q.cap);
@@ -508,7 +509,9 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 				const uint4 *src = reinterpret_cast<const uint4 *>(Q.items + item);
 				const uint4 v0 = __ldcg(src), v1 = __ldcg(src + 1), v2 = __ldcg(src + 2), v3 = __ldcg(src + 3);
 				owner = v3.x, step_box = v3.y;
-				if (!already_decided(res, owner, step_box & 0x0FFFFFFFu)) {
+				// Motions: skip boxes of steps that can no longer be the first colliding one.  (For state bitmasks the
+				// same check only runs before a leaf test: it would cost a dependent L2 round trip per refill here.)
+				if (res.mode == RESULT_BITS || !already_decided(res, owner, step_box & 0x0FFFFFFFu)) {
 					cb.cx = __uint_as_float(v0.x), cb.cy = __uint_as_float(v0.y), cb.cz = __uint_as_float(v0.z);
 					cb.r[0] = __uint_as_float(v0.w), cb.r[1] = __uint_as_float(v1.x), cb.r[2] = __uint_as_float(v1.y);
 					cb.r[3] = __uint_as_float(v1.z), cb.r[4] = __uint_as_float(v1.w), cb.r[5] = __uint_as_float(v2.x);
@@ -529,10 +532,10 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 			chunk_lo += min(avail, (unsigned) __popc(idle_mask));
 			continue;  // re-evaluate who is idle (a refill may have come up short at a chunk boundary)
 		}
-		// ---- descend ----------------------------------------------------------------------------------------------
+		// ---- descend: until another action becomes worthwhile (enough idle lanes to refill, enough parked lanes for a
+		//      leaf batch) or nobody is left walking ------------------------------------------------------------------
 		bool run = node < n_nodes && pending < 0;
-		unsigned go = __ballot_sync(FULL, run);
-		const int low_water = exhausted ? 1 : DESCEND_MIN;
+		unsigned go = __ballot_sync(FULL, run), parked = __ballot_sync(FULL, pending >= 0);
 		while (go) {
 			if (run) {
 				const float4 a = __ldg(sc.nodes + 2 * node);
@@ -545,36 +548,40 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 				run = node < n_nodes && pending < 0;
 			}
 			go = __ballot_sync(FULL, run);
-			if (__popc(go) < low_water) break;
+			parked = __ballot_sync(FULL, pending >= 0);
+			if (__popc(parked) >= LEAF_MIN) break;
+			if (!exhausted && 32 - __popc(go) - __popc(parked) >= REFILL_MIN) break;
 		}
-		// ---- leaves -------------------------------------------------------------------------------------------------
-		if (pending >= 0) {
-			const unsigned first = (unsigned) pending >> 4, cnt = ((unsigned) pending & 15u) + 1u;
-			pending = -1;
-			const unsigned step = step_box & 0x0FFFFFFFu;
-			if (already_decided(res, owner, step)) {
-				node = END;
-			} else {
-				const double2 *ex = reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(Q.items + item) + ITEM_EXACT_OFFSET);
-				const double2 e0 = __ldcg(ex), e1 = __ldcg(ex + 1), e2 = __ldcg(ex + 2), e3 = __ldcg(ex + 3);
-				double half_buf[3];
-				const double *half;
-				if (explicit_boxes) {
-					const double *bx = explicit_boxes + (size_t) owner * 10;
-					half_buf[0] = __ldg(bx + 7) * 0.5, half_buf[1] = __ldg(bx + 8) * 0.5, half_buf[2] = __ldg(bx + 9) * 0.5;
-					half = half_buf;
-				} else {
-					half = rb.boxes[step_box >> 28].half;
-				}
-				const ExactBox eb = make_exact_box(D3{e0.x, e0.y, e1.x}, Q4{e1.y, e2.x, e2.y, e3.x}, half);
-				bool hit = false;
-				for (unsigned k = 0; k < cnt && !hit; ++k) {
-					lc.leaf++;
-					hit = box_triangle_hit(eb, sc.tris + 9ull * (first + k));
-				}
-				if (hit) {
-					report_hit(res, owner, step);
+		// ---- leaves: parked lanes run the exact test together, once there are enough of them or nothing else can move -----
+		if (__popc(parked) >= LEAF_MIN || (!go && parked)) {
+			if (pending >= 0) {
+				const unsigned first = (unsigned) pending >> 4, cnt = ((unsigned) pending & 15u) + 1u;
+				pending = -1;
+				const unsigned step = step_box & 0x0FFFFFFFu;
+				if (already_decided(res, owner, step)) {
 					node = END;
+				} else {
+					const double2 *ex = reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(Q.items + item) + ITEM_EXACT_OFFSET);
+					const double2 e0 = __ldcg(ex), e1 = __ldcg(ex + 1), e2 = __ldcg(ex + 2), e3 = __ldcg(ex + 3);
+					double half_buf[3];
+					const double *half;
+					if (explicit_boxes) {
+						const double *bx = explicit_boxes + (size_t) owner * 10;
+						half_buf[0] = __ldg(bx + 7) * 0.5, half_buf[1] = __ldg(bx + 8) * 0.5, half_buf[2] = __ldg(bx + 9) * 0.5;
+						half = half_buf;
+					} else {
+						half = rb.boxes[step_box >> 28].half;
+					}
+					const ExactBox eb = make_exact_box(D3{e0.x, e0.y, e1.x}, Q4{e1.y, e2.x, e2.y, e3.x}, half);
+					bool hit = false;
+					for (unsigned k = 0; k < cnt && !hit; ++k) {
+						lc.leaf++;
+						hit = box_triangle_hit(eb, sc.tris + 9ull * (first + k));
+					}
+					if (hit) {
+						report_hit(res, owner, step);
+						node = END;
+					}
 				}
 			}
 		}
@@ -694,12 +701,12 @@ static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const do
 								const Results &res, size_t worst_case_items, cudaStream_t stream) {
 	size_t bound = worst_case_items < Q.cap ? worst_case_items : Q.cap;
 	static int min_blocks = 0;
-	static TraverseTuning tune{8, 20};
+	static TraverseTuning tune{8, 8};
 	if (!min_blocks) {
 		const char *e = getenv("MGODPL_TRAVERSE_BLOCKS");
 		min_blocks = e ? atoi(e) : 4;
 		if ((e = getenv("MGODPL_REFILL_MIN"))) tune.refill_min = atoi(e);
-		if ((e = getenv("MGODPL_DESCEND_MIN"))) tune.descend_min = atoi(e);
+		if ((e = getenv("MGODPL_LEAF_MIN"))) tune.leaf_min = atoi(e);
 	}
 	switch (min_blocks) {
 		case 8: k_traverse<8><<<grid_for(bound, BLOCK_B, 8), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune); break;

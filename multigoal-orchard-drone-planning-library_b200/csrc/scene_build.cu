@@ -87,34 +87,92 @@ __global__ void k_topology(const unsigned long long *__restrict__ keys, int n, i
 	if (i == 0) parent[0] = -1;
 }
 
-/// Bottom-up: bounds, triangle counts, first triangle slot, and — with leaves collapsed at `max_leaf` triangles —
-/// the number of nodes the flattened subtree will occupy.
+__device__ __forceinline__ float half_area6(float4 alo, float4 ahi, float4 blo, float4 bhi) {
+	float x = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), y = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y),
+		  z = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+	return x * y + y * z + z * x;
+}
+__device__ __forceinline__ float half_area1(float4 lo, float4 hi) {
+	float x = hi.x - lo.x, y = hi.y - lo.y, z = hi.z - lo.z;
+	return x * y + y * z + z * x;
+}
+
+/// Bottom-up pass over the binary tree (atomic arrival flags: the second child to arrive owns the parent):
+///  * bounds, triangle counts and — with leaves collapsed at `max_leaf` triangles — the flattened subtree size;
+///  * optionally the SAH refinement: at every internal node, the best of the four child <-> grandchild rotations
+///    (Kensler 2008) is applied if it lowers the surface area of the restructured child.  Everything a rotation
+///    touches lies inside the node's own, already finished subtree, so the sweep stays race-free.
 __global__ void k_refit(int n, const uint32_t *__restrict__ ids, const float4 *__restrict__ tlo, const float4 *__restrict__ thi,
-						const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ parent,
-						float4 *__restrict__ blo, float4 *__restrict__ bhi, unsigned *__restrict__ tri_count,
-						unsigned *__restrict__ first_slot, unsigned *__restrict__ eff_size, unsigned *__restrict__ flags,
-						unsigned max_leaf) {
+						int *left, int *right, int *parent, float4 *blo, float4 *bhi, unsigned *tri_count, unsigned *eff_size,
+						unsigned *__restrict__ flags, unsigned max_leaf, int rotate, int init_leaves) {
 	int j = blockIdx.x * TB + threadIdx.x;
 	if (j >= n) return;
 	int node = j + n - 1;
-	uint32_t t = ids[j];
-	blo[node] = tlo[t], bhi[node] = thi[t];
-	tri_count[node] = 1, first_slot[node] = j, eff_size[node] = 1;
+	if (init_leaves) {
+		uint32_t t = ids[j];
+		blo[node] = tlo[t], bhi[node] = thi[t];
+		tri_count[node] = 1, eff_size[node] = 1;
+	}
 	__threadfence();
-	int p = n > 1 ? parent[node] : -1;
+	int p = n > 1 ? __ldcg(parent + node) : -1;
 	while (p >= 0) {
 		if (atomicAdd(&flags[p], 1u) == 0) return;  // first child to arrive leaves; the second one merges
 		__threadfence();
-		int l = left[p], r = right[p];
+		int l = __ldcg(left + p), r = __ldcg(right + p);
 		float4 llo = __ldcg(blo + l), lhi = __ldcg(bhi + l), rlo = __ldcg(blo + r), rhi = __ldcg(bhi + r);
+		if (rotate) {
+			// candidates: (child kept, child restructured, grandchild promoted, grandchild staying)
+			float best = 0.f;
+			int kind = -1;
+			int rl = -1, rr = -1, ll = -1, lr = -1;
+			float4 rllo, rlhi, rrlo, rrhi, lllo, llhi, lrlo, lrhi;
+			if (r < n - 1) {
+				rl = __ldcg(left + r), rr = __ldcg(right + r);
+				rllo = __ldcg(blo + rl), rlhi = __ldcg(bhi + rl), rrlo = __ldcg(blo + rr), rrhi = __ldcg(bhi + rr);
+				const float base = half_area1(rlo, rhi);
+				float d0 = half_area6(llo, lhi, rrlo, rrhi) - base;  // swap L <-> RL : R' = (L, RR)
+				float d1 = half_area6(llo, lhi, rllo, rlhi) - base;  // swap L <-> RR : R' = (RL, L)
+				if (d0 < best) best = d0, kind = 0;
+				if (d1 < best) best = d1, kind = 1;
+			}
+			if (l < n - 1) {
+				ll = __ldcg(left + l), lr = __ldcg(right + l);
+				lllo = __ldcg(blo + ll), llhi = __ldcg(bhi + ll), lrlo = __ldcg(blo + lr), lrhi = __ldcg(bhi + lr);
+				const float base = half_area1(llo, lhi);
+				float d2 = half_area6(rlo, rhi, lrlo, lrhi) - base;  // swap R <-> LL : L' = (R, LR)
+				float d3 = half_area6(rlo, rhi, lllo, llhi) - base;  // swap R <-> LR : L' = (LL, R)
+				if (d2 < best) best = d2, kind = 2;
+				if (d3 < best) best = d3, kind = 3;
+			}
+			if (kind >= 0) {
+				// restructured child c keeps grandchild `stay` and receives the other child `in`; grandchild `up` moves to p
+				const bool right_side = kind < 2;
+				const int c = right_side ? r : l, in = right_side ? l : r;
+				const int up = kind == 0 ? rl : kind == 1 ? rr : kind == 2 ? ll : lr;
+				const int stay = kind == 0 ? rr : kind == 1 ? rl : kind == 2 ? lr : ll;
+				left[c] = in, right[c] = stay;
+				parent[in] = c, parent[up] = p;
+				left[p] = up, right[p] = c;
+				const float4 ilo = right_side ? llo : rlo, ihi = right_side ? lhi : rhi;
+				const float4 slo = kind == 0 ? rrlo : kind == 1 ? rllo : kind == 2 ? lrlo : lllo;
+				const float4 shi = kind == 0 ? rrhi : kind == 1 ? rlhi : kind == 2 ? lrhi : llhi;
+				blo[c] = make_float4(fminf(ilo.x, slo.x), fminf(ilo.y, slo.y), fminf(ilo.z, slo.z), 0.f);
+				bhi[c] = make_float4(fmaxf(ihi.x, shi.x), fmaxf(ihi.y, shi.y), fmaxf(ihi.z, shi.z), 0.f);
+				const unsigned cnt = __ldcg(tri_count + in) + __ldcg(tri_count + stay);
+				tri_count[c] = cnt;
+				eff_size[c] = cnt <= max_leaf ? 1u : 1u + __ldcg(eff_size + in) + __ldcg(eff_size + stay);
+				__threadfence();
+				l = up, r = c;
+				llo = __ldcg(blo + l), lhi = __ldcg(bhi + l), rlo = __ldcg(blo + r), rhi = __ldcg(bhi + r);
+			}
+		}
 		blo[p] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.f);
 		bhi[p] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.f);
 		unsigned cnt = __ldcg(tri_count + l) + __ldcg(tri_count + r);
 		tri_count[p] = cnt;
-		first_slot[p] = min(__ldcg(first_slot + l), __ldcg(first_slot + r));
 		eff_size[p] = cnt <= max_leaf ? 1u : 1u + __ldcg(eff_size + l) + __ldcg(eff_size + r);
 		__threadfence();
-		p = parent[p];
+		p = __ldcg(parent + p);
 	}
 }
 
@@ -123,23 +181,38 @@ __device__ __forceinline__ float half_area(float4 lo, float4 hi) {
 	return x * y + y * z + z * x;
 }
 
-/// One thread per construction node: if the node survives collapsing, find its preorder slot by walking to the
-/// root, then emit the 32-byte traversal node (centre, skip | half extent, leaf info).
+/// One thread per construction node.  Walking to the root yields the node's preorder slot (nodes before it) and its
+/// leaf rank (triangles before it), for whatever shape the rotations left the tree in.  Surviving nodes emit their
+/// 32-byte traversal record (centre, skip | half extent, leaf info); original leaves also place their triangle — 9 fp64
+/// world coordinates — at its leaf-order slot, so every (collapsed) leaf owns a contiguous run of slots.
 __global__ void k_flatten(int n, const int *__restrict__ left, const int *__restrict__ parent, const float4 *__restrict__ blo,
-						  const float4 *__restrict__ bhi, const unsigned *__restrict__ tri_count,
-						  const unsigned *__restrict__ first_slot, const unsigned *__restrict__ eff_size, unsigned max_leaf,
-						  float4 *__restrict__ nodes, BuildStats *__restrict__ stats) {
+						  const float4 *__restrict__ bhi, const unsigned *__restrict__ tri_count, const unsigned *__restrict__ eff_size,
+						  unsigned max_leaf, const double *__restrict__ verts, const uint32_t *__restrict__ tris,
+						  const uint32_t *__restrict__ ids, float4 *__restrict__ nodes, double *__restrict__ tri_out,
+						  uint32_t *__restrict__ slot_ids, BuildStats *__restrict__ stats) {
 	int x = blockIdx.x * TB + threadIdx.x;
 	if (x >= 2 * n - 1) return;
 	const int root = 0;  // internal node 0, or — when n == 1 — the single leaf (id n-1 == 0)
 	int p = parent[x];   // -1 for the root
-	if (p >= 0 && tri_count[p] <= max_leaf) return;  // swallowed by a collapsed ancestor
-	unsigned pre = 0, depth = 0;
+	const bool swallowed = p >= 0 && tri_count[p] <= max_leaf;  // inside a collapsed leaf
+	const bool original_leaf = x >= n - 1;
+	if (swallowed && !original_leaf) return;
+	unsigned pre = 0, depth = 0, tri_before = 0;
 	for (int c = x; p >= 0; c = p, p = parent[p]) {
-		int l = left[p];
-		pre += 1u + (c == l ? 0u : eff_size[l]);
+		const int l = left[p];
+		if (c != l) pre += eff_size[l], tri_before += tri_count[l];
+		pre += 1u;
 		++depth;
 	}
+	if (original_leaf) {
+		const uint32_t t = ids[x - (n - 1)];
+		slot_ids[tri_before] = t;
+		for (int k = 0; k < 3; ++k) {
+			const double *v = verts + 3ull * tris[3ull * t + k];
+			tri_out[9ull * tri_before + 3 * k] = v[0], tri_out[9ull * tri_before + 3 * k + 1] = v[1], tri_out[9ull * tri_before + 3 * k + 2] = v[2];
+		}
+	}
+	if (swallowed) return;
 	const unsigned cnt = tri_count[x];
 	const bool leaf = cnt <= max_leaf;
 	const float4 lo = blo[x], hi = bhi[x];
@@ -151,7 +224,7 @@ __global__ void k_flatten(int n, const int *__restrict__ left, const int *__rest
 		h[a] = __double2float_ru(0.5 * ((double) hi3[a] - (double) lo3[a]) + fabs(cd - (double) c[a]));
 	}
 	const unsigned skip = pre + eff_size[x];
-	const int info = leaf ? (int) (first_slot[x] << 4 | (cnt - 1)) : -1;
+	const int info = leaf ? (int) (tri_before << 4 | (cnt - 1)) : -1;
 	nodes[2 * pre] = make_float4(c[0], c[1], c[2], __uint_as_float(skip));
 	nodes[2 * pre + 1] = make_float4(h[0], h[1], h[2], __int_as_float(info));
 	// statistics
@@ -162,18 +235,6 @@ __global__ void k_flatten(int n, const int *__restrict__ left, const int *__rest
 		atomicAdd(&stats->n_leaves, 1ull);
 		atomicMax(&stats->max_leaf, cnt);
 		atomicMax(&stats->max_depth, depth);
-	}
-}
-
-/// Triangle payload in leaf (= Morton) order: 9 fp64 world coordinates per slot.
-__global__ void k_emit_tris(const double *__restrict__ verts, const uint32_t *__restrict__ tris, const uint32_t *__restrict__ ids,
-							unsigned nt, double *__restrict__ out) {
-	unsigned j = blockIdx.x * TB + threadIdx.x;
-	if (j >= nt) return;
-	uint32_t t = ids[j];
-	for (int k = 0; k < 3; ++k) {
-		const double *v = verts + 3ull * tris[3ull * t + k];
-		out[9ull * j + 3 * k] = v[0], out[9ull * j + 3 * k + 1] = v[1], out[9ull * j + 3 * k + 2] = v[2];
 	}
 }
 
@@ -211,14 +272,15 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 	Scratch tmp;
 	float4 *tlo, *thi, *blo, *bhi;
 	unsigned long long *keys, *keys2;
-	uint32_t *ids, *ids2;
+	uint32_t *ids, *ids0, *ids2;  // final slot -> triangle (kept) | unsorted | Morton-sorted
 	int *left, *right, *parent;
-	unsigned *tri_count, *first_slot, *eff_size, *flags;
+	unsigned *tri_count, *eff_size, *flags;
 	BuildStats *d_stats;
 	BS_CHECK(tmp.alloc(&tlo, nt));
 	BS_CHECK(tmp.alloc(&thi, nt));
 	BS_CHECK(tmp.alloc(&keys, nt));
 	BS_CHECK(tmp.alloc(&keys2, nt));
+	BS_CHECK(tmp.alloc(&ids0, nt));
 	BS_CHECK(tmp.alloc(&ids2, nt));
 	BS_CHECK(tmp.alloc(&left, nt));
 	BS_CHECK(tmp.alloc(&right, nt));
@@ -226,7 +288,6 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 	BS_CHECK(tmp.alloc(&blo, 2 * nt));
 	BS_CHECK(tmp.alloc(&bhi, 2 * nt));
 	BS_CHECK(tmp.alloc(&tri_count, 2 * nt));
-	BS_CHECK(tmp.alloc(&first_slot, 2 * nt));
 	BS_CHECK(tmp.alloc(&eff_size, 2 * nt));
 	BS_CHECK(tmp.alloc(&flags, nt));
 	BS_CHECK(tmp.alloc(&d_stats, 1));
@@ -241,14 +302,14 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 	D3 inv{hi[0] > lo[0] ? 1.0 / (hi[0] - lo[0]) : 0.0, hi[1] > lo[1] ? 1.0 / (hi[1] - lo[1]) : 0.0,
 		   hi[2] > lo[2] ? 1.0 / (hi[2] - lo[2]) : 0.0};
 	k_prepare<<<gt, TB, 0, stream>>>(d_verts, d_tris, (unsigned) nt, D3{origin[0], origin[1], origin[2]},
-									 D3{lo[0], lo[1], lo[2]}, inv, tlo, thi, keys, ids2);
+									 D3{lo[0], lo[1], lo[2]}, inv, tlo, thi, keys, ids0);
 	BS_CHECK(cudaGetLastError());
 	{
 		size_t bytes = 0;
-		BS_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys2, ids2, ids, n, 0, 63, stream));
+		BS_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys, keys2, ids0, ids2, n, 0, 63, stream));
 		void *ws;
 		BS_CHECK(tmp.alloc((char **) &ws, bytes));
-		BS_CHECK(cub::DeviceRadixSort::SortPairs(ws, bytes, keys, keys2, ids2, ids, n, 0, 63, stream));
+		BS_CHECK(cub::DeviceRadixSort::SortPairs(ws, bytes, keys, keys2, ids0, ids2, n, 0, 63, stream));
 	}
 	BS_CHECK(cudaMemsetAsync(flags, 0, nt * sizeof(unsigned), stream));
 	BS_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(BuildStats), stream));
@@ -257,19 +318,22 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 		k_topology<<<gt, TB, 0, stream>>>(keys2, n, left, right, parent);
 		BS_CHECK(cudaGetLastError());
 	}
-	k_refit<<<gt, TB, 0, stream>>>(n, ids, tlo, thi, left, right, parent, blo, bhi, tri_count, first_slot, eff_size, flags,
-								   max_leaf_size);
-	BS_CHECK(cudaGetLastError());
+	// Pass 0 fits the bounds; with refinement on, it and two more sweeps also apply SAH-lowering rotations.
+	const int sweeps = refine && n > 2 ? 3 : 1;
+	for (int sweep = 0; sweep < sweeps; ++sweep) {
+		if (sweep) BS_CHECK(cudaMemsetAsync(flags, 0, nt * sizeof(unsigned), stream));
+		k_refit<<<gt, TB, 0, stream>>>(n, ids2, tlo, thi, left, right, parent, blo, bhi, tri_count, eff_size, flags, max_leaf_size,
+									   refine && n > 2, sweep == 0);
+		BS_CHECK(cudaGetLastError());
+	}
 	// The flattened size is the root's effective size; fetch it before allocating the node array.
 	unsigned n_nodes = 0;
 	BS_CHECK(cudaMemcpyAsync(&n_nodes, eff_size, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
 	BS_CHECK(cudaStreamSynchronize(stream));
 	BS_CHECK(cudaMalloc((void **) &out->nodes, (size_t) n_nodes * 2 * sizeof(float4)));
 	BS_CHECK(cudaMalloc((void **) &out->tris, nt * 9 * sizeof(double)));
-	k_flatten<<<(unsigned) ((2 * nt - 1 + TB - 1) / TB), TB, 0, stream>>>(n, left, parent, blo, bhi, tri_count, first_slot,
-																		  eff_size, max_leaf_size, out->nodes, d_stats);
-	BS_CHECK(cudaGetLastError());
-	k_emit_tris<<<gt, TB, 0, stream>>>(d_verts, d_tris, ids, (unsigned) nt, out->tris);
+	k_flatten<<<(unsigned) ((2 * nt - 1 + TB - 1) / TB), TB, 0, stream>>>(n, left, parent, blo, bhi, tri_count, eff_size, max_leaf_size,
+																		  d_verts, d_tris, ids2, out->nodes, out->tris, ids, d_stats);
 	BS_CHECK(cudaGetLastError());
 	BS_CHECK(cudaEventRecord(ev1, stream));
 	BuildStats st{};
