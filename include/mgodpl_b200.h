@@ -169,6 +169,16 @@ int mgodpl_sample_goals_device(mgodpl_scene *scene, const mgodpl_robot *robot, c
 							   const double *d_draws, size_t s, uint64_t seed, double distance_from_target,
 							   uint32_t *d_hit_bits, uint32_t *d_collisions, double *d_states_out, void *stream);
 
+/* ---- k nearest neighbours under equal_weights_distance (src/planning/distance.cpp:17-25): the NearestNeighborsGNAT
+ *      query issued before every batch of PRM edge checks (src/planning/tsp_over_prm.cpp:44-45, 383-386), for all n
+ *      states at once.  causal != 0: state i only sees states j < i, i.e. the roadmap as it stood when the reference
+ *      inserted node i.  idx: n x k indices ascending by distance (-1 pads when fewer than k candidates exist);
+ *      dist (optional): n x k distances (NaN pads).  1 <= k <= 32. ------------------------------------------------------- */
+int mgodpl_knn(const double *states, size_t n, size_t stride, int32_t n_joint_values, int32_t k, int32_t causal, int32_t *idx,
+			   double *dist, void *stream);
+int mgodpl_knn_device(const double *d_states, size_t n, size_t stride, int32_t n_joint_values, int32_t k, int32_t causal,
+					  int32_t *d_idx, double *d_dist, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

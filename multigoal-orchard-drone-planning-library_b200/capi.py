@@ -27,7 +27,7 @@ EXPORTS = [
     "mgodpl_scene_destroy", "mgodpl_scene_get_info", "mgodpl_scene_get_counters", "mgodpl_robot_create",
     "mgodpl_robot_destroy", "mgodpl_robot_n_variables", "mgodpl_forward_kinematics", "mgodpl_check_boxes",
     "mgodpl_check_states", "mgodpl_check_states_device", "mgodpl_check_motions", "mgodpl_check_motions_device",
-    "mgodpl_check_path", "mgodpl_sample_goals", "mgodpl_sample_goals_device",
+    "mgodpl_check_path", "mgodpl_sample_goals", "mgodpl_sample_goals_device", "mgodpl_knn", "mgodpl_knn_device",
 ]
 
 
@@ -105,6 +105,12 @@ def _p(a, t=C.c_double):
 
 def _stream(stream) -> C.c_void_p:
     return C.c_void_p(int(stream) if stream else 0)
+
+
+def _dptr(x) -> C.c_void_p:
+    if x is None:
+        return C.c_void_p(0)
+    return C.c_void_p(x.data_ptr() if hasattr(x, "data_ptr") else int(x))
 
 
 def unpack_bits(words: np.ndarray, n: int) -> np.ndarray:
@@ -266,13 +272,23 @@ def sample_goals(scene: Scene, robot: Robot, targets, samples: int, draws=None, 
     return dict(hit=hits, collisions=counts, states=states, words=words)
 
 
+def knn(states, k: int, causal: bool = False, want_dist: bool = True, stream=None):
+    """(idx[n,k], dist[n,k]) nearest neighbours under equal_weights_distance; causal: only j < i (incremental PRM)."""
+    s = _states2d(states)
+    n = len(s)
+    idx = np.full((n, k), -1, np.int32)
+    dist = np.zeros((n, k)) if want_dist else None
+    _check(lib().mgodpl_knn(_p(s), C.c_size_t(n), C.c_size_t(s.shape[1]), s.shape[1] - 7, k, int(causal), _p(idx, C.c_int32),
+                            _p(dist), _stream(stream)))
+    return idx, dist
+
+
+def knn_device(d_states, n: int, stride: int, n_joint_values: int, k: int, d_idx, d_dist=None, causal: bool = False, stream=None):
+    _check(lib().mgodpl_knn_device(_dptr(d_states), C.c_size_t(n), C.c_size_t(stride), n_joint_values, k, int(causal),
+                                   _dptr(d_idx), _dptr(d_dist), _stream(stream)))
+
+
 # ---- device-pointer variants (torch tensors or raw pointers; asynchronous on `stream`) -------------------------------
-def _dptr(x) -> C.c_void_p:
-    if x is None:
-        return C.c_void_p(0)
-    return C.c_void_p(x.data_ptr() if hasattr(x, "data_ptr") else int(x))
-
-
 def check_states_device(scene: Scene, robot: Robot, d_states, n: int, stride: int, n_joint_values: int, d_hit_bits,
                         stream=None):
     _check(lib().mgodpl_check_states_device(scene.h, robot.h, _dptr(d_states), C.c_size_t(n), C.c_size_t(stride),

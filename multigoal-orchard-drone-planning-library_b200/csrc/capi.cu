@@ -721,4 +721,40 @@ int mgodpl_sample_goals(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	return MGODPL_OK;
 }
 
+// ---- k nearest neighbours over equal_weights_distance (the GNAT query of tsp_over_prm.cpp:44-45, batched) -------------------
+int mgodpl_knn_device(const double *d_states, size_t n, size_t stride, int32_t js, int32_t k, int32_t causal, int32_t *d_idx,
+					  double *d_dist, void *stream_) {
+	if (js < 0 || js > MGODPL_MAX_JOINT_VALUES || stride < (size_t) (7 + js)) return fail(MGODPL_E_INVALID_ARGUMENT, "bad state layout");
+	if (k < 1 || k > 32) return fail(MGODPL_E_INVALID_ARGUMENT, "k must be in 1..32");
+	if (n && (!d_states || !d_idx)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (n >= 0x7FFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "too many states");
+	if (int rc = require_device()) return rc;
+	CU(launch_knn(d_states, n, stride, js, k, causal, d_idx, d_dist, (cudaStream_t) stream_));
+	return MGODPL_OK;
+}
+
+int mgodpl_knn(const double *states, size_t n, size_t stride, int32_t js, int32_t k, int32_t causal, int32_t *idx, double *dist,
+			   void *stream_) {
+	if (js < 0 || js > MGODPL_MAX_JOINT_VALUES || stride < (size_t) (7 + js)) return fail(MGODPL_E_INVALID_ARGUMENT, "bad state layout");
+	if (k < 1 || k > 32) return fail(MGODPL_E_INVALID_ARGUMENT, "k must be in 1..32");
+	if (n && (!states || !idx)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (n >= 0x7FFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "too many states");
+	if (int rc = require_device()) return rc;
+	if (!n) return MGODPL_OK;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	double *d_s = nullptr, *d_d = nullptr;
+	int32_t *d_i = nullptr;
+	cudaError_t e = cudaMalloc((void **) &d_s, n * stride * 8);
+	if (e == cudaSuccess) e = cudaMalloc((void **) &d_i, n * k * 4);
+	if (e == cudaSuccess && dist) e = cudaMalloc((void **) &d_d, n * k * 8);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, states, n * stride * 8, cudaMemcpyHostToDevice, stream);
+	if (e == cudaSuccess) e = launch_knn(d_s, n, stride, js, k, causal, d_i, d_d, stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(idx, d_i, n * k * 4, cudaMemcpyDeviceToHost, stream);
+	if (e == cudaSuccess && dist) e = cudaMemcpyAsync(dist, d_d, n * k * 8, cudaMemcpyDeviceToHost, stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+	cudaFree(d_s), cudaFree(d_i), cudaFree(d_d);
+	if (e != cudaSuccess) return fail_cuda(e, "knn");
+	return MGODPL_OK;
+}
+
 }  // extern "C"

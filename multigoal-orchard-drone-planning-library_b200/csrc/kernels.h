@@ -30,6 +30,10 @@ cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const do
 cudaError_t launch_forward_kinematics(const RobotDev &rb, const double *d_states, size_t n, size_t stride, double *d_out,
 									  cudaStream_t stream);
 
+/// Exact k-NN over equal_weights_distance; causal != 0 restricts node i to neighbours j < i (incremental PRM insertion).
+cudaError_t launch_knn(const double *d_states, size_t n, size_t stride, int js, int k, int causal, int32_t *d_idx, double *d_dist,
+					   cudaStream_t stream);
+
 /// Result of the device BVH build: device buffers owned by the caller (cudaFree).
 struct BuiltScene {
 	float4 *nodes = nullptr;

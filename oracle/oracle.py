@@ -287,6 +287,16 @@ def gen_goal_states(robot: Robot, target, n: int, seed=42, distance_from_target=
     return out
 
 
+def knn(states, k: int, causal: bool = False):
+    states = _arr(states)
+    n, stride = states.shape
+    idx = np.zeros((n, k), np.int32)
+    dist = np.zeros((n, k))
+    lib().orc_knn(_d(states), C.c_size_t(n), C.c_size_t(stride), stride - 7, k, int(causal),
+                  idx.ctypes.data_as(C.POINTER(C.c_int32)), _d(dist))
+    return idx, dist
+
+
 def from_ee_and_vector(robot: Robot, point, vec):
     out = np.zeros(8)
     lib().orc_from_ee_and_vector(robot.h, _d(_arr(point)), _d(_arr(vec)), _d(out))

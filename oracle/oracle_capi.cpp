@@ -273,6 +273,23 @@ void orc_goal_sample_counts(void *scene, void *robot, unsigned seed, const doubl
 		}
 	});
 }
+/// k nearest neighbours under equal_weights_distance by exhaustive search — what NearestNeighborsGNAT::nearestK returns
+/// (src/planning/nearest_neighbours/NearestNeighborsGNAT.h:180-189 with the metric set at tsp_over_prm.cpp:383-386).
+/// causal: state i only sees states j < i (the roadmap when node i was inserted, tsp_over_prm.cpp:33-66).
+void orc_knn(const double *states, size_t n, size_t stride, int js, int k, int causal, int32_t *idx, double *dist) {
+	std::vector<State> st;
+	for (size_t i = 0; i < n; ++i) st.push_back(load_state(states + i * stride, js));
+	for (size_t i = 0; i < n; ++i) {
+		std::vector<std::pair<double, int32_t>> c;
+		for (size_t j = 0; j < (causal ? i : n); ++j)
+			if (j != i) c.push_back({equal_weights_distance(st[i], st[j]), (int32_t) j});
+		std::stable_sort(c.begin(), c.end(), [](auto &a, auto &b) { return a.first < b.first; });
+		for (int q = 0; q < k; ++q) {
+			idx[i * k + q] = q < (int) c.size() ? c[q].second : -1;
+			dist[i * k + q] = q < (int) c.size() ? c[q].first : std::numeric_limits<double>::quiet_NaN();
+		}
+	}
+}
 void orc_from_ee_and_vector(void *robot, const double *point3, const double *vec3, double *out8) {
 	store_state(from_end_effector_and_vector(*(Robot *) robot, {point3[0], point3[1], point3[2]}, {vec3[0], vec3[1], vec3[2]}), out8);
 }

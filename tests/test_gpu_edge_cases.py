@@ -225,3 +225,35 @@ def test_goal_sampling_device_rng_and_distance(gpu, oracle, env):
     d = gpu.sample_goals(env["dscene"], env["drb"], t[:2], 64, draws=draws, distance_from_target=0.2, want_states=True)
     want_states = np.stack([oracle.gen_goal_states(env["orb"], x, 64, seed=9, distance_from_target=0.2) for x in t[:2]])
     assert np.abs(d["states"] - want_states).max() < 1e-12
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_knn_matches_exhaustive_oracle(gpu, oracle, env, causal):
+    """§8f rank 1: exact k-NN under equal_weights_distance (the GNAT query before PRM edge validation)."""
+    st = oracle.gen_uniform_states(env["orb"], 700, seed=12)
+    idx, dist = gpu.capi.knn(st, 10, causal=causal)
+    widx, wdist = oracle.knn(st, 10, causal=causal)
+    assert np.allclose(np.nan_to_num(dist, nan=-1), np.nan_to_num(wdist, nan=-1), rtol=0, atol=1e-12)
+    same = idx == widx
+    # the device libm may order exact ties / 1-ulp near-ties differently; everything else must match
+    assert same.mean() > 0.999
+    bad = ~same
+    assert np.abs(dist[bad] - wdist[bad]).max(initial=0) < 1e-12
+    if causal:
+        assert (idx[0] == -1).all() and (idx[5, :5] >= 0).all() and (idx[5, 5:] == -1).all()
+        assert (idx < np.arange(700)[:, None]).all()
+
+
+def test_prm_edge_validation_pipeline(gpu, oracle, env):
+    """BASELINE config 4 in miniature: sample nodes -> state filter -> causal k-NN -> one batch of edge motions."""
+    st = oracle.gen_uniform_states(env["orb"], 1500, seed=77, h_range=3.0, v_range=4.0)
+    free = ~gpu.check_states(env["dscene"], env["drb"], st)
+    nodes = st[free]
+    idx, dist = gpu.capi.knn(nodes, 5, causal=True)
+    src, dst = np.nonzero(idx >= 0)
+    a, b = nodes[idx[src, dst]], nodes[src]  # motion_collides(neighbour, state), tsp_over_prm.cpp:51-53
+    got = gpu.check_motions(env["dscene"], env["drb"], a, b)
+    want = env["oscene"].check_motions(env["orb"], a, b, band=True, threads=8)
+    ok = want["min_abs_clearance"] > BAND
+    assert np.array_equal(got["hit"][ok], want["hit"][ok]) and np.array_equal(got["n_steps"], want["n_steps"])
+    assert 0.05 < want["hit"].mean() < 0.95
