@@ -249,7 +249,7 @@ def extra_workloads(mg, torch, scene, tree, dev, stream):
     st[:, 7] = (u[:, 4] * 2 - 1) * (np.pi / 2)
     st[:, 8] = (u[:, 5] * 2 - 1) * (np.pi / 2)
     d_hit = torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev)
-    for name, hh, vv in (("states_10M_prm_box_h5_v10", 5.0, 10.0), ("states_10M_config1_box", h, float(lo[2] + 1.0))):
+    for name, hh, vv in (("states_10M_prm_box_h5_v10", 5.0, 10.0), ("config1_states_10M_sampling_difficulty_box", h, float(lo[2] + 1.0))):
         st[:, 0] = (u[:, 0] * 2 - 1) * hh
         st[:, 1] = (u[:, 1] * 2 - 1) * hh
         st[:, 2] = u[:, 2] * vv
@@ -269,17 +269,81 @@ def extra_workloads(mg, torch, scene, tree, dev, stream):
     d_t = torch.from_numpy(tree.fruit_centers.copy()).to(dev)
     d_gh = torch.zeros(f * ((s + 31) // 32), dtype=torch.int32, device=dev)
     d_cnt = torch.zeros(f, dtype=torch.int32, device=dev)
-    for _ in range(2):
-        mg.capi.sample_goals_device(scene, robot, d_t, f, s, d_gh, d_collisions=d_cnt, stream=stream)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        mg.capi.sample_goals_device(scene, robot, d_t, f, s, d_gh, d_collisions=d_cnt, stream=stream)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
-    out["goal_sampling_500x1000"] = {"samples_per_sec": f * s / (ms * 1e-3), "ms": ms,
-                                     "collision_rate": float(d_cnt.cpu().numpy().sum() / (f * s))}
+
+    def timed(fn, reps=3, warm=2):
+        for _ in range(warm):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms = timed(lambda: mg.capi.sample_goals_device(scene, robot, d_t, f, s, d_gh, d_collisions=d_cnt, stream=stream))
+    out["config3_goal_sampling_500x1000"] = {"samples_per_sec": f * s / (ms * 1e-3), "ms": ms,
+                                             "collision_rate": float(d_cnt.cpu().numpy().sum() / (f * s))}
+    del st, u, d_hit
+    # ---- config 4: PRM edge validation, 100k roadmap nodes, k = 10 (causal k-NN = the reference's incremental insertion) ----
+    try:
+        prm_model = mg.robots.create_procedural_robot_model(0.75, (0,))
+        prm_robot = prm_model.to_device()
+        cand = mg.robots.generate_uniform_random_states(prm_model, mg.robots.Mt19937(7), 104_000, 5.0, 10.0)
+        free = ~mg.capi.check_states(scene, prm_robot, cand)
+        nodes = np.ascontiguousarray(cand[free][:100_000])
+        nn, k = len(nodes), 10
+        d_nodes = torch.from_numpy(nodes).to(dev)
+        d_idx = torch.zeros((nn, k), dtype=torch.int32, device=dev)
+        ms_knn = timed(lambda: mg.capi.knn_device(d_nodes, nn, 9, 2, k, d_idx, causal=True, stream=stream), reps=1, warm=1)
+        idx = d_idx.cpu().numpy()
+        src, col = np.nonzero(idx >= 0)
+        d_ea = torch.from_numpy(np.ascontiguousarray(nodes[idx[src, col]])).to(dev)   # motion_collides(neighbour, state)
+        d_eb = torch.from_numpy(np.ascontiguousarray(nodes[src])).to(dev)
+        me = len(src)
+        d_eh = torch.zeros((me + 31) // 32, dtype=torch.int32, device=dev)
+        d_et = torch.zeros(me, dtype=torch.float64, device=dev)
+        d_es = torch.zeros(me, dtype=torch.int32, device=dev)
+        ms_e = timed(lambda: mg.capi.check_motions_device(scene, prm_robot, d_ea, d_eb, me, 9, 2, d_eh, MAX_STEP, d_et, d_es, stream=stream))
+        eh = mg.capi.unpack_bits(d_eh.cpu().numpy().view(np.uint32), me)
+        sc = ref_equivalent_states(eh, d_et.cpu().numpy(), d_es.cpu().numpy().astype(np.int64)).sum()
+        out["config4_prm_edges_100k_nodes_k10"] = {"edges": me, "edges_per_sec": me / (ms_e * 1e-3), "states_per_sec": float(sc) / (ms_e * 1e-3),
+                                                    "ms_edge_validation": ms_e, "ms_knn_100k_causal": ms_knn,
+                                                    "edge_collision_rate": float(eh.mean()), "mean_steps": float(d_es.float().mean().item())}
+        del d_ea, d_eb, d_eh, d_et, d_es, d_idx, d_nodes
+    except Exception as e:  # an extra must never cost the headline line
+        out["config4_prm_edges_100k_nodes_k10"] = {"error": repr(e)}
+    # ---- config 5: 8-tree orchard row (~2 M triangles; scene > L2), 10 M states + 1 M motions on this GPU -------------------
+    try:
+        orchard = mg.scenes.make_orchard()
+        omesh = orchard.collision_mesh(True)
+        oscene = mg.Scene.from_mesh(omesh)
+        oinfo = oscene.info()
+        gen = torch.Generator(device=dev).manual_seed(5)
+        n = 10_000_000
+        u = torch.rand((n, 6), generator=gen, device=dev, dtype=torch.float64)
+        st = torch.zeros((n, 9), dtype=torch.float64, device=dev)
+        st[:, 0], st[:, 1], st[:, 2] = (u[:, 0] * 2 - 1) * 10.0, (u[:, 1] * 2 - 1) * 5.0, u[:, 2] * 10.0   # SURVEY §8d config 5 box
+        yaw = u[:, 3] * (2 * np.pi)
+        st[:, 5], st[:, 6] = torch.sin(yaw / 2), torch.cos(yaw / 2)
+        st[:, 7], st[:, 8] = (u[:, 4] * 2 - 1) * (np.pi / 2), (u[:, 5] * 2 - 1) * (np.pi / 2)
+        d_hit = torch.zeros((n + 31) // 32, dtype=torch.int32, device=dev)
+        ms_s = timed(lambda: mg.capi.check_states_device(oscene, robot, st, n, 9, 2, d_hit, stream=stream))
+        rate = float(mg.capi.unpack_bits(d_hit.cpu().numpy().view(np.uint32), n).mean())
+        mm = 1_000_000
+        d_ma, d_mb = st[:mm].contiguous(), st[mm:2 * mm].contiguous()
+        d_mh = torch.zeros((mm + 31) // 32, dtype=torch.int32, device=dev)
+        d_mt = torch.zeros(mm, dtype=torch.float64, device=dev)
+        d_ms = torch.zeros(mm, dtype=torch.int32, device=dev)
+        ms_m = timed(lambda: mg.capi.check_motions_device(oscene, robot, d_ma, d_mb, mm, 9, 2, d_mh, MAX_STEP, d_mt, d_ms, stream=stream))
+        mh = mg.capi.unpack_bits(d_mh.cpu().numpy().view(np.uint32), mm)
+        sc = ref_equivalent_states(mh, d_mt.cpu().numpy(), d_ms.cpu().numpy().astype(np.int64)).sum()
+        out["config5_orchard_8_trees"] = {"triangles": int(oinfo.n_triangles), "scene_bytes": int(oinfo.device_bytes), "build_ms": oinfo.build_ms,
+                                          "states_10M": {"states_per_sec": n / (ms_s * 1e-3), "ms": ms_s, "collision_rate": rate},
+                                          "motions_1M": {"motions_per_sec": mm / (ms_m * 1e-3), "states_per_sec": float(sc) / (ms_m * 1e-3),
+                                                         "ms": ms_m, "collision_rate": float(mh.mean())}}
+    except Exception as e:
+        out["config5_orchard_8_trees"] = {"error": repr(e)}
     return out
 
 
