@@ -98,6 +98,7 @@ typedef struct mgodpl_counters {
 	uint64_t leaf_tests;       /* exact box/triangle tests */
 	uint64_t motions_checked;
 	uint64_t uncertain_steps;  /* motions whose step count sat within 1e-9 of an integer boundary (re-derived on host) */
+	uint64_t max_nodes_per_box;/* longest single box descent (BVH records visited): the traversal's critical path */
 } mgodpl_counters;
 
 const char *mgodpl_last_error(void);

@@ -61,7 +61,8 @@ class SceneInfo(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("states_checked", C.c_uint64), ("boxes_traversed", C.c_uint64), ("nodes_visited", C.c_uint64),
-                ("leaf_tests", C.c_uint64), ("motions_checked", C.c_uint64), ("uncertain_steps", C.c_uint64)]
+                ("leaf_tests", C.c_uint64), ("motions_checked", C.c_uint64), ("uncertain_steps", C.c_uint64),
+                ("max_nodes_per_box", C.c_uint64)]
 
 
 def build_library(verbose: bool = False) -> str:

@@ -197,26 +197,24 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 		cudaFree(d_verts);
 		cudaFree(d_tris);
 		if (e != cudaSuccess) {
-			cudaFree(sc->built.nodes), cudaFree(sc->built.tris), cudaFree(sc->built.tri_ids);
+			cudaFree(sc->built.nodes), cudaFree(sc->built.tris), cudaFree(sc->built.tris32), cudaFree(sc->built.tri_ids);
 			return fail_cuda(e, "build_scene");
 		}
 	}
 	SceneDev &d = sc->dev;
 	d.nodes = sc->built.nodes;
 	d.tris = sc->built.tris;
+	d.tris32 = sc->built.tris32;
 	d.n_nodes = sc->built.n_nodes;
 	d.n_tris = sc->built.n_tris;
 	for (int a = 0; a < 3; ++a) d.origin[a] = origin[a];
 	// fp32 cull tests carry ~1e-7 relative error on coordinates up to max_abs (plus robot reach): inflate every
 	// box by a margin two orders of magnitude above that.  Exactness is restored by the fp64 leaf test.
 	d.margin = (float) std::max(2e-5, 4e-6 * (max_abs + 2.0));
-	if (d.n_nodes) {
-		float4 root[2];
-		CU(cudaMemcpy(root, d.nodes, sizeof(root), cudaMemcpyDeviceToHost));
-		d.root_c[0] = root[0].x, d.root_c[1] = root[0].y, d.root_c[2] = root[0].z;
-		d.root_h[0] = root[1].x, d.root_h[1] = root[1].y, d.root_h[2] = root[1].z;
-	} else {
-		for (int a = 0; a < 3; ++a) d.root_c[a] = 0.f, d.root_h[a] = -1.f;  // nothing overlaps an empty scene
+	for (int a = 0; a < 3; ++a) d.root_c[a] = sc->built.root_c[a], d.root_h[a] = sc->built.root_h[a];  // empty scene: half = -1
+	if (sc->built.max_depth > 60) {
+		mgodpl_scene_destroy(sc.release());
+		return fail(MGODPL_E_INVALID_ARGUMENT, "BVH deeper than the traversal stack (pathological triangle distribution)");
 	}
 	if (opts && (opts->flags & MGODPL_SCENE_COUNTERS)) {
 		CU(cudaMalloc((void **) &sc->d_counters, CNT_N * sizeof(unsigned long long)));
@@ -243,7 +241,7 @@ int mgodpl_scene_create_u64(const double *verts, size_t nv, const uint64_t *tris
 }
 int mgodpl_scene_destroy(mgodpl_scene *s) {
 	if (!s) return MGODPL_OK;
-	cudaFree(s->built.nodes), cudaFree(s->built.tris), cudaFree(s->built.tri_ids), cudaFree(s->d_counters);
+	cudaFree(s->built.nodes), cudaFree(s->built.tris), cudaFree(s->built.tris32), cudaFree(s->built.tri_ids), cudaFree(s->d_counters);
 	delete s;
 	return MGODPL_OK;
 }
@@ -260,6 +258,7 @@ int mgodpl_scene_get_counters(mgodpl_scene *s, mgodpl_counters *out, int reset) 
 	CU(cudaMemcpy(v, s->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
 	out->states_checked = v[CNT_STATES], out->boxes_traversed = v[CNT_BOXES], out->nodes_visited = v[CNT_NODES];
 	out->leaf_tests = v[CNT_LEAF], out->motions_checked = v[CNT_MOTIONS], out->uncertain_steps = v[CNT_UNCERTAIN];
+	out->max_nodes_per_box = v[CNT_MAX_BOX_NODES];
 	if (reset) CU(cudaMemset(s->d_counters, 0, sizeof(v)));
 	return MGODPL_OK;
 }

@@ -8,21 +8,24 @@
 namespace mgodpl_b200 {
 
 // ---------------------------------------------------------------------------------------------------------------
-// Scene BVH, flattened in depth-first preorder with skip links ("stackless" traversal: a visit either steps to
-// node+1 or jumps to node.skip).  One node = two float4 = 32 B, so a lane fetches a node with two LDG.128:
-//   a = (centre.x, centre.y, centre.z, as_float(skip))       coordinates are relative to SceneDev::origin
-//   b = (half.x,   half.y,   half.z,   as_float(leaf_info))  half extents are rounded outward
-// leaf_info < 0  : internal node
-// leaf_info >= 0 : leaf; (leaf_info >> 4) = first triangle slot, (leaf_info & 15) + 1 = triangle count
+// Scene BVH: binary tree over the triangles, one 64-byte record per internal node (four float4 = four 16-byte loads,
+// one 64 B half-line), records in depth-first preorder so a left child sits right behind its parent.  A record holds
+// BOTH children (boxes relative to SceneDev::origin, centre + half extent rounded outward, and references):
+//   f4[0] = (L.cx, L.cy, L.cz, L.hx)   f4[1] = (L.hy, L.hz, R.cx, R.cy)   f4[2] = (R.cz, R.hx, R.hy, R.hz)
+//   f4[3] = (as_float(L.ref), as_float(R.ref), -, -)
+// ref >= 0 : record index of an internal child
+// ref <  0 : leaf; info = -1 - ref, (info >> 4) = first triangle slot, (info & 15) + 1 = triangle count
+// One visit therefore tests two boxes per dependent fetch, and leaves never cost a fetch of their own.
 // Triangles are stored in leaf (preorder) order as 9 fp64 world coordinates, so a leaf's triangles are contiguous.
 // ---------------------------------------------------------------------------------------------------------------
 struct SceneDev {
-	const float4 *nodes;     // 2 * n_nodes float4
-	const double *tris;      // 9 * n_tris doubles (v0 v1 v2), world frame, leaf order
+	const float4 *nodes;     // 4 * n_nodes float4
+	const double *tris;      // 9 * n_tris doubles (v0 v1 v2), world frame, leaf order: the exact test reads these
+	const float4 *tris32;    // 3 * n_tris float4 (v0 v1 v2 relative to origin, w unused): the fp32 pre-filter reads these
 	uint32_t n_nodes;
 	uint32_t n_tris;
 	double origin[3];        // fp32 node coordinates are relative to this point (centre of the scene bounds)
-	float root_c[3], root_h[3]; // root bounds relative to origin (same as node 0)
+	float root_c[3], root_h[3]; // scene bounds relative to origin (centre, half extent)
 	float margin;            // conservative inflation applied to every fp32 cull test
 	unsigned long long *counters; // mgodpl_counters as 6 x u64, or nullptr
 };
@@ -74,6 +77,6 @@ struct Tf64 {
 };
 
 // Counter slots (mgodpl_counters order)
-enum { CNT_STATES = 0, CNT_BOXES, CNT_NODES, CNT_LEAF, CNT_MOTIONS, CNT_UNCERTAIN, CNT_N };
+enum { CNT_STATES = 0, CNT_BOXES, CNT_NODES, CNT_LEAF, CNT_MOTIONS, CNT_UNCERTAIN, CNT_MAX_BOX_NODES, CNT_N };
 
 }  // namespace mgodpl_b200

@@ -125,6 +125,65 @@ __device__ __forceinline__ bool cull_overlap(const CullBox &b, float ncx, float 
 	return !sep;
 }
 
+/// fp32 pre-filter of the narrow phase: the same 13 separating axes as the exact test, evaluated in fp32 on
+/// origin-relative coordinates against the *inflated* culling box.  It may only answer "certainly separated": the
+/// inflation (SceneDev::margin, >= 10x the fp32 error of these projections at scene scale) turns every rounding
+/// error into a slightly larger box, and any axis — even an inexact one — that separates the triangle from the larger
+/// box separates it from the real one.  Everything else (overlap or a near miss) goes to the fp64 test.
+enum TriVerdict : int { TRI_SEPARATED = 0, TRI_HIT = 1, TRI_UNKNOWN = 2 };
+/// The pre-filter can also answer "certainly hit" in the one situation where that is trivially sound: a triangle
+/// vertex lies inside the box shrunk by the margin.  (Most real contacts of small tree triangles with a link box are
+/// of this kind, so the fp64 test is left with grazing configurations only.)
+__device__ __forceinline__ int tri_classify(const CullBox &b, float margin, float4 v0, float4 v1, float4 v2) {
+	float px[3], py[3], pz[3];
+	const float4 v[3] = {v0, v1, v2};
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const float dx = v[k].x - b.cx, dy = v[k].y - b.cy, dz = v[k].z - b.cz;
+		px[k] = b.r[0] * dx + b.r[3] * dy + b.r[6] * dz;
+		py[k] = b.r[1] * dx + b.r[4] * dy + b.r[7] * dz;
+		pz[k] = b.r[2] * dx + b.r[5] * dy + b.r[8] * dz;
+	}
+	if (fminf(px[0], fminf(px[1], px[2])) > b.hx || fmaxf(px[0], fmaxf(px[1], px[2])) < -b.hx) return TRI_SEPARATED;
+	if (fminf(py[0], fminf(py[1], py[2])) > b.hy || fmaxf(py[0], fmaxf(py[1], py[2])) < -b.hy) return TRI_SEPARATED;
+	if (fminf(pz[0], fminf(pz[1], pz[2])) > b.hz || fmaxf(pz[0], fmaxf(pz[1], pz[2])) < -b.hz) return TRI_SEPARATED;
+	{
+		const float sx = b.hx - 2.f * margin, sy = b.hy - 2.f * margin, sz = b.hz - 2.f * margin;  // true extent minus the margin
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+			if (fabsf(px[k]) < sx && fabsf(py[k]) < sy && fabsf(pz[k]) < sz) return TRI_HIT;
+	}
+	const float fx[3] = {px[1] - px[0], px[2] - px[1], px[0] - px[2]};
+	const float fy[3] = {py[1] - py[0], py[2] - py[1], py[0] - py[2]};
+	const float fz[3] = {pz[1] - pz[0], pz[2] - pz[1], pz[0] - pz[2]};
+	{  // triangle plane
+		const float nx = fy[0] * fz[1] - fz[0] * fy[1], ny = fz[0] * fx[1] - fx[0] * fz[1], nz = fx[0] * fy[1] - fy[0] * fx[1];
+		const float q0 = nx * px[0] + ny * py[0] + nz * pz[0], q1 = nx * px[1] + ny * py[1] + nz * pz[1],
+					q2 = nx * px[2] + ny * py[2] + nz * pz[2];
+		const float rad = b.hx * fabsf(nx) + b.hy * fabsf(ny) + b.hz * fabsf(nz);
+		if (fminf(q0, fminf(q1, q2)) > rad || fmaxf(q0, fmaxf(q1, q2)) < -rad) return TRI_SEPARATED;
+	}
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {  // box axis x edge k: project all three vertices (no "two are equal" shortcut)
+		{
+			const float q0 = py[0] * fz[k] - pz[0] * fy[k], q1 = py[1] * fz[k] - pz[1] * fy[k], q2 = py[2] * fz[k] - pz[2] * fy[k];
+			const float rad = b.hy * fabsf(fz[k]) + b.hz * fabsf(fy[k]);
+			if (fminf(q0, fminf(q1, q2)) > rad || fmaxf(q0, fmaxf(q1, q2)) < -rad) return TRI_SEPARATED;
+		}
+		{
+			const float q0 = pz[0] * fx[k] - px[0] * fz[k], q1 = pz[1] * fx[k] - px[1] * fz[k], q2 = pz[2] * fx[k] - px[2] * fz[k];
+			const float rad = b.hx * fabsf(fz[k]) + b.hz * fabsf(fx[k]);
+			if (fminf(q0, fminf(q1, q2)) > rad || fmaxf(q0, fmaxf(q1, q2)) < -rad) return TRI_SEPARATED;
+		}
+		{
+			const float q0 = px[0] * fy[k] - py[0] * fx[k], q1 = px[1] * fy[k] - py[1] * fx[k], q2 = px[2] * fy[k] - py[2] * fx[k];
+			const float rad = b.hx * fabsf(fy[k]) + b.hy * fabsf(fx[k]);
+			if (fminf(q0, fminf(q1, q2)) > rad || fmaxf(q0, fmaxf(q1, q2)) < -rad) return TRI_SEPARATED;
+		}
+	}
+	return TRI_UNKNOWN;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Exact narrow phase: closed oriented box vs closed triangle, 13-axis separating-axis test in the box frame, fp64.
 // Stands where FCL's box/triangle test stood behind fcl::collide (collision_detection.cpp:36-45); touching counts

@@ -38,9 +38,11 @@ cudaError_t launch_knn(const double *d_states, size_t n, size_t stride, int js, 
 struct BuiltScene {
 	float4 *nodes = nullptr;
 	double *tris = nullptr;
+	float4 *tris32 = nullptr;
 	uint32_t *tri_ids = nullptr;  // original triangle index of every stored triangle slot
 	uint32_t n_nodes = 0, n_tris = 0, n_leaves = 0, max_depth = 0, max_leaf = 0;
 	double sah_cost = 0, build_ms = 0;
+	float root_c[3] = {0, 0, 0}, root_h[3] = {-1, -1, -1};  // scene bounds relative to the origin, rounded outward
 	size_t device_bytes = 0;
 };
 /// d_verts: nv x 3 doubles, d_tris: nt x 3 uint32 (device).  lo/hi: scene bounds (host, from the vertices used).

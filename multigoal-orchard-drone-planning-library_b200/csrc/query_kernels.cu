@@ -87,27 +87,85 @@ __device__ __forceinline__ ExactBox make_exact_box(D3 c, Q4 q, const double *hal
 	return eb;
 }
 
+/// fp32 classification of a leaf's triangles against one box: returns TRI_HIT as soon as one triangle certainly
+/// touches, otherwise the set of triangles that still need the exact test (bit k of *unknown).
+__device__ __forceinline__ bool leaf_prefilter(const SceneDev &sc, const CullBox &cb, int ref, unsigned *unknown) {
+	const unsigned info = (unsigned) (-1 - ref), first = info >> 4, cnt = (info & 15u) + 1u;
+	*unknown = 0;
+	for (unsigned k = 0; k < cnt; ++k) {
+		const float4 *t = sc.tris32 + 3ull * (first + k);
+		const int v = tri_classify(cb, sc.margin, __ldg(t), __ldg(t + 1), __ldg(t + 2));
+		if (v == TRI_HIT) return true;
+		if (v == TRI_UNKNOWN) *unknown |= 1u << k;
+	}
+	return false;
+}
+
+/// The exact phase of one parked lane, kept out of line: re-read the fp64 pose of the queued box, build the exact box
+/// and test the triangles the pre-filter could not decide.  Rare and register-hungry (fp64): as a separate function its
+/// register demand does not shape the traversal loop.
+__device__ __noinline__ bool exact_leaf_test(const SceneDev &sc, const void *exact_pose, const double *half, int ref, unsigned unknown,
+											 unsigned *n_tests) {
+	const unsigned info = (unsigned) (-1 - ref), first = info >> 4, cnt = (info & 15u) + 1u;
+	const double2 *ex = reinterpret_cast<const double2 *>(exact_pose);
+	const double2 e0 = __ldcg(ex), e1 = __ldcg(ex + 1), e2 = __ldcg(ex + 2), e3 = __ldcg(ex + 3);
+	const ExactBox eb = make_exact_box(D3{e0.x, e0.y, e1.x}, Q4{e1.y, e2.x, e2.y, e3.x}, half);
+	for (unsigned k = 0; k < cnt; ++k) {
+		if (!(unknown >> k & 1u)) continue;
+		++*n_tests;
+		if (box_triangle_hit(eb, sc.tris + 9ull * (first + k))) return true;
+	}
+	return false;
+}
+
+constexpr int STACK_DEPTH = 64;        // scene creation rejects trees deeper than 60 levels
+constexpr int REF_END = (int) 0x80000000;  // "nothing left to visit"
+
+/// Test both children of record `cur`; returns the next reference to visit (pushing the other overlapping child).
+__device__ __forceinline__ int visit_record(const SceneDev &sc, const CullBox &cb, int cur, int *stack, int &sp) {
+	const float4 *rec = sc.nodes + 4ull * (unsigned) cur;
+	const float4 n0 = __ldg(rec), n1 = __ldg(rec + 1), n2 = __ldg(rec + 2), n3 = __ldg(rec + 3);
+	const bool ov_l = cull_overlap(cb, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
+	const bool ov_r = cull_overlap(cb, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+	const int lref = __float_as_int(n3.x), rref = __float_as_int(n3.y);
+	int next = REF_END;
+	if (ov_l) next = lref;
+	if (ov_r) {
+		if (next == REF_END) next = rref;
+		else stack[sp++] = rref;
+	}
+	if (next == REF_END && sp > 0) next = stack[--sp];
+	return next;
+}
+
+/// Exact test of the box against every triangle of one leaf reference.
+__device__ __forceinline__ bool leaf_hit(const SceneDev &sc, const CullBox &cb, const ExactBox &eb, int ref, LocalCounters &lc) {
+	const unsigned info = (unsigned) (-1 - ref), first = info >> 4, cnt = (info & 15u) + 1u;
+	unsigned unknown;
+	if (leaf_prefilter(sc, cb, ref, &unknown)) return true;
+	for (unsigned k = 0; k < cnt; ++k) {
+		if (!(unknown >> k & 1u)) continue;
+		lc.leaf++;
+		if (box_triangle_hit(eb, sc.tris + 9ull * (first + k))) return true;
+	}
+	return false;
+}
+
 /// Plain one-thread traversal (stage A's queue-overflow path): does the box touch any triangle of the scene?
 __device__ __noinline__ bool box_hits_scene(const SceneDev &sc, const CullBox &cb, D3 c, Q4 q, const double *half,
 											LocalCounters &lc) {
+	if (!sc.n_nodes) return false;
 	const ExactBox eb = make_exact_box(c, q, half);
-	const unsigned n_nodes = sc.n_nodes;
-	unsigned node = 0;
+	int stack[STACK_DEPTH], sp = 0, cur = 0;
 	lc.boxes++;
-	while (node < n_nodes) {
-		const float4 a = __ldg(sc.nodes + 2 * node);
-		const float4 b = __ldg(sc.nodes + 2 * node + 1);
-		const bool ov = cull_overlap(cb, a.x, a.y, a.z, b.x, b.y, b.z);
-		const int leaf = __float_as_int(b.w);
-		lc.nodes++;
-		if (ov && leaf >= 0) {
-			const unsigned first = (unsigned) leaf >> 4, cnt = ((unsigned) leaf & 15u) + 1u;
-			for (unsigned k = 0; k < cnt; ++k) {
-				lc.leaf++;
-				if (box_triangle_hit(eb, sc.tris + 9ull * (first + k))) return true;
-			}
+	while (cur != REF_END) {
+		if (cur >= 0) {
+			lc.nodes++;
+			cur = visit_record(sc, cb, cur, stack, sp);
+		} else {
+			if (leaf_hit(sc, cb, eb, cur, lc)) return true;
+			cur = sp > 0 ? stack[--sp] : REF_END;
 		}
-		node = (ov && leaf < 0) ? node + 1 : __float_as_uint(a.w);
 	}
 	return false;
 }
@@ -460,8 +518,9 @@ k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant
 // Stage B: drain the queue.  Persistent warps, one box per lane, "while-while" with lane refill:
 //   refill   lanes whose box is finished take the next queued boxes (warp-local chunks of the queue, so neighbouring
 //            lanes hold neighbouring interpolation steps / samples and walk the tree together);
-//   descend  every lane steps through the skip-link BVH until it reaches an overlapping leaf (it parks there) or runs
-//            out of nodes (it goes idle); the warp leaves this loop once a refill or a leaf batch is worthwhile;
+//   descend  every lane walks the BVH (one 64-byte record = both children per visit, small per-lane stack) until it
+//            reaches an overlapping leaf (it parks there) or runs out of nodes (it goes idle); the warp leaves this
+//            loop once a refill or a leaf batch is worthwhile;
 //   leaves   lanes parked on a leaf run the exact fp64 box/triangle test together, in batches of >= leaf_min lanes
 //            (the test is ~400 instructions; running it for 3 lanes at a time cost as much as all descents).
 // Without refill a warp's time is its slowest lane (a few boxes deep in the canopy among many that die at the top
@@ -478,20 +537,21 @@ __global__ void __launch_bounds__(BLOCK_B, MIN_BLOCKS)
 k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ explicit_boxes,
 		   QueueDev Q, Results res, TraverseTuning tune) {
 	const int REFILL_MIN = tune.refill_min, LEAF_MIN = tune.leaf_min;
-	constexpr unsigned FULL = 0xffffffffu, END = 0xffffffffu;
+	constexpr unsigned FULL = 0xffffffffu;
 	const unsigned lane = threadIdx.x & 31;
-	const unsigned n_items = min(__ldcg(Q.count), Q.cap);
-	const unsigned n_nodes = sc.n_nodes;
+	const unsigned n_items = sc.n_nodes ? min(__ldcg(Q.count), Q.cap) : 0u;
 	LocalCounters lc;
 	unsigned chunk_lo = 0, chunk_hi = 0;  // warp-uniform: unclaimed part of this warp's chunk
 	bool exhausted = false;               // warp-uniform: the queue has nothing left to claim
-	// lane state
+	// lane state: cur >= 0 walking (record index) | cur < 0 parked on a leaf reference | REF_END idle
 	CullBox cb{};
-	unsigned node = END, owner = 0, step_box = 0, item = 0;
-	int pending = -1;  // leaf info of an overlapping leaf awaiting its exact test
+	unsigned owner = 0, step_box = 0, item = 0;
+	int cur = REF_END, sp = 0;
+	int stack[STACK_DEPTH];
+	unsigned box_nodes = 0, max_box_nodes = 0;  // longest single descent (counters only)
 
 	for (;;) {
-		const bool idle = node >= n_nodes && pending < 0;
+		const bool idle = cur == REF_END;
 		const unsigned idle_mask = __ballot_sync(FULL, idle);
 		if (idle_mask == FULL && exhausted) break;
 		// ---- refill ---------------------------------------------------------------------------------------------
@@ -525,8 +585,9 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 						h0 = (float) hh[0], h1 = (float) hh[1], h2 = (float) hh[2];
 					}
 					finish_cull_box(sc, cb, h0, h1, h2);
-					node = 0;
+					cur = 0, sp = 0;
 					lc.boxes++;
+					max_box_nodes = max(max_box_nodes, box_nodes), box_nodes = 0;
 				}
 			}
 			chunk_lo += min(avail, (unsigned) __popc(idle_mask));
@@ -534,59 +595,52 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 		}
 		// ---- descend: until another action becomes worthwhile (enough idle lanes to refill, enough parked lanes for a
 		//      leaf batch) or nobody is left walking ------------------------------------------------------------------
-		bool run = node < n_nodes && pending < 0;
-		unsigned go = __ballot_sync(FULL, run), parked = __ballot_sync(FULL, pending >= 0);
+		unsigned go = __ballot_sync(FULL, cur >= 0), parked = __ballot_sync(FULL, cur < 0 && cur != REF_END);
 		while (go) {
-			if (run) {
-				const float4 a = __ldg(sc.nodes + 2 * node);
-				const float4 b = __ldg(sc.nodes + 2 * node + 1);
-				const bool ov = cull_overlap(cb, a.x, a.y, a.z, b.x, b.y, b.z);
-				const int leaf = __float_as_int(b.w);
-				lc.nodes++;
-				if (ov && leaf >= 0) pending = leaf;
-				node = (ov && leaf < 0) ? node + 1 : __float_as_uint(a.w);
-				run = node < n_nodes && pending < 0;
+			if (cur >= 0) {
+				lc.nodes++, box_nodes++;
+				cur = visit_record(sc, cb, cur, stack, sp);
 			}
-			go = __ballot_sync(FULL, run);
-			parked = __ballot_sync(FULL, pending >= 0);
+			go = __ballot_sync(FULL, cur >= 0);
+			parked = __ballot_sync(FULL, cur < 0 && cur != REF_END);
 			if (__popc(parked) >= LEAF_MIN) break;
 			if (!exhausted && 32 - __popc(go) - __popc(parked) >= REFILL_MIN) break;
 		}
 		// ---- leaves: parked lanes run the exact test together, once there are enough of them or nothing else can move -----
 		if (__popc(parked) >= LEAF_MIN || (!go && parked)) {
-			if (pending >= 0) {
-				const unsigned first = (unsigned) pending >> 4, cnt = ((unsigned) pending & 15u) + 1u;
-				pending = -1;
+			if (cur < 0 && cur != REF_END) {
 				const unsigned step = step_box & 0x0FFFFFFFu;
 				if (already_decided(res, owner, step)) {
-					node = END;
+					cur = REF_END;
 				} else {
-					const double2 *ex = reinterpret_cast<const double2 *>(reinterpret_cast<const char *>(Q.items + item) + ITEM_EXACT_OFFSET);
-					const double2 e0 = __ldcg(ex), e1 = __ldcg(ex + 1), e2 = __ldcg(ex + 2), e3 = __ldcg(ex + 3);
-					double half_buf[3];
-					const double *half;
-					if (explicit_boxes) {
-						const double *bx = explicit_boxes + (size_t) owner * 10;
-						half_buf[0] = __ldg(bx + 7) * 0.5, half_buf[1] = __ldg(bx + 8) * 0.5, half_buf[2] = __ldg(bx + 9) * 0.5;
-						half = half_buf;
-					} else {
-						half = rb.boxes[step_box >> 28].half;
-					}
-					const ExactBox eb = make_exact_box(D3{e0.x, e0.y, e1.x}, Q4{e1.y, e2.x, e2.y, e3.x}, half);
-					bool hit = false;
-					for (unsigned k = 0; k < cnt && !hit; ++k) {
-						lc.leaf++;
-						hit = box_triangle_hit(eb, sc.tris + 9ull * (first + k));
+					unsigned unknown = 0;
+					bool hit = leaf_prefilter(sc, cb, cur, &unknown);
+					if (!hit && unknown) {
+						double half_buf[3];
+						const double *half;
+						if (explicit_boxes) {
+							const double *bx = explicit_boxes + (size_t) owner * 10;
+							half_buf[0] = __ldg(bx + 7) * 0.5, half_buf[1] = __ldg(bx + 8) * 0.5, half_buf[2] = __ldg(bx + 9) * 0.5;
+							half = half_buf;
+						} else {
+							half = rb.boxes[step_box >> 28].half;
+						}
+						unsigned n_exact = 0;
+						hit = exact_leaf_test(sc, reinterpret_cast<const char *>(Q.items + item) + ITEM_EXACT_OFFSET, half, cur, unknown, &n_exact);
+						lc.leaf += n_exact;
 					}
 					if (hit) {
 						report_hit(res, owner, step);
-						node = END;
+						cur = REF_END;
+					} else {
+						cur = sp > 0 ? stack[--sp] : REF_END;
 					}
 				}
 			}
 		}
 	}
 	flush_counters(sc, lc);
+	if (sc.counters) atomicMax(sc.counters + CNT_MAX_BOX_NODES, (unsigned long long) max(max_box_nodes, box_nodes));
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -181,15 +181,28 @@ __device__ __forceinline__ float half_area(float4 lo, float4 hi) {
 	return x * y + y * z + z * x;
 }
 
-/// One thread per construction node.  Walking to the root yields the node's preorder slot (nodes before it) and its
-/// leaf rank (triangles before it), for whatever shape the rotations left the tree in.  Surviving nodes emit their
-/// 32-byte traversal record (centre, skip | half extent, leaf info); original leaves also place their triangle — 9 fp64
-/// world coordinates — at its leaf-order slot, so every (collapsed) leaf owns a contiguous run of slots.
-__global__ void k_flatten(int n, const int *__restrict__ left, const int *__restrict__ parent, const float4 *__restrict__ blo,
-						  const float4 *__restrict__ bhi, const unsigned *__restrict__ tri_count, const unsigned *__restrict__ eff_size,
-						  unsigned max_leaf, const double *__restrict__ verts, const uint32_t *__restrict__ tris,
-						  const uint32_t *__restrict__ ids, float4 *__restrict__ nodes, double *__restrict__ tri_out,
-						  uint32_t *__restrict__ slot_ids, BuildStats *__restrict__ stats) {
+__device__ __forceinline__ void centre_half(float4 lo, float4 hi, float *c, float *h) {
+	const float lo3[3] = {lo.x, lo.y, lo.z}, hi3[3] = {hi.x, hi.y, hi.z};
+	for (int a = 0; a < 3; ++a) {
+		double cd = 0.5 * ((double) lo3[a] + (double) hi3[a]);
+		c[a] = (float) cd;
+		h[a] = __double2float_ru(0.5 * ((double) hi3[a] - (double) lo3[a]) + fabs(cd - (double) c[a]));  // rounded outward
+	}
+}
+
+/// One thread per construction node.  Walking to the root yields the node's preorder rank among the surviving internal
+/// nodes and its leaf rank (triangles before it), for whatever shape the rotations left the tree in.
+///  * every surviving internal node emits one 64-byte traversal record holding BOTH children's boxes and references
+///    (see device_types.cuh), so a visit tests two boxes per dependent fetch and leaves never cost a fetch of their own;
+///  * every original leaf places its triangle — 9 fp64 world coordinates — at its leaf-order slot, so each (collapsed)
+///    leaf owns a contiguous run of slots.
+__global__ void k_flatten(int n, const int *__restrict__ left, const int *__restrict__ right, const int *__restrict__ parent,
+						  const float4 *__restrict__ blo, const float4 *__restrict__ bhi, const unsigned *__restrict__ tri_count,
+						  const unsigned *__restrict__ eff_size, unsigned max_leaf, const double *__restrict__ verts,
+						  const uint32_t *__restrict__ tris, const uint32_t *__restrict__ ids, float4 *__restrict__ nodes,
+						  double *__restrict__ tri_out, float4 *__restrict__ tri32_out, D3 origin, uint32_t *__restrict__ slot_ids,
+						  float4 *__restrict__ root_box,
+						  BuildStats *__restrict__ stats) {
 	int x = blockIdx.x * TB + threadIdx.x;
 	if (x >= 2 * n - 1) return;
 	const int root = 0;  // internal node 0, or — when n == 1 — the single leaf (id n-1 == 0)
@@ -197,10 +210,10 @@ __global__ void k_flatten(int n, const int *__restrict__ left, const int *__rest
 	const bool swallowed = p >= 0 && tri_count[p] <= max_leaf;  // inside a collapsed leaf
 	const bool original_leaf = x >= n - 1;
 	if (swallowed && !original_leaf) return;
-	unsigned pre = 0, depth = 0, tri_before = 0;
+	unsigned pre = 0, depth = 0, tri_before = 0;  // pre: internal records before this node in preorder
 	for (int c = x; p >= 0; c = p, p = parent[p]) {
 		const int l = left[p];
-		if (c != l) pre += eff_size[l], tri_before += tri_count[l];
+		if (c != l) pre += (eff_size[l] - 1u) / 2u, tri_before += tri_count[l];
 		pre += 1u;
 		++depth;
 	}
@@ -210,23 +223,13 @@ __global__ void k_flatten(int n, const int *__restrict__ left, const int *__rest
 		for (int k = 0; k < 3; ++k) {
 			const double *v = verts + 3ull * tris[3ull * t + k];
 			tri_out[9ull * tri_before + 3 * k] = v[0], tri_out[9ull * tri_before + 3 * k + 1] = v[1], tri_out[9ull * tri_before + 3 * k + 2] = v[2];
+			tri32_out[3ull * tri_before + k] = make_float4((float) (v[0] - origin.x), (float) (v[1] - origin.y), (float) (v[2] - origin.z), 0.f);
 		}
 	}
 	if (swallowed) return;
 	const unsigned cnt = tri_count[x];
 	const bool leaf = cnt <= max_leaf;
 	const float4 lo = blo[x], hi = bhi[x];
-	float c[3], h[3];
-	const float lo3[3] = {lo.x, lo.y, lo.z}, hi3[3] = {hi.x, hi.y, hi.z};
-	for (int a = 0; a < 3; ++a) {
-		double cd = 0.5 * ((double) lo3[a] + (double) hi3[a]);
-		c[a] = (float) cd;
-		h[a] = __double2float_ru(0.5 * ((double) hi3[a] - (double) lo3[a]) + fabs(cd - (double) c[a]));
-	}
-	const unsigned skip = pre + eff_size[x];
-	const int info = leaf ? (int) (tri_before << 4 | (cnt - 1)) : -1;
-	nodes[2 * pre] = make_float4(c[0], c[1], c[2], __uint_as_float(skip));
-	nodes[2 * pre + 1] = make_float4(h[0], h[1], h[2], __int_as_float(info));
 	// statistics
 	const float root_area = half_area(blo[root], bhi[root]);
 	double cost = root_area > 0.f ? (double) half_area(lo, hi) / (double) root_area * (leaf ? (double) cnt : 1.0) : 0.0;
@@ -236,6 +239,29 @@ __global__ void k_flatten(int n, const int *__restrict__ left, const int *__rest
 		atomicMax(&stats->max_leaf, cnt);
 		atomicMax(&stats->max_depth, depth);
 	}
+	if (x == root) root_box[0] = lo, root_box[1] = hi;
+	float c0[3], h0[3], c1[3], h1[3];
+	int lref, rref;
+	if (leaf) {
+		if (x != root) return;  // leaves live inside their parent's record
+		// the whole scene fits one leaf: a single record whose second child can never overlap
+		centre_half(lo, hi, c0, h0);
+		lref = -1 - (int) (0u << 4 | (cnt - 1));
+		c1[0] = c1[1] = c1[2] = 0.f, h1[0] = h1[1] = h1[2] = -3.0e38f;
+		rref = lref;
+	} else {
+		const int l = left[x], r = right[x];
+		const unsigned cl = tri_count[l], cr = tri_count[r];
+		centre_half(blo[l], bhi[l], c0, h0);
+		centre_half(blo[r], bhi[r], c1, h1);
+		lref = cl <= max_leaf ? -1 - (int) (tri_before << 4 | (cl - 1)) : (int) (pre + 1u);
+		rref = cr <= max_leaf ? -1 - (int) ((tri_before + cl) << 4 | (cr - 1)) : (int) (pre + 1u + (eff_size[l] - 1u) / 2u);
+	}
+	float4 *rec = nodes + 4ull * pre;
+	rec[0] = make_float4(c0[0], c0[1], c0[2], h0[0]);
+	rec[1] = make_float4(h0[1], h0[2], c1[0], c1[1]);
+	rec[2] = make_float4(c1[2], h1[0], h1[1], h1[2]);
+	rec[3] = make_float4(__int_as_float(lref), __int_as_float(rref), 0.f, 0.f);
 }
 
 struct Scratch {
@@ -327,14 +353,21 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 		BS_CHECK(cudaGetLastError());
 	}
 	// The flattened size is the root's effective size; fetch it before allocating the node array.
-	unsigned n_nodes = 0;
-	BS_CHECK(cudaMemcpyAsync(&n_nodes, eff_size, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+	unsigned root_size = 0;
+	BS_CHECK(cudaMemcpyAsync(&root_size, eff_size, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
 	BS_CHECK(cudaStreamSynchronize(stream));
-	BS_CHECK(cudaMalloc((void **) &out->nodes, (size_t) n_nodes * 2 * sizeof(float4)));
+	const unsigned n_nodes = root_size > 1 ? (root_size - 1) / 2 : 1;  // one 64-byte record per surviving internal node
+	float4 *d_root_box;
+	BS_CHECK(tmp.alloc(&d_root_box, 2));
+	BS_CHECK(cudaMalloc((void **) &out->nodes, (size_t) n_nodes * 4 * sizeof(float4)));
 	BS_CHECK(cudaMalloc((void **) &out->tris, nt * 9 * sizeof(double)));
-	k_flatten<<<(unsigned) ((2 * nt - 1 + TB - 1) / TB), TB, 0, stream>>>(n, left, parent, blo, bhi, tri_count, eff_size, max_leaf_size,
-																		  d_verts, d_tris, ids2, out->nodes, out->tris, ids, d_stats);
+	BS_CHECK(cudaMalloc((void **) &out->tris32, nt * 3 * sizeof(float4)));
+	k_flatten<<<(unsigned) ((2 * nt - 1 + TB - 1) / TB), TB, 0, stream>>>(n, left, right, parent, blo, bhi, tri_count, eff_size,
+																		  max_leaf_size, d_verts, d_tris, ids2, out->nodes, out->tris, out->tris32,
+																		  D3{origin[0], origin[1], origin[2]}, ids, d_root_box, d_stats);
 	BS_CHECK(cudaGetLastError());
+	float4 h_root[2];
+	BS_CHECK(cudaMemcpyAsync(h_root, d_root_box, sizeof(h_root), cudaMemcpyDeviceToHost, stream));
 	BS_CHECK(cudaEventRecord(ev1, stream));
 	BuildStats st{};
 	BS_CHECK(cudaMemcpyAsync(&st, d_stats, sizeof(st), cudaMemcpyDeviceToHost, stream));
@@ -350,7 +383,18 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 	out->max_leaf = st.max_leaf;
 	out->sah_cost = st.sah;
 	out->build_ms = ms;
-	out->device_bytes = (size_t) n_nodes * 32 + nt * 72 + nt * 4;
+	out->device_bytes = (size_t) n_nodes * 64 + nt * 72 + nt * 48 + nt * 4;
+	float rc[3], rh[3];
+	{
+		// same outward rounding as the device (centre in fp32, half extent padded by the centre's rounding error)
+		const float lo3[3] = {h_root[0].x, h_root[0].y, h_root[0].z}, hi3[3] = {h_root[1].x, h_root[1].y, h_root[1].z};
+		for (int a = 0; a < 3; ++a) {
+			double cd = 0.5 * ((double) lo3[a] + (double) hi3[a]);
+			rc[a] = (float) cd;
+			rh[a] = std::nextafter((float) (0.5 * ((double) hi3[a] - (double) lo3[a]) + std::fabs(cd - (double) rc[a])), 3.0e38f);
+		}
+	}
+	for (int a = 0; a < 3; ++a) out->root_c[a] = rc[a], out->root_h[a] = rh[a];
 	return cudaSuccess;
 }
 

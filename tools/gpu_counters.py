@@ -38,6 +38,6 @@ for leaf in [int(x) for x in (sys.argv[1:] or [1, 2, 4, 8])]:
             k = {x: v / 5 for x, v in c.items()}
             print(f"leaf={leaf} nodes={info.n_nodes} depth={info.max_depth} sah={info.sah_cost:.1f} | states={k['states_checked']:.3g} "
                   f"boxes={k['boxes_traversed']:.3g} nodes/box={k['nodes_visited']/max(k['boxes_traversed'],1):.1f} "
-                  f"leaftests/box={k['leaf_tests']/max(k['boxes_traversed'],1):.2f} ms(with counters)={ms:.3f}")
+                  f"leaftests/box={k['leaf_tests']/max(k['boxes_traversed'],1):.2f} max_records/box={c['max_nodes_per_box']} ms(with counters)={ms:.3f}")
         else:
             print(f"leaf={leaf} ms={ms:.3f}")
