@@ -487,7 +487,7 @@ int mgodpl_check_boxes(mgodpl_scene *scene, const double *boxes, size_t n, uint3
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Lease ws(scene->pool);
 	Carver c;
-	const size_t words = (n + 31) / 32, qb = query_scratch_bytes(n);
+	const size_t words = (n + 31) / 32, qb = query_scratch_bytes(n * 9 / 8 + 4096);
 	size_t o_in = c.take(n * 80), o_out = c.take(words * 4), o_q = c.take(qb);
 	CU(ws->reserve(c.off, words * 4));
 	CU(cudaMemcpyAsync(ws->dev + o_in, boxes, n * 80, cudaMemcpyHostToDevice, stream));
@@ -508,7 +508,7 @@ int mgodpl_check_states_device(mgodpl_scene *scene, const mgodpl_robot *robot, c
 	if (int rc = require_device()) return rc;
 	if (!n) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
-	const size_t qb = query_scratch_bytes(n * (size_t) robot->dev.n_boxes, n);
+	const size_t qb = query_scratch_bytes(n * (size_t) robot->dev.n_boxes + 4096, state_survivor_slots(n));
 	char *scratch = nullptr;
 	CU(scene->device_scratch(stream, qb, &scratch));
 	CU(launch_check_states(scene->dev, robot->dev, d_states, n, stride, d_hit_bits, scratch, qb, stream));
@@ -526,7 +526,7 @@ int mgodpl_check_states(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Lease ws(scene->pool);
 	Carver c;
-	const size_t in_b = n * stride * 8, words = (n + 31) / 32, qb = query_scratch_bytes(n * (size_t) robot->dev.n_boxes, n);
+	const size_t in_b = n * stride * 8, words = (n + 31) / 32, qb = query_scratch_bytes(n * (size_t) robot->dev.n_boxes + 4096, state_survivor_slots(n));
 	size_t o_in = c.take(in_b), o_out = c.take(words * 4), o_q = c.take(qb);
 	CU(ws->reserve(c.off, words * 4));
 	// Caller memory goes straight to the device; only the (small) result is staged through pinned memory.
@@ -682,7 +682,7 @@ int mgodpl_sample_goals_device(mgodpl_scene *scene, const mgodpl_robot *robot, c
 	if (int rc = require_device()) return rc;
 	if (!f || !s) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
-	const size_t qb = query_scratch_bytes(f * s * (size_t) robot->dev.n_boxes);
+	const size_t qb = query_scratch_bytes(f * s * (size_t) robot->dev.n_boxes * 9 / 8 + 4096);
 	char *scratch = nullptr;
 	CU(scene->device_scratch(stream, qb, &scratch));
 	CU(launch_sample_goals(scene->dev, robot->dev, d_targets, f, d_draws, robot->d_limits, s, seed, dist, d_hit_bits, d_collisions,
@@ -700,7 +700,7 @@ int mgodpl_sample_goals(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	const int nv = robot->dev.n_vars;
 	Lease ws(scene->pool);
 	Carver c;
-	const size_t wpr = (s + 31) / 32, qb = query_scratch_bytes(f * s * (size_t) robot->dev.n_boxes);
+	const size_t wpr = (s + 31) / 32, qb = query_scratch_bytes(f * s * (size_t) robot->dev.n_boxes * 9 / 8 + 4096);
 	size_t o_t = c.take(f * 24), o_d = c.take(draws ? s * (1 + nv) * 8 : 0);
 	size_t o_hit = c.take(f * wpr * 4), o_cnt = c.take(f * 4);
 	const size_t small_hi = c.off;

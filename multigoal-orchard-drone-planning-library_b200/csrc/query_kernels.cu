@@ -170,9 +170,43 @@ __device__ __noinline__ bool box_hits_scene(const SceneDev &sc, const CullBox &c
 	return false;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sharded append lists.  A single append counter serialises in L2: ~300 k warp-level atomics on one address cost
+// ~0.3 ms, 3x the HBM time of a 10 M-state batch.  Both work lists therefore keep SHARDS counters; shard s owns the
+// 32-slot blocks s, s + SHARDS, s + 2 SHARDS, ... of the list, a producer warp always appends to the same shard, and
+// consumers walk the flat slot range, skipping the holes (slots beyond their shard's count).  Blocks of 32 keep a
+// warp's consecutive appends contiguous, so neighbouring consumer lanes still see neighbouring queries.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr unsigned SHARDS = 64, SHARD_BLOCK = 32;
+constexpr unsigned COUNTER_STRIDE = 32;  // one 128-byte line per counter: neighbouring counters would share an L2 atomic unit
+constexpr size_t SCRATCH_HEADER = 2 * SHARDS * COUNTER_STRIDE * sizeof(unsigned) + 256;
+
+__device__ __forceinline__ unsigned my_shard() { return (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (SHARDS - 1); }
+__device__ __forceinline__ unsigned shard_slot(unsigned shard, unsigned local) {
+	return ((local / SHARD_BLOCK) * SHARDS + shard) * SHARD_BLOCK + (local % SHARD_BLOCK);
+}
+/// Consumers copy the SHARDS counters of a finished list into shared memory once per block (block-wide call).
+__device__ __forceinline__ void load_shard_counts(unsigned *s_counts, const unsigned *counts) {
+	if (threadIdx.x < SHARDS) s_counts[threadIdx.x] = __ldcg(counts + threadIdx.x * COUNTER_STRIDE);
+	__syncthreads();
+}
+/// Is flat slot `idx` filled?
+__device__ __forceinline__ bool slot_filled(const unsigned *s_counts, unsigned idx) {
+	const unsigned blk = idx / SHARD_BLOCK, shard = blk % SHARDS, local = (blk / SHARDS) * SHARD_BLOCK + idx % SHARD_BLOCK;
+	return local < s_counts[shard];
+}
+/// Flat slot range that covers every filled slot (warp-uniform; all 32 lanes must call).
+__device__ __forceinline__ unsigned slot_range(const unsigned *s_counts, unsigned cap) {
+	const unsigned lane = threadIdx.x & 31;
+	unsigned m = max(s_counts[lane], s_counts[lane + 32]);
+	for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+	const unsigned long long r = (unsigned long long) ((m + SHARD_BLOCK - 1) / SHARD_BLOCK) * SHARDS * SHARD_BLOCK;
+	return (unsigned) (r < cap ? r : cap);
+}
+
 struct QueueDev {
 	Item *items;
-	unsigned *count;   // items appended so far (may exceed cap: the excess was traversed inline)
+	unsigned *counts;  // SHARDS append counters (a shard may run past cap: the excess was traversed inline)
 	unsigned *cursor;  // stage B's chunk dispenser
 	unsigned cap;
 };
@@ -184,8 +218,9 @@ __device__ __forceinline__ void emit_box(const SceneDev &sc, const QueueDev &Q, 
 	if (!cull_overlap(cb, sc.root_c[0], sc.root_c[1], sc.root_c[2], sc.root_h[0], sc.root_h[1], sc.root_h[2])) return;
 	cg::coalesced_group g = cg::coalesced_threads();
 	unsigned base = 0;
-	if (g.thread_rank() == 0) base = atomicAdd(Q.count, g.size());
-	const unsigned pos = g.shfl(base, 0) + g.thread_rank();
+	const unsigned shard = my_shard();
+	if (g.thread_rank() == 0) base = atomicAdd(Q.counts + shard * COUNTER_STRIDE, g.size());
+	const unsigned pos = shard_slot(shard, g.shfl(base, 0) + g.thread_rank());
 	if (pos < Q.cap) {
 		uint4 *dst = reinterpret_cast<uint4 *>(Q.items + pos);
 		__stcg(dst + 0, make_uint4(__float_as_uint(cb.cx), __float_as_uint(cb.cy), __float_as_uint(cb.cz), __float_as_uint(cb.r[0])));
@@ -246,25 +281,59 @@ __device__ __forceinline__ void expand_state(const SceneDev &sc, const RobotDev 
 /// Survivor list between the broad cull (A1) and FK expansion (A2): 8-byte entries (owner, step).
 struct SurvivorsDev {
 	uint2 *entries;
-	unsigned *count;  // entries appended (<= cap is guaranteed by the launchers' sizing or by inline expansion)
+	unsigned *counts;  // SHARDS append counters; slots at or beyond cap are expanded inline by the producer
 	unsigned cap;
 };
 
-/// A1 for explicit states: read only the base translation (24 of the state's 72+ bytes) and keep the states whose
-/// reach sphere touches the scene bounds.
-__global__ void __launch_bounds__(BLOCK_A)
+/// Overflow path of the survivor list (badly skewed batches only), kept out of line so that the streaming kernel
+/// below stays small: expand one state on the spot.
+__device__ __noinline__ void expand_state_now(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
+											  const double *row, unsigned owner) {
+	LocalCounters lc;
+	if (finite7(row)) expand_state(sc, rb, Q, res, Pose{D3{row[0], row[1], row[2]}, Q4{row[3], row[4], row[5], row[6]}}, row + 7, owner, 0u, lc);
+}
+
+/// A1 for explicit states: stream the state rows through shared memory with fully coalesced loads (a warp's 32 rows
+/// are one contiguous span; warps run independently, so one warp's append round trip never stalls another's loads),
+/// then keep the states whose reach sphere touches the scene bounds.  This
+/// stage is the HBM-bound part of a state batch: 8 (7 + J_s) bytes per state, read exactly once.
+__global__ void __launch_bounds__(BLOCK_A, 8)
 k_cull_states(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ states,
-			  size_t n, size_t stride, SurvivorsDev S) {
+			  size_t n, size_t stride, SurvivorsDev S, QueueDev Q, Results res) {
+	extern __shared__ double s_rows[];  // BLOCK_A * stride: one 32-row span per warp, no block-wide barrier
 	unsigned n_states = 0;
-	for (size_t i = (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < n; i += (size_t) gridDim.x * BLOCK_A) {
-		const double *r = states + i * stride;
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	double *rows = s_rows + (size_t) warp * 32 * stride;
+	const size_t n_spans = (n + 31) / 32, warps_total = (size_t) gridDim.x * (BLOCK_A / 32);
+	for (size_t span = (size_t) blockIdx.x * (BLOCK_A / 32) + warp; span < n_spans; span += warps_total) {
+		const size_t i0 = span * 32;
+		const unsigned cnt = (unsigned) min((size_t) 32, n - i0);
+		const double *src = states + i0 * stride;
+		const unsigned total = cnt * (unsigned) stride;
+		__syncwarp();
+		if (cnt == 32) {  // 32 * stride doubles starting on a 256-byte boundary: 16-byte loads
+			const double2 *src2 = reinterpret_cast<const double2 *>(src);
+			double2 *rows2 = reinterpret_cast<double2 *>(rows);
+			for (unsigned e = lane; e < total / 2; e += 32) rows2[e] = __ldcs(src2 + e);
+		} else {
+			for (unsigned e = lane; e < total; e += 32) rows[e] = __ldcs(src + e);
+		}
+		__syncwarp();
+		if (lane >= cnt) continue;
+		const double *r = rows + lane * stride;
 		n_states++;
-		const D3 t{__ldg(r), __ldg(r + 1), __ldg(r + 2)};
-		if (robot_out_of_reach(sc, rb, t)) continue;
+		if (robot_out_of_reach(sc, rb, D3{r[0], r[1], r[2]})) continue;
 		cg::coalesced_group g = cg::coalesced_threads();
 		unsigned base = 0;
-		if (g.thread_rank() == 0) base = atomicAdd(S.count, g.size());
-		S.entries[g.shfl(base, 0) + g.thread_rank()] = make_uint2((unsigned) i, 0u);  // cap == n: cannot overflow
+		const unsigned shard = my_shard();
+		if (g.thread_rank() == 0) base = atomicAdd(S.counts + shard * COUNTER_STRIDE, g.size());
+		const unsigned pos = shard_slot(shard, g.shfl(base, 0) + g.thread_rank());
+		const unsigned i = (unsigned) (i0 + lane);
+		if (pos < S.cap) {
+			S.entries[pos] = make_uint2(i, 0u);
+		} else {
+			expand_state_now(sc, rb, Q, res, r, i);  // list full (badly skewed batch)
+		}
 	}
 	LocalCounters lc;
 	lc.states = n_states;
@@ -277,8 +346,11 @@ __global__ void __launch_bounds__(BLOCK_A)
 k_expand_states(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ states,
 				size_t stride, SurvivorsDev S, QueueDev Q, Results res) {
 	LocalCounters lc;
-	const unsigned n = min(__ldcg(S.count), S.cap);
+	__shared__ unsigned s_counts[SHARDS];
+	load_shard_counts(s_counts, S.counts);
+	const unsigned n = slot_range(s_counts, S.cap);
 	for (unsigned k = blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
+		if (!slot_filled(s_counts, k)) continue;
 		const unsigned i = __ldcg(&S.entries[k]).x;
 		const double *r = states + (size_t) i * stride;
 		double row[ROW_MAX];
@@ -471,8 +543,16 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 			if (!empty && t0 <= t1) {
 				const double lo = floor(t0 * (double) n_steps) - 1.0, hi = ceil(t1 * (double) n_steps) + 1.0;
 				s_lo = (unsigned) fmax(lo, 0.0);
-				const unsigned s_hi = (unsigned) fmin(hi, (double) n_steps);
-				len = s_hi - s_lo + 1;
+				unsigned s_hi = (unsigned) fmin(hi, (double) n_steps);
+				// The slab range is the box-shaped superset of the rounded "within reach" region, which is convex: trim
+				// both ends with the exact test stage A2 applies (same t, same lerp), so A2 mostly sees real survivors.
+				auto outside = [&](unsigned s) {
+					const double t = n_steps ? (double) s / (double) n_steps : 0.0;
+					return robot_out_of_reach(sc, rb, D3{(1.0 - t) * ar[0] + t * br[0], (1.0 - t) * ar[1] + t * br[1], (1.0 - t) * ar[2] + t * br[2]});
+				};
+				for (int guard = 0; guard < 64 && s_lo < s_hi && outside(s_lo); ++guard) ++s_lo;
+				for (int guard = 0; guard < 64 && s_hi > s_lo && outside(s_hi); ++guard) --s_hi;
+				len = (s_lo == s_hi && outside(s_lo)) ? 0u : s_hi - s_lo + 1;
 			}
 		}
 		__syncwarp();  // slerp_out[] of this warp's motions is read by other lanes on the overflow path
@@ -484,10 +564,12 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 			const unsigned l = __shfl_sync(0xffffffffu, len, src), lo = __shfl_sync(0xffffffffu, s_lo, src);
 			const unsigned mot = (unsigned) (i - lane + src), ns = __shfl_sync(0xffffffffu, n_steps, src);
 			unsigned base = 0;
-			if (lane == 0) base = atomicAdd(S.count, l);
+			const unsigned shard = my_shard();
+			if (lane == 0) base = atomicAdd(S.counts + shard * COUNTER_STRIDE, l);
 			base = __shfl_sync(0xffffffffu, base, 0);
 			for (unsigned k = lane; k < l; k += 32) {
-				if (base + k < S.cap) S.entries[base + k] = make_uint2(mot, lo + k);
+				const unsigned pos = shard_slot(shard, base + k);
+				if (pos < S.cap) S.entries[pos] = make_uint2(mot, lo + k);
 				else expand_motion_step(sc, rb, Q, res, a + (size_t) mot * stride, b + (size_t) mot * stride, ns, slerp_out[mot], mot, lo + k, lc);
 			}
 		}
@@ -505,8 +587,11 @@ k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant
 					  const double *__restrict__ b, size_t stride, const uint32_t *__restrict__ n_steps,
 					  const double2 *__restrict__ slerp_k, SurvivorsDev S, QueueDev Q, Results res) {
 	LocalCounters lc;
-	const unsigned n = min(__ldcg(S.count), S.cap);
+	__shared__ unsigned s_counts[SHARDS];
+	load_shard_counts(s_counts, S.counts);
+	const unsigned n = slot_range(s_counts, S.cap);
 	for (unsigned k = blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
+		if (!slot_filled(s_counts, k)) continue;
 		const uint2 e = __ldcg(&S.entries[k]);
 		expand_motion_step(sc, rb, Q, res, a + (size_t) e.x * stride, b + (size_t) e.x * stride, __ldg(n_steps + e.x), __ldg(slerp_k + e.x),
 						   e.x, e.y, lc);
@@ -539,7 +624,9 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 	const int REFILL_MIN = tune.refill_min, LEAF_MIN = tune.leaf_min;
 	constexpr unsigned FULL = 0xffffffffu;
 	const unsigned lane = threadIdx.x & 31;
-	const unsigned n_items = sc.n_nodes ? min(__ldcg(Q.count), Q.cap) : 0u;
+	__shared__ unsigned s_counts[SHARDS];
+	load_shard_counts(s_counts, Q.counts);
+	const unsigned n_items = sc.n_nodes ? slot_range(s_counts, Q.cap) : 0u;  // flat slot range, holes included
 	LocalCounters lc;
 	unsigned chunk_lo = 0, chunk_hi = 0;  // warp-uniform: unclaimed part of this warp's chunk
 	bool exhausted = false;               // warp-uniform: the queue has nothing left to claim
@@ -564,7 +651,7 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 				exhausted = chunk_lo >= n_items;
 			}
 			const unsigned avail = chunk_hi - chunk_lo, rank = __popc(idle_mask & ((1u << lane) - 1u));
-			if (idle && rank < avail) {
+			if (idle && rank < avail && slot_filled(s_counts, chunk_lo + rank)) {
 				item = chunk_lo + rank;
 				const uint4 *src = reinterpret_cast<const uint4 *>(Q.items + item);
 				const uint4 v0 = __ldcg(src), v1 = __ldcg(src + 1), v2 = __ldcg(src + 2), v3 = __ldcg(src + 3);
@@ -717,26 +804,30 @@ static unsigned grid_for(size_t work_items, int block, int blocks_per_sm) {
 	return (unsigned) (blocks < cap ? (blocks ? blocks : 1) : cap);
 }
 
+/// Survivor slots for n explicit states: the sharded list has holes, so leave room for imbalance between shards.
+size_t state_survivor_slots(size_t n) { return n + n / 4 + SHARDS * SHARD_BLOCK; }
+
 size_t query_scratch_bytes(size_t worst_case_boxes, size_t survivor_entries) {
 	size_t cap = worst_case_boxes < QUEUE_MAX_ITEMS ? worst_case_boxes : QUEUE_MAX_ITEMS;
 	size_t scap = survivor_entries < SURVIVOR_MAX_ENTRIES ? survivor_entries : SURVIVOR_MAX_ENTRIES;
-	return 256 + ((scap * sizeof(uint2) + 255) & ~(size_t) 255) + (cap ? cap : 1) * sizeof(Item);
+	return SCRATCH_HEADER + ((scap * sizeof(uint2) + 255) & ~(size_t) 255) + (cap ? cap : 1) * sizeof(Item);
 }
 
-/// Scratch layout: [256 B header: queue count, queue cursor, survivor count][survivor entries][queue items].
+/// Scratch layout: [header: queue shard counters | survivor shard counters | queue cursor][survivor entries][queue items].
 static void carve(void *scratch, size_t scratch_bytes, size_t survivor_entries, SurvivorsDev *S, QueueDev *Q) {
 	char *p = reinterpret_cast<char *>(scratch);
-	Q->count = reinterpret_cast<unsigned *>(p);
-	Q->cursor = Q->count + 1;
+	unsigned *hdr = reinterpret_cast<unsigned *>(p);
+	Q->counts = hdr;
+	Q->cursor = hdr + 2 * SHARDS * COUNTER_STRIDE;
 	size_t scap = survivor_entries < SURVIVOR_MAX_ENTRIES ? survivor_entries : SURVIVOR_MAX_ENTRIES;
 	size_t sbytes = (scap * sizeof(uint2) + 255) & ~(size_t) 255;
 	if (S) {
-		S->count = Q->count + 2;
-		S->entries = reinterpret_cast<uint2 *>(p + 256);
+		S->counts = hdr + SHARDS * COUNTER_STRIDE;
+		S->entries = reinterpret_cast<uint2 *>(p + SCRATCH_HEADER);
 		S->cap = (unsigned) scap;
 	}
-	Q->items = reinterpret_cast<Item *>(p + 256 + sbytes);
-	size_t cap = scratch_bytes > 256 + sbytes ? (scratch_bytes - 256 - sbytes) / sizeof(Item) : 0;
+	Q->items = reinterpret_cast<Item *>(p + SCRATCH_HEADER + sbytes);
+	size_t cap = scratch_bytes > SCRATCH_HEADER + sbytes ? (scratch_bytes - SCRATCH_HEADER - sbytes) / sizeof(Item) : 0;
 	Q->cap = (unsigned) (cap < QUEUE_MAX_ITEMS ? cap : QUEUE_MAX_ITEMS);
 }
 static QueueDev carve_queue(void *scratch, size_t scratch_bytes) {
@@ -755,7 +846,7 @@ static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const do
 								const Results &res, size_t worst_case_items, cudaStream_t stream) {
 	size_t bound = worst_case_items < Q.cap ? worst_case_items : Q.cap;
 	static int min_blocks = 0;
-	static TraverseTuning tune{8, 8};
+	static TraverseTuning tune{16, 8};
 	if (!min_blocks) {
 		const char *e = getenv("MGODPL_TRAVERSE_BLOCKS");
 		min_blocks = e ? atoi(e) : 4;
@@ -776,12 +867,16 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 	if (!n) return cudaSuccess;
 	SurvivorsDev S;
 	QueueDev Q;
-	carve(scratch, scratch_bytes, n, &S, &Q);
-	if (S.cap < n) return cudaErrorInvalidValue;  // callers split batches at SURVIVOR_MAX_ENTRIES
+	carve(scratch, scratch_bytes, state_survivor_slots(n), &S, &Q);
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
-	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 4 * sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
-	k_cull_states<<<grid_for(n, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_states, n, stride, S);
+	static bool attr = false;
+	if (!attr) {
+		cudaFuncSetAttribute(k_cull_states, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_A * ROW_MAX * 8);
+		attr = true;
+	}
+	k_cull_states<<<grid_for(n, BLOCK_A, 8), BLOCK_A, BLOCK_A * stride * sizeof(double), stream>>>(sc, rb, d_states, n, stride, S, Q, res);
 	LQ_CHECK(cudaGetLastError());
 	k_expand_states<<<grid_for(n, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_states, stride, S, Q, res);
 	LQ_CHECK(cudaGetLastError());
@@ -794,7 +889,7 @@ cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t
 	QueueDev Q = carve_queue(scratch, scratch_bytes);
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	RobotDev none{};
-	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 4 * sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
 	k_expand_boxes<<<grid_for(n, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, d_boxes, n, Q, res);
 	LQ_CHECK(cudaGetLastError());
@@ -810,7 +905,7 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	QueueDev Q;
 	carve(scratch, scratch_bytes, survivor_entries, &S, &Q);
 	Results res{RESULT_FIRST_STEP, nullptr, d_first_step};
-	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 4 * sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_first_step, 0xff, m * sizeof(unsigned), stream));
 	if (d_uncertain) LQ_CHECK(cudaMemsetAsync(d_uncertain, 0, ((m + 31) / 32) * 4, stream));
 	k_motion_ranges<<<grid_for(m, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
@@ -831,7 +926,7 @@ cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const do
 	QueueDev Q = carve_queue(scratch, scratch_bytes);
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	const size_t wpr = (s + 31) / 32;
-	LQ_CHECK(cudaMemsetAsync(Q.count, 0, 4 * sizeof(unsigned), stream));
+	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, f * wpr * 4, stream));
 	k_expand_goals<<<grid_for(f * s, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_targets, f, s, d_draws, d_limits, seed,
 																		distance_from_target, d_states_out, Q, res);
