@@ -613,8 +613,9 @@ k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant
 // ---------------------------------------------------------------------------------------------------------------
 constexpr unsigned QUEUE_CHUNK = 64;    // items a warp claims per cursor atomic
 struct TraverseTuning {
-	int refill_min;  // idle lanes that trigger a refill
-	int leaf_min;    // parked lanes (on an overlapping leaf) that trigger a batch of exact tests
+	int refill_min;   // idle lanes that trigger a refill
+	int leaf_min;     // parked lanes (on an overlapping leaf) that trigger a batch of exact tests
+	int no_prefilter; // MGODPL_NO_PREFILTER=1: every leaf triangle goes to the fp64 test (tests compare both modes)
 };
 
 template<int MIN_BLOCKS>
@@ -700,8 +701,8 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 				if (already_decided(res, owner, step)) {
 					cur = REF_END;
 				} else {
-					unsigned unknown = 0;
-					bool hit = leaf_prefilter(sc, cb, cur, &unknown);
+					unsigned unknown = 0xffffu;
+					bool hit = tune.no_prefilter ? false : leaf_prefilter(sc, cb, cur, &unknown);
 					if (!hit && unknown) {
 						double half_buf[3];
 						const double *half;
@@ -807,9 +808,28 @@ static unsigned grid_for(size_t work_items, int block, int blocks_per_sm) {
 /// Survivor slots for n explicit states: the sharded list has holes, so leave room for imbalance between shards.
 size_t state_survivor_slots(size_t n) { return n + n / 4 + SHARDS * SHARD_BLOCK; }
 
+/// Capacity limits of the two work lists.  MGODPL_QUEUE_MAX_ITEMS / MGODPL_SURVIVOR_MAX_ENTRIES shrink them (tests use
+/// this to drive every query through the inline overflow paths).
+static size_t queue_max_items() {
+	static size_t v = 0;
+	if (!v) {
+		const char *e = getenv("MGODPL_QUEUE_MAX_ITEMS");
+		v = e && atoll(e) > 0 ? (size_t) atoll(e) : QUEUE_MAX_ITEMS;
+	}
+	return v;
+}
+static size_t survivor_max_entries() {
+	static size_t v = 0;
+	if (!v) {
+		const char *e = getenv("MGODPL_SURVIVOR_MAX_ENTRIES");
+		v = e && atoll(e) > 0 ? (size_t) atoll(e) : SURVIVOR_MAX_ENTRIES;
+	}
+	return v;
+}
+
 size_t query_scratch_bytes(size_t worst_case_boxes, size_t survivor_entries) {
-	size_t cap = worst_case_boxes < QUEUE_MAX_ITEMS ? worst_case_boxes : QUEUE_MAX_ITEMS;
-	size_t scap = survivor_entries < SURVIVOR_MAX_ENTRIES ? survivor_entries : SURVIVOR_MAX_ENTRIES;
+	size_t cap = worst_case_boxes < queue_max_items() ? worst_case_boxes : queue_max_items();
+	size_t scap = survivor_entries < survivor_max_entries() ? survivor_entries : survivor_max_entries();
 	return SCRATCH_HEADER + ((scap * sizeof(uint2) + 255) & ~(size_t) 255) + (cap ? cap : 1) * sizeof(Item);
 }
 
@@ -819,7 +839,7 @@ static void carve(void *scratch, size_t scratch_bytes, size_t survivor_entries, 
 	unsigned *hdr = reinterpret_cast<unsigned *>(p);
 	Q->counts = hdr;
 	Q->cursor = hdr + 2 * SHARDS * COUNTER_STRIDE;
-	size_t scap = survivor_entries < SURVIVOR_MAX_ENTRIES ? survivor_entries : SURVIVOR_MAX_ENTRIES;
+	size_t scap = survivor_entries < survivor_max_entries() ? survivor_entries : survivor_max_entries();
 	size_t sbytes = (scap * sizeof(uint2) + 255) & ~(size_t) 255;
 	if (S) {
 		S->counts = hdr + SHARDS * COUNTER_STRIDE;
@@ -828,7 +848,7 @@ static void carve(void *scratch, size_t scratch_bytes, size_t survivor_entries, 
 	}
 	Q->items = reinterpret_cast<Item *>(p + SCRATCH_HEADER + sbytes);
 	size_t cap = scratch_bytes > SCRATCH_HEADER + sbytes ? (scratch_bytes - SCRATCH_HEADER - sbytes) / sizeof(Item) : 0;
-	Q->cap = (unsigned) (cap < QUEUE_MAX_ITEMS ? cap : QUEUE_MAX_ITEMS);
+	Q->cap = (unsigned) (cap < queue_max_items() ? cap : queue_max_items());
 }
 static QueueDev carve_queue(void *scratch, size_t scratch_bytes) {
 	QueueDev Q;
@@ -846,12 +866,13 @@ static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const do
 								const Results &res, size_t worst_case_items, cudaStream_t stream) {
 	size_t bound = worst_case_items < Q.cap ? worst_case_items : Q.cap;
 	static int min_blocks = 0;
-	static TraverseTuning tune{16, 8};
+	static TraverseTuning tune{16, 8, 0};
 	if (!min_blocks) {
 		const char *e = getenv("MGODPL_TRAVERSE_BLOCKS");
 		min_blocks = e ? atoi(e) : 4;
 		if ((e = getenv("MGODPL_REFILL_MIN"))) tune.refill_min = atoi(e);
 		if ((e = getenv("MGODPL_LEAF_MIN"))) tune.leaf_min = atoi(e);
+		if ((e = getenv("MGODPL_NO_PREFILTER"))) tune.no_prefilter = atoi(e);
 	}
 	switch (min_blocks) {
 		case 8: k_traverse<8><<<grid_for(bound, BLOCK_B, 8), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune); break;
