@@ -192,7 +192,7 @@ def run_ours(args):
         return
     peak, peak_kind = peaks()
     ms_per_step = total_ms / args.steps
-    b_scene = info.n_nodes * 32 + info.n_triangles * 72
+    b_scene = int(info.device_bytes)  # BVH records + both triangle copies, read at most once per launch from HBM
     algo_bytes = m * B_MOTION + b_scene
     achieved = algo_bytes / (np.mean(step_ms) * 1e-3) / 1e9
     traffic = None

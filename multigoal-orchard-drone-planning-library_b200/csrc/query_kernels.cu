@@ -582,7 +582,8 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 }
 
 /// A2 for motions: one thread per surviving (motion, step).
-__global__ void __launch_bounds__(BLOCK_A)
+template<int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK_A, MIN_BLOCKS)
 k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
 					  const double *__restrict__ b, size_t stride, const uint32_t *__restrict__ n_steps,
 					  const double2 *__restrict__ slerp_k, SurvivorsDev S, QueueDev Q, Results res) {
@@ -932,7 +933,16 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	k_motion_ranges<<<grid_for(m, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
 																	  d_n_steps, d_uncertain, (double2 *) d_slerp, S, Q, res);
 	LQ_CHECK(cudaGetLastError());
-	k_expand_motion_steps<<<grid_for(S.cap, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const double2 *) d_slerp, S, Q, res);
+	static int a2_blocks = 0;
+	if (!a2_blocks) {
+		const char *e = getenv("MGODPL_EXPAND_BLOCKS");
+		a2_blocks = e ? atoi(e) : 2;
+	}
+	switch (a2_blocks) {
+		case 4: k_expand_motion_steps<4><<<grid_for(S.cap, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const double2 *) d_slerp, S, Q, res); break;
+		case 3: k_expand_motion_steps<3><<<grid_for(S.cap, BLOCK_A, 3), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const double2 *) d_slerp, S, Q, res); break;
+		default: k_expand_motion_steps<2><<<grid_for(S.cap, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const double2 *) d_slerp, S, Q, res); break;
+	}
 	LQ_CHECK(cudaGetLastError());
 	LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (size_t) Q.cap, stream));
 	k_finish_motions<<<(unsigned) ((m + 255) / 256), 256, 0, stream>>>(d_first_step, d_n_steps, m, d_hit_bits, d_toi);
