@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -49,6 +50,19 @@ int require_device() {
 struct Workspace {
 	char *dev = nullptr, *host = nullptr;
 	size_t dev_cap = 0, host_cap = 0;
+	// two side streams for copy/compute overlap inside one host-buffer call (created on first use)
+	cudaStream_t side[2] = {nullptr, nullptr};
+	cudaEvent_t ev_start = nullptr, ev_done[2] = {nullptr, nullptr};
+	cudaError_t side_streams() {
+		if (side[0]) return cudaSuccess;
+		cudaError_t e = cudaSuccess;
+		for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+			e = cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming);
+		}
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
+		return e;
+	}
 	cudaError_t reserve(size_t dev_bytes, size_t host_bytes) {
 		if (dev_bytes > dev_cap) {
 			if (dev) cudaFree(dev);
@@ -71,6 +85,11 @@ struct Workspace {
 	~Workspace() {
 		if (dev) cudaFree(dev);
 		if (host) cudaFreeHost(host);
+		for (int i = 0; i < 2; ++i) {
+			if (side[i]) cudaStreamDestroy(side[i]);
+			if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+		}
+		if (ev_start) cudaEventDestroy(ev_start);
 	}
 };
 
@@ -597,22 +616,50 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Lease ws(scene->pool);
 	Carver c;
-	const size_t in_b = m * stride * 8, words = (m + 31) / 32, qb = motion_scratch_bytes(m, robot->dev.n_boxes);
+	// Large batches are cut into chunks that alternate between two side streams, so chunk k+1's H2D copy and chunk
+	// k-1's D2H copy overlap chunk k's kernels.  Chunk boundaries are multiples of 32: result words never straddle.
+	static size_t chunk_pref = 0;
+	if (!chunk_pref) {
+		const char *e = getenv("MGODPL_E2E_CHUNKS");
+		chunk_pref = e && atoi(e) > 0 ? (size_t) atoi(e) : 2;
+	}
+	const size_t n_chunks = m >= 32768 ? chunk_pref : 1;
+	const size_t chunk_m = n_chunks == 1 ? m : ((m + n_chunks - 1) / n_chunks + 31) / 32 * 32;
+	const size_t in_b = m * stride * 8, words = (m + 31) / 32, qb = motion_scratch_bytes(chunk_m, robot->dev.n_boxes);
 	size_t o_a = c.take(in_b), o_b = c.take(in_b), o_first = c.take(m * 4), o_slerp = c.take(m * 16);
-	// outputs are contiguous so that one D2H copy brings them all back
 	size_t o_hit = c.take(words * 4), o_unc = c.take(words * 4), o_steps = c.take(m * 4), o_toi = c.take(toi ? m * 8 : 0);
 	const size_t out_lo = o_hit, out_hi = c.off;
 	size_t o_ovr = c.take(m * 4);
 	const size_t host_hi = c.off;
-	size_t o_q = c.take(qb);
+	size_t o_q = c.take(qb), o_q2 = c.take(n_chunks > 1 ? qb : 0);
 	CU(ws->reserve(c.off, host_hi - out_lo));
 	char *D = ws->dev, *H = ws->host - out_lo;  // host staging mirrors the device layout from out_lo onwards
-	CU(cudaMemcpyAsync(D + o_a, a, in_b, cudaMemcpyHostToDevice, stream));
-	CU(cudaMemcpyAsync(D + o_b, b, in_b, cudaMemcpyHostToDevice, stream));
-	CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a), (const double *) (D + o_b), m, stride, js, max_step,
-							nullptr, (uint32_t *) (D + o_hit), toi ? (double *) (D + o_toi) : nullptr, (uint32_t *) (D + o_steps),
-							(uint32_t *) (D + o_unc), (unsigned *) (D + o_first), D + o_slerp, D + o_q, qb, motion_survivors(m), stream));
-	CU(cudaMemcpyAsync(H + out_lo, D + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, stream));
+	if (n_chunks > 1) {
+		CU(ws->side_streams());
+		CU(cudaEventRecord(ws->ev_start, stream));
+		for (int s = 0; s < 2; ++s) CU(cudaStreamWaitEvent(ws->side[s], ws->ev_start, 0));
+	}
+	for (size_t ci = 0; ci < n_chunks; ++ci) {
+		const size_t lo = ci * chunk_m, hi = std::min(m, lo + chunk_m);
+		if (lo >= hi) break;
+		const size_t mc = hi - lo, w_lo = lo / 32, w_n = (mc + 31) / 32;
+		cudaStream_t s = n_chunks > 1 ? ws->side[ci & 1] : stream;
+		CU(cudaMemcpyAsync(D + o_a + lo * stride * 8, a + lo * stride, mc * stride * 8, cudaMemcpyHostToDevice, s));
+		CU(cudaMemcpyAsync(D + o_b + lo * stride * 8, b + lo * stride, mc * stride * 8, cudaMemcpyHostToDevice, s));
+		CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a) + lo * stride, (const double *) (D + o_b) + lo * stride, mc,
+								stride, js, max_step, nullptr, (uint32_t *) (D + o_hit) + w_lo, toi ? (double *) (D + o_toi) + lo : nullptr,
+								(uint32_t *) (D + o_steps) + lo, (uint32_t *) (D + o_unc) + w_lo, (unsigned *) (D + o_first) + lo,
+								D + o_slerp + lo * 16, D + ((ci & 1) ? o_q2 : o_q), qb, motion_survivors(mc), s));
+		CU(cudaMemcpyAsync(H + o_hit + w_lo * 4, D + o_hit + w_lo * 4, w_n * 4, cudaMemcpyDeviceToHost, s));
+		CU(cudaMemcpyAsync(H + o_unc + w_lo * 4, D + o_unc + w_lo * 4, w_n * 4, cudaMemcpyDeviceToHost, s));
+		CU(cudaMemcpyAsync(H + o_steps + lo * 4, D + o_steps + lo * 4, mc * 4, cudaMemcpyDeviceToHost, s));
+		if (toi) CU(cudaMemcpyAsync(H + o_toi + lo * 8, D + o_toi + lo * 8, mc * 8, cudaMemcpyDeviceToHost, s));
+	}
+	if (n_chunks > 1)
+		for (int s = 0; s < 2; ++s) {
+			CU(cudaEventRecord(ws->ev_done[s], ws->side[s]));
+			CU(cudaStreamWaitEvent(stream, ws->ev_done[s], 0));
+		}
 	CU(cudaStreamSynchronize(stream));
 	// Step-count fix-up: the device libm may differ from the host's by an ulp, which only matters when distance /
 	// max_step sits on an integer boundary.  Re-derive those on the host and re-run if any count disagrees.
