@@ -104,6 +104,50 @@ inline MotionResults check_motions(const robot_model::RobotModel &robot, const g
 	return r;
 }
 
+/// k nearest neighbours of every state among the states that precede it (causal = true: the roadmap as it stood when
+/// the reference inserted that node, tsp_over_prm.cpp:33-66) or among all other states, under equal_weights_distance —
+/// what NearestNeighborsGNAT::nearestK answers (tsp_over_prm.cpp:44-45, 383-386), for the whole batch at once.
+struct NearestNeighbours {
+	size_t k = 0;
+	std::vector<int32_t> index;    // n x k, ascending by distance, -1 pads
+	std::vector<double> distance;  // n x k, NaN pads
+};
+inline NearestNeighbours nearest_k(const RobotState *states, size_t n, size_t k, bool causal = true, void *stream = nullptr) {
+	const size_t js = gpu::common_joint_values(states, n), stride = 7 + js;
+	std::vector<double> buf(n * stride);
+	for (size_t i = 0; i < n; ++i) gpu::pack_state(states[i], js, buf.data() + i * stride);
+	NearestNeighbours r{k, std::vector<int32_t>(n * k), std::vector<double>(n * k)};
+	gpu::throw_status(mgodpl_knn(buf.data(), n, stride, (int32_t) js, (int32_t) k, causal ? 1 : 0, r.index.data(), r.distance.data(), stream));
+	return r;
+}
+
+/// PRM edge validation in one batch (add_and_connect_roadmap_node, tsp_over_prm.cpp:33-66, for every node at once):
+/// for node i and each of its k nearest earlier nodes j, motion_collides(nodes[j], nodes[i]); collision-free pairs
+/// become edges weighted by equal_weights_distance.
+struct RoadmapEdge {
+	size_t from, to;
+	double weight;
+};
+inline std::vector<RoadmapEdge> validate_prm_edges(const robot_model::RobotModel &robot, const gpu::Scene &scene,
+												   const std::vector<RobotState> &nodes, size_t k) {
+	NearestNeighbours nn = nearest_k(nodes.data(), nodes.size(), k, true);
+	std::vector<RobotState> a, b;
+	std::vector<RoadmapEdge> cand;
+	for (size_t i = 0; i < nodes.size(); ++i)
+		for (size_t q = 0; q < k; ++q) {
+			const int32_t j = nn.index[i * k + q];
+			if (j < 0) continue;
+			a.push_back(nodes[(size_t) j]), b.push_back(nodes[i]);
+			cand.push_back({(size_t) j, i, nn.distance[i * k + q]});
+		}
+	if (cand.empty()) return {};
+	MotionResults r = check_motions(robot, scene, a.data(), b.data(), a.size());
+	std::vector<RoadmapEdge> edges;
+	for (size_t e = 0; e < cand.size(); ++e)
+		if (!bit(r.hit_bits, e)) edges.push_back(cand[e]);
+	return edges;
+}
+
 // ---- the reference's free functions --------------------------------------------------------------------------------------
 /// collision_detection.h:29-31.  Throws "Only boxes are implemented for collision geometry." for non-box shapes.
 inline bool check_link_collision(const robot_model::RobotModel::Link &link, const gpu::Scene &tree_trunk_object, const math::Transformd &link_tf) {

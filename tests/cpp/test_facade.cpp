@@ -3,6 +3,7 @@
 // infrastructure).  Modelled on the reference's own test style: seeded randomised properties
 // (test/math/Transform_test.cpp:16-65) and the legacy collision tests (test/planning/MyCollisionEnvTest.cpp:13-78,
 // src_old/test/collision_checking_test.cpp:30-57).  Needs a CUDA device; run by tests/test_gpu_facade.py.
+#include <algorithm>
 #include <cstdio>
 #include <thread>
 
@@ -212,6 +213,31 @@ int main() {
 			CHECK(gs.collisions[f] == collisions);
 		}
 		CHECK(gs.collisions[3] == 0);  // a target far from the tree is always reachable
+	}
+	// -- batched PRM edge validation = the reference's sequential insert-and-connect loop -----------------------------------
+	{
+		random_numbers::RandomNumberGenerator rng(11);
+		std::vector<RobotState> nodes;
+		while (nodes.size() < 300) {
+			RobotState s = generateUniformRandomState(robot, rng, 3.0, 4.0);
+			if (!orc::check_robot_collision(orobot, oscene, to_orc(s))) nodes.push_back(s);
+		}
+		const size_t k = 5;
+		std::vector<RoadmapEdge> edges = validate_prm_edges(robot, scene, nodes, k);
+		// reference semantics (tsp_over_prm.cpp:33-66): node i connects to its k nearest among nodes 0..i-1 when the motion is free
+		size_t expected = 0, found = 0;
+		for (size_t i = 0; i < nodes.size(); ++i) {
+			std::vector<std::pair<double, size_t>> d;
+			for (size_t j = 0; j < i; ++j) d.push_back({equal_weights_distance(nodes[i], nodes[j]), j});
+			std::stable_sort(d.begin(), d.end(), [](auto &x, auto &y) { return x.first < y.first; });
+			for (size_t q = 0; q < std::min(k, d.size()); ++q) {
+				if (orc::check_motion_collides(orobot, oscene, to_orc(nodes[d[q].second]), to_orc(nodes[i])).hit) continue;
+				++expected;
+				for (auto &e: edges) found += e.from == d[q].second && e.to == i && std::fabs(e.weight - d[q].first) < 1e-12;
+			}
+		}
+		std::printf("PRM: %zu edges validated on the GPU, %zu expected, %zu matched\n", edges.size(), expected, found);
+		CHECK(edges.size() == expected && found == expected);
 	}
 	// -- error vocabulary -------------------------------------------------------------------------------------------------------
 	{
