@@ -63,34 +63,54 @@ def ref_equivalent_states(hit, toi, n_steps):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING warm-up + timed region (B200_PROFILING.md recipe).  NVML is polled
+    every few ms (the timed region lasts tens of ms); nvidia-smi is the fallback."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.sm, self.max_sm, self.mask, self.stop_flag, self.how = index, [], None, 0, threading.Event(), "nvml"
 
     def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag.is_set():
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                self.mask |= int(reasons(h))
+                self.stop_flag.wait(0.003)
+            return
+        except Exception:
+            self.how = "nvidia-smi"
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        bits = [0x8, 0x40, 0x20, 0x4]
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")]
+                if r[0].isdigit():
+                    self.sm.append(int(r[0]))
+                    self.max_sm = int(r[1]) if r[1].isdigit() else self.max_sm
+                    for i, bit in enumerate(bits):
+                        if r[2 + i].lower().startswith("active"):
+                            self.mask |= bit
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons,
-                "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_sm, "reasons": ["unsampled"]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "reasons": [n for b, n in self.REASONS.items() if self.mask & b],
+                "samples": len(sm), "sm_mhz_min": sm[0], "how": self.how}
 
 
 def run_ours(args):
@@ -123,36 +143,56 @@ def run_ours(args):
     d_toi = torch.zeros(m, dtype=torch.float64, device=dev)
     d_steps = torch.zeros(m, dtype=torch.int32, device=dev)
     d_unc = torch.zeros(words, dtype=torch.int32, device=dev)
-    gathered = [torch.empty_like(d_hit) for _ in range(world)] if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)  # 256 MiB > 126 MB of L2
+    # N > 1: the only exchange on this path is the gather of the packed result words (12.5 KB per rank).  It is
+    # latency-bound, so it is issued asynchronously once per batch (NCCL's own stream) and overlaps the next batch's
+    # kernels; result buffers alternate so a gather never reads words the next step is rewriting.
+    hit_bufs = [d_hit, torch.zeros_like(d_hit)]
+    gathered = [[torch.empty_like(d_hit) for _ in range(world)] for _ in range(2)] if world > 1 else None
+    pending = [None, None]
 
-    def step():
-        mg.capi.check_motions_device(scene, robot, d_a, d_b, m, stride, js, d_hit, MAX_STEP, d_toi, d_steps, d_unc,
+    def step(k=0):
+        slot = k & 1
+        if world > 1 and pending[slot] is not None:
+            pending[slot].wait()  # the gather that last read this buffer (two steps ago)
+            pending[slot] = None
+        mg.capi.check_motions_device(scene, robot, d_a, d_b, m, stride, js, hit_bufs[slot], MAX_STEP, d_toi, d_steps, d_unc,
                                      stream=stream)
         if world > 1:
-            dist.all_gather(gathered, d_hit)
+            pending[slot] = dist.all_gather(gathered[slot], hit_bufs[slot], async_op=True)
 
-    for _ in range(args.warmup):
-        step()
+    def drain():
+        for i in range(2):
+            if pending[i] is not None:
+                pending[i].wait()
+                pending[i] = None
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for k in range(args.warmup):
+        step(k)
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
     for k in range(args.steps):
         flush.fill_(k)  # evict inputs and scene from L2 (outside the timed events)
         ev[k][0].record()
-        step()
+        step(k)
         ev[k][1].record()
+    drain()  # the stream now waits for the gathers still in flight ...
+    tail = torch.cuda.Event(enable_timing=True)
+    tail.record()  # ... and this event closes the timed region after them
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     sampler.stop_flag.set()
     sampler.join()
+    d_hit = hit_bufs[(args.steps - 1) & 1]
     step_ms = [s.elapsed_time(e) for s, e in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    total_ms = torch.tensor([sum(step_ms) + ev[-1][1].elapsed_time(tail)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
@@ -427,7 +467,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
