@@ -19,7 +19,9 @@
  *    ignored by FK but counts in the motion distance, exactly like the reference.
  *  - result bitmasks: query i -> bit (i & 31) of word (i >> 5); tail bits are zero.  Bit set == collides.
  *  - "_device" variants take device pointers and only enqueue work on `stream` (a cudaStream_t passed as void*);
- *    the others take host pointers, copy in, run, copy out and synchronise `stream` before returning.
+ *    the others take host pointers, copy in, run, copy out and synchronise `stream` before returning.  (One exception:
+ *    a device-variant batch whose worst case exceeds the internal box queue — more than 2^25 candidate boxes — reads one
+ *    counter block back, i.e. synchronises `stream` once, to learn how many passes it needs.)
  *  - handles are immutable after creation and may be used from several host threads at once.
  *  - there is no CPU fallback: without a CUDA device every entry point returns MGODPL_E_NO_DEVICE.
  */

@@ -7,7 +7,7 @@
 namespace mgodpl_b200 {
 
 /// Upper bound on queued boxes per launch (64 B each); beyond it stage A traverses inline.
-constexpr size_t QUEUE_MAX_ITEMS = 8u << 20;
+constexpr size_t QUEUE_MAX_ITEMS = 32u << 20;
 /// Bytes of device scratch a query launch wants for `worst_case_boxes` candidate boxes (queue header + items).
 /// Upper bound on survivor-list entries (8 B each) between the broad cull and FK expansion.
 constexpr size_t SURVIVOR_MAX_ENTRIES = 64u << 20;

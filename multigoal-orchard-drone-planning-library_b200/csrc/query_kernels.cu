@@ -179,7 +179,8 @@ __device__ __noinline__ bool box_hits_scene(const SceneDev &sc, const CullBox &c
 // ---------------------------------------------------------------------------------------------------------------
 constexpr unsigned SHARDS = 64, SHARD_BLOCK = 32;
 constexpr unsigned COUNTER_STRIDE = 32;  // one 128-byte line per counter: neighbouring counters would share an L2 atomic unit
-constexpr size_t SCRATCH_HEADER = 2 * SHARDS * COUNTER_STRIDE * sizeof(unsigned) + 256;
+constexpr size_t QUEUE_HEADER = SHARDS * COUNTER_STRIDE * sizeof(unsigned) + 256;  // queue counters + cursor: reset before every pass
+constexpr size_t SCRATCH_HEADER = QUEUE_HEADER + SHARDS * COUNTER_STRIDE * sizeof(unsigned);
 
 __device__ __forceinline__ unsigned my_shard() { return (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (SHARDS - 1); }
 __device__ __forceinline__ unsigned shard_slot(unsigned shard, unsigned local) {
@@ -344,12 +345,12 @@ k_cull_states(const __grid_constant__ SceneDev sc, const __grid_constant__ Robot
 /// (check_robot_collision, collision_detection.cpp:57-80).
 __global__ void __launch_bounds__(BLOCK_A)
 k_expand_states(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ states,
-				size_t stride, SurvivorsDev S, QueueDev Q, Results res) {
+				size_t stride, SurvivorsDev S, unsigned pass_lo, unsigned pass_hi, QueueDev Q, Results res) {
 	LocalCounters lc;
 	__shared__ unsigned s_counts[SHARDS];
 	load_shard_counts(s_counts, S.counts);
-	const unsigned n = slot_range(s_counts, S.cap);
-	for (unsigned k = blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
+	const unsigned n = min(slot_range(s_counts, S.cap), pass_hi);
+	for (unsigned k = pass_lo + blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
 		if (!slot_filled(s_counts, k)) continue;
 		const unsigned i = __ldcg(&S.entries[k]).x;
 		const double *r = states + (size_t) i * stride;
@@ -363,9 +364,9 @@ k_expand_states(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 
 /// Explicit world-frame boxes: check_link_collision (collision_detection.cpp:16-55), n x (tf7, size3).
 __global__ void __launch_bounds__(BLOCK_A)
-k_expand_boxes(const __grid_constant__ SceneDev sc, const double *__restrict__ boxes, size_t n, QueueDev Q, Results res) {
+k_expand_boxes(const __grid_constant__ SceneDev sc, const double *__restrict__ boxes, size_t pass_lo, size_t n, QueueDev Q, Results res) {
 	LocalCounters lc;
-	for (size_t i = (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < n; i += (size_t) gridDim.x * BLOCK_A) {
+	for (size_t i = pass_lo + (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < n; i += (size_t) gridDim.x * BLOCK_A) {
 		double v[10];
 #pragma unroll
 		for (int k = 0; k < 10; ++k) v[k] = __ldg(boxes + i * 10 + k);
@@ -391,11 +392,12 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // 
 __global__ void __launch_bounds__(BLOCK_A)
 k_expand_goals(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ targets,
 			   size_t rows, size_t per_row, const double *__restrict__ draws, const double *__restrict__ limits,
-			   unsigned long long seed, double distance_from_target, double *__restrict__ states_out, QueueDev Q, Results res) {
+			   unsigned long long seed, double distance_from_target, double *__restrict__ states_out, size_t pass_lo, size_t pass_hi,
+			   QueueDev Q, Results res) {
 	LocalCounters lc;
 	const int nv = rb.n_vars;
-	const size_t total = rows * per_row, bits_per_row = ((per_row + 31) / 32) * 32;
-	for (size_t i = (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < total; i += (size_t) gridDim.x * BLOCK_A) {
+	const size_t total = min(rows * per_row, pass_hi), bits_per_row = ((per_row + 31) / 32) * 32;
+	for (size_t i = pass_lo + (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < total; i += (size_t) gridDim.x * BLOCK_A) {
 		const size_t row = i / per_row, s = i - row * per_row;
 		double jv[MGODPL_MAX_JOINT_VALUES], yaw;
 		if (draws) {
@@ -586,12 +588,12 @@ template<int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK_A, MIN_BLOCKS)
 k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
 					  const double *__restrict__ b, size_t stride, const uint32_t *__restrict__ n_steps,
-					  const double2 *__restrict__ slerp_k, SurvivorsDev S, QueueDev Q, Results res) {
+					  const double2 *__restrict__ slerp_k, SurvivorsDev S, unsigned pass_lo, unsigned pass_hi, QueueDev Q, Results res) {
 	LocalCounters lc;
 	__shared__ unsigned s_counts[SHARDS];
 	load_shard_counts(s_counts, S.counts);
-	const unsigned n = slot_range(s_counts, S.cap);
-	for (unsigned k = blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
+	const unsigned n = min(slot_range(s_counts, S.cap), pass_hi);
+	for (unsigned k = pass_lo + blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
 		if (!slot_filled(s_counts, k)) continue;
 		const uint2 e = __ldcg(&S.entries[k]);
 		expand_motion_step(sc, rb, Q, res, a + (size_t) e.x * stride, b + (size_t) e.x * stride, __ldg(n_steps + e.x), __ldg(slerp_k + e.x),
@@ -839,11 +841,11 @@ static void carve(void *scratch, size_t scratch_bytes, size_t survivor_entries, 
 	char *p = reinterpret_cast<char *>(scratch);
 	unsigned *hdr = reinterpret_cast<unsigned *>(p);
 	Q->counts = hdr;
-	Q->cursor = hdr + 2 * SHARDS * COUNTER_STRIDE;
+	Q->cursor = hdr + SHARDS * COUNTER_STRIDE;
 	size_t scap = survivor_entries < survivor_max_entries() ? survivor_entries : survivor_max_entries();
 	size_t sbytes = (scap * sizeof(uint2) + 255) & ~(size_t) 255;
 	if (S) {
-		S->counts = hdr + SHARDS * COUNTER_STRIDE;
+		S->counts = hdr + QUEUE_HEADER / sizeof(unsigned);
 		S->entries = reinterpret_cast<uint2 *>(p + SCRATCH_HEADER);
 		S->cap = (unsigned) scap;
 	}
@@ -884,6 +886,31 @@ static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const do
 	return cudaGetLastError();
 }
 
+/// Stage A2 + B run in passes over the candidates so that a pass can never produce more boxes than the queue holds
+/// (pass size = queue capacity / boxes per state).  A batch whose worst case fits runs one pass with no host
+/// involvement; otherwise the survivor count is read back once and only the passes that have work are launched.  (Before this, a 1 M-motion orchard batch pushed 3/4 of
+/// its boxes through stage A's one-thread-per-box overflow path: 14 ms instead of ~2.)
+/// How far the survivor list actually got (flat slot range).  Only called when a batch cannot be guaranteed to fit one
+/// pass: a small synchronous read-back of the shard counters is cheaper than launching passes over an empty tail.
+static cudaError_t survivor_slot_range(const SurvivorsDev &S, cudaStream_t stream, size_t *range) {
+	static thread_local unsigned h_counts[SHARDS * COUNTER_STRIDE];
+	cudaError_t e = cudaMemcpyAsync(h_counts, S.counts, sizeof(h_counts), cudaMemcpyDeviceToHost, stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+	if (e != cudaSuccess) return e;
+	unsigned m = 0;
+	for (unsigned s = 0; s < SHARDS; ++s) m = h_counts[s * COUNTER_STRIDE] > m ? h_counts[s * COUNTER_STRIDE] : m;
+	size_t r = (size_t) ((m + SHARD_BLOCK - 1) / SHARD_BLOCK) * SHARDS * SHARD_BLOCK;
+	*range = r < S.cap ? r : S.cap;
+	return cudaSuccess;
+}
+
+static size_t pass_size(const QueueDev &Q, int boxes_per_state) {
+	size_t r = (size_t) Q.cap / (size_t) (boxes_per_state > 0 ? boxes_per_state : 1);
+	const size_t grain = (size_t) SHARDS * SHARD_BLOCK;
+	r = r / grain * grain;
+	return r ? r : grain;
+}
+
 cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const double *d_states, size_t n, size_t stride,
 								uint32_t *d_hit_bits, void *scratch, size_t scratch_bytes, cudaStream_t stream) {
 	if (!n) return cudaSuccess;
@@ -900,9 +927,17 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 	}
 	k_cull_states<<<grid_for(n, BLOCK_A, 8), BLOCK_A, BLOCK_A * stride * sizeof(double), stream>>>(sc, rb, d_states, n, stride, S, Q, res);
 	LQ_CHECK(cudaGetLastError());
-	k_expand_states<<<grid_for(n, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_states, stride, S, Q, res);
-	LQ_CHECK(cudaGetLastError());
-	return run_traverse(sc, rb, nullptr, Q, res, n * (size_t) rb.n_boxes, stream);
+	const size_t R = pass_size(Q, rb.n_boxes);
+	size_t end = S.cap;
+	if (end > R) LQ_CHECK(survivor_slot_range(S, stream, &end));
+	for (size_t lo = 0; lo < end || lo == 0; lo += R) {
+		const size_t hi = lo + R < end ? lo + R : end;
+		if (lo) LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
+		k_expand_states<<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_states, stride, S, (unsigned) lo, (unsigned) hi, Q, res);
+		LQ_CHECK(cudaGetLastError());
+		LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (hi - lo) * (size_t) rb.n_boxes, stream));
+	}
+	return cudaSuccess;
 }
 
 cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t n, uint32_t *d_hit_bits, void *scratch,
@@ -911,11 +946,16 @@ cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t
 	QueueDev Q = carve_queue(scratch, scratch_bytes);
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	RobotDev none{};
-	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
-	k_expand_boxes<<<grid_for(n, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, d_boxes, n, Q, res);
-	LQ_CHECK(cudaGetLastError());
-	return run_traverse(sc, none, d_boxes, Q, res, n, stream);
+	const size_t R = pass_size(Q, 1);
+	for (size_t lo = 0; lo < n; lo += R) {
+		const size_t hi = lo + R < n ? lo + R : n;
+		LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
+		k_expand_boxes<<<grid_for(hi - lo, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, d_boxes, lo, hi, Q, res);
+		LQ_CHECK(cudaGetLastError());
+		LQ_CHECK(run_traverse(sc, none, d_boxes, Q, res, hi - lo, stream));
+	}
+	return cudaSuccess;
 }
 
 cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const double *d_a, const double *d_b, size_t m,
@@ -933,18 +973,18 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	k_motion_ranges<<<grid_for(m, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
 																	  d_n_steps, d_uncertain, (double2 *) d_slerp, S, Q, res);
 	LQ_CHECK(cudaGetLastError());
-	static int a2_blocks = 0;
-	if (!a2_blocks) {
-		const char *e = getenv("MGODPL_EXPAND_BLOCKS");
-		a2_blocks = e ? atoi(e) : 2;
+	const size_t R = pass_size(Q, rb.n_boxes);
+	size_t end = S.cap;
+	if (end > R) LQ_CHECK(survivor_slot_range(S, stream, &end));
+	for (size_t lo = 0; lo < end || lo == 0; lo += R) {
+		const size_t hi = lo + R < end ? lo + R : end;
+		// pass 0 shares the queue with stage A1's own overflow path (a survivor list that ran full expands inline)
+		if (lo) LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
+		k_expand_motion_steps<2><<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const double2 *) d_slerp, S,
+																						 (unsigned) lo, (unsigned) hi, Q, res);
+		LQ_CHECK(cudaGetLastError());
+		LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (hi - lo) * (size_t) rb.n_boxes, stream));
 	}
-	switch (a2_blocks) {
-		case 4: k_expand_motion_steps<4><<<grid_for(S.cap, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const double2 *) d_slerp, S, Q, res); break;
-		case 3: k_expand_motion_steps<3><<<grid_for(S.cap, BLOCK_A, 3), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const double2 *) d_slerp, S, Q, res); break;
-		default: k_expand_motion_steps<2><<<grid_for(S.cap, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const double2 *) d_slerp, S, Q, res); break;
-	}
-	LQ_CHECK(cudaGetLastError());
-	LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (size_t) Q.cap, stream));
 	k_finish_motions<<<(unsigned) ((m + 255) / 256), 256, 0, stream>>>(d_first_step, d_n_steps, m, d_hit_bits, d_toi);
 	return cudaGetLastError();
 }
@@ -956,13 +996,17 @@ cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const do
 	if (!f || !s) return cudaSuccess;
 	QueueDev Q = carve_queue(scratch, scratch_bytes);
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
-	const size_t wpr = (s + 31) / 32;
-	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
+	const size_t wpr = (s + 31) / 32, total = f * s;
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, f * wpr * 4, stream));
-	k_expand_goals<<<grid_for(f * s, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_targets, f, s, d_draws, d_limits, seed,
-																		distance_from_target, d_states_out, Q, res);
-	LQ_CHECK(cudaGetLastError());
-	LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, f * s * (size_t) rb.n_boxes, stream));
+	const size_t R = pass_size(Q, rb.n_boxes);  // the callers size the queue with 1/8 head-room for shard imbalance
+	for (size_t lo = 0; lo < total; lo += R) {
+		const size_t hi = lo + R < total ? lo + R : total;
+		LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
+		k_expand_goals<<<grid_for(hi - lo, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_targets, f, s, d_draws, d_limits, seed, distance_from_target,
+																			  d_states_out, lo, hi, Q, res);
+		LQ_CHECK(cudaGetLastError());
+		LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (hi - lo) * (size_t) rb.n_boxes, stream));
+	}
 	if (d_collisions) {
 		k_count_rows<<<(unsigned) f, 128, 0, stream>>>(d_hit_bits, f, wpr, d_collisions);
 		LQ_CHECK(cudaGetLastError());
