@@ -2,7 +2,10 @@
 // collapsing -> depth-first preorder flattening with skip links.  Stands where meshToFclBVH stood
 // (src/planning/fcl_utils.cpp:23-56): same input (the Mesh's vertices and index triples, identity pose), a different
 // acceleration structure.  Runs once per scene; everything it produces stays resident in HBM.
+#include <cstdlib>
+
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "geometry.cuh"
 #include "kernels.h"
@@ -95,6 +98,69 @@ __device__ __forceinline__ float half_area6(float4 alo, float4 ahi, float4 blo, 
 __device__ __forceinline__ float half_area1(float4 lo, float4 hi) {
 	float x = hi.x - lo.x, y = hi.y - lo.y, z = hi.z - lo.z;
 	return x * y + y * z + z * x;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SAH-driven topology: parallel locally-ordered clustering (Meister & Bittner 2018) over the Morton-sorted leaves.
+// Every round, each cluster looks `PLOC_RADIUS` neighbours to either side for the partner that minimises the surface
+// area of the merged box; mutual nearest neighbours merge; the survivors are compacted in order.  Compared with
+// splitting on Morton bits this builds the tree bottom-up by the quantity the traversal cost depends on.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PLOC_RADIUS = 16;
+
+__global__ void k_ploc_init(int n, const uint32_t *__restrict__ ids, const float4 *__restrict__ tlo, const float4 *__restrict__ thi,
+							int *__restrict__ cn, float4 *__restrict__ clo, float4 *__restrict__ chi) {
+	int j = blockIdx.x * TB + threadIdx.x;
+	if (j >= n) return;
+	const uint32_t t = ids[j];
+	cn[j] = j + n - 1, clo[j] = tlo[t], chi[j] = thi[t];
+}
+
+__global__ void k_ploc_nearest(int c, int radius, const float4 *__restrict__ clo, const float4 *__restrict__ chi, int *__restrict__ nn) {
+	int i = blockIdx.x * TB + threadIdx.x;
+	if (i >= c) return;
+	const float4 lo = clo[i], hi = chi[i];
+	float best = 3.0e38f;
+	int arg = -1;
+	const int j0 = max(0, i - radius), j1 = min(c - 1, i + radius);
+	for (int j = j0; j <= j1; ++j) {
+		if (j == i) continue;
+		const float a = half_area6(lo, hi, clo[j], chi[j]);
+		if (a < best) best = a, arg = j;  // ties keep the smaller index: deterministic
+	}
+	nn[i] = arg;
+}
+
+__global__ void k_ploc_merge(int c, int *__restrict__ cn, float4 *__restrict__ clo, float4 *__restrict__ chi, const int *__restrict__ nn,
+							 int *__restrict__ next_id, int *__restrict__ left, int *__restrict__ right, int *__restrict__ parent,
+							 unsigned *__restrict__ keep) {
+	int i = blockIdx.x * TB + threadIdx.x;
+	if (i >= c) return;
+	const int j = nn[i];
+	const bool mutual = j >= 0 && nn[j] == i;
+	if (mutual && i > j) {
+		keep[i] = 0;  // absorbed by the lower-indexed partner
+		return;
+	}
+	keep[i] = 1;
+	if (!mutual) return;
+	const int id = atomicSub(next_id, 1);  // internal ids count down: the last merge of the build receives id 0 = the root
+	const int a = cn[i], b = cn[j];
+	left[id] = a, right[id] = b;
+	parent[a] = id, parent[b] = id;
+	const float4 alo = clo[i], ahi = chi[i], blo2 = clo[j], bhi2 = chi[j];
+	cn[i] = id;
+	clo[i] = make_float4(fminf(alo.x, blo2.x), fminf(alo.y, blo2.y), fminf(alo.z, blo2.z), 0.f);
+	chi[i] = make_float4(fmaxf(ahi.x, bhi2.x), fmaxf(ahi.y, bhi2.y), fmaxf(ahi.z, bhi2.z), 0.f);
+}
+
+__global__ void k_ploc_compact(int c, const unsigned *__restrict__ keep, const unsigned *__restrict__ pos, const int *__restrict__ cn,
+							   const float4 *__restrict__ clo, const float4 *__restrict__ chi, int *__restrict__ cn2,
+							   float4 *__restrict__ clo2, float4 *__restrict__ chi2) {
+	int i = blockIdx.x * TB + threadIdx.x;
+	if (i >= c || !keep[i]) return;
+	const unsigned p = pos[i];
+	cn2[p] = cn[i], clo2[p] = clo[i], chi2[p] = chi[i];
 }
 
 /// Bottom-up pass over the binary tree (atomic arrival flags: the second child to arrive owns the parent):
@@ -340,9 +406,51 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 	BS_CHECK(cudaMemsetAsync(flags, 0, nt * sizeof(unsigned), stream));
 	BS_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(BuildStats), stream));
 	BS_CHECK(cudaMemsetAsync(parent, 0xff, 2 * nt * sizeof(int), stream));
-	if (n > 1) {
-		k_topology<<<gt, TB, 0, stream>>>(keys2, n, left, right, parent);
+	if (n > 1 && !refine) {
+		k_topology<<<gt, TB, 0, stream>>>(keys2, n, left, right, parent);  // plain LBVH: split on Morton bits
 		BS_CHECK(cudaGetLastError());
+	} else if (n > 1) {
+		int *cn[2], *nn, *d_next;
+		float4 *clo[2], *chi[2];
+		unsigned *keep, *pos;
+		for (int b = 0; b < 2; ++b) {
+			BS_CHECK(tmp.alloc(&cn[b], nt));
+			BS_CHECK(tmp.alloc(&clo[b], nt));
+			BS_CHECK(tmp.alloc(&chi[b], nt));
+		}
+		BS_CHECK(tmp.alloc(&nn, nt));
+		BS_CHECK(tmp.alloc(&keep, nt + 1));
+		BS_CHECK(tmp.alloc(&pos, nt + 1));
+		BS_CHECK(tmp.alloc(&d_next, 1));
+		size_t scan_bytes = 0;
+		BS_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, keep, pos, n + 1, stream));
+		void *scan_ws;
+		BS_CHECK(tmp.alloc((char **) &scan_ws, scan_bytes));
+		const int first_id = n - 2;
+		BS_CHECK(cudaMemcpyAsync(d_next, &first_id, sizeof(int), cudaMemcpyHostToDevice, stream));
+		k_ploc_init<<<gt, TB, 0, stream>>>(n, ids2, tlo, thi, cn[0], clo[0], chi[0]);
+		BS_CHECK(cudaGetLastError());
+		static int ploc_radius = 0;
+		if (!ploc_radius) {
+			const char *e = getenv("MGODPL_PLOC_RADIUS");
+			ploc_radius = e && atoi(e) > 0 ? atoi(e) : PLOC_RADIUS;
+		}
+		int c = n, cur = 0;
+		while (c > 1) {
+			const unsigned g = (unsigned) ((c + TB - 1) / TB);
+			k_ploc_nearest<<<g, TB, 0, stream>>>(c, ploc_radius, clo[cur], chi[cur], nn);
+			k_ploc_merge<<<g, TB, 0, stream>>>(c, cn[cur], clo[cur], chi[cur], nn, d_next, left, right, parent, keep);
+			BS_CHECK(cudaGetLastError());
+			BS_CHECK(cudaMemsetAsync(keep + c, 0, sizeof(unsigned), stream));
+			BS_CHECK(cub::DeviceScan::ExclusiveSum(scan_ws, scan_bytes, keep, pos, c + 1, stream));
+			k_ploc_compact<<<g, TB, 0, stream>>>(c, keep, pos, cn[cur], clo[cur], chi[cur], cn[cur ^ 1], clo[cur ^ 1], chi[cur ^ 1]);
+			BS_CHECK(cudaGetLastError());
+			unsigned c_new = 0;
+			BS_CHECK(cudaMemcpyAsync(&c_new, pos + c, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+			BS_CHECK(cudaStreamSynchronize(stream));
+			if ((int) c_new >= c) return cudaErrorUnknown;  // every round merges at least the globally closest pair
+			c = (int) c_new, cur ^= 1;
+		}
 	}
 	// Pass 0 fits the bounds; with refinement on, it and two more sweeps also apply SAH-lowering rotations.
 	const int sweeps = refine && n > 2 ? 3 : 1;
