@@ -15,6 +15,7 @@
 // Far-away states (the majority under PRM-style sampling) cost a 24-byte read and a handful of flops in stage A;
 // boxes that do need a tree descent are compacted, so stage B runs converged and at full occupancy.  If the queue
 // would overflow, stage A traverses the box on the spot — capacity is a performance knob, never a correctness one.
+#include <algorithm>
 #include <cooperative_groups.h>
 #include <cstdlib>
 
@@ -180,7 +181,7 @@ __device__ __noinline__ bool box_hits_scene(const SceneDev &sc, const CullBox &c
 constexpr unsigned SHARDS = 64, SHARD_BLOCK = 32;
 constexpr unsigned COUNTER_STRIDE = 32;  // one 128-byte line per counter: neighbouring counters would share an L2 atomic unit
 constexpr size_t QUEUE_HEADER = SHARDS * COUNTER_STRIDE * sizeof(unsigned) + 256;  // queue counters + cursor: reset before every pass
-constexpr size_t SCRATCH_HEADER = QUEUE_HEADER + SHARDS * COUNTER_STRIDE * sizeof(unsigned);
+constexpr size_t SCRATCH_HEADER = QUEUE_HEADER + 2 * SHARDS * COUNTER_STRIDE * sizeof(unsigned);  // + two survivor lists
 
 __device__ __forceinline__ unsigned my_shard() { return (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) & (SHARDS - 1); }
 __device__ __forceinline__ unsigned shard_slot(unsigned shard, unsigned local) {
@@ -477,13 +478,14 @@ __global__ void __launch_bounds__(BLOCK_A)
 k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
 				const double *__restrict__ b, size_t m, size_t stride, int js, double max_step,
 				const uint32_t *__restrict__ n_steps_override, uint32_t *__restrict__ n_steps_out,
-				uint32_t *__restrict__ uncertain_bits, double2 *__restrict__ slerp_out, SurvivorsDev S, QueueDev Q, Results res) {
+				uint32_t *__restrict__ uncertain_bits, double2 *__restrict__ slerp_out, SurvivorsDev S, SurvivorsDev S_tail,
+				unsigned head_steps, QueueDev Q, Results res) {
 	const unsigned lane = threadIdx.x & 31;
 	LocalCounters lc;
 	unsigned long long n_uncertain = 0, n_motions = 0;
 	const size_t m_pad = (m + 31) & ~(size_t) 31;
 	for (size_t i = (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < m_pad; i += (size_t) gridDim.x * BLOCK_A) {
-		unsigned s_lo = 0, len = 0, n_steps = 0;
+		unsigned s_lo = 0, len = 0, n_steps = 0, head = head_steps;
 		if (i < m) {
 			const double *A = a + i * stride, *B = b + i * stride;
 			double ar[7], br[7];
@@ -496,6 +498,7 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 			const double cc = fmin(fmax(c, -1.0), 1.0);
 			d += acos(2.0 * cc * cc - 1.0);
 			for (int k = 0; k < js; ++k) d += fabs(__ldg(A + 7 + k) - __ldg(B + 7 + k));
+			const double trans = sqrt(dx * dx + dy * dy + dz * dz);
 			const double x = d / max_step;
 			double nd = ceil(x);
 			bool uncertain = fabs(x - rint(x)) < 1e-9 * fmax(1.0, x);
@@ -555,6 +558,9 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 				for (int guard = 0; guard < 64 && s_lo < s_hi && outside(s_lo); ++guard) ++s_lo;
 				for (int guard = 0; guard < 64 && s_hi > s_lo && outside(s_hi); ++guard) --s_hi;
 				len = (s_lo == s_hi && outside(s_lo)) ? 0u : s_hi - s_lo + 1;
+				// head_steps == 0: adaptive head — the steps it takes to cross the reach shell around the scene bounds plus
+				// ~0.75 m of canopy, where a colliding motion typically finds its first hit
+				if (!head_steps) head = (unsigned) fmin(fmax((rb.reach + 0.75) * (double) n_steps / fmax(trans, 1e-3 * (double) n_steps), 8.0), 256.0);
 			}
 		}
 		__syncwarp();  // slerp_out[] of this warp's motions is read by other lanes on the overflow path
@@ -565,14 +571,22 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 			todo &= todo - 1;
 			const unsigned l = __shfl_sync(0xffffffffu, len, src), lo = __shfl_sync(0xffffffffu, s_lo, src);
 			const unsigned mot = (unsigned) (i - lane + src), ns = __shfl_sync(0xffffffffu, n_steps, src);
-			unsigned base = 0;
+			// The first head_steps steps of the range go to the head list, the rest to the tail list: the head is expanded
+			// and traversed first, and tail entries of motions that already collided by then are never expanded.
 			const unsigned shard = my_shard();
-			if (lane == 0) base = atomicAdd(S.counts + shard * COUNTER_STRIDE, l);
-			base = __shfl_sync(0xffffffffu, base, 0);
-			for (unsigned k = lane; k < l; k += 32) {
-				const unsigned pos = shard_slot(shard, base + k);
-				if (pos < S.cap) S.entries[pos] = make_uint2(mot, lo + k);
-				else expand_motion_step(sc, rb, Q, res, a + (size_t) mot * stride, b + (size_t) mot * stride, ns, slerp_out[mot], mot, lo + k, lc);
+			const unsigned l_head = min(l, __shfl_sync(0xffffffffu, head, src));
+			for (int part = 0; part < 2; ++part) {
+				const SurvivorsDev &L = part ? S_tail : S;
+				const unsigned first = part ? l_head : 0u, cnt = part ? l - l_head : l_head;
+				if (!cnt) continue;
+				unsigned base = 0;
+				if (lane == 0) base = atomicAdd(L.counts + shard * COUNTER_STRIDE, cnt);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				for (unsigned k = lane; k < cnt; k += 32) {
+					const unsigned pos = shard_slot(shard, base + k), step = lo + first + k;
+					if (pos < L.cap) L.entries[pos] = make_uint2(mot, step);
+					else expand_motion_step(sc, rb, Q, res, a + (size_t) mot * stride, b + (size_t) mot * stride, ns, slerp_out[mot], mot, step, lc);
+				}
 			}
 		}
 	}
@@ -588,7 +602,8 @@ template<int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK_A, MIN_BLOCKS)
 k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
 					  const double *__restrict__ b, size_t stride, const uint32_t *__restrict__ n_steps,
-					  const double2 *__restrict__ slerp_k, SurvivorsDev S, unsigned pass_lo, unsigned pass_hi, QueueDev Q, Results res) {
+					  const double2 *__restrict__ slerp_k, SurvivorsDev S, unsigned pass_lo, unsigned pass_hi, int skip_decided, QueueDev Q,
+					  Results res) {
 	LocalCounters lc;
 	__shared__ unsigned s_counts[SHARDS];
 	load_shard_counts(s_counts, S.counts);
@@ -596,6 +611,7 @@ k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant
 	for (unsigned k = pass_lo + blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
 		if (!slot_filled(s_counts, k)) continue;
 		const uint2 e = __ldcg(&S.entries[k]);
+		if (skip_decided && __ldcg(res.first_step + e.x) <= e.y) continue;  // an earlier step of this motion already collides
 		expand_motion_step(sc, rb, Q, res, a + (size_t) e.x * stride, b + (size_t) e.x * stride, __ldg(n_steps + e.x), __ldg(slerp_k + e.x),
 						   e.x, e.y, lc);
 	}
@@ -837,7 +853,8 @@ size_t query_scratch_bytes(size_t worst_case_boxes, size_t survivor_entries) {
 }
 
 /// Scratch layout: [header: queue shard counters | survivor shard counters | queue cursor][survivor entries][queue items].
-static void carve(void *scratch, size_t scratch_bytes, size_t survivor_entries, SurvivorsDev *S, QueueDev *Q) {
+static void carve(void *scratch, size_t scratch_bytes, size_t survivor_entries, SurvivorsDev *S, QueueDev *Q,
+				  SurvivorsDev *S_tail = nullptr, size_t head_entries = 0) {
 	char *p = reinterpret_cast<char *>(scratch);
 	unsigned *hdr = reinterpret_cast<unsigned *>(p);
 	Q->counts = hdr;
@@ -848,6 +865,16 @@ static void carve(void *scratch, size_t scratch_bytes, size_t survivor_entries, 
 		S->counts = hdr + QUEUE_HEADER / sizeof(unsigned);
 		S->entries = reinterpret_cast<uint2 *>(p + SCRATCH_HEADER);
 		S->cap = (unsigned) scap;
+	}
+	if (S && S_tail) {  // split the entry region: [head | tail]
+		const size_t grain = (size_t) SHARDS * SHARD_BLOCK;
+		size_t hcap = head_entries < scap / 2 ? head_entries : scap / 2;
+		hcap = (hcap + grain - 1) / grain * grain;
+		if (hcap > scap) hcap = scap;
+		S->cap = (unsigned) hcap;
+		S_tail->counts = S->counts + SHARDS * COUNTER_STRIDE;
+		S_tail->entries = S->entries + hcap;
+		S_tail->cap = (unsigned) (scap - hcap);
 	}
 	Q->items = reinterpret_cast<Item *>(p + SCRATCH_HEADER + sbytes);
 	size_t cap = scratch_bytes > SCRATCH_HEADER + sbytes ? (scratch_bytes - SCRATCH_HEADER - sbytes) / sizeof(Item) : 0;
@@ -892,15 +919,19 @@ static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const do
 /// its boxes through stage A's one-thread-per-box overflow path: 14 ms instead of ~2.)
 /// How far the survivor list actually got (flat slot range).  Only called when a batch cannot be guaranteed to fit one
 /// pass: a small synchronous read-back of the shard counters is cheaper than launching passes over an empty tail.
-static cudaError_t survivor_slot_range(const SurvivorsDev &S, cudaStream_t stream, size_t *range) {
-	static thread_local unsigned h_counts[SHARDS * COUNTER_STRIDE];
-	cudaError_t e = cudaMemcpyAsync(h_counts, S.counts, sizeof(h_counts), cudaMemcpyDeviceToHost, stream);
+static cudaError_t survivor_slot_ranges(const SurvivorsDev *lists, int n_lists, cudaStream_t stream, size_t *ranges) {
+	// the lists' counter blocks are adjacent in the scratch header: one copy, one synchronisation
+	static thread_local unsigned h_counts[2 * SHARDS * COUNTER_STRIDE];
+	cudaError_t e = cudaMemcpyAsync(h_counts, lists[0].counts, (size_t) n_lists * SHARDS * COUNTER_STRIDE * sizeof(unsigned),
+									cudaMemcpyDeviceToHost, stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
 	if (e != cudaSuccess) return e;
-	unsigned m = 0;
-	for (unsigned s = 0; s < SHARDS; ++s) m = h_counts[s * COUNTER_STRIDE] > m ? h_counts[s * COUNTER_STRIDE] : m;
-	size_t r = (size_t) ((m + SHARD_BLOCK - 1) / SHARD_BLOCK) * SHARDS * SHARD_BLOCK;
-	*range = r < S.cap ? r : S.cap;
+	for (int l = 0; l < n_lists; ++l) {
+		unsigned m = 0;
+		for (unsigned s = 0; s < SHARDS; ++s) m = std::max(m, h_counts[(l * SHARDS + s) * COUNTER_STRIDE]);
+		size_t r = (size_t) ((m + SHARD_BLOCK - 1) / SHARD_BLOCK) * SHARDS * SHARD_BLOCK;
+		ranges[l] = r < lists[l].cap ? r : lists[l].cap;
+	}
 	return cudaSuccess;
 }
 
@@ -929,7 +960,7 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 	LQ_CHECK(cudaGetLastError());
 	const size_t R = pass_size(Q, rb.n_boxes);
 	size_t end = S.cap;
-	if (end > R) LQ_CHECK(survivor_slot_range(S, stream, &end));
+	if (end > R) LQ_CHECK(survivor_slot_ranges(&S, 1, stream, &end));
 	for (size_t lo = 0; lo < end || lo == 0; lo += R) {
 		const size_t hi = lo + R < end ? lo + R : end;
 		if (lo) LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
@@ -963,27 +994,42 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned *d_first_step, void *d_slerp,
 								 void *scratch, size_t scratch_bytes, size_t survivor_entries, cudaStream_t stream) {
 	if (!m) return cudaSuccess;
-	SurvivorsDev S;
+	SurvivorsDev S, S_tail;
 	QueueDev Q;
-	carve(scratch, scratch_bytes, survivor_entries, &S, &Q);
+	static unsigned head_steps = 0;
+	if (!head_steps) {
+		const char *e = getenv("MGODPL_HEAD_STEPS");
+		head_steps = e && atoi(e) > 0 ? (unsigned) atoi(e) : 0x80000000u;  // default: adaptive per motion
+	}
+	const unsigned head_arg = head_steps == 0x80000000u ? 0u : head_steps;
+	carve(scratch, scratch_bytes, survivor_entries, &S, &Q, &S_tail, m * (size_t) (head_arg ? head_arg : 48u));
 	Results res{RESULT_FIRST_STEP, nullptr, d_first_step};
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_first_step, 0xff, m * sizeof(unsigned), stream));
 	if (d_uncertain) LQ_CHECK(cudaMemsetAsync(d_uncertain, 0, ((m + 31) / 32) * 4, stream));
 	k_motion_ranges<<<grid_for(m, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
-																	  d_n_steps, d_uncertain, (double2 *) d_slerp, S, Q, res);
+																	  d_n_steps, d_uncertain, (double2 *) d_slerp, S, S_tail, head_arg, Q, res);
 	LQ_CHECK(cudaGetLastError());
+	// Head list first (the steps right after a motion comes within reach of the scene), then the tail with the
+	// "already collided" skip: most of a colliding motion's in-reach steps lie after its first hit.
 	const size_t R = pass_size(Q, rb.n_boxes);
-	size_t end = S.cap;
-	if (end > R) LQ_CHECK(survivor_slot_range(S, stream, &end));
-	for (size_t lo = 0; lo < end || lo == 0; lo += R) {
-		const size_t hi = lo + R < end ? lo + R : end;
-		// pass 0 shares the queue with stage A1's own overflow path (a survivor list that ran full expands inline)
-		if (lo) LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
-		k_expand_motion_steps<2><<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const double2 *) d_slerp, S,
-																						 (unsigned) lo, (unsigned) hi, Q, res);
-		LQ_CHECK(cudaGetLastError());
-		LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (hi - lo) * (size_t) rb.n_boxes, stream));
+	bool first_pass = true;
+	const SurvivorsDev lists[2] = {S, S_tail};
+	size_t ends[2] = {S.cap, S_tail.cap};
+	if (ends[0] > R || ends[1] > R) LQ_CHECK(survivor_slot_ranges(lists, 2, stream, ends));
+	for (int part = 0; part < 2; ++part) {
+		const SurvivorsDev &L = lists[part];
+		const size_t end = ends[part];
+		for (size_t lo = 0; lo < end; lo += R) {
+			const size_t hi = lo + R < end ? lo + R : end;
+			// the first pass shares the queue with stage A1's own overflow path (a survivor list that ran full expands inline)
+			if (!first_pass) LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
+			first_pass = false;
+			k_expand_motion_steps<2><<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const double2 *) d_slerp, L,
+																							 (unsigned) lo, (unsigned) hi, part, Q, res);
+			LQ_CHECK(cudaGetLastError());
+			LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (hi - lo) * (size_t) rb.n_boxes, stream));
+		}
 	}
 	k_finish_motions<<<(unsigned) ((m + 255) / 256), 256, 0, stream>>>(d_first_step, d_n_steps, m, d_hit_bits, d_toi);
 	return cudaGetLastError();
