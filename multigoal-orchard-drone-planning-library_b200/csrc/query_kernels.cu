@@ -130,12 +130,19 @@ __device__ __forceinline__ int visit_record(const SceneDev &sc, const CullBox &c
 	const bool ov_r = cull_overlap(cb, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
 	const int lref = __float_as_int(n3.x), rref = __float_as_int(n3.y);
 	int next = REF_END;
-	if (ov_l) next = lref;
-	if (ov_r) {
-		if (next == REF_END) next = rref;
-		else stack[sp++] = rref;
+	if (ov_l && ov_r) {
+		// any-hit query: walk into the child whose centre is nearer to the box first — a colliding box finds its hit sooner
+		const float lx = n0.x - cb.cx, ly = n0.y - cb.cy, lz = n0.z - cb.cz, rx = n1.z - cb.cx, ry = n1.w - cb.cy, rz = n2.x - cb.cz;
+		const bool right_first = rx * rx + ry * ry + rz * rz < lx * lx + ly * ly + lz * lz;
+		next = right_first ? rref : lref;
+		stack[sp++] = right_first ? lref : rref;
+	} else if (ov_l) {
+		next = lref;
+	} else if (ov_r) {
+		next = rref;
+	} else if (sp > 0) {
+		next = stack[--sp];
 	}
-	if (next == REF_END && sp > 0) next = stack[--sp];
 	return next;
 }
 
