@@ -253,12 +253,12 @@ def run_ours(args):
         "states_checked_per_motion": states_all / motions_all, "collision_rate": float(hit.mean()),
         "e2e": {"value": e2e_value, "unit": "states/s", "h2d_bytes_per_step": int(2 * m * stride * 8),
                 "d2h_bytes_per_step": int(2 * words * 4 + m * 4 + m * 8), "steps": e2e_steps},
-        # our kernels inside the device-timed region: k_motion_ranges, k_expand_motion_steps, k_traverse, k_finish_motions per step
-        "gpu_launches": 4 * args.steps,
+        # our kernels inside the device-timed region, per step: k_motion_ranges, 2 x (k_expand_motion_steps, k_traverse), k_finish_motions
+        "gpu_launches": 6 * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_kind": peak_kind,
-                     "kernel": "check_motions pipeline: k_motion_ranges + k_expand_motion_steps + k_traverse (dominant, ~58 % of the step per "
-                               "profiles/r01_launch_list_final.txt) + k_finish_motions",
+                     "kernel": "check_motions pipeline: k_motion_ranges + 2 x (k_expand_motion_steps + k_traverse) + k_finish_motions; k_traverse is the "
+                               "dominant kernel (~51 % of the step per profiles/r01_ncu_full_final_motion_pipeline.txt)",
                      "algorithmic_bytes_per_launch": algo_bytes},
         "clocks": sampler.summary(),
         "scene": {"build_ms": info.build_ms, "sah_cost": info.sah_cost, "max_depth": int(info.max_depth),
