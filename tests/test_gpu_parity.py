@@ -93,3 +93,72 @@ def test_check_boxes_matches_oracle(gpu, oracle, scene_pair):
     rep = parity_report(got, want, clearance)
     assert rep["n_mismatch_outside_band"] == 0, rep
     assert 0.05 < want.mean() < 0.95
+
+
+def _quat(axis, angle):
+    axis = np.asarray(axis, float) / np.linalg.norm(axis)
+    return [*(axis * np.sin(angle / 2)), np.cos(angle / 2)]
+
+
+def build_odd_robot(oracle):
+    """A robot the procedural generator never makes: two arms branching off the base, a joint declared child->parent
+    (crossed from linkB: the variable transform is inverted, RobotModel.cpp:66-67), attachments with rotations, a link
+    with two shapes that carry their own transforms, a fixed joint in the middle of a chain and a link no joint reaches
+    (it keeps the root transform, RobotModel.cpp:23-24)."""
+    r = oracle.Robot(None)
+    base = r.add_link("flying_base")
+    r.add_box(base, (0.6, 0.5, 0.2))
+    left = r.add_link("left_arm")
+    r.add_box(left, (0.05, 0.6, 0.05))
+    r.add_box(left, (0.2, 0.05, 0.05), (0.0, 0.3, 0.0, *_quat((0, 0, 1), 0.4)))
+    right = r.add_link("right_arm")
+    r.add_box(right, (0.04, 0.5, 0.04), (0.0, 0.0, 0.02, 0, 0, 0, 1))
+    fore = r.add_link("forearm")
+    r.add_box(fore, (0.05, 0.4, 0.05))
+    ee = r.add_link("end_effector")
+    orphan = r.add_link("orphan")
+    r.add_box(orphan, (0.1, 0.1, 0.5), (0.0, 0.0, 0.35, 0, 0, 0, 1))
+    r.add_joint(base, left, (0.3, 0.1, 0, *_quat((0, 0, 1), 0.3)), (0, -0.3, 0, 0, 0, 0, 1), oracle.REVOLUTE, (1, 0, 0), -1.2, 1.2)
+    # declared from the child's side: link_a = right arm, link_b = base
+    r.add_joint(right, base, (0, -0.25, 0, *_quat((1, 0, 0), 0.2)), (-0.3, 0.1, 0, *_quat((0, 1, 0), -0.25)), oracle.REVOLUTE, (0, 0, 1), -1.0, 1.0)
+    r.add_joint(left, fore, (0, 0.3, 0, 0, 0, 0, 1), (0, -0.2, 0, *_quat((0, 0, 1), 0.1)), oracle.REVOLUTE, (0, 1, 0), -1.5, 1.5)
+    r.add_joint(fore, ee, (0, 0.2, 0, 0, 0, 0, 1), (0, 0, 0, 0, 0, 0, 1), oracle.FIXED)
+    return r
+
+
+def test_general_robot_topologies(gpu, oracle, scene_pair):
+    """FK op list, box ordering and reach bound on a branching robot with an inverted joint and an unreachable link."""
+    dscene, oscene, _ = scene_pair
+    orb = build_odd_robot(oracle)
+    drb = device_robot_from_oracle(gpu, orb)
+    assert orb.n_variables == drb.n_variables == 3
+    rng = np.random.default_rng(8)
+    n = 6000
+    yaw = rng.uniform(-np.pi, np.pi, n)
+    tilt = rng.uniform(-0.4, 0.4, (n, 2))
+    q = np.array([oracle.tf_then([0, 0, 0, *_quat((0, 0, 1), y)], [0, 0, 0, *_quat((1, 0, 0), a)])[3:] for y, a in zip(yaw, tilt[:, 0])])
+    states = np.concatenate([rng.uniform([-2.2, -2.2, 0.2], [2.2, 2.2, 3.4], (n, 3)), q, rng.uniform(-1.0, 1.0, (n, 3)), rng.uniform(-9, 9, (n, 1))], axis=1)
+    got_fk = gpu.forward_kinematics(drb, states[:300])
+    want_fk = np.stack([orb.fk(s) for s in states[:300]])
+    assert np.abs(got_fk - want_fk).max() < 1e-12
+    want, cl = oscene.check_states(orb, states, clearance=True, threads=8)
+    rep = parity_report(gpu.check_states(dscene, drb, states), want, cl)
+    assert rep["n_mismatch_outside_band"] == 0, rep
+    assert 0.05 < want.mean() < 0.95
+    a, b = states[:1500], states[1500:3000]
+    wm = oscene.check_motions(orb, a, b, band=True, threads=8)
+    gm = gpu.check_motions(dscene, drb, a, b)
+    assert np.array_equal(gm["n_steps"], wm["n_steps"])  # the surplus 4th joint value counts in the distance (SURVEY Q6)
+    ok = wm["min_abs_clearance"] > BAND
+    assert np.array_equal(gm["hit"][ok], wm["hit"][ok])
+    both = gm["hit"] & wm["hit"] & ok
+    assert np.array_equal(gm["toi"][both], wm["toi"][both])
+    # goal sampling through the forearm chain
+    draws = oracle.goal_draws(orb, 400, seed=3)
+    assert draws.shape[1] == 4
+    targets = np.array([[0.4, 0.3, 1.9], [-0.5, 0.2, 2.3], [3.5, 3.5, 1.0]])
+    gg = gpu.sample_goals(dscene, drb, targets, 400, draws=draws, want_states=True)
+    want_states = np.stack([oracle.gen_goal_states(orb, t, 400, seed=3) for t in targets])
+    assert np.abs(gg["states"] - want_states).max() < 1e-12
+    wg, cg = oscene.check_states(orb, want_states.reshape(-1, want_states.shape[-1]), clearance=True, threads=8)
+    assert parity_report(gg["hit"].reshape(-1), wg, cg)["n_mismatch_outside_band"] == 0
