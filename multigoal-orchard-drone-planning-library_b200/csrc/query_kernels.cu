@@ -32,21 +32,17 @@ constexpr unsigned NO_HIT = 0xFFFFFFFFu;
 constexpr int ROW_MAX = 7 + MGODPL_MAX_JOINT_VALUES;
 
 // ---------------------------------------------------------------------------------------------------------------
-// Work queue: 128-byte items.  The fp32 culling box (centre relative to the scene origin + rotation) is what the
-// traversal keeps in registers; the fp64 pose is only re-read when a leaf needs the exact test.
+// Work queue: 64-byte items = the box's exact fp64 pose (centre + quaternion) and its owner.  Stage B derives the
+// fp32 culling box from it when a lane picks the item up (a dozen conversions and ~25 fp32 flops) and re-reads the
+// same 64 bytes in the rare case a leaf needs the exact test; half the queue traffic of carrying both forms.
 // ---------------------------------------------------------------------------------------------------------------
 struct __align__(16) Item {
-	float cull_c[3];
-	float cull_r[9];
-	unsigned owner;
-	unsigned step_box;  // step | box << 28
-	unsigned pad0[2];
 	double c[3];
 	double q[4];
-	double pad1;
+	unsigned owner;
+	unsigned step_box;  // step | box << 28
 };
-static_assert(sizeof(Item) == 128, "queue item must be 128 bytes");
-constexpr unsigned ITEM_EXACT_OFFSET = 64;  // byte offset of Item::c
+static_assert(sizeof(Item) == 64, "queue item must be 64 bytes");
 
 enum ResultMode : int { RESULT_BITS = 0, RESULT_FIRST_STEP = 1 };
 
@@ -231,16 +227,11 @@ __device__ __forceinline__ void emit_box(const SceneDev &sc, const QueueDev &Q, 
 	if (g.thread_rank() == 0) base = atomicAdd(Q.counts + shard * COUNTER_STRIDE, g.size());
 	const unsigned pos = shard_slot(shard, g.shfl(base, 0) + g.thread_rank());
 	if (pos < Q.cap) {
-		uint4 *dst = reinterpret_cast<uint4 *>(Q.items + pos);
-		__stcg(dst + 0, make_uint4(__float_as_uint(cb.cx), __float_as_uint(cb.cy), __float_as_uint(cb.cz), __float_as_uint(cb.r[0])));
-		__stcg(dst + 1, make_uint4(__float_as_uint(cb.r[1]), __float_as_uint(cb.r[2]), __float_as_uint(cb.r[3]), __float_as_uint(cb.r[4])));
-		__stcg(dst + 2, make_uint4(__float_as_uint(cb.r[5]), __float_as_uint(cb.r[6]), __float_as_uint(cb.r[7]), __float_as_uint(cb.r[8])));
-		__stcg(dst + 3, make_uint4(owner, step | box << 28, 0u, 0u));
-		double2 *dd = reinterpret_cast<double2 *>(dst + 4);
-		__stcg(dd + 0, make_double2(c.x, c.y));
-		__stcg(dd + 1, make_double2(c.z, q.x));
-		__stcg(dd + 2, make_double2(q.y, q.z));
-		__stcg(dd + 3, make_double2(q.w, 0.0));
+		double2 *dst = reinterpret_cast<double2 *>(Q.items + pos);
+		__stcg(dst + 0, make_double2(c.x, c.y));
+		__stcg(dst + 1, make_double2(c.z, q.x));
+		__stcg(dst + 2, make_double2(q.y, q.z));
+		__stcg(dst + 3, make_double2(q.w, __hiloint2double((int) (step | box << 28), (int) owner)));
 	} else if (!already_decided(res, owner, step)) {
 		if (box_hits_scene(sc, cb, c, q, half, lc)) report_hit(res, owner, step);
 	}
@@ -680,25 +671,21 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 			const unsigned avail = chunk_hi - chunk_lo, rank = __popc(idle_mask & ((1u << lane) - 1u));
 			if (idle && rank < avail && slot_filled(s_counts, chunk_lo + rank)) {
 				item = chunk_lo + rank;
-				const uint4 *src = reinterpret_cast<const uint4 *>(Q.items + item);
-				const uint4 v0 = __ldcg(src), v1 = __ldcg(src + 1), v2 = __ldcg(src + 2), v3 = __ldcg(src + 3);
-				owner = v3.x, step_box = v3.y;
+				const double2 *src = reinterpret_cast<const double2 *>(Q.items + item);
+				const double2 v0 = __ldcg(src), v1 = __ldcg(src + 1), v2 = __ldcg(src + 2), v3 = __ldcg(src + 3);
+				owner = (unsigned) __double2loint(v3.y), step_box = (unsigned) __double2hiint(v3.y);
 				// Motions: skip boxes of steps that can no longer be the first colliding one.  (For state bitmasks the
 				// same check only runs before a leaf test: it would cost a dependent L2 round trip per refill here.)
 				if (res.mode == RESULT_BITS || !already_decided(res, owner, step_box & 0x0FFFFFFFu)) {
-					cb.cx = __uint_as_float(v0.x), cb.cy = __uint_as_float(v0.y), cb.cz = __uint_as_float(v0.z);
-					cb.r[0] = __uint_as_float(v0.w), cb.r[1] = __uint_as_float(v1.x), cb.r[2] = __uint_as_float(v1.y);
-					cb.r[3] = __uint_as_float(v1.z), cb.r[4] = __uint_as_float(v1.w), cb.r[5] = __uint_as_float(v2.x);
-					cb.r[6] = __uint_as_float(v2.y), cb.r[7] = __uint_as_float(v2.z), cb.r[8] = __uint_as_float(v2.w);
-					float h0, h1, h2;
+					double half_d[3];
 					if (explicit_boxes) {
 						const double *bx = explicit_boxes + (size_t) owner * 10;
-						h0 = (float) (__ldg(bx + 7) * 0.5), h1 = (float) (__ldg(bx + 8) * 0.5), h2 = (float) (__ldg(bx + 9) * 0.5);
+						half_d[0] = __ldg(bx + 7) * 0.5, half_d[1] = __ldg(bx + 8) * 0.5, half_d[2] = __ldg(bx + 9) * 0.5;
 					} else {
 						const double *hh = rb.boxes[step_box >> 28].half;
-						h0 = (float) hh[0], h1 = (float) hh[1], h2 = (float) hh[2];
+						half_d[0] = hh[0], half_d[1] = hh[1], half_d[2] = hh[2];
 					}
-					finish_cull_box(sc, cb, h0, h1, h2);
+					cb = make_cull_box(sc, D3{v0.x, v0.y, v1.x}, Q4{v1.y, v2.x, v2.y, v3.x}, half_d);
 					cur = 0, sp = 0;
 					lc.boxes++;
 					max_box_nodes = max(max_box_nodes, box_nodes), box_nodes = 0;
@@ -740,7 +727,7 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 							half = rb.boxes[step_box >> 28].half;
 						}
 						unsigned n_exact = 0;
-						hit = exact_leaf_test(sc, reinterpret_cast<const char *>(Q.items + item) + ITEM_EXACT_OFFSET, half, cur, unknown, &n_exact);
+						hit = exact_leaf_test(sc, reinterpret_cast<const char *>(Q.items + item), half, cur, unknown, &n_exact);
 						lc.leaf += n_exact;
 					}
 					if (hit) {
