@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -614,6 +615,10 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	if (int rc = require_device()) return rc;
 	if (!m) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
+	static const bool trace = getenv("MGODPL_TRACE_E2E") != nullptr;  // dev aid: where a host-buffer call spends its time
+	auto now = [] { return std::chrono::steady_clock::now(); };
+	const auto t_begin = now();
+	static thread_local cudaEvent_t tev[2][4] = {};
 	Lease ws(scene->pool);
 	Carver c;
 	// Large batches are cut into chunks that alternate between two side streams, so chunk k+1's H2D copy and chunk
@@ -644,23 +649,33 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		if (lo >= hi) break;
 		const size_t mc = hi - lo, w_lo = lo / 32, w_n = (mc + 31) / 32;
 		cudaStream_t s = n_chunks > 1 ? ws->side[ci & 1] : stream;
+		if (trace && ci < 2) {
+			for (int k = 0; k < 4; ++k)
+				if (!tev[ci][k]) CU(cudaEventCreate(&tev[ci][k]));
+			CU(cudaEventRecord(tev[ci][0], s));
+		}
 		CU(cudaMemcpyAsync(D + o_a + lo * stride * 8, a + lo * stride, mc * stride * 8, cudaMemcpyHostToDevice, s));
 		CU(cudaMemcpyAsync(D + o_b + lo * stride * 8, b + lo * stride, mc * stride * 8, cudaMemcpyHostToDevice, s));
+		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][1], s));
 		CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a) + lo * stride, (const double *) (D + o_b) + lo * stride, mc,
 								stride, js, max_step, nullptr, (uint32_t *) (D + o_hit) + w_lo, toi ? (double *) (D + o_toi) + lo : nullptr,
 								(uint32_t *) (D + o_steps) + lo, (uint32_t *) (D + o_unc) + w_lo, (unsigned *) (D + o_first) + lo,
 								D + o_slerp + lo * 16, D + ((ci & 1) ? o_q2 : o_q), qb, motion_survivors(mc), s));
+		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][2], s));
 		CU(cudaMemcpyAsync(H + o_hit + w_lo * 4, D + o_hit + w_lo * 4, w_n * 4, cudaMemcpyDeviceToHost, s));
 		CU(cudaMemcpyAsync(H + o_unc + w_lo * 4, D + o_unc + w_lo * 4, w_n * 4, cudaMemcpyDeviceToHost, s));
 		CU(cudaMemcpyAsync(H + o_steps + lo * 4, D + o_steps + lo * 4, mc * 4, cudaMemcpyDeviceToHost, s));
 		if (toi) CU(cudaMemcpyAsync(H + o_toi + lo * 8, D + o_toi + lo * 8, mc * 8, cudaMemcpyDeviceToHost, s));
+		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][3], s));
 	}
 	if (n_chunks > 1)
 		for (int s = 0; s < 2; ++s) {
 			CU(cudaEventRecord(ws->ev_done[s], ws->side[s]));
 			CU(cudaStreamWaitEvent(stream, ws->ev_done[s], 0));
 		}
+	const auto t_enqueued = now();
 	CU(cudaStreamSynchronize(stream));
+	const auto t_synced = now();
 	// Step-count fix-up: the device libm may differ from the host's by an ulp, which only matters when distance /
 	// max_step sits on an integer boundary.  Re-derive those on the host and re-run if any count disagrees.
 	uint32_t *h_unc = (uint32_t *) (H + o_unc), *h_steps = (uint32_t *) (H + o_steps), *h_ovr = (uint32_t *) (H + o_ovr);
@@ -689,9 +704,24 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		CU(cudaMemcpyAsync(H + out_lo, D + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, stream));
 		CU(cudaStreamSynchronize(stream));
 	}
+	const auto t_fixed = now();
 	memcpy(hit_bits, H + o_hit, words * 4);
 	if (toi) memcpy(toi, H + o_toi, m * 8);
 	if (n_steps_out) memcpy(n_steps_out, h_steps, m * 4);
+	if (trace) {
+		auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+		fprintf(stderr, "[mgodpl] check_motions m=%zu: enqueue %.0f us, wait %.0f us, fix-up %.0f us (%zu re-derived), copy-out %.0f us\n", m,
+				us(t_begin, t_enqueued), us(t_enqueued, t_synced), us(t_synced, t_fixed), n_fix, us(t_fixed, now()));
+		for (size_t ci = 0; ci < n_chunks && ci < 2; ++ci) {
+			float h2d = 0, ker = 0, d2h = 0, off = 0;
+			cudaEventElapsedTime(&h2d, tev[ci][0], tev[ci][1]);
+			cudaEventElapsedTime(&ker, tev[ci][1], tev[ci][2]);
+			cudaEventElapsedTime(&d2h, tev[ci][2], tev[ci][3]);
+			cudaEventElapsedTime(&off, tev[0][0], tev[ci][0]);
+			fprintf(stderr, "[mgodpl]   chunk %zu: starts +%.0f us, H2D %.0f us, kernels %.0f us, D2H %.0f us\n", ci, off * 1e3, h2d * 1e3,
+					ker * 1e3, d2h * 1e3);
+		}
+	}
 	return MGODPL_OK;
 }
 
