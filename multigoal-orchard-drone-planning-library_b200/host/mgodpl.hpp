@@ -1,6 +1,7 @@
 // Umbrella header of the host-side mirror: the reference's planning-layer API for the collision-query path.
 #pragma once
 #include "mgodpl/collision_detection.hpp"
+#include "mgodpl/local_optimization.hpp"
 #include "mgodpl/math.hpp"
 #include "mgodpl/robot_model.hpp"
 #include "mgodpl/sampling.hpp"

@@ -6,7 +6,9 @@
 //   experiments::createProceduralRobotModel  src/experiment_utils/procedural_robot_models.cpp:86-169
 // Host FK is kept because callers (goal samplers) need it; the batched, GPU-side FK lives behind the C ABI.
 #pragma once
+#include <algorithm>
 #include <cassert>
+#include <cmath>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -59,10 +61,25 @@ struct RobotPath {
 	static RobotPath singleton(RobotState s) { return {{std::move(s)}}; }
 	size_t n_waypoints() const { return states.size(); }
 };
-struct PathPoint {
+struct PathPoint {  // RobotPath.h:116-170
 	size_t segment_i = 0;
 	double segment_t = 0.0;
+	static PathPoint fromScalar(double d, const RobotPath &path) {
+		PathPoint p;
+		p.segment_i = std::min((size_t) std::floor(d), path.states.size() - 2);
+		p.segment_t = d - (double) p.segment_i;
+		return p;
+	}
+	double toScalar() const { return (double) segment_i + segment_t; }
+	PathPoint adjustByScalar(double d, const RobotPath &path) const { return fromScalar(toScalar() + d, path); }
+	bool operator<(const PathPoint &o) const { return toScalar() < o.toScalar(); }
+	bool operator>(const PathPoint &o) const { return toScalar() > o.toScalar(); }
 };
+/// RobotPath.cpp:13-23.
+inline RobotState interpolate(const PathPoint &path_point, const RobotPath &robot_path) {
+	assert(path_point.segment_i + 1 < robot_path.states.size() && "Segment index is out of bounds");
+	return interpolate(robot_path.states[path_point.segment_i], robot_path.states[path_point.segment_i + 1], path_point.segment_t);
+}
 
 namespace gpu {
 /// Owner of a mgodpl_robot handle; built lazily from a RobotModel and shared by its copies.

@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <limits>
 #include <numeric>
+#include <functional>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -631,6 +632,10 @@ struct Rng {  // std::mt19937 façade; distribution objects are built per call e
 		std::normal_distribution<double> d(0.0, 1.0);
 		return d(gen);
 	}
+	int uniform_integer(int lo, int hi) {  // RandomNumberGenerator.h:48-52
+		std::uniform_int_distribution<int> d(lo, hi);
+		return d(gen);
+	}
 };
 
 /// state_tools.cpp:44-67 — one joint value per *joint* (fixed joints included).
@@ -683,6 +688,97 @@ inline State from_end_effector_and_vector(const Robot &robot, const V3 &ee_point
 	V3 ee = fk[robot.find_link("end_effector")].t;
 	s.base.t = s.base.t + ee_point - ee;
 	return s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Path points and local optimisation (shortcutting): src/planning/RobotPath.h:116-170, RobotPath.cpp:13-23,
+// local_optimization.cpp:23-174, and the 100-iteration loop of tsp_over_prm.cpp:594-612.
+// ---------------------------------------------------------------------------------------------------------
+using Path = std::vector<State>;
+using MotionFn = std::function<bool(const State &, const State &)>;
+
+struct PathPoint {  // RobotPath.h:116-170
+	size_t segment_i = 0;
+	double segment_t = 0.0;
+	double to_scalar() const { return (double) segment_i + segment_t; }
+	static PathPoint from_scalar(double d, const Path &path) {
+		PathPoint p;
+		p.segment_i = (size_t) std::floor(d);
+		p.segment_i = std::min(p.segment_i, path.size() - 2);
+		p.segment_t = d - (double) p.segment_i;
+		return p;
+	}
+	PathPoint adjust_by_scalar(double d, const Path &path) const { return from_scalar(to_scalar() + d, path); }
+};
+/// RobotPath.cpp:13-23.
+inline State interpolate(const PathPoint &pt, const Path &path) {
+	return interpolate(path[pt.segment_i], path[pt.segment_i + 1], pt.segment_t);
+}
+/// local_optimization.cpp:23-45.
+inline bool try_shortcut_by_deleting_waypoint(Path &path, size_t waypoint, const MotionFn &motion_collides) {
+	if (motion_collides(path[waypoint - 1], path[waypoint + 1])) return false;
+	path.erase(path.begin() + (long) waypoint);
+	return true;
+}
+/// local_optimization.cpp:47-76 — note the two motions checked are (current → pulled) and (pulled → next).
+inline bool try_midpoint_pull(Path &path, size_t waypoint, double pull_factor, const MotionFn &motion_collides) {
+	State midpoint = interpolate(path[waypoint - 1], path[waypoint + 1], 0.5);
+	State pulled = interpolate(path[waypoint], midpoint, pull_factor);
+	if (motion_collides(path[waypoint], pulled) || motion_collides(pulled, path[waypoint + 1])) return false;
+	path[waypoint] = pulled;
+	return true;
+}
+/// local_optimization.cpp:78-111.
+inline bool try_shortcut_between_path_points(Path &path, const PathPoint &start, const PathPoint &end,
+											 const MotionFn &motion_collides) {
+	State st1 = interpolate(start, path), st2 = interpolate(end, path);
+	if (motion_collides(st1, st2)) return false;
+	Path out(path.begin(), path.begin() + (long) start.segment_i);
+	out.push_back(st1);
+	out.push_back(st2);
+	out.insert(out.end(), path.begin() + (long) end.segment_i + 1, path.end());
+	path = std::move(out);
+	return true;
+}
+/// local_optimization.cpp:113-117.
+inline PathPoint generate_random_path_point(const Path &path, Rng &rng) {
+	PathPoint p;
+	p.segment_i = (size_t) rng.uniform_integer(0, (int) (path.size() - 2));
+	p.segment_t = rng.uniform_real(0.0, 1.0);
+	return p;
+}
+/// local_optimization.cpp:119-136.
+inline bool try_deleting_every_waypoint(Path &path, const MotionFn &motion_collides) {
+	size_t cursor = 1;
+	bool shortened = false;
+	while (cursor + 1 < path.size()) {
+		if (try_shortcut_by_deleting_waypoint(path, cursor, motion_collides)) shortened = true;
+		else cursor++;
+	}
+	return shortened;
+}
+/// local_optimization.cpp:138-153.
+inline bool try_shortcutting_randomly_locally(Path &path, Rng &rng, const MotionFn &motion_collides) {
+	PathPoint middle = generate_random_path_point(path, rng);
+	double radius = rng.uniform_real(0.5, 2.0);
+	PathPoint start = middle.adjust_by_scalar(-radius, path), end = middle.adjust_by_scalar(radius, path);
+	return try_shortcut_between_path_points(path, start, end, motion_collides);
+}
+/// local_optimization.cpp:155-173.
+inline bool try_shortcutting_randomly_globally(Path &path, const MotionFn &motion_collides, Rng &rng) {
+	PathPoint start = generate_random_path_point(path, rng), end = generate_random_path_point(path, rng);
+	if (start.to_scalar() > end.to_scalar()) std::swap(start, end);
+	return try_shortcut_between_path_points(path, start, end, motion_collides);
+}
+/// tsp_over_prm.cpp:594-612 — `iterations` attempts, stopping early once the path is trivial; returns the number
+/// of attempts that shortened the path.
+inline size_t optimize_path_segment(Path &path, const MotionFn &motion_collides, Rng &rng, size_t iterations = 100) {
+	size_t n_success = 0;
+	for (size_t i = 0; i < iterations; ++i) {
+		if (path.size() <= 2) break;
+		if (try_shortcutting_randomly_globally(path, motion_collides, rng)) ++n_success;
+	}
+	return n_success;
 }
 
 }  // namespace orc

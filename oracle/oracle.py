@@ -55,6 +55,7 @@ def lib():
         L.orc_angular_distance.restype = C.c_double
         L.orc_motion_steps.restype = C.c_uint64
         L.orc_check_path.restype = C.c_long
+        L.orc_shortcut_path.restype = C.c_long
         _lib = L
     return _lib
 
@@ -71,11 +72,13 @@ def ref():
         R.ref_scene_create.restype = C.c_void_p
         R.ref_distance.restype = C.c_double
         R.ref_check_path.restype = C.c_long
+        R.ref_shortcut_path.restype = C.c_long
         _ref = R
     return _ref
 
 
 HORIZONTAL, VERTICAL = 0, 1
+SHORTCUT_GLOBALLY, DELETE_EVERY_WAYPOINT, SHORTCUT_LOCALLY, MIDPOINT_PULL = 0, 1, 2, 3
 REVOLUTE, FIXED = 0, 1
 
 
@@ -250,6 +253,17 @@ class Scene:
         return lib().orc_check_path(self.h, robot.h, _d(states), C.c_size_t(w), C.c_size_t(stride), stride - 7,
                                     C.c_double(max_step))
 
+    def shortcut_path(self, robot: Robot, states, seed=42, iterations=100, mode=SHORTCUT_GLOBALLY, pull=0.5, max_step=0.1):
+        """local_optimization.cpp driven as tsp_over_prm.cpp:594-612 does; returns dict(path, n_success, n_checks)."""
+        states = _arr(states)
+        w, stride = states.shape
+        out = np.zeros((w + 2 * iterations + 2, stride))
+        out_w, checks = C.c_size_t(0), C.c_size_t(0)
+        ok = lib().orc_shortcut_path(self.h, robot.h, _d(states), C.c_size_t(w), C.c_size_t(stride), stride - 7, C.c_uint(seed),
+                                     C.c_size_t(iterations), mode, C.c_double(pull), C.c_double(max_step), _d(out),
+                                     C.c_size_t(len(out)), C.byref(out_w), C.byref(checks))
+        return dict(path=out[:out_w.value].copy(), n_success=int(ok), n_checks=int(checks.value))
+
     def goal_sample_counts(self, robot: Robot, targets, samples: int, seed=42, threads=1, want_hits=False):
         targets = _arr(targets).reshape(-1, 3)
         f = len(targets)
@@ -367,6 +381,16 @@ class RefScene:
         states = _arr(states)
         w, stride = states.shape
         return ref().ref_check_path(self.h, robot.h, _d(states), C.c_size_t(w), C.c_size_t(stride), stride - 7)
+
+    def shortcut_path(self, robot: RefRobot, states, seed=42, iterations=100, mode=SHORTCUT_GLOBALLY, pull=0.5):
+        states = _arr(states)
+        w, stride = states.shape
+        out = np.zeros((w + 2 * iterations + 2, stride))
+        out_w, checks = C.c_size_t(0), C.c_size_t(0)
+        ok = ref().ref_shortcut_path(self.h, robot.h, _d(states), C.c_size_t(w), C.c_size_t(stride), stride - 7, C.c_uint(seed),
+                                     C.c_size_t(iterations), mode, C.c_double(pull), _d(out), C.c_size_t(len(out)),
+                                     C.byref(out_w), C.byref(checks))
+        return dict(path=out[:out_w.value].copy(), n_success=int(ok), n_checks=int(checks.value))
 
     def __del__(self):
         try:

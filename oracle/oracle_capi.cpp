@@ -294,4 +294,35 @@ void orc_from_ee_and_vector(void *robot, const double *point3, const double *vec
 	store_state(from_end_effector_and_vector(*(Robot *) robot, {point3[0], point3[1], point3[2]}, {vec3[0], vec3[1], vec3[2]}), out8);
 }
 
+// ---- local optimisation (shortcutting) ---------------------------------------------------------------------
+/// Runs one of the reference's path optimisers on a path of w states with one std::mt19937(seed) stream and the
+/// oracle's check_motion_collides as the motion check.  mode 0: `iterations` x tryShortcuttingRandomlyGlobally
+/// (tsp_over_prm.cpp:594-612); 1: tryDeletingEveryWaypoint; 2: `iterations` x tryShortcuttingRandomlyLocally;
+/// 3: one tryMidpointPull(pull) sweep over the interior waypoints.  Writes the resulting path (out_cap rows of
+/// `stride`), its length to *out_w, the number of motion checks to *n_checks; returns the number of successes.
+long orc_shortcut_path(void *scene, void *robot, const double *states, size_t w, size_t stride, int js, unsigned seed,
+					   size_t iterations, int mode, double pull, double max_step, double *out_states, size_t out_cap,
+					   size_t *out_w, size_t *n_checks) {
+	Path path;
+	for (size_t i = 0; i < w; ++i) path.push_back(load_state(states + i * stride, js));
+	Rng rng(seed);
+	size_t checks = 0;
+	MotionFn motion = [&](const State &a, const State &b) {
+		++checks;
+		return check_motion_collides(*(Robot *) robot, *(Scene *) scene, a, b, max_step).hit;
+	};
+	long ok = 0;
+	if (mode == 0) ok = (long) optimize_path_segment(path, motion, rng, iterations);
+	else if (mode == 1) ok = try_deleting_every_waypoint(path, motion);
+	else if (mode == 2) {
+		for (size_t i = 0; i < iterations && path.size() > 2; ++i) ok += try_shortcutting_randomly_locally(path, rng, motion);
+	} else {
+		for (size_t i = 1; i + 1 < path.size(); ++i) ok += try_midpoint_pull(path, i, pull, motion);
+	}
+	for (size_t i = 0; i < path.size() && i < out_cap; ++i) store_state(path[i], out_states + i * stride);
+	*out_w = path.size();
+	if (n_checks) *n_checks = checks;
+	return ok;
+}
+
 }  // extern "C"

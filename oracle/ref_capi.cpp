@@ -21,6 +21,7 @@
 #include "planning/distance.h"
 #include "planning/fcl_utils.h"
 #include "planning/goal_sampling.h"
+#include "planning/local_optimization.h"
 #include "planning/state_tools.h"
 
 #include <fcl/narrowphase/collision_object.h>
@@ -30,6 +31,8 @@
 // procedural, so an empty visual mesh changes nothing on this path.
 namespace mgodpl {
 Mesh from_dae(const std::string &) { return {}; }
+// local_optimization.cpp:117-136 defines this overload; the header only declares a (robot, path, obstacle) one.
+bool tryDeletingEveryWaypoint(RobotPath &path, const std::function<bool(const RobotState &, const RobotState &)> &check_motion_collides);
 }
 
 using namespace mgodpl;
@@ -132,6 +135,38 @@ void ref_gen_goal_states(void *robot, unsigned seed, const double *target3, doub
 void ref_from_ee_and_vector(void *robot, const double *point3, const double *vec3, double *out8) {
 	store_state(fromEndEffectorAndVector(*(robot_model::RobotModel *) robot, math::Vec3d(point3[0], point3[1], point3[2]),
 										 math::Vec3d(vec3[0], vec3[1], vec3[2])), out8);
+}
+
+/// Same contract as orc_shortcut_path, over the reference's own local_optimization.cpp / RobotPath.cpp.
+long ref_shortcut_path(void *scene, void *robot, const double *states, size_t w, size_t stride, int js, unsigned seed,
+					   size_t iterations, int mode, double pull, double *out_states, size_t out_cap, size_t *out_w,
+					   size_t *n_checks) {
+	auto &rb = *(robot_model::RobotModel *) robot;
+	auto &sc = ((RefScene *) scene)->object;
+	RobotPath path;
+	for (size_t i = 0; i < w; ++i) path.append(load_state(states + i * stride, js));
+	random_numbers::RandomNumberGenerator rng(seed);
+	size_t checks = 0;
+	std::function<bool(const RobotState &, const RobotState &)> motion = [&](const RobotState &a, const RobotState &b) {
+		++checks;
+		return check_motion_collides(rb, sc, a, b);
+	};
+	long ok = 0;
+	if (mode == 0) {
+		for (size_t i = 0; i < iterations; ++i) {  // tsp_over_prm.cpp:594-612
+			if (path.states.size() <= 2) break;
+			ok += tryShortcuttingRandomlyGlobally(path, motion, rng);
+		}
+	} else if (mode == 1) ok = tryDeletingEveryWaypoint(path, motion);
+	else if (mode == 2) {
+		for (size_t i = 0; i < iterations && path.states.size() > 2; ++i) ok += tryShortcuttingRandomlyLocally(path, rng, motion);
+	} else {
+		for (size_t i = 1; i + 1 < path.states.size(); ++i) ok += tryMidpointPull(path, i, pull, motion);
+	}
+	for (size_t i = 0; i < path.states.size() && i < out_cap; ++i) store_state(path.states[i], out_states + i * stride);
+	*out_w = path.states.size();
+	if (n_checks) *n_checks = checks;
+	return ok;
 }
 
 }  // extern "C"

@@ -239,6 +239,84 @@ int main() {
 		std::printf("PRM: %zu edges validated on the GPU, %zu expected, %zu matched\n", edges.size(), expected, found);
 		CHECK(edges.size() == expected && found == expected);
 	}
+	// -- path shortcutting: batched drivers == the reference's sequential loops (oracle as motion check) ------------------
+	{
+		auto same_state = [](const RobotState &s, const orc::State &o) {
+			return s.base_tf.translation.x() == o.base.t.x && s.base_tf.translation.y() == o.base.t.y && s.base_tf.translation.z() == o.base.t.z &&
+				   s.base_tf.orientation.x == o.base.q.x && s.base_tf.orientation.y == o.base.q.y && s.base_tf.orientation.z == o.base.q.z &&
+				   s.base_tf.orientation.w == o.base.q.w && s.joint_values == o.joints;
+		};
+		auto same_path = [&](const RobotPath &p, const orc::Path &o) {
+			if (p.states.size() != o.size()) return false;
+			for (size_t i = 0; i < o.size(); ++i)
+				if (!same_state(p.states[i], o[i])) return false;
+			return true;
+		};
+		const orc::MotionFn omotion = [&](const orc::State &a, const orc::State &b) { return orc::check_motion_collides(orobot, oscene, a, b).hit; };
+		const CollisionEnvironment env{robot, scene};
+		const CollisionFunctions fns = collision_functions_in_environment(env);
+		size_t total_success = 0, total_batches = 0, total_attempts = 0;
+		for (unsigned seed = 0; seed < 6; ++seed) {
+			random_numbers::RandomNumberGenerator make(300 + seed);
+			RobotPath path0;
+			for (int i = 0; i < 14; ++i) path0.append(generateUniformRandomState(robot, make, 1.8, 2.6));
+			orc::Path opath0;
+			for (auto &st: path0.states) opath0.push_back(to_orc(st));
+			// PathPoint arithmetic and interpolation, bit for bit
+			for (double d: {0.0, 0.25, 3.75, 12.999, 13.5, 40.0}) {
+				PathPoint p = PathPoint::fromScalar(d, path0);
+				orc::PathPoint q = orc::PathPoint::from_scalar(d, opath0);
+				CHECK(p.segment_i == q.segment_i && p.segment_t == q.segment_t && p.toScalar() == q.to_scalar());
+				if (p.segment_t <= 1.0) CHECK(same_state(interpolate(p, path0), orc::interpolate(q, opath0)));
+			}
+			{  // globally: tsp_over_prm.cpp:594-612
+				RobotPath path = path0;
+				orc::Path opath = opath0;
+				random_numbers::RandomNumberGenerator rng(seed + 11);
+				orc::Rng orng(seed + 11);
+				const size_t want = orc::optimize_path_segment(opath, omotion, orng, 60);
+				const ShortcutStats st = shortcut_path_globally(robot, scene, path, rng, 60);
+				CHECK(st.successes == want && same_path(path, opath));
+				CHECK(rng.uniformReal(0, 1) == orng.uniform_real(0, 1));  // generator left where the sequential loop leaves it
+				CHECK(st.batches <= st.successes + 1 && st.attempts <= 60);
+				total_success += st.successes, total_batches += st.batches, total_attempts += st.attempts;
+				// the one-attempt-at-a-time API through the planner-facing closure gives the same path
+				RobotPath seq = path0;
+				random_numbers::RandomNumberGenerator rng2(seed + 11);
+				for (int i = 0; i < 60 && seq.states.size() > 2; ++i) tryShortcuttingRandomlyGlobally(seq, fns.motion_collides, rng2);
+				CHECK(seq.states == path.states);
+			}
+			{  // locally
+				RobotPath path = path0;
+				orc::Path opath = opath0;
+				random_numbers::RandomNumberGenerator rng(seed + 23);
+				orc::Rng orng(seed + 23);
+				size_t want = 0;
+				for (int i = 0; i < 40 && opath.size() > 2; ++i) want += orc::try_shortcutting_randomly_locally(opath, orng, omotion);
+				const ShortcutStats st = shortcut_path_locally(robot, scene, path, rng, 40);
+				CHECK(st.successes == want && same_path(path, opath));
+				CHECK(rng.uniformReal(0, 1) == orng.uniform_real(0, 1));
+			}
+			{  // deleting waypoints: closure overload and batched scene overload
+				RobotPath a = path0, b = path0;
+				orc::Path opath = opath0;
+				const bool want = orc::try_deleting_every_waypoint(opath, omotion);
+				ShortcutStats st;
+				CHECK(tryDeletingEveryWaypoint(a, fns.motion_collides) == want && same_path(a, opath));
+				CHECK(tryDeletingEveryWaypoint(robot, b, scene, &st) == want && same_path(b, opath));
+				CHECK(st.batches <= st.successes + 1);
+			}
+			{  // midpoint pull sweep
+				RobotPath path = path0;
+				orc::Path opath = opath0;
+				for (size_t i = 1; i + 1 < opath.size(); ++i)
+					CHECK(tryMidpointPull(path, i, 0.5, fns.motion_collides) == orc::try_midpoint_pull(opath, i, 0.5, omotion));
+				CHECK(same_path(path, opath));
+			}
+		}
+		std::printf("shortcutting: %zu attempts, %zu successes, %zu GPU batches\n", total_attempts, total_success, total_batches);
+		CHECK(total_success > 0 && total_batches < total_attempts);
+	}
 	// -- error vocabulary -------------------------------------------------------------------------------------------------------
 	{
 		robot_model::RobotModel bad;

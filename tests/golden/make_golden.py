@@ -67,7 +67,17 @@ out["scene"] = dict(tree=dict(seed=5, trunk_triangles=3000, leaf_triangles=0, n_
                     motion_hits="".join("1" if h else "0" for h in mh), motion_toi=hx(np.nan_to_num(mt, nan=-1.0)),
                     path=hx(path), path_shape=list(path.shape), path_first_colliding_segment=int(path_first),
                     mesh_checksum=float(mesh.vertices.sum()).hex(), n_triangles=int(mesh.n_triangles))
+# Path shortcutting (local_optimization.cpp:23-174 driven as tsp_over_prm.cpp:594-612 does), same scene and robot.
+short = []
+for case, (first, seed, iters, mode) in enumerate([(200, 5, 30, o.SHORTCUT_GLOBALLY), (214, 6, 30, o.SHORTCUT_GLOBALLY),
+                                                  (228, 7, 0, o.DELETE_EVERY_WAYPOINT), (242, 8, 25, o.SHORTCUT_LOCALLY),
+                                                  (256, 9, 0, o.MIDPOINT_PULL)]):
+    r = rs.shortcut_path(rr, st[first:first + 14], seed=seed, iterations=iters, mode=mode)
+    short.append(dict(first_state=first, n_waypoints=14, seed=seed, iterations=iters, mode=mode, pull=0.5,
+                      n_success=r["n_success"], n_checks=r["n_checks"], path=hx(r["path"]), path_shape=list(r["path"].shape)))
+out["shortcutting"] = short
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.json"), "w") as f:
     json.dump(out, f, indent=1)
 print("wrote reference_vectors.json:", len(out["robots"]), "robots;", int(hits.sum()), "/ 400 states collide;",
-      int(mh.sum()), "/ 100 motions collide; path first =", path_first)
+      int(mh.sum()), "/ 100 motions collide; path first =", path_first, "; shortcut successes",
+      [c["n_success"] for c in short], "waypoints left", [c["path_shape"][0] for c in short])

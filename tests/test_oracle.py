@@ -179,6 +179,22 @@ def test_golden_scene_checks(oracle, golden, mg):
     assert s.check_path(r, path) == g["path_first_colliding_segment"] == 2
 
 
+def test_golden_shortcutting(oracle, golden, mg):
+    """local_optimization.cpp (+ RobotPath.cpp, the mt19937 draws of generateRandomPathPoint) as run from the reference's sources."""
+    g = golden["scene"]
+    mesh = mg.scenes.make_tree(**g["tree"]).trunk_mesh
+    r = oracle.Robot(g["robot"][0], tuple(g["robot"][1]))
+    s = oracle.Scene(mesh.vertices, mesh.triangles)
+    st = oracle.gen_uniform_states(r, g["n_states"], seed=g["states_seed"], h_range=g["h_range"], v_range=g["v_range"])
+    assert len(golden["shortcutting"]) == 5
+    for c in golden["shortcutting"]:
+        got = s.shortcut_path(r, st[c["first_state"]:c["first_state"] + c["n_waypoints"]], seed=c["seed"], iterations=c["iterations"],
+                              mode=c["mode"], pull=c["pull"])
+        assert got["n_success"] == c["n_success"] and got["n_checks"] == c["n_checks"]
+        assert np.array_equal(got["path"], unhex(c["path"], c["path_shape"]))
+    assert sum(c["n_success"] for c in golden["shortcutting"]) > 0
+
+
 # ---- live cross-check against the reference's own sources (present in the build container and, prebuilt, on the box) --
 def test_oracle_matches_reference_sources_live(oracle, mg):
     if not oracle.have_ref():
@@ -204,6 +220,16 @@ def test_oracle_matches_reference_sources_live(oracle, mg):
     rh, rt = rs.check_motions(rr, st[:300], st[300:])
     assert np.array_equal(res["hit"], rh)
     assert np.array_equal(np.nan_to_num(res["toi"], nan=-1), np.nan_to_num(rt, nan=-1))
+    # shortcutting: same final path, successes and number of motion checks (runs that reach a zero-length motion are the
+    # documented NaN-pose deviation, SURVEY Q8 — 30 attempts on 14 waypoints stay clear of it)
+    for seed in range(4):
+        path = st[seed * 14:(seed + 1) * 14]
+        for mode, iters in ((oracle.SHORTCUT_GLOBALLY, 30), (oracle.DELETE_EVERY_WAYPOINT, 0), (oracle.SHORTCUT_LOCALLY, 30),
+                            (oracle.MIDPOINT_PULL, 0)):
+            a = s.shortcut_path(r, path, seed=seed, iterations=iters, mode=mode)
+            b = rs.shortcut_path(rr, path, seed=seed, iterations=iters, mode=mode)
+            assert a["n_success"] == b["n_success"] and a["n_checks"] == b["n_checks"], (seed, mode)
+            assert np.array_equal(a["path"], b["path"]), (seed, mode)
 
 
 # ---- properties inherited from the reference's legacy tests ------------------------------------------------------------
