@@ -182,6 +182,23 @@ int mgodpl_knn(const double *states, size_t n, size_t stride, int32_t n_joint_va
 int mgodpl_knn_device(const double *d_states, size_t n, size_t stride, int32_t n_joint_values, int32_t k, int32_t causal,
 					  int32_t *d_idx, double *d_dist, void *stream);
 
+/* ---- shortest paths on the roadmap: runDijkstra (src/planning/tsp_over_prm.cpp:80-97, boost::dijkstra_shortest_paths on
+ *      the undirected PRMGraph of tsp_over_prm.h:25-26) as calculate_goal_to_goal_paths calls it once per goal sample and
+ *      once from the start node (tsp_over_prm.cpp:497-517) — all sources in one call.  edges: n_edges x (u, v), undirected;
+ *      weights: fp64, finite, >= 0 (equal_weights_distance of the endpoints, tsp_over_prm.cpp:56-58).  dist: n_sources x
+ *      n_vertices, source-major (distance_lookup[i][v], tsp_over_prm.h:90-97) — bit-identical to Dijkstra's labels, DBL_MAX
+ *      where unreachable (boost's default infinity); pred (optional): same shape, the vertex before v on a shortest path,
+ *      v itself for the source and for unreachable vertices.  Where several neighbours tie exactly, the one nearer the
+ *      source, then the lower index, is reported (boost reports whichever its heap relaxed first).  sweeps_out (optional):
+ *      label-correcting sweeps enqueued.  The _device variant takes the graph in CSR form (row_offsets: n_vertices + 1,
+ *      neighbours / weights: both directions of every edge) in device memory and synchronises the stream before returning. */
+int mgodpl_roadmap_shortest_paths(uint32_t n_vertices, const uint32_t *edges, const double *weights, size_t n_edges,
+								  const uint32_t *sources, size_t n_sources, double *dist, uint32_t *pred, uint32_t *sweeps_out,
+								  void *stream);
+int mgodpl_roadmap_shortest_paths_device(const uint32_t *d_row_offsets, const uint32_t *d_neighbours, const double *d_weights,
+										 uint32_t n_vertices, const uint32_t *d_sources, size_t n_sources, double *d_dist,
+										 uint32_t *d_pred, uint32_t *sweeps_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

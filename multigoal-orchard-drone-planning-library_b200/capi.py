@@ -28,6 +28,7 @@ EXPORTS = [
     "mgodpl_robot_destroy", "mgodpl_robot_n_variables", "mgodpl_forward_kinematics", "mgodpl_check_boxes",
     "mgodpl_check_states", "mgodpl_check_states_device", "mgodpl_check_motions", "mgodpl_check_motions_device",
     "mgodpl_check_path", "mgodpl_sample_goals", "mgodpl_sample_goals_device", "mgodpl_knn", "mgodpl_knn_device",
+    "mgodpl_roadmap_shortest_paths", "mgodpl_roadmap_shortest_paths_device",
 ]
 
 
@@ -287,6 +288,34 @@ def knn(states, k: int, causal: bool = False, want_dist: bool = True, stream=Non
 def knn_device(d_states, n: int, stride: int, n_joint_values: int, k: int, d_idx, d_dist=None, causal: bool = False, stream=None):
     _check(lib().mgodpl_knn_device(_dptr(d_states), C.c_size_t(n), C.c_size_t(stride), n_joint_values, k, int(causal),
                                    _dptr(d_idx), _dptr(d_dist), _stream(stream)))
+
+
+def roadmap_shortest_paths(n_vertices: int, edges, weights, sources, want_pred: bool = True, stream=None):
+    """Shortest paths from every source over an undirected roadmap (runDijkstra per source, tsp_over_prm.cpp:80-97).
+
+    Returns dict(dist[n_sources, n_vertices], pred[n_sources, n_vertices] | None, sweeps)."""
+    edges = np.ascontiguousarray(edges, dtype=np.uint32).reshape(-1, 2)
+    weights = _f64(weights).reshape(-1)
+    sources = np.ascontiguousarray(sources, dtype=np.uint32).reshape(-1)
+    if len(weights) != len(edges):
+        raise MgodplError(-1, "one weight per edge")
+    dist = np.zeros((len(sources), n_vertices))
+    pred = np.zeros((len(sources), n_vertices), np.uint32) if want_pred else None
+    sweeps = C.c_uint32(0)
+    _check(lib().mgodpl_roadmap_shortest_paths(C.c_uint32(n_vertices), _p(edges, C.c_uint32), _p(weights), C.c_size_t(len(edges)),
+                                               _p(sources, C.c_uint32), C.c_size_t(len(sources)), _p(dist), _p(pred, C.c_uint32),
+                                               C.byref(sweeps), _stream(stream)))
+    return dict(dist=dist, pred=pred, sweeps=int(sweeps.value))
+
+
+def roadmap_shortest_paths_device(d_row_offsets, d_neighbours, d_weights, n_vertices: int, d_sources, n_sources: int, d_dist,
+                                  d_pred=None, stream=None) -> int:
+    """CSR graph and outputs in device memory; synchronises the stream; returns the number of sweeps enqueued."""
+    sweeps = C.c_uint32(0)
+    _check(lib().mgodpl_roadmap_shortest_paths_device(_dptr(d_row_offsets), _dptr(d_neighbours), _dptr(d_weights),
+                                                      C.c_uint32(n_vertices), _dptr(d_sources), C.c_size_t(n_sources),
+                                                      _dptr(d_dist), _dptr(d_pred), C.byref(sweeps), _stream(stream)))
+    return int(sweeps.value)
 
 
 # ---- device-pointer variants (torch tensors or raw pointers; asynchronous on `stream`) -------------------------------

@@ -833,4 +833,91 @@ int mgodpl_knn(const double *states, size_t n, size_t stride, int32_t js, int32_
 	return MGODPL_OK;
 }
 
+// ---- roadmap shortest paths (runDijkstra per goal sample, tsp_over_prm.cpp:80-97 and :497-517, batched) ---------------------
+namespace {
+unsigned *pinned_flag() {
+	static thread_local unsigned *flag = nullptr;
+	if (!flag && cudaMallocHost((void **) &flag, 64) != cudaSuccess) flag = nullptr, cudaGetLastError();
+	return flag;
+}
+}  // namespace
+
+int mgodpl_roadmap_shortest_paths_device(const uint32_t *d_row_offsets, const uint32_t *d_neighbours, const double *d_weights,
+										 uint32_t n_vertices, const uint32_t *d_sources, size_t n_sources, double *d_dist, uint32_t *d_pred,
+										 uint32_t *sweeps_out, void *stream_) {
+	if (n_vertices && n_sources && (!d_row_offsets || !d_sources || !d_dist)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (int rc = require_device()) return rc;
+	if (sweeps_out) *sweeps_out = 0;
+	if (!n_vertices || !n_sources) return MGODPL_OK;
+	unsigned *flag = pinned_flag();
+	if (!flag) return fail(MGODPL_E_OUT_OF_MEMORY, "pinned host memory");
+	void *scratch = nullptr;
+	cudaError_t e = cudaMalloc(&scratch, roadmap_scratch_bytes(n_vertices, n_sources));
+	if (e == cudaSuccess)
+		e = launch_roadmap_shortest_paths(d_row_offsets, d_neighbours, d_weights, n_vertices, d_sources, n_sources, d_dist, d_pred, scratch, flag,
+										  sweeps_out, (cudaStream_t) stream_);
+	if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) stream_);
+	cudaFree(scratch);
+	if (e != cudaSuccess) return fail_cuda(e, "roadmap_shortest_paths");
+	return MGODPL_OK;
+}
+
+int mgodpl_roadmap_shortest_paths(uint32_t n_vertices, const uint32_t *edges, const double *weights, size_t n_edges,
+								  const uint32_t *sources, size_t n_sources, double *dist, uint32_t *pred, uint32_t *sweeps_out,
+								  void *stream_) {
+	if (n_edges && (!edges || !weights)) return fail(MGODPL_E_INVALID_ARGUMENT, "null edge list");
+	if (n_sources && n_vertices && (!sources || !dist)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (2 * n_edges >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "too many edges");
+	for (size_t e = 0; e < n_edges; ++e) {
+		if (edges[2 * e] >= n_vertices || edges[2 * e + 1] >= n_vertices) return fail(MGODPL_E_INVALID_ARGUMENT, "edge endpoint out of range");
+		// boost::dijkstra_shortest_paths throws negative_edge; NaN weights would never compare
+		if (!(weights[e] >= 0.0) || std::isinf(weights[e])) return fail(MGODPL_E_INVALID_ARGUMENT, "edge weights must be finite and non-negative");
+	}
+	for (size_t s = 0; s < n_sources; ++s)
+		if (sources[s] >= n_vertices) return fail(MGODPL_E_INVALID_ARGUMENT, "source vertex out of range");
+	if (int rc = require_device()) return rc;
+	if (sweeps_out) *sweeps_out = 0;
+	if (!n_vertices || !n_sources) return MGODPL_OK;
+	// CSR with both directions of every undirected edge, neighbours in edge-list order (boost's out-edge order)
+	std::vector<uint32_t> row(n_vertices + 1, 0), col(2 * n_edges);
+	std::vector<double> w(2 * n_edges);
+	for (size_t e = 0; e < n_edges; ++e) ++row[edges[2 * e] + 1], ++row[edges[2 * e + 1] + 1];
+	for (uint32_t v = 0; v < n_vertices; ++v) row[v + 1] += row[v];
+	{
+		std::vector<uint32_t> cursor(row.begin(), row.end() - 1);
+		for (size_t e = 0; e < n_edges; ++e) {
+			const uint32_t a = edges[2 * e], b = edges[2 * e + 1];
+			col[cursor[a]] = b, w[cursor[a]++] = weights[e];
+			col[cursor[b]] = a, w[cursor[b]++] = weights[e];
+		}
+	}
+	cudaStream_t stream = (cudaStream_t) stream_;
+	uint32_t *d_row = nullptr, *d_col = nullptr, *d_src = nullptr, *d_pred = nullptr;
+	double *d_w = nullptr, *d_dist = nullptr;
+	const size_t cells = n_sources * (size_t) n_vertices;
+	cudaError_t e = cudaMalloc((void **) &d_row, row.size() * 4);
+	if (e == cudaSuccess) e = cudaMalloc((void **) &d_col, col.size() * 4 + 4);
+	if (e == cudaSuccess) e = cudaMalloc((void **) &d_w, w.size() * 8 + 8);
+	if (e == cudaSuccess) e = cudaMalloc((void **) &d_src, n_sources * 4);
+	if (e == cudaSuccess) e = cudaMalloc((void **) &d_dist, cells * 8);
+	if (e == cudaSuccess && pred) e = cudaMalloc((void **) &d_pred, cells * 4);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_row, row.data(), row.size() * 4, cudaMemcpyHostToDevice, stream);
+	if (e == cudaSuccess && !col.empty()) e = cudaMemcpyAsync(d_col, col.data(), col.size() * 4, cudaMemcpyHostToDevice, stream);
+	if (e == cudaSuccess && !w.empty()) e = cudaMemcpyAsync(d_w, w.data(), w.size() * 8, cudaMemcpyHostToDevice, stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_src, sources, n_sources * 4, cudaMemcpyHostToDevice, stream);
+	int rc = MGODPL_OK;
+	if (e == cudaSuccess) {
+		rc = mgodpl_roadmap_shortest_paths_device(d_row, d_col, d_w, n_vertices, d_src, n_sources, d_dist, d_pred, sweeps_out, stream_);
+		if (rc == MGODPL_OK) {
+			e = cudaMemcpyAsync(dist, d_dist, cells * 8, cudaMemcpyDeviceToHost, stream);
+			if (e == cudaSuccess && pred) e = cudaMemcpyAsync(pred, d_pred, cells * 4, cudaMemcpyDeviceToHost, stream);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+		}
+	}
+	cudaFree(d_row), cudaFree(d_col), cudaFree(d_w), cudaFree(d_src), cudaFree(d_dist), cudaFree(d_pred);
+	if (rc != MGODPL_OK) return rc;
+	if (e != cudaSuccess) return fail_cuda(e, "roadmap_shortest_paths");
+	return MGODPL_OK;
+}
+
 }  // extern "C"

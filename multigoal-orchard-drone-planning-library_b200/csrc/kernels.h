@@ -1,4 +1,4 @@
-// Host-callable launchers of the device kernels (query_kernels.cu, scene_build.cu).
+// Host-callable launchers of the device kernels (query_kernels.cu, scene_build.cu, knn_kernels.cu, roadmap_kernels.cu).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -34,6 +34,13 @@ cudaError_t launch_forward_kinematics(const RobotDev &rb, const double *d_states
 /// Exact k-NN over equal_weights_distance; causal != 0 restricts node i to neighbours j < i (incremental PRM insertion).
 cudaError_t launch_knn(const double *d_states, size_t n, size_t stride, int js, int k, int causal, int32_t *d_idx, double *d_dist,
 					   cudaStream_t stream);
+
+/// Shortest paths from many sources at once over a CSR roadmap (both directions of every undirected edge present).
+/// d_dist / d_pred: n_sources x n, source-major; d_pred may be null.  Synchronises `stream` (convergence read-backs).
+size_t roadmap_scratch_bytes(unsigned n, size_t n_sources);
+cudaError_t launch_roadmap_shortest_paths(const uint32_t *d_row, const uint32_t *d_col, const double *d_weight, unsigned n,
+										  const uint32_t *d_sources, size_t n_sources, double *d_dist, uint32_t *d_pred, void *scratch,
+										  unsigned *h_flag_pinned, unsigned *sweeps_out, cudaStream_t stream);
 
 /// Result of the device BVH build: device buffers owned by the caller (cudaFree).
 struct BuiltScene {

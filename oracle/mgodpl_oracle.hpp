@@ -23,6 +23,7 @@
 #include <limits>
 #include <numeric>
 #include <functional>
+#include <queue>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -779,6 +780,60 @@ inline size_t optimize_path_segment(Path &path, const MotionFn &motion_collides,
 		if (try_shortcutting_randomly_globally(path, motion_collides, rng)) ++n_success;
 	}
 	return n_success;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Roadmap shortest paths: runDijkstra (src/planning/tsp_over_prm.cpp:80-97) = boost::dijkstra_shortest_paths on
+// the undirected PRMGraph (tsp_over_prm.h:25-26), retrace_path (:111-128).  Boost.Graph is a third-party
+// dependency absent from /root/reference (nixpkgs 24.05 pins boost 1.81): PARITY UNPINNED for this function.
+// Restated from its published algorithm: labels start at numeric_limits<double>::max() ("infinity") with every
+// vertex its own predecessor; the closest unsettled vertex is settled next; an edge (u, v, w) relaxes v when
+// d[u] + w < d[v] (strict), recording u as predecessor.  Distances do not depend on the heap's tie order;
+// predecessors do when two relaxations tie exactly.
+// ---------------------------------------------------------------------------------------------------------
+struct Roadmap {
+	struct Arc {
+		uint32_t to;
+		double weight;
+	};
+	std::vector<std::vector<Arc>> out;  // both directions of every undirected edge, in insertion order
+	explicit Roadmap(size_t n) : out(n) {}
+	void add_edge(uint32_t a, uint32_t b, double w) {
+		out[a].push_back({b, w});
+		out[b].push_back({a, w});
+	}
+};
+inline void run_dijkstra(const Roadmap &g, uint32_t source, std::vector<double> &dist, std::vector<uint32_t> &pred) {
+	const double inf = std::numeric_limits<double>::max();
+	dist.assign(g.out.size(), inf);
+	pred.resize(g.out.size());
+	std::iota(pred.begin(), pred.end(), 0u);
+	dist[source] = 0.0;
+	using Entry = std::pair<double, uint32_t>;
+	std::priority_queue<Entry, std::vector<Entry>, std::greater<Entry>> heap;
+	heap.push({0.0, source});
+	std::vector<char> settled(g.out.size(), 0);
+	while (!heap.empty()) {
+		auto [d, u] = heap.top();
+		heap.pop();
+		if (settled[u]) continue;
+		settled[u] = 1;
+		for (const auto &arc: g.out[u]) {
+			const double cand = d + arc.weight;
+			if (cand < dist[arc.to]) {
+				dist[arc.to] = cand;
+				pred[arc.to] = u;
+				heap.push({cand, arc.to});
+			}
+		}
+	}
+}
+/// tsp_over_prm.cpp:111-128 — vertices from just after the start node up to the goal (the start itself is not emitted).
+inline std::vector<uint32_t> retrace_path(const std::vector<uint32_t> &pred, uint32_t goal) {
+	std::vector<uint32_t> path;
+	for (uint32_t cur = goal; pred[cur] != cur; cur = pred[cur]) path.push_back(cur);
+	std::reverse(path.begin(), path.end());
+	return path;
 }
 
 }  // namespace orc

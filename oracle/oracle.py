@@ -311,6 +311,20 @@ def knn(states, k: int, causal: bool = False):
     return idx, dist
 
 
+def roadmap_shortest_paths(n_vertices: int, edges, weights, sources, threads=1):
+    """runDijkstra (tsp_over_prm.cpp:80-97) from every source; returns (dist, pred), each n_sources x n_vertices."""
+    edges = np.ascontiguousarray(edges, dtype=np.uint32).reshape(-1, 2)
+    weights = _arr(weights).reshape(-1)
+    sources = np.ascontiguousarray(sources, dtype=np.uint32).reshape(-1)
+    dist = np.zeros((len(sources), n_vertices))
+    pred = np.zeros((len(sources), n_vertices), np.uint32)
+    u32p = C.POINTER(C.c_uint32)
+    lib().orc_roadmap_shortest_paths(C.c_uint32(n_vertices), edges.ctypes.data_as(u32p), _d(weights), C.c_size_t(len(edges)),
+                                     sources.ctypes.data_as(u32p), C.c_size_t(len(sources)), _d(dist), pred.ctypes.data_as(u32p),
+                                     threads)
+    return dist, pred
+
+
 def from_ee_and_vector(robot: Robot, point, vec):
     out = np.zeros(8)
     lib().orc_from_ee_and_vector(robot.h, _d(_arr(point)), _d(_arr(vec)), _d(out))

@@ -325,4 +325,21 @@ long orc_shortcut_path(void *scene, void *robot, const double *states, size_t w,
 	return ok;
 }
 
+// ---- roadmap shortest paths --------------------------------------------------------------------------------
+/// Dijkstra from every source over an undirected edge list; dist / pred: n_sources x n_vertices, source-major.
+void orc_roadmap_shortest_paths(uint32_t n_vertices, const uint32_t *edges, const double *weights, size_t n_edges,
+								const uint32_t *sources, size_t n_sources, double *dist, uint32_t *pred, int threads) {
+	Roadmap g(n_vertices);
+	for (size_t e = 0; e < n_edges; ++e) g.add_edge(edges[2 * e], edges[2 * e + 1], weights[e]);
+	parallel_for(n_sources, threads, [&](size_t lo, size_t hi, int) {
+		std::vector<double> d;
+		std::vector<uint32_t> p;
+		for (size_t s = lo; s < hi; ++s) {
+			run_dijkstra(g, sources[s], d, p);
+			std::copy(d.begin(), d.end(), dist + s * n_vertices);
+			if (pred) std::copy(p.begin(), p.end(), pred + s * n_vertices);
+		}
+	});
+}
+
 }  // extern "C"

@@ -238,6 +238,41 @@ int main() {
 		}
 		std::printf("PRM: %zu edges validated on the GPU, %zu expected, %zu matched\n", edges.size(), expected, found);
 		CHECK(edges.size() == expected && found == expected);
+		// -- goal-to-goal shortest paths on that roadmap (tsp_over_prm.cpp:497-517) against the oracle's Dijkstra ---------
+		const PRMGraph graph = roadmap_from_edges(nodes, edges);
+		orc::Roadmap ograph(nodes.size());
+		for (auto &e: edges) ograph.add_edge((uint32_t) e.from, (uint32_t) e.to, e.weight);
+		std::vector<PRMGraph::vertex_descriptor> goals;
+		for (size_t v = 3; v < nodes.size(); v += 7) goals.push_back(v);
+		const GoalToGoalPathResults g2g = calculate_goal_to_goal_paths(graph, goals);
+		CHECK(g2g.distance_lookup.size() == goals.size() && g2g.predecessor_lookup.size() == goals.size());
+		size_t bad_dist = 0, bad_pred = 0, reachable = 0;
+		auto check_source = [&](uint32_t source, const std::vector<double> &dist, const std::vector<PRMGraph::vertex_descriptor> &pred) {
+			std::vector<double> od;
+			std::vector<uint32_t> op;
+			orc::run_dijkstra(ograph, source, od, op);
+			for (size_t v = 0; v < nodes.size(); ++v) {
+				bad_dist += dist[v] != od[v];
+				reachable += od[v] < std::numeric_limits<double>::max();
+				bad_pred += pred[v] != op[v];  // generic weights: no exact ties, so boost, the oracle and the GPU agree
+			}
+		};
+		for (size_t i = 0; i < goals.size(); ++i) check_source((uint32_t) goals[i], g2g.distance_lookup[i], g2g.predecessor_lookup[i]);
+		check_source(0, g2g.start_to_goals_distances, g2g.start_to_goals_predecessors);
+		std::printf("roadmap: %zu sources x %zu vertices, %zu reachable labels, %zu distance / %zu predecessor mismatches\n", goals.size() + 1,
+					nodes.size(), reachable, bad_dist, bad_pred);
+		CHECK(bad_dist == 0 && bad_pred == 0 && reachable > nodes.size());
+		auto [d0, p0] = runDijkstra(graph, goals[0]);
+		CHECK(d0 == g2g.distance_lookup[0] && p0 == g2g.predecessor_lookup[0]);
+		// retrace_path: same vertex sequence as the oracle's, start node omitted
+		for (size_t v = 0; v < nodes.size(); v += 11) {
+			std::vector<uint32_t> op(p0.begin(), p0.end());
+			const auto want = orc::retrace_path(op, (uint32_t) v);
+			const RobotPath got = retrace_path(graph, p0, v);
+			bool same = got.states.size() == want.size();
+			for (size_t i = 0; same && i < want.size(); ++i) same = got.states[i] == nodes[want[i]];
+			CHECK(same);
+		}
 	}
 	// -- path shortcutting: batched drivers == the reference's sequential loops (oracle as motion check) ------------------
 	{
