@@ -267,13 +267,13 @@ def run_ours(args):
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(mesh, a, b, use_ref=False)
     if not args.no_extra:
-        line["extra"] = extra_workloads(mg, torch, scene, tree, dev, stream)
+        line["extra"] = extra_workloads(mg, torch, scene, tree, dev, stream, cpu_leg=not args.no_cpu_baseline)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def extra_workloads(mg, torch, scene, tree, dev, stream):
+def extra_workloads(mg, torch, scene, tree, dev, stream, cpu_leg=True):
     """Secondary numbers (not the headline): 10 M state checks and 500 x 1000 goal samples on the same tree."""
     out = {}
     model = mg.robots.create_procedural_robot_model(1.0, (0,))
@@ -338,7 +338,8 @@ def extra_workloads(mg, torch, scene, tree, dev, stream):
         nn, k = len(nodes), 10
         d_nodes = torch.from_numpy(nodes).to(dev)
         d_idx = torch.zeros((nn, k), dtype=torch.int32, device=dev)
-        ms_knn = timed(lambda: mg.capi.knn_device(d_nodes, nn, 9, 2, k, d_idx, causal=True, stream=stream), reps=1, warm=1)
+        d_nd = torch.zeros((nn, k), dtype=torch.float64, device=dev)
+        ms_knn = timed(lambda: mg.capi.knn_device(d_nodes, nn, 9, 2, k, d_idx, d_nd, causal=True, stream=stream), reps=1, warm=1)
         idx = d_idx.cpu().numpy()
         src, col = np.nonzero(idx >= 0)
         d_ea = torch.from_numpy(np.ascontiguousarray(nodes[idx[src, col]])).to(dev)   # motion_collides(neighbour, state)
@@ -353,6 +354,47 @@ def extra_workloads(mg, torch, scene, tree, dev, stream):
         out["config4_prm_edges_100k_nodes_k10"] = {"edges": me, "edges_per_sec": me / (ms_e * 1e-3), "states_per_sec": float(sc) / (ms_e * 1e-3),
                                                     "ms_edge_validation": ms_e, "ms_knn_100k_causal": ms_knn,
                                                     "edge_collision_rate": float(eh.mean()), "mean_steps": float(d_es.float().mean().item())}
+        try:
+            # ---- next step of the planner: shortest paths from every goal sample over the validated roadmap (runDijkstra per
+            # source, tsp_over_prm.cpp:497-517), 1024 sources at once --------------------------------------------------------
+            free_e = ~eh
+            eu, ev = idx[src, col][free_e].astype(np.int64), src[free_e].astype(np.int64)
+            ew = d_nd.cpu().numpy()[src, col][free_e]
+            both_u, both_v, both_w = np.r_[eu, ev], np.r_[ev, eu], np.r_[ew, ew]
+            order = np.argsort(both_u, kind="stable")
+            row = np.zeros(nn + 1, np.int64)
+            np.add.at(row, both_u + 1, 1)
+            d_row = torch.from_numpy(np.cumsum(row).astype(np.uint32).view(np.int32)).to(dev)
+            d_col = torch.from_numpy(both_v[order].astype(np.uint32).view(np.int32)).to(dev)
+            d_w = torch.from_numpy(np.ascontiguousarray(both_w[order])).to(dev)
+            g = 1024
+            sources = np.random.default_rng(4).choice(nn, g, replace=False).astype(np.uint32)
+            d_src = torch.from_numpy(sources.view(np.int32)).to(dev)
+            d_dist = torch.empty((g, nn), dtype=torch.float64, device=dev)
+            d_pred = torch.empty((g, nn), dtype=torch.int32, device=dev)
+            mg.capi.roadmap_shortest_paths_device(d_row, d_col, d_w, nn, d_src, g, d_dist, d_pred, stream=stream)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sweeps = mg.capi.roadmap_shortest_paths_device(d_row, d_col, d_w, nn, d_src, g, d_dist, d_pred, stream=stream)
+            torch.cuda.synchronize()
+            ms_sp = (time.perf_counter() - t0) * 1e3
+            sp = {"sources": g, "vertices": nn, "edges": int(free_e.sum()), "ms": ms_sp, "sources_per_sec": g / (ms_sp * 1e-3),
+                  "labels_per_sec": g * nn / (ms_sp * 1e-3), "sweeps_enqueued": sweeps,
+                  "reachable_fraction": float((d_dist[:8] < 1e300).float().mean().item())}
+            if cpu_leg:
+                from oracle import oracle as o  # CPU baseline leg only: the oracle's Dijkstra on the host cores, bounded sample
+                threads = os.cpu_count() or 1
+                n_cpu = min(g, 2 * threads)
+                t0 = time.perf_counter()
+                want, _ = o.roadmap_shortest_paths(nn, np.stack([eu, ev], 1), ew, sources[:n_cpu], threads=threads)
+                cpu_s = time.perf_counter() - t0
+                sp["cpu_port_sources_per_sec"] = n_cpu / cpu_s
+                sp["cpu_port_threads"] = threads
+                sp["distances_bit_equal_to_cpu_dijkstra"] = bool(np.array_equal(want, d_dist[:n_cpu].cpu().numpy()))
+            out["config4_roadmap_shortest_paths_1024_sources"] = sp
+            del d_dist, d_pred
+        except Exception as e:
+            out["config4_roadmap_shortest_paths_1024_sources"] = {"error": repr(e)}
         del d_ea, d_eb, d_eh, d_et, d_es, d_idx, d_nodes
     except Exception as e:  # an extra must never cost the headline line
         out["config4_prm_edges_100k_nodes_k10"] = {"error": repr(e)}

@@ -9,8 +9,9 @@
 // value Dijkstra's algorithm returns (it evaluates the same sums, d[u] + w, along the same minimising paths).
 //
 // Layout: sources are packed 32 to a *source block*; labels are stored [block][vertex][32 sources], so a warp that
-// owns (block, vertex) reads one 256-byte line per neighbour, lanes = sources.  A few source blocks (as many as keep
-// their labels inside L2) are swept to convergence before the next group starts.  Per (block, vertex) "moved in the
+// owns (block, vertex) reads one 256-byte line per neighbour, lanes = sources.  Source blocks are swept to convergence a
+// group at a time (256 MB of labels per group: large enough to amortise launches and convergence read-backs — smaller,
+// L2-resident groups measured slower — small enough to bound scratch memory).  Per (block, vertex) "moved in the
 // previous sweep" flags let a warp skip vertices none of whose neighbours moved.
 #include <cfloat>
 
@@ -47,30 +48,30 @@ __global__ void __launch_bounds__(SSSP_BLOCK)
 k_sssp_sweep(const uint32_t *__restrict__ row, const uint32_t *__restrict__ col, const double *__restrict__ weight, unsigned n,
 			 unsigned n_blocks, double *labels, unsigned char *moved, unsigned t, unsigned k, unsigned *sweep_flags) {
 	if (__ldcg(sweep_flags + k) == 0) return;
-	const size_t warp = ((size_t) blockIdx.x * SSSP_BLOCK + threadIdx.x) >> 5;
-	if (warp >= (size_t) n_blocks * n) return;
-	const unsigned lane = threadIdx.x & 31, b = (unsigned) (warp / n), v = (unsigned) (warp % n);
+	const unsigned lane = threadIdx.x & 31, b = blockIdx.y;
 	const size_t plane = (size_t) n_blocks * n;
 	const unsigned char *moved_before = moved + (size_t) (t % 3) * plane + (size_t) b * n;
 	unsigned char *moved_now = moved + (size_t) ((t + 1) % 3) * plane + (size_t) b * n;
 	unsigned char *moved_next = moved + (size_t) ((t + 2) % 3) * plane + (size_t) b * n;
-	if (lane == 0) moved_next[v] = 0;
-	const unsigned e0 = __ldg(row + v), e1 = __ldg(row + v + 1);
-	bool any = false;
-	for (unsigned e = e0 + lane; e < e1; e += 32) any |= __ldcg(moved_before + __ldg(col + e)) != 0;
-	if (!__any_sync(0xffffffffu, any)) return;
-	double *mine = labels + ((size_t) b * n + v) * 32 + lane;
 	const double *base = labels + (size_t) b * n * 32 + lane;
-	const double before = __ldcg(mine);
-	double best = before;
+	bool raised = false;
+	for (unsigned v = blockIdx.x * (SSSP_BLOCK / 32) + (threadIdx.x >> 5); v < n; v += gridDim.x * (SSSP_BLOCK / 32)) {
+		if (lane == 0) moved_next[v] = 0;
+		const unsigned e0 = __ldg(row + v), e1 = __ldg(row + v + 1);
+		bool any = false;
+		for (unsigned e = e0 + lane; e < e1; e += 32) any |= __ldcg(moved_before + __ldg(col + e)) != 0;
+		if (!__any_sync(0xffffffffu, any)) continue;
+		double *mine = labels + ((size_t) b * n + v) * 32 + lane;
+		const double before = __ldcg(mine);
+		double best = before;
 #pragma unroll 4
-	for (unsigned e = e0; e < e1; ++e) best = fmin(best, __ldcg(base + (size_t) __ldg(col + e) * 32) + __ldg(weight + e));
-	const bool lower = best < before;
-	if (lower) __stcg(mine, best);
-	if (__any_sync(0xffffffffu, lower) && lane == 0) {
-		moved_now[v] = 1;
-		sweep_flags[k + 1] = 1;
+		for (unsigned e = e0; e < e1; ++e) best = fmin(best, __ldcg(base + (size_t) __ldg(col + e) * 32) + __ldg(weight + e));
+		const bool lower = best < before;
+		if (lower) __stcg(mine, best);
+		if (__any_sync(0xffffffffu, lower) && lane == 0) moved_now[v] = 1, raised = true;
 	}
+	// test before set: a hundred thousand warps storing to one address serialise in L2 and stall every load behind them
+	if (raised && __ldcg(sweep_flags + k + 1) == 0) sweep_flags[k + 1] = 1;
 }
 
 /// Final pass for one group: pick each vertex's predecessor (the neighbour u with d[u] + w == d[v]; ties go to the
@@ -116,8 +117,8 @@ k_sssp_finish(const uint32_t *__restrict__ row, const uint32_t *__restrict__ col
 size_t roadmap_group_blocks(unsigned n, size_t n_sources) {
 	static size_t l2_budget = 0;
 	if (!l2_budget) {
-		const char *e = getenv("MGODPL_SSSP_L2_BYTES");
-		l2_budget = e && atoll(e) > 0 ? (size_t) atoll(e) : (size_t) 64 << 20;
+		const char *e = getenv("MGODPL_SSSP_GROUP_BYTES");
+		l2_budget = e && atoll(e) > 0 ? (size_t) atoll(e) : (size_t) 256 << 20;
 	}
 	const size_t total_blocks = (n_sources + 31) / 32;
 	size_t g = l2_budget / ((size_t) n * 256 + 1);
@@ -146,8 +147,9 @@ cudaError_t launch_roadmap_shortest_paths(const uint32_t *d_row, const uint32_t 
 		const size_t first_source = b0 * 32;
 		k_sssp_init<<<148 * 8, SSSP_BLOCK, 0, stream>>>(labels, moved, n, nb);
 		k_sssp_seed<<<(nb * 32 + 127) / 128, 128, 0, stream>>>(labels, moved, n, nb, d_sources, first_source, n_sources);
-		const size_t warps = (size_t) nb * n;
-		const unsigned grid = (unsigned) ((warps * 32 + SSSP_BLOCK - 1) / SSSP_BLOCK);
+		// a few resident waves per source block: a sweep that finds the batch already converged costs microseconds, not a full grid
+		const unsigned per_block = (n + SSSP_BLOCK / 32 - 1) / (SSSP_BLOCK / 32), cap = (148u * 8u * 4u + nb - 1) / nb;
+		const dim3 grid(per_block < cap ? per_block : cap, nb);
 		unsigned t = 0;
 		for (;;) {
 			// flags[0] != 0 lets the batch start; flags[k + 1] is raised by sweep k when it moved a label
