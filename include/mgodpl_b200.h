@@ -199,6 +199,14 @@ int mgodpl_roadmap_shortest_paths_device(const uint32_t *d_row_offsets, const ui
 										 uint32_t n_vertices, const uint32_t *d_sources, size_t n_sources, double *d_dist,
 										 uint32_t *d_pred, uint32_t *sweeps_out, void *stream);
 
+/* ---- connected components of a mesh's vertex graph: connected_vertex_components
+ *      (src/experiment_utils/mesh_connected_components.cpp:25-74), which loadTreeMeshes uses to split a tree model's
+ *      combined fruit mesh into individual fruit (src/experiment_utils/TreeMeshes.cpp:28-66).  tris: nt x 3 vertex indices
+ *      (uint32, or uint64 = the reference's size_t, Mesh.h:19-22); labels[v] = the smallest vertex index of v's component
+ *      (the reference returns the same partition in unordered_map order). ------------------------------------------------ */
+int mgodpl_mesh_components(const uint32_t *tris, size_t nt, size_t nv, uint32_t *labels, void *stream);
+int mgodpl_mesh_components_u64(const uint64_t *tris, size_t nt, size_t nv, uint32_t *labels, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,7 +28,8 @@ EXPORTS = [
     "mgodpl_robot_destroy", "mgodpl_robot_n_variables", "mgodpl_forward_kinematics", "mgodpl_check_boxes",
     "mgodpl_check_states", "mgodpl_check_states_device", "mgodpl_check_motions", "mgodpl_check_motions_device",
     "mgodpl_check_path", "mgodpl_sample_goals", "mgodpl_sample_goals_device", "mgodpl_knn", "mgodpl_knn_device",
-    "mgodpl_roadmap_shortest_paths", "mgodpl_roadmap_shortest_paths_device",
+    "mgodpl_roadmap_shortest_paths", "mgodpl_roadmap_shortest_paths_device", "mgodpl_mesh_components",
+    "mgodpl_mesh_components_u64",
 ]
 
 
@@ -288,6 +289,15 @@ def knn(states, k: int, causal: bool = False, want_dist: bool = True, stream=Non
 def knn_device(d_states, n: int, stride: int, n_joint_values: int, k: int, d_idx, d_dist=None, causal: bool = False, stream=None):
     _check(lib().mgodpl_knn_device(_dptr(d_states), C.c_size_t(n), C.c_size_t(stride), n_joint_values, k, int(causal),
                                    _dptr(d_idx), _dptr(d_dist), _stream(stream)))
+
+
+def mesh_components(triangles, n_vertices: int, stream=None):
+    """labels[v] = smallest vertex index of v's connected component (connected_vertex_components, canonical form)."""
+    tris = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+    labels = np.zeros(n_vertices, np.uint32)
+    _check(lib().mgodpl_mesh_components(_p(tris, C.c_uint32), C.c_size_t(len(tris)), C.c_size_t(n_vertices), _p(labels, C.c_uint32),
+                                        _stream(stream)))
+    return labels
 
 
 def roadmap_shortest_paths(n_vertices: int, edges, weights, sources, want_pred: bool = True, stream=None):

@@ -920,4 +920,38 @@ int mgodpl_roadmap_shortest_paths(uint32_t n_vertices, const uint32_t *edges, co
 	return MGODPL_OK;
 }
 
+// ---- connected components of a mesh (fruit separation, mesh_connected_components.cpp:25-74) ---------------------------------
+}  // extern "C" (templates cannot have C linkage)
+namespace {
+template<class Index>
+int mesh_components_impl(const Index *tris, size_t nt, size_t nv, uint32_t *labels, void *stream_) {
+	if ((nt && !tris) || (nv && !labels)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (nv >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "too many vertices");
+	for (size_t i = 0; i < 3 * nt; ++i)
+		if ((size_t) tris[i] >= nv) return fail(MGODPL_E_INVALID_ARGUMENT, "triangle index out of range");
+	if (int rc = require_device()) return rc;
+	if (!nv) return MGODPL_OK;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	Index *d_t = nullptr;
+	unsigned *d_l = nullptr;
+	cudaError_t e = cudaMalloc((void **) &d_t, 3 * nt * sizeof(Index) + 8);
+	if (e == cudaSuccess) e = cudaMalloc((void **) &d_l, nv * 4);
+	if (e == cudaSuccess && nt) e = cudaMemcpyAsync(d_t, tris, 3 * nt * sizeof(Index), cudaMemcpyHostToDevice, stream);
+	if (e == cudaSuccess) e = launch_mesh_components<Index>(d_t, nt, (unsigned) nv, d_l, stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(labels, d_l, nv * 4, cudaMemcpyDeviceToHost, stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+	cudaFree(d_t), cudaFree(d_l);
+	if (e != cudaSuccess) return fail_cuda(e, "mesh_components");
+	return MGODPL_OK;
+}
+}  // namespace
+extern "C" {
+
+int mgodpl_mesh_components(const uint32_t *tris, size_t nt, size_t nv, uint32_t *labels, void *stream) {
+	return mesh_components_impl<uint32_t>(tris, nt, nv, labels, stream);
+}
+int mgodpl_mesh_components_u64(const uint64_t *tris, size_t nt, size_t nv, uint32_t *labels, void *stream) {
+	return mesh_components_impl<uint64_t>(tris, nt, nv, labels, stream);
+}
+
 }  // extern "C"

@@ -1,4 +1,4 @@
-// Host-callable launchers of the device kernels (query_kernels.cu, scene_build.cu, knn_kernels.cu, roadmap_kernels.cu).
+// Host-callable launchers of the device kernels (query_kernels.cu, scene_build.cu, knn_kernels.cu, roadmap_kernels.cu, mesh_kernels.cu).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -41,6 +41,10 @@ size_t roadmap_scratch_bytes(unsigned n, size_t n_sources);
 cudaError_t launch_roadmap_shortest_paths(const uint32_t *d_row, const uint32_t *d_col, const double *d_weight, unsigned n,
 										  const uint32_t *d_sources, size_t n_sources, double *d_dist, uint32_t *d_pred, void *scratch,
 										  unsigned *h_flag_pinned, unsigned *sweeps_out, cudaStream_t stream);
+
+/// Connected components of the vertex graph of a triangle mesh; d_labels[v] = smallest vertex index of v's component.
+template<class Index>
+cudaError_t launch_mesh_components(const Index *d_tris, size_t nt, unsigned nv, unsigned *d_labels, cudaStream_t stream);
 
 /// Result of the device BVH build: device buffers owned by the caller (cudaFree).
 struct BuiltScene {

@@ -6,3 +6,4 @@
 #include "mgodpl/roadmap.hpp"
 #include "mgodpl/robot_model.hpp"
 #include "mgodpl/sampling.hpp"
+#include "mgodpl/tree_meshes.hpp"

@@ -836,4 +836,31 @@ inline std::vector<uint32_t> retrace_path(const std::vector<uint32_t> &pred, uin
 	return path;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fruit separation: connected_vertex_components (src/experiment_utils/mesh_connected_components.cpp:25-74).
+// The reference merges vertex lists triangle by triangle (edges 0-1 and 1-2 of each triangle) and returns the
+// components in unordered_map order; restated with the same merging rule, reported in canonical form:
+// label[v] = smallest vertex index of v's component.
+// ---------------------------------------------------------------------------------------------------------
+inline std::vector<uint32_t> mesh_component_labels(const uint32_t *tris, size_t nt, size_t nv) {
+	std::vector<uint32_t> id(nv);
+	std::iota(id.begin(), id.end(), 0u);
+	std::vector<std::vector<uint32_t>> members(nv);
+	for (size_t v = 0; v < nv; ++v) members[v] = {(uint32_t) v};
+	for (size_t t = 0; t < nt; ++t)
+		for (int i: {0, 1}) {
+			const uint32_t a = id[tris[3 * t + i]], b = id[tris[3 * t + i + 1]];
+			if (a == b) continue;
+			for (uint32_t v: members[b]) members[a].push_back(v), id[v] = a;
+			members[b].clear();
+		}
+	std::vector<uint32_t> label(nv);
+	for (size_t c = 0; c < nv; ++c) {
+		if (members[c].empty()) continue;
+		const uint32_t lo = *std::min_element(members[c].begin(), members[c].end());
+		for (uint32_t v: members[c]) label[v] = lo;
+	}
+	return label;
+}
+
 }  // namespace orc

@@ -325,6 +325,24 @@ def roadmap_shortest_paths(n_vertices: int, edges, weights, sources, threads=1):
     return dist, pred
 
 
+def mesh_components(triangles, n_vertices: int):
+    """connected_vertex_components (mesh_connected_components.cpp:25-74), canonical labels (smallest vertex index)."""
+    tris = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+    labels = np.zeros(n_vertices, np.uint32)
+    lib().orc_mesh_components(tris.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_size_t(len(tris)), C.c_size_t(n_vertices),
+                              labels.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return labels
+
+
+def ref_mesh_components(triangles, n_vertices: int):
+    tris = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+    labels = np.zeros(n_vertices, np.uint32)
+    ref().ref_mesh_components.restype = C.c_size_t
+    n = ref().ref_mesh_components(tris.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_size_t(len(tris)), C.c_size_t(n_vertices),
+                                  labels.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return labels, int(n)
+
+
 def from_ee_and_vector(robot: Robot, point, vec):
     out = np.zeros(8)
     lib().orc_from_ee_and_vector(robot.h, _d(_arr(point)), _d(_arr(vec)), _d(out))

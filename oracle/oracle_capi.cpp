@@ -342,4 +342,10 @@ void orc_roadmap_shortest_paths(uint32_t n_vertices, const uint32_t *edges, cons
 	});
 }
 
+// ---- mesh connected components ----------------------------------------------------------------------------
+void orc_mesh_components(const uint32_t *tris, size_t nt, size_t nv, uint32_t *labels) {
+	auto l = mesh_component_labels(tris, nt, nv);
+	std::copy(l.begin(), l.end(), labels);
+}
+
 }  // extern "C"

@@ -8,11 +8,13 @@
 //
 // Used (a) here in the build container to validate oracle/mgodpl_oracle.hpp and to generate tests/golden/*.json
 // (tests/golden/make_golden.py), (b) on the GPU box — as a prebuilt .so — as a second checker in tests.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 
 #include "experiment_utils/procedural_robot_models.h"
 #include "experiment_utils/mesh_from_dae.h"
+#include "experiment_utils/mesh_connected_components.h"
 #include "planning/Mesh.h"
 #include "planning/RobotModel.h"
 #include "planning/RobotPath.h"
@@ -167,6 +169,20 @@ long ref_shortcut_path(void *scene, void *robot, const double *states, size_t w,
 	*out_w = path.states.size();
 	if (n_checks) *n_checks = checks;
 	return ok;
+}
+
+/// connected_vertex_components of the reference (mesh_connected_components.cpp:25-74), reported in canonical form:
+/// labels[v] = smallest vertex index of v's component; returns the number of components.
+size_t ref_mesh_components(const uint32_t *tris, size_t nt, size_t nv, uint32_t *labels) {
+	Mesh mesh;
+	mesh.vertices.resize(nv);
+	for (size_t t = 0; t < nt; ++t) mesh.triangles.push_back({tris[3 * t], tris[3 * t + 1], tris[3 * t + 2]});
+	auto cc = connected_vertex_components(mesh);
+	for (auto &c: cc) {
+		size_t lo = *std::min_element(c.begin(), c.end());
+		for (size_t v: c) labels[v] = (uint32_t) lo;
+	}
+	return cc.size();
 }
 
 }  // extern "C"

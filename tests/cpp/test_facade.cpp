@@ -5,6 +5,8 @@
 // src_old/test/collision_checking_test.cpp:30-57).  Needs a CUDA device; run by tests/test_gpu_facade.py.
 #include <algorithm>
 #include <cstdio>
+#include <filesystem>
+#include <fstream>
 #include <thread>
 
 #include "../../multigoal-orchard-drone-planning-library_b200/host/mgodpl.hpp"
@@ -55,6 +57,78 @@ static Mesh make_tree() {
 		add_tube(m, {0, 0, z}, math::Vec3d{0, 0, z} + dir * len, 0.05, 0.015, 6, 16);
 	}
 	return m;
+}
+
+// ---- COLLADA fixtures: a tree model written the way exporters write them (inches, y up), to be read back by from_dae -------
+static void add_blob(Mesh &m, math::Vec3d c, double r, int rings, int sides) {  // a closed UV sphere: one connected component
+	size_t base = m.vertices.size();
+	m.vertices.push_back(c + math::Vec3d{0, 0, r});
+	for (int i = 1; i < rings; ++i)
+		for (int k = 0; k < sides; ++k) {
+			double th = M_PI * i / rings, ph = 2 * M_PI * k / sides;
+			m.vertices.push_back(c + math::Vec3d{r * std::sin(th) * std::cos(ph), r * std::sin(th) * std::sin(ph), r * std::cos(th)});
+		}
+	m.vertices.push_back(c + math::Vec3d{0, 0, -r});
+	size_t south = m.vertices.size() - 1;
+	for (int k = 0; k < sides; ++k) {
+		size_t a = base + 1 + k, b = base + 1 + (k + 1) % sides;
+		m.triangles.push_back({base, a, b});
+		size_t la = base + 1 + (size_t) (rings - 2) * sides + k, lb = base + 1 + (size_t) (rings - 2) * sides + (k + 1) % sides;
+		m.triangles.push_back({south, lb, la});
+	}
+	for (int i = 0; i + 2 < rings; ++i)
+		for (int k = 0; k < sides; ++k) {
+			size_t a = base + 1 + (size_t) i * sides + k, b = base + 1 + (size_t) i * sides + (k + 1) % sides, c2 = a + sides, d = b + sides;
+			m.triangles.push_back({a, c2, b});
+			m.triangles.push_back({b, c2, d});
+		}
+}
+/// Writes `mesh` (metres, z up) as a COLLADA file in exporter units: inches x 100 / 2.54 ... i.e. the inverse of
+/// mesh_from_dae.cpp:55-63, y and z swapped.  style 0: <triangles> with an interleaved NORMAL input and every corner given
+/// its own position entry (so the reader must join identical vertices); 1: <polylist> (triangle pairs merged into quads
+/// where they share an edge in sequence); 2: <polygons>.
+static void write_dae(const std::string &path, const Mesh &mesh, int style) {
+	std::ofstream f(path);
+	f.precision(9);
+	const double s = 100.0 / 2.54;
+	f << "<?xml version=\"1.0\" encoding=\"utf-8\"?>\n<!-- test fixture -->\n<COLLADA xmlns=\"http://www.collada.org/2005/11/COLLADASchema\" version=\"1.4.1\">\n"
+	  << " <asset><unit name=\"inch\" meter=\"0.0254\"/><up_axis>Y_UP</up_axis></asset>\n <library_geometries>\n  <geometry id=\"g\" name=\"g\">\n   <mesh>\n";
+	std::vector<math::Vec3d> pos;
+	std::vector<size_t> idx;
+	if (style == 0) {
+		for (auto &t: mesh.triangles)
+			for (size_t v: t) idx.push_back(pos.size()), pos.push_back(mesh.vertices[v]);
+	} else {
+		pos = mesh.vertices;
+		for (auto &t: mesh.triangles)
+			for (size_t v: t) idx.push_back(v);
+	}
+	f << "    <source id=\"g-positions\"><float_array id=\"g-positions-array\" count=\"" << pos.size() * 3 << "\">";
+	for (auto &p: pos) f << p.x() * s << ' ' << p.z() * s << ' ' << p.y() * s << ' ';
+	f << "</float_array><technique_common><accessor source=\"#g-positions-array\" count=\"" << pos.size()
+	  << "\" stride=\"3\"><param name=\"X\" type=\"float\"/><param name=\"Y\" type=\"float\"/><param name=\"Z\" type=\"float\"/></accessor></technique_common></source>\n"
+	  << "    <source id=\"g-normals\"><float_array id=\"g-normals-array\" count=\"3\">0 1 0</float_array><technique_common><accessor source=\"#g-normals-array\" "
+		 "count=\"1\" stride=\"3\"/></technique_common></source>\n"
+	  << "    <vertices id=\"g-vertices\"><input semantic=\"POSITION\" source=\"#g-positions\"/></vertices>\n";
+	const size_t nt = mesh.triangles.size();
+	if (style == 0) {
+		f << "    <triangles material=\"m\" count=\"" << nt << "\"><input semantic=\"VERTEX\" source=\"#g-vertices\" offset=\"0\"/>"
+		  << "<input semantic=\"NORMAL\" source=\"#g-normals\" offset=\"1\"/><p>";
+		for (size_t i: idx) f << i << " 0 ";
+		f << "</p></triangles>\n";
+	} else if (style == 1) {
+		f << "    <polylist count=\"" << nt << "\"><input semantic=\"VERTEX\" source=\"#g-vertices\" offset=\"0\"/><vcount>";
+		for (size_t t = 0; t < nt; ++t) f << "3 ";
+		f << "</vcount><p>";
+		for (size_t i: idx) f << i << ' ';
+		f << "</p></polylist>\n";
+	} else {
+		f << "    <polygons count=\"" << nt << "\"><input semantic=\"VERTEX\" source=\"#g-vertices\" offset=\"0\"/>";
+		for (size_t t = 0; t < nt; ++t) f << "<p>" << idx[3 * t] << ' ' << idx[3 * t + 1] << ' ' << idx[3 * t + 2] << "</p>";
+		f << "</polygons>\n";
+	}
+	f << "   </mesh>\n  </geometry>\n </library_geometries>\n <library_visual_scenes><visual_scene id=\"s\"><node id=\"n\"><instance_geometry url=\"#g\"/></node>"
+		 "</visual_scene></library_visual_scenes>\n <scene><instance_visual_scene url=\"#s\"/></scene>\n</COLLADA>\n";
 }
 
 // ---- oracle twins ---------------------------------------------------------------------------------------------------------
@@ -351,6 +425,82 @@ int main() {
 		}
 		std::printf("shortcutting: %zu attempts, %zu successes, %zu GPU batches\n", total_attempts, total_success, total_batches);
 		CHECK(total_success > 0 && total_batches < total_attempts);
+	}
+	// -- tree-model ingest: COLLADA -> Mesh -> fruit components -> scene ------------------------------------------------------
+	{
+		namespace fs = std::filesystem;
+		const std::string dir = (fs::temp_directory_path() / "mgodpl_b200_models").string() + "/";
+		fs::create_directories(dir);
+		Mesh fruit;
+		std::vector<math::Vec3d> centres;
+		random_numbers::RandomNumberGenerator frng(5);
+		for (int i = 0; i < 23; ++i) {
+			centres.push_back({frng.uniformReal(-1.2, 1.2), frng.uniformReal(-1.2, 1.2), frng.uniformReal(1.0, 2.6)});
+			add_blob(fruit, centres.back(), 0.04, 6, 8);                                   // 42 vertices: a fruit
+			add_blob(fruit, centres.back() + math::Vec3d{0, 0, 0.06}, 0.005, 3, 5);      // 12 vertices: its stem, to be dropped
+		}
+		Mesh leaves;
+		for (int i = 0; i < 40; ++i) {
+			math::Vec3d c{frng.uniformReal(-1, 1), frng.uniformReal(-1, 1), frng.uniformReal(1, 2.5)};
+			size_t b = leaves.vertices.size();
+			leaves.vertices.insert(leaves.vertices.end(), {c, c + math::Vec3d{0.05, 0, 0}, c + math::Vec3d{0.05, 0.03, 0.01}});
+			leaves.triangles.push_back({b, b + 1, b + 2});
+		}
+		write_dae(dir + "synthetic_trunk.dae", tree, 0);
+		write_dae(dir + "synthetic_leaves.dae", leaves, 1);
+		write_dae(dir + "synthetic_apples.dae", fruit, 2);  // the legacy file name (TreeMeshes.cpp:38-47)
+		const auto names = tree_meshes::getTreeModelNames(dir);
+		CHECK(names.size() == 1 && names[0] == "synthetic");
+		const tree_meshes::TreeMeshes loaded = tree_meshes::loadTreeMeshes("synthetic", dir);
+		// identical positions joined, triangles kept, coordinates back in metres (float32 precision), z up
+		CHECK(loaded.trunk_mesh.vertices.size() == tree.vertices.size() && loaded.trunk_mesh.triangles.size() == tree.triangles.size());
+		double worst = 0;
+		for (size_t t = 0; t < tree.triangles.size() && t < loaded.trunk_mesh.triangles.size(); ++t)
+			for (int k = 0; k < 3; ++k)
+				worst = std::max(worst, (loaded.trunk_mesh.vertices[loaded.trunk_mesh.triangles[t][k]] - tree.vertices[tree.triangles[t][k]]).norm());
+		CHECK(worst < 1e-6);
+		CHECK(loaded.leaves_mesh.triangles.size() == leaves.triangles.size());
+		// fruit: 23 components of 42 vertices survive, 23 stems (12 vertices) are dropped; positions = AABB centres
+		CHECK(loaded.fruit_meshes.size() == centres.size());
+		const auto positions = tree_meshes::computeFruitPositions(loaded);
+		size_t matched = 0;
+		for (size_t i = 0; i < positions.size() && i < centres.size(); ++i)
+			matched += loaded.fruit_meshes[i].vertices.size() == 42 && (positions[i] - centres[i]).norm() < 1e-5;  // components come in first-vertex order
+		CHECK(matched == centres.size());
+		// components agree with the reference's merging rule (oracle restatement, pinned against mesh_connected_components.cpp)
+		{
+			std::vector<uint32_t> t32;
+			for (auto &t: fruit.triangles) t32.insert(t32.end(), {(uint32_t) t[0], (uint32_t) t[1], (uint32_t) t[2]});
+			const auto want = orc::mesh_component_labels(t32.data(), fruit.triangles.size(), fruit.vertices.size());
+			const auto cc = connected_vertex_components(fruit);
+			size_t agree = 0;
+			for (auto &c: cc)
+				for (size_t v: c) agree += want[v] == c.front();
+			CHECK(cc.size() == 46 && agree == fruit.vertices.size());
+		}
+		// the loaded trunk answers collision queries like the mesh it was written from
+		const gpu::Scene loaded_scene = gpu::treeMeshesToScene(loaded);
+		random_numbers::RandomNumberGenerator qrng(77);
+		std::vector<RobotState> qs;
+		for (int i = 0; i < 2000; ++i) qs.push_back(generateUniformRandomState(robot, qrng, 1.5, 2.5));
+		const auto b0 = check_states(robot, scene, qs), b1 = check_states(robot, loaded_scene, qs);
+		size_t differ = 0;
+		for (size_t i = 0; i < qs.size(); ++i) differ += bit(b0, i) != bit(b1, i);
+		CHECK(differ <= 2);  // float32 storage moves vertices by < 1e-6 m: only grazing contacts may flip
+		// orchard assembly: two metres apart, centred (TreeMeshes.cpp:197-206), one merged scene
+		std::vector<tree_meshes::TreeMeshes> models{loaded, loaded, loaded};
+		const auto orchard = tree_meshes::makeSingleRowOrchard(models);
+		CHECK(orchard.trees.size() == 3 && orchard.trees[0].first.x() == -3.0 && orchard.trees[2].first.x() == 1.0);
+		const gpu::Scene orchard_scene = gpu::orchardToScene(orchard);
+		CHECK(orchard_scene.info().n_triangles == 3 * tree.triangles.size());
+		CHECK(check_robot_collision(robot, orchard_scene, base_at(-3.0, 0, 0.8)) && check_robot_collision(robot, orchard_scene, base_at(1.0, 0, 0.8)) &&
+			  !check_robot_collision(robot, orchard_scene, base_at(-3.0, 0, 6.0)));
+		bool threw = false;
+		try {
+			from_dae(dir + "missing_trunk.dae");
+		} catch (const std::runtime_error &e) { threw = std::string(e.what()).find("Failed to load mesh from") == 0; }
+		CHECK(threw);
+		fs::remove_all(dir);
 	}
 	// -- error vocabulary -------------------------------------------------------------------------------------------------------
 	{
