@@ -562,28 +562,43 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 			}
 		}
 		__syncwarp();  // slerp_out[] of this warp's motions is read by other lanes on the overflow path
-		// cooperative append: for every lane with a non-empty range, the whole warp writes its (motion, step) pairs
-		unsigned todo = __ballot_sync(0xffffffffu, len > 0);
-		while (todo) {
-			const int src = __ffs(todo) - 1;
-			todo &= todo - 1;
-			const unsigned l = __shfl_sync(0xffffffffu, len, src), lo = __shfl_sync(0xffffffffu, s_lo, src);
-			const unsigned mot = (unsigned) (i - lane + src), ns = __shfl_sync(0xffffffffu, n_steps, src);
-			// The first head_steps steps of the range go to the head list, the rest to the tail list: the head is expanded
-			// and traversed first, and tail entries of motions that already collided by then are never expanded.
+		// cooperative append.  One allocation per warp and list: a prefix sum over the lanes' range lengths and a single
+		// atomicAdd of the total (a chain of per-motion atomics, each a dependent L2 round trip, used to be this kernel's
+		// critical path).  The first `head` steps of a range go to the head list, the rest to the tail list: the head is
+		// expanded and traversed first, and tail entries of motions that already collided by then are never expanded.
+		const unsigned l_head = min(len, head), l_tail = len - l_head;
+		unsigned incl_h = l_head, incl_t = l_tail;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const unsigned x = __shfl_up_sync(0xffffffffu, incl_h, o), y = __shfl_up_sync(0xffffffffu, incl_t, o);
+			if ((int) lane >= o) incl_h += x, incl_t += y;
+		}
+		const unsigned tot_h = __shfl_sync(0xffffffffu, incl_h, 31), tot_t = __shfl_sync(0xffffffffu, incl_t, 31);
+		if (tot_h + tot_t) {
 			const unsigned shard = my_shard();
-			const unsigned l_head = min(l, __shfl_sync(0xffffffffu, head, src));
-			for (int part = 0; part < 2; ++part) {
-				const SurvivorsDev &L = part ? S_tail : S;
-				const unsigned first = part ? l_head : 0u, cnt = part ? l - l_head : l_head;
-				if (!cnt) continue;
-				unsigned base = 0;
-				if (lane == 0) base = atomicAdd(L.counts + shard * COUNTER_STRIDE, cnt);
-				base = __shfl_sync(0xffffffffu, base, 0);
-				for (unsigned k = lane; k < cnt; k += 32) {
-					const unsigned pos = shard_slot(shard, base + k), step = lo + first + k;
-					if (pos < L.cap) L.entries[pos] = make_uint2(mot, step);
-					else expand_motion_step(sc, rb, Q, res, a + (size_t) mot * stride, b + (size_t) mot * stride, ns, slerp_out[mot], mot, step, lc);
+			unsigned base_h = 0, base_t = 0;
+			if (lane == 0) {
+				if (tot_h) base_h = atomicAdd(S.counts + shard * COUNTER_STRIDE, tot_h);
+				if (tot_t) base_t = atomicAdd(S_tail.counts + shard * COUNTER_STRIDE, tot_t);
+			}
+			base_h = __shfl_sync(0xffffffffu, base_h, 0) + incl_h - l_head;
+			base_t = __shfl_sync(0xffffffffu, base_t, 0) + incl_t - l_tail;
+			unsigned todo = __ballot_sync(0xffffffffu, len > 0);
+			while (todo) {  // for every lane with a non-empty range, the whole warp writes its (motion, step) pairs
+				const int src = __ffs(todo) - 1;
+				todo &= todo - 1;
+				const unsigned lo = __shfl_sync(0xffffffffu, s_lo, src), lh = __shfl_sync(0xffffffffu, l_head, src);
+				const unsigned mot = (unsigned) (i - lane + src), ns = __shfl_sync(0xffffffffu, n_steps, src);
+				const unsigned cnts[2] = {lh, __shfl_sync(0xffffffffu, l_tail, src)};
+				const unsigned bases[2] = {__shfl_sync(0xffffffffu, base_h, src), __shfl_sync(0xffffffffu, base_t, src)};
+				for (int part = 0; part < 2; ++part) {
+					const SurvivorsDev &L = part ? S_tail : S;
+					const unsigned first = part ? lh : 0u;
+					for (unsigned k = lane; k < cnts[part]; k += 32) {
+						const unsigned pos = shard_slot(shard, bases[part] + k), step = lo + first + k;
+						if (pos < L.cap) L.entries[pos] = make_uint2(mot, step);
+						else expand_motion_step(sc, rb, Q, res, a + (size_t) mot * stride, b + (size_t) mot * stride, ns, slerp_out[mot], mot, step, lc);
+					}
 				}
 			}
 		}
