@@ -436,10 +436,15 @@ k_expand_goals(const __grid_constant__ SceneDev sc, const __grid_constant__ Robo
 /// rule of Quaternion.cpp:12-20), exact reach cull, FK, box emit.  A/B point at the two endpoint rows.
 __device__ __forceinline__ void expand_motion_step(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
 												   const double *__restrict__ A, const double *__restrict__ B, unsigned n_steps,
-												   double2 slerp_k, unsigned motion, unsigned step, LocalCounters &lc) {
+												   double2 slerp_k, unsigned motion, unsigned step, LocalCounters &lc,
+												   const unsigned *skip_if_first_hit_le = nullptr) {
+	// the "an earlier step of this motion already collides" probe travels with the endpoint rows: one round trip, not two
+	unsigned first_hit = NO_HIT;
+	if (skip_if_first_hit_le) first_hit = __ldcg(skip_if_first_hit_le);
 	double a[7], b[7];
 #pragma unroll
 	for (int k = 0; k < 7; ++k) a[k] = __ldg(A + k), b[k] = __ldg(B + k);
+	if (first_hit <= step) return;
 	lc.states++;
 	// for n_steps == 0 the reference evaluates t = 0/0; here the start state is checked once.
 	const double t = n_steps ? (double) step / (double) n_steps : 0.0;
@@ -624,9 +629,8 @@ k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant
 	for (unsigned k = pass_lo + blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
 		if (!slot_filled(s_counts, k)) continue;
 		const uint2 e = __ldcg(&S.entries[k]);
-		if (skip_decided && __ldcg(res.first_step + e.x) <= e.y) continue;  // an earlier step of this motion already collides
 		expand_motion_step(sc, rb, Q, res, a + (size_t) e.x * stride, b + (size_t) e.x * stride, __ldg(n_steps + e.x), __ldg(slerp_k + e.x),
-						   e.x, e.y, lc);
+						   e.x, e.y, lc, skip_decided ? res.first_step + e.x : nullptr);
 	}
 	flush_counters(sc, lc);
 }
@@ -691,16 +695,20 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 				owner = (unsigned) __double2loint(v3.y), step_box = (unsigned) __double2hiint(v3.y);
 				// Motions: skip boxes of steps that can no longer be the first colliding one.  (For state bitmasks the
 				// same check only runs before a leaf test: it would cost a dependent L2 round trip per refill here.)
-				if (res.mode == RESULT_BITS || !already_decided(res, owner, step_box & 0x0FFFFFFFu)) {
-					double half_d[3];
-					if (explicit_boxes) {
-						const double *bx = explicit_boxes + (size_t) owner * 10;
-						half_d[0] = __ldg(bx + 7) * 0.5, half_d[1] = __ldg(bx + 8) * 0.5, half_d[2] = __ldg(bx + 9) * 0.5;
-					} else {
-						const double *hh = rb.boxes[step_box >> 28].half;
-						half_d[0] = hh[0], half_d[1] = hh[1], half_d[2] = hh[2];
-					}
-					cb = make_cull_box(sc, D3{v0.x, v0.y, v1.x}, Q4{v1.y, v2.x, v2.y, v3.x}, half_d);
+				// The probe is issued first and consumed last, so the cull box is built while it is in flight; the lane
+				// is idle, so overwriting `cb` for a box that turns out to be skipped costs nothing.
+				unsigned first_hit = NO_HIT;
+				if (res.mode != RESULT_BITS) first_hit = __ldcg(res.first_step + owner);
+				double half_d[3];
+				if (explicit_boxes) {
+					const double *bx = explicit_boxes + (size_t) owner * 10;
+					half_d[0] = __ldg(bx + 7) * 0.5, half_d[1] = __ldg(bx + 8) * 0.5, half_d[2] = __ldg(bx + 9) * 0.5;
+				} else {
+					const double *hh = rb.boxes[step_box >> 28].half;
+					half_d[0] = hh[0], half_d[1] = hh[1], half_d[2] = hh[2];
+				}
+				cb = make_cull_box(sc, D3{v0.x, v0.y, v1.x}, Q4{v1.y, v2.x, v2.y, v3.x}, half_d);
+				if (res.mode == RESULT_BITS || !(first_hit <= (step_box & 0x0FFFFFFFu))) {
 					cur = 0, sp = 0;
 					lc.boxes++;
 					max_box_nodes = max(max_box_nodes, box_nodes), box_nodes = 0;
