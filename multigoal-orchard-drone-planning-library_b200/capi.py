@@ -236,17 +236,34 @@ def check_states(scene: Scene, robot: Robot, states, stream=None, packed: bool =
     return words if packed else unpack_bits(words, n)
 
 
-def check_motions(scene: Scene, robot: Robot, a, b, max_step: float = 0.1, want_toi: bool = True, stream=None) -> dict:
+def check_motions(scene: Scene, robot: Robot, a, b, max_step: float = 0.1, want_toi: bool = True, stream=None,
+                  out: dict | None = None) -> dict:
+    """M x check_motion_collides.  Returns dict(hit[bool m], toi[m], n_steps[m], words[packed]).
+
+    ``out``: a dict from ``motion_result_buffers(m)`` to write into instead of allocating (repeated calls on batches of
+    one size); it is returned with words / toi / n_steps (uint32) filled and no unpacked ``hit``."""
     a, b = _states2d(a), _states2d(b)
     assert a.shape == b.shape
     m = len(a)
-    words = np.zeros((m + 31) // 32, np.uint32)
-    toi = np.zeros(m) if want_toi else None
-    steps = np.zeros(m, np.uint32)
+    if out is None:
+        words = np.zeros((m + 31) // 32, np.uint32)
+        toi = np.zeros(m) if want_toi else None
+        steps = np.zeros(m, np.uint32)
+    else:
+        words, toi, steps = out["words"], out["toi"] if want_toi else None, out["n_steps"]
+        if len(words) != (m + 31) // 32 or len(steps) != m or (toi is not None and len(toi) != m):
+            raise MgodplError(-1, "result buffers do not match the batch size")
     _check(lib().mgodpl_check_motions(scene.h, robot.h, _p(a), _p(b), C.c_size_t(m), C.c_size_t(a.shape[1]),
                                       a.shape[1] - 7, C.c_double(max_step), _p(words, C.c_uint32), _p(toi),
                                       _p(steps, C.c_uint32), _stream(stream)))
+    if out is not None:
+        return out
     return dict(hit=unpack_bits(words, m), toi=toi, n_steps=steps.astype(np.int64), words=words)
+
+
+def motion_result_buffers(m: int) -> dict:
+    """Reusable result arrays for ``check_motions(..., out=...)``."""
+    return dict(words=np.zeros((m + 31) // 32, np.uint32), toi=np.zeros(m), n_steps=np.zeros(m, np.uint32))
 
 
 def check_path(scene: Scene, robot: Robot, states, max_step: float = 0.1, stream=None) -> int:

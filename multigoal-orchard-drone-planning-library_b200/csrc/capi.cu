@@ -54,6 +54,9 @@ struct Workspace {
 	// two side streams for copy/compute overlap inside one host-buffer call (created on first use)
 	cudaStream_t side[2] = {nullptr, nullptr};
 	cudaEvent_t ev_start = nullptr, ev_done[2] = {nullptr, nullptr};
+	static constexpr size_t MAX_CHUNKS = 8;
+	cudaEvent_t ev_chunk[MAX_CHUNKS] = {};  // "results of chunk k are in pinned memory"
+
 	cudaError_t side_streams() {
 		if (side[0]) return cudaSuccess;
 		cudaError_t e = cudaSuccess;
@@ -62,6 +65,7 @@ struct Workspace {
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming);
 		}
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
+		for (size_t i = 0; i < MAX_CHUNKS && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ev_chunk[i], cudaEventDisableTiming);
 		return e;
 	}
 	cudaError_t reserve(size_t dev_bytes, size_t host_bytes) {
@@ -91,6 +95,8 @@ struct Workspace {
 			if (ev_done[i]) cudaEventDestroy(ev_done[i]);
 		}
 		if (ev_start) cudaEventDestroy(ev_start);
+		for (auto ev: ev_chunk)
+			if (ev) cudaEventDestroy(ev);
 	}
 };
 
@@ -112,8 +118,13 @@ struct WorkspacePool {
 struct Lease {
 	WorkspacePool &pool;
 	std::unique_ptr<Workspace> ws;
+	bool settled = false;  // set once the call has synchronised with everything it enqueued on this workspace
 	explicit Lease(WorkspacePool &p) : pool(p), ws(p.acquire()) {}
-	~Lease() { pool.release(std::move(ws)); }
+	~Lease() {
+		// an error return may leave copies or kernels in flight on the workspace: wait before another call can reuse it
+		if (!settled) cudaDeviceSynchronize(), cudaGetLastError();
+		pool.release(std::move(ws));
+	}
 	Workspace *operator->() { return ws.get(); }
 };
 
@@ -515,6 +526,7 @@ int mgodpl_check_boxes(mgodpl_scene *scene, const double *boxes, size_t n, uint3
 	CU(cudaMemcpyAsync(ws->host, ws->dev + o_out, words * 4, cudaMemcpyDeviceToHost, stream));
 	CU(cudaStreamSynchronize(stream));
 	memcpy(hit_bits, ws->host, words * 4);
+	ws.settled = true;
 	return MGODPL_OK;
 }
 
@@ -556,6 +568,7 @@ int mgodpl_check_states(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	CU(cudaMemcpyAsync(ws->host, ws->dev + o_out, words * 4, cudaMemcpyDeviceToHost, stream));
 	CU(cudaStreamSynchronize(stream));
 	memcpy(hit_bits, ws->host, words * 4);
+	ws.settled = true;
 	return MGODPL_OK;
 }
 
@@ -626,7 +639,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	static size_t chunk_pref = 0;
 	if (!chunk_pref) {
 		const char *e = getenv("MGODPL_E2E_CHUNKS");
-		chunk_pref = e && atoi(e) > 0 ? (size_t) atoi(e) : 2;
+		chunk_pref = e && atoi(e) > 0 ? std::min((size_t) atoi(e), Workspace::MAX_CHUNKS) : 2;
 	}
 	const size_t n_chunks = m >= 32768 ? chunk_pref : 1;
 	const size_t chunk_m = n_chunks == 1 ? m : ((m + n_chunks - 1) / n_chunks + 31) / 32 * 32;
@@ -667,6 +680,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		CU(cudaMemcpyAsync(H + o_steps + lo * 4, D + o_steps + lo * 4, mc * 4, cudaMemcpyDeviceToHost, s));
 		if (toi) CU(cudaMemcpyAsync(H + o_toi + lo * 8, D + o_toi + lo * 8, mc * 8, cudaMemcpyDeviceToHost, s));
 		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][3], s));
+		if (n_chunks > 1) CU(cudaEventRecord(ws->ev_chunk[ci], s));
 	}
 	if (n_chunks > 1)
 		for (int s = 0; s < 2; ++s) {
@@ -674,26 +688,41 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 			CU(cudaStreamWaitEvent(stream, ws->ev_done[s], 0));
 		}
 	const auto t_enqueued = now();
-	CU(cudaStreamSynchronize(stream));
-	const auto t_synced = now();
 	// Step-count fix-up: the device libm may differ from the host's by an ulp, which only matters when distance /
 	// max_step sits on an integer boundary.  Re-derive those on the host and re-run if any count disagrees.
 	uint32_t *h_unc = (uint32_t *) (H + o_unc), *h_steps = (uint32_t *) (H + o_steps), *h_ovr = (uint32_t *) (H + o_ovr);
 	size_t n_fix = 0;
-	for (size_t w = 0; w < words; ++w) {
-		uint32_t bits = h_unc[w];
-		while (bits) {
-			int k = __builtin_ctz(bits);
-			bits &= bits - 1;
-			size_t i = w * 32 + k;
-			uint32_t want = host_n_steps(a + i * stride, b + i * stride, js, max_step);
-			if (want != h_steps[i]) {
-				if (!n_fix) memset(h_ovr, 0xff, m * 4);
-				h_ovr[i] = want;
-				++n_fix;
+	// Results of motions [lo, hi) are in pinned memory: look for step counts to fix up and hand the range to the caller.
+	auto deliver = [&](size_t lo, size_t hi) {
+		const size_t w_lo = lo / 32, w_hi = (hi + 31) / 32;
+		for (size_t w = w_lo; w < w_hi; ++w) {
+			uint32_t bits = h_unc[w];
+			while (bits) {
+				int k = __builtin_ctz(bits);
+				bits &= bits - 1;
+				size_t i = w * 32 + k;
+				uint32_t want = host_n_steps(a + i * stride, b + i * stride, js, max_step);
+				if (want != h_steps[i]) {
+					if (!n_fix) memset(h_ovr, 0xff, m * 4);
+					h_ovr[i] = want;
+					++n_fix;
+				}
 			}
 		}
+		memcpy(hit_bits + w_lo, H + o_hit + w_lo * 4, (w_hi - w_lo) * 4);
+		if (toi) memcpy(toi + lo, H + o_toi + lo * 8, (hi - lo) * 8);
+		if (n_steps_out) memcpy(n_steps_out + lo, h_steps + lo, (hi - lo) * 4);
+	};
+	if (n_chunks > 1) {
+		// a chunk's results are handed over while the chunks behind it are still on the GPU
+		for (size_t ci = 0; ci < n_chunks && ci * chunk_m < m; ++ci) {
+			CU(cudaEventSynchronize(ws->ev_chunk[ci]));
+			deliver(ci * chunk_m, std::min(m, (ci + 1) * chunk_m));
+		}
 	}
+	CU(cudaStreamSynchronize(stream));
+	if (n_chunks == 1) deliver(0, m);
+	const auto t_synced = now();
 	if (n_fix) {
 		// Rare path (the boundary set is normally empty for sampled states): re-run with the corrected counts pinned.
 		CU(cudaMemcpyAsync(D + o_ovr, h_ovr, m * 4, cudaMemcpyHostToDevice, stream));
@@ -703,15 +732,14 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 								(unsigned *) (D + o_first), D + o_slerp, D + o_q, qb, motion_survivors(m), stream));
 		CU(cudaMemcpyAsync(H + out_lo, D + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, stream));
 		CU(cudaStreamSynchronize(stream));
+		memcpy(hit_bits, H + o_hit, words * 4);
+		if (toi) memcpy(toi, H + o_toi, m * 8);
+		if (n_steps_out) memcpy(n_steps_out, h_steps, m * 4);
 	}
-	const auto t_fixed = now();
-	memcpy(hit_bits, H + o_hit, words * 4);
-	if (toi) memcpy(toi, H + o_toi, m * 8);
-	if (n_steps_out) memcpy(n_steps_out, h_steps, m * 4);
 	if (trace) {
 		auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
-		fprintf(stderr, "[mgodpl] check_motions m=%zu: enqueue %.0f us, wait %.0f us, fix-up %.0f us (%zu re-derived), copy-out %.0f us\n", m,
-				us(t_begin, t_enqueued), us(t_enqueued, t_synced), us(t_synced, t_fixed), n_fix, us(t_fixed, now()));
+		fprintf(stderr, "[mgodpl] check_motions m=%zu: enqueue %.0f us, wait + fix-up scan + copy-out %.0f us, re-run %.0f us (%zu re-derived)\n", m,
+				us(t_begin, t_enqueued), us(t_enqueued, t_synced), us(t_synced, now()), n_fix);
 		for (size_t ci = 0; ci < n_chunks && ci < 2; ++ci) {
 			float h2d = 0, ker = 0, d2h = 0, off = 0;
 			cudaEventElapsedTime(&h2d, tev[ci][0], tev[ci][1]);
@@ -722,6 +750,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 					ker * 1e3, d2h * 1e3);
 		}
 	}
+	ws.settled = true;
 	return MGODPL_OK;
 }
 
@@ -794,6 +823,7 @@ int mgodpl_sample_goals(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	CU(cudaStreamSynchronize(stream));
 	memcpy(hit_bits, H + o_hit, f * wpr * 4);
 	if (collisions) memcpy(collisions, H + o_cnt, f * 4);
+	ws.settled = true;
 	return MGODPL_OK;
 }
 
