@@ -3,7 +3,9 @@
 Every state / motion / goal sample is independent given the (replicated, read-only) scene, so a batch is split into
 contiguous index ranges whose boundaries are multiples of 32: result bitmask words then never straddle two ranks and
 the gathered mask is the plain concatenation of the per-rank words.  No collective is needed on the data path; only
-the packed result words are gathered.
+the packed result words are gathered.  Row-shaped results (time of impact, goal-sample counts, the roadmap's
+per-source distance tables — sources are independent too, and a shard of 32 is one source block of the kernel) are
+sharded the same way and gathered with `gather_rows`.
 """
 from __future__ import annotations
 
@@ -35,6 +37,21 @@ def gather_words(local_words, n: int, rank: int, world_size: int, group=None):
     pad = max(sizes) if sizes else 0
     buf = torch.zeros(pad, dtype=torch.int32, device=local_words.device)
     buf[: local_words.numel()] = local_words.view(torch.int32)
+    out = [torch.empty_like(buf) for _ in range(world_size)]
+    dist.all_gather(out, buf, group=group)
+    return torch.cat([o[:s] for o, s in zip(out, sizes)])
+
+
+def gather_rows(local_rows, n: int, rank: int, world_size: int, group=None, align: int = 32):
+    """All-gather row-sharded results (one row per query: roadmap distance tables sharded by source, goal-sample counts
+    sharded by fruit, toi values ...).  `local_rows`: this rank's [hi - lo, ...] torch tensor for shard_range(n, rank)."""
+    import torch
+    import torch.distributed as dist
+
+    sizes = [hi - lo for lo, hi in (shard_range(n, r, world_size, align) for r in range(world_size))]
+    pad = max(sizes) if sizes else 0
+    buf = torch.zeros((pad,) + tuple(local_rows.shape[1:]), dtype=local_rows.dtype, device=local_rows.device)
+    buf[: local_rows.shape[0]] = local_rows
     out = [torch.empty_like(buf) for _ in range(world_size)]
     dist.all_gather(out, buf, group=group)
     return torch.cat([o[:s] for o, s in zip(out, sizes)])

@@ -121,6 +121,15 @@ full = mg.sharding.gather_words(torch.from_numpy(words.view(np.int32).copy()), n
 got = mg.capi.unpack_bits(full.numpy().view(np.uint32), n)
 want = scene.check_states(robot, states)
 assert np.array_equal(got, want), (rank, int((got != want).sum()))
+# roadmap shortest paths shard by source (a shard of 32 = one source block): each rank solves its sources, rows are gathered
+rng = np.random.default_rng(5)
+nv, edges, w = 300, rng.integers(0, 300, (900, 2)).astype(np.uint32), rng.uniform(0.1, 2.0, 900)
+sources = rng.integers(0, nv, 70).astype(np.uint32)
+lo, hi = mg.sharding.shard_range(len(sources), rank, 2)
+d_local, _ = o.roadmap_shortest_paths(nv, edges, w, sources[lo:hi])
+d_full = mg.sharding.gather_rows(torch.from_numpy(d_local), len(sources), rank, 2).numpy()
+d_want, _ = o.roadmap_shortest_paths(nv, edges, w, sources)
+assert (lo, hi) == ((0, 64), (64, 70))[rank] and np.array_equal(d_full, d_want)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok", int(want.sum()))
