@@ -18,8 +18,19 @@ namespace mgodpl_b200 {
 // One visit therefore tests two boxes per dependent fetch, and leaves never cost a fetch of their own.
 // Triangles are stored in leaf (preorder) order as 9 fp64 world coordinates, so a leaf's triangles are contiguous.
 // ---------------------------------------------------------------------------------------------------------------
+//
+// Stage B walks a 4-wide form of the same tree: every second level is folded into its parent, so a 128-byte record
+// (eight float4) holds up to four children, child k as
+//   f4[2k] = (cx, cy, cz, as_float(ref))   f4[2k+1] = (hx, hy, hz, -)
+// with the same reference encoding (ref >= 0: wide record index) and WIDE_EMPTY in unused slots.  Half as many dependent
+// fetches per descent as the binary records, which remain for the one-thread overflow path.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int WIDE_EMPTY = (int) 0x80000000;
 struct SceneDev {
 	const float4 *nodes;     // 4 * n_nodes float4
+	const float4 *wide;      // 8 * n_wide float4, or nullptr (MGODPL_WIDE_BVH=0): stage B then walks the binary records
+	uint32_t n_wide;
+	float4 top[8];           // copy of wide record 0 (the root's up to four grandchildren): stage A culls against it before queueing
 	const double *tris;      // 9 * n_tris doubles (v0 v1 v2), world frame, leaf order: the exact test reads these
 	const float4 *tris32;    // 3 * n_tris float4 (v0 v1 v2 relative to origin, w unused): the fp32 pre-filter reads these
 	uint32_t n_nodes;

@@ -116,6 +116,7 @@ __device__ __noinline__ bool exact_leaf_test(const SceneDev &sc, const void *exa
 }
 
 constexpr int STACK_DEPTH = 64;        // scene creation rejects trees deeper than 60 levels
+constexpr int WIDE_STACK_DEPTH = 96;   // 4-wide records: at most 30 levels, up to three pushes each
 constexpr int REF_END = (int) 0x80000000;  // "nothing left to visit"
 
 /// Test both children of record `cur`; returns the next reference to visit (pushing the other overlapping child).
@@ -139,6 +140,28 @@ __device__ __forceinline__ int visit_record(const SceneDev &sc, const CullBox &c
 	} else if (sp > 0) {
 		next = stack[--sp];
 	}
+	return next;
+}
+
+/// The same for a 4-wide record: up to four boxes per dependent fetch; the nearest overlapping child is visited next, the
+/// others are pushed.
+__device__ __forceinline__ int visit_wide(const SceneDev &sc, const CullBox &cb, int cur, int *stack, int &sp) {
+	const float4 *rec = sc.wide + 8ull * (unsigned) cur;
+	float4 a[4], b[4];
+#pragma unroll
+	for (int k = 0; k < 4; ++k) a[k] = __ldg(rec + 2 * k), b[k] = __ldg(rec + 2 * k + 1);
+	int next = REF_END;
+	float next_d = 0.f;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const int ref = __float_as_int(a[k].w);
+		if (ref == WIDE_EMPTY || !cull_overlap(cb, a[k].x, a[k].y, a[k].z, b[k].x, b[k].y, b[k].z)) continue;
+		const float dx = a[k].x - cb.cx, dy = a[k].y - cb.cy, dz = a[k].z - cb.cz, d = dx * dx + dy * dy + dz * dz;
+		if (next == REF_END) next = ref, next_d = d;
+		else if (d < next_d) stack[sp++] = next, next = ref, next_d = d;
+		else stack[sp++] = ref;
+	}
+	if (next == REF_END && sp > 0) next = stack[--sp];
 	return next;
 }
 
@@ -221,6 +244,16 @@ __device__ __forceinline__ void emit_box(const SceneDev &sc, const QueueDev &Q, 
 										 const double *half, unsigned owner, unsigned step, unsigned box, LocalCounters &lc) {
 	const CullBox cb = make_cull_box(sc, c, q, half);
 	if (!cull_overlap(cb, sc.root_c[0], sc.root_c[1], sc.root_c[2], sc.root_h[0], sc.root_h[1], sc.root_h[2])) return;
+	if (sc.wide) {
+		// One level further while the box is in registers anyway: the root record's (up to four) children travel with the
+		// kernel parameters.  A box that misses all of them would cost stage B a queue item, a refill and a record fetch.
+		bool any = false;
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			any |= __float_as_int(sc.top[2 * k].w) != WIDE_EMPTY &&
+				   cull_overlap(cb, sc.top[2 * k].x, sc.top[2 * k].y, sc.top[2 * k].z, sc.top[2 * k + 1].x, sc.top[2 * k + 1].y, sc.top[2 * k + 1].z);
+		if (!any) return;
+	}
 	cg::coalesced_group g = cg::coalesced_threads();
 	unsigned base = 0;
 	const unsigned shard = my_shard();
@@ -654,7 +687,7 @@ struct TraverseTuning {
 	int no_prefilter; // MGODPL_NO_PREFILTER=1: every leaf triangle goes to the fp64 test (tests compare both modes)
 };
 
-template<int MIN_BLOCKS>
+template<int MIN_BLOCKS, bool WIDE>
 __global__ void __launch_bounds__(BLOCK_B, MIN_BLOCKS)
 k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ explicit_boxes,
 		   QueueDev Q, Results res, TraverseTuning tune) {
@@ -671,7 +704,7 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 	CullBox cb{};
 	unsigned owner = 0, step_box = 0, item = 0;
 	int cur = REF_END, sp = 0;
-	int stack[STACK_DEPTH];
+	int stack[WIDE ? WIDE_STACK_DEPTH : STACK_DEPTH];
 	unsigned box_nodes = 0, max_box_nodes = 0;  // longest single descent (counters only)
 
 	for (;;) {
@@ -723,7 +756,7 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 		while (go) {
 			if (cur >= 0) {
 				lc.nodes++, box_nodes++;
-				cur = visit_record(sc, cb, cur, stack, sp);
+				cur = WIDE ? visit_wide(sc, cb, cur, stack, sp) : visit_record(sc, cb, cur, stack, sp);
 			}
 			go = __ballot_sync(FULL, cur >= 0);
 			parked = __ballot_sync(FULL, cur < 0 && cur != REF_END);
@@ -921,12 +954,17 @@ static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const do
 		if ((e = getenv("MGODPL_LEAF_MIN"))) tune.leaf_min = atoi(e);
 		if ((e = getenv("MGODPL_NO_PREFILTER"))) tune.no_prefilter = atoi(e);
 	}
+	const bool wide = sc.wide != nullptr;
+#define MGODPL_LAUNCH_TRAVERSE(MB)                                                                                                      \
+	if (wide) k_traverse<MB, true><<<grid_for(bound, BLOCK_B, MB), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune);       \
+	else k_traverse<MB, false><<<grid_for(bound, BLOCK_B, MB), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune)
 	switch (min_blocks) {
-		case 8: k_traverse<8><<<grid_for(bound, BLOCK_B, 8), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune); break;
-		case 6: k_traverse<6><<<grid_for(bound, BLOCK_B, 6), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune); break;
-		case 5: k_traverse<5><<<grid_for(bound, BLOCK_B, 5), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune); break;
-		default: k_traverse<4><<<grid_for(bound, BLOCK_B, 4), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune); break;
+		case 8: MGODPL_LAUNCH_TRAVERSE(8); break;
+		case 6: MGODPL_LAUNCH_TRAVERSE(6); break;
+		case 5: MGODPL_LAUNCH_TRAVERSE(5); break;
+		default: MGODPL_LAUNCH_TRAVERSE(4); break;
 	}
+#undef MGODPL_LAUNCH_TRAVERSE
 	return cudaGetLastError();
 }
 
