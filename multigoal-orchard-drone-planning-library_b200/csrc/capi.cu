@@ -677,7 +677,7 @@ int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, 
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Carver c;
 	const size_t qb = motion_scratch_bytes(m, robot->dev.n_boxes);
-	size_t o_first = c.take(m * 4), o_steps = c.take(d_n_steps ? 0 : m * 4), o_slerp = c.take(m * 16), o_q = c.take(qb);
+	size_t o_first = c.take(m * 4), o_steps = c.take(d_n_steps ? 0 : m * 4), o_slerp = c.take(m * 32), o_q = c.take(qb);
 	char *scratch = nullptr;
 	CU(scene->device_scratch(stream, c.off, &scratch));
 	CU(launch_check_motions(scene->dev, robot->dev, d_a, d_b, m, stride, js, max_step, d_override, d_hit_bits, d_toi,
@@ -728,7 +728,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	const size_t n_chunks = m >= 32768 ? chunk_pref : 1;
 	const size_t chunk_m = n_chunks == 1 ? m : ((m + n_chunks - 1) / n_chunks + 31) / 32 * 32;
 	const size_t in_b = m * stride * 8, words = (m + 31) / 32, qb = motion_scratch_bytes(chunk_m, robot->dev.n_boxes);
-	size_t o_a = c.take(in_b), o_b = c.take(in_b), o_first = c.take(m * 4), o_slerp = c.take(m * 16);
+	size_t o_a = c.take(in_b), o_b = c.take(in_b), o_first = c.take(m * 4), o_slerp = c.take(m * 32);
 	size_t o_hit = c.take(words * 4), o_unc = c.take(words * 4), o_steps = c.take(m * 4), o_toi = c.take(toi ? m * 8 : 0);
 	const size_t out_lo = o_hit, out_hi = c.off;
 	size_t o_ovr = c.take(m * 4);
@@ -757,7 +757,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a) + lo * stride, (const double *) (D + o_b) + lo * stride, mc,
 								stride, js, max_step, nullptr, (uint32_t *) (D + o_hit) + w_lo, toi ? (double *) (D + o_toi) + lo : nullptr,
 								(uint32_t *) (D + o_steps) + lo, (uint32_t *) (D + o_unc) + w_lo, (unsigned *) (D + o_first) + lo,
-								D + o_slerp + lo * 16, D + ((ci & 1) ? o_q2 : o_q), qb, motion_survivors(mc), s));
+								D + o_slerp + lo * 32, D + ((ci & 1) ? o_q2 : o_q), qb, motion_survivors(mc), s));
 		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][2], s));
 		CU(cudaMemcpyAsync(H + o_hit + w_lo * 4, D + o_hit + w_lo * 4, w_n * 4, cudaMemcpyDeviceToHost, s));
 		CU(cudaMemcpyAsync(H + o_unc + w_lo * 4, D + o_unc + w_lo * 4, w_n * 4, cudaMemcpyDeviceToHost, s));

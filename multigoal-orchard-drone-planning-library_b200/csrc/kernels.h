@@ -18,7 +18,7 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 								uint32_t *d_hit_bits, void *scratch, size_t scratch_bytes, cudaStream_t stream);
 cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t n, uint32_t *d_hit_bits, void *scratch,
 							   size_t scratch_bytes, cudaStream_t stream);
-/// d_n_steps, d_first_step (m x u32 each) and d_slerp (m x 16 B) are mandatory work buffers; d_toi / d_uncertain /
+/// d_n_steps, d_first_step (m x u32 each) and d_slerp (m x 32 B) are mandatory work buffers; d_toi / d_uncertain /
 /// d_override are optional.
 cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const double *d_a, const double *d_b, size_t m,
 								 size_t stride, int js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,

@@ -465,11 +465,23 @@ k_expand_goals(const __grid_constant__ SceneDev sc, const __grid_constant__ Robo
 	flush_counters(sc, lc);
 }
 
+/// Per-motion constants of the Eigen slerp rule (Quaternion.cpp:12-20), computed once in stage A1: with theta =
+/// acos(|dot|) the weights sin((1-t) theta) / sin(theta) and sin(t theta) / sin(theta) become, by the angle-difference
+/// identity, cos(t theta) - cot(theta) sin(t theta) and sin(t theta) / sin(theta): one sincos per step, no division.
+/// theta < 0 flags the linear-weights case; the sign of inv_sin carries "dot < 0" (second weight negated).
+struct __align__(16) SlerpConst {
+	double theta, inv_sin, cot, pad;
+};
+__device__ __forceinline__ SlerpConst load_slerp(const SlerpConst *p) {
+	const double2 lo = __ldg(reinterpret_cast<const double2 *>(p)), hi = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+	return SlerpConst{lo.x, lo.y, hi.x, 0.0};
+}
+
 /// One interpolation step of one motion: interpolate(a, b, t) (RobotState.cpp:14-24, Transform.h:69-78, Eigen slerp
 /// rule of Quaternion.cpp:12-20), exact reach cull, FK, box emit.  A/B point at the two endpoint rows.
 __device__ __forceinline__ void expand_motion_step(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
 												   const double *__restrict__ A, const double *__restrict__ B, unsigned n_steps,
-												   double2 slerp_k, unsigned motion, unsigned step, LocalCounters &lc,
+												   SlerpConst slerp_k, unsigned motion, unsigned step, LocalCounters &lc,
 												   const unsigned *skip_if_first_hit_le = nullptr) {
 	// the "an earlier step of this motion already collides" probe travels with the endpoint rows: one round trip, not two
 	unsigned first_hit = NO_HIT;
@@ -486,17 +498,16 @@ __device__ __forceinline__ void expand_motion_step(const SceneDev &sc, const Rob
 	Pose base{tr, Q4{a[3], a[4], a[5], a[6]}};
 	double jv[MGODPL_MAX_JOINT_VALUES];
 	if (n_steps) {
-		// slerp_k = (theta, sin(theta)) of the motion, theta < 0 flags the linear-weights case, the sign of .y carries
-		// "dot < 0" (second weight negated) — all per-motion constants of the Eigen rule, computed once in stage A1.
 		double w0, w1;
-		if (slerp_k.x < 0.0) {
+		if (slerp_k.theta < 0.0) {
 			w0 = 1.0 - t, w1 = t;
 		} else {
-			const double st = fabs(slerp_k.y);
-			w0 = sin((1.0 - t) * slerp_k.x) / st;
-			w1 = sin(t * slerp_k.x) / st;
+			double s1, c1;
+			sincos(t * slerp_k.theta, &s1, &c1);
+			w0 = c1 - slerp_k.cot * s1;
+			w1 = s1 * fabs(slerp_k.inv_sin);
 		}
-		if (signbit(slerp_k.y)) w1 = -w1;
+		if (signbit(slerp_k.inv_sin)) w1 = -w1;
 		base.q = Q4{w0 * a[3] + w1 * b[3], w0 * a[4] + w1 * b[4], w0 * a[5] + w1 * b[5], w0 * a[6] + w1 * b[6]};
 		for (int k = 0; k < rb.n_vars; ++k) jv[k] = __ldg(A + 7 + k) * (1 - t) + __ldg(B + 7 + k) * t;
 	} else {
@@ -514,7 +525,7 @@ __global__ void __launch_bounds__(BLOCK_A)
 k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
 				const double *__restrict__ b, size_t m, size_t stride, int js, double max_step,
 				const uint32_t *__restrict__ n_steps_override, uint32_t *__restrict__ n_steps_out,
-				uint32_t *__restrict__ uncertain_bits, double2 *__restrict__ slerp_out, SurvivorsDev S, SurvivorsDev S_tail,
+				uint32_t *__restrict__ uncertain_bits, SlerpConst *__restrict__ slerp_out, SurvivorsDev S, SurvivorsDev S_tail,
 				unsigned head_steps, QueueDev Q, Results res) {
 	const unsigned lane = threadIdx.x & 31;
 	LocalCounters lc;
@@ -549,13 +560,13 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 				// Eigen slerp rule (Quaternion.cpp:12-20): dot over (x, y, z, w); linear weights when |dot| >= 1 - eps
 				const double dq = ar[3] * br[3] + ar[4] * br[4] + ar[5] * br[5] + ar[6] * br[6];
 				const double ad = fabs(dq);
-				double2 k;
-				if (ad >= 1.0 - 2.220446049250313e-16) {
-					k.x = -1.0, k.y = 1.0;
-				} else {
-					k.x = acos(ad), k.y = sin(k.x);
+				SlerpConst k{-1.0, 1.0, 0.0, 0.0};
+				if (ad < 1.0 - 2.220446049250313e-16) {
+					k.theta = acos(ad);
+					const double st = sin(k.theta);
+					k.inv_sin = 1.0 / st, k.cot = ad / st;
 				}
-				if (dq < 0.0) k.y = -k.y;
+				if (dq < 0.0) k.inv_sin = -k.inv_sin;
 				slerp_out[i] = k;
 			}
 			if (uncertain && uncertain_bits) atomicOr(uncertain_bits + (i >> 5), 1u << (i & 31));
@@ -653,7 +664,7 @@ template<int MIN_BLOCKS>
 __global__ void __launch_bounds__(BLOCK_A, MIN_BLOCKS)
 k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
 					  const double *__restrict__ b, size_t stride, const uint32_t *__restrict__ n_steps,
-					  const double2 *__restrict__ slerp_k, SurvivorsDev S, unsigned pass_lo, unsigned pass_hi, int skip_decided, QueueDev Q,
+					  const SlerpConst *__restrict__ slerp_k, SurvivorsDev S, unsigned pass_lo, unsigned pass_hi, int skip_decided, QueueDev Q,
 					  Results res) {
 	LocalCounters lc;
 	__shared__ unsigned s_counts[SHARDS];
@@ -662,7 +673,7 @@ k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant
 	for (unsigned k = pass_lo + blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
 		if (!slot_filled(s_counts, k)) continue;
 		const uint2 e = __ldcg(&S.entries[k]);
-		expand_motion_step(sc, rb, Q, res, a + (size_t) e.x * stride, b + (size_t) e.x * stride, __ldg(n_steps + e.x), __ldg(slerp_k + e.x),
+		expand_motion_step(sc, rb, Q, res, a + (size_t) e.x * stride, b + (size_t) e.x * stride, __ldg(n_steps + e.x), load_slerp(slerp_k + e.x),
 						   e.x, e.y, lc, skip_decided ? res.first_step + e.x : nullptr);
 	}
 	flush_counters(sc, lc);
@@ -1063,7 +1074,7 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	LQ_CHECK(cudaMemsetAsync(d_first_step, 0xff, m * sizeof(unsigned), stream));
 	if (d_uncertain) LQ_CHECK(cudaMemsetAsync(d_uncertain, 0, ((m + 31) / 32) * 4, stream));
 	k_motion_ranges<<<grid_for(m, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
-																	  d_n_steps, d_uncertain, (double2 *) d_slerp, S, S_tail, head_arg, Q, res);
+																	  d_n_steps, d_uncertain, (SlerpConst *) d_slerp, S, S_tail, head_arg, Q, res);
 	LQ_CHECK(cudaGetLastError());
 	// Head list first (the steps right after a motion comes within reach of the scene), then the tail with the
 	// "already collided" skip: most of a colliding motion's in-reach steps lie after its first hit.
@@ -1080,7 +1091,7 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 			// the first pass shares the queue with stage A1's own overflow path (a survivor list that ran full expands inline)
 			if (!first_pass) LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
 			first_pass = false;
-			k_expand_motion_steps<2><<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const double2 *) d_slerp, L,
+			k_expand_motion_steps<2><<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const SlerpConst *) d_slerp, L,
 																							 (unsigned) lo, (unsigned) hi, part, Q, res);
 			LQ_CHECK(cudaGetLastError());
 			LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (hi - lo) * (size_t) rb.n_boxes, stream));
