@@ -234,7 +234,7 @@ def run_ours(args):
         return
     peak, peak_kind = peaks()
     ms_per_step = total_ms / args.steps
-    b_scene = int(info.device_bytes)  # BVH records + both triangle copies, read at most once per launch from HBM
+    b_scene = int(info.traversal_bytes)  # the records stage B walks + both triangle copies, read at most once per launch from HBM
     algo_bytes = m * B_MOTION + b_scene
     achieved = algo_bytes / (np.mean(step_ms) * 1e-3) / 1e9
     traffic = None

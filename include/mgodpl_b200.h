@@ -89,6 +89,8 @@ typedef struct mgodpl_scene_info {
 	double build_ms;       /* device time of the BVH build */
 	double sah_cost;       /* surface-area-heuristic cost of the final tree (C_node = 1, C_tri = 1) */
 	uint32_t max_depth, max_leaf_size;
+	uint64_t n_wide_nodes;  /* 128-byte 4-wide records the traversal walks (0: it walks the n_nodes 64-byte binary records) */
+	uint64_t traversal_bytes; /* bytes one pass over the traversal's own data reads: its records + both triangle copies */
 } mgodpl_scene_info;
 
 /* Deterministic cost counters: the reference's own observability hook on this path is an invocation counter

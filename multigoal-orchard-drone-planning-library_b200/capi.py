@@ -58,7 +58,7 @@ class SceneInfo(C.Structure):
     _fields_ = [("n_triangles", C.c_uint64), ("n_nodes", C.c_uint64), ("n_leaves", C.c_uint64),
                 ("device_bytes", C.c_uint64), ("bounds_lo", C.c_double * 3), ("bounds_hi", C.c_double * 3),
                 ("build_ms", C.c_double), ("sah_cost", C.c_double), ("max_depth", C.c_uint32),
-                ("max_leaf_size", C.c_uint32)]
+                ("max_leaf_size", C.c_uint32), ("n_wide_nodes", C.c_uint64), ("traversal_bytes", C.c_uint64)]
 
 
 class Counters(C.Structure):

@@ -338,6 +338,8 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 	mgodpl_scene_info &in = sc->info;
 	in.n_triangles = nt, in.n_nodes = d.n_nodes, in.n_leaves = sc->built.n_leaves;
 	in.device_bytes = sc->built.device_bytes;
+	in.n_wide_nodes = d.n_wide;
+	in.traversal_bytes = (d.wide ? (uint64_t) d.n_wide * 128 : (uint64_t) d.n_nodes * 64) + (uint64_t) nt * (72 + 48);
 	for (int a = 0; a < 3; ++a) in.bounds_lo[a] = lo[a], in.bounds_hi[a] = hi[a];
 	in.build_ms = sc->built.build_ms, in.sah_cost = sc->built.sah_cost;
 	in.max_depth = sc->built.max_depth, in.max_leaf_size = sc->built.max_leaf;
