@@ -526,7 +526,7 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 				const double *__restrict__ b, size_t m, size_t stride, int js, double max_step,
 				const uint32_t *__restrict__ n_steps_override, uint32_t *__restrict__ n_steps_out,
 				uint32_t *__restrict__ uncertain_bits, SlerpConst *__restrict__ slerp_out, SurvivorsDev S, SurvivorsDev S_tail,
-				unsigned head_steps, QueueDev Q, Results res) {
+				unsigned head_steps, int trim, QueueDev Q, Results res) {
 	const unsigned lane = threadIdx.x & 31;
 	LocalCounters lc;
 	unsigned long long n_uncertain = 0, n_motions = 0;
@@ -602,8 +602,8 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 					const double t = n_steps ? (double) s / (double) n_steps : 0.0;
 					return robot_out_of_reach(sc, rb, D3{(1.0 - t) * ar[0] + t * br[0], (1.0 - t) * ar[1] + t * br[1], (1.0 - t) * ar[2] + t * br[2]});
 				};
-				for (int guard = 0; guard < 64 && s_lo < s_hi && outside(s_lo); ++guard) ++s_lo;
-				for (int guard = 0; guard < 64 && s_hi > s_lo && outside(s_hi); ++guard) --s_hi;
+				for (int guard = 0; guard < trim && s_lo < s_hi && outside(s_lo); ++guard) ++s_lo;
+				for (int guard = 0; guard < trim && s_hi > s_lo && outside(s_hi); ++guard) --s_hi;
 				len = (s_lo == s_hi && outside(s_lo)) ? 0u : s_hi - s_lo + 1;
 				// head_steps == 0: adaptive head — the steps it takes to cross the reach shell around the scene bounds plus
 				// ~0.75 m of canopy, where a colliding motion typically finds its first hit
@@ -1068,13 +1068,18 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 		head_steps = e && atoi(e) > 0 ? (unsigned) atoi(e) : 0x80000000u;  // default: adaptive per motion
 	}
 	const unsigned head_arg = head_steps == 0x80000000u ? 0u : head_steps;
+	static int trim = -1;
+	if (trim < 0) {
+		const char *e = getenv("MGODPL_TRIM");
+		trim = e ? atoi(e) : 16;
+	}
 	carve(scratch, scratch_bytes, survivor_entries, &S, &Q, &S_tail, m * (size_t) (head_arg ? head_arg : 48u));
 	Results res{RESULT_FIRST_STEP, nullptr, d_first_step};
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_first_step, 0xff, m * sizeof(unsigned), stream));
 	if (d_uncertain) LQ_CHECK(cudaMemsetAsync(d_uncertain, 0, ((m + 31) / 32) * 4, stream));
 	k_motion_ranges<<<grid_for(m, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
-																	  d_n_steps, d_uncertain, (SlerpConst *) d_slerp, S, S_tail, head_arg, Q, res);
+																	  d_n_steps, d_uncertain, (SlerpConst *) d_slerp, S, S_tail, head_arg, trim, Q, res);
 	LQ_CHECK(cudaGetLastError());
 	// Head list first (the steps right after a motion comes within reach of the scene), then the tail with the
 	// "already collided" skip: most of a colliding motion's in-reach steps lie after its first hit.
