@@ -141,7 +141,6 @@ struct Carver {
 }  // namespace
 
 struct mgodpl_scene {
-	float4 *d_wide = nullptr;
 	SceneDev dev{};
 	BuiltScene built{};
 	mgodpl_scene_info info{};
@@ -167,70 +166,6 @@ struct mgodpl_robot {
 	double *d_limits = nullptr;  // n_vars x (min, max)
 	std::vector<double> limits;
 };
-
-namespace {
-/// Folds every second level of the binary records into its parent: 4-wide records in depth-first preorder (see
-/// device_types.cuh).  Host-side, once per scene: the records are a few megabytes and the pass is linear.
-std::vector<float> widen_records(const std::vector<float> &bin, uint32_t n_nodes) {
-	struct Child {
-		float c[3], h[3];
-		int ref;
-	};
-	auto children_of = [&](uint32_t rec, Child out[2]) {
-		const float *f = bin.data() + 16ull * rec;
-		out[0] = {{f[0], f[1], f[2]}, {f[3], f[4], f[5]}, 0};
-		out[1] = {{f[6], f[7], f[8]}, {f[9], f[10], f[11]}, 0};
-		std::memcpy(&out[0].ref, f + 12, 4), std::memcpy(&out[1].ref, f + 13, 4);
-	};
-	std::vector<float> wide;
-	wide.reserve(32ull * (n_nodes / 2 + 1));
-	struct Job {
-		uint32_t bin_rec;
-		size_t patch;  // float index of the parent's reference slot, or SIZE_MAX for the root
-	};
-	std::vector<Job> todo{{0u, SIZE_MAX}};
-	while (!todo.empty()) {
-		const Job job = todo.back();
-		todo.pop_back();
-		const uint32_t me = (uint32_t) (wide.size() / 32);
-		if (job.patch != SIZE_MAX) {
-			const int ref = (int) me;
-			std::memcpy(&wide[job.patch], &ref, 4);
-		}
-		wide.resize(wide.size() + 32, 0.f);
-		Child slots[4];
-		int n_slots = 0;
-		Child pair[2];
-		children_of(job.bin_rec, pair);
-		for (int k = 0; k < 2; ++k) {
-			if (pair[k].h[0] < 0.f) continue;  // the empty second child of a single-leaf scene
-			if (pair[k].ref < 0) slots[n_slots++] = pair[k];  // a leaf stays a direct child
-			else {
-				Child grand[2];
-				children_of((uint32_t) pair[k].ref, grand);
-				slots[n_slots++] = grand[0], slots[n_slots++] = grand[1];
-			}
-		}
-		float *rec = wide.data() + 32ull * me;
-		std::vector<Job> mine;
-		for (int k = 0; k < 4; ++k) {
-			float *a = rec + 8 * k, *b = a + 4;
-			int ref = WIDE_EMPTY;
-			if (k < n_slots) {
-				a[0] = slots[k].c[0], a[1] = slots[k].c[1], a[2] = slots[k].c[2];
-				b[0] = slots[k].h[0], b[1] = slots[k].h[1], b[2] = slots[k].h[2];
-				ref = slots[k].ref;
-				if (ref >= 0) mine.push_back({(uint32_t) ref, (size_t) (32ull * me + 8 * k + 3)});
-			} else {
-				b[0] = b[1] = b[2] = -3.0e38f;
-			}
-			std::memcpy(a + 3, &ref, 4);
-		}
-		for (auto it = mine.rbegin(); it != mine.rend(); ++it) todo.push_back(*it);  // first internal child right behind its parent
-	}
-	return wide;
-}
-}  // namespace
 
 // =================================================================================================================
 extern "C" {
@@ -288,12 +223,13 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 		}
 		e = cudaMemcpyAsync(d_verts, verts, nv * 3 * sizeof(double), cudaMemcpyHostToDevice, stream);
 		if (e == cudaSuccess) e = cudaMemcpyAsync(d_tris, idx.data(), nt * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
-		if (e == cudaSuccess) e = build_scene(d_verts, nv, d_tris, nt, lo, hi, origin, leaf, refine, &sc->built, stream);
+		static const bool want_wide = !(getenv("MGODPL_WIDE_BVH") && atoi(getenv("MGODPL_WIDE_BVH")) == 0);
+		if (e == cudaSuccess) e = build_scene(d_verts, nv, d_tris, nt, lo, hi, origin, leaf, refine, want_wide, &sc->built, stream);
 		cudaStreamSynchronize(stream);
 		cudaFree(d_verts);
 		cudaFree(d_tris);
 		if (e != cudaSuccess) {
-			cudaFree(sc->built.nodes), cudaFree(sc->built.tris), cudaFree(sc->built.tris32), cudaFree(sc->built.tri_ids);
+			cudaFree(sc->built.nodes), cudaFree(sc->built.wide), cudaFree(sc->built.tris), cudaFree(sc->built.tris32), cudaFree(sc->built.tri_ids);
 			return fail_cuda(e, "build_scene");
 		}
 	}
@@ -312,23 +248,9 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 		mgodpl_scene_destroy(sc.release());
 		return fail(MGODPL_E_INVALID_ARGUMENT, "BVH deeper than the traversal stack (pathological triangle distribution)");
 	}
-	static const bool want_wide = !(getenv("MGODPL_WIDE_BVH") && atoi(getenv("MGODPL_WIDE_BVH")) == 0);
-	if (want_wide && d.n_nodes) {
-		std::vector<float> bin(16ull * d.n_nodes);
-		cudaError_t e = cudaMemcpy(bin.data(), d.nodes, bin.size() * 4, cudaMemcpyDeviceToHost);
-		std::vector<float> wide;
-		if (e == cudaSuccess) {
-			wide = widen_records(bin, d.n_nodes);
-			e = cudaMalloc((void **) &sc->d_wide, wide.size() * 4);
-		}
-		if (e == cudaSuccess) e = cudaMemcpy(sc->d_wide, wide.data(), wide.size() * 4, cudaMemcpyHostToDevice);
-		if (e != cudaSuccess) {
-			mgodpl_scene_destroy(sc.release());
-			return fail_cuda(e, "wide BVH records");
-		}
-		d.wide = sc->d_wide, d.n_wide = (uint32_t) (wide.size() / 32);
-		std::memcpy(d.top, wide.data(), sizeof(d.top));
-		sc->built.device_bytes += wide.size() * 4;
+	if (sc->built.wide) {
+		d.wide = sc->built.wide, d.n_wide = sc->built.n_wide;
+		std::memcpy(d.top, sc->built.top, sizeof(d.top));
 	}
 	if (opts && (opts->flags & MGODPL_SCENE_COUNTERS)) {
 		CU(cudaMalloc((void **) &sc->d_counters, CNT_N * sizeof(unsigned long long)));
@@ -357,7 +279,7 @@ int mgodpl_scene_create_u64(const double *verts, size_t nv, const uint64_t *tris
 }
 int mgodpl_scene_destroy(mgodpl_scene *s) {
 	if (!s) return MGODPL_OK;
-	cudaFree(s->d_wide);
+	cudaFree(s->built.wide);
 	cudaFree(s->built.nodes), cudaFree(s->built.tris), cudaFree(s->built.tris32), cudaFree(s->built.tri_ids), cudaFree(s->d_counters);
 	delete s;
 	return MGODPL_OK;

@@ -49,6 +49,9 @@ cudaError_t launch_mesh_components(const Index *d_tris, size_t nt, unsigned nv, 
 /// Result of the device BVH build: device buffers owned by the caller (cudaFree).
 struct BuiltScene {
 	float4 *nodes = nullptr;
+	float4 *wide = nullptr;       // 4-wide records folded from `nodes` (nullptr when not requested)
+	float4 top[8] = {};          // host copy of wide record 0
+	uint32_t n_wide = 0;
 	double *tris = nullptr;
 	float4 *tris32 = nullptr;
 	uint32_t *tri_ids = nullptr;  // original triangle index of every stored triangle slot
@@ -59,7 +62,7 @@ struct BuiltScene {
 };
 /// d_verts: nv x 3 doubles, d_tris: nt x 3 uint32 (device).  lo/hi: scene bounds (host, from the vertices used).
 cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris, size_t nt, const double *lo,
-						const double *hi, const double *origin, unsigned max_leaf_size, bool refine, BuiltScene *out,
+						const double *hi, const double *origin, unsigned max_leaf_size, bool refine, bool wide, BuiltScene *out,
 						cudaStream_t stream);
 
 }  // namespace mgodpl_b200

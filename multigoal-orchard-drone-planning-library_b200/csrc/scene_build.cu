@@ -267,7 +267,7 @@ __global__ void k_flatten(int n, const int *__restrict__ left, const int *__rest
 						  const unsigned *__restrict__ eff_size, unsigned max_leaf, const double *__restrict__ verts,
 						  const uint32_t *__restrict__ tris, const uint32_t *__restrict__ ids, float4 *__restrict__ nodes,
 						  double *__restrict__ tri_out, float4 *__restrict__ tri32_out, D3 origin, uint32_t *__restrict__ slot_ids,
-						  float4 *__restrict__ root_box,
+						  float4 *__restrict__ root_box, unsigned *__restrict__ even_depth,
 						  BuildStats *__restrict__ stats) {
 	int x = blockIdx.x * TB + threadIdx.x;
 	if (x >= 2 * n - 1) return;
@@ -323,11 +323,51 @@ __global__ void k_flatten(int n, const int *__restrict__ left, const int *__rest
 		lref = cl <= max_leaf ? -1 - (int) (tri_before << 4 | (cl - 1)) : (int) (pre + 1u);
 		rref = cr <= max_leaf ? -1 - (int) ((tri_before + cl) << 4 | (cr - 1)) : (int) (pre + 1u + (eff_size[l] - 1u) / 2u);
 	}
+	even_depth[pre] = (depth & 1u) == 0u;  // these records become the 4-wide records (k_fold_wide)
 	float4 *rec = nodes + 4ull * pre;
 	rec[0] = make_float4(c0[0], c0[1], c0[2], h0[0]);
 	rec[1] = make_float4(h0[1], h0[2], c1[0], c1[1]);
 	rec[2] = make_float4(c1[2], h1[0], h1[1], h1[2]);
 	rec[3] = make_float4(__int_as_float(lref), __int_as_float(rref), 0.f, 0.f);
+}
+
+/// Folds every second level of the binary records into its parent (4-wide records, device_types.cuh): one thread per
+/// even-depth binary record; its wide index is its rank among the even-depth records in preorder (an exclusive scan of
+/// the even-depth flags), so the wide records are in depth-first preorder too.
+__global__ void k_fold_wide(const float4 *__restrict__ nodes, unsigned n_nodes, const unsigned *__restrict__ even_depth,
+							const unsigned *__restrict__ wide_index, float4 *__restrict__ wide) {
+	const unsigned x = blockIdx.x * TB + threadIdx.x;
+	if (x >= n_nodes || !even_depth[x]) return;
+	float4 *out = wide + 8ull * wide_index[x];
+	int slot = 0;
+	auto put = [&](float cx, float cy, float cz, float hx, float hy, float hz, int ref) {
+		if (ref >= 0) ref = (int) wide_index[ref];  // an internal grandchild: itself an even-depth record
+		out[2 * slot] = make_float4(cx, cy, cz, __int_as_float(ref));
+		out[2 * slot + 1] = make_float4(hx, hy, hz, 0.f);
+		++slot;
+	};
+	auto children = [&](unsigned rec, bool expand) {
+		const float4 a = nodes[4ull * rec], b = nodes[4ull * rec + 1], c = nodes[4ull * rec + 2], d = nodes[4ull * rec + 3];
+		const float box[2][6] = {{a.x, a.y, a.z, a.w, b.x, b.y}, {b.z, b.w, c.x, c.y, c.z, c.w}};
+		const int ref[2] = {__float_as_int(d.x), __float_as_int(d.y)};
+		for (int k = 0; k < 2; ++k) {
+			if (box[k][3] < 0.f) continue;  // the empty second child of a single-leaf scene
+			if (expand && ref[k] >= 0) {
+				// an internal child sits at odd depth: it is absorbed, its two children become children of this record
+				const unsigned r2 = (unsigned) ref[k];
+				const float4 a2 = nodes[4ull * r2], b2 = nodes[4ull * r2 + 1], c2 = nodes[4ull * r2 + 2], d2 = nodes[4ull * r2 + 3];
+				put(a2.x, a2.y, a2.z, a2.w, b2.x, b2.y, __float_as_int(d2.x));
+				put(b2.z, b2.w, c2.x, c2.y, c2.z, c2.w, __float_as_int(d2.y));
+			} else {
+				put(box[k][0], box[k][1], box[k][2], box[k][3], box[k][4], box[k][5], ref[k]);
+			}
+		}
+	};
+	children(x, true);
+	for (; slot < 4; ++slot) {
+		out[2 * slot] = make_float4(0.f, 0.f, 0.f, __int_as_float(WIDE_EMPTY));
+		out[2 * slot + 1] = make_float4(-3.0e38f, -3.0e38f, -3.0e38f, 0.f);
+	}
 }
 
 struct Scratch {
@@ -352,7 +392,7 @@ struct Scratch {
 	} while (0)
 
 cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris, size_t nt, const double *lo, const double *hi,
-						const double *origin, unsigned max_leaf_size, bool refine, BuiltScene *out, cudaStream_t stream) {
+						const double *origin, unsigned max_leaf_size, bool refine, bool wide, BuiltScene *out, cudaStream_t stream) {
 	(void) nv;
 	(void) refine;
 	*out = BuiltScene{};
@@ -467,13 +507,31 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 	const unsigned n_nodes = root_size > 1 ? (root_size - 1) / 2 : 1;  // one 64-byte record per surviving internal node
 	float4 *d_root_box;
 	BS_CHECK(tmp.alloc(&d_root_box, 2));
+	unsigned *even_depth, *wide_index;
+	BS_CHECK(tmp.alloc(&even_depth, (size_t) n_nodes + 1));
+	BS_CHECK(tmp.alloc(&wide_index, (size_t) n_nodes + 1));
+	BS_CHECK(cudaMemsetAsync(even_depth, 0, ((size_t) n_nodes + 1) * sizeof(unsigned), stream));
 	BS_CHECK(cudaMalloc((void **) &out->nodes, (size_t) n_nodes * 4 * sizeof(float4)));
 	BS_CHECK(cudaMalloc((void **) &out->tris, nt * 9 * sizeof(double)));
 	BS_CHECK(cudaMalloc((void **) &out->tris32, nt * 3 * sizeof(float4)));
 	k_flatten<<<(unsigned) ((2 * nt - 1 + TB - 1) / TB), TB, 0, stream>>>(n, left, right, parent, blo, bhi, tri_count, eff_size,
 																		  max_leaf_size, d_verts, d_tris, ids2, out->nodes, out->tris, out->tris32,
-																		  D3{origin[0], origin[1], origin[2]}, ids, d_root_box, d_stats);
+																		  D3{origin[0], origin[1], origin[2]}, ids, d_root_box, even_depth, d_stats);
 	BS_CHECK(cudaGetLastError());
+	unsigned n_wide = 0;
+	if (wide) {
+		size_t scan_bytes = 0;
+		BS_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, even_depth, wide_index, n_nodes + 1, stream));
+		void *scan_ws;
+		BS_CHECK(tmp.alloc((char **) &scan_ws, scan_bytes));
+		BS_CHECK(cub::DeviceScan::ExclusiveSum(scan_ws, scan_bytes, even_depth, wide_index, n_nodes + 1, stream));
+		BS_CHECK(cudaMemcpyAsync(&n_wide, wide_index + n_nodes, sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+		BS_CHECK(cudaStreamSynchronize(stream));
+		BS_CHECK(cudaMalloc((void **) &out->wide, (size_t) n_wide * 8 * sizeof(float4)));
+		k_fold_wide<<<(n_nodes + TB - 1) / TB, TB, 0, stream>>>(out->nodes, n_nodes, even_depth, wide_index, out->wide);
+		BS_CHECK(cudaGetLastError());
+		BS_CHECK(cudaMemcpyAsync(out->top, out->wide, sizeof(out->top), cudaMemcpyDeviceToHost, stream));
+	}
 	float4 h_root[2];
 	BS_CHECK(cudaMemcpyAsync(h_root, d_root_box, sizeof(h_root), cudaMemcpyDeviceToHost, stream));
 	BS_CHECK(cudaEventRecord(ev1, stream));
@@ -491,7 +549,8 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 	out->max_leaf = st.max_leaf;
 	out->sah_cost = st.sah;
 	out->build_ms = ms;
-	out->device_bytes = (size_t) n_nodes * 64 + nt * 72 + nt * 48 + nt * 4;
+	out->n_wide = n_wide;
+	out->device_bytes = (size_t) n_nodes * 64 + (size_t) n_wide * 128 + nt * 72 + nt * 48 + nt * 4;
 	float rc[3], rh[3];
 	{
 		// same outward rounding as the device (centre in fp32, half extent padded by the centre's rounding error)
