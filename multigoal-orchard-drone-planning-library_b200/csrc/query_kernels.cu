@@ -272,13 +272,27 @@ __device__ __forceinline__ void emit_box(const SceneDev &sc, const QueueDev &Q, 
 
 __device__ __forceinline__ bool finite7(const double *p) { return isfinite(p[0] + p[1] + p[2] + p[3] + p[4] + p[5] + p[6]); }
 
-/// Whole-robot cull: does the sphere (base origin, rb.reach) miss the scene bounds?
-__device__ __forceinline__ bool robot_out_of_reach(const SceneDev &sc, const RobotDev &rb, D3 t) {
-	double dx = fmax(fabs(t.x - (sc.origin[0] + (double) sc.root_c[0])) - (double) sc.root_h[0], 0.0);
-	double dy = fmax(fabs(t.y - (sc.origin[1] + (double) sc.root_c[1])) - (double) sc.root_h[1], 0.0);
-	double dz = fmax(fabs(t.z - (sc.origin[2] + (double) sc.root_c[2])) - (double) sc.root_h[2], 0.0);
-	double r = rb.reach + (double) sc.margin;
-	return !(dx * dx + dy * dy + dz * dz <= r * r);  // NaN counts as out of reach
+/// Whole-robot cull: does the sphere (base origin, rb.reach) miss the scene bounds — and, one level down, the boxes of
+/// all of the root's children?  (A tree's bounding box is mostly air around the trunk; the children's boxes are not.)
+__device__ __forceinline__ bool robot_out_of_reach(const SceneDev &sc, const RobotDev &rb, D3 t, bool one_level_down = true) {
+	const double px = t.x - sc.origin[0], py = t.y - sc.origin[1], pz = t.z - sc.origin[2];
+	double dx = fmax(fabs(px - (double) sc.root_c[0]) - (double) sc.root_h[0], 0.0);
+	double dy = fmax(fabs(py - (double) sc.root_c[1]) - (double) sc.root_h[1], 0.0);
+	double dz = fmax(fabs(pz - (double) sc.root_c[2]) - (double) sc.root_h[2], 0.0);
+	const double r = rb.reach + (double) sc.margin;
+	if (!(dx * dx + dy * dy + dz * dz <= r * r)) return true;  // NaN counts as out of reach
+	if (!sc.wide || !one_level_down) return false;
+	const float fx = (float) px, fy = (float) py, fz = (float) pz, fr = (float) r + 1e-4f;  // fp32 is enough one level down: conservative radius
+	bool near = false;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		if (__float_as_int(sc.top[2 * k].w) == WIDE_EMPTY) continue;
+		const float ex = fmaxf(fabsf(fx - sc.top[2 * k].x) - sc.top[2 * k + 1].x, 0.f);
+		const float ey = fmaxf(fabsf(fy - sc.top[2 * k].y) - sc.top[2 * k + 1].y, 0.f);
+		const float ez = fmaxf(fabsf(fz - sc.top[2 * k].z) - sc.top[2 * k + 1].z, 0.f);
+		near |= ex * ex + ey * ey + ez * ez <= fr * fr;
+	}
+	return !near;
 }
 
 /// FK for the links that carry collision geometry + one emit per box (check_robot_collision,
@@ -494,7 +508,7 @@ __device__ __forceinline__ void expand_motion_step(const SceneDev &sc, const Rob
 	// for n_steps == 0 the reference evaluates t = 0/0; here the start state is checked once.
 	const double t = n_steps ? (double) step / (double) n_steps : 0.0;
 	const D3 tr{(1.0 - t) * a[0] + t * b[0], (1.0 - t) * a[1] + t * b[1], (1.0 - t) * a[2] + t * b[2]};
-	if (robot_out_of_reach(sc, rb, tr)) return;
+	if (robot_out_of_reach(sc, rb, tr, false)) return;
 	Pose base{tr, Q4{a[3], a[4], a[5], a[6]}};
 	double jv[MGODPL_MAX_JOINT_VALUES];
 	if (n_steps) {
@@ -600,7 +614,7 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 				// both ends with the exact test stage A2 applies (same t, same lerp), so A2 mostly sees real survivors.
 				auto outside = [&](unsigned s) {
 					const double t = n_steps ? (double) s / (double) n_steps : 0.0;
-					return robot_out_of_reach(sc, rb, D3{(1.0 - t) * ar[0] + t * br[0], (1.0 - t) * ar[1] + t * br[1], (1.0 - t) * ar[2] + t * br[2]});
+					return robot_out_of_reach(sc, rb, D3{(1.0 - t) * ar[0] + t * br[0], (1.0 - t) * ar[1] + t * br[1], (1.0 - t) * ar[2] + t * br[2]}, false);
 				};
 				for (int guard = 0; guard < trim && s_lo < s_hi && outside(s_lo); ++guard) ++s_lo;
 				for (int guard = 0; guard < trim && s_hi > s_lo && outside(s_hi); ++guard) --s_hi;
