@@ -206,6 +206,40 @@ def test_motion_symmetry_property_at_scale(gpu, oracle, env):
     assert (f["toi"][both] >= 0).all() and (f["toi"][both] <= 1).all()
 
 
+def test_engineered_collisions_are_found(gpu, oracle, env):
+    """The reference's legacy engineered_collision test (test/planning/MyCollisionEnvTest.cpp:149-219), for the sampled checker:
+    move a motion so that, at one of its sampled steps, a point inside a random link box lands on a random point of a
+    random triangle.  The motion must be reported colliding, no later than that step."""
+    rng = np.random.default_rng(17)
+    orb, drb, mesh = env["orb"], env["drb"], env["mesh"]
+    boxes, _ = orb.describe()
+    states = oracle.gen_uniform_states(orb, 400, seed=23, h_range=3.0, v_range=4.0)
+    a, b = states[:200].copy(), states[200:].copy()
+    t_contact = np.zeros(200)
+    for i in range(200):
+        n = oracle.motion_steps(oracle.distance(a[i], b[i]))
+        step = int(rng.integers(0, n + 1))
+        t = step / n
+        mid = oracle.interpolate(a[i], b[i], t)
+        bx = boxes[rng.integers(0, len(boxes))]
+        link_tf = orb.fk(mid)[int(bx[0])]
+        local = (rng.uniform(-0.4, 0.4, 3)) * bx[1:4]                      # strictly inside the box
+        p_box = oracle.tf_then(oracle.tf_then(link_tf, bx[4:11]), np.r_[local, 0, 0, 0, 1])[:3]
+        tri = mesh.vertices[mesh.triangles[rng.integers(0, len(mesh.triangles))]]
+        u, v = rng.uniform(0, 1, 2)
+        if u + v > 1:
+            u, v = 1 - u, 1 - v
+        shift = tri[0] + u * (tri[1] - tri[0]) + v * (tri[2] - tri[0]) - p_box
+        a[i, :3] += shift
+        b[i, :3] += shift
+        t_contact[i] = t
+    res = gpu.check_motions(env["dscene"], drb, a, b)
+    assert res["hit"].all()
+    assert (res["toi"] <= t_contact + 1e-12).all()
+    want = env["oscene"].check_motions(orb, a, b)
+    assert np.array_equal(res["hit"], want["hit"]) and np.allclose(res["toi"], want["toi"], rtol=0, atol=0)
+
+
 def test_goal_sampling_device_rng_and_distance(gpu, oracle, env):
     t = env["tree"].fruit_centers[:8]
     a = gpu.sample_goals(env["dscene"], env["drb"], t, 500, seed=1, want_states=True)

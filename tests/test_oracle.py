@@ -233,6 +233,34 @@ def test_oracle_matches_reference_sources_live(oracle, mg):
 
 
 # ---- properties inherited from the reference's legacy tests ------------------------------------------------------------
+def test_engineered_collisions_are_found_by_the_oracle(oracle, mg):
+    """Legacy engineered_collision test (test/planning/MyCollisionEnvTest.cpp:149-219) restated for the sampled checker — the
+    same construction the GPU suite runs (tests/test_gpu_edge_cases.py)."""
+    tree = mg.scenes.make_tree(seed=4, trunk_triangles=1500, leaf_triangles=1500, n_fruit=2)
+    mesh = tree.collision_mesh(True)
+    orb, osc = oracle.Robot(0.75, (0,)), oracle.Scene(mesh.vertices, mesh.triangles)
+    rng = np.random.default_rng(17)
+    boxes, _ = orb.describe()
+    states = oracle.gen_uniform_states(orb, 120, seed=23, h_range=3.0, v_range=4.0)
+    a, b, tc = states[:60].copy(), states[60:].copy(), np.zeros(60)
+    for i in range(60):
+        n = oracle.motion_steps(oracle.distance(a[i], b[i]))
+        t = int(rng.integers(0, n + 1)) / n
+        bx = boxes[rng.integers(0, len(boxes))]
+        link_tf = orb.fk(oracle.interpolate(a[i], b[i], t))[int(bx[0])]
+        p_box = oracle.tf_then(oracle.tf_then(link_tf, bx[4:11]), np.r_[rng.uniform(-0.4, 0.4, 3) * bx[1:4], 0, 0, 0, 1])[:3]
+        tri = mesh.vertices[mesh.triangles[rng.integers(0, len(mesh.triangles))]]
+        u, v = rng.uniform(0, 1, 2)
+        if u + v > 1:
+            u, v = 1 - u, 1 - v
+        shift = tri[0] + u * (tri[1] - tri[0]) + v * (tri[2] - tri[0]) - p_box
+        a[i, :3] += shift
+        b[i, :3] += shift
+        tc[i] = t
+    res = osc.check_motions(orb, a, b)
+    assert res["hit"].all() and (res["toi"] <= tc + 1e-12).all()
+
+
 def test_motion_check_symmetry(oracle, mg):
     """check(s1, s2) == check(s2, s1) (src_old/test/collision_checking_test.cpp:30-57)."""
     tree = mg.scenes.make_tree(seed=4, trunk_triangles=3000, leaf_triangles=0, n_fruit=2)
