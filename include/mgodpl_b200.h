@@ -183,6 +183,11 @@ int mgodpl_knn(const double *states, size_t n, size_t stride, int32_t n_joint_va
 			   double *dist, void *stream);
 int mgodpl_knn_device(const double *d_states, size_t n, size_t stride, int32_t n_joint_values, int32_t k, int32_t causal,
 					  int32_t *d_idx, double *d_dist, void *stream);
+/* The same query for states that are not part of the index: goal samples and the start state are connected to their k
+ * nearest *infrastructure* nodes but never inserted into the GNAT (sample_and_connect_goal_states,
+ * src/planning/tsp_over_prm.cpp:297-344; :621-629).  idx: n_queries x k indices into `database`. */
+int mgodpl_knn_query(const double *database, size_t n_database, const double *queries, size_t n_queries, size_t stride,
+					 int32_t n_joint_values, int32_t k, int32_t *idx, double *dist, void *stream);
 
 /* ---- shortest paths on the roadmap: runDijkstra (src/planning/tsp_over_prm.cpp:80-97, boost::dijkstra_shortest_paths on
  *      the undirected PRMGraph of tsp_over_prm.h:25-26) as calculate_goal_to_goal_paths calls it once per goal sample and

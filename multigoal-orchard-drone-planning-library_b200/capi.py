@@ -27,7 +27,7 @@ EXPORTS = [
     "mgodpl_scene_destroy", "mgodpl_scene_get_info", "mgodpl_scene_get_counters", "mgodpl_robot_create",
     "mgodpl_robot_destroy", "mgodpl_robot_n_variables", "mgodpl_forward_kinematics", "mgodpl_check_boxes",
     "mgodpl_check_states", "mgodpl_check_states_device", "mgodpl_check_motions", "mgodpl_check_motions_device",
-    "mgodpl_check_path", "mgodpl_sample_goals", "mgodpl_sample_goals_device", "mgodpl_knn", "mgodpl_knn_device",
+    "mgodpl_check_path", "mgodpl_sample_goals", "mgodpl_sample_goals_device", "mgodpl_knn", "mgodpl_knn_device", "mgodpl_knn_query",
     "mgodpl_roadmap_shortest_paths", "mgodpl_roadmap_shortest_paths_device", "mgodpl_mesh_components",
     "mgodpl_mesh_components_u64",
 ]
@@ -300,6 +300,17 @@ def knn(states, k: int, causal: bool = False, want_dist: bool = True, stream=Non
     dist = np.zeros((n, k)) if want_dist else None
     _check(lib().mgodpl_knn(_p(s), C.c_size_t(n), C.c_size_t(s.shape[1]), s.shape[1] - 7, k, int(causal), _p(idx, C.c_int32),
                             _p(dist), _stream(stream)))
+    return idx, dist
+
+
+def knn_query(database, queries, k: int, want_dist: bool = True, stream=None):
+    """(idx[n_q,k], dist[n_q,k]): the k nearest rows of `database` for every row of `queries` (equal_weights_distance)."""
+    db, q = _states2d(database), _states2d(queries)
+    assert db.shape[1] == q.shape[1]
+    idx = np.full((len(q), k), -1, np.int32)
+    dist = np.zeros((len(q), k)) if want_dist else None
+    _check(lib().mgodpl_knn_query(_p(db), C.c_size_t(len(db)), _p(q), C.c_size_t(len(q)), C.c_size_t(q.shape[1]), q.shape[1] - 7, k,
+                                  _p(idx, C.c_int32), _p(dist), _stream(stream)))
     return idx, dist
 
 

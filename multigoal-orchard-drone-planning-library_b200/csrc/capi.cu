@@ -871,6 +871,32 @@ int mgodpl_knn(const double *states, size_t n, size_t stride, int32_t js, int32_
 	return MGODPL_OK;
 }
 
+int mgodpl_knn_query(const double *database, size_t n_db, const double *queries, size_t n_q, size_t stride, int32_t js, int32_t k,
+					 int32_t *idx, double *dist, void *stream_) {
+	if (js < 0 || js > MGODPL_MAX_JOINT_VALUES || stride < (size_t) (7 + js)) return fail(MGODPL_E_INVALID_ARGUMENT, "bad state layout");
+	if (k < 1 || k > 32) return fail(MGODPL_E_INVALID_ARGUMENT, "k must be in 1..32");
+	if ((n_db && !database) || (n_q && (!queries || !idx))) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (n_db >= 0x7FFFFFFFull || n_q >= 0x7FFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "too many states");
+	if (int rc = require_device()) return rc;
+	if (!n_q) return MGODPL_OK;
+	cudaStream_t stream = (cudaStream_t) stream_;
+	double *d_db = nullptr, *d_q = nullptr, *d_d = nullptr;
+	int32_t *d_i = nullptr;
+	cudaError_t e = cudaMalloc((void **) &d_db, n_db * stride * 8 + 8);
+	if (e == cudaSuccess) e = cudaMalloc((void **) &d_q, n_q * stride * 8);
+	if (e == cudaSuccess) e = cudaMalloc((void **) &d_i, n_q * k * 4);
+	if (e == cudaSuccess && dist) e = cudaMalloc((void **) &d_d, n_q * k * 8);
+	if (e == cudaSuccess && n_db) e = cudaMemcpyAsync(d_db, database, n_db * stride * 8, cudaMemcpyHostToDevice, stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, queries, n_q * stride * 8, cudaMemcpyHostToDevice, stream);
+	if (e == cudaSuccess) e = launch_knn_query(d_db, n_db, d_q, n_q, stride, js, k, d_i, d_d, stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(idx, d_i, n_q * k * 4, cudaMemcpyDeviceToHost, stream);
+	if (e == cudaSuccess && dist) e = cudaMemcpyAsync(dist, d_d, n_q * k * 8, cudaMemcpyDeviceToHost, stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+	cudaFree(d_db), cudaFree(d_q), cudaFree(d_i), cudaFree(d_d);
+	if (e != cudaSuccess) return fail_cuda(e, "knn_query");
+	return MGODPL_OK;
+}
+
 // ---- roadmap shortest paths (runDijkstra per goal sample, tsp_over_prm.cpp:80-97 and :497-517, batched) ---------------------
 namespace {
 unsigned *pinned_flag() {

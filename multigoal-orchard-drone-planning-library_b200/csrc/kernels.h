@@ -34,6 +34,9 @@ cudaError_t launch_forward_kinematics(const RobotDev &rb, const double *d_states
 /// Exact k-NN over equal_weights_distance; causal != 0 restricts node i to neighbours j < i (incremental PRM insertion).
 cudaError_t launch_knn(const double *d_states, size_t n, size_t stride, int js, int k, int causal, int32_t *d_idx, double *d_dist,
 					   cudaStream_t stream);
+/// The same for n_q query states against a separate database of n_db states (both with the same row layout).
+cudaError_t launch_knn_query(const double *d_database, size_t n_db, const double *d_queries, size_t n_q, size_t stride, int js, int k,
+							 int32_t *d_idx, double *d_dist, cudaStream_t stream);
 
 /// Shortest paths from many sources at once over a CSR roadmap (both directions of every undirected edge present).
 /// d_dist / d_pred: n_sources x n, source-major; d_pred may be null.  Synchronises `stream` (convergence read-backs).

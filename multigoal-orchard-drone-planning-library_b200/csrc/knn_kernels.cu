@@ -13,8 +13,10 @@ constexpr int KNN_MAX_K = 32;
 constexpr int KNN_ROW_MAX = 7 + MGODPL_MAX_JOINT_VALUES;
 
 __global__ void __launch_bounds__(KNN_BLOCK)
-k_knn(const double *__restrict__ states, size_t n, size_t stride, int js, int k, int causal, int32_t *__restrict__ out_idx,
-	  double *__restrict__ out_dist) {
+k_knn(const double *__restrict__ states, size_t n, const double *__restrict__ cands, size_t n_cands, size_t stride, int js, int k,
+	  int mode, int32_t *__restrict__ out_idx, double *__restrict__ out_dist) {
+	// mode 0: every other row of the same array; 1 (causal): rows before the query; 2: a separate database, nothing excluded
+	const int causal = mode == 1;
 	extern __shared__ double tile[];  // KNN_BLOCK rows of (7 + js) doubles
 	const int row = 7 + js;
 	const size_t q = (size_t) blockIdx.x * KNN_BLOCK + threadIdx.x;
@@ -26,16 +28,16 @@ k_knn(const double *__restrict__ states, size_t n, size_t stride, int js, int k,
 	for (int i = 0; i < k; ++i) best_d[i] = __longlong_as_double(0x7ff0000000000000ll), best_i[i] = -1;
 	// causal: candidates j < q only; the block's last query bounds the tiles worth visiting
 	const size_t last_q = min(n, (size_t) (blockIdx.x + 1) * KNN_BLOCK);
-	const size_t n_cand = causal ? last_q : n;
+	const size_t n_cand = causal ? last_q : n_cands;
 	for (size_t t0 = 0; t0 < n_cand; t0 += KNN_BLOCK) {
 		__syncthreads();
 		const size_t tn = min((size_t) KNN_BLOCK, n_cand - t0);
-		for (size_t e = threadIdx.x; e < tn * row; e += KNN_BLOCK) tile[e] = __ldg(states + (t0 + e / row) * stride + e % row);
+		for (size_t e = threadIdx.x; e < tn * row; e += KNN_BLOCK) tile[e] = __ldg(cands + (t0 + e / row) * stride + e % row);
 		__syncthreads();
 		if (q >= n) continue;
 		for (size_t c = 0; c < tn; ++c) {
 			const size_t j = t0 + c;
-			if (causal ? j >= q : j == q) continue;
+			if (causal ? j >= q : (mode == 0 && j == q)) continue;
 			const double *o = tile + c * row;
 			// equal_weights_distance in the reference's operand order (distance.cpp:17-25, Quaternion.h:78-85)
 			const double dx = me[0] - o[0], dy = me[1] - o[1], dz = me[2] - o[2];
@@ -65,7 +67,18 @@ cudaError_t launch_knn(const double *d_states, size_t n, size_t stride, int js, 
 	if (!n) return cudaSuccess;
 	if (k < 1 || k > KNN_MAX_K) return cudaErrorInvalidValue;
 	const size_t smem = (size_t) KNN_BLOCK * (7 + js) * sizeof(double);
-	k_knn<<<(unsigned) ((n + KNN_BLOCK - 1) / KNN_BLOCK), KNN_BLOCK, smem, stream>>>(d_states, n, stride, js, k, causal, d_idx, d_dist);
+	k_knn<<<(unsigned) ((n + KNN_BLOCK - 1) / KNN_BLOCK), KNN_BLOCK, smem, stream>>>(d_states, n, d_states, n, stride, js, k, causal ? 1 : 0, d_idx,
+																					 d_dist);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_knn_query(const double *d_database, size_t n_db, const double *d_queries, size_t n_q, size_t stride, int js, int k,
+							 int32_t *d_idx, double *d_dist, cudaStream_t stream) {
+	if (!n_q) return cudaSuccess;
+	if (k < 1 || k > KNN_MAX_K) return cudaErrorInvalidValue;
+	const size_t smem = (size_t) KNN_BLOCK * (7 + js) * sizeof(double);
+	k_knn<<<(unsigned) ((n_q + KNN_BLOCK - 1) / KNN_BLOCK), KNN_BLOCK, smem, stream>>>(d_queries, n_q, d_database, n_db, stride, js, k, 2, d_idx,
+																					   d_dist);
 	return cudaGetLastError();
 }
 

@@ -502,6 +502,75 @@ int main() {
 		CHECK(threw);
 		fs::remove_all(dir);
 	}
+	// -- roadmap construction in batches == the reference's node-by-node loops (tsp_over_prm.cpp:33-66, 244-344, 411-483) ------
+	{
+		auto same_state = [](const RobotState &s, const orc::State &o) {
+			return s.base_tf.translation.x() == o.base.t.x && s.base_tf.translation.y() == o.base.t.y && s.base_tf.translation.z() == o.base.t.z &&
+				   s.base_tf.orientation.x == o.base.q.x && s.base_tf.orientation.y == o.base.q.y && s.base_tf.orientation.z == o.base.q.z &&
+				   s.base_tf.orientation.w == o.base.q.w && s.joint_values == o.joints;
+		};
+		struct Edge {
+			size_t u, v;
+			double w;
+		};
+		const size_t max_samples = 400, k = 5;
+		const GoalSampleParams gp{4, 3, 40};
+		std::vector<math::Vec3d> fruit;
+		random_numbers::RandomNumberGenerator frng(9);
+		for (int i = 0; i < 12; ++i) fruit.push_back({frng.uniformReal(-1.0, 1.0), frng.uniformReal(-1.0, 1.0), frng.uniformReal(0.8, 2.2)});
+		// the reference, one node at a time, with the oracle as state / motion check and an exhaustive nearest-neighbour search
+		orc::Rng orng(31);
+		std::vector<orc::State> onodes;
+		std::vector<Edge> oedges;
+		size_t n_infra = 0;
+		auto connect = [&](const orc::State &s, size_t kk) {
+			std::vector<std::pair<double, size_t>> d;
+			for (size_t j = 0; j < n_infra; ++j) d.push_back({orc::equal_weights_distance(s, onodes[j]), j});
+			std::stable_sort(d.begin(), d.end(), [](auto &x, auto &y) { return x.first < y.first; });
+			const size_t me = onodes.size();
+			for (size_t q = 0; q < std::min(kk, d.size()); ++q)
+				if (!orc::check_motion_collides(orobot, oscene, onodes[d[q].second], s).hit) oedges.push_back({me, d[q].second, d[q].first});
+			onodes.push_back(s);
+		};
+		for (size_t i = 0; i < max_samples; ++i) {
+			const orc::State s = orc::generate_uniform_random_state(orobot, orng, 2.0, 3.0);
+			if (orc::check_robot_collision(orobot, oscene, s)) continue;
+			connect(s, k);
+			n_infra = onodes.size();  // infrastructure nodes join the index
+		}
+		std::vector<size_t> want_groups(fruit.size(), 0);
+		const int ofb = orobot.find_link("flying_base"), oee = orobot.find_link("end_effector");
+		for (size_t g = 0; g < fruit.size(); ++g)
+			for (size_t attempt = 0; attempt < gp.max_attempts && want_groups[g] < gp.max_valid_samples; ++attempt) {
+				orc::State s = orc::gen_goal_state_uniform(orng, {fruit[g].x(), fruit[g].y(), fruit[g].z()}, 0.0, orobot, ofb, oee);
+				if (orc::check_robot_collision(orobot, oscene, s)) continue;
+				s.joints.resize(onodes[0].joints.size(), 0.0);  // defined stand-in for the reference's out-of-bounds read (see prm.hpp)
+				connect(s, gp.k_neighbors);  // goal samples are not added to the index
+				++want_groups[g];
+			}
+		// the facade: a handful of GPU calls
+		random_numbers::RandomNumberGenerator rng(31);
+		PRM prm = build_infrastructure_roadmap(robot, scene, rng, max_samples, k, 2.0, 3.0);
+		CHECK(prm.n_infrastructure == n_infra && prm.graph.num_vertices() == n_infra);
+		const auto [goal_nodes, group_sizes] = sample_goal_states(fruit, prm, gp, robot, scene, rng);
+		CHECK(group_sizes == want_groups && prm.graph.num_vertices() == onodes.size());
+		CHECK(rng.uniformReal(0, 1) == orng.uniform_real(0, 1));
+		size_t same_vertices = 0, same_edges = 0, n_goals = 0;
+		for (size_t v = 0; v < std::min(onodes.size(), prm.graph.num_vertices()); ++v) same_vertices += same_state(prm.graph[v], onodes[v]);
+		for (size_t e = 0; e < std::min(oedges.size(), prm.graph.num_edges()); ++e)
+			same_edges += prm.graph.edges[2 * e] == oedges[e].u && prm.graph.edges[2 * e + 1] == oedges[e].v &&
+						  std::fabs(prm.graph.weights[e] - oedges[e].w) < 1e-12;  // device vs host libm: last-ulp differences in acos
+		for (size_t g: group_sizes) n_goals += g;
+		std::printf("roadmap construction: %zu infrastructure + %zu goal vertices, %zu edges (reference loop: %zu), %zu identical\n", n_infra, n_goals,
+					prm.graph.num_edges(), oedges.size(), same_edges);
+		CHECK(same_vertices == onodes.size() && prm.graph.num_edges() == oedges.size() && same_edges == oedges.size());
+		CHECK(goal_nodes.size() == n_goals && n_goals > 0 && (goal_nodes.empty() || goal_nodes.front() == n_infra));
+		// the start state joins like a goal sample (tsp_over_prm.cpp:621-629); then the planner's shortest-path tables come from one call
+		const auto start = add_and_connect_roadmap_node(base_at(1.9, 1.9, 2.5), prm, k, robot, scene);
+		CHECK(start == onodes.size());
+		const GoalToGoalPathResults g2g = calculate_goal_to_goal_paths(prm.graph, goal_nodes);
+		CHECK(g2g.distance_lookup.size() == goal_nodes.size() && g2g.start_to_goals_distances.size() == prm.graph.num_vertices());
+	}
 	// -- error vocabulary -------------------------------------------------------------------------------------------------------
 	{
 		robot_model::RobotModel bad;

@@ -278,6 +278,24 @@ def test_knn_matches_exhaustive_oracle(gpu, oracle, env, causal):
         assert (idx < np.arange(700)[:, None]).all()
 
 
+def test_knn_query_against_a_separate_database(gpu, oracle, env):
+    """Goal samples / the start state look up their nearest *infrastructure* nodes without being part of the index
+    (tsp_over_prm.cpp:297-344): exhaustive search with the oracle's equal_weights_distance."""
+    orb = env["orb"]
+    db = oracle.gen_uniform_states(orb, 300, seed=5)
+    qs = oracle.gen_uniform_states(orb, 40, seed=6)
+    idx, dist = gpu.capi.knn_query(db, qs, 7)
+    for i, q in enumerate(qs):
+        d = np.array([oracle.distance(q, x) for x in db])
+        order = np.argsort(d, kind="stable")[:7]
+        assert np.array_equal(idx[i], order) and np.allclose(dist[i], d[order], rtol=0, atol=1e-12)  # device acos: last ulp
+    # fewer database rows than k: padded with -1 / NaN; an empty database gives only padding
+    idx, dist = gpu.capi.knn_query(db[:3], qs[:2], 5)
+    assert (idx[:, 3:] == -1).all() and np.isnan(dist[:, 3:]).all() and (idx[:, :3] >= 0).all()
+    idx, _ = gpu.capi.knn_query(db[:0], qs[:2], 2)
+    assert (idx == -1).all()
+
+
 def test_prm_edge_validation_pipeline(gpu, oracle, env):
     """BASELINE config 4 in miniature: sample nodes -> state filter -> causal k-NN -> one batch of edge motions."""
     st = oracle.gen_uniform_states(env["orb"], 1500, seed=77, h_range=3.0, v_range=4.0)
