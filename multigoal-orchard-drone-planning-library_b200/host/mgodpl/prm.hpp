@@ -5,6 +5,7 @@
 //   sample_and_connect_goal_states                        src/planning/tsp_over_prm.cpp:297-344
 //   build_infrastructure_roadmap                          src/planning/tsp_over_prm.cpp:411-429
 //   sample_goal_states                                    src/planning/tsp_over_prm.cpp:447-483
+//   construct_final_path                                  src/planning/tsp_over_prm.cpp:189-234
 // The reference grows the roadmap one node at a time: sample, check the state, ask the GNAT for the k nearest
 // *infrastructure* nodes, check k motions, insert.  None of the random draws depends on a collision result (except the
 // early stop of goal sampling, handled by drawing ahead on a copy of the generator), and the k nearest nodes of node i
@@ -12,6 +13,7 @@
 // edge, comes out of a handful of batched GPU calls.  The GNAT is replaced by the exact k-NN kernels (same answers, ties
 // aside); the nodes that take part in nearest-neighbour queries are the first `n_infrastructure` vertices of the graph.
 #pragma once
+#include "local_optimization.hpp"
 #include "roadmap.hpp"
 #include "sampling.hpp"
 
@@ -137,6 +139,36 @@ inline std::pair<std::vector<PRMGraph::vertex_descriptor>, std::vector<size_t>> 
 		for (size_t a = 0; a < used; ++a) (void) genGoalStateUniform(rng, fruit_positions[g], robot, base_link, end_effector_link);
 	}
 	return {add_and_connect_roadmap_nodes(valid, prm, params.k_neighbors, robot, scene), group_sizes};
+}
+
+/// construct_final_path (tsp_over_prm.cpp:189-234): the path from the start node through the goal samples of `tour` (indices
+/// into goal_nodes, in visiting order — the reference gets it from its OR-Tools TSP, pick_visitation_order :156-175, which is
+/// outside this library), each leg retraced through the predecessor tables and handed to `optimize_segment`.
+inline RobotPath construct_final_path(const PRMGraph &graph, const std::vector<std::vector<PRMGraph::vertex_descriptor>> &predecessor_lookup,
+									  const std::vector<PRMGraph::vertex_descriptor> &start_to_goals_predecessors,
+									  const std::vector<PRMGraph::vertex_descriptor> &goal_nodes, const std::vector<size_t> &tour,
+									  const std::function<bool(RobotPath &)> &optimize_segment) {
+	RobotPath path;
+	if (tour.empty()) return path;
+	RobotPath initial_path = retrace_path(graph, start_to_goals_predecessors, goal_nodes[tour[0]]);
+	optimize_segment(initial_path);
+	path.append(initial_path);
+	for (size_t i = 1; i < tour.size(); ++i) {
+		RobotPath goal_to_goal_path = retrace_path(graph, predecessor_lookup[tour[i - 1]], goal_nodes[tour[i]]);
+		optimize_segment(goal_to_goal_path);
+		path.append(goal_to_goal_path);
+	}
+	return path;
+}
+
+/// The `optimize_path_segment` closure of plan_path_tsp_over_prm (tsp_over_prm.cpp:594-612) on the batched shortcutting
+/// driver: 100 x tryShortcuttingRandomlyGlobally per leg, same path and generator state, a few GPU calls.
+inline std::function<bool(RobotPath &)> optimize_path_segment_fn(const robot_model::RobotModel &robot, const gpu::Scene &scene,
+																  random_numbers::RandomNumberGenerator &rng, size_t iterations = 100) {
+	return [&robot, &scene, &rng, iterations](RobotPath &path) {
+		if (path.states.size() > 2) shortcut_path_globally(robot, scene, path, rng, iterations);
+		return false;  // the reference's lambda never sets its `successful` flag either (tsp_over_prm.cpp:595-611)
+	};
 }
 
 }  // namespace mgodpl

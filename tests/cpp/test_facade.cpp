@@ -570,6 +570,31 @@ int main() {
 		CHECK(start == onodes.size());
 		const GoalToGoalPathResults g2g = calculate_goal_to_goal_paths(prm.graph, goal_nodes);
 		CHECK(g2g.distance_lookup.size() == goal_nodes.size() && g2g.start_to_goals_distances.size() == prm.graph.num_vertices());
+		// construct_final_path (tsp_over_prm.cpp:189-234) over a fixed visiting order (the TSP itself is OR-Tools, out of scope):
+		// legs retraced and shortcut on the GPU == the oracle's Dijkstra, retrace and sequential shortcutting loop
+		std::vector<size_t> tour;
+		for (size_t i = 0; i < goal_nodes.size(); i += 3) tour.push_back(i);
+		const RobotPath final_path = construct_final_path(prm.graph, g2g.predecessor_lookup, g2g.start_to_goals_predecessors, goal_nodes, tour,
+														  optimize_path_segment_fn(robot, scene, rng, 40));
+		orc::Roadmap ograph(prm.graph.num_vertices());
+		for (size_t e = 0; e < prm.graph.num_edges(); ++e) ograph.add_edge(prm.graph.edges[2 * e], prm.graph.edges[2 * e + 1], prm.graph.weights[e]);
+		const orc::MotionFn omotion = [&](const orc::State &a, const orc::State &b) { return orc::check_motion_collides(orobot, oscene, a, b).hit; };
+		onodes.push_back(to_orc(prm.graph[start]));
+		orc::Path want_path;
+		for (size_t i = 0; i < tour.size(); ++i) {
+			std::vector<double> od;
+			std::vector<uint32_t> op;
+			orc::run_dijkstra(ograph, i ? (uint32_t) goal_nodes[tour[i - 1]] : 0u, od, op);
+			orc::Path leg;
+			for (uint32_t v: orc::retrace_path(op, (uint32_t) goal_nodes[tour[i]])) leg.push_back(onodes[v]);
+			if (leg.size() > 2) orc::optimize_path_segment(leg, omotion, orng, 40);
+			want_path.insert(want_path.end(), leg.begin(), leg.end());
+		}
+		bool same = final_path.states.size() == want_path.size();
+		for (size_t i = 0; same && i < want_path.size(); ++i) same = same_state(final_path.states[i], want_path[i]);
+		std::printf("final path: %zu legs, %zu waypoints (reference pipeline: %zu)\n", tour.size(), final_path.states.size(), want_path.size());
+		CHECK(same && !want_path.empty());
+		CHECK(rng.uniformReal(0, 1) == orng.uniform_real(0, 1));
 	}
 	// -- error vocabulary -------------------------------------------------------------------------------------------------------
 	{
