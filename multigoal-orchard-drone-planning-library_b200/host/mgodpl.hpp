@@ -6,5 +6,6 @@
 #include "mgodpl/prm.hpp"
 #include "mgodpl/roadmap.hpp"
 #include "mgodpl/robot_model.hpp"
+#include "mgodpl/rrt.hpp"
 #include "mgodpl/sampling.hpp"
 #include "mgodpl/tree_meshes.hpp"

@@ -596,6 +596,45 @@ int main() {
 		CHECK(same && !want_path.empty());
 		CHECK(rng.uniformReal(0, 1) == orng.uniform_real(0, 1));
 	}
+	// -- RRT (rrt.cppm:82-188): the windowed driver grows the tree of the sequential loop ---------------------------------
+	{
+		const RobotState root = base_at(1.9, 1.9, 2.5);
+		const auto sampler = [&](random_numbers::RandomNumberGenerator &g) { return generateUniformRandomState(robot, g, 2.0, 3.0); };
+		const DistanceFn dist = [](const RobotState &a, const RobotState &b) { return equal_weights_distance(a, b); };
+		for (size_t stop_at: {size_t(0), size_t(45)}) {
+			// reference loop with the oracle as state / motion check
+			random_numbers::RandomNumberGenerator rng_seq(77);
+			std::vector<RRTNode> want;
+			rrt(root, [&] { return sampler(rng_seq); }, [&](const RobotState &s) { return orc::check_robot_collision(orobot, oscene, to_orc(s)); },
+				[&](const RobotState &a, const RobotState &b) { return orc::check_motion_collides(orobot, oscene, to_orc(a), to_orc(b)).hit; }, dist, 400,
+				[&](const std::vector<RRTNode> &nodes) {
+					want = nodes;
+					return stop_at && nodes.size() >= stop_at;
+				});
+			random_numbers::RandomNumberGenerator rng_b(77);
+			RrtStats st;
+			const std::vector<RRTNode> got = rrt_batched(root, sampler, rng_b, robot, scene, 400,
+														 [&](const std::vector<RRTNode> &nodes) { return stop_at && nodes.size() >= stop_at; }, 64, &st);
+			bool same = got.size() == want.size();
+			for (size_t i = 0; same && i < want.size(); ++i) same = got[i].state == want[i].state && got[i].parent_index == want[i].parent_index;
+			std::printf("rrt: %zu nodes after %zu samples, %zu GPU calls, %zu re-speculated (sequential loop: %zu nodes)\n", got.size(), st.iterations,
+						st.gpu_calls, st.respeculated, want.size());
+			CHECK(same && want.size() > 20);
+			CHECK(rng_b.uniformReal(0, 1) == rng_seq.uniformReal(0, 1));
+			CHECK(st.gpu_calls < st.iterations);  // the sequential loop makes up to two calls per sample
+			if (stop_at) {
+				const RobotPath back = retrace(got);
+				CHECK(back.states.front() == got.back().state && back.states.back() == root);
+			}
+		}
+		// the closure-based rrt on the GPU closures and rrt_path_to_acceptable
+		const CollisionEnvironment env{robot, scene};
+		const CollisionFunctions fns = collision_functions_in_environment(env);
+		random_numbers::RandomNumberGenerator rng_c(77);
+		const auto path = rrt_path_to_acceptable(root, [&] { return sampler(rng_c); }, fns.state_collides, fns.motion_collides, dist, 60,
+												 [](const RobotState &s) { return s.base_tf.translation.z() < 0.6; });
+		CHECK(!path || (path->states.back() == root && path->states.front().base_tf.translation.z() < 0.6));
+	}
 	// -- error vocabulary -------------------------------------------------------------------------------------------------------
 	{
 		robot_model::RobotModel bad;
