@@ -8,4 +8,5 @@
 #include "mgodpl/robot_model.hpp"
 #include "mgodpl/rrt.hpp"
 #include "mgodpl/sampling.hpp"
+#include "mgodpl/scanning_motions.hpp"
 #include "mgodpl/tree_meshes.hpp"

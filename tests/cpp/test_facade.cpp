@@ -635,6 +635,33 @@ int main() {
 												 [](const RobotState &s) { return s.base_tf.translation.z() < 0.6; });
 		CHECK(!path || (path->states.back() == root && path->states.front().base_tf.translation.z() < 0.6));
 	}
+	// -- scanning motions (scanning_motions.cpp:15-97): one batch per arc == the reference's check-and-stop loop ---------
+	{
+		size_t arcs = 0, states_total = 0, cut_short = 0;
+		random_numbers::RandomNumberGenerator srng(3);
+		for (int trial = 0; trial < 12; ++trial) {
+			const math::Vec3d fruit{srng.uniformReal(-0.9, 0.9), srng.uniformReal(-0.9, 0.9), srng.uniformReal(0.9, 2.0)};
+			const double lon = srng.uniformReal(-M_PI, M_PI), lat = srng.uniformReal(-0.3, 0.6), scan_distance = 0.4;
+			for (Direction dir: {Direction::LEFT, Direction::RIGHT}) {
+				const RobotPath got = generateSidewaysScanningMotion(robot, scene, fruit, lon, lat, scan_distance, dir);
+				// reference loop with the oracle as collision check
+				std::vector<RobotState> want;
+				const double step = (dir == Direction::LEFT ? -1.0 : 1.0) * M_PI / 32.0;
+				for (int i = 1; i < 32; ++i) {
+					const math::Vec3d rel = spherical_geometry::RelativeVertex{lon + i * step, lat}.to_cartesian();
+					const RobotState st = fromEndEffectorAndVector(robot, fruit + rel.normalized() * scan_distance, rel);
+					if (orc::check_robot_collision(orobot, oscene, to_orc(st))) break;
+					want.push_back(st);
+				}
+				CHECK(got.states == want);
+				++arcs, states_total += want.size(), cut_short += want.size() < 31;
+			}
+			const RobotPath both = createLeftRightScanningMotion(robot, scene, fruit, lon, lat, scan_distance);
+			CHECK(both.states.size() % 2 == 0);
+		}
+		std::printf("scanning motions: %zu arcs, %zu states kept, %zu arcs cut at a collision\n", arcs, states_total, cut_short);
+		CHECK(cut_short > 0 && cut_short < arcs);
+	}
 	// -- error vocabulary -------------------------------------------------------------------------------------------------------
 	{
 		robot_model::RobotModel bad;
