@@ -21,13 +21,13 @@ struct RelativeVertex {
 /// scanning_motions.cpp:15-56.
 inline RobotPath generateSidewaysScanningMotion(const robot_model::RobotModel &robot, const gpu::Scene &treeTrunkObject, const math::Vec3d &fruitCenter,
 												double initialLongitude, double initialLatitude, double scanDistance, Direction direction) {
-	const int MAX_ITERATIONS = 32;
-	double STEP_SIZE = M_PI / (double) MAX_ITERATIONS;
-	if (direction == Direction::LEFT) STEP_SIZE = -STEP_SIZE;
+	constexpr int n_steps = 32;  // the arc spans half a turn in 32 steps; step 0 (the start itself) is not part of the motion
+	const double step = (direction == Direction::LEFT ? -M_PI : M_PI) / n_steps;
 	std::vector<RobotState> arc;
-	for (int i = 1; i < MAX_ITERATIONS; ++i) {
-		const math::Vec3d relativeVertex = spherical_geometry::RelativeVertex{initialLongitude + i * STEP_SIZE, initialLatitude}.to_cartesian();
-		arc.push_back(fromEndEffectorAndVector(robot, fruitCenter + relativeVertex.normalized() * scanDistance, relativeVertex));
+	arc.reserve(n_steps - 1);
+	for (int i = 1; i < n_steps; ++i) {
+		const math::Vec3d outward = spherical_geometry::RelativeVertex{initialLongitude + i * step, initialLatitude}.to_cartesian();
+		arc.push_back(fromEndEffectorAndVector(robot, fruitCenter + outward.normalized() * scanDistance, outward));
 	}
 	const std::vector<uint32_t> collides = check_states(robot, treeTrunkObject, arc);
 	size_t keep = 0;

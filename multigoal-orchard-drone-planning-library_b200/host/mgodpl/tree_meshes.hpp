@@ -345,12 +345,9 @@ struct SimplifiedOrchard {
 	std::vector<std::pair<math::Vec3d, TreeMeshes>> trees;
 };
 inline SimplifiedOrchard makeSingleRowOrchard(std::vector<TreeMeshes> &tree_models) {
-	double x_displacement = tree_models.size() * 2.0 * -0.5;
 	SimplifiedOrchard orchard;
-	for (const auto &model: tree_models) {
-		orchard.trees.push_back({{x_displacement, 0.0, 0.0}, model});
-		x_displacement += 2.0;
-	}
+	const double first_x = -1.0 * (double) tree_models.size();  // n trees, 2 m apart, starting n metres left of the origin
+	for (size_t i = 0; i < tree_models.size(); ++i) orchard.trees.push_back({{first_x + 2.0 * (double) i, 0.0, 0.0}, tree_models[i]});
 	return orchard;
 }
 
