@@ -56,6 +56,10 @@ def test_overflow_and_no_prefilter_paths_agree_with_the_fast_path(gpu):
         "no fp32 pre-filter (every leaf triangle through the fp64 test)": {"MGODPL_NO_PREFILTER": "1"},
         "refill / leaf batching extremes": {"MGODPL_REFILL_MIN": "1", "MGODPL_LEAF_MIN": "32"},
         "high-occupancy traversal variant": {"MGODPL_TRAVERSE_BLOCKS": "8", "MGODPL_REFILL_MIN": "32", "MGODPL_LEAF_MIN": "1"},
+        "binary records only (no 4-wide fold, no root-record cull)": {"MGODPL_WIDE_BVH": "0"},
+        "binary records with tiny lists": {"MGODPL_WIDE_BVH": "0", "MGODPL_QUEUE_MAX_ITEMS": "64", "MGODPL_SURVIVOR_MAX_ENTRIES": "128"},
+        "no range trimming / deep trimming": {"MGODPL_TRIM": "0"},
+        "fixed head of 4 steps": {"MGODPL_HEAD_STEPS": "4"},
     }
     for name, env in variants.items():
         got = run_variant(env)
