@@ -82,6 +82,7 @@ typedef struct mgodpl_scene_opts {
 } mgodpl_scene_opts;
 #define MGODPL_SCENE_COUNTERS 1u   /* keep device-side work counters (states, nodes visited, leaf tests) */
 #define MGODPL_SCENE_NO_REFINE 2u  /* plain Morton LBVH, skip the SAH refinement passes */
+#define MGODPL_SCENE_NO_CLEARANCE_GRID 4u /* skip the clearance grid (the one-byte-per-cell "certainly free" broad phase) */
 
 typedef struct mgodpl_scene_info {
 	uint64_t n_triangles, n_nodes, n_leaves, device_bytes;
@@ -91,6 +92,8 @@ typedef struct mgodpl_scene_info {
 	uint32_t max_depth, max_leaf_size;
 	uint64_t n_wide_nodes;  /* 128-byte 4-wide records the traversal walks (0: it walks the n_nodes 64-byte binary records) */
 	uint64_t traversal_bytes; /* bytes one pass over the traversal's own data reads: its records + both triangle copies */
+	uint64_t clearance_cells; /* cells of the clearance grid (one byte each), 0 = none */
+	double clearance_cell_size, clearance_build_ms;
 } mgodpl_scene_info;
 
 /* Deterministic cost counters: the reference's own observability hook on this path is an invocation counter

@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libmgodpl_b200.so")
 
 MAX_LINKS, MAX_BOXES, MAX_JOINT_VALUES = 12, 12, 16
-SCENE_COUNTERS, SCENE_NO_REFINE = 1, 2
+SCENE_COUNTERS, SCENE_NO_REFINE, SCENE_NO_CLEARANCE_GRID = 1, 2, 4
 JOINT_REVOLUTE, JOINT_FIXED = 0, 1
 SHAPE_BOX, SHAPE_MESH = 0, 1
 
@@ -58,7 +58,8 @@ class SceneInfo(C.Structure):
     _fields_ = [("n_triangles", C.c_uint64), ("n_nodes", C.c_uint64), ("n_leaves", C.c_uint64),
                 ("device_bytes", C.c_uint64), ("bounds_lo", C.c_double * 3), ("bounds_hi", C.c_double * 3),
                 ("build_ms", C.c_double), ("sah_cost", C.c_double), ("max_depth", C.c_uint32),
-                ("max_leaf_size", C.c_uint32), ("n_wide_nodes", C.c_uint64), ("traversal_bytes", C.c_uint64)]
+                ("max_leaf_size", C.c_uint32), ("n_wide_nodes", C.c_uint64), ("traversal_bytes", C.c_uint64),
+                ("clearance_cells", C.c_uint64), ("clearance_cell_size", C.c_double), ("clearance_build_ms", C.c_double)]
 
 
 class Counters(C.Structure):
@@ -124,10 +125,12 @@ def unpack_bits(words: np.ndarray, n: int) -> np.ndarray:
 class Scene:
     """Device-resident BVH over a triangle soup; stands where ``fcl::CollisionObjectd`` stood."""
 
-    def __init__(self, vertices, triangles, counters: bool = False, max_leaf_size: int = 0, refine: bool = True):
+    def __init__(self, vertices, triangles, counters: bool = False, max_leaf_size: int = 0, refine: bool = True,
+                 clearance_grid: bool = True):
         v = _f64(vertices).reshape(-1, 3)
         t = np.ascontiguousarray(triangles)
-        opts = SceneOpts((SCENE_COUNTERS if counters else 0) | (0 if refine else SCENE_NO_REFINE), max_leaf_size)
+        opts = SceneOpts((SCENE_COUNTERS if counters else 0) | (0 if refine else SCENE_NO_REFINE) |
+                         (0 if clearance_grid else SCENE_NO_CLEARANCE_GRID), max_leaf_size)
         self.h = C.c_void_p()
         if t.dtype == np.uint64:
             t = t.reshape(-1, 3)

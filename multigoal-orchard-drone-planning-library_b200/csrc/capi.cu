@@ -111,8 +111,15 @@ struct WorkspacePool {
 		return w;
 	}
 	void release(std::unique_ptr<Workspace> w) {
-		std::lock_guard<std::mutex> g(mu);
-		free_list.push_back(std::move(w));
+		// keep a few workspaces of ordinary size around; a very large one (or a fifth idle one) goes back to the driver
+		// instead of pinning device memory for the life of the handle
+		std::unique_lock<std::mutex> g(mu);
+		if (free_list.size() < 4 && w->dev_cap <= ((size_t) 1 << 30)) {
+			free_list.push_back(std::move(w));
+			return;
+		}
+		g.unlock();
+		w.reset();
 	}
 };
 struct Lease {
@@ -138,6 +145,28 @@ struct Carver {
 	}
 };
 
+/// Scratch of the calls that take no scene handle (forward kinematics, k-NN, roadmap shortest paths, mesh components):
+/// pooled like a scene's, so a planner calling them in a loop pays no cudaMalloc / cudaFree (each an implicit device sync).
+/// Device-pointer calls without a scene handle only enqueue work, so their scratch must outlive the call: one workspace per
+/// stream, used in stream order, its mutex held while a call enqueues (same scheme as mgodpl_scene::stream_slot).
+struct GlobalStreamSlot {
+	std::mutex mu;
+	Workspace ws;
+};
+GlobalStreamSlot &global_stream_slot(cudaStream_t stream) {
+	static std::mutex mu;
+	static auto *slots = new std::map<cudaStream_t, std::unique_ptr<GlobalStreamSlot>>;  // never destroyed (see global_pool)
+	std::lock_guard<std::mutex> g(mu);
+	auto &s = (*slots)[stream];
+	if (!s) s = std::make_unique<GlobalStreamSlot>();
+	return *s;
+}
+
+WorkspacePool &global_pool() {
+	static WorkspacePool *pool = new WorkspacePool;  // never destroyed: static destructors run after the CUDA runtime has shut down
+	return *pool;
+}
+
 }  // namespace
 
 struct mgodpl_scene {
@@ -148,15 +177,19 @@ struct mgodpl_scene {
 	WorkspacePool pool;  // host-buffer calls: one exclusive workspace per call, held until the call has synchronised
 	// Device-buffer calls only enqueue work, so their scratch must outlive the call: one workspace per stream, reused in
 	// stream order (growing it frees the old block with cudaFree, which waits for the device first).
+	// Two host threads may enqueue on the same stream (both passing NULL, say): the slot's mutex is held from the scratch
+	// look-up to the last launch of a call, so calls on one stream never interleave their launches or resize under each other.
+	struct StreamSlot {
+		std::mutex mu;
+		Workspace ws;
+	};
 	std::mutex stream_mu;
-	std::map<cudaStream_t, std::unique_ptr<Workspace>> stream_ws;
-	cudaError_t device_scratch(cudaStream_t stream, size_t bytes, char **out) {
+	std::map<cudaStream_t, std::unique_ptr<StreamSlot>> stream_ws;
+	StreamSlot &stream_slot(cudaStream_t stream) {
 		std::lock_guard<std::mutex> g(stream_mu);
-		auto &w = stream_ws[stream];
-		if (!w) w = std::make_unique<Workspace>();
-		cudaError_t e = w->reserve(bytes, 0);
-		*out = w->dev;
-		return e;
+		auto &s = stream_ws[stream];
+		if (!s) s = std::make_unique<StreamSlot>();
+		return *s;
 	}
 };
 
@@ -224,12 +257,15 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 		e = cudaMemcpyAsync(d_verts, verts, nv * 3 * sizeof(double), cudaMemcpyHostToDevice, stream);
 		if (e == cudaSuccess) e = cudaMemcpyAsync(d_tris, idx.data(), nt * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream);
 		static const bool want_wide = !(getenv("MGODPL_WIDE_BVH") && atoi(getenv("MGODPL_WIDE_BVH")) == 0);
-		if (e == cudaSuccess) e = build_scene(d_verts, nv, d_tris, nt, lo, hi, origin, leaf, refine, want_wide, &sc->built, stream);
+		static const bool env_grid = !(getenv("MGODPL_CLEARANCE_GRID") && atoi(getenv("MGODPL_CLEARANCE_GRID")) == 0);
+		const bool want_grid = env_grid && !(opts && (opts->flags & MGODPL_SCENE_NO_CLEARANCE_GRID));
+		if (e == cudaSuccess) e = build_scene(d_verts, nv, d_tris, nt, lo, hi, origin, leaf, refine, want_wide, want_grid, &sc->built, stream);
 		cudaStreamSynchronize(stream);
 		cudaFree(d_verts);
 		cudaFree(d_tris);
 		if (e != cudaSuccess) {
 			cudaFree(sc->built.nodes), cudaFree(sc->built.wide), cudaFree(sc->built.tris), cudaFree(sc->built.tris32), cudaFree(sc->built.tri_ids);
+			cudaFree(sc->built.clear);
 			return fail_cuda(e, "build_scene");
 		}
 	}
@@ -244,7 +280,7 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 	// box by a margin two orders of magnitude above that.  Exactness is restored by the fp64 leaf test.
 	d.margin = (float) std::max(2e-5, 4e-6 * (max_abs + 2.0));
 	for (int a = 0; a < 3; ++a) d.root_c[a] = sc->built.root_c[a], d.root_h[a] = sc->built.root_h[a];  // empty scene: half = -1
-	if (sc->built.max_depth > 60) {
+	if (sc->built.max_depth > 48) {
 		mgodpl_scene_destroy(sc.release());
 		return fail(MGODPL_E_INVALID_ARGUMENT, "BVH deeper than the traversal stack (pathological triangle distribution)");
 	}
@@ -252,9 +288,19 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 		d.wide = sc->built.wide, d.n_wide = sc->built.n_wide;
 		std::memcpy(d.top, sc->built.top, sizeof(d.top));
 	}
+	if (sc->built.clear) {
+		d.clear = sc->built.clear;
+		for (int a = 0; a < 3; ++a) d.clear_n[a] = sc->built.clear_n[a], d.clear_lo[a] = sc->built.clear_lo[a];
+		d.clear_inv = 1.0f / sc->built.clear_cell, d.clear_q = sc->built.clear_quantum;
+		d.clear_pad = sc->built.clear_max - 1e-3f;  // outside the grid = at least the pad away from the bounds, minus fp32 slack
+	}
 	if (opts && (opts->flags & MGODPL_SCENE_COUNTERS)) {
-		CU(cudaMalloc((void **) &sc->d_counters, CNT_N * sizeof(unsigned long long)));
-		CU(cudaMemset(sc->d_counters, 0, CNT_N * sizeof(unsigned long long)));
+		cudaError_t e = cudaMalloc((void **) &sc->d_counters, CNT_N * sizeof(unsigned long long));
+		if (e == cudaSuccess) e = cudaMemset(sc->d_counters, 0, CNT_N * sizeof(unsigned long long));
+		if (e != cudaSuccess) {
+			mgodpl_scene_destroy(sc.release());
+			return fail_cuda(e, "scene counters");
+		}
 		d.counters = sc->d_counters;
 	}
 	mgodpl_scene_info &in = sc->info;
@@ -265,6 +311,8 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 	for (int a = 0; a < 3; ++a) in.bounds_lo[a] = lo[a], in.bounds_hi[a] = hi[a];
 	in.build_ms = sc->built.build_ms, in.sah_cost = sc->built.sah_cost;
 	in.max_depth = sc->built.max_depth, in.max_leaf_size = sc->built.max_leaf;
+	in.clearance_cells = (uint64_t) sc->built.clear_n[0] * sc->built.clear_n[1] * sc->built.clear_n[2];
+	in.clearance_cell_size = sc->built.clear_cell, in.clearance_build_ms = sc->built.clear_build_ms;
 	*out = sc.release();
 	return MGODPL_OK;
 }
@@ -279,7 +327,7 @@ int mgodpl_scene_create_u64(const double *verts, size_t nv, const uint64_t *tris
 }
 int mgodpl_scene_destroy(mgodpl_scene *s) {
 	if (!s) return MGODPL_OK;
-	cudaFree(s->built.wide);
+	cudaFree(s->built.wide), cudaFree(s->built.clear);
 	cudaFree(s->built.nodes), cudaFree(s->built.tris), cudaFree(s->built.tris32), cudaFree(s->built.tri_ids), cudaFree(s->d_counters);
 	delete s;
 	return MGODPL_OK;
@@ -404,6 +452,8 @@ int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_
 	for (int j = 0; j < n_joints; ++j) n_vars += joints[j].joint_type == MGODPL_JOINT_REVOLUTE;
 	d.n_vars = n_vars;
 	if (n_vars > MGODPL_MAX_JOINT_VALUES) return fail(MGODPL_E_UNSUPPORTED_ROBOT, "too many joint variables");
+	for (int k = 0; k < d.n_ops; ++k)  // joint graphs with cycles can push a joint twice and run the variable cursor past the end
+		if (d.ops[k].var >= n_vars) return fail(MGODPL_E_UNSUPPORTED_ROBOT, "joint graph is not a tree: a joint variable index exceeds the variable count");
 	if (ee_link >= 0 && !visited[ee_link]) return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: end effector unreachable from root");
 
 	// Boxes (sorted by the op that reaches their link, root first), the links FK must reach for collision, and the
@@ -426,6 +476,28 @@ int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_
 		HTf tf = load_tf(sh.transform);
 		memcpy(b.t, tf.t, sizeof(tf.t)), memcpy(b.q, tf.q, sizeof(tf.q));
 		b.tf_identity = rot_is_identity(tf.q) && tf.t[0] == 0.0 && tf.t[1] == 0.0 && tf.t[2] == 0.0;
+		{
+			// cover the box with BOX_SPHERES equal spheres: the axis split (n0 x n1 x n2 <= BOX_SPHERES sub-boxes) whose
+			// circumscribed spheres are smallest
+			int best_n[3] = {1, 1, 1};
+			double best_r = vnorm(b.half);
+			for (int n0 = 1; n0 <= BOX_SPHERES; ++n0)
+				for (int n1 = 1; n0 * n1 <= BOX_SPHERES; ++n1)
+					for (int n2 = 1; n0 * n1 * n2 <= BOX_SPHERES; ++n2) {
+						const double sub[3] = {b.half[0] / n0, b.half[1] / n1, b.half[2] / n2};
+						if (vnorm(sub) < best_r) best_r = vnorm(sub), best_n[0] = n0, best_n[1] = n1, best_n[2] = n2;
+					}
+			int k = 0;
+			for (int i0 = 0; i0 < best_n[0]; ++i0)
+				for (int i1 = 0; i1 < best_n[1]; ++i1)
+					for (int i2 = 0; i2 < best_n[2]; ++i2, ++k) {
+						const int idx[3] = {i0, i1, i2};
+						for (int a = 0; a < 3; ++a) b.sphere_c[k][a] = (float) (-b.half[a] + (2 * idx[a] + 1) * b.half[a] / best_n[a]);
+					}
+			for (; k < BOX_SPHERES; ++k)
+				for (int a = 0; a < 3; ++a) b.sphere_c[k][a] = b.sphere_c[k - 1][a];  // fewer sub-boxes than slots: repeat the last
+			b.sphere_r = (float) (best_r * (1.0 + 1e-6) + 1e-6);
+		}
 		needed[b.link] = 1;
 		reach = std::max(reach, depth_reach[b.link] + vnorm(tf.t) + vnorm(b.half));
 	}
@@ -460,6 +532,24 @@ int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_
 			for (size_t f = e + 1; f < executed.size(); ++f)
 				if (d.ops[executed[f]].parent == d.ops[executed[e]].child && !(d.ops[executed[f]].flags & FK_PARENT_IS_PREV))
 					d.ops[executed[e]].flags |= FK_STORE;
+	}
+	{
+		// chain robots (every procedural drone): each collision op's parent is the previous collision op's child
+		d.chain = 1;
+		for (int k = 0; k < d.n_ops; ++k)
+			if ((d.ops[k].flags & FK_FOR_COLLISION) && !(d.ops[k].flags & FK_PARENT_IS_PREV)) d.chain = 0;
+		// ops from the root to the end effector, for goal sampling (genGoalStateUniform needs the end-effector pose only)
+		d.n_ee_path = 0;
+		if (ee_link >= 0) {
+			std::vector<int> path;
+			for (int link = ee_link; link != root_link;) {
+				int k = link_rank[link] - 1;  // the op that produced this link
+				if (k < 0) break;
+				path.push_back(k);
+				link = d.ops[k].parent;
+			}
+			for (auto it = path.rbegin(); it != path.rend(); ++it) d.ee_path[d.n_ee_path++] = (int8_t) *it;
+		}
 	}
 	// Joint limits for device-side goal sampling: one (min, max) per variable in variable order.
 	rb->limits.assign(2 * std::max(n_vars, 1), 0.0);
@@ -504,15 +594,16 @@ int mgodpl_forward_kinematics(const mgodpl_robot *robot, const double *states, s
 	cudaStream_t stream = (cudaStream_t) stream_;
 	if (!n) return MGODPL_OK;
 	size_t in_b = n * stride * 8, out_b = n * robot->dev.n_links * 7 * 8;
-	double *d_in = nullptr, *d_out = nullptr;
-	CU(cudaMalloc((void **) &d_in, in_b));
-	cudaError_t e = cudaMalloc((void **) &d_out, out_b);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, states, in_b, cudaMemcpyHostToDevice, stream);
-	if (e == cudaSuccess) e = launch_forward_kinematics(robot->dev, d_in, n, stride, d_out, stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-	cudaFree(d_in), cudaFree(d_out);
-	if (e != cudaSuccess) return fail_cuda(e, "forward_kinematics");
+	Lease ws(global_pool());
+	Carver c;
+	const size_t o_in = c.take(in_b), o_out = c.take(out_b);
+	CU(ws->reserve(c.off, 0));
+	double *d_in = (double *) (ws->dev + o_in), *d_out = (double *) (ws->dev + o_out);
+	CU(cudaMemcpyAsync(d_in, states, in_b, cudaMemcpyHostToDevice, stream));
+	CU(launch_forward_kinematics(robot->dev, d_in, n, stride, d_out, stream));
+	CU(cudaMemcpyAsync(out, d_out, out_b, cudaMemcpyDeviceToHost, stream));
+	CU(cudaStreamSynchronize(stream));
+	ws.settled = true;
 	return MGODPL_OK;
 }
 
@@ -549,9 +640,10 @@ int mgodpl_check_states_device(mgodpl_scene *scene, const mgodpl_robot *robot, c
 	if (!n) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	const size_t qb = query_scratch_bytes(n * (size_t) robot->dev.n_boxes + 4096, state_survivor_slots(n));
-	char *scratch = nullptr;
-	CU(scene->device_scratch(stream, qb, &scratch));
-	CU(launch_check_states(scene->dev, robot->dev, d_states, n, stride, d_hit_bits, scratch, qb, stream));
+	auto &slot = scene->stream_slot(stream);
+	std::lock_guard<std::mutex> enqueue(slot.mu);
+	CU(slot.ws.reserve(qb, 0));
+	CU(launch_check_states(scene->dev, robot->dev, d_states, n, stride, d_hit_bits, slot.ws.dev, qb, stream));
 	return MGODPL_OK;
 }
 
@@ -602,8 +694,10 @@ int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, 
 	Carver c;
 	const size_t qb = motion_scratch_bytes(m, robot->dev.n_boxes);
 	size_t o_first = c.take(m * 4), o_steps = c.take(d_n_steps ? 0 : m * 4), o_slerp = c.take(m * 32), o_q = c.take(qb);
-	char *scratch = nullptr;
-	CU(scene->device_scratch(stream, c.off, &scratch));
+	auto &slot = scene->stream_slot(stream);
+	std::lock_guard<std::mutex> enqueue(slot.mu);
+	CU(slot.ws.reserve(c.off, 0));
+	char *scratch = slot.ws.dev;
 	CU(launch_check_motions(scene->dev, robot->dev, d_a, d_b, m, stride, js, max_step, d_override, d_hit_bits, d_toi,
 							d_n_steps ? d_n_steps : (uint32_t *) (scratch + o_steps), d_uncertain, (unsigned *) (scratch + o_first),
 							scratch + o_slerp, scratch + o_q, qb, motion_survivors(m), stream));
@@ -797,10 +891,11 @@ int mgodpl_sample_goals_device(mgodpl_scene *scene, const mgodpl_robot *robot, c
 	if (!f || !s) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	const size_t qb = query_scratch_bytes(f * s * (size_t) robot->dev.n_boxes * 9 / 8 + 4096);
-	char *scratch = nullptr;
-	CU(scene->device_scratch(stream, qb, &scratch));
+	auto &slot = scene->stream_slot(stream);
+	std::lock_guard<std::mutex> enqueue(slot.mu);
+	CU(slot.ws.reserve(qb, 0));
 	CU(launch_sample_goals(scene->dev, robot->dev, d_targets, f, d_draws, robot->d_limits, s, seed, dist, d_hit_bits, d_collisions,
-						   d_states_out, scratch, qb, stream));
+						   d_states_out, slot.ws.dev, qb, stream));
 	return MGODPL_OK;
 }
 
@@ -843,7 +938,11 @@ int mgodpl_knn_device(const double *d_states, size_t n, size_t stride, int32_t j
 	if (n && (!d_states || !d_idx)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
 	if (n >= 0x7FFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "too many states");
 	if (int rc = require_device()) return rc;
-	CU(launch_knn(d_states, n, stride, js, k, causal, d_idx, d_dist, (cudaStream_t) stream_));
+	if (!n) return MGODPL_OK;
+	auto &slot = global_stream_slot((cudaStream_t) stream_);
+	std::lock_guard<std::mutex> enqueue(slot.mu);
+	CU(slot.ws.reserve(knn_scratch_bytes(n, n, k), 0));
+	CU(launch_knn(d_states, n, stride, js, k, causal, d_idx, d_dist, slot.ws.dev, (cudaStream_t) stream_));
 	return MGODPL_OK;
 }
 
@@ -856,18 +955,18 @@ int mgodpl_knn(const double *states, size_t n, size_t stride, int32_t js, int32_
 	if (int rc = require_device()) return rc;
 	if (!n) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
-	double *d_s = nullptr, *d_d = nullptr;
-	int32_t *d_i = nullptr;
-	cudaError_t e = cudaMalloc((void **) &d_s, n * stride * 8);
-	if (e == cudaSuccess) e = cudaMalloc((void **) &d_i, n * k * 4);
-	if (e == cudaSuccess && dist) e = cudaMalloc((void **) &d_d, n * k * 8);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, states, n * stride * 8, cudaMemcpyHostToDevice, stream);
-	if (e == cudaSuccess) e = launch_knn(d_s, n, stride, js, k, causal, d_i, d_d, stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(idx, d_i, n * k * 4, cudaMemcpyDeviceToHost, stream);
-	if (e == cudaSuccess && dist) e = cudaMemcpyAsync(dist, d_d, n * k * 8, cudaMemcpyDeviceToHost, stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-	cudaFree(d_s), cudaFree(d_i), cudaFree(d_d);
-	if (e != cudaSuccess) return fail_cuda(e, "knn");
+	Lease ws(global_pool());
+	Carver c;
+	const size_t o_s = c.take(n * stride * 8), o_i = c.take(n * k * 4), o_d = c.take(dist ? n * k * 8 : 0), o_p = c.take(knn_scratch_bytes(n, n, k));
+	CU(ws->reserve(c.off, 0));
+	double *d_s = (double *) (ws->dev + o_s), *d_d = dist ? (double *) (ws->dev + o_d) : nullptr;
+	int32_t *d_i = (int32_t *) (ws->dev + o_i);
+	CU(cudaMemcpyAsync(d_s, states, n * stride * 8, cudaMemcpyHostToDevice, stream));
+	CU(launch_knn(d_s, n, stride, js, k, causal, d_i, d_d, ws->dev + o_p, stream));
+	CU(cudaMemcpyAsync(idx, d_i, n * k * 4, cudaMemcpyDeviceToHost, stream));
+	if (dist) CU(cudaMemcpyAsync(dist, d_d, n * k * 8, cudaMemcpyDeviceToHost, stream));
+	CU(cudaStreamSynchronize(stream));
+	ws.settled = true;
 	return MGODPL_OK;
 }
 
@@ -880,20 +979,20 @@ int mgodpl_knn_query(const double *database, size_t n_db, const double *queries,
 	if (int rc = require_device()) return rc;
 	if (!n_q) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
-	double *d_db = nullptr, *d_q = nullptr, *d_d = nullptr;
-	int32_t *d_i = nullptr;
-	cudaError_t e = cudaMalloc((void **) &d_db, n_db * stride * 8 + 8);
-	if (e == cudaSuccess) e = cudaMalloc((void **) &d_q, n_q * stride * 8);
-	if (e == cudaSuccess) e = cudaMalloc((void **) &d_i, n_q * k * 4);
-	if (e == cudaSuccess && dist) e = cudaMalloc((void **) &d_d, n_q * k * 8);
-	if (e == cudaSuccess && n_db) e = cudaMemcpyAsync(d_db, database, n_db * stride * 8, cudaMemcpyHostToDevice, stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(d_q, queries, n_q * stride * 8, cudaMemcpyHostToDevice, stream);
-	if (e == cudaSuccess) e = launch_knn_query(d_db, n_db, d_q, n_q, stride, js, k, d_i, d_d, stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(idx, d_i, n_q * k * 4, cudaMemcpyDeviceToHost, stream);
-	if (e == cudaSuccess && dist) e = cudaMemcpyAsync(dist, d_d, n_q * k * 8, cudaMemcpyDeviceToHost, stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-	cudaFree(d_db), cudaFree(d_q), cudaFree(d_i), cudaFree(d_d);
-	if (e != cudaSuccess) return fail_cuda(e, "knn_query");
+	Lease ws(global_pool());
+	Carver c;
+	const size_t o_db = c.take(n_db * stride * 8 + 8), o_q = c.take(n_q * stride * 8), o_i = c.take(n_q * k * 4), o_d = c.take(dist ? n_q * k * 8 : 0);
+	const size_t o_p = c.take(knn_scratch_bytes(n_q, n_db, k));
+	CU(ws->reserve(c.off, 0));
+	double *d_db = (double *) (ws->dev + o_db), *d_q = (double *) (ws->dev + o_q), *d_d = dist ? (double *) (ws->dev + o_d) : nullptr;
+	int32_t *d_i = (int32_t *) (ws->dev + o_i);
+	if (n_db) CU(cudaMemcpyAsync(d_db, database, n_db * stride * 8, cudaMemcpyHostToDevice, stream));
+	CU(cudaMemcpyAsync(d_q, queries, n_q * stride * 8, cudaMemcpyHostToDevice, stream));
+	CU(launch_knn_query(d_db, n_db, d_q, n_q, stride, js, k, d_i, d_d, ws->dev + o_p, stream));
+	CU(cudaMemcpyAsync(idx, d_i, n_q * k * 4, cudaMemcpyDeviceToHost, stream));
+	if (dist) CU(cudaMemcpyAsync(dist, d_d, n_q * k * 8, cudaMemcpyDeviceToHost, stream));
+	CU(cudaStreamSynchronize(stream));
+	ws.settled = true;
 	return MGODPL_OK;
 }
 
@@ -915,14 +1014,12 @@ int mgodpl_roadmap_shortest_paths_device(const uint32_t *d_row_offsets, const ui
 	if (!n_vertices || !n_sources) return MGODPL_OK;
 	unsigned *flag = pinned_flag();
 	if (!flag) return fail(MGODPL_E_OUT_OF_MEMORY, "pinned host memory");
-	void *scratch = nullptr;
-	cudaError_t e = cudaMalloc(&scratch, roadmap_scratch_bytes(n_vertices, n_sources));
-	if (e == cudaSuccess)
-		e = launch_roadmap_shortest_paths(d_row_offsets, d_neighbours, d_weights, n_vertices, d_sources, n_sources, d_dist, d_pred, scratch, flag,
-										  sweeps_out, (cudaStream_t) stream_);
-	if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) stream_);
-	cudaFree(scratch);
-	if (e != cudaSuccess) return fail_cuda(e, "roadmap_shortest_paths");
+	Lease ws(global_pool());
+	CU(ws->reserve(roadmap_scratch_bytes(n_vertices, n_sources), 0));
+	CU(launch_roadmap_shortest_paths(d_row_offsets, d_neighbours, d_weights, n_vertices, d_sources, n_sources, d_dist, d_pred, ws->dev, flag,
+									 sweeps_out, (cudaStream_t) stream_));
+	CU(cudaStreamSynchronize((cudaStream_t) stream_));
+	ws.settled = true;
 	return MGODPL_OK;
 }
 
@@ -956,31 +1053,25 @@ int mgodpl_roadmap_shortest_paths(uint32_t n_vertices, const uint32_t *edges, co
 		}
 	}
 	cudaStream_t stream = (cudaStream_t) stream_;
-	uint32_t *d_row = nullptr, *d_col = nullptr, *d_src = nullptr, *d_pred = nullptr;
-	double *d_w = nullptr, *d_dist = nullptr;
 	const size_t cells = n_sources * (size_t) n_vertices;
-	cudaError_t e = cudaMalloc((void **) &d_row, row.size() * 4);
-	if (e == cudaSuccess) e = cudaMalloc((void **) &d_col, col.size() * 4 + 4);
-	if (e == cudaSuccess) e = cudaMalloc((void **) &d_w, w.size() * 8 + 8);
-	if (e == cudaSuccess) e = cudaMalloc((void **) &d_src, n_sources * 4);
-	if (e == cudaSuccess) e = cudaMalloc((void **) &d_dist, cells * 8);
-	if (e == cudaSuccess && pred) e = cudaMalloc((void **) &d_pred, cells * 4);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(d_row, row.data(), row.size() * 4, cudaMemcpyHostToDevice, stream);
-	if (e == cudaSuccess && !col.empty()) e = cudaMemcpyAsync(d_col, col.data(), col.size() * 4, cudaMemcpyHostToDevice, stream);
-	if (e == cudaSuccess && !w.empty()) e = cudaMemcpyAsync(d_w, w.data(), w.size() * 8, cudaMemcpyHostToDevice, stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(d_src, sources, n_sources * 4, cudaMemcpyHostToDevice, stream);
-	int rc = MGODPL_OK;
-	if (e == cudaSuccess) {
-		rc = mgodpl_roadmap_shortest_paths_device(d_row, d_col, d_w, n_vertices, d_src, n_sources, d_dist, d_pred, sweeps_out, stream_);
-		if (rc == MGODPL_OK) {
-			e = cudaMemcpyAsync(dist, d_dist, cells * 8, cudaMemcpyDeviceToHost, stream);
-			if (e == cudaSuccess && pred) e = cudaMemcpyAsync(pred, d_pred, cells * 4, cudaMemcpyDeviceToHost, stream);
-			if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-		}
-	}
-	cudaFree(d_row), cudaFree(d_col), cudaFree(d_w), cudaFree(d_src), cudaFree(d_dist), cudaFree(d_pred);
-	if (rc != MGODPL_OK) return rc;
-	if (e != cudaSuccess) return fail_cuda(e, "roadmap_shortest_paths");
+	Lease ws(global_pool());
+	Carver c;
+	const size_t o_row = c.take(row.size() * 4), o_col = c.take(col.size() * 4 + 4), o_w = c.take(w.size() * 8 + 8), o_src = c.take(n_sources * 4);
+	const size_t o_dist = c.take(cells * 8), o_pred = c.take(pred ? cells * 4 : 0);
+	CU(ws->reserve(c.off, 0));
+	uint32_t *d_row = (uint32_t *) (ws->dev + o_row), *d_col = (uint32_t *) (ws->dev + o_col), *d_src = (uint32_t *) (ws->dev + o_src);
+	uint32_t *d_pred = pred ? (uint32_t *) (ws->dev + o_pred) : nullptr;
+	double *d_w = (double *) (ws->dev + o_w), *d_dist = (double *) (ws->dev + o_dist);
+	CU(cudaMemcpyAsync(d_row, row.data(), row.size() * 4, cudaMemcpyHostToDevice, stream));
+	if (!col.empty()) CU(cudaMemcpyAsync(d_col, col.data(), col.size() * 4, cudaMemcpyHostToDevice, stream));
+	if (!w.empty()) CU(cudaMemcpyAsync(d_w, w.data(), w.size() * 8, cudaMemcpyHostToDevice, stream));
+	CU(cudaMemcpyAsync(d_src, sources, n_sources * 4, cudaMemcpyHostToDevice, stream));
+	// (the device variant leases a second workspace for its label scratch and synchronises the stream)
+	if (int rc = mgodpl_roadmap_shortest_paths_device(d_row, d_col, d_w, n_vertices, d_src, n_sources, d_dist, d_pred, sweeps_out, stream_)) return rc;
+	CU(cudaMemcpyAsync(dist, d_dist, cells * 8, cudaMemcpyDeviceToHost, stream));
+	if (pred) CU(cudaMemcpyAsync(pred, d_pred, cells * 4, cudaMemcpyDeviceToHost, stream));
+	CU(cudaStreamSynchronize(stream));
+	ws.settled = true;
 	return MGODPL_OK;
 }
 
@@ -996,16 +1087,17 @@ int mesh_components_impl(const Index *tris, size_t nt, size_t nv, uint32_t *labe
 	if (int rc = require_device()) return rc;
 	if (!nv) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
-	Index *d_t = nullptr;
-	unsigned *d_l = nullptr;
-	cudaError_t e = cudaMalloc((void **) &d_t, 3 * nt * sizeof(Index) + 8);
-	if (e == cudaSuccess) e = cudaMalloc((void **) &d_l, nv * 4);
-	if (e == cudaSuccess && nt) e = cudaMemcpyAsync(d_t, tris, 3 * nt * sizeof(Index), cudaMemcpyHostToDevice, stream);
-	if (e == cudaSuccess) e = launch_mesh_components<Index>(d_t, nt, (unsigned) nv, d_l, stream);
-	if (e == cudaSuccess) e = cudaMemcpyAsync(labels, d_l, nv * 4, cudaMemcpyDeviceToHost, stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-	cudaFree(d_t), cudaFree(d_l);
-	if (e != cudaSuccess) return fail_cuda(e, "mesh_components");
+	Lease ws(global_pool());
+	Carver c;
+	const size_t o_t = c.take(3 * nt * sizeof(Index) + 8), o_l = c.take(nv * 4);
+	CU(ws->reserve(c.off, 0));
+	Index *d_t = (Index *) (ws->dev + o_t);
+	unsigned *d_l = (unsigned *) (ws->dev + o_l);
+	if (nt) CU(cudaMemcpyAsync(d_t, tris, 3 * nt * sizeof(Index), cudaMemcpyHostToDevice, stream));
+	CU(launch_mesh_components<Index>(d_t, nt, (unsigned) nv, d_l, stream));
+	CU(cudaMemcpyAsync(labels, d_l, nv * 4, cudaMemcpyDeviceToHost, stream));
+	CU(cudaStreamSynchronize(stream));
+	ws.settled = true;
 	return MGODPL_OK;
 }
 }  // namespace

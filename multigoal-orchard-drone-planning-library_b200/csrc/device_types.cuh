@@ -39,7 +39,28 @@ struct SceneDev {
 	float root_c[3], root_h[3]; // scene bounds relative to origin (centre, half extent)
 	float margin;            // conservative inflation applied to every fp32 cull test
 	unsigned long long *counters; // mgodpl_counters as 6 x u64, or nullptr
+	// Clearance grid (scene_build.cu, k_clearance_grid): a regular grid over the scene bounds grown by `clear_pad`; cell value v
+	// (u8) says "no triangle lies within v * clear_q metres of ANY point of this cell" (distance from the cell centre to the
+	// nearest triangle, minus the cell's half diagonal, rounded down).  One byte load answers "is this sphere free of the scene"
+	// for most candidates long before FK or a BVH descent; it can only say "certainly free", never "hit".
+	const unsigned char *clear;  // clear_n[0] * clear_n[1] * clear_n[2] cells, x fastest; nullptr = no grid
+	int clear_n[3];
+	float clear_lo[3];       // grid corner relative to origin
+	float clear_inv;         // 1 / cell size
+	float clear_q;           // metres per quantum
+	float clear_pad;         // what a point outside the grid is known to clear (it is that far from the scene bounds)
 };
+
+/// Lower bound on the distance from origin-relative point (x, y, z) to the nearest triangle; 0 when nothing is known.
+/// NaN coordinates land in the "outside the grid" branch.
+__device__ __forceinline__ float scene_clearance(const SceneDev &sc, float x, float y, float z) {
+	if (!sc.clear) return 0.f;
+	const float gx = (x - sc.clear_lo[0]) * sc.clear_inv, gy = (y - sc.clear_lo[1]) * sc.clear_inv, gz = (z - sc.clear_lo[2]) * sc.clear_inv;
+	if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < (float) sc.clear_n[0] && gy < (float) sc.clear_n[1] && gz < (float) sc.clear_n[2]))
+		return sc.clear_pad;
+	const size_t cell = ((size_t) (int) gz * sc.clear_n[1] + (int) gy) * sc.clear_n[0] + (int) gx;
+	return (float) __ldg(sc.clear + cell) * sc.clear_q;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Robot: the reference's explicit-stack DFS (RobotModel.cpp:17-90) only depends on the model, never on the state,
@@ -67,18 +88,27 @@ enum : int32_t {
 	FK_STORE = 32         // a later, non-adjacent collision op uses this child as its parent: keep it in the link table
 };
 
+constexpr int BOX_SPHERES = 4;
 struct BoxDev {
 	int32_t link;
 	int32_t tf_identity;  // shape transform is exactly identity
 	double half[3];
 	double t[3], q[4];    // shape transform relative to the link
+	// BOX_SPHERES equal spheres (centres in the box frame, one radius) that together cover the box: the box is free of the
+	// scene when every sphere is (clearance grid, SceneDev::clear)
+	float sphere_c[BOX_SPHERES][3];
+	float sphere_r;
+	int32_t pad_;
 };
 
 struct RobotDev {
 	int32_t n_links, n_ops, n_boxes, n_vars;
 	int32_t root, ee;
 	int32_t root_box_begin, root_box_end;  // boxes of the root link (boxes are sorted by the op that reaches their link)
+	int32_t chain;        // every collision op continues from the previous one: FK needs no link table
+	int32_t n_ee_path;    // ops on the way from the root to the end effector (ee_path), in execution order
 	double reach;         // radius around the root link origin that contains every box for every joint value
+	int8_t ee_path[MGODPL_MAX_LINKS];
 	FkOp ops[MGODPL_MAX_LINKS];
 	BoxDev boxes[MGODPL_MAX_BOXES];
 };

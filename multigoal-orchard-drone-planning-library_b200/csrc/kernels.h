@@ -32,11 +32,13 @@ cudaError_t launch_forward_kinematics(const RobotDev &rb, const double *d_states
 									  cudaStream_t stream);
 
 /// Exact k-NN over equal_weights_distance; causal != 0 restricts node i to neighbours j < i (incremental PRM insertion).
-cudaError_t launch_knn(const double *d_states, size_t n, size_t stride, int js, int k, int causal, int32_t *d_idx, double *d_dist,
+/// `scratch`: knn_scratch_bytes(n_queries, n_candidates, k) bytes of device memory (the per-chunk partial lists).
+size_t knn_scratch_bytes(size_t n_q, size_t n_c, int k);
+cudaError_t launch_knn(const double *d_states, size_t n, size_t stride, int js, int k, int causal, int32_t *d_idx, double *d_dist, void *scratch,
 					   cudaStream_t stream);
 /// The same for n_q query states against a separate database of n_db states (both with the same row layout).
 cudaError_t launch_knn_query(const double *d_database, size_t n_db, const double *d_queries, size_t n_q, size_t stride, int js, int k,
-							 int32_t *d_idx, double *d_dist, cudaStream_t stream);
+							 int32_t *d_idx, double *d_dist, void *scratch, cudaStream_t stream);
 
 /// Shortest paths from many sources at once over a CSR roadmap (both directions of every undirected edge present).
 /// d_dist / d_pred: n_sources x n, source-major; d_pred may be null.  Synchronises `stream` (convergence read-backs).
@@ -61,11 +63,16 @@ struct BuiltScene {
 	uint32_t n_nodes = 0, n_tris = 0, n_leaves = 0, max_depth = 0, max_leaf = 0;
 	double sah_cost = 0, build_ms = 0;
 	float root_c[3] = {0, 0, 0}, root_h[3] = {-1, -1, -1};  // scene bounds relative to the origin, rounded outward
-	size_t device_bytes = 0;
+	size_t device_bytes = 0, device_bytes_extra = 0;
+	unsigned char *clear = nullptr;  // clearance grid (SceneDev::clear), nullptr when not requested
+	int clear_n[3] = {0, 0, 0};
+	float clear_lo[3] = {0, 0, 0}, clear_cell = 0, clear_max = 0, clear_quantum = 0, clear_build_ms = 0;
 };
+/// How far beyond the scene bounds the clearance grid reaches = the largest clearance it can certify (metres).
+constexpr double CLEAR_PAD = 1.6;
 /// d_verts: nv x 3 doubles, d_tris: nt x 3 uint32 (device).  lo/hi: scene bounds (host, from the vertices used).
 cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris, size_t nt, const double *lo,
-						const double *hi, const double *origin, unsigned max_leaf_size, bool refine, bool wide, BuiltScene *out,
-						cudaStream_t stream);
+						const double *hi, const double *origin, unsigned max_leaf_size, bool refine, bool wide, bool clearance_grid,
+						BuiltScene *out, cudaStream_t stream);
 
 }  // namespace mgodpl_b200

@@ -2,84 +2,213 @@
 // before PRM edge validation.  The reference keeps a GNAT (src/planning/nearest_neighbours/NearestNeighborsGNAT.h,
 // queried at src/planning/tsp_over_prm.cpp:44-45) and inserts nodes one at a time, so node i is connected to its k
 // nearest among the nodes inserted *before* it; `causal` reproduces exactly that neighbourhood for a whole batch.
-// Brute force, tiled through shared memory: one thread per query, 128 candidates staged per tile, top-k kept sorted.
+//
+// Brute force, tiled in two dimensions: block (x, y) holds 128 queries (one per thread) and scans candidate chunk y,
+// staged 128 rows at a time through shared memory.  Work units are uniform — in causal mode the chunks that lie
+// entirely behind a query tile are simply not scanned, instead of the last query tiles scanning 100 k candidates while
+// the first scan 128 — and the grid is as large as the batch allows.  Each thread keeps its best K of the chunk sorted
+// in registers (K a template parameter: no runtime-indexed arrays); a second kernel merges the per-chunk lists in
+// chunk order, which preserves the tie rule of the sequential scan (equal distances: lower index first).
+//
+// Nearly every candidate is rejected by its translation distance alone (every other term of the metric is
+// non-negative).  That test runs in fp32 on squared distances with a margin that covers the fp32 rounding, so it can only
+// reject candidates the fp64 test would reject too; whatever passes is measured in fp64 in the reference's operand order.
 #include "geometry.cuh"
 #include "kernels.h"
 
 namespace mgodpl_b200 {
 
-constexpr int KNN_BLOCK = 128;
+constexpr int KNN_BLOCK = 128;   // queries per block = candidates per shared-memory tile
 constexpr int KNN_MAX_K = 32;
-constexpr int KNN_ROW_MAX = 7 + MGODPL_MAX_JOINT_VALUES;
+constexpr int KNN_MAX_CHUNKS = 64;
 
+template<int K>
+struct TopK {
+	// Ascending list in registers.  Only k <= K entries are wanted: the first K - k slots hold -inf sentinels that nothing
+	// can pass, so the k real entries live in slots [K - k, K), the k-th best is always d[K - 1], and no register is ever
+	// indexed with a runtime value.
+	double d[K];
+	int32_t i[K];
+	__device__ __forceinline__ void init(int k) {
+#pragma unroll
+		for (int p = 0; p < K; ++p) d[p] = __longlong_as_double(p < K - k ? 0xfff0000000000000ll : 0x7ff0000000000000ll), i[p] = -1;
+	}
+	__device__ __forceinline__ double thr() const { return d[K - 1]; }
+	/// Precondition: dist < thr().  The newcomer replaces the worst entry and bubbles up; it stops behind equal distances,
+	/// so among ties the entry inserted first (the lower index) stays first.
+	__device__ __forceinline__ void insert(double dist, int32_t idx) {
+		d[K - 1] = dist, i[K - 1] = idx;
+#pragma unroll
+		for (int s = 0; s < K - 1; ++s) {
+			const int p = K - 1 - s;
+			const bool sw = d[p - 1] > d[p];
+			const double td = d[p];
+			const int32_t ti = i[p];
+			d[p] = sw ? d[p - 1] : td, i[p] = sw ? i[p - 1] : ti;
+			d[p - 1] = sw ? td : d[p - 1], i[p - 1] = sw ? ti : i[p - 1];
+		}
+	}
+	/// Real entry number o (0 = best) sits in slot K - k + o.
+	template<class F>
+	__device__ __forceinline__ void for_each(int k, F f) const {
+#pragma unroll
+		for (int p = 0; p < K; ++p) {
+			const int o = p - (K - k);
+			if (o >= 0) f(o, d[p], i[p]);
+		}
+	}
+};
+
+/// grid (query tiles, candidate chunks).  mode 0: every other row of the same array; 1 (causal): rows before the query;
+/// 2: a separate database, nothing excluded.  part_*: [query][chunk][k] partial lists.
+template<int K>
 __global__ void __launch_bounds__(KNN_BLOCK)
-k_knn(const double *__restrict__ states, size_t n, const double *__restrict__ cands, size_t n_cands, size_t stride, int js, int k,
-	  int mode, int32_t *__restrict__ out_idx, double *__restrict__ out_dist) {
-	// mode 0: every other row of the same array; 1 (causal): rows before the query; 2: a separate database, nothing excluded
-	const int causal = mode == 1;
-	extern __shared__ double tile[];  // KNN_BLOCK rows of (7 + js) doubles
+k_knn_scan(const double *__restrict__ queries, size_t n_q, const double *__restrict__ cands, size_t n_c, size_t stride, int js, int k, int mode,
+		   size_t chunk, int n_chunks, int32_t *__restrict__ part_idx, double *__restrict__ part_dist) {
+	extern __shared__ __align__(16) unsigned char knn_smem[];
 	const int row = 7 + js;
+	double *tile = reinterpret_cast<double *>(knn_smem);                         // KNN_BLOCK x row
+	float4 *txyz = reinterpret_cast<float4 *>(tile + (size_t) KNN_BLOCK * row);  // KNN_BLOCK fp32 translations
+	double *qj = reinterpret_cast<double *>(txyz + KNN_BLOCK);                   // KNN_BLOCK x js: the queries' joint values
 	const size_t q = (size_t) blockIdx.x * KNN_BLOCK + threadIdx.x;
-	double me[KNN_ROW_MAX];
-	if (q < n)
-		for (int i = 0; i < row; ++i) me[i] = __ldg(states + q * stride + i);
-	double best_d[KNN_MAX_K];
-	int32_t best_i[KNN_MAX_K];
-	for (int i = 0; i < k; ++i) best_d[i] = __longlong_as_double(0x7ff0000000000000ll), best_i[i] = -1;
-	// causal: candidates j < q only; the block's last query bounds the tiles worth visiting
-	const size_t last_q = min(n, (size_t) (blockIdx.x + 1) * KNN_BLOCK);
-	const size_t n_cand = causal ? last_q : n_cands;
-	for (size_t t0 = 0; t0 < n_cand; t0 += KNN_BLOCK) {
+	const bool live = q < n_q;
+	double me[7] = {0, 0, 0, 0, 0, 0, 1};
+	if (live) {
+#pragma unroll
+		for (int a = 0; a < 7; ++a) me[a] = __ldg(queries + q * stride + a);
+		for (int a = 0; a < js; ++a) qj[threadIdx.x * js + a] = __ldg(queries + q * stride + 7 + a);
+	}
+	const float mx = (float) me[0], my = (float) me[1], mz = (float) me[2];
+	const float mag = fabsf(mx) + fabsf(my) + fabsf(mz) + 1.f;
+	TopK<K> best;
+	best.init(k);
+	float thr2 = __int_as_float(0x7f800000);  // fp32 rejection threshold on the squared translation distance (+inf: list not full)
+	// causal: only candidates j < q; the block's last query bounds what is worth scanning
+	const size_t last_q = min(n_q, ((size_t) blockIdx.x + 1) * KNN_BLOCK);
+	const size_t c_end = min(mode == 1 ? min(n_c, last_q) : n_c, ((size_t) blockIdx.y + 1) * chunk);
+	for (size_t t0 = (size_t) blockIdx.y * chunk; t0 < c_end; t0 += KNN_BLOCK) {
 		__syncthreads();
-		const size_t tn = min((size_t) KNN_BLOCK, n_cand - t0);
+		const size_t tn = min((size_t) KNN_BLOCK, c_end - t0);
 		for (size_t e = threadIdx.x; e < tn * row; e += KNN_BLOCK) tile[e] = __ldg(cands + (t0 + e / row) * stride + e % row);
 		__syncthreads();
-		if (q >= n) continue;
-		for (size_t c = 0; c < tn; ++c) {
+		if (threadIdx.x < tn) txyz[threadIdx.x] = make_float4((float) tile[threadIdx.x * row], (float) tile[threadIdx.x * row + 1], (float) tile[threadIdx.x * row + 2], 0.f);
+		__syncthreads();
+		if (!live) continue;
+		const size_t tn_me = mode == 1 ? (q > t0 ? min(tn, q - t0) : 0) : tn;
+		for (size_t c = 0; c < tn_me; ++c) {
+			const float4 o32 = txyz[c];
+			const float fx = mx - o32.x, fy = my - o32.y, fz = mz - o32.z;
+			if (fx * fx + fy * fy + fz * fz > thr2) continue;  // certainly no nearer than the k-th best
 			const size_t j = t0 + c;
-			if (causal ? j >= q : (mode == 0 && j == q)) continue;
+			if (mode == 0 && j == q) continue;
 			const double *o = tile + c * row;
 			// equal_weights_distance in the reference's operand order (distance.cpp:17-25, Quaternion.h:78-85)
 			const double dx = me[0] - o[0], dy = me[1] - o[1], dz = me[2] - o[2];
 			double d = sqrt(dx * dx + dy * dy + dz * dz);
-			if (d >= best_d[k - 1]) continue;  // the remaining terms are non-negative
+			if (d >= best.thr()) continue;  // the remaining terms are non-negative
 			const double cq = fmin(fmax(me[6] * o[6] + me[3] * o[3] + me[4] * o[4] + me[5] * o[5], -1.0), 1.0);
 			d += acos(2.0 * cq * cq - 1.0);
-			for (int i = 0; i < js; ++i) d += fabs(me[7 + i] - o[7 + i]);
-			if (!(d < best_d[k - 1])) continue;
-			int pos = k - 1;  // insertion into the ascending list; ties keep the earlier index first
-			while (pos > 0 && best_d[pos - 1] > d) {
-				best_d[pos] = best_d[pos - 1], best_i[pos] = best_i[pos - 1];
-				--pos;
+			for (int a = 0; a < js; ++a) d += fabs(qj[threadIdx.x * js + a] - o[7 + a]);
+			if (!(d < best.thr())) continue;
+			best.insert(d, (int32_t) j);
+			if (best.thr() < 1e30) {
+				// fp32 bound: coordinates carry <= 2^-24 relative rounding each, and only candidates within thr of the query matter
+				const float t = __double2float_ru(best.thr()) * 1.00001f + 4e-7f * (mag + __double2float_ru(best.thr()));
+				thr2 = t * t * 1.000001f;
 			}
-			best_d[pos] = d, best_i[pos] = (int32_t) j;
 		}
 	}
-	if (q < n)
-		for (int i = 0; i < k; ++i) {
-			out_idx[q * k + i] = best_i[i];
-			if (out_dist) out_dist[q * k + i] = best_i[i] >= 0 ? best_d[i] : __longlong_as_double(0x7ff8000000000000ll);
-		}
+	if (live) {
+		int32_t *pi = part_idx + (q * n_chunks + blockIdx.y) * (size_t) k;
+		double *pd = part_dist + (q * n_chunks + blockIdx.y) * (size_t) k;
+		best.for_each(k, [&](int o, double d, int32_t j) { pi[o] = j, pd[o] = d; });
+	}
 }
 
-cudaError_t launch_knn(const double *d_states, size_t n, size_t stride, int js, int k, int causal, int32_t *d_idx, double *d_dist,
+/// One thread per query: merge the per-chunk lists (ascending chunk = ascending candidate index) into the final k.
+template<int K>
+__global__ void __launch_bounds__(KNN_BLOCK)
+k_knn_merge(size_t n_q, int k, int n_chunks, const int32_t *__restrict__ part_idx, const double *__restrict__ part_dist,
+			int32_t *__restrict__ out_idx, double *__restrict__ out_dist) {
+	const size_t q = (size_t) blockIdx.x * KNN_BLOCK + threadIdx.x;
+	if (q >= n_q) return;
+	TopK<K> best;
+	best.init(k);
+	for (int c = 0; c < n_chunks; ++c) {
+		const int32_t *pi = part_idx + (q * n_chunks + c) * (size_t) k;
+		const double *pd = part_dist + (q * n_chunks + c) * (size_t) k;
+		for (int p = 0; p < k; ++p) {
+			const int32_t j = pi[p];
+			const double d = pd[p];
+			if (j < 0 || !(d < best.thr())) break;  // lists are ascending: nothing further in this chunk can enter
+			best.insert(d, j);
+		}
+	}
+	best.for_each(k, [&](int o, double d, int32_t j) {
+		out_idx[q * k + o] = j;
+		if (out_dist) out_dist[q * k + o] = j >= 0 ? d : __longlong_as_double(0x7ff8000000000000ll);
+	});
+}
+
+namespace {
+struct KnnPlan {
+	size_t chunk;
+	int n_chunks;
+};
+KnnPlan knn_plan(size_t n_q, size_t n_c) {
+	int sms = 148, dev = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	const size_t q_tiles = (n_q + KNN_BLOCK - 1) / KNN_BLOCK, c_tiles = std::max<size_t>(1, (n_c + KNN_BLOCK - 1) / KNN_BLOCK);
+	// enough blocks to fill the GPU a few times over, but no more chunks than there are candidate tiles (or KNN_MAX_CHUNKS)
+	size_t want = (8 * (size_t) std::max(sms, 1) + q_tiles - 1) / std::max<size_t>(q_tiles, 1);
+	want = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(want, c_tiles), KNN_MAX_CHUNKS));
+	const size_t tiles_per_chunk = (c_tiles + want - 1) / want;
+	KnnPlan p;
+	p.chunk = tiles_per_chunk * KNN_BLOCK;
+	p.n_chunks = (int) ((c_tiles + tiles_per_chunk - 1) / tiles_per_chunk);
+	return p;
+}
+
+template<int K>
+cudaError_t run_knn(const double *d_q, size_t n_q, const double *d_c, size_t n_c, size_t stride, int js, int k, int mode, int32_t *d_idx,
+					double *d_dist, void *scratch, cudaStream_t stream) {
+	const KnnPlan p = knn_plan(n_q, n_c);
+	int32_t *part_idx = reinterpret_cast<int32_t *>(scratch);
+	double *part_dist = reinterpret_cast<double *>(reinterpret_cast<char *>(scratch) + ((n_q * p.n_chunks * k * sizeof(int32_t) + 255) & ~(size_t) 255));
+	const size_t smem = (size_t) KNN_BLOCK * ((7 + js) * sizeof(double) + sizeof(float4) + js * sizeof(double));
+	const dim3 grid((unsigned) ((n_q + KNN_BLOCK - 1) / KNN_BLOCK), (unsigned) p.n_chunks);
+	k_knn_scan<K><<<grid, KNN_BLOCK, smem, stream>>>(d_q, n_q, d_c, n_c, stride, js, k, mode, p.chunk, p.n_chunks, part_idx, part_dist);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+	k_knn_merge<K><<<grid.x, KNN_BLOCK, 0, stream>>>(n_q, k, p.n_chunks, part_idx, part_dist, d_idx, d_dist);
+	return cudaGetLastError();
+}
+
+cudaError_t dispatch_knn(const double *d_q, size_t n_q, const double *d_c, size_t n_c, size_t stride, int js, int k, int mode, int32_t *d_idx,
+						 double *d_dist, void *scratch, cudaStream_t stream) {
+	if (k < 1 || k > KNN_MAX_K) return cudaErrorInvalidValue;
+	if (k <= 8) return run_knn<8>(d_q, n_q, d_c, n_c, stride, js, k, mode, d_idx, d_dist, scratch, stream);
+	if (k <= 16) return run_knn<16>(d_q, n_q, d_c, n_c, stride, js, k, mode, d_idx, d_dist, scratch, stream);
+	return run_knn<32>(d_q, n_q, d_c, n_c, stride, js, k, mode, d_idx, d_dist, scratch, stream);
+}
+}  // namespace
+
+size_t knn_scratch_bytes(size_t n_q, size_t n_c, int k) {
+	const KnnPlan p = knn_plan(n_q, n_c);
+	return ((n_q * p.n_chunks * k * sizeof(int32_t) + 255) & ~(size_t) 255) + n_q * p.n_chunks * k * sizeof(double) + 256;
+}
+
+cudaError_t launch_knn(const double *d_states, size_t n, size_t stride, int js, int k, int causal, int32_t *d_idx, double *d_dist, void *scratch,
 					   cudaStream_t stream) {
 	if (!n) return cudaSuccess;
-	if (k < 1 || k > KNN_MAX_K) return cudaErrorInvalidValue;
-	const size_t smem = (size_t) KNN_BLOCK * (7 + js) * sizeof(double);
-	k_knn<<<(unsigned) ((n + KNN_BLOCK - 1) / KNN_BLOCK), KNN_BLOCK, smem, stream>>>(d_states, n, d_states, n, stride, js, k, causal ? 1 : 0, d_idx,
-																					 d_dist);
-	return cudaGetLastError();
+	return dispatch_knn(d_states, n, d_states, n, stride, js, k, causal ? 1 : 0, d_idx, d_dist, scratch, stream);
 }
 
 cudaError_t launch_knn_query(const double *d_database, size_t n_db, const double *d_queries, size_t n_q, size_t stride, int js, int k,
-							 int32_t *d_idx, double *d_dist, cudaStream_t stream) {
+							 int32_t *d_idx, double *d_dist, void *scratch, cudaStream_t stream) {
 	if (!n_q) return cudaSuccess;
-	if (k < 1 || k > KNN_MAX_K) return cudaErrorInvalidValue;
-	const size_t smem = (size_t) KNN_BLOCK * (7 + js) * sizeof(double);
-	k_knn<<<(unsigned) ((n_q + KNN_BLOCK - 1) / KNN_BLOCK), KNN_BLOCK, smem, stream>>>(d_queries, n_q, d_database, n_db, stride, js, k, 2, d_idx,
-																					   d_dist);
-	return cudaGetLastError();
+	return dispatch_knn(d_queries, n_q, d_database, n_db, stride, js, k, 2, d_idx, d_dist, scratch, stream);
 }
 
 }  // namespace mgodpl_b200

@@ -1,0 +1,584 @@
+// Stage A2 + B fused: one persistent kernel expands candidate robot states into link boxes AND walks the BVH with them.
+//
+// Included by query_kernels.cu (after the shared helpers).  Every warp is an independent worker with its own region
+// of shared memory; nothing a warp produces ever travels through HBM:
+//
+//   expand   all 32 lanes take one candidate each (a surviving state, one interpolation step of a motion, a goal sample,
+//            an explicit box): interpolate / FK in fp64, cull each link box (scene bounds, clearance grid, the root
+//            record's children) and drop the survivors into the warp's RING of 64-byte box items in shared memory.
+//            Ring slots are owned by lanes (SPL each), so producing needs no allocation; a FIFO of slot numbers
+//            ("pending") hands the boxes to whichever lanes are free.
+//   descend  every lane that holds a box visits one BVH record per step (4-wide: up to four fp32 OBB-vs-AABB tests per
+//            dependent fetch), keeps the nearest overlapping internal child, pushes the others on its stack (shared
+//            memory, [depth][lane]; a small local array only beyond STACK_SMEM entries) and appends overlapping LEAF
+//            children to the warp's leaf FIFO — a lane never stops at a leaf.
+//   leaves   as soon as the FIFO holds 32 (box, leaf) pairs the whole warp tests 32 of them at once, one pair per lane,
+//            whichever lane walked the box: rebuild the cull box from the item, fp32 pre-filter, exact fp64 test for
+//            what it cannot decide.  A hit is reported with an atomic and marks the ring slot dead; the lane walking
+//            that box drops it at its next step.
+//   refill   lanes whose descent is over take the next pending box at once; a ring slot goes back to its owner when the
+//            descent is over AND the last of its leaf pairs has been tested (whichever happens last releases it).
+//
+// The any-hit early exit of the one-box-per-lane traversal ("park at the first overlapping leaf, test, stop on a hit")
+// becomes "keep walking until the next leaf batch": only ~2 % of the boxes of a PRM-style batch hit anything, so the
+// extra visits are noise, while the three kinds of work each run with (nearly) full warps.
+#pragma once
+
+namespace mgodpl_b200 {
+
+constexpr int BLOCK_P = 128;          // 4 warps per block, each an independent worker
+constexpr int SPL = 4;                // ring slots owned by each lane
+constexpr int RING = 32 * SPL;
+constexpr int STACK_SMEM = 24;        // per-lane stack entries kept in shared memory
+constexpr int STACK_LOCAL = 48;       // beyond that: local memory (never touched by trees of sane depth)
+constexpr int LEAF_FIFO = 256;        // power of two, >= 31 + 4 * 32
+constexpr unsigned CLAIM_ROUNDS = 4;  // large batches: candidates a warp claims per cursor atomic = 32 * CLAIM_ROUNDS
+
+struct __align__(16) WarpMem {
+	Item ring[RING];
+	int stack[STACK_SMEM][32];
+	int leaf_ref[LEAF_FIFO];
+	unsigned char leaf_slot[LEAF_FIFO];
+	int pairs[RING];            // (box, leaf) pairs of the box in this slot still waiting in the leaf FIFO
+	unsigned char pend[RING];
+	unsigned char dead[RING];   // a leaf test found a hit for the box in this slot (or its owner is decided already)
+	unsigned char done[RING];   // the descent of the box in this slot is over; the slot goes back once `pairs` reaches 0
+	unsigned freed[32];         // byte k of word l: slot l * SPL + k is free again (set by whoever finished it last)
+};
+
+enum SourceKind : int { SRC_STATES = 0, SRC_MOTION_STEPS = 1, SRC_GOALS = 2, SRC_BOXES = 3 };
+
+/// Where the candidates come from (one struct for all kinds; unused members stay zero).
+struct SourceArgs {
+	// SRC_STATES / SRC_MOTION_STEPS: survivor lists of stage A1 (one for states; head then tail for motions)
+	SurvivorsDev list[2];
+	int n_lists;
+	const double *states;  // SRC_STATES rows
+	const double *a, *b;   // SRC_MOTION_STEPS endpoint rows
+	size_t stride;
+	const uint32_t *n_steps;
+	const SlerpConst *slerp;
+	// SRC_GOALS
+	const double *targets, *draws, *limits;
+	size_t rows, per_row;
+	unsigned long long seed;
+	double distance_from_target;
+	double *states_out;
+	// SRC_BOXES
+	const double *boxes;
+	size_t total;  // SRC_GOALS / SRC_BOXES: number of candidates
+};
+
+struct PipeTuning {
+	int refill_min;    // free lanes that trigger a refill while others are still walking
+	int no_prefilter;  // MGODPL_NO_PREFILTER=1: every leaf triangle goes to the fp64 test
+	unsigned claim;    // candidates a warp claims per cursor atomic (a multiple of 32)
+};
+
+// ---- joint-value sources: a joint value is fetched when its FK op needs it (no per-thread joint array) ------------------
+struct JointsFromRow {
+	const double *p;
+	__device__ __forceinline__ double operator()(int var) const { return __ldg(p + var); }
+};
+struct JointsLerp {  // RobotState.cpp:19-21: a (1 - t) + b t
+	const double *a, *b;
+	double t;
+	bool moving;
+	__device__ __forceinline__ double operator()(int var) const {
+		return moving ? __ldg(a + var) * (1 - t) + __ldg(b + var) * t : __ldg(a + var);
+	}
+};
+struct JointsGoal {  // genUprightState's draws (goal_sampling.cpp:13-49): caller-supplied, or a counter-based generator
+	const double *draw_row, *limits;
+	unsigned long long seed, ctr;
+	__device__ __forceinline__ double operator()(int var) const {
+		if (draw_row) return __ldg(draw_row + 1 + var);
+		return limits[2 * var] + (limits[2 * var + 1] - limits[2 * var]) * u01_from_bits(mix64(seed ^ mix64(ctr + 1 + var)));
+	}
+};
+
+template<class Joints>
+__device__ __forceinline__ Pose fk_apply_j(const FkOp &op, const Pose &parent, const Joints &joints) {
+	Pose p = then(parent, D3{op.pre_t[0], op.pre_t[1], op.pre_t[2]}, Q4{op.pre_q[0], op.pre_q[1], op.pre_q[2], op.pre_q[3]},
+				  op.flags & FK_PRE_ROT_ID);
+	if (op.var >= 0) {
+		double s, c;
+		sincos(joints(op.var) / 2.0, &s, &c);
+		if (op.flags & FK_INVERT) s = -s;
+		p.q = qmul(p.q, Q4{op.axis[0] * s, op.axis[1] * s, op.axis[2] * s, c});
+	}
+	return then(p, D3{op.post_t[0], op.post_t[1], op.post_t[2]}, Q4{op.post_q[0], op.post_q[1], op.post_q[2], op.post_q[3]},
+				op.flags & FK_POST_ROT_ID);
+}
+
+/// The culls a box goes through before it is worth a ring slot: scene bounds, clearance grid, the root record's children.
+__device__ __forceinline__ bool box_may_touch_scene(const SceneDev &sc, D3 c, Q4 q, const double *half, const BoxDev *spheres) {
+	if (!sc.n_nodes) return false;  // empty scene
+	const CullBox cb = make_cull_box(sc, c, q, half);
+	if (!cull_overlap(cb, sc.root_c[0], sc.root_c[1], sc.root_c[2], sc.root_h[0], sc.root_h[1], sc.root_h[2])) return false;
+	if (sc.clear) {
+		bool free_of_scene = true;
+		if (spheres) {
+			const float need = spheres->sphere_r + sc.margin + 1e-4f;
+#pragma unroll
+			for (int k = 0; k < BOX_SPHERES; ++k) {
+				const float ox = spheres->sphere_c[k][0], oy = spheres->sphere_c[k][1], oz = spheres->sphere_c[k][2];
+				free_of_scene &= scene_clearance(sc, cb.cx + cb.r[0] * ox + cb.r[1] * oy + cb.r[2] * oz, cb.cy + cb.r[3] * ox + cb.r[4] * oy + cb.r[5] * oz,
+												 cb.cz + cb.r[6] * ox + cb.r[7] * oy + cb.r[8] * oz) > need;
+			}
+		} else {
+			free_of_scene = scene_clearance(sc, cb.cx, cb.cy, cb.cz) > sqrtf(cb.hx * cb.hx + cb.hy * cb.hy + cb.hz * cb.hz) + 1e-4f;
+		}
+		if (free_of_scene) return false;
+	}
+	if (sc.wide) {
+		bool any = false;
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			any |= __float_as_int(sc.top[2 * k].w) != WIDE_EMPTY &&
+				   cull_overlap(cb, sc.top[2 * k].x, sc.top[2 * k].y, sc.top[2 * k].z, sc.top[2 * k + 1].x, sc.top[2 * k + 1].y, sc.top[2 * k + 1].z);
+		if (!any) return false;
+	}
+	return true;
+}
+
+/// Per-lane view of the warp's worker state.  Members marked (u) hold the same value in every lane.
+struct Worker {
+	WarpMem *wm;
+	unsigned lane;
+	unsigned own_free;             // bit k: own slot lane * SPL + k is free
+	unsigned pend_head, pend_tail; // (u) FIFO of slots waiting for a lane
+	unsigned leaf_head, leaf_tail; // (u) FIFO of (slot, leaf) pairs waiting for a test
+
+	/// Producer side, called by all 32 lanes together: lanes with `want` drop their box into one of their own slots.
+	__device__ __forceinline__ void emit(bool want, D3 c, Q4 q, unsigned owner, unsigned step, unsigned box) {
+		const unsigned m = __ballot_sync(0xffffffffu, want);
+		if (!m) return;
+		if (want) {
+			const int k = __ffs(own_free) - 1;
+			own_free &= own_free - 1;
+			const unsigned slot = lane * SPL + k;
+			double2 *dst = reinterpret_cast<double2 *>(wm->ring + slot);
+			dst[0] = make_double2(c.x, c.y);
+			dst[1] = make_double2(c.z, q.x);
+			dst[2] = make_double2(q.y, q.z);
+			dst[3] = make_double2(q.w, __hiloint2double((int) (step | box << 28), (int) owner));
+			wm->dead[slot] = 0, wm->done[slot] = 0, wm->pairs[slot] = 0;
+			wm->pend[(pend_tail + __popc(m & ((1u << lane) - 1u))) & (RING - 1)] = (unsigned char) slot;
+		}
+		pend_tail += __popc(m);
+	}
+	/// Collect the slots other lanes have released since the last look.
+	__device__ __forceinline__ void reclaim() {
+		const unsigned f = wm->freed[lane];
+		if (f) {
+			wm->freed[lane] = 0;
+#pragma unroll
+			for (int k = 0; k < SPL; ++k)
+				if ((f >> (8 * k)) & 0xffu) own_free |= 1u << k;
+		}
+	}
+};
+
+/// FK for the links that carry collision geometry, one `emit` per box (check_robot_collision, collision_detection.cpp:57-80;
+/// check_link_collision :16-55).  All 32 lanes run the same loop (the robot is the same for everyone) so that every
+/// emit is a convergent point; lanes whose candidate is dead (`alive` false) skip the arithmetic.  Only the boxes
+/// [box_lo, box_hi) are emitted (robots with more boxes than a lane owns ring slots are expanded in several groups).
+/// CHAIN: every collision op continues from the previous one, so the running pose stays in registers and no link table
+/// exists at all (every procedural drone; RobotDev::chain).
+template<bool CHAIN, class Joints>
+__device__ __forceinline__ void expand_boxes(const SceneDev &sc, const RobotDev &rb, Worker &w, bool alive, const Pose &base, const Joints &joints,
+											 unsigned owner, unsigned step, int box_lo, int box_hi) {
+	auto boxes_of = [&](const Pose &link, int lo, int hi) {
+		lo = max(lo, box_lo), hi = min(hi, box_hi);
+		for (int bi = lo; bi < hi; ++bi) {
+			bool want = false;
+			Pose p = link;
+			if (alive) {
+				const BoxDev &bx = rb.boxes[bi];
+				if (!bx.tf_identity) p = then(link, D3{bx.t[0], bx.t[1], bx.t[2]}, Q4{bx.q[0], bx.q[1], bx.q[2], bx.q[3]}, false);
+				want = box_may_touch_scene(sc, p.t, p.q, bx.half, &bx);
+			}
+			w.emit(want, p.t, p.q, owner, step, (unsigned) bi);
+		}
+	};
+	boxes_of(base, rb.root_box_begin, rb.root_box_end);
+	Pose cur = base;
+	Pose link_tf[CHAIN ? 1 : MGODPL_MAX_LINKS];
+	if (!CHAIN) link_tf[rb.root] = base;
+	for (int i = 0; i < rb.n_ops; ++i) {
+		const FkOp &op = rb.ops[i];
+		if (!(op.flags & FK_FOR_COLLISION)) continue;
+		if (op.box_begin >= box_hi && op.box_begin < op.box_end) break;  // boxes are sorted by op: nothing of this group is left
+		if (alive) {
+			cur = fk_apply_j(op, (CHAIN || (op.flags & FK_PARENT_IS_PREV)) ? cur : link_tf[op.parent], joints);
+			if (!CHAIN && (op.flags & FK_STORE)) link_tf[op.child] = cur;
+		}
+		boxes_of(cur, op.box_begin, op.box_end);
+	}
+}
+
+/// Exact phase of a leaf test with the pose passed by value (the pipeline's items live in shared memory).
+__device__ __noinline__ bool exact_leaf_test_pose(const SceneDev &sc, D3 c, Q4 q, const double *half, int ref, unsigned unknown, unsigned *n_tests) {
+	const unsigned info = (unsigned) (-1 - ref), first = info >> 4, cnt = (info & 15u) + 1u;
+	const ExactBox eb = make_exact_box(c, q, half);
+	for (unsigned k = 0; k < cnt; ++k) {
+		if (!(unknown >> k & 1u)) continue;
+		++*n_tests;
+		if (box_triangle_hit(eb, sc.tris + 9ull * (first + k))) return true;
+	}
+	return false;
+}
+
+template<int KIND, bool CHAIN, bool WIDE>
+__global__ void __launch_bounds__(BLOCK_P, 4)
+k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const __grid_constant__ SourceArgs src, unsigned *cursor,
+		   Results res, PipeTuning tune) {
+	constexpr unsigned FULL = 0xffffffffu;
+	extern __shared__ __align__(16) unsigned char pipe_smem[];
+	__shared__ unsigned s_counts[2][SHARDS];
+	const unsigned lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
+	WarpMem *wm = reinterpret_cast<WarpMem *>(pipe_smem) + (threadIdx.x >> 5);
+	LocalCounters lc;
+
+	// ---- candidate index space ------------------------------------------------------------------------------------------------
+	unsigned long long range0 = 0, total = 0;  // (u) flat slots of list 0; all candidates
+	if (KIND == SRC_STATES || KIND == SRC_MOTION_STEPS) {
+		for (int l = 0; l < src.n_lists; ++l)
+			if (threadIdx.x < SHARDS) s_counts[l][threadIdx.x] = __ldcg(src.list[l].counts + threadIdx.x * COUNTER_STRIDE);
+		__syncthreads();
+		range0 = slot_range(s_counts[0], src.list[0].cap);
+		total = range0 + (src.n_lists > 1 ? slot_range(s_counts[1], src.list[1].cap) : 0u);
+	} else {
+		total = src.total;
+	}
+	const int n_groups = KIND == SRC_BOXES ? 1 : max(1, (rb.n_boxes + SPL - 1) / SPL);  // box groups per candidate
+	const int group_boxes = KIND == SRC_BOXES ? 1 : min(rb.n_boxes, SPL);
+	total *= (unsigned) n_groups;
+
+	Worker w{wm, lane, (1u << SPL) - 1u, 0u, 0u, 0u, 0u};
+	wm->freed[lane] = 0;
+	unsigned long long chunk_lo = 0, chunk_hi = 0;  // (u) unclaimed part of this warp's chunk of candidates
+	bool exhausted = total == 0;                     // (u)
+	// lane state: the box being walked (cur == REF_END: none)
+	CullBox cb{};
+	int cur = REF_END, sp = 0;
+	unsigned slot = 0;
+	int lstack[STACK_LOCAL];
+	unsigned box_nodes = 0, max_box_nodes = 0, stalls = 0;
+	__syncwarp();
+
+	auto push = [&](int v) {
+		if (sp < STACK_SMEM) wm->stack[sp][lane] = v;
+		else lstack[sp - STACK_SMEM] = v;
+		++sp;
+	};
+	auto pop = [&]() {
+		--sp;
+		return sp < STACK_SMEM ? wm->stack[sp][lane] : lstack[sp - STACK_SMEM];
+	};
+	auto half_of = [&](unsigned owner, unsigned step_box, double *buf) -> const double * {
+		if (KIND == SRC_BOXES) {
+			const double *bx = src.boxes + (size_t) owner * 10;
+			buf[0] = __ldg(bx + 7) * 0.5, buf[1] = __ldg(bx + 8) * 0.5, buf[2] = __ldg(bx + 9) * 0.5;
+			return buf;
+		}
+		return rb.boxes[step_box >> 28].half;
+	};
+	auto release = [&](unsigned s) { reinterpret_cast<volatile unsigned char *>(wm->freed)[s] = 1; };  // s = owner lane * SPL + k
+	/// One batch of leaf tests: pair `leaf_head + lane` for lane < batch, whichever lane walked the box.
+	auto leaf_batch = [&](unsigned batch) {
+		if (lane < batch) {
+			const unsigned e = (w.leaf_head + lane) & (LEAF_FIFO - 1);
+			const unsigned s = wm->leaf_slot[e];
+			const int ref = wm->leaf_ref[e];
+			if (!wm->dead[s]) {
+				const double2 *it = reinterpret_cast<const double2 *>(wm->ring + s);
+				const double2 v0 = it[0], v1 = it[1], v2 = it[2], v3 = it[3];
+				const unsigned owner = (unsigned) __double2loint(v3.y), step_box = (unsigned) __double2hiint(v3.y), step = step_box & 0x0FFFFFFFu;
+				if (already_decided(res, owner, step)) {
+					wm->dead[s] = 1;
+				} else {
+					double hb[3];
+					const double *half = half_of(owner, step_box, hb);
+					const D3 c{v0.x, v0.y, v1.x};
+					const Q4 q{v1.y, v2.x, v2.y, v3.x};
+					const CullBox tb = make_cull_box(sc, c, q, half);
+					unsigned unknown = 0xffffu;
+					bool hit = tune.no_prefilter ? false : leaf_prefilter(sc, tb, ref, &unknown);
+					if (!hit && unknown) {
+						unsigned n_exact = 0;
+						hit = exact_leaf_test_pose(sc, c, q, half, ref, unknown, &n_exact);
+						lc.leaf += n_exact;
+					}
+					if (hit) {
+						report_hit(res, owner, step);
+						wm->dead[s] = 1;
+					}
+				}
+			}
+			// last pair of a box whose descent is over: the slot goes back to its owner
+			if (atomicSub(&wm->pairs[s], 1) == 1 && wm->done[s]) release(s);
+		}
+		w.leaf_head += batch;
+	};
+
+	for (;;) {
+		__syncwarp();
+		const unsigned n_leaf = w.leaf_tail - w.leaf_head, n_pend = w.pend_tail - w.pend_head;
+		const unsigned walking = __ballot_sync(FULL, cur != REF_END), n_free = 32u - __popc(walking);
+		// ---- leaves: 32 pairs waiting -> one full-warp batch ----------------------------------------------------------------
+		if (n_leaf >= 32u) {
+			leaf_batch(32u);
+			continue;
+		}
+		// ---- refill: free lanes take pending boxes ------------------------------------------------------------------------------
+		if (n_pend && n_free && ((int) n_free >= tune.refill_min || !walking || n_pend >= 64u)) {
+			const unsigned rank = __popc(~walking & lt);
+			if (cur == REF_END && rank < n_pend) {
+				slot = wm->pend[(w.pend_head + rank) & (RING - 1)];
+				const double2 *it = reinterpret_cast<const double2 *>(wm->ring + slot);
+				const double2 v0 = it[0], v1 = it[1], v2 = it[2], v3 = it[3];
+				const unsigned owner = (unsigned) __double2loint(v3.y), step_box = (unsigned) __double2hiint(v3.y);
+				unsigned first_hit = NO_HIT;
+				if (res.mode != RESULT_BITS) first_hit = __ldcg(res.first_step + owner);  // issued first, consumed last
+				double hb[3];
+				const double *half = half_of(owner, step_box, hb);
+				cb = make_cull_box(sc, D3{v0.x, v0.y, v1.x}, Q4{v1.y, v2.x, v2.y, v3.x}, half);
+				// motions: a box of a step that can no longer be the first colliding one is dropped at once
+				if (res.mode == RESULT_BITS || !(first_hit <= (step_box & 0x0FFFFFFFu))) {
+					cur = 0, sp = 0;
+					lc.boxes++;
+					max_box_nodes = max(max_box_nodes, box_nodes), box_nodes = 0;
+				} else {
+					release(slot);
+				}
+			}
+			w.pend_head += min(n_pend, n_free);
+			stalls = 0;
+			continue;
+		}
+		// ---- expand: keep at least a warp's worth of boxes pending while candidates remain ----------------------------------------
+		if (!exhausted && n_pend < 32u) {
+			w.reclaim();
+			const bool can = __popc(w.own_free) >= group_boxes;
+			const unsigned can_mask = __ballot_sync(FULL, can);
+			if (can_mask) {
+				stalls = 0;
+				if (chunk_lo == chunk_hi) {
+					unsigned long long lo = 0;
+					if (lane == 0) lo = atomicAdd(cursor, tune.claim);
+					lo = __shfl_sync(FULL, lo, 0);
+					chunk_lo = min(lo, total), chunk_hi = min(lo + tune.claim, total);
+					if (chunk_lo >= total) {
+						exhausted = true;
+						continue;
+					}
+				}
+				const unsigned avail = (unsigned) min(chunk_hi - chunk_lo, (unsigned long long) 32u), rank = __popc(can_mask & lt);
+				bool alive = can && rank < avail;
+				const unsigned long long idx = chunk_lo + rank;
+				chunk_lo += min(avail, (unsigned) __popc(can_mask));
+				const unsigned long long cand = idx / (unsigned) n_groups;
+				const int box_lo = (int) (idx % (unsigned) n_groups) * SPL, box_hi = box_lo + SPL;
+				Pose base{};
+				unsigned owner = 0, step = 0;
+				if (KIND == SRC_STATES) {
+					const double *row = nullptr;
+					if (alive) {
+						alive = slot_filled(s_counts[0], (unsigned) cand);
+						if (alive) {
+							owner = __ldcg(&src.list[0].entries[cand]).x;
+							row = src.states + (size_t) owner * src.stride;
+							double r7[7];
+#pragma unroll
+							for (int j = 0; j < 7; ++j) r7[j] = __ldg(row + j);
+							alive = finite7(r7);
+							base = Pose{D3{r7[0], r7[1], r7[2]}, Q4{r7[3], r7[4], r7[5], r7[6]}};
+						}
+					}
+					expand_boxes<CHAIN>(sc, rb, w, alive, base, JointsFromRow{row + 7}, owner, 0u, box_lo, box_hi);  // (stage A1 counted the states)
+				} else if (KIND == SRC_MOTION_STEPS) {
+					JointsLerp jl{nullptr, nullptr, 0.0, false};
+					if (alive) {
+						const bool tail = cand >= range0;
+						const unsigned k = (unsigned) (tail ? cand - range0 : cand);
+						alive = slot_filled(s_counts[tail ? 1 : 0], k);
+						if (alive) {
+							const uint2 e = __ldcg(&src.list[tail ? 1 : 0].entries[k]);
+							owner = e.x, step = e.y;
+							const unsigned first_hit = __ldcg(res.first_step + owner);  // travels with the endpoint rows: one round trip
+							const double *A = src.a + (size_t) owner * src.stride, *B = src.b + (size_t) owner * src.stride;
+							const unsigned ns = __ldg(src.n_steps + owner);
+							double a7[7], b7[7];
+#pragma unroll
+							for (int j = 0; j < 7; ++j) a7[j] = __ldg(A + j), b7[j] = __ldg(B + j);
+							alive = !(first_hit <= step);
+							if (alive) {
+								lc.states += box_lo == 0;
+								// for n_steps == 0 the reference evaluates t = 0/0; here the start state is checked once.
+								const double t = ns ? (double) step / (double) ns : 0.0;
+								const D3 tr{(1.0 - t) * a7[0] + t * b7[0], (1.0 - t) * a7[1] + t * b7[1], (1.0 - t) * a7[2] + t * b7[2]};
+								alive = !robot_out_of_reach(sc, rb, tr, false);
+								if (alive) {
+									base = Pose{tr, Q4{a7[3], a7[4], a7[5], a7[6]}};
+									if (ns) {  // Eigen slerp rule with the per-motion constants of stage A1
+										const SlerpConst sk = load_slerp(src.slerp + owner);
+										double w0, w1;
+										if (sk.theta < 0.0) {
+											w0 = 1.0 - t, w1 = t;
+										} else {
+											double s1, c1;
+											sincos(t * sk.theta, &s1, &c1);
+											w0 = c1 - sk.cot * s1;
+											w1 = s1 * fabs(sk.inv_sin);
+										}
+										if (signbit(sk.inv_sin)) w1 = -w1;
+										base.q = Q4{w0 * a7[3] + w1 * b7[3], w0 * a7[4] + w1 * b7[4], w0 * a7[5] + w1 * b7[5], w0 * a7[6] + w1 * b7[6]};
+									}
+									jl = JointsLerp{A + 7, B + 7, t, ns != 0};
+									alive = isfinite(base.q.x + base.q.y + base.q.z + base.q.w);
+								}
+							}
+						}
+					}
+					expand_boxes<CHAIN>(sc, rb, w, alive, base, jl, owner, step, box_lo, box_hi);
+				} else if (KIND == SRC_GOALS) {
+					JointsGoal jg{nullptr, src.limits, src.seed, 0ull};
+					if (alive) {
+						const size_t row = (size_t) (cand / src.per_row), s = (size_t) (cand - row * src.per_row);
+						const int nv = rb.n_vars;
+						double yaw;
+						if (src.draws) {
+							jg.draw_row = src.draws + s * (size_t) (1 + nv);
+							yaw = __ldg(jg.draw_row);
+						} else {
+							jg.ctr = cand * (unsigned long long) (1 + nv);
+							yaw = -M_PI + 2.0 * M_PI * u01_from_bits(mix64(src.seed ^ mix64(jg.ctr)));
+						}
+						// genUprightState: base at the origin, rotation about z by yaw (Quaternion.h:53-62 with axis UnitZ); FK to the end
+						// effector along the op path that leads to it; base shifted so the end effector lands on the target
+						double sy, cy;
+						sincos(yaw / 2.0, &sy, &cy);
+						const Q4 yq{0 * sy, 0 * sy, 1 * sy, cy};
+						Pose ee{{0, 0, 0}, yq};
+						for (int k = 0; k < rb.n_ee_path; ++k) ee = fk_apply_j(rb.ops[rb.ee_path[k]], ee, jg);
+						D3 delta = D3{__ldg(src.targets + 3 * row), __ldg(src.targets + 3 * row + 1), __ldg(src.targets + 3 * row + 2)} - ee.t;
+						if (src.distance_from_target > 0.0) delta = delta + qrot(ee.q, D3{0.0, -src.distance_from_target, 0.0});
+						base = Pose{D3{0, 0, 0} + delta, yq};
+						if (src.states_out && box_lo == 0) {
+							double *o = src.states_out + cand * (size_t) (7 + nv);
+							o[0] = base.t.x, o[1] = base.t.y, o[2] = base.t.z;
+							o[3] = base.q.x, o[4] = base.q.y, o[5] = base.q.z, o[6] = base.q.w;
+							for (int k = 0; k < nv; ++k) o[7 + k] = jg(k);
+						}
+						lc.states += box_lo == 0;
+						owner = (unsigned) (row * (((src.per_row + 31) / 32) * 32) + s);
+						alive = !robot_out_of_reach(sc, rb, base.t);
+					}
+					expand_boxes<CHAIN>(sc, rb, w, alive, base, jg, owner, 0u, box_lo, box_hi);
+				} else {  // SRC_BOXES: check_link_collision (collision_detection.cpp:16-55), n x (tf7, size3)
+					bool want = false;
+					if (alive) {
+						double v[10];
+#pragma unroll
+						for (int k = 0; k < 10; ++k) v[k] = __ldg(src.boxes + cand * 10 + k);
+						const double half[3] = {v[7] * 0.5, v[8] * 0.5, v[9] * 0.5};
+						base = Pose{D3{v[0], v[1], v[2]}, Q4{v[3], v[4], v[5], v[6]}};
+						want = finite7(v) && box_may_touch_scene(sc, base.t, base.q, half, nullptr);
+						owner = (unsigned) cand;
+					}
+					w.emit(want, base.t, base.q, owner, 0u, 0u);
+				}
+				continue;
+			}
+		}
+		// ---- descend: one record per walking lane, until something else becomes worthwhile -----------------------------------------
+		if (walking) {
+			stalls = 0;
+			for (;;) {
+				unsigned leaf_bits = 0;
+				int leaf_refs[4] = {0, 0, 0, 0};
+				const bool was_walking = cur != REF_END;
+				if (was_walking) {
+					if (wm->dead[slot]) {
+						cur = REF_END;
+					} else {
+						lc.nodes++, box_nodes++;
+						int next = REF_END;
+						float next_d = 0.f;
+						if (WIDE) {
+							const float4 *rec = sc.wide + 8ull * (unsigned) cur;
+							float4 a[4], b[4];
+#pragma unroll
+							for (int k = 0; k < 4; ++k) a[k] = __ldg(rec + 2 * k), b[k] = __ldg(rec + 2 * k + 1);
+#pragma unroll
+							for (int k = 0; k < 4; ++k) {
+								const int ref = __float_as_int(a[k].w);
+								if (ref == WIDE_EMPTY || !cull_overlap(cb, a[k].x, a[k].y, a[k].z, b[k].x, b[k].y, b[k].z)) continue;
+								if (ref < 0) {
+									leaf_bits |= 1u << k, leaf_refs[k] = ref;
+									continue;
+								}
+								const float dx = a[k].x - cb.cx, dy = a[k].y - cb.cy, dz = a[k].z - cb.cz, d = dx * dx + dy * dy + dz * dz;
+								if (next == REF_END) next = ref, next_d = d;
+								else if (d < next_d) push(next), next = ref, next_d = d;
+								else push(ref);
+							}
+						} else {
+							const float4 *rec = sc.nodes + 4ull * (unsigned) cur;
+							const float4 n0 = __ldg(rec), n1 = __ldg(rec + 1), n2 = __ldg(rec + 2), n3 = __ldg(rec + 3);
+							const bool ov_l = cull_overlap(cb, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y), ov_r = cull_overlap(cb, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+							const int lref = __float_as_int(n3.x), rref = __float_as_int(n3.y);
+							if (ov_l) {
+								if (lref < 0) leaf_bits |= 1u, leaf_refs[0] = lref;
+								else next = lref;
+							}
+							if (ov_r) {
+								if (rref < 0) leaf_bits |= 2u, leaf_refs[1] = rref;
+								else if (next == REF_END) next = rref;
+								else push(rref);
+							}
+						}
+						if (next == REF_END && sp > 0) next = pop();
+						cur = next;
+					}
+				}
+				__syncwarp();
+#pragma unroll
+				for (int k = 0; k < (WIDE ? 4 : 2); ++k) {
+					const bool mine = (leaf_bits >> k) & 1u;
+					const unsigned m = __ballot_sync(FULL, mine);
+					if (!m) continue;
+					if (mine) {
+						const unsigned e = (w.leaf_tail + __popc(m & lt)) & (LEAF_FIFO - 1);
+						wm->leaf_ref[e] = leaf_refs[k];
+						wm->leaf_slot[e] = (unsigned char) slot;
+					}
+					w.leaf_tail += __popc(m);
+				}
+				if (leaf_bits) wm->pairs[slot] += __popc(leaf_bits);  // only the walking lane adds; testers subtract in another phase
+				if (was_walking && cur == REF_END) {  // descent over (or cut short by a hit): hand the slot back, now or with its last pair
+					if (wm->pairs[slot] == 0) release(slot);
+					else wm->done[slot] = 1;
+				}
+				const unsigned still = __ballot_sync(FULL, cur != REF_END);
+				if (!still || w.leaf_tail - w.leaf_head >= 32u) break;
+				// enough lanes have run dry and there is (or can be) something to give them: go and refill
+				if ((int) (32u - __popc(still)) >= tune.refill_min && (n_pend || !exhausted)) break;
+			}
+			continue;
+		}
+		// ---- nothing walking and nothing to hand out: test what is left in the leaf FIFO (that also frees ring slots) ----------------
+		if (n_leaf) {
+			leaf_batch(n_leaf);
+			continue;
+		}
+		if (exhausted && !n_pend) break;
+		if (++stalls > 64u) break;  // unreachable by construction (every slot is free here, so expansion can proceed); never spin
+	}
+	flush_counters(sc, lc);
+	if (sc.counters) atomicMax(sc.counters + CNT_MAX_BOX_NODES, (unsigned long long) max(max_box_nodes, box_nodes));
+}
+
+}  // namespace mgodpl_b200

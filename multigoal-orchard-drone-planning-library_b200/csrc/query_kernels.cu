@@ -241,9 +241,25 @@ struct QueueDev {
 
 /// Stage A tail: cull one box against the scene bounds and hand it to stage B (or traverse it here on overflow).
 __device__ __forceinline__ void emit_box(const SceneDev &sc, const QueueDev &Q, const Results &res, D3 c, Q4 q,
-										 const double *half, unsigned owner, unsigned step, unsigned box, LocalCounters &lc) {
+										 const double *half, const BoxDev *spheres, unsigned owner, unsigned step, unsigned box, LocalCounters &lc) {
 	const CullBox cb = make_cull_box(sc, c, q, half);
 	if (!cull_overlap(cb, sc.root_c[0], sc.root_c[1], sc.root_c[2], sc.root_h[0], sc.root_h[1], sc.root_h[2])) return;
+	if (sc.clear) {
+		// clearance grid: the box is certainly free when each of the spheres that cover it is (independent one-byte loads)
+		bool free_of_scene = true;
+		if (spheres) {
+			const float need = spheres->sphere_r + sc.margin + 1e-4f;
+#pragma unroll
+			for (int k = 0; k < BOX_SPHERES; ++k) {
+				const float ox = spheres->sphere_c[k][0], oy = spheres->sphere_c[k][1], oz = spheres->sphere_c[k][2];
+				free_of_scene &= scene_clearance(sc, cb.cx + cb.r[0] * ox + cb.r[1] * oy + cb.r[2] * oz, cb.cy + cb.r[3] * ox + cb.r[4] * oy + cb.r[5] * oz,
+												 cb.cz + cb.r[6] * ox + cb.r[7] * oy + cb.r[8] * oz) > need;
+			}
+		} else {
+			free_of_scene = scene_clearance(sc, cb.cx, cb.cy, cb.cz) > sqrtf(cb.hx * cb.hx + cb.hy * cb.hy + cb.hz * cb.hz) + 1e-4f;
+		}
+		if (free_of_scene) return;
+	}
 	if (sc.wide) {
 		// One level further while the box is in registers anyway: the root record's (up to four) children travel with the
 		// kernel parameters.  A box that misses all of them would cost stage B a queue item, a refill and a record fetch.
@@ -281,8 +297,9 @@ __device__ __forceinline__ bool robot_out_of_reach(const SceneDev &sc, const Rob
 	double dz = fmax(fabs(pz - (double) sc.root_c[2]) - (double) sc.root_h[2], 0.0);
 	const double r = rb.reach + (double) sc.margin;
 	if (!(dx * dx + dy * dy + dz * dz <= r * r)) return true;  // NaN counts as out of reach
+	const float fx = (float) px, fy = (float) py, fz = (float) pz, fr = (float) r + 1e-4f;  // fp32 is enough from here on: conservative radius
+	if (sc.clear) return scene_clearance(sc, fx, fy, fz) > fr;  // the grid knows the distance to the triangles themselves
 	if (!sc.wide || !one_level_down) return false;
-	const float fx = (float) px, fy = (float) py, fz = (float) pz, fr = (float) r + 1e-4f;  // fp32 is enough one level down: conservative radius
 	bool near = false;
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
@@ -303,7 +320,7 @@ __device__ __forceinline__ void emit_link_boxes(const SceneDev &sc, const RobotD
 	for (int bi = lo; bi < hi; ++bi) {
 		const BoxDev &bx = rb.boxes[bi];
 		const Pose w = bx.tf_identity ? link : then(link, D3{bx.t[0], bx.t[1], bx.t[2]}, Q4{bx.q[0], bx.q[1], bx.q[2], bx.q[3]}, false);
-		emit_box(sc, Q, res, w.t, w.q, bx.half, owner, step, (unsigned) bi, lc);
+		emit_box(sc, Q, res, w.t, w.q, bx.half, &bx, owner, step, (unsigned) bi, lc);
 	}
 }
 __device__ __forceinline__ void expand_state(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
@@ -352,13 +369,14 @@ k_cull_states(const __grid_constant__ SceneDev sc, const __grid_constant__ Robot
 	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	double *rows = s_rows + (size_t) warp * 32 * stride;
 	const size_t n_spans = (n + 31) / 32, warps_total = (size_t) gridDim.x * (BLOCK_A / 32);
+	const bool aligned16 = (reinterpret_cast<size_t>(states) & 15) == 0;  // a caller's slice may start on an odd row: 8-byte loads then
 	for (size_t span = (size_t) blockIdx.x * (BLOCK_A / 32) + warp; span < n_spans; span += warps_total) {
 		const size_t i0 = span * 32;
 		const unsigned cnt = (unsigned) min((size_t) 32, n - i0);
 		const double *src = states + i0 * stride;
 		const unsigned total = cnt * (unsigned) stride;
 		__syncwarp();
-		if (cnt == 32) {  // 32 * stride doubles starting on a 256-byte boundary: 16-byte loads
+		if (cnt == 32 && aligned16) {  // 32 * stride doubles = a whole number of 16-byte pairs: 16-byte loads
 			const double2 *src2 = reinterpret_cast<const double2 *>(src);
 			double2 *rows2 = reinterpret_cast<double2 *>(rows);
 			for (unsigned e = lane; e < total / 2; e += 32) rows2[e] = __ldcs(src2 + e);
@@ -418,7 +436,7 @@ k_expand_boxes(const __grid_constant__ SceneDev sc, const double *__restrict__ b
 		for (int k = 0; k < 10; ++k) v[k] = __ldg(boxes + i * 10 + k);
 		if (!finite7(v)) continue;
 		const double half[3] = {v[7] * 0.5, v[8] * 0.5, v[9] * 0.5};
-		emit_box(sc, Q, res, D3{v[0], v[1], v[2]}, Q4{v[3], v[4], v[5], v[6]}, half, (unsigned) i, 0u, 0u, lc);
+		emit_box(sc, Q, res, D3{v[0], v[1], v[2]}, Q4{v[3], v[4], v[5], v[6]}, half, nullptr, (unsigned) i, 0u, 0u, lc);
 	}
 	flush_counters(sc, lc);
 }
@@ -612,13 +630,38 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 				unsigned s_hi = (unsigned) fmin(hi, (double) n_steps);
 				// The slab range is the box-shaped superset of the rounded "within reach" region, which is convex: trim
 				// both ends with the exact test stage A2 applies (same t, same lerp), so A2 mostly sees real survivors.
-				auto outside = [&](unsigned s) {
+				// `gap(s)` > 0: at step s the whole robot clears the scene by at least that much (distance from the base origin
+				// to the scene bounds, or to the triangles themselves where the clearance grid knows it, minus the reach).  The
+				// base moves step_len per step and distances are 1-Lipschitz, so a gap of g rules out floor(g / step_len) steps at
+				// once: a few look-ups walk each end of the range up to the first step that can touch anything.
+				auto gap = [&](unsigned s) {
 					const double t = n_steps ? (double) s / (double) n_steps : 0.0;
-					return robot_out_of_reach(sc, rb, D3{(1.0 - t) * ar[0] + t * br[0], (1.0 - t) * ar[1] + t * br[1], (1.0 - t) * ar[2] + t * br[2]}, false);
+					const double px = (1.0 - t) * ar[0] + t * br[0] - sc.origin[0], py = (1.0 - t) * ar[1] + t * br[1] - sc.origin[1],
+								 pz = (1.0 - t) * ar[2] + t * br[2] - sc.origin[2];
+					const double ex = fmax(fabs(px - (double) sc.root_c[0]) - (double) sc.root_h[0], 0.0);
+					const double ey = fmax(fabs(py - (double) sc.root_c[1]) - (double) sc.root_h[1], 0.0);
+					const double ez = fmax(fabs(pz - (double) sc.root_c[2]) - (double) sc.root_h[2], 0.0);
+					const double r = rb.reach + (double) sc.margin + 1e-4;
+					double g = sqrt(ex * ex + ey * ey + ez * ez) - r;
+					if (sc.clear && g <= 0.0) g = (double) scene_clearance(sc, (float) px, (float) py, (float) pz) - r;
+					return g;
 				};
-				for (int guard = 0; guard < trim && s_lo < s_hi && outside(s_lo); ++guard) ++s_lo;
-				for (int guard = 0; guard < trim && s_hi > s_lo && outside(s_hi); ++guard) --s_hi;
-				len = (s_lo == s_hi && outside(s_lo)) ? 0u : s_hi - s_lo + 1;
+				const double step_len = n_steps ? trans / (double) n_steps : 0.0;
+				auto steps_cleared = [&](double g, unsigned room) {  // NaN positions count as clear, one step at a time
+					if (!(g > 0.0) || !(step_len > 0.0)) return 1u;
+					return (unsigned) fmin(fmax(floor(g / step_len), 1.0), (double) max(room, 1u));
+				};
+				for (int guard = 0; guard < trim && s_lo < s_hi; ++guard) {
+					const double g = gap(s_lo);
+					if (g <= 0.0) break;
+					s_lo += steps_cleared(g, s_hi - s_lo);
+				}
+				for (int guard = 0; guard < trim && s_hi > s_lo; ++guard) {
+					const double g = gap(s_hi);
+					if (g <= 0.0) break;
+					s_hi -= steps_cleared(g, s_hi - s_lo);
+				}
+				len = (s_lo == s_hi && !(gap(s_lo) <= 0.0)) ? 0u : s_hi - s_lo + 1;
 				// head_steps == 0: adaptive head — the steps it takes to cross the reach shell around the scene bounds plus
 				// ~0.75 m of canopy, where a colliding motion typically finds its first hit
 				if (!head_steps) head = (unsigned) fmin(fmax((rb.reach + 0.75) * (double) n_steps / fmax(trans, 1e-3 * (double) n_steps), 8.0), 256.0);
@@ -825,6 +868,10 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 	if (sc.counters) atomicMax(sc.counters + CNT_MAX_BOX_NODES, (unsigned long long) max(max_box_nodes, box_nodes));
 }
 
+}  // namespace mgodpl_b200
+#include "pipeline.cuh"
+namespace mgodpl_b200 {
+
 // ---------------------------------------------------------------------------------------------------------------
 // Stage C (motions): first colliding step -> packed hit bit and toi = step / n_steps (collision_detection.cpp:95-101).
 // ---------------------------------------------------------------------------------------------------------------
@@ -883,15 +930,36 @@ k_forward_kinematics(const __grid_constant__ RobotDev rb, const double *__restri
 // ---------------------------------------------------------------------------------------------------------------
 // Launchers
 // ---------------------------------------------------------------------------------------------------------------
-static int sm_count() {
-	static int n = 0;
-	if (!n) {
-		int dev = 0;
-		cudaGetDevice(&dev);
-		cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-		if (n <= 0) n = 148;
+static int sm_count() {  // of the current device (a process may drive several)
+	int dev = 0, n = 0;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+	return n > 0 ? n : 148;
+}
+
+/// Environment knobs, read once (thread-safe: function-local static of a struct initialised by one expression).
+struct Knobs {
+	int pipeline, pipe_refill_min, pipe_blocks, pipe_claim, no_prefilter, traverse_blocks, refill_min, leaf_min, trim;
+	unsigned head_steps;
+	size_t queue_max_items, survivor_max_entries;
+	static int geti(const char *name, int dflt) {
+		const char *e = getenv(name);
+		return e ? atoi(e) : dflt;
 	}
-	return n;
+	static size_t getz(const char *name, size_t dflt) {
+		const char *e = getenv(name);
+		return e && atoll(e) > 0 ? (size_t) atoll(e) : dflt;
+	}
+	Knobs()
+		: pipeline(geti("MGODPL_PIPELINE", 0)), pipe_refill_min(geti("MGODPL_PIPE_REFILL_MIN", 8)), pipe_blocks(geti("MGODPL_PIPE_BLOCKS", 4)), pipe_claim(geti("MGODPL_PIPE_CLAIM", 0)),
+		  no_prefilter(geti("MGODPL_NO_PREFILTER", 0)), traverse_blocks(geti("MGODPL_TRAVERSE_BLOCKS", 4)), refill_min(geti("MGODPL_REFILL_MIN", 16)),
+		  leaf_min(geti("MGODPL_LEAF_MIN", 8)), trim(geti("MGODPL_TRIM", 16)),
+		  head_steps(geti("MGODPL_HEAD_STEPS", 0) > 0 ? (unsigned) geti("MGODPL_HEAD_STEPS", 0) : 0u),
+		  queue_max_items(getz("MGODPL_QUEUE_MAX_ITEMS", QUEUE_MAX_ITEMS)), survivor_max_entries(getz("MGODPL_SURVIVOR_MAX_ENTRIES", SURVIVOR_MAX_ENTRIES)) {}
+};
+static const Knobs &knobs() {
+	static const Knobs k;
+	return k;
 }
 /// Grids are a multiple of the SM count (148 on B200) times the resident blocks per SM, or smaller for small inputs.
 static unsigned grid_for(size_t work_items, int block, int blocks_per_sm) {
@@ -904,24 +972,11 @@ size_t state_survivor_slots(size_t n) { return n + n / 4 + SHARDS * SHARD_BLOCK;
 
 /// Capacity limits of the two work lists.  MGODPL_QUEUE_MAX_ITEMS / MGODPL_SURVIVOR_MAX_ENTRIES shrink them (tests use
 /// this to drive every query through the inline overflow paths).
-static size_t queue_max_items() {
-	static size_t v = 0;
-	if (!v) {
-		const char *e = getenv("MGODPL_QUEUE_MAX_ITEMS");
-		v = e && atoll(e) > 0 ? (size_t) atoll(e) : QUEUE_MAX_ITEMS;
-	}
-	return v;
-}
-static size_t survivor_max_entries() {
-	static size_t v = 0;
-	if (!v) {
-		const char *e = getenv("MGODPL_SURVIVOR_MAX_ENTRIES");
-		v = e && atoll(e) > 0 ? (size_t) atoll(e) : SURVIVOR_MAX_ENTRIES;
-	}
-	return v;
-}
+static size_t queue_max_items() { return knobs().queue_max_items; }
+static size_t survivor_max_entries() { return knobs().survivor_max_entries; }
 
 size_t query_scratch_bytes(size_t worst_case_boxes, size_t survivor_entries) {
+	if (knobs().pipeline) worst_case_boxes = 0;  // the fused kernel keeps its boxes in shared memory: no queue in HBM
 	size_t cap = worst_case_boxes < queue_max_items() ? worst_case_boxes : queue_max_items();
 	size_t scap = survivor_entries < survivor_max_entries() ? survivor_entries : survivor_max_entries();
 	return SCRATCH_HEADER + ((scap * sizeof(uint2) + 255) & ~(size_t) 255) + (cap ? cap : 1) * sizeof(Item);
@@ -970,15 +1025,8 @@ static QueueDev carve_queue(void *scratch, size_t scratch_bytes) {
 static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const double *explicit_boxes, const QueueDev &Q,
 								const Results &res, size_t worst_case_items, cudaStream_t stream) {
 	size_t bound = worst_case_items < Q.cap ? worst_case_items : Q.cap;
-	static int min_blocks = 0;
-	static TraverseTuning tune{16, 8, 0};
-	if (!min_blocks) {
-		const char *e = getenv("MGODPL_TRAVERSE_BLOCKS");
-		min_blocks = e ? atoi(e) : 4;
-		if ((e = getenv("MGODPL_REFILL_MIN"))) tune.refill_min = atoi(e);
-		if ((e = getenv("MGODPL_LEAF_MIN"))) tune.leaf_min = atoi(e);
-		if ((e = getenv("MGODPL_NO_PREFILTER"))) tune.no_prefilter = atoi(e);
-	}
+	const int min_blocks = knobs().traverse_blocks;
+	const TraverseTuning tune{knobs().refill_min, knobs().leaf_min, knobs().no_prefilter};
 	const bool wide = sc.wide != nullptr;
 #define MGODPL_LAUNCH_TRAVERSE(MB)                                                                                                      \
 	if (wide) k_traverse<MB, true><<<grid_for(bound, BLOCK_B, MB), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune);       \
@@ -991,6 +1039,35 @@ static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const do
 	}
 #undef MGODPL_LAUNCH_TRAVERSE
 	return cudaGetLastError();
+}
+
+/// The fused expansion + traversal kernel (pipeline.cuh) over `bound` candidates at most.
+template<int KIND, bool CHAIN, bool WIDE>
+static cudaError_t launch_pipeline_inst(const SceneDev &sc, const RobotDev &rb, const SourceArgs &src, unsigned *cursor, const Results &res,
+										size_t bound, cudaStream_t stream) {
+	constexpr size_t smem = (BLOCK_P / 32) * sizeof(WarpMem);
+	auto kernel = k_pipeline<KIND, CHAIN, WIDE>;
+	LQ_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));  // per device, idempotent
+	PipeTuning tune{knobs().pipe_refill_min, knobs().no_prefilter, 32u * CLAIM_ROUNDS};
+	const size_t resident = (size_t) sm_count() * (size_t) std::max(1, std::min(knobs().pipe_blocks, 4));
+	// small batches: one claim of 32 per warp so that the work spreads over the SMs; large ones: fewer cursor atomics
+	if (bound < resident * (BLOCK_P / 32) * tune.claim) tune.claim = 32u;
+	if (knobs().pipe_claim > 0) tune.claim = 32u * (unsigned) knobs().pipe_claim;
+	size_t blocks = (bound + (BLOCK_P / 32) * tune.claim - 1) / ((BLOCK_P / 32) * tune.claim);
+	blocks = std::max<size_t>(1, std::min(blocks, resident));
+	kernel<<<(unsigned) blocks, BLOCK_P, smem, stream>>>(sc, rb, src, cursor, res, tune);
+	return cudaGetLastError();
+}
+template<int KIND>
+static cudaError_t launch_pipeline(const SceneDev &sc, const RobotDev &rb, const SourceArgs &src, unsigned *cursor, const Results &res, size_t bound,
+								   cudaStream_t stream) {
+	if (!sc.n_nodes && KIND != SRC_GOALS) return cudaSuccess;  // an empty scene collides with nothing (goal sampling still writes its states)
+	if (bound >= 0xFFF00000ull) return cudaErrorInvalidValue;   // the candidate cursor is 32 bits wide
+	const bool wide = sc.wide != nullptr, chain = KIND == SRC_BOXES || rb.chain;
+	if (wide) return chain ? launch_pipeline_inst<KIND, true, true>(sc, rb, src, cursor, res, bound, stream)
+						   : launch_pipeline_inst<KIND, KIND == SRC_BOXES, true>(sc, rb, src, cursor, res, bound, stream);
+	return chain ? launch_pipeline_inst<KIND, true, false>(sc, rb, src, cursor, res, bound, stream)
+				 : launch_pipeline_inst<KIND, KIND == SRC_BOXES, false>(sc, rb, src, cursor, res, bound, stream);
 }
 
 /// Stage A2 + B run in passes over the candidates so that a pass can never produce more boxes than the queue holds
@@ -1031,13 +1108,14 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
-	static bool attr = false;
-	if (!attr) {
-		cudaFuncSetAttribute(k_cull_states, cudaFuncAttributeMaxDynamicSharedMemorySize, BLOCK_A * ROW_MAX * 8);
-		attr = true;
-	}
+	if (knobs().pipeline) Q.cap = 0;  // the fused kernel keeps its boxes on chip; only stage A1's overflow path would queue, and traverses inline instead
 	k_cull_states<<<grid_for(n, BLOCK_A, 8), BLOCK_A, BLOCK_A * stride * sizeof(double), stream>>>(sc, rb, d_states, n, stride, S, Q, res);
 	LQ_CHECK(cudaGetLastError());
+	if (knobs().pipeline) {
+		SourceArgs src{};
+		src.list[0] = S, src.n_lists = 1, src.states = d_states, src.stride = stride;
+		return launch_pipeline<SRC_STATES>(sc, rb, src, Q.cursor, res, std::min<size_t>(S.cap, n + SHARDS * SHARD_BLOCK) * (size_t) ((rb.n_boxes + SPL - 1) / SPL > 0 ? (rb.n_boxes + SPL - 1) / SPL : 1), stream);
+	}
 	const size_t R = pass_size(Q, rb.n_boxes);
 	size_t end = S.cap;
 	if (end > R) LQ_CHECK(survivor_slot_ranges(&S, 1, stream, &end));
@@ -1058,6 +1136,12 @@ cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	RobotDev none{};
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
+	if (knobs().pipeline) {
+		LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
+		SourceArgs src{};
+		src.boxes = d_boxes, src.total = n;
+		return launch_pipeline<SRC_BOXES>(sc, none, src, Q.cursor, res, n, stream);
+	}
 	const size_t R = pass_size(Q, 1);
 	for (size_t lo = 0; lo < n; lo += R) {
 		const size_t hi = lo + R < n ? lo + R : n;
@@ -1076,25 +1160,28 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	if (!m) return cudaSuccess;
 	SurvivorsDev S, S_tail;
 	QueueDev Q;
-	static unsigned head_steps = 0;
-	if (!head_steps) {
-		const char *e = getenv("MGODPL_HEAD_STEPS");
-		head_steps = e && atoi(e) > 0 ? (unsigned) atoi(e) : 0x80000000u;  // default: adaptive per motion
-	}
-	const unsigned head_arg = head_steps == 0x80000000u ? 0u : head_steps;
-	static int trim = -1;
-	if (trim < 0) {
-		const char *e = getenv("MGODPL_TRIM");
-		trim = e ? atoi(e) : 16;
-	}
+	const unsigned head_arg = knobs().head_steps;  // 0: adaptive per motion
+	const int trim = knobs().trim;
 	carve(scratch, scratch_bytes, survivor_entries, &S, &Q, &S_tail, m * (size_t) (head_arg ? head_arg : 48u));
 	Results res{RESULT_FIRST_STEP, nullptr, d_first_step};
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_first_step, 0xff, m * sizeof(unsigned), stream));
 	if (d_uncertain) LQ_CHECK(cudaMemsetAsync(d_uncertain, 0, ((m + 31) / 32) * 4, stream));
+	if (knobs().pipeline) Q.cap = 0;
 	k_motion_ranges<<<grid_for(m, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
 																	  d_n_steps, d_uncertain, (SlerpConst *) d_slerp, S, S_tail, head_arg, trim, Q, res);
 	LQ_CHECK(cudaGetLastError());
+	if (knobs().pipeline) {
+		// one launch walks the head list, then the tail list: by the time a warp reaches a motion's tail steps, the head steps of
+		// (almost) every motion have been decided, and tail steps behind a hit are dropped when they are claimed
+		SourceArgs src{};
+		src.list[0] = S, src.list[1] = S_tail, src.n_lists = 2, src.a = d_a, src.b = d_b, src.stride = stride;
+		src.n_steps = d_n_steps, src.slerp = (const SlerpConst *) d_slerp;
+		const size_t groups = (size_t) std::max(1, (rb.n_boxes + SPL - 1) / SPL);
+		LQ_CHECK(launch_pipeline<SRC_MOTION_STEPS>(sc, rb, src, Q.cursor, res, ((size_t) S.cap + S_tail.cap) * groups, stream));
+		k_finish_motions<<<(unsigned) ((m + 255) / 256), 256, 0, stream>>>(d_first_step, d_n_steps, m, d_hit_bits, d_toi);
+		return cudaGetLastError();
+	}
 	// Head list first (the steps right after a motion comes within reach of the scene), then the tail with the
 	// "already collided" skip: most of a colliding motion's in-reach steps lie after its first hit.
 	const size_t R = pass_size(Q, rb.n_boxes);
@@ -1129,6 +1216,18 @@ cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const do
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	const size_t wpr = (s + 31) / 32, total = f * s;
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, f * wpr * 4, stream));
+	if (knobs().pipeline) {
+		LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
+		SourceArgs src{};
+		src.targets = d_targets, src.draws = d_draws, src.limits = d_limits, src.rows = f, src.per_row = s, src.seed = seed;
+		src.distance_from_target = distance_from_target, src.states_out = d_states_out, src.total = total;
+		LQ_CHECK(launch_pipeline<SRC_GOALS>(sc, rb, src, Q.cursor, res, total * (size_t) std::max(1, (rb.n_boxes + SPL - 1) / SPL), stream));
+		if (d_collisions) {
+			k_count_rows<<<(unsigned) f, 128, 0, stream>>>(d_hit_bits, f, wpr, d_collisions);
+			LQ_CHECK(cudaGetLastError());
+		}
+		return cudaSuccess;
+	}
 	const size_t R = pass_size(Q, rb.n_boxes);  // the callers size the queue with 1/8 head-room for shard imbalance
 	for (size_t lo = 0; lo < total; lo += R) {
 		const size_t hi = lo + R < total ? lo + R : total;

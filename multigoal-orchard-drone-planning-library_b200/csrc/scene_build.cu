@@ -370,6 +370,101 @@ __global__ void k_fold_wide(const float4 *__restrict__ nodes, unsigned n_nodes, 
 	}
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Clearance grid (SceneDev::clear): one thread per cell runs a nearest-triangle query from the cell centre over the
+// binary records (nearest child first, subtrees beyond the best distance so far pruned), in fp32 on origin-relative
+// coordinates.  Everything errs towards SMALLER clearances: the triangle distance is the minimum over the three edge
+// segments and (where the projection falls inside, judged generously) the plane — each the distance to some point of
+// the triangle or less; then the cell's half diagonal (the distance is 1-Lipschitz) and a safety term are subtracted
+// and the value is rounded down to the u8 quantum.
+// ---------------------------------------------------------------------------------------------------------------
+struct F3 {
+	float x, y, z;
+};
+__device__ __forceinline__ F3 f3sub(F3 a, F3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ float f3dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float seg_dist2(F3 p, F3 a, F3 b) {
+	const F3 ab = f3sub(b, a), ap = f3sub(p, a);
+	const float l2 = f3dot(ab, ab);
+	float t = l2 > 0.f ? f3dot(ap, ab) / l2 : 0.f;
+	t = fminf(fmaxf(t, 0.f), 1.f);
+	const F3 d{ap.x - t * ab.x, ap.y - t * ab.y, ap.z - t * ab.z};
+	return f3dot(d, d);
+}
+__device__ __forceinline__ float tri_dist2_lower(F3 p, F3 a, F3 b, F3 c) {
+	float d2 = fminf(seg_dist2(p, a, b), fminf(seg_dist2(p, b, c), seg_dist2(p, c, a)));
+	const F3 ab = f3sub(b, a), ac = f3sub(c, a), ap = f3sub(p, a);
+	const F3 n{ab.y * ac.z - ab.z * ac.y, ab.z * ac.x - ab.x * ac.z, ab.x * ac.y - ab.y * ac.x};
+	const float n2 = f3dot(n, n);
+	if (n2 > 0.f) {
+		// barycentric sign tests of the projection, with slack: a projection wrongly taken for "inside" can only lower the result
+		const F3 bp = f3sub(p, b), cp = f3sub(p, c), bc = f3sub(c, b), ca = f3sub(a, c);
+		auto side = [&](F3 e, F3 q) { return (e.y * q.z - e.z * q.y) * n.x + (e.z * q.x - e.x * q.z) * n.y + (e.x * q.y - e.y * q.x) * n.z; };
+		const float slack = -1e-3f * n2;
+		if (side(ab, ap) >= slack && side(bc, bp) >= slack && side(ca, cp) >= slack) {
+			const float h = f3dot(ap, n);
+			d2 = fminf(d2, h * h / n2);
+		}
+	}
+	return d2;
+}
+__device__ __forceinline__ float box_dist2(F3 p, float cx, float cy, float cz, float hx, float hy, float hz) {
+	const float dx = fmaxf(fabsf(p.x - cx) - hx, 0.f), dy = fmaxf(fabsf(p.y - cy) - hy, 0.f), dz = fmaxf(fabsf(p.z - cz) - hz, 0.f);
+	return dx * dx + dy * dy + dz * dz;
+}
+
+__global__ void __launch_bounds__(TB)
+k_clearance_grid(const float4 *__restrict__ nodes, const float4 *__restrict__ tris32, int nx, int ny, int nz, F3 lo, float cell,
+				 float cmax, float quantum, unsigned char *__restrict__ out) {
+	const size_t i = (size_t) blockIdx.x * TB + threadIdx.x;
+	if (i >= (size_t) nx * ny * nz) return;
+	const int ix = (int) (i % nx), iy = (int) ((i / nx) % ny), iz = (int) (i / ((size_t) nx * ny));
+	const F3 p{lo.x + (ix + 0.5f) * cell, lo.y + (iy + 0.5f) * cell, lo.z + (iz + 0.5f) * cell};
+	const float half_diag = 0.8660255f * cell, safety = 2e-4f + 1e-5f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z));
+	const float cutoff = cmax + half_diag + safety;
+	float best2 = cutoff * cutoff;
+	int stack[64];
+	float stack_d2[64];
+	int sp = 0, cur = 0;
+	while (true) {
+		if (cur >= 0) {
+			const float4 *rec = nodes + 4ull * (unsigned) cur;
+			const float4 n0 = __ldg(rec), n1 = __ldg(rec + 1), n2 = __ldg(rec + 2), n3 = __ldg(rec + 3);
+			const float dl = box_dist2(p, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y), dr = box_dist2(p, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w);
+			const int lref = __float_as_int(n3.x), rref = __float_as_int(n3.y);
+			const bool tl = dl < best2, tr = dr < best2;
+			if (tl && tr) {
+				const bool right_first = dr < dl;
+				stack[sp] = right_first ? lref : rref, stack_d2[sp] = right_first ? dl : dr, ++sp;
+				cur = right_first ? rref : lref;
+				continue;
+			}
+			if (tl || tr) {
+				cur = tl ? lref : rref;
+				continue;
+			}
+		} else {
+			const unsigned info = (unsigned) (-1 - cur), first = info >> 4, cnt = (info & 15u) + 1u;
+			for (unsigned k = 0; k < cnt; ++k) {
+				const float4 a = __ldg(tris32 + 3ull * (first + k)), b = __ldg(tris32 + 3ull * (first + k) + 1), c = __ldg(tris32 + 3ull * (first + k) + 2);
+				best2 = fminf(best2, tri_dist2_lower(p, F3{a.x, a.y, a.z}, F3{b.x, b.y, b.z}, F3{c.x, c.y, c.z}));
+			}
+		}
+		bool found = false;
+		while (sp > 0) {
+			--sp;
+			if (stack_d2[sp] < best2) {
+				cur = stack[sp], found = true;
+				break;
+			}
+		}
+		if (!found) break;
+	}
+	const float d = fminf(fmaxf(sqrtf(best2) - half_diag - safety, 0.f), cmax);
+	out[i] = (unsigned char) fminf(floorf(d / quantum), 255.f);
+}
+
 struct Scratch {
 	std::vector<void *> ptrs;
 	template<class T>
@@ -392,7 +487,8 @@ struct Scratch {
 	} while (0)
 
 cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris, size_t nt, const double *lo, const double *hi,
-						const double *origin, unsigned max_leaf_size, bool refine, bool wide, BuiltScene *out, cudaStream_t stream) {
+						const double *origin, unsigned max_leaf_size, bool refine, bool wide, bool clearance_grid, BuiltScene *out,
+						cudaStream_t stream) {
 	(void) nv;
 	(void) refine;
 	*out = BuiltScene{};
@@ -535,11 +631,43 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 	float4 h_root[2];
 	BS_CHECK(cudaMemcpyAsync(h_root, d_root_box, sizeof(h_root), cudaMemcpyDeviceToHost, stream));
 	BS_CHECK(cudaEventRecord(ev1, stream));
+	cudaEvent_t ev2 = nullptr;
+	if (clearance_grid) {
+		// grid over the scene bounds grown by CLEAR_PAD; cell size from a cell budget, never finer than 2 cm
+		const double pad = CLEAR_PAD;
+		double ext[3], vol = 1.0;
+		for (int a = 0; a < 3; ++a) ext[a] = (hi[a] - lo[a]) + 2.0 * pad, vol *= ext[a];
+		static size_t max_cells = 0;
+		if (!max_cells) {
+			const char *e = getenv("MGODPL_CLEARANCE_CELLS");
+			max_cells = e && atoll(e) > 0 ? (size_t) atoll(e) : (size_t) 6 << 20;
+		}
+		double cell = std::max(0.02, std::cbrt(vol / (double) max_cells));
+		int dims[3];
+		for (int a = 0; a < 3; ++a) dims[a] = std::max(1, (int) std::ceil(ext[a] / cell));
+		const size_t cells = (size_t) dims[0] * dims[1] * dims[2];
+		BS_CHECK(cudaMalloc((void **) &out->clear, cells));
+		for (int a = 0; a < 3; ++a) out->clear_n[a] = dims[a], out->clear_lo[a] = (float) (lo[a] - pad - origin[a]);
+		out->clear_cell = (float) cell, out->clear_max = (float) pad, out->clear_quantum = (float) (pad / 255.0);
+		k_clearance_grid<<<(unsigned) ((cells + TB - 1) / TB), TB, 0, stream>>>(out->nodes, out->tris32, dims[0], dims[1], dims[2],
+																				   F3{out->clear_lo[0], out->clear_lo[1], out->clear_lo[2]}, out->clear_cell,
+																				   out->clear_max, out->clear_quantum, out->clear);
+		BS_CHECK(cudaGetLastError());
+		BS_CHECK(cudaEventCreate(&ev2));
+		BS_CHECK(cudaEventRecord(ev2, stream));
+		out->device_bytes_extra = cells;
+	}
 	BuildStats st{};
 	BS_CHECK(cudaMemcpyAsync(&st, d_stats, sizeof(st), cudaMemcpyDeviceToHost, stream));
 	BS_CHECK(cudaStreamSynchronize(stream));
 	float ms = 0;
 	cudaEventElapsedTime(&ms, ev0, ev1);
+	if (ev2) {
+		float ms2 = 0;
+		cudaEventElapsedTime(&ms2, ev1, ev2);
+		out->clear_build_ms = ms2;
+		cudaEventDestroy(ev2);
+	}
 	cudaEventDestroy(ev0);
 	cudaEventDestroy(ev1);
 	out->n_nodes = n_nodes;
@@ -550,7 +678,7 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 	out->sah_cost = st.sah;
 	out->build_ms = ms;
 	out->n_wide = n_wide;
-	out->device_bytes = (size_t) n_nodes * 64 + (size_t) n_wide * 128 + nt * 72 + nt * 48 + nt * 4;
+	out->device_bytes = (size_t) n_nodes * 64 + (size_t) n_wide * 128 + nt * 72 + nt * 48 + nt * 4 + out->device_bytes_extra;
 	float rc[3], rh[3];
 	{
 		// same outward rounding as the device (centre in fp32, half extent padded by the centre's rounding error)

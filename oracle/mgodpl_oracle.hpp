@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <limits>
 #include <numeric>
+#include <optional>
 #include <functional>
 #include <queue>
 #include <random>
@@ -689,6 +690,54 @@ inline State from_end_effector_and_vector(const Robot &robot, const V3 &ee_point
 	V3 ee = fk[robot.find_link("end_effector")].t;
 	s.base.t = s.base.t + ee_point - ee;
 	return s;
+}
+
+/// state_tools.cpp:69-75 — the direction the arm points in: the end effector's orientation applied to -y.
+inline V3 arm_vector_from_state(const Robot &robot, const State &s) {
+	auto fk = forward_kinematics(robot, s.joints.data(), robot.find_link("flying_base"), s.base);
+	return qrot(fk[robot.find_link("end_effector")].q, V3{0.0, -1.0, 0.0});
+}
+using StateFn = std::function<bool(const State &)>;
+/// goal_sampling.cpp:101-124 — up to max_attempts x (three fresh Gaussians -> unit vector -> fromEndEffectorAndVector ->
+/// state check); the first collision-free candidate is returned.
+inline std::optional<State> generate_uniform_random_arm_vector_state(const Robot &robot, const StateFn &collides, const V3 &fruit_center,
+																	 Rng &rng, int max_attempts, double ee_distance) {
+	for (int attempt = 0; attempt < max_attempts; ++attempt) {
+		// The reference writes `math::Vec3d arm_vec(rng.gaussian01(), rng.gaussian01(), rng.gaussian01())`: the order in which
+		// the three arguments are evaluated is unspecified in C++.  clang (the reference's own toolchain, flake.nix:19-28)
+		// goes left to right, GCC right to left; the restatement follows whichever compiler builds it, so that it agrees
+		// with oracle/_ref (the reference's sources under the same compiler) draw for draw.
+#if defined(__clang__)
+		const double gx = rng.gaussian01(), gy = rng.gaussian01(), gz = rng.gaussian01();
+#else
+		const double gz = rng.gaussian01(), gy = rng.gaussian01(), gx = rng.gaussian01();
+#endif
+		const double norm = std::sqrt(gx * gx + gy * gy + gz * gz);  // Vec3d::normalized (Vec3.h:276-278): component / norm
+		const V3 v{gx / norm, gy / norm, gz / norm};
+		State cand = from_end_effector_and_vector(robot, fruit_center - v * ee_distance, V3{-v.x, -v.y, -v.z});
+		if (!collides(cand)) return cand;
+	}
+	return std::nullopt;
+}
+/// goal_sampling.cpp:81-99 — findGoalStateByUniformSampling.
+inline std::optional<State> find_goal_state_by_uniform_sampling(const V3 &target, const Robot &robot, int flying_base, int end_effector,
+																const StateFn &collides, Rng &rng, size_t max_attempts) {
+	for (size_t i = 0; i < max_attempts; ++i) {
+		State s = gen_goal_state_uniform(rng, target, 0.0, robot, flying_base, end_effector);
+		if (!collides(s)) return s;
+	}
+	return std::nullopt;
+}
+/// goal_sampling.cppm:37-56 — at most max_samples x (sample -> state check -> operation); the first non-empty result wins.
+template<class T>
+std::optional<T> try_at_valid_goal_samples(const StateFn &collides, const std::function<State()> &goal_sample, int max_samples,
+										   const std::function<std::optional<T>(const State &)> &operation) {
+	for (int i = 0; i < max_samples; ++i) {
+		State goal = goal_sample();
+		if (!collides(goal))
+			if (auto r = operation(goal)) return r;
+	}
+	return std::nullopt;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -349,6 +349,34 @@ def from_ee_and_vector(robot: Robot, point, vec):
     return out
 
 
+def arm_vector(robot: Robot, state):
+    state = _arr(state)
+    out = np.zeros(3)
+    lib().orc_arm_vector(robot.h, _d(state), len(state) - 7, _d(out))
+    return out
+
+
+def _sample_goal_states(L, fn, scene, robot, which, targets, seed, max_attempts, ee_distance, row):
+    targets = _arr(targets).reshape(-1, 3)
+    n = len(targets)
+    out = np.zeros((n, row))
+    found = np.zeros(n, np.uint8)
+    nxt = np.zeros(n, np.uint32)
+    getattr(L, fn)(scene.h, robot.h, which, C.c_uint(seed), _d(targets), C.c_size_t(n), int(max_attempts), C.c_double(ee_distance),
+                   _d(out), found.ctypes.data_as(_u8p), nxt.ctypes.data_as(_u32p))
+    return dict(states=out, found=found.astype(bool), next_draw=nxt)
+
+
+def sample_arm_vector_states(scene: "Scene", robot: Robot, targets, seed=42, max_attempts=100, ee_distance=0.0):
+    """generateUniformRandomArmVectorState (goal_sampling.cpp:101-124) per target with std::mt19937(seed + i)."""
+    return _sample_goal_states(lib(), "orc_sample_goal_states", scene, robot, 0, targets, seed, max_attempts, ee_distance, 8)
+
+
+def sample_uniform_goal_states(scene: "Scene", robot: Robot, targets, seed=42, max_attempts=100):
+    """findGoalStateByUniformSampling (goal_sampling.cpp:81-99) per target with std::mt19937(seed + i)."""
+    return _sample_goal_states(lib(), "orc_sample_goal_states", scene, robot, 1, targets, seed, max_attempts, 0.0, 7 + robot.n_variables)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # The reference's own sources (oracle/_ref) — same call shapes, for cross-checking the restatement.
 # ---------------------------------------------------------------------------------------------------------------
@@ -449,3 +477,18 @@ def ref_from_ee_and_vector(robot: RefRobot, point, vec):
     out = np.zeros(8)
     ref().ref_from_ee_and_vector(robot.h, _d(_arr(point)), _d(_arr(vec)), _d(out))
     return out
+
+
+def ref_arm_vector(robot: RefRobot, state):
+    state = _arr(state)
+    out = np.zeros(3)
+    ref().ref_arm_vector(robot.h, _d(state), len(state) - 7, _d(out))
+    return out
+
+
+def ref_sample_arm_vector_states(scene: "RefScene", robot: RefRobot, targets, seed=42, max_attempts=100, ee_distance=0.0):
+    return _sample_goal_states(ref(), "ref_sample_goal_states", scene, robot, 0, targets, seed, max_attempts, ee_distance, 8)
+
+
+def ref_sample_uniform_goal_states(scene: "RefScene", robot: RefRobot, targets, n_variables: int, seed=42, max_attempts=100):
+    return _sample_goal_states(ref(), "ref_sample_goal_states", scene, robot, 1, targets, seed, max_attempts, 0.0, 7 + n_variables)

@@ -294,6 +294,32 @@ void orc_from_ee_and_vector(void *robot, const double *point3, const double *vec
 	store_state(from_end_effector_and_vector(*(Robot *) robot, {point3[0], point3[1], point3[2]}, {vec3[0], vec3[1], vec3[2]}), out8);
 }
 
+void orc_arm_vector(void *robot, const double *state, int js, double *out3) {
+	V3 v = arm_vector_from_state(*(Robot *) robot, load_state(state, js));
+	out3[0] = v.x, out3[1] = v.y, out3[2] = v.z;
+}
+/// generateUniformRandomArmVectorState / findGoalStateByUniformSampling (goal_sampling.cpp:81-124) for n targets, each with a
+/// fresh std::mt19937(seed + i) and the oracle's check_robot_collision.  out: n x 8 (found ? state : NaN), found: n flags,
+/// next_draw: n x the generator's next raw output (pins how many draws the loop consumed).  which: 0 arm-vector, 1 uniform.
+void orc_sample_goal_states(void *scene, void *robot, int which, unsigned seed, const double *targets, size_t n, int max_attempts,
+							double ee_distance, double *out, uint8_t *found, uint32_t *next_draw) {
+	auto &rb = *(Robot *) robot;
+	auto &sc = *(Scene *) scene;
+	const int fb = rb.find_link("flying_base"), ee = rb.find_link("end_effector");
+	const size_t row = 7 + (which == 0 ? 1 : (size_t) rb.n_variables());
+	StateFn collides = [&](const State &s) { return check_robot_collision(rb, sc, s); };
+	for (size_t i = 0; i < n; ++i) {
+		Rng rng(seed + (unsigned) i);
+		const V3 t{targets[3 * i], targets[3 * i + 1], targets[3 * i + 2]};
+		std::optional<State> s = which == 0 ? generate_uniform_random_arm_vector_state(rb, collides, t, rng, max_attempts, ee_distance)
+											: find_goal_state_by_uniform_sampling(t, rb, fb, ee, collides, rng, (size_t) max_attempts);
+		found[i] = s.has_value();
+		for (size_t k = 0; k < row; ++k) out[i * row + k] = std::numeric_limits<double>::quiet_NaN();
+		if (s) store_state(*s, out + i * row);
+		next_draw[i] = (uint32_t) rng.uniform_integer(0, std::numeric_limits<int>::max());
+	}
+}
+
 // ---- local optimisation (shortcutting) ---------------------------------------------------------------------
 /// Runs one of the reference's path optimisers on a path of w states with one std::mt19937(seed) stream and the
 /// oracle's check_motion_collides as the motion check.  mode 0: `iterations` x tryShortcuttingRandomlyGlobally

@@ -139,6 +139,30 @@ void ref_from_ee_and_vector(void *robot, const double *point3, const double *vec
 										 math::Vec3d(vec3[0], vec3[1], vec3[2])), out8);
 }
 
+void ref_arm_vector(void *robot, const double *state, int js, double *out3) {
+	math::Vec3d v = arm_vector_from_state(*(robot_model::RobotModel *) robot, load_state(state, js));
+	out3[0] = v.x(), out3[1] = v.y(), out3[2] = v.z();
+}
+/// Same contract as orc_sample_goal_states, over the reference's own goal_sampling.cpp (generateUniformRandomArmVectorState,
+/// findGoalStateByUniformSampling) and collision_detection.cpp.
+void ref_sample_goal_states(void *scene, void *robot, int which, unsigned seed, const double *targets, size_t n, int max_attempts,
+							double ee_distance, double *out, uint8_t *found, uint32_t *next_draw) {
+	auto &rb = *(robot_model::RobotModel *) robot;
+	auto &sc = *(RefScene *) scene;
+	const auto fb = rb.findLinkByName("flying_base"), ee = rb.findLinkByName("end_effector");
+	const size_t row = 7 + (which == 0 ? 1 : rb.count_joint_variables());
+	for (size_t i = 0; i < n; ++i) {
+		random_numbers::RandomNumberGenerator rng(seed + (unsigned) i);
+		const math::Vec3d t(targets[3 * i], targets[3 * i + 1], targets[3 * i + 2]);
+		std::optional<RobotState> s = which == 0 ? generateUniformRandomArmVectorState(rb, sc.object, t, rng, max_attempts, ee_distance)
+												 : findGoalStateByUniformSampling(t, rb, fb, ee, sc.object, rng, (size_t) max_attempts);
+		found[i] = s.has_value();
+		for (size_t k = 0; k < row; ++k) out[i * row + k] = std::numeric_limits<double>::quiet_NaN();
+		if (s) store_state(*s, out + i * row);
+		next_draw[i] = (uint32_t) rng.uniformInteger(0, std::numeric_limits<int>::max());
+	}
+}
+
 /// Same contract as orc_shortcut_path, over the reference's own local_optimization.cpp / RobotPath.cpp.
 long ref_shortcut_path(void *scene, void *robot, const double *states, size_t w, size_t stride, int js, unsigned seed,
 					   size_t iterations, int mode, double pull, double *out_states, size_t out_cap, size_t *out_w,

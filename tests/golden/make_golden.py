@@ -76,6 +76,19 @@ for case, (first, seed, iters, mode) in enumerate([(200, 5, 30, o.SHORTCUT_GLOBA
     short.append(dict(first_state=first, n_waypoints=14, seed=seed, iterations=iters, mode=mode, pull=0.5,
                       n_success=r["n_success"], n_checks=r["n_checks"], path=hx(r["path"]), path_shape=list(r["path"].shape)))
 out["shortcutting"] = short
+# a17 / a18: arm_vector_from_state (state_tools.cpp:69-75), generateUniformRandomArmVectorState and
+# findGoalStateByUniformSampling (goal_sampling.cpp:81-124) on the same scene, one std::mt19937(seed + i) per target.
+# (The three Gaussians of an arm vector are constructor arguments, evaluated in an unspecified order: these vectors hold
+# what g++ — the compiler oracle/_ref is built with — produces; see oracle/mgodpl_oracle.hpp.)
+targets = np.concatenate([tree.fruit_centers, np.array([[0.4, 0.3, 1.2], [-0.5, 0.2, 2.0], [0.1, -0.6, 2.6], [0.9, 0.9, 1.0]])])
+av = o.ref_sample_arm_vector_states(rs, rr, targets, seed=11, max_attempts=40, ee_distance=0.05)
+ug = o.ref_sample_uniform_goal_states(rs, rr, targets, 1, seed=5, max_attempts=12)
+out["goal_states"] = dict(targets=hx(targets), n_targets=len(targets),
+                          arm_vector=dict(seed=11, max_attempts=40, ee_distance=0.05, found=[int(x) for x in av["found"]],
+                                          next_draw=[int(x) for x in av["next_draw"]], states=hx(np.nan_to_num(av["states"], nan=-7.0))),
+                          uniform=dict(seed=5, max_attempts=12, found=[int(x) for x in ug["found"]], next_draw=[int(x) for x in ug["next_draw"]],
+                                       states=hx(np.nan_to_num(ug["states"], nan=-7.0))),
+                          arm_vector_of=hx(np.stack([o.ref_arm_vector(rr, x[:8]) for x in st[:16]])))
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.json"), "w") as f:
     json.dump(out, f, indent=1)
 print("wrote reference_vectors.json:", len(out["robots"]), "robots;", int(hits.sum()), "/ 400 states collide;",

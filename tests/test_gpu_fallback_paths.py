@@ -60,6 +60,8 @@ def test_overflow_and_no_prefilter_paths_agree_with_the_fast_path(gpu):
         "binary records with tiny lists": {"MGODPL_WIDE_BVH": "0", "MGODPL_QUEUE_MAX_ITEMS": "64", "MGODPL_SURVIVOR_MAX_ENTRIES": "128"},
         "no range trimming / deep trimming": {"MGODPL_TRIM": "0"},
         "fixed head of 4 steps": {"MGODPL_HEAD_STEPS": "4"},
+        "no clearance grid (bounds / root-record culls only)": {"MGODPL_CLEARANCE_GRID": "0"},
+        "coarse clearance grid (4096 cells)": {"MGODPL_CLEARANCE_CELLS": "4096"},
     }
     for name, env in variants.items():
         got = run_variant(env)

@@ -196,6 +196,27 @@ def test_golden_shortcutting(oracle, golden, mg):
 
 
 # ---- live cross-check against the reference's own sources (present in the build container and, prebuilt, on the box) --
+def test_golden_goal_states(oracle, golden, mg):
+    """a17 / a18 from the reference's sources: arm_vector_from_state, generateUniformRandomArmVectorState,
+    findGoalStateByUniformSampling — same states, found after the same number of generator draws."""
+    g, gs = golden["scene"], golden["goal_states"]
+    mesh = mg.scenes.make_tree(**g["tree"]).trunk_mesh
+    r = oracle.Robot(g["robot"][0], tuple(g["robot"][1]))
+    s = oracle.Scene(mesh.vertices, mesh.triangles)
+    targets = unhex(gs["targets"], (gs["n_targets"], 3))
+    a = gs["arm_vector"]
+    got = oracle.sample_arm_vector_states(s, r, targets, seed=a["seed"], max_attempts=a["max_attempts"], ee_distance=a["ee_distance"])
+    assert got["found"].astype(int).tolist() == a["found"] and got["next_draw"].tolist() == a["next_draw"]
+    assert np.array_equal(np.nan_to_num(got["states"], nan=-7.0), unhex(a["states"], (gs["n_targets"], 8)))
+    u = gs["uniform"]
+    got = oracle.sample_uniform_goal_states(s, r, targets, seed=u["seed"], max_attempts=u["max_attempts"])
+    assert got["found"].astype(int).tolist() == u["found"] and got["next_draw"].tolist() == u["next_draw"]
+    assert np.array_equal(np.nan_to_num(got["states"], nan=-7.0), unhex(u["states"], (gs["n_targets"], 8)))
+    assert 0 < sum(u["found"]) and 0 < sum(a["found"])
+    st = oracle.gen_uniform_states(r, g["n_states"], seed=g["states_seed"], h_range=g["h_range"], v_range=g["v_range"])
+    assert np.array_equal(np.stack([oracle.arm_vector(r, x[:8]) for x in st[:16]]), unhex(gs["arm_vector_of"], (16, 3)))
+
+
 def test_oracle_matches_reference_sources_live(oracle, mg):
     if not oracle.have_ref():
         pytest.skip("oracle/_ref not built (needs /root/reference); the committed golden fixtures cover this")
@@ -220,6 +241,19 @@ def test_oracle_matches_reference_sources_live(oracle, mg):
     rh, rt = rs.check_motions(rr, st[:300], st[300:])
     assert np.array_equal(res["hit"], rh)
     assert np.array_equal(np.nan_to_num(res["toi"], nan=-1), np.nan_to_num(rt, nan=-1))
+    # a17 / a18: arm vector, arm-vector goal states and uniform goal states — same states found after the same number of draws
+    for x in st[:40]:
+        assert np.array_equal(oracle.arm_vector(r, x[:8]), oracle.ref_arm_vector(rr, x[:8]))
+    targets = np.concatenate([tree.fruit_centers, rng.uniform([-1, -1, 0.3], [1, 1, 2.8], (30, 3))])
+    for ee_distance, attempts in ((0.0, 50), (0.1, 3)):
+        a = oracle.sample_arm_vector_states(s, r, targets, seed=11, max_attempts=attempts, ee_distance=ee_distance)
+        b = oracle.ref_sample_arm_vector_states(rs, rr, targets, seed=11, max_attempts=attempts, ee_distance=ee_distance)
+        assert np.array_equal(a["found"], b["found"]) and np.array_equal(a["next_draw"], b["next_draw"])
+        assert np.array_equal(a["states"], b["states"], equal_nan=True) and a["found"].any()
+    a = oracle.sample_uniform_goal_states(s, r, targets, seed=5, max_attempts=20)
+    b = oracle.ref_sample_uniform_goal_states(rs, rr, targets, r.n_variables, seed=5, max_attempts=20)
+    assert np.array_equal(a["found"], b["found"]) and np.array_equal(a["next_draw"], b["next_draw"])
+    assert np.array_equal(a["states"], b["states"], equal_nan=True) and a["found"].any() and not a["found"].all()
     # shortcutting: same final path, successes and number of motion checks (runs that reach a zero-length motion are the
     # documented NaN-pose deviation, SURVEY Q8 — 30 attempts on 14 waypoints stay clear of it)
     for seed in range(4):
