@@ -110,6 +110,13 @@ typedef struct mgodpl_counters {
 
 const char *mgodpl_last_error(void);
 int mgodpl_device_count(void);
+/* Multi-GPU hosts: a scene is built on the calling thread's current CUDA device and stays bound to it (every later call on
+ * the handle runs there, whatever device is current in the caller, and restores the caller's device).  Robot handles hold no
+ * device memory and work with scenes on any device.  mgodpl_set_device = cudaSetDevice for callers that do not link the CUDA
+ * runtime themselves (one scene replica per device, one host thread per replica: the reference's analogue is its
+ * std::for_each(std::execution::par, ...) over problems, src/benchmarks/goal_sample_success_rate.cpp:165-172). */
+int mgodpl_set_device(int device);
+int mgodpl_scene_device(const mgodpl_scene *scene, int *device);
 
 /* ---- scene: replaces meshToFclBVH(const Mesh&) / treeMeshesToFclCollisionObject (src/planning/fcl_utils.cpp:23-60) ----
  * verts: nv x 3 doubles; tris: nt x 3 vertex indices.  Builds the linear BVH on the current CUDA device. */

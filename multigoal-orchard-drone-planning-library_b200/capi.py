@@ -23,7 +23,7 @@ STATUS = {0: "OK", 1: "INVALID_ARGUMENT", 2: "UNSUPPORTED_SHAPE", 3: "LINK_NOT_F
           5: "CUDA", 6: "NO_DEVICE", 7: "OUT_OF_MEMORY", 8: "UNSUPPORTED_ROBOT"}
 
 EXPORTS = [
-    "mgodpl_last_error", "mgodpl_device_count", "mgodpl_scene_create", "mgodpl_scene_create_u64",
+    "mgodpl_last_error", "mgodpl_device_count", "mgodpl_set_device", "mgodpl_scene_device", "mgodpl_scene_create", "mgodpl_scene_create_u64",
     "mgodpl_scene_destroy", "mgodpl_scene_get_info", "mgodpl_scene_get_counters", "mgodpl_robot_create",
     "mgodpl_robot_destroy", "mgodpl_robot_n_variables", "mgodpl_forward_kinematics", "mgodpl_check_boxes",
     "mgodpl_check_states", "mgodpl_check_states_device", "mgodpl_check_motions", "mgodpl_check_motions_device",

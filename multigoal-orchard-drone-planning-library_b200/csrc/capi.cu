@@ -47,6 +47,21 @@ int require_device() {
 	return MGODPL_OK;
 }
 
+/// Scene handles are bound to the device they were built on: every call on a scene runs there, whatever device is current
+/// in the calling thread, and leaves the caller's current device as it found it.
+struct DeviceGuard {
+	int prev = -1;
+	bool changed = false;
+	explicit DeviceGuard(int want) {
+		if (cudaGetDevice(&prev) == cudaSuccess && prev != want) changed = cudaSetDevice(want) == cudaSuccess;
+	}
+	~DeviceGuard() {
+		if (changed) cudaSetDevice(prev);
+	}
+	DeviceGuard(const DeviceGuard &) = delete;
+	DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 /// A growable device + pinned-host staging area, one per in-flight host-buffer call.
 struct Workspace {
 	char *dev = nullptr, *host = nullptr;
@@ -170,6 +185,7 @@ WorkspacePool &global_pool() {
 }  // namespace
 
 struct mgodpl_scene {
+	int device = 0;  // the CUDA device that holds the BVH
 	SceneDev dev{};
 	BuiltScene built{};
 	mgodpl_scene_info info{};
@@ -196,8 +212,6 @@ struct mgodpl_scene {
 struct mgodpl_robot {
 	RobotDev dev{};
 	int n_joints = 0;
-	double *d_limits = nullptr;  // n_vars x (min, max)
-	std::vector<double> limits;
 };
 
 // =================================================================================================================
@@ -212,6 +226,17 @@ int mgodpl_device_count(void) {
 		return 0;
 	}
 	return n;
+}
+
+int mgodpl_set_device(int device) {
+	if (int rc = require_device()) return rc;
+	CU(cudaSetDevice(device));
+	return MGODPL_OK;
+}
+int mgodpl_scene_device(const mgodpl_scene *scene, int *device) {
+	if (!scene || !device) return fail(MGODPL_E_INVALID_ARGUMENT, "null argument");
+	*device = scene->device;
+	return MGODPL_OK;
 }
 
 // ---- scene ---------------------------------------------------------------------------------------------------------
@@ -237,6 +262,7 @@ static int scene_create_impl(const double *verts, size_t nv, const uint32_t *tri
 	if (!nt) lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0.0;
 	if (int rc = require_device()) return rc;
 	auto sc = std::make_unique<mgodpl_scene>();
+	cudaGetDevice(&sc->device);
 	double origin[3], max_abs = 0.0;
 	for (int a = 0; a < 3; ++a) {
 		origin[a] = 0.5 * (lo[a] + hi[a]);
@@ -327,6 +353,7 @@ int mgodpl_scene_create_u64(const double *verts, size_t nv, const uint64_t *tris
 }
 int mgodpl_scene_destroy(mgodpl_scene *s) {
 	if (!s) return MGODPL_OK;
+	DeviceGuard on_device(s->device);
 	cudaFree(s->built.wide), cudaFree(s->built.clear);
 	cudaFree(s->built.nodes), cudaFree(s->built.tris), cudaFree(s->built.tris32), cudaFree(s->built.tri_ids), cudaFree(s->d_counters);
 	delete s;
@@ -341,6 +368,7 @@ int mgodpl_scene_get_counters(mgodpl_scene *s, mgodpl_counters *out, int reset) 
 	if (!s || !out) return fail(MGODPL_E_INVALID_ARGUMENT, "null argument");
 	memset(out, 0, sizeof(*out));
 	if (!s->d_counters) return fail(MGODPL_E_INVALID_ARGUMENT, "scene was created without MGODPL_SCENE_COUNTERS");
+	DeviceGuard on_device(s->device);
 	unsigned long long v[CNT_N];
 	CU(cudaMemcpy(v, s->d_counters, sizeof(v), cudaMemcpyDeviceToHost));
 	out->states_checked = v[CNT_STATES], out->boxes_traversed = v[CNT_BOXES], out->nodes_visited = v[CNT_NODES];
@@ -551,25 +579,22 @@ int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_
 			for (auto it = path.rbegin(); it != path.rend(); ++it) d.ee_path[d.n_ee_path++] = (int8_t) *it;
 		}
 	}
-	// Joint limits for device-side goal sampling: one (min, max) per variable in variable order.
-	rb->limits.assign(2 * std::max(n_vars, 1), 0.0);
+	// Joint limits for device-side goal sampling: one (min, max) per variable in variable order.  They travel inside RobotDev
+	// (kernel parameters), so a robot handle owns no device memory and works with scenes on any device.
 	{
 		int v = 0;
 		for (int j = 0; j < n_joints; ++j)
 			if (joints[j].joint_type == MGODPL_JOINT_REVOLUTE) {
-				rb->limits[2 * v] = joints[j].min_angle, rb->limits[2 * v + 1] = joints[j].max_angle;
+				d.limits[2 * v] = joints[j].min_angle, d.limits[2 * v + 1] = joints[j].max_angle;
 				++v;
 			}
 	}
-	CU(cudaMalloc((void **) &rb->d_limits, rb->limits.size() * sizeof(double)));
-	CU(cudaMemcpy(rb->d_limits, rb->limits.data(), rb->limits.size() * sizeof(double), cudaMemcpyHostToDevice));
 	*out = rb.release();
 	return MGODPL_OK;
 }
 
 int mgodpl_robot_destroy(mgodpl_robot *r) {
 	if (!r) return MGODPL_OK;
-	cudaFree(r->d_limits);
 	delete r;
 	return MGODPL_OK;
 }
@@ -613,6 +638,7 @@ int mgodpl_check_boxes(mgodpl_scene *scene, const double *boxes, size_t n, uint3
 	if (n && (!boxes || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
 	if (n > SURVIVOR_MAX_ENTRIES) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^26 queries in one call: split the batch");
 	if (int rc = require_device()) return rc;
+	DeviceGuard on_device(scene->device);
 	if (!n) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Lease ws(scene->pool);
@@ -637,6 +663,7 @@ int mgodpl_check_states_device(mgodpl_scene *scene, const mgodpl_robot *robot, c
 	if (n && (!d_states || !d_hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
 	if (n > SURVIVOR_MAX_ENTRIES) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^26 queries in one call: split the batch");
 	if (int rc = require_device()) return rc;
+	DeviceGuard on_device(scene->device);
 	if (!n) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	const size_t qb = query_scratch_bytes(n * (size_t) robot->dev.n_boxes + 4096, state_survivor_slots(n));
@@ -654,6 +681,7 @@ int mgodpl_check_states(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	if (n && (!states || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
 	if (n > SURVIVOR_MAX_ENTRIES) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^26 queries in one call: split the batch");
 	if (int rc = require_device()) return rc;
+	DeviceGuard on_device(scene->device);
 	if (!n) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Lease ws(scene->pool);
@@ -689,6 +717,7 @@ int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, 
 	if (m && (!d_a || !d_b || !d_hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
 	if (m >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^32-2 queries in one call");
 	if (int rc = require_device()) return rc;
+	DeviceGuard on_device(scene->device);
 	if (!m) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Carver c;
@@ -728,6 +757,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	if (m && (!a || !b || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
 	if (m >= 0xFFFFFFFFull) return fail(MGODPL_E_INVALID_ARGUMENT, "more than 2^32-2 queries in one call");
 	if (int rc = require_device()) return rc;
+	DeviceGuard on_device(scene->device);
 	if (!m) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	static const bool trace = getenv("MGODPL_TRACE_E2E") != nullptr;  // dev aid: where a host-buffer call spends its time
@@ -738,11 +768,10 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	Carver c;
 	// Large batches are cut into chunks that alternate between two side streams, so chunk k+1's H2D copy and chunk
 	// k-1's D2H copy overlap chunk k's kernels.  Chunk boundaries are multiples of 32: result words never straddle.
-	static size_t chunk_pref = 0;
-	if (!chunk_pref) {
+	static const size_t chunk_pref = [] {
 		const char *e = getenv("MGODPL_E2E_CHUNKS");
-		chunk_pref = e && atoi(e) > 0 ? std::min((size_t) atoi(e), Workspace::MAX_CHUNKS) : 2;
-	}
+		return e && atoi(e) > 0 ? std::min((size_t) atoi(e), Workspace::MAX_CHUNKS) : (size_t) 2;
+	}();
 	const size_t n_chunks = m >= 32768 ? chunk_pref : 1;
 	const size_t chunk_m = n_chunks == 1 ? m : ((m + n_chunks - 1) / n_chunks + 31) / 32 * 32;
 	const size_t in_b = m * stride * 8, words = (m + 31) / 32, qb = motion_scratch_bytes(chunk_m, robot->dev.n_boxes);
@@ -888,13 +917,14 @@ int mgodpl_sample_goals_device(mgodpl_scene *scene, const mgodpl_robot *robot, c
 	if (int rc = check_goal_args(scene, robot, f, s)) return rc;
 	if (f && s && (!d_targets || !d_hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
 	if (int rc = require_device()) return rc;
+	DeviceGuard on_device(scene->device);
 	if (!f || !s) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	const size_t qb = query_scratch_bytes(f * s * (size_t) robot->dev.n_boxes * 9 / 8 + 4096);
 	auto &slot = scene->stream_slot(stream);
 	std::lock_guard<std::mutex> enqueue(slot.mu);
 	CU(slot.ws.reserve(qb, 0));
-	CU(launch_sample_goals(scene->dev, robot->dev, d_targets, f, d_draws, robot->d_limits, s, seed, dist, d_hit_bits, d_collisions,
+	CU(launch_sample_goals(scene->dev, robot->dev, d_targets, f, d_draws, s, seed, dist, d_hit_bits, d_collisions,
 						   d_states_out, slot.ws.dev, qb, stream));
 	return MGODPL_OK;
 }
@@ -904,6 +934,7 @@ int mgodpl_sample_goals(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	if (int rc = check_goal_args(scene, robot, f, s)) return rc;
 	if (f && s && (!targets || !hit_bits)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
 	if (int rc = require_device()) return rc;
+	DeviceGuard on_device(scene->device);
 	if (!f || !s) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	const int nv = robot->dev.n_vars;
@@ -919,7 +950,7 @@ int mgodpl_sample_goals(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	CU(cudaMemcpyAsync(D + o_t, targets, f * 24, cudaMemcpyHostToDevice, stream));
 	if (draws) CU(cudaMemcpyAsync(D + o_d, draws, s * (1 + nv) * 8, cudaMemcpyHostToDevice, stream));
 	CU(launch_sample_goals(scene->dev, robot->dev, (const double *) (D + o_t), f, draws ? (const double *) (D + o_d) : nullptr,
-						   robot->d_limits, s, seed, dist, (uint32_t *) (D + o_hit), (uint32_t *) (D + o_cnt),
+						   s, seed, dist, (uint32_t *) (D + o_hit), (uint32_t *) (D + o_cnt),
 						   states_out ? (double *) (D + o_st) : nullptr, D + o_q, qb, stream));
 	CU(cudaMemcpyAsync(H + o_hit, D + o_hit, small_hi - o_hit, cudaMemcpyDeviceToHost, stream));
 	if (states_out) CU(cudaMemcpyAsync(states_out, D + o_st, f * s * (7 + nv) * 8, cudaMemcpyDeviceToHost, stream));

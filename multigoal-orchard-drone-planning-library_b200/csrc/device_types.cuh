@@ -56,10 +56,12 @@ struct SceneDev {
 __device__ __forceinline__ float scene_clearance(const SceneDev &sc, float x, float y, float z) {
 	if (!sc.clear) return 0.f;
 	const float gx = (x - sc.clear_lo[0]) * sc.clear_inv, gy = (y - sc.clear_lo[1]) * sc.clear_inv, gz = (z - sc.clear_lo[2]) * sc.clear_inv;
-	if (!(gx >= 0.f && gy >= 0.f && gz >= 0.f && gx < (float) sc.clear_n[0] && gy < (float) sc.clear_n[1] && gz < (float) sc.clear_n[2]))
+	// float -> int conversion saturates and maps NaN to 0; the unsigned compares reject negative cells and cells beyond the grid
+	// (a NaN coordinate is caught by the explicit test: it must not alias cell 0)
+	const unsigned ix = (unsigned) __float2int_rd(gx), iy = (unsigned) __float2int_rd(gy), iz = (unsigned) __float2int_rd(gz);
+	if (ix >= (unsigned) sc.clear_n[0] || iy >= (unsigned) sc.clear_n[1] || iz >= (unsigned) sc.clear_n[2] || !(gx + gy + gz == gx + gy + gz))
 		return sc.clear_pad;
-	const size_t cell = ((size_t) (int) gz * sc.clear_n[1] + (int) gy) * sc.clear_n[0] + (int) gx;
-	return (float) __ldg(sc.clear + cell) * sc.clear_q;
+	return (float) __ldg(sc.clear + ((iz * (unsigned) sc.clear_n[1] + iy) * (unsigned) sc.clear_n[0] + ix)) * sc.clear_q;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -109,6 +111,7 @@ struct RobotDev {
 	int32_t n_ee_path;    // ops on the way from the root to the end effector (ee_path), in execution order
 	double reach;         // radius around the root link origin that contains every box for every joint value
 	int8_t ee_path[MGODPL_MAX_LINKS];
+	double limits[2 * MGODPL_MAX_JOINT_VALUES];  // (min, max) per joint variable: device-side goal sampling draws inside them
 	FkOp ops[MGODPL_MAX_LINKS];
 	BoxDev boxes[MGODPL_MAX_BOXES];
 };

@@ -25,7 +25,7 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned *d_first_step, void *d_slerp,
 								 void *scratch, size_t scratch_bytes, size_t survivor_entries, cudaStream_t stream);
 cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const double *d_targets, size_t f,
-								const double *d_draws, const double *d_limits, size_t s, unsigned long long seed,
+								const double *d_draws, size_t s, unsigned long long seed,
 								double distance_from_target, uint32_t *d_hit_bits, uint32_t *d_collisions,
 								double *d_states_out, void *scratch, size_t scratch_bytes, cudaStream_t stream);
 cudaError_t launch_forward_kinematics(const RobotDev &rb, const double *d_states, size_t n, size_t stride, double *d_out,

@@ -6,7 +6,8 @@
 //   expand   all 32 lanes take one candidate each (a surviving state, one interpolation step of a motion, a goal sample,
 //            an explicit box): interpolate / FK in fp64, cull each link box (scene bounds, clearance grid, the root
 //            record's children) and drop the survivors into the warp's RING of 64-byte box items in shared memory.
-//            Ring slots are owned by lanes (SPL each), so producing needs no allocation; a FIFO of slot numbers
+//            Free ring slots sit on a per-warp stack; every emit and every release happens at a point all 32 lanes reach
+//            together, so slots are handed out and returned by ballot rank, without atomics.  A FIFO of slot numbers
 //            ("pending") hands the boxes to whichever lanes are free.
 //   descend  every lane that holds a box visits one BVH record per step (4-wide: up to four fp32 OBB-vs-AABB tests per
 //            dependent fetch), keeps the nearest overlapping internal child, pushes the others on its stack (shared
@@ -27,8 +28,8 @@
 namespace mgodpl_b200 {
 
 constexpr int BLOCK_P = 128;          // 4 warps per block, each an independent worker
-constexpr int SPL = 4;                // ring slots owned by each lane
-constexpr int RING = 32 * SPL;
+constexpr int SPL = 4;                // boxes of one candidate expanded per round (robots with more boxes take several rounds)
+constexpr int RING = 128;             // box items per warp
 constexpr int STACK_SMEM = 24;        // per-lane stack entries kept in shared memory
 constexpr int STACK_LOCAL = 48;       // beyond that: local memory (never touched by trees of sane depth)
 constexpr int LEAF_FIFO = 256;        // power of two, >= 31 + 4 * 32
@@ -43,10 +44,10 @@ struct __align__(16) WarpMem {
 	unsigned char pend[RING];
 	unsigned char dead[RING];   // a leaf test found a hit for the box in this slot (or its owner is decided already)
 	unsigned char done[RING];   // the descent of the box in this slot is over; the slot goes back once `pairs` reaches 0
-	unsigned freed[32];         // byte k of word l: slot l * SPL + k is free again (set by whoever finished it last)
+	unsigned char free_slots[RING];  // stack of free ring slots
 };
 
-enum SourceKind : int { SRC_STATES = 0, SRC_MOTION_STEPS = 1, SRC_GOALS = 2, SRC_BOXES = 3 };
+enum SourceKind : int { SRC_STATES = 0, SRC_MOTION_STEPS = 1, SRC_GOALS = 2, SRC_BOXES = 3, SRC_QUEUE = 4 };
 
 /// Where the candidates come from (one struct for all kinds; unused members stay zero).
 struct SourceArgs {
@@ -59,18 +60,21 @@ struct SourceArgs {
 	const uint32_t *n_steps;
 	const SlerpConst *slerp;
 	// SRC_GOALS
-	const double *targets, *draws, *limits;
+	const double *targets, *draws;
 	size_t rows, per_row;
 	unsigned long long seed;
 	double distance_from_target;
 	double *states_out;
-	// SRC_BOXES
+	// SRC_BOXES (and SRC_QUEUE with explicit boxes: the half extents live here)
 	const double *boxes;
 	size_t total;  // SRC_GOALS / SRC_BOXES: number of candidates
+	// SRC_QUEUE: boxes already expanded and culled by a stage A2 kernel (the two-kernel path), sharded list in HBM
+	QueueDev queue;
 };
 
 struct PipeTuning {
 	int refill_min;    // free lanes that trigger a refill while others are still walking
+	unsigned leaf_min; // (box, leaf) pairs that trigger a leaf batch (<= 32)
 	int no_prefilter;  // MGODPL_NO_PREFILTER=1: every leaf triangle goes to the fp64 test
 	unsigned claim;    // candidates a warp claims per cursor atomic (a multiple of 32)
 };
@@ -98,7 +102,7 @@ struct JointsGoal {  // genUprightState's draws (goal_sampling.cpp:13-49): calle
 };
 
 template<class Joints>
-__device__ __forceinline__ Pose fk_apply_j(const FkOp &op, const Pose &parent, const Joints &joints) {
+__device__ __noinline__ Pose fk_apply_j(const FkOp &op, const Pose &parent, const Joints &joints) {
 	Pose p = then(parent, D3{op.pre_t[0], op.pre_t[1], op.pre_t[2]}, Q4{op.pre_q[0], op.pre_q[1], op.pre_q[2], op.pre_q[3]},
 				  op.flags & FK_PRE_ROT_ID);
 	if (op.var >= 0) {
@@ -112,7 +116,7 @@ __device__ __forceinline__ Pose fk_apply_j(const FkOp &op, const Pose &parent, c
 }
 
 /// The culls a box goes through before it is worth a ring slot: scene bounds, clearance grid, the root record's children.
-__device__ __forceinline__ bool box_may_touch_scene(const SceneDev &sc, D3 c, Q4 q, const double *half, const BoxDev *spheres) {
+__device__ __noinline__ bool box_may_touch_scene(const SceneDev &sc, D3 c, Q4 q, const double *half, const BoxDev *spheres) {
 	if (!sc.n_nodes) return false;  // empty scene
 	const CullBox cb = make_cull_box(sc, c, q, half);
 	if (!cull_overlap(cb, sc.root_c[0], sc.root_c[1], sc.root_c[2], sc.root_h[0], sc.root_h[1], sc.root_h[2])) return false;
@@ -130,8 +134,7 @@ __device__ __forceinline__ bool box_may_touch_scene(const SceneDev &sc, D3 c, Q4
 			free_of_scene = scene_clearance(sc, cb.cx, cb.cy, cb.cz) > sqrtf(cb.hx * cb.hx + cb.hy * cb.hy + cb.hz * cb.hz) + 1e-4f;
 		}
 		if (free_of_scene) return false;
-	}
-	if (sc.wide) {
+	} else if (sc.wide) {
 		bool any = false;
 #pragma unroll
 		for (int k = 0; k < 4; ++k)
@@ -146,37 +149,35 @@ __device__ __forceinline__ bool box_may_touch_scene(const SceneDev &sc, D3 c, Q4
 struct Worker {
 	WarpMem *wm;
 	unsigned lane;
-	unsigned own_free;             // bit k: own slot lane * SPL + k is free
+	unsigned n_free;               // (u) free ring slots (on wm->free_slots)
 	unsigned pend_head, pend_tail; // (u) FIFO of slots waiting for a lane
 	unsigned leaf_head, leaf_tail; // (u) FIFO of (slot, leaf) pairs waiting for a test
 
-	/// Producer side, called by all 32 lanes together: lanes with `want` drop their box into one of their own slots.
+	/// Producer side, called by all 32 lanes together: lanes with `want` drop their box into a free slot.
 	__device__ __forceinline__ void emit(bool want, D3 c, Q4 q, unsigned owner, unsigned step, unsigned box) {
 		const unsigned m = __ballot_sync(0xffffffffu, want);
 		if (!m) return;
 		if (want) {
-			const int k = __ffs(own_free) - 1;
-			own_free &= own_free - 1;
-			const unsigned slot = lane * SPL + k;
+			const unsigned rank = __popc(m & ((1u << lane) - 1u));
+			const unsigned slot = wm->free_slots[n_free - 1u - rank];
 			double2 *dst = reinterpret_cast<double2 *>(wm->ring + slot);
 			dst[0] = make_double2(c.x, c.y);
 			dst[1] = make_double2(c.z, q.x);
 			dst[2] = make_double2(q.y, q.z);
 			dst[3] = make_double2(q.w, __hiloint2double((int) (step | box << 28), (int) owner));
 			wm->dead[slot] = 0, wm->done[slot] = 0, wm->pairs[slot] = 0;
-			wm->pend[(pend_tail + __popc(m & ((1u << lane) - 1u))) & (RING - 1)] = (unsigned char) slot;
+			wm->pend[(pend_tail + rank) & (RING - 1)] = (unsigned char) slot;
 		}
-		pend_tail += __popc(m);
+		n_free -= __popc(m), pend_tail += __popc(m);
+		__syncwarp();
 	}
-	/// Collect the slots other lanes have released since the last look.
-	__device__ __forceinline__ void reclaim() {
-		const unsigned f = wm->freed[lane];
-		if (f) {
-			wm->freed[lane] = 0;
-#pragma unroll
-			for (int k = 0; k < SPL; ++k)
-				if ((f >> (8 * k)) & 0xffu) own_free |= 1u << k;
-		}
+	/// Called by all 32 lanes together: lanes with `rel` give slot `s` back.
+	__device__ __forceinline__ void release(bool rel, unsigned s) {
+		const unsigned m = __ballot_sync(0xffffffffu, rel);
+		if (!m) return;
+		if (rel) wm->free_slots[n_free + __popc(m & ((1u << lane) - 1u))] = (unsigned char) s;
+		n_free += __popc(m);
+		__syncwarp();
 	}
 };
 
@@ -249,15 +250,22 @@ k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 		__syncthreads();
 		range0 = slot_range(s_counts[0], src.list[0].cap);
 		total = range0 + (src.n_lists > 1 ? slot_range(s_counts[1], src.list[1].cap) : 0u);
+	} else if (KIND == SRC_QUEUE) {
+		if (threadIdx.x < SHARDS) s_counts[0][threadIdx.x] = __ldcg(src.queue.counts + threadIdx.x * COUNTER_STRIDE);
+		__syncthreads();
+		total = slot_range(s_counts[0], src.queue.cap);
 	} else {
 		total = src.total;
 	}
-	const int n_groups = KIND == SRC_BOXES ? 1 : max(1, (rb.n_boxes + SPL - 1) / SPL);  // box groups per candidate
-	const int group_boxes = KIND == SRC_BOXES ? 1 : min(rb.n_boxes, SPL);
+	constexpr bool ONE_BOX = KIND == SRC_BOXES || KIND == SRC_QUEUE;  // a candidate is a single box
+	const int n_groups = ONE_BOX ? 1 : max(1, (rb.n_boxes + SPL - 1) / SPL);  // box groups per candidate
+	const int group_boxes = ONE_BOX ? 1 : min(rb.n_boxes, SPL);
 	total *= (unsigned) n_groups;
+	// few candidates per warp: claim one round at a time so that the work spreads over all the warps of the grid
+	const unsigned claim = total > (unsigned long long) gridDim.x * (BLOCK_P / 32) * 32ull * 16ull ? tune.claim : 32u;
 
-	Worker w{wm, lane, (1u << SPL) - 1u, 0u, 0u, 0u, 0u};
-	wm->freed[lane] = 0;
+	Worker w{wm, lane, (unsigned) RING, 0u, 0u, 0u, 0u};
+	for (int k = lane; k < RING; k += 32) wm->free_slots[k] = (unsigned char) k;
 	unsigned long long chunk_lo = 0, chunk_hi = 0;  // (u) unclaimed part of this warp's chunk of candidates
 	bool exhausted = total == 0;                     // (u)
 	// lane state: the box being walked (cur == REF_END: none)
@@ -278,19 +286,20 @@ k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 		return sp < STACK_SMEM ? wm->stack[sp][lane] : lstack[sp - STACK_SMEM];
 	};
 	auto half_of = [&](unsigned owner, unsigned step_box, double *buf) -> const double * {
-		if (KIND == SRC_BOXES) {
+		if (KIND == SRC_BOXES || (KIND == SRC_QUEUE && src.boxes)) {
 			const double *bx = src.boxes + (size_t) owner * 10;
 			buf[0] = __ldg(bx + 7) * 0.5, buf[1] = __ldg(bx + 8) * 0.5, buf[2] = __ldg(bx + 9) * 0.5;
 			return buf;
 		}
 		return rb.boxes[step_box >> 28].half;
 	};
-	auto release = [&](unsigned s) { reinterpret_cast<volatile unsigned char *>(wm->freed)[s] = 1; };  // s = owner lane * SPL + k
 	/// One batch of leaf tests: pair `leaf_head + lane` for lane < batch, whichever lane walked the box.
 	auto leaf_batch = [&](unsigned batch) {
+		bool last_pair = false;
+		unsigned s = 0;
 		if (lane < batch) {
 			const unsigned e = (w.leaf_head + lane) & (LEAF_FIFO - 1);
-			const unsigned s = wm->leaf_slot[e];
+			s = wm->leaf_slot[e];
 			const int ref = wm->leaf_ref[e];
 			if (!wm->dead[s]) {
 				const double2 *it = reinterpret_cast<const double2 *>(wm->ring + s);
@@ -317,9 +326,10 @@ k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 					}
 				}
 			}
-			// last pair of a box whose descent is over: the slot goes back to its owner
-			if (atomicSub(&wm->pairs[s], 1) == 1 && wm->done[s]) release(s);
+			// last pair of a box whose descent is over: the slot goes back on the free stack
+			last_pair = atomicSub(&wm->pairs[s], 1) == 1 && wm->done[s];
 		}
+		w.release(last_pair, s);
 		w.leaf_head += batch;
 	};
 
@@ -328,13 +338,14 @@ k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 		const unsigned n_leaf = w.leaf_tail - w.leaf_head, n_pend = w.pend_tail - w.pend_head;
 		const unsigned walking = __ballot_sync(FULL, cur != REF_END), n_free = 32u - __popc(walking);
 		// ---- leaves: 32 pairs waiting -> one full-warp batch ----------------------------------------------------------------
-		if (n_leaf >= 32u) {
-			leaf_batch(32u);
+		if (n_leaf >= tune.leaf_min) {
+			leaf_batch(min(n_leaf, 32u));
 			continue;
 		}
 		// ---- refill: free lanes take pending boxes ------------------------------------------------------------------------------
 		if (n_pend && n_free && ((int) n_free >= tune.refill_min || !walking || n_pend >= 64u)) {
 			const unsigned rank = __popc(~walking & lt);
+			bool drop = false;
 			if (cur == REF_END && rank < n_pend) {
 				slot = wm->pend[(w.pend_head + rank) & (RING - 1)];
 				const double2 *it = reinterpret_cast<const double2 *>(wm->ring + slot);
@@ -351,25 +362,27 @@ k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 					lc.boxes++;
 					max_box_nodes = max(max_box_nodes, box_nodes), box_nodes = 0;
 				} else {
-					release(slot);
+					drop = true;
 				}
 			}
+			w.release(drop, slot);
 			w.pend_head += min(n_pend, n_free);
 			stalls = 0;
 			continue;
 		}
 		// ---- expand: keep at least a warp's worth of boxes pending while candidates remain ----------------------------------------
-		if (!exhausted && n_pend < 32u) {
-			w.reclaim();
-			const bool can = __popc(w.own_free) >= group_boxes;
-			const unsigned can_mask = __ballot_sync(FULL, can);
-			if (can_mask) {
+		// (a full round wants 32 x group_boxes free slots; narrower rounds only when the lanes would otherwise starve)
+		const unsigned can_lanes = min(32u, w.n_free / (unsigned) max(group_boxes, 1));
+		if (!exhausted && n_pend < 32u && (can_lanes == 32u || (can_lanes && !n_leaf && (!n_pend || !walking)))) {
+			const bool can = lane < can_lanes;
+			const unsigned can_mask = can_lanes == 32u ? FULL : (1u << can_lanes) - 1u;
+			{
 				stalls = 0;
 				if (chunk_lo == chunk_hi) {
 					unsigned long long lo = 0;
-					if (lane == 0) lo = atomicAdd(cursor, tune.claim);
+					if (lane == 0) lo = atomicAdd(cursor, claim);
 					lo = __shfl_sync(FULL, lo, 0);
-					chunk_lo = min(lo, total), chunk_hi = min(lo + tune.claim, total);
+					chunk_lo = min(lo, total), chunk_hi = min(lo + claim, total);
 					if (chunk_lo >= total) {
 						exhausted = true;
 						continue;
@@ -444,7 +457,7 @@ k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 					}
 					expand_boxes<CHAIN>(sc, rb, w, alive, base, jl, owner, step, box_lo, box_hi);
 				} else if (KIND == SRC_GOALS) {
-					JointsGoal jg{nullptr, src.limits, src.seed, 0ull};
+					JointsGoal jg{nullptr, rb.limits, src.seed, 0ull};
 					if (alive) {
 						const size_t row = (size_t) (cand / src.per_row), s = (size_t) (cand - row * src.per_row);
 						const int nv = rb.n_vars;
@@ -477,6 +490,16 @@ k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 						alive = !robot_out_of_reach(sc, rb, base.t);
 					}
 					expand_boxes<CHAIN>(sc, rb, w, alive, base, jg, owner, 0u, box_lo, box_hi);
+				} else if (KIND == SRC_QUEUE) {  // a box queued by a stage A2 kernel: copy it on chip
+					bool want = alive && slot_filled(s_counts[0], (unsigned) cand);
+					unsigned step_box = 0;
+					if (want) {
+						const double2 *it = reinterpret_cast<const double2 *>(src.queue.items + cand);
+						const double2 v0 = __ldcg(it), v1 = __ldcg(it + 1), v2 = __ldcg(it + 2), v3 = __ldcg(it + 3);
+						base = Pose{D3{v0.x, v0.y, v1.x}, Q4{v1.y, v2.x, v2.y, v3.x}};
+						owner = (unsigned) __double2loint(v3.y), step_box = (unsigned) __double2hiint(v3.y);
+					}
+					w.emit(want, base.t, base.q, owner, step_box & 0x0FFFFFFFu, step_box >> 28);
 				} else {  // SRC_BOXES: check_link_collision (collision_detection.cpp:16-55), n x (tf7, size3)
 					bool want = false;
 					if (alive) {
@@ -506,25 +529,31 @@ k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 					} else {
 						lc.nodes++, box_nodes++;
 						int next = REF_END;
-						float next_d = 0.f;
+						float next_d = __int_as_float(0x7f800000);
 						if (WIDE) {
+							// straight-line code for the four children: overlap, leaf / internal, distance; then the nearest internal child
 							const float4 *rec = sc.wide + 8ull * (unsigned) cur;
 							float4 a[4], b[4];
 #pragma unroll
 							for (int k = 0; k < 4; ++k) a[k] = __ldg(rec + 2 * k), b[k] = __ldg(rec + 2 * k + 1);
+							float d[4];
 #pragma unroll
 							for (int k = 0; k < 4; ++k) {
-								const int ref = __float_as_int(a[k].w);
-								if (ref == WIDE_EMPTY || !cull_overlap(cb, a[k].x, a[k].y, a[k].z, b[k].x, b[k].y, b[k].z)) continue;
-								if (ref < 0) {
-									leaf_bits |= 1u << k, leaf_refs[k] = ref;
-									continue;
-								}
-								const float dx = a[k].x - cb.cx, dy = a[k].y - cb.cy, dz = a[k].z - cb.cz, d = dx * dx + dy * dy + dz * dz;
-								if (next == REF_END) next = ref, next_d = d;
-								else if (d < next_d) push(next), next = ref, next_d = d;
-								else push(ref);
+								leaf_refs[k] = __float_as_int(a[k].w);
+								const bool ov = (leaf_refs[k] != WIDE_EMPTY) & cull_overlap(cb, a[k].x, a[k].y, a[k].z, b[k].x, b[k].y, b[k].z);
+								const bool leaf = ov & (leaf_refs[k] < 0);
+								leaf_bits |= (leaf ? 1u : 0u) << k;
+								const float dx = a[k].x - cb.cx, dy = a[k].y - cb.cy, dz = a[k].z - cb.cz;
+								d[k] = (ov & !leaf) ? dx * dx + dy * dy + dz * dz : __int_as_float(0x7f800000);
 							}
+#pragma unroll
+							for (int k = 0; k < 4; ++k) {
+								const bool nearer = d[k] < next_d;
+								next = nearer ? leaf_refs[k] : next, next_d = nearer ? d[k] : next_d;
+							}
+#pragma unroll
+							for (int k = 0; k < 4; ++k)
+								if (d[k] < __int_as_float(0x7f800000) && leaf_refs[k] != next) push(leaf_refs[k]);
 						} else {
 							const float4 *rec = sc.nodes + 4ull * (unsigned) cur;
 							const float4 n0 = __ldg(rec), n1 = __ldg(rec + 1), n2 = __ldg(rec + 2), n3 = __ldg(rec + 3);
@@ -545,25 +574,30 @@ k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 					}
 				}
 				__syncwarp();
+				{
+					// append the overlapping leaf children to the FIFO: a warp-wide exclusive scan of the per-lane counts (0..4)
+					// from three ballots, then every lane writes its own pairs
+					const unsigned cnt = __popc(leaf_bits);
+					const unsigned b0 = __ballot_sync(FULL, cnt & 1u), b1 = __ballot_sync(FULL, cnt & 2u), b2 = __ballot_sync(FULL, cnt & 4u);
+					if (b0 | b1 | b2) {
+						unsigned e = w.leaf_tail + __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
 #pragma unroll
-				for (int k = 0; k < (WIDE ? 4 : 2); ++k) {
-					const bool mine = (leaf_bits >> k) & 1u;
-					const unsigned m = __ballot_sync(FULL, mine);
-					if (!m) continue;
-					if (mine) {
-						const unsigned e = (w.leaf_tail + __popc(m & lt)) & (LEAF_FIFO - 1);
-						wm->leaf_ref[e] = leaf_refs[k];
-						wm->leaf_slot[e] = (unsigned char) slot;
+						for (int k = 0; k < (WIDE ? 4 : 2); ++k)
+							if ((leaf_bits >> k) & 1u) {
+								wm->leaf_ref[e & (LEAF_FIFO - 1)] = leaf_refs[k];
+								wm->leaf_slot[e & (LEAF_FIFO - 1)] = (unsigned char) slot;
+								++e;
+							}
+						w.leaf_tail += __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
 					}
-					w.leaf_tail += __popc(m);
 				}
 				if (leaf_bits) wm->pairs[slot] += __popc(leaf_bits);  // only the walking lane adds; testers subtract in another phase
-				if (was_walking && cur == REF_END) {  // descent over (or cut short by a hit): hand the slot back, now or with its last pair
-					if (wm->pairs[slot] == 0) release(slot);
-					else wm->done[slot] = 1;
-				}
+				// descent over (or cut short by a hit): hand the slot back, now or with its last pair
+				const bool over = was_walking && cur == REF_END, pairs_left = over && wm->pairs[slot] != 0;
+				if (pairs_left) wm->done[slot] = 1;
+				w.release(over && !pairs_left, slot);
 				const unsigned still = __ballot_sync(FULL, cur != REF_END);
-				if (!still || w.leaf_tail - w.leaf_head >= 32u) break;
+				if (!still || w.leaf_tail - w.leaf_head >= tune.leaf_min) break;
 				// enough lanes have run dry and there is (or can be) something to give them: go and refill
 				if ((int) (32u - __popc(still)) >= tune.refill_min && (n_pend || !exhausted)) break;
 			}

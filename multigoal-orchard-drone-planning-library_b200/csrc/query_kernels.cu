@@ -67,6 +67,15 @@ __device__ __forceinline__ void flush_counters(const SceneDev &sc, const LocalCo
 	}
 }
 
+/// The same from a single lane in divergent code (rare paths only).
+__device__ __forceinline__ void flush_counters_lane(const SceneDev &sc, const LocalCounters &lc) {
+	if (!sc.counters) return;
+	if (lc.states) atomicAdd(sc.counters + 0, (unsigned long long) lc.states);
+	if (lc.boxes) atomicAdd(sc.counters + 1, (unsigned long long) lc.boxes);
+	if (lc.nodes) atomicAdd(sc.counters + 2, (unsigned long long) lc.nodes);
+	if (lc.leaf) atomicAdd(sc.counters + 3, (unsigned long long) lc.leaf);
+}
+
 __device__ __forceinline__ bool already_decided(const Results &res, unsigned owner, unsigned step) {
 	if (res.mode == RESULT_BITS) return (__ldcg(res.hit_bits + (owner >> 5)) >> (owner & 31)) & 1u;
 	return __ldcg(res.first_step + owner) <= step;  // an earlier (or this) step already collides
@@ -115,12 +124,19 @@ __device__ __noinline__ bool exact_leaf_test(const SceneDev &sc, const void *exa
 	return false;
 }
 
-constexpr int STACK_DEPTH = 64;        // scene creation rejects trees deeper than 60 levels
-constexpr int WIDE_STACK_DEPTH = 96;   // 4-wide records: at most 30 levels, up to three pushes each
+constexpr int STACK_DEPTH = 52;        // scene creation rejects trees deeper than 48 levels
+constexpr int WIDE_STACK_DEPTH = 72;   // 4-wide records: at most 24 levels, up to three pushes each
 constexpr int REF_END = (int) 0x80000000;  // "nothing left to visit"
 
 /// Test both children of record `cur`; returns the next reference to visit (pushing the other overlapping child).
-__device__ __forceinline__ int visit_record(const SceneDev &sc, const CullBox &cb, int cur, int *stack, int &sp) {
+struct LocalStack {
+	int *data;
+	int sp;
+	__device__ __forceinline__ void push(int v) { data[sp++] = v; }
+	__device__ __forceinline__ int pop() { return data[--sp]; }
+};
+template<class Stack>
+__device__ __forceinline__ int visit_record(const SceneDev &sc, const CullBox &cb, int cur, Stack &st) {
 	const float4 *rec = sc.nodes + 4ull * (unsigned) cur;
 	const float4 n0 = __ldg(rec), n1 = __ldg(rec + 1), n2 = __ldg(rec + 2), n3 = __ldg(rec + 3);
 	const bool ov_l = cull_overlap(cb, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y);
@@ -132,36 +148,68 @@ __device__ __forceinline__ int visit_record(const SceneDev &sc, const CullBox &c
 		const float lx = n0.x - cb.cx, ly = n0.y - cb.cy, lz = n0.z - cb.cz, rx = n1.z - cb.cx, ry = n1.w - cb.cy, rz = n2.x - cb.cz;
 		const bool right_first = rx * rx + ry * ry + rz * rz < lx * lx + ly * ly + lz * lz;
 		next = right_first ? rref : lref;
-		stack[sp++] = right_first ? lref : rref;
+		st.push(right_first ? lref : rref);
 	} else if (ov_l) {
 		next = lref;
 	} else if (ov_r) {
 		next = rref;
-	} else if (sp > 0) {
-		next = stack[--sp];
+	} else if (st.sp > 0) {
+		next = st.pop();
 	}
 	return next;
 }
 
+/// Per-lane traversal stack: the first STACK_SHARED entries live in shared memory ([depth][thread]: conflict-free), only
+/// deeper ones in a local array (trees of ordinary depth never get there).
+constexpr int STACK_SHARED = 16;
+struct LaneStack {
+	int *shared;  // &s_stack[0][threadIdx.x]; entries are blockDim.x ints apart
+	int *local;
+	int stride, sp;
+	// The shared array has one spare row: entries beyond STACK_SHARED are (also) written there, so the store needs no branch;
+	// the local copy is what counts for them.
+	__device__ __forceinline__ void push(int v) {
+		shared[min(sp, STACK_SHARED) * stride] = v;
+		if (sp >= STACK_SHARED) local[sp - STACK_SHARED] = v;
+		++sp;
+	}
+	__device__ __forceinline__ int pop() {
+		--sp;
+		int v = shared[min(sp, STACK_SHARED) * stride];
+		if (sp >= STACK_SHARED) v = local[sp - STACK_SHARED];
+		return v;
+	}
+};
+
 /// The same for a 4-wide record: up to four boxes per dependent fetch; the nearest overlapping child is visited next, the
-/// others are pushed.
-__device__ __forceinline__ int visit_wide(const SceneDev &sc, const CullBox &cb, int cur, int *stack, int &sp) {
+/// others are pushed.  Written without per-child branches: the four overlap tests, distances and the nearest-child selection
+/// are straight-line code for every lane of the warp, only the (short) pushes are predicated.
+template<class Stack>
+__device__ __forceinline__ int visit_wide(const SceneDev &sc, const CullBox &cb, int cur, Stack &st) {
 	const float4 *rec = sc.wide + 8ull * (unsigned) cur;
 	float4 a[4], b[4];
 #pragma unroll
 	for (int k = 0; k < 4; ++k) a[k] = __ldg(rec + 2 * k), b[k] = __ldg(rec + 2 * k + 1);
-	int next = REF_END;
-	float next_d = 0.f;
+	int ref[4];
+	float d[4];
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
-		const int ref = __float_as_int(a[k].w);
-		if (ref == WIDE_EMPTY || !cull_overlap(cb, a[k].x, a[k].y, a[k].z, b[k].x, b[k].y, b[k].z)) continue;
-		const float dx = a[k].x - cb.cx, dy = a[k].y - cb.cy, dz = a[k].z - cb.cz, d = dx * dx + dy * dy + dz * dz;
-		if (next == REF_END) next = ref, next_d = d;
-		else if (d < next_d) stack[sp++] = next, next = ref, next_d = d;
-		else stack[sp++] = ref;
+		ref[k] = __float_as_int(a[k].w);
+		const bool ov = (ref[k] != WIDE_EMPTY) & cull_overlap(cb, a[k].x, a[k].y, a[k].z, b[k].x, b[k].y, b[k].z);
+		const float dx = a[k].x - cb.cx, dy = a[k].y - cb.cy, dz = a[k].z - cb.cz;
+		d[k] = ov ? dx * dx + dy * dy + dz * dz : __int_as_float(0x7f800000);
 	}
-	if (next == REF_END && sp > 0) next = stack[--sp];
+	int next = REF_END;
+	float next_d = __int_as_float(0x7f800000);
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const bool nearer = d[k] < next_d;
+		next = nearer ? ref[k] : next, next_d = nearer ? d[k] : next_d;
+	}
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+		if (d[k] < __int_as_float(0x7f800000) && ref[k] != next) st.push(ref[k]);
+	if (next == REF_END && st.sp > 0) next = st.pop();
 	return next;
 }
 
@@ -183,15 +231,16 @@ __device__ __noinline__ bool box_hits_scene(const SceneDev &sc, const CullBox &c
 											LocalCounters &lc) {
 	if (!sc.n_nodes) return false;
 	const ExactBox eb = make_exact_box(c, q, half);
-	int stack[STACK_DEPTH], sp = 0, cur = 0;
+	int stack[STACK_DEPTH], cur = 0;
+	LocalStack st{stack, 0};
 	lc.boxes++;
 	while (cur != REF_END) {
 		if (cur >= 0) {
 			lc.nodes++;
-			cur = visit_record(sc, cb, cur, stack, sp);
+			cur = visit_record(sc, cb, cur, st);
 		} else {
 			if (leaf_hit(sc, cb, eb, cur, lc)) return true;
-			cur = sp > 0 ? stack[--sp] : REF_END;
+			cur = st.sp > 0 ? st.pop() : REF_END;
 		}
 	}
 	return false;
@@ -259,9 +308,8 @@ __device__ __forceinline__ void emit_box(const SceneDev &sc, const QueueDev &Q, 
 			free_of_scene = scene_clearance(sc, cb.cx, cb.cy, cb.cz) > sqrtf(cb.hx * cb.hx + cb.hy * cb.hy + cb.hz * cb.hz) + 1e-4f;
 		}
 		if (free_of_scene) return;
-	}
-	if (sc.wide) {
-		// One level further while the box is in registers anyway: the root record's (up to four) children travel with the
+	} else if (sc.wide) {
+		// (without a clearance grid) One level further while the box is in registers anyway: the root record's (up to four) children travel with the
 		// kernel parameters.  A box that misses all of them would cost stage B a queue item, a refill and a record fetch.
 		bool any = false;
 #pragma unroll
@@ -455,7 +503,7 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // 
 /// Result bit index = row * (32 * words_per_row) + sample.
 __global__ void __launch_bounds__(BLOCK_A)
 k_expand_goals(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ targets,
-			   size_t rows, size_t per_row, const double *__restrict__ draws, const double *__restrict__ limits,
+			   size_t rows, size_t per_row, const double *__restrict__ draws,
 			   unsigned long long seed, double distance_from_target, double *__restrict__ states_out, size_t pass_lo, size_t pass_hi,
 			   QueueDev Q, Results res) {
 	LocalCounters lc;
@@ -472,7 +520,7 @@ k_expand_goals(const __grid_constant__ SceneDev sc, const __grid_constant__ Robo
 			unsigned long long ctr = i * (unsigned long long) (1 + nv);
 			yaw = -M_PI + 2.0 * M_PI * u01_from_bits(mix64(seed ^ mix64(ctr)));
 			for (int k = 0; k < nv; ++k)
-				jv[k] = limits[2 * k] + (limits[2 * k + 1] - limits[2 * k]) * u01_from_bits(mix64(seed ^ mix64(ctr + 1 + k)));
+				jv[k] = rb.limits[2 * k] + (rb.limits[2 * k + 1] - rb.limits[2 * k]) * u01_from_bits(mix64(seed ^ mix64(ctr + 1 + k)));
 		}
 		// genUprightState: base at the origin, rotation about z by yaw (Quaternion.h:53-62 with axis UnitZ)
 		double sy, cy;
@@ -547,6 +595,15 @@ __device__ __forceinline__ void expand_motion_step(const SceneDev &sc, const Rob
 	}
 	if (!isfinite(base.q.x + base.q.y + base.q.z + base.q.w)) return;
 	expand_state(sc, rb, Q, res, base, jv, motion, step, lc);
+}
+
+/// Overflow path of the motion survivor lists (a list ran full: badly skewed batches only), kept out of line so that its
+/// register demand and code do not shape k_motion_ranges: expand one interpolation step on the spot.
+__device__ __noinline__ void expand_motion_step_now(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
+													const double *A, const double *B, unsigned n_steps, const SlerpConst *slerp_k, unsigned motion, unsigned step) {
+	LocalCounters lc;
+	expand_motion_step(sc, rb, Q, res, A, B, n_steps, *slerp_k, motion, step, lc);
+	flush_counters_lane(sc, lc);
 }
 
 /// A1 for motions, one thread per motion: the step count of check_motion_collides (collision_detection.cpp:88-92)
@@ -634,34 +691,38 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 				// to the scene bounds, or to the triangles themselves where the clearance grid knows it, minus the reach).  The
 				// base moves step_len per step and distances are 1-Lipschitz, so a gap of g rules out floor(g / step_len) steps at
 				// once: a few look-ups walk each end of the range up to the first step that can touch anything.
+				// (fp32 on origin-relative coordinates with a reciprocal instead of divisions: this runs per look-up on a few lanes
+				// of the warp; 1e-3 m of extra reach and a 1e-3 relative cut of the stride swallow every rounding it introduces.)
+				const float fa[3] = {(float) (ar[0] - sc.origin[0]), (float) (ar[1] - sc.origin[1]), (float) (ar[2] - sc.origin[2])};
+				const float fd[3] = {(float) (br[0] - ar[0]), (float) (br[1] - ar[1]), (float) (br[2] - ar[2])};
+				const float inv_n = n_steps ? 1.0f / (float) n_steps : 0.f;
+				const float fr = (float) (rb.reach + (double) sc.margin) + 1e-3f;
+				const float step_len = n_steps ? (float) trans * inv_n : 0.f;
+				const float inv_step = step_len > 0.f ? 0.999f / step_len : 0.f;
 				auto gap = [&](unsigned s) {
-					const double t = n_steps ? (double) s / (double) n_steps : 0.0;
-					const double px = (1.0 - t) * ar[0] + t * br[0] - sc.origin[0], py = (1.0 - t) * ar[1] + t * br[1] - sc.origin[1],
-								 pz = (1.0 - t) * ar[2] + t * br[2] - sc.origin[2];
-					const double ex = fmax(fabs(px - (double) sc.root_c[0]) - (double) sc.root_h[0], 0.0);
-					const double ey = fmax(fabs(py - (double) sc.root_c[1]) - (double) sc.root_h[1], 0.0);
-					const double ez = fmax(fabs(pz - (double) sc.root_c[2]) - (double) sc.root_h[2], 0.0);
-					const double r = rb.reach + (double) sc.margin + 1e-4;
-					double g = sqrt(ex * ex + ey * ey + ez * ez) - r;
-					if (sc.clear && g <= 0.0) g = (double) scene_clearance(sc, (float) px, (float) py, (float) pz) - r;
+					const float t = (float) s * inv_n;
+					const float px = fa[0] + t * fd[0], py = fa[1] + t * fd[1], pz = fa[2] + t * fd[2];
+					const float ex = fmaxf(fabsf(px - sc.root_c[0]) - sc.root_h[0], 0.f), ey = fmaxf(fabsf(py - sc.root_c[1]) - sc.root_h[1], 0.f),
+								ez = fmaxf(fabsf(pz - sc.root_c[2]) - sc.root_h[2], 0.f);
+					float g = sqrtf(ex * ex + ey * ey + ez * ez) - fr;
+					if (sc.clear && g <= 0.f) g = scene_clearance(sc, px, py, pz) - fr;
 					return g;
 				};
-				const double step_len = n_steps ? trans / (double) n_steps : 0.0;
-				auto steps_cleared = [&](double g, unsigned room) {  // NaN positions count as clear, one step at a time
-					if (!(g > 0.0) || !(step_len > 0.0)) return 1u;
-					return (unsigned) fmin(fmax(floor(g / step_len), 1.0), (double) max(room, 1u));
+				auto steps_cleared = [&](float g, unsigned room) {  // NaN positions count as clear, one step at a time
+					if (!(g > 0.f) || !(inv_step > 0.f)) return 1u;
+					return (unsigned) fminf(fmaxf(floorf(g * inv_step), 1.f), (float) max(room, 1u));
 				};
 				for (int guard = 0; guard < trim && s_lo < s_hi; ++guard) {
-					const double g = gap(s_lo);
-					if (g <= 0.0) break;
+					const float g = gap(s_lo);
+					if (g <= 0.f) break;
 					s_lo += steps_cleared(g, s_hi - s_lo);
 				}
 				for (int guard = 0; guard < trim && s_hi > s_lo; ++guard) {
-					const double g = gap(s_hi);
-					if (g <= 0.0) break;
+					const float g = gap(s_hi);
+					if (g <= 0.f) break;
 					s_hi -= steps_cleared(g, s_hi - s_lo);
 				}
-				len = (s_lo == s_hi && !(gap(s_lo) <= 0.0)) ? 0u : s_hi - s_lo + 1;
+				len = (s_lo == s_hi && !(gap(s_lo) <= 0.f)) ? 0u : s_hi - s_lo + 1;
 				// head_steps == 0: adaptive head — the steps it takes to cross the reach shell around the scene bounds plus
 				// ~0.75 m of canopy, where a colliding motion typically finds its first hit
 				if (!head_steps) head = (unsigned) fmin(fmax((rb.reach + 0.75) * (double) n_steps / fmax(trans, 1e-3 * (double) n_steps), 8.0), 256.0);
@@ -703,7 +764,7 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 					for (unsigned k = lane; k < cnts[part]; k += 32) {
 						const unsigned pos = shard_slot(shard, bases[part] + k), step = lo + first + k;
 						if (pos < L.cap) L.entries[pos] = make_uint2(mot, step);
-						else expand_motion_step(sc, rb, Q, res, a + (size_t) mot * stride, b + (size_t) mot * stride, ns, slerp_out[mot], mot, step, lc);
+						else expand_motion_step_now(sc, rb, Q, res, a + (size_t) mot * stride, b + (size_t) mot * stride, ns, slerp_out + mot, mot, step);
 					}
 				}
 			}
@@ -765,14 +826,18 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 	__shared__ unsigned s_counts[SHARDS];
 	load_shard_counts(s_counts, Q.counts);
 	const unsigned n_items = sc.n_nodes ? slot_range(s_counts, Q.cap) : 0u;  // flat slot range, holes included
+	// few items per warp: claim one refill at a time so that the queue spreads over all the warps (a short queue is a latency problem)
+	const unsigned claim = n_items > gridDim.x * (BLOCK_B / 32) * QUEUE_CHUNK * 4u ? QUEUE_CHUNK : 32u;
 	LocalCounters lc;
 	unsigned chunk_lo = 0, chunk_hi = 0;  // warp-uniform: unclaimed part of this warp's chunk
 	bool exhausted = false;               // warp-uniform: the queue has nothing left to claim
 	// lane state: cur >= 0 walking (record index) | cur < 0 parked on a leaf reference | REF_END idle
 	CullBox cb{};
 	unsigned owner = 0, step_box = 0, item = 0;
-	int cur = REF_END, sp = 0;
-	int stack[WIDE ? WIDE_STACK_DEPTH : STACK_DEPTH];
+	int cur = REF_END;
+	__shared__ int s_stack[STACK_SHARED + 1][BLOCK_B];
+	int stack_overflow[(WIDE ? WIDE_STACK_DEPTH : STACK_DEPTH) - STACK_SHARED];
+	LaneStack st{&s_stack[0][threadIdx.x], stack_overflow, BLOCK_B, 0};
 	unsigned box_nodes = 0, max_box_nodes = 0;  // longest single descent (counters only)
 
 	for (;;) {
@@ -783,9 +848,9 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 		if (!exhausted && (__popc(idle_mask) >= REFILL_MIN)) {
 			if (chunk_lo == chunk_hi) {
 				unsigned lo = 0;
-				if (lane == 0) lo = atomicAdd(Q.cursor, QUEUE_CHUNK);
+				if (lane == 0) lo = atomicAdd(Q.cursor, claim);
 				lo = __shfl_sync(FULL, lo, 0);
-				chunk_lo = min(lo, n_items), chunk_hi = min(lo + QUEUE_CHUNK, n_items);
+				chunk_lo = min(lo, n_items), chunk_hi = min(lo + claim, n_items);
 				exhausted = chunk_lo >= n_items;
 			}
 			const unsigned avail = chunk_hi - chunk_lo, rank = __popc(idle_mask & ((1u << lane) - 1u));
@@ -810,7 +875,7 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 				}
 				cb = make_cull_box(sc, D3{v0.x, v0.y, v1.x}, Q4{v1.y, v2.x, v2.y, v3.x}, half_d);
 				if (res.mode == RESULT_BITS || !(first_hit <= (step_box & 0x0FFFFFFFu))) {
-					cur = 0, sp = 0;
+					cur = 0, st.sp = 0;
 					lc.boxes++;
 					max_box_nodes = max(max_box_nodes, box_nodes), box_nodes = 0;
 				}
@@ -824,7 +889,7 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 		while (go) {
 			if (cur >= 0) {
 				lc.nodes++, box_nodes++;
-				cur = WIDE ? visit_wide(sc, cb, cur, stack, sp) : visit_record(sc, cb, cur, stack, sp);
+				cur = WIDE ? visit_wide(sc, cb, cur, st) : visit_record(sc, cb, cur, st);
 			}
 			go = __ballot_sync(FULL, cur >= 0);
 			parked = __ballot_sync(FULL, cur < 0 && cur != REF_END);
@@ -858,7 +923,7 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 						report_hit(res, owner, step);
 						cur = REF_END;
 					} else {
-						cur = sp > 0 ? stack[--sp] : REF_END;
+						cur = st.sp > 0 ? st.pop() : REF_END;
 					}
 				}
 			}
@@ -939,7 +1004,7 @@ static int sm_count() {  // of the current device (a process may drive several)
 
 /// Environment knobs, read once (thread-safe: function-local static of a struct initialised by one expression).
 struct Knobs {
-	int pipeline, pipe_refill_min, pipe_blocks, pipe_claim, no_prefilter, traverse_blocks, refill_min, leaf_min, trim;
+	int pipeline, pipe_refill_min, pipe_leaf_min, pipe_blocks, pipe_claim, no_prefilter, traverse_blocks, refill_min, leaf_min, trim;
 	unsigned head_steps;
 	size_t queue_max_items, survivor_max_entries;
 	static int geti(const char *name, int dflt) {
@@ -951,7 +1016,7 @@ struct Knobs {
 		return e && atoll(e) > 0 ? (size_t) atoll(e) : dflt;
 	}
 	Knobs()
-		: pipeline(geti("MGODPL_PIPELINE", 0)), pipe_refill_min(geti("MGODPL_PIPE_REFILL_MIN", 8)), pipe_blocks(geti("MGODPL_PIPE_BLOCKS", 4)), pipe_claim(geti("MGODPL_PIPE_CLAIM", 0)),
+		: pipeline(geti("MGODPL_PIPELINE", 0)), pipe_refill_min(geti("MGODPL_PIPE_REFILL_MIN", 8)), pipe_leaf_min(geti("MGODPL_PIPE_LEAF_MIN", 32)), pipe_blocks(geti("MGODPL_PIPE_BLOCKS", 4)), pipe_claim(geti("MGODPL_PIPE_CLAIM", 0)),
 		  no_prefilter(geti("MGODPL_NO_PREFILTER", 0)), traverse_blocks(geti("MGODPL_TRAVERSE_BLOCKS", 4)), refill_min(geti("MGODPL_REFILL_MIN", 16)),
 		  leaf_min(geti("MGODPL_LEAF_MIN", 8)), trim(geti("MGODPL_TRIM", 16)),
 		  head_steps(geti("MGODPL_HEAD_STEPS", 0) > 0 ? (unsigned) geti("MGODPL_HEAD_STEPS", 0) : 0u),
@@ -976,7 +1041,7 @@ static size_t queue_max_items() { return knobs().queue_max_items; }
 static size_t survivor_max_entries() { return knobs().survivor_max_entries; }
 
 size_t query_scratch_bytes(size_t worst_case_boxes, size_t survivor_entries) {
-	if (knobs().pipeline) worst_case_boxes = 0;  // the fused kernel keeps its boxes in shared memory: no queue in HBM
+	if (knobs().pipeline == 1) worst_case_boxes = 0;  // the fused kernel keeps its boxes in shared memory: no queue in HBM
 	size_t cap = worst_case_boxes < queue_max_items() ? worst_case_boxes : queue_max_items();
 	size_t scap = survivor_entries < survivor_max_entries() ? survivor_entries : survivor_max_entries();
 	return SCRATCH_HEADER + ((scap * sizeof(uint2) + 255) & ~(size_t) 255) + (cap ? cap : 1) * sizeof(Item);
@@ -1022,25 +1087,6 @@ static QueueDev carve_queue(void *scratch, size_t scratch_bytes) {
 		if (e_ != cudaSuccess) return e_; \
 	} while (0)
 
-static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const double *explicit_boxes, const QueueDev &Q,
-								const Results &res, size_t worst_case_items, cudaStream_t stream) {
-	size_t bound = worst_case_items < Q.cap ? worst_case_items : Q.cap;
-	const int min_blocks = knobs().traverse_blocks;
-	const TraverseTuning tune{knobs().refill_min, knobs().leaf_min, knobs().no_prefilter};
-	const bool wide = sc.wide != nullptr;
-#define MGODPL_LAUNCH_TRAVERSE(MB)                                                                                                      \
-	if (wide) k_traverse<MB, true><<<grid_for(bound, BLOCK_B, MB), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune);       \
-	else k_traverse<MB, false><<<grid_for(bound, BLOCK_B, MB), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune)
-	switch (min_blocks) {
-		case 8: MGODPL_LAUNCH_TRAVERSE(8); break;
-		case 6: MGODPL_LAUNCH_TRAVERSE(6); break;
-		case 5: MGODPL_LAUNCH_TRAVERSE(5); break;
-		default: MGODPL_LAUNCH_TRAVERSE(4); break;
-	}
-#undef MGODPL_LAUNCH_TRAVERSE
-	return cudaGetLastError();
-}
-
 /// The fused expansion + traversal kernel (pipeline.cuh) over `bound` candidates at most.
 template<int KIND, bool CHAIN, bool WIDE>
 static cudaError_t launch_pipeline_inst(const SceneDev &sc, const RobotDev &rb, const SourceArgs &src, unsigned *cursor, const Results &res,
@@ -1048,7 +1094,7 @@ static cudaError_t launch_pipeline_inst(const SceneDev &sc, const RobotDev &rb, 
 	constexpr size_t smem = (BLOCK_P / 32) * sizeof(WarpMem);
 	auto kernel = k_pipeline<KIND, CHAIN, WIDE>;
 	LQ_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));  // per device, idempotent
-	PipeTuning tune{knobs().pipe_refill_min, knobs().no_prefilter, 32u * CLAIM_ROUNDS};
+	PipeTuning tune{knobs().pipe_refill_min, (unsigned) std::max(1, std::min(knobs().pipe_leaf_min, 32)), knobs().no_prefilter, 32u * CLAIM_ROUNDS};
 	const size_t resident = (size_t) sm_count() * (size_t) std::max(1, std::min(knobs().pipe_blocks, 4));
 	// small batches: one claim of 32 per warp so that the work spreads over the SMs; large ones: fewer cursor atomics
 	if (bound < resident * (BLOCK_P / 32) * tune.claim) tune.claim = 32u;
@@ -1063,11 +1109,36 @@ static cudaError_t launch_pipeline(const SceneDev &sc, const RobotDev &rb, const
 								   cudaStream_t stream) {
 	if (!sc.n_nodes && KIND != SRC_GOALS) return cudaSuccess;  // an empty scene collides with nothing (goal sampling still writes its states)
 	if (bound >= 0xFFF00000ull) return cudaErrorInvalidValue;   // the candidate cursor is 32 bits wide
-	const bool wide = sc.wide != nullptr, chain = KIND == SRC_BOXES || rb.chain;
+	constexpr bool one_box = KIND == SRC_BOXES || KIND == SRC_QUEUE;  // no FK in the kernel: a single instantiation
+	const bool wide = sc.wide != nullptr, chain = one_box || rb.chain;
 	if (wide) return chain ? launch_pipeline_inst<KIND, true, true>(sc, rb, src, cursor, res, bound, stream)
-						   : launch_pipeline_inst<KIND, KIND == SRC_BOXES, true>(sc, rb, src, cursor, res, bound, stream);
+						   : launch_pipeline_inst<KIND, one_box, true>(sc, rb, src, cursor, res, bound, stream);
 	return chain ? launch_pipeline_inst<KIND, true, false>(sc, rb, src, cursor, res, bound, stream)
-				 : launch_pipeline_inst<KIND, KIND == SRC_BOXES, false>(sc, rb, src, cursor, res, bound, stream);
+				 : launch_pipeline_inst<KIND, one_box, false>(sc, rb, src, cursor, res, bound, stream);
+}
+
+static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const double *explicit_boxes, const QueueDev &Q,
+								const Results &res, size_t worst_case_items, cudaStream_t stream) {
+	size_t bound = worst_case_items < Q.cap ? worst_case_items : Q.cap;
+	if (knobs().pipeline == 2) {  // the pipeline kernel fed from the queue: warp-wide leaf batches and shared-memory stacks, expansion stays a kernel of its own
+		SourceArgs src{};
+		src.queue = Q, src.boxes = explicit_boxes;
+		return launch_pipeline<SRC_QUEUE>(sc, rb, src, Q.cursor, res, bound, stream);
+	}
+	const int min_blocks = knobs().traverse_blocks;
+	const TraverseTuning tune{knobs().refill_min, knobs().leaf_min, knobs().no_prefilter};
+	const bool wide = sc.wide != nullptr;
+#define MGODPL_LAUNCH_TRAVERSE(MB)                                                                                                      \
+	if (wide) k_traverse<MB, true><<<grid_for(bound, BLOCK_B, MB), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune);       \
+	else k_traverse<MB, false><<<grid_for(bound, BLOCK_B, MB), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune)
+	switch (min_blocks) {
+		case 8: MGODPL_LAUNCH_TRAVERSE(8); break;
+		case 6: MGODPL_LAUNCH_TRAVERSE(6); break;
+		case 5: MGODPL_LAUNCH_TRAVERSE(5); break;
+		default: MGODPL_LAUNCH_TRAVERSE(4); break;
+	}
+#undef MGODPL_LAUNCH_TRAVERSE
+	return cudaGetLastError();
 }
 
 /// Stage A2 + B run in passes over the candidates so that a pass can never produce more boxes than the queue holds
@@ -1108,10 +1179,10 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
-	if (knobs().pipeline) Q.cap = 0;  // the fused kernel keeps its boxes on chip; only stage A1's overflow path would queue, and traverses inline instead
+	if (knobs().pipeline == 1) Q.cap = 0;  // the fused kernel keeps its boxes on chip; only stage A1's overflow path would queue, and traverses inline instead
 	k_cull_states<<<grid_for(n, BLOCK_A, 8), BLOCK_A, BLOCK_A * stride * sizeof(double), stream>>>(sc, rb, d_states, n, stride, S, Q, res);
 	LQ_CHECK(cudaGetLastError());
-	if (knobs().pipeline) {
+	if (knobs().pipeline == 1) {
 		SourceArgs src{};
 		src.list[0] = S, src.n_lists = 1, src.states = d_states, src.stride = stride;
 		return launch_pipeline<SRC_STATES>(sc, rb, src, Q.cursor, res, std::min<size_t>(S.cap, n + SHARDS * SHARD_BLOCK) * (size_t) ((rb.n_boxes + SPL - 1) / SPL > 0 ? (rb.n_boxes + SPL - 1) / SPL : 1), stream);
@@ -1136,7 +1207,7 @@ cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	RobotDev none{};
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
-	if (knobs().pipeline) {
+	if (knobs().pipeline == 1) {
 		LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
 		SourceArgs src{};
 		src.boxes = d_boxes, src.total = n;
@@ -1167,11 +1238,11 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_first_step, 0xff, m * sizeof(unsigned), stream));
 	if (d_uncertain) LQ_CHECK(cudaMemsetAsync(d_uncertain, 0, ((m + 31) / 32) * 4, stream));
-	if (knobs().pipeline) Q.cap = 0;
+	if (knobs().pipeline == 1) Q.cap = 0;
 	k_motion_ranges<<<grid_for(m, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
 																	  d_n_steps, d_uncertain, (SlerpConst *) d_slerp, S, S_tail, head_arg, trim, Q, res);
 	LQ_CHECK(cudaGetLastError());
-	if (knobs().pipeline) {
+	if (knobs().pipeline == 1) {
 		// one launch walks the head list, then the tail list: by the time a warp reaches a motion's tail steps, the head steps of
 		// (almost) every motion have been decided, and tail steps behind a hit are dropped when they are claimed
 		SourceArgs src{};
@@ -1208,7 +1279,7 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 }
 
 cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const double *d_targets, size_t f,
-								const double *d_draws, const double *d_limits, size_t s, unsigned long long seed,
+								const double *d_draws, size_t s, unsigned long long seed,
 								double distance_from_target, uint32_t *d_hit_bits, uint32_t *d_collisions,
 								double *d_states_out, void *scratch, size_t scratch_bytes, cudaStream_t stream) {
 	if (!f || !s) return cudaSuccess;
@@ -1216,10 +1287,10 @@ cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const do
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	const size_t wpr = (s + 31) / 32, total = f * s;
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, f * wpr * 4, stream));
-	if (knobs().pipeline) {
+	if (knobs().pipeline == 1) {
 		LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
 		SourceArgs src{};
-		src.targets = d_targets, src.draws = d_draws, src.limits = d_limits, src.rows = f, src.per_row = s, src.seed = seed;
+		src.targets = d_targets, src.draws = d_draws, src.rows = f, src.per_row = s, src.seed = seed;
 		src.distance_from_target = distance_from_target, src.states_out = d_states_out, src.total = total;
 		LQ_CHECK(launch_pipeline<SRC_GOALS>(sc, rb, src, Q.cursor, res, total * (size_t) std::max(1, (rb.n_boxes + SPL - 1) / SPL), stream));
 		if (d_collisions) {
@@ -1232,7 +1303,7 @@ cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const do
 	for (size_t lo = 0; lo < total; lo += R) {
 		const size_t hi = lo + R < total ? lo + R : total;
 		LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
-		k_expand_goals<<<grid_for(hi - lo, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_targets, f, s, d_draws, d_limits, seed, distance_from_target,
+		k_expand_goals<<<grid_for(hi - lo, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_targets, f, s, d_draws, seed, distance_from_target,
 																			  d_states_out, lo, hi, Q, res);
 		LQ_CHECK(cudaGetLastError());
 		LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (hi - lo) * (size_t) rb.n_boxes, stream));

@@ -522,9 +522,16 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 	BS_CHECK(cudaMalloc((void **) &ids, nt * sizeof(uint32_t)));  // kept: slot -> original triangle
 	out->tri_ids = ids;
 
-	cudaEvent_t ev0, ev1;
-	BS_CHECK(cudaEventCreate(&ev0));
-	BS_CHECK(cudaEventCreate(&ev1));
+	struct Events {  // destroyed on every exit path
+		cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+		~Events() {
+			for (cudaEvent_t x: e)
+				if (x) cudaEventDestroy(x);
+		}
+	} evs;
+	BS_CHECK(cudaEventCreate(&evs.e[0]));
+	BS_CHECK(cudaEventCreate(&evs.e[1]));
+	cudaEvent_t &ev0 = evs.e[0], &ev1 = evs.e[1], &ev2 = evs.e[2];
 	BS_CHECK(cudaEventRecord(ev0, stream));
 
 	D3 inv{hi[0] > lo[0] ? 1.0 / (hi[0] - lo[0]) : 0.0, hi[1] > lo[1] ? 1.0 / (hi[1] - lo[1]) : 0.0,
@@ -566,11 +573,10 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 		BS_CHECK(cudaMemcpyAsync(d_next, &first_id, sizeof(int), cudaMemcpyHostToDevice, stream));
 		k_ploc_init<<<gt, TB, 0, stream>>>(n, ids2, tlo, thi, cn[0], clo[0], chi[0]);
 		BS_CHECK(cudaGetLastError());
-		static int ploc_radius = 0;
-		if (!ploc_radius) {
+		static const int ploc_radius = [] {
 			const char *e = getenv("MGODPL_PLOC_RADIUS");
-			ploc_radius = e && atoi(e) > 0 ? atoi(e) : PLOC_RADIUS;
-		}
+			return e && atoi(e) > 0 ? atoi(e) : PLOC_RADIUS;
+		}();
 		int c = n, cur = 0;
 		while (c > 1) {
 			const unsigned g = (unsigned) ((c + TB - 1) / TB);
@@ -631,17 +637,16 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 	float4 h_root[2];
 	BS_CHECK(cudaMemcpyAsync(h_root, d_root_box, sizeof(h_root), cudaMemcpyDeviceToHost, stream));
 	BS_CHECK(cudaEventRecord(ev1, stream));
-	cudaEvent_t ev2 = nullptr;
 	if (clearance_grid) {
 		// grid over the scene bounds grown by CLEAR_PAD; cell size from a cell budget, never finer than 2 cm
 		const double pad = CLEAR_PAD;
 		double ext[3], vol = 1.0;
 		for (int a = 0; a < 3; ++a) ext[a] = (hi[a] - lo[a]) + 2.0 * pad, vol *= ext[a];
-		static size_t max_cells = 0;
-		if (!max_cells) {
+		static const size_t max_cells = [] {  // initialised once, thread-safe
 			const char *e = getenv("MGODPL_CLEARANCE_CELLS");
-			max_cells = e && atoll(e) > 0 ? (size_t) atoll(e) : (size_t) 6 << 20;
-		}
+			const size_t v = e && atoll(e) > 0 ? (size_t) atoll(e) : (size_t) 6 << 20;
+			return std::min<size_t>(v, (size_t) 1 << 30);  // cell indices are 32-bit on the device
+		}();
 		double cell = std::max(0.02, std::cbrt(vol / (double) max_cells));
 		int dims[3];
 		for (int a = 0; a < 3; ++a) dims[a] = std::max(1, (int) std::ceil(ext[a] / cell));
@@ -666,10 +671,7 @@ cudaError_t build_scene(const double *d_verts, size_t nv, const uint32_t *d_tris
 		float ms2 = 0;
 		cudaEventElapsedTime(&ms2, ev1, ev2);
 		out->clear_build_ms = ms2;
-		cudaEventDestroy(ev2);
 	}
-	cudaEventDestroy(ev0);
-	cudaEventDestroy(ev1);
 	out->n_nodes = n_nodes;
 	out->n_tris = (uint32_t) nt;
 	out->n_leaves = (uint32_t) st.n_leaves;

@@ -288,6 +288,80 @@ int main() {
 		}
 		CHECK(gs.collisions[3] == 0);  // a target far from the tree is always reachable
 	}
+	// -- a17 / a19: fromEndEffectorAndVector, arm_vector_from_state, project_to_goal, goal_region_sampler,
+	//    try_at_valid_goal_samples, generateUniformRandomArmVectorState against the oracle's restatements (pinned to the
+	//    reference's state_tools.cpp / goal_sampling.cpp through oracle/_ref and tests/golden) ------------------------------------
+	{
+		auto same_state = [](const RobotState &a, const orc::State &b) {
+			return a.base_tf.translation.x() == b.base.t.x && a.base_tf.translation.y() == b.base.t.y && a.base_tf.translation.z() == b.base.t.z &&
+				   a.base_tf.orientation.x == b.base.q.x && a.base_tf.orientation.y == b.base.q.y && a.base_tf.orientation.z == b.base.q.z &&
+				   a.base_tf.orientation.w == b.base.q.w && a.joint_values == b.joints;
+		};
+		random_numbers::RandomNumberGenerator rng(77);
+		for (int i = 0; i < 200; ++i) {
+			const math::Vec3d p{rng.uniformReal(-2, 2), rng.uniformReal(-2, 2), rng.uniformReal(0, 3)};
+			const math::Vec3d v{rng.gaussian01(), rng.gaussian01(), rng.gaussian01()};
+			const RobotState st = fromEndEffectorAndVector(robot, p, v);                                   // state_tools.cpp:14-42
+			CHECK(same_state(st, orc::from_end_effector_and_vector(orobot, {p.x(), p.y(), p.z()}, {v.x(), v.y(), v.z()})));
+			const math::Vec3d av = arm_vector_from_state(robot, st);                                         // state_tools.cpp:69-75
+			const orc::V3 oav = orc::arm_vector_from_state(orobot, to_orc(st));
+			CHECK(av.x() == oav.x && av.y() == oav.y && av.z() == oav.z);
+			// the arm points back along `v`, and the end effector sits on p
+			CHECK((av.normalized() - v.normalized()).norm() < 1e-9);
+			CHECK((robot_model::forwardKinematics(robot, st, flying_base).forLink(end_effector).translation - p).norm() < 1e-12);
+			// project_to_goal (goal_sampling.cppm:58-79) = the deterministic half of genGoalStateUniform
+			RobotState up = genUprightState(robot, rng);
+			const RobotState pg = project_to_goal(robot, up, flying_base, end_effector, p);
+			CHECK(same_state(pg, orc::project_upright_to_goal(orobot, to_orc(up), {p.x(), p.y(), p.z()}, 0.0, 0, (int) end_effector)));
+		}
+		// goal_region_sampler (goal_sampling.cppm:93-106): the closure draws from the caller's generator
+		random_numbers::RandomNumberGenerator g1(5);
+		orc::Rng g2(5);
+		auto sampler = goal_region_sampler(robot, g1);
+		for (int i = 0; i < 50; ++i) {
+			const math::Vec3d t{0.1 * i - 2.0, 0.3, 1.5};
+			CHECK(same_state(sampler(t), orc::gen_goal_state_uniform(g2, {t.x(), t.y(), t.z()}, 0.0, orobot, 0, (int) end_effector)));
+		}
+		// try_at_valid_goal_samples (goal_sampling.cppm:37-56) over the GPU state check vs over the oracle's
+		CollisionEnvironment env{robot, scene};
+		const CollisionFunctions fns = collision_functions_in_environment(env);
+		const orc::StateFn ocollides = [&](const orc::State &st) { return orc::check_robot_collision(orobot, oscene, st); };
+		size_t found = 0, none = 0;
+		for (int trial = 0; trial < 24; ++trial) {
+			const math::Vec3d t{0.5 * std::cos(trial), 0.5 * std::sin(trial), 1.0 + 0.05 * trial};
+			random_numbers::RandomNumberGenerator r1(900 + trial);
+			orc::Rng r2(900 + trial);
+			int ops1 = 0, ops2 = 0;
+			// the operation accepts every third valid sample: exercises "valid but operation declined"
+			auto got = try_at_valid_goal_samples<RobotState>(
+					fns.state_collides, [&] { return genGoalStateUniform(r1, t, robot, flying_base, end_effector); }, 12,
+					[&](const RobotState &st) -> std::optional<RobotState> { return ++ops1 % 3 == 0 ? std::optional<RobotState>(st) : std::nullopt; });
+			auto want = orc::try_at_valid_goal_samples<orc::State>(
+					ocollides, [&] { return orc::gen_goal_state_uniform(r2, {t.x(), t.y(), t.z()}, 0.0, orobot, 0, (int) end_effector); }, 12,
+					[&](const orc::State &st) -> std::optional<orc::State> { return ++ops2 % 3 == 0 ? std::optional<orc::State>(st) : std::nullopt; });
+			CHECK(got.has_value() == want.has_value() && ops1 == ops2);
+			if (got && want) CHECK(same_state(*got, *want));
+			CHECK(r1.uniformReal(0, 1) == r2.uniform_real(0, 1));
+			found += got.has_value(), none += !got.has_value();
+		}
+		CHECK(found > 0 && none > 0);
+		// generateUniformRandomArmVectorState (goal_sampling.cpp:101-124): batched look-ahead vs the sequential loop
+		size_t av_found = 0, av_none = 0;
+		for (int trial = 0; trial < 40; ++trial) {
+			const math::Vec3d fruit{0.6 * std::cos(0.7 * trial), 0.6 * std::sin(0.7 * trial), 0.8 + 0.03 * trial};
+			const int attempts = trial % 4 == 0 ? 2 : 60;
+			random_numbers::RandomNumberGenerator r1(300 + trial);
+			orc::Rng r2(300 + trial);
+			auto got = generateUniformRandomArmVectorState(robot, scene, fruit, r1, attempts, 0.05);
+			auto want = orc::generate_uniform_random_arm_vector_state(orobot, ocollides, {fruit.x(), fruit.y(), fruit.z()}, r2, attempts, 0.05);
+			CHECK(got.has_value() == want.has_value());
+			if (got && want) CHECK(same_state(*got, *want));
+			CHECK(r1.uniformReal(0, 1) == r2.uniform_real(0, 1));  // both generators consumed the same draws
+			av_found += got.has_value(), av_none += !got.has_value();
+		}
+		std::printf("goal helpers: try_at_valid_goal_samples %zu found / %zu none; arm-vector states %zu found / %zu none\n", found, none, av_found, av_none);
+		CHECK(av_found > 0);
+	}
 	// -- batched PRM edge validation = the reference's sequential insert-and-connect loop -----------------------------------
 	{
 		random_numbers::RandomNumberGenerator rng(11);

@@ -130,10 +130,44 @@ d_local, _ = o.roadmap_shortest_paths(nv, edges, w, sources[lo:hi])
 d_full = mg.sharding.gather_rows(torch.from_numpy(d_local), len(sources), rank, 2).numpy()
 d_want, _ = o.roadmap_shortest_paths(nv, edges, w, sources)
 assert (lo, hi) == ((0, 64), (64, 70))[rank] and np.array_equal(d_full, d_want)
+# motions: shards balanced by the predicted state checks per motion (known before launch), ragged gather of words and toi rows
+m = 900
+a, b = states[:m // 2 * 2:2][:400], states[1:m // 2 * 2:2][:400]
+costs = mg.sharding.predicted_motion_costs(a, b)
+whole = scene.check_motions(robot, a, b)
+assert np.array_equal(costs, whole["n_steps"] + 1)
+bounds = mg.sharding.balanced_bounds(costs, 2)
+assert bounds[0][0] == 0 and bounds[0][1] == bounds[1][0] and bounds[1][1] == len(a) and bounds[0][1] % 32 == 0
+lo, hi = bounds[rank]
+mine = scene.check_motions(robot, a[lo:hi], b[lo:hi])
+w = np.packbits(mine["hit"], bitorder="little")
+w = np.concatenate([w, np.zeros((-len(w)) % 4, np.uint8)]).view(np.uint32)
+words = mg.sharding.gather_ragged(torch.from_numpy(w.view(np.int32).copy()), bounds, rank).numpy().view(np.uint32)
+toi = mg.sharding.gather_ragged(torch.from_numpy(mine["toi"]), bounds, rank, per_query_words=False).numpy()
+assert np.array_equal(mg.capi.unpack_bits(words, len(a)), whole["hit"]) and np.array_equal(toi, whole["toi"], equal_nan=True)
+shard_cost = [costs[l:h].sum() for l, h in bounds]
+assert max(shard_cost) <= 1.2 * (sum(shard_cost) / 2)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok", int(want.sum()))
 """
+
+
+def test_balanced_bounds_cover_align_and_balance(mg):
+    rng = np.random.default_rng(0)
+    for n in [0, 1, 31, 33, 1000, 100_003]:
+        costs = rng.integers(1, 300, n)
+        for world in [1, 2, 3, 8]:
+            b = mg.sharding.balanced_bounds(costs, world)
+            assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+            for (lo, hi), (lo2, _) in zip(b, b[1:]):
+                assert hi == lo2 and lo <= hi and (lo % 32 == 0 or lo == n)
+            if n >= 32 * world * 50:
+                tot = [costs[lo:hi].sum() for lo, hi in b]
+                assert max(tot) < 1.02 * costs.sum() / world
+    # all the cost in one place: the other shards are simply empty, nothing is lost
+    b = mg.sharding.balanced_bounds([0] * 64 + [5] + [0] * 63, 4)
+    assert b[0][0] == 0 and b[-1][1] == 128 and sum(hi - lo for lo, hi in b) == 128
 
 
 def test_two_rank_gloo_shard_and_gather(tmp_path):
