@@ -37,6 +37,7 @@ M_MOTIONS = 100_000
 ARM, JOINTS = 0.75, (0,)
 TREE = dict(seed=42, trunk_triangles=50_000, leaf_triangles=150_000, n_fruit=500)
 MAX_STEP = 0.1
+GATHER_EVERY = 4  # N > 1: result words of this many consecutive batches share one all-gather
 # our kernels inside the device-timed region, per step
 LAUNCHES_PER_STEP = 6
 KERNEL_NOTE = ("check_motions pipeline: k_motion_ranges + 2 x (k_expand_motion_steps + k_traverse) + k_finish_motions; k_traverse is the "
@@ -151,24 +152,32 @@ def run_ours(args):
     d_steps = torch.zeros(m, dtype=torch.int32, device=dev)
     d_unc = torch.zeros(words, dtype=torch.int32, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)  # 256 MiB > 126 MB of L2
-    # N > 1: the only exchange on this path is the gather of the packed result words (12.5 KB per rank).  It is
-    # latency-bound, so it is issued asynchronously once per batch (NCCL's own stream) and overlaps the next batch's
-    # kernels; result buffers alternate so a gather never reads words the next step is rewriting.
-    hit_bufs = [d_hit, torch.zeros_like(d_hit)]
-    gathered = [[torch.empty_like(d_hit) for _ in range(world)] for _ in range(2)] if world > 1 else None
+    # N > 1: the only exchange on this path is the gather of the packed result words (12.5 KB per rank and batch).  It is
+    # latency-bound and nothing waits for it inside a batch, so the words of GATHER_EVERY consecutive batches travel in one
+    # asynchronous all-gather (NCCL's own stream), overlapping the following batches' kernels; two such groups of result
+    # buffers alternate so that a gather never reads words a later step is rewriting.
+    G = GATHER_EVERY if world > 1 else 1
+    hit_groups = [torch.zeros((G, words), dtype=torch.int32, device=dev) for _ in range(2)]
+    gathered = [torch.empty((world, G, words), dtype=torch.int32, device=dev) for _ in range(2)] if world > 1 else None
     pending = [None, None]
+    d_hit = hit_groups[0][0]
 
     def step(k=0):
-        slot = k & 1
-        if world > 1 and pending[slot] is not None:
-            pending[slot].wait()  # the gather that last read this buffer (two steps ago)
-            pending[slot] = None
-        mg.capi.check_motions_device(scene, robot, d_a, d_b, m, stride, js, hit_bufs[slot], MAX_STEP, d_toi, d_steps, d_unc,
+        group, slot = (k // G) & 1, k % G
+        if world > 1 and slot == 0 and pending[group] is not None:
+            pending[group].wait()  # the gather that last read this group of buffers (two groups ago)
+            pending[group] = None
+        mg.capi.check_motions_device(scene, robot, d_a, d_b, m, stride, js, hit_groups[group][slot], MAX_STEP, d_toi, d_steps, d_unc,
                                      stream=stream)
-        if world > 1:
-            pending[slot] = dist.all_gather(gathered[slot], hit_bufs[slot], async_op=True)
+        if world > 1 and slot == G - 1:
+            pending[group] = dist.all_gather_into_tensor(gathered[group], hit_groups[group], async_op=True)
 
-    def drain():
+    def drain(last_step=None):
+        if world > 1 and last_step is not None and (last_step + 1) % G:  # a partly filled group at the end still has to travel
+            group = (last_step // G) & 1
+            if pending[group] is not None:
+                pending[group].wait()
+            pending[group] = dist.all_gather_into_tensor(gathered[group], hit_groups[group], async_op=True)
         for i in range(2):
             if pending[i] is not None:
                 pending[i].wait()
@@ -178,7 +187,7 @@ def run_ours(args):
     sampler.start()
     for k in range(args.warmup):
         step(k)
-    drain()
+    drain(args.warmup - 1)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -189,7 +198,7 @@ def run_ours(args):
         ev[k][0].record()
         step(k)
         ev[k][1].record()
-    drain()  # the stream now waits for the gathers still in flight ...
+    drain(args.steps - 1)  # the stream now waits for the gathers still in flight ...
     tail = torch.cuda.Event(enable_timing=True)
     tail.record()  # ... and this event closes the timed region after them
     torch.cuda.synchronize()
@@ -197,7 +206,7 @@ def run_ours(args):
         dist.barrier()
     sampler.stop_flag.set()
     sampler.join()
-    d_hit = hit_bufs[(args.steps - 1) & 1]
+    d_hit = hit_groups[((args.steps - 1) // G) & 1][(args.steps - 1) % G]
     step_ms = [s.elapsed_time(e) for s, e in ev]
     total_ms = torch.tensor([sum(step_ms) + ev[-1][1].elapsed_time(tail)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -265,7 +274,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "motions_per_gpu": m, "triangles": int(info.n_triangles), "bvh_nodes": int(info.n_nodes),
-                   "l2": "flushed before every timed step (256 MiB write)", "parallelism": f"replicated scene x{world}, batch sharded"},
+                   "l2": "flushed before every timed step (256 MiB write)", "parallelism": f"replicated scene x{world}, batch sharded" + (f", result words all-gathered every {G} batches (async)" if world > 1 else "")},
         "motions_per_sec": motions_all * args.steps / (total_ms * 1e-3),
         "states_checked_per_motion": states_all / motions_all, "collision_rate": float(hit.mean()),
         "e2e": {"value": e2e_value, "unit": "states/s", "h2d_bytes_per_step": int(2 * m * stride * 8),
@@ -285,7 +294,7 @@ def run_ours(args):
     # scene — what actually limits this path is L1/L2-level traversal traffic and FP32 issue, not HBM.
     try:
         cscene = mg.Scene.from_mesh(mesh, counters=True)
-        mg.capi.check_motions_device(cscene, robot, d_a, d_b, m, stride, js, hit_bufs[0], MAX_STEP, d_toi, d_steps, d_unc, stream=stream)
+        mg.capi.check_motions_device(cscene, robot, d_a, d_b, m, stride, js, hit_groups[0][0], MAX_STEP, d_toi, d_steps, d_unc, stream=stream)
         torch.cuda.synchronize()
         c = cscene.counters()
         rec_bytes = 128 if int(info.n_wide_nodes) else 64
@@ -321,7 +330,7 @@ def run_ours(args):
 ORCHARD_STATES, ORCHARD_MOTIONS = 10_000_000, 1_000_000
 
 
-def orchard_strong_scaling(mg, torch, dist, dev, stream, rank, world, steps=5):
+def orchard_strong_scaling(mg, torch, dist, dev, stream, rank, world, steps=6):
     """BASELINE configs[4]: the 8-tree orchard row (~2 M triangles, makeSingleRowOrchard, TreeMeshes.cpp:197-206) replicated
     on every GPU; ONE fixed batch of 10 M state checks + 1 M motions split over the ranks (strong scaling).  States: equal
     32-aligned shards.  Motions: shards balanced by the predicted state checks per motion, ceil(d / 0.1) + 1, which is known
@@ -348,6 +357,8 @@ def orchard_strong_scaling(mg, torch, dist, dev, stream, rank, world, steps=5):
     costs = mg.sharding.predicted_motion_costs(d_ma.cpu().numpy(), d_mb.cpu().numpy(), MAX_STEP)
     partition_ms = (time.perf_counter() - t0) * 1e3
 
+    side = torch.cuda.Stream(device=dev)
+
     def plan(w):
         sb = [mg.sharding.shard_range(n, r, w) for r in range(w)]
         mb = mg.sharding.balanced_bounds(costs, w)
@@ -358,40 +369,59 @@ def orchard_strong_scaling(mg, torch, dist, dev, stream, rank, world, steps=5):
         return sb, mb, pad_s, pad_m, pad_mw
 
     def run(w, r, gather):
-        """Time `steps` batches on shard r of w; returns (ms per batch, state words, motion words, toi, n_steps) of the shard."""
+        """Time `steps` batches on shard r of w; returns (ms per batch, the gathered staging buffers of the last batch, plan, n_steps)."""
         sb, mb, pad_s, pad_m, pad_mw = plan(w)
         (slo, shi), (mlo, mhi) = sb[r], mb[r]
-        # one staging buffer per rank: [state words | motion words | toi], gathered with one collective
+        # one staging buffer per rank: [state words | motion words | toi], gathered with ONE collective per batch.  Two sets
+        # alternate, so the (asynchronous) gather of batch i overlaps the kernels of batch i + 1.
         words_total = pad_s + pad_mw + 2 * pad_m
-        local = torch.zeros(words_total, dtype=torch.int32, device=dev)
-        d_sw, d_mw = local[:pad_s], local[pad_s:pad_s + pad_mw]
-        d_toi = local[pad_s + pad_mw:].view(torch.float64)
+        local = [torch.zeros(words_total, dtype=torch.int32, device=dev) for _ in range(2)]
+        everyone = [torch.empty(w * words_total, dtype=torch.int32, device=dev) for _ in range(2)] if gather else None
         d_steps = torch.zeros(max(mhi - mlo, 1), dtype=torch.int32, device=dev)
-        everyone = torch.empty(w * words_total, dtype=torch.int32, device=dev) if gather else None
         d_states, a_sh, b_sh = st[slo:shi], d_ma[mlo:mhi], d_mb[mlo:mhi]
+        pending = [None, None]
 
-        def batch():
+        def batch(k):
+            buf = local[k & 1]
+            d_sw, d_mw, d_toi = buf[:pad_s], buf[pad_s:pad_s + pad_mw], buf[pad_s + pad_mw:].view(torch.float64)
+            if pending[k & 1] is not None:
+                pending[k & 1].wait()  # the gather that last read this staging buffer (two batches ago)
+                pending[k & 1] = None
+            # the state half and the motion half of a batch are independent: they run on two streams (a small shard is bound by
+            # the latency of its few launches, not by throughput), joined before the results travel
+            side.wait_stream(torch.cuda.current_stream())
             if shi > slo:
-                mg.capi.check_states_device(oscene, robot, d_states, shi - slo, 9, 2, d_sw, stream=stream)
+                with torch.cuda.stream(side):
+                    mg.capi.check_states_device(oscene, robot, d_states, shi - slo, 9, 2, d_sw, stream=side.cuda_stream)
             if mhi > mlo:
                 mg.capi.check_motions_device(oscene, robot, a_sh, b_sh, mhi - mlo, 9, 2, d_mw, MAX_STEP, d_toi, d_steps, stream=stream)
+            torch.cuda.current_stream().wait_stream(side)
             if gather:
-                dist.all_gather_into_tensor(everyone, local)
-        for _ in range(2):
-            batch()
+                pending[k & 1] = dist.all_gather_into_tensor(everyone[k & 1], buf, async_op=True)
+
+        def drain():
+            for i in range(2):
+                if pending[i] is not None:
+                    pending[i].wait()
+                    pending[i] = None
+        for k in range(2):
+            batch(k)
+        drain()
         torch.cuda.synchronize()
         if gather:
             dist.barrier()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         for k in range(steps):
-            evs[k][0].record()
-            batch()
-            evs[k][1].record()
+            batch(k)
+        drain()  # the stream waits for the gathers still in flight: they are inside the timed region
+        e1.record()
         torch.cuda.synchronize()
-        ms = torch.tensor([sum(x.elapsed_time(y) for x, y in evs) / steps], dtype=torch.float64, device=dev)
+        ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
         if gather:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        full = everyone.view(w, words_total) if gather else local.view(1, words_total)
+        last = (steps - 1) & 1
+        full = everyone[last].view(w, words_total) if gather else local[last].view(1, words_total)
         return float(ms.item()), full, (sb, mb, pad_s, pad_m, pad_mw), d_steps
 
     ms_n, full, (sb, mb, pad_s, pad_m, pad_mw), _ = run(world, rank, world > 1)

@@ -129,7 +129,7 @@ struct WorkspacePool {
 		// keep a few workspaces of ordinary size around; a very large one (or a fifth idle one) goes back to the driver
 		// instead of pinning device memory for the life of the handle
 		std::unique_lock<std::mutex> g(mu);
-		if (free_list.size() < 4 && w->dev_cap <= ((size_t) 1 << 30)) {
+		if (free_list.size() < 4 && w->dev_cap <= ((size_t) 4 << 30)) {
 			free_list.push_back(std::move(w));
 			return;
 		}
@@ -701,11 +701,12 @@ int mgodpl_check_states(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 }
 
 // ---- motions ---------------------------------------------------------------------------------------------------------------
-/// Queue sizing for motions: the step count is only known on the device, so assume ~128 steps per motion (the PRM
-/// sampler averages ~104) — a wrong guess only moves work between stage B and stage A's inline path.
-static size_t motion_survivors(size_t m) { return m * 128; }
+/// Work-list sizing for motions: what survives the clearance-grid trimming is only known on the device, so assume up to 64
+/// steps per motion within reach of the scene (the PRM sampler on a single tree averages ~7).  A wrong guess only moves work
+/// to the overflow paths: a full survivor list expands inline, a full queue traverses inline.
+static size_t motion_survivors(size_t m) { return m * 64; }
 static size_t motion_scratch_bytes(size_t m, int n_boxes) {
-	return query_scratch_bytes(m * 128 * (size_t) n_boxes, motion_survivors(m));
+	return query_scratch_bytes(m * 32 * (size_t) n_boxes, motion_survivors(m));  // head and tail list hold m * 32 entries each
 }
 
 int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, const double *d_a, const double *d_b, size_t m,

@@ -79,72 +79,6 @@ struct PipeTuning {
 	unsigned claim;    // candidates a warp claims per cursor atomic (a multiple of 32)
 };
 
-// ---- joint-value sources: a joint value is fetched when its FK op needs it (no per-thread joint array) ------------------
-struct JointsFromRow {
-	const double *p;
-	__device__ __forceinline__ double operator()(int var) const { return __ldg(p + var); }
-};
-struct JointsLerp {  // RobotState.cpp:19-21: a (1 - t) + b t
-	const double *a, *b;
-	double t;
-	bool moving;
-	__device__ __forceinline__ double operator()(int var) const {
-		return moving ? __ldg(a + var) * (1 - t) + __ldg(b + var) * t : __ldg(a + var);
-	}
-};
-struct JointsGoal {  // genUprightState's draws (goal_sampling.cpp:13-49): caller-supplied, or a counter-based generator
-	const double *draw_row, *limits;
-	unsigned long long seed, ctr;
-	__device__ __forceinline__ double operator()(int var) const {
-		if (draw_row) return __ldg(draw_row + 1 + var);
-		return limits[2 * var] + (limits[2 * var + 1] - limits[2 * var]) * u01_from_bits(mix64(seed ^ mix64(ctr + 1 + var)));
-	}
-};
-
-template<class Joints>
-__device__ __noinline__ Pose fk_apply_j(const FkOp &op, const Pose &parent, const Joints &joints) {
-	Pose p = then(parent, D3{op.pre_t[0], op.pre_t[1], op.pre_t[2]}, Q4{op.pre_q[0], op.pre_q[1], op.pre_q[2], op.pre_q[3]},
-				  op.flags & FK_PRE_ROT_ID);
-	if (op.var >= 0) {
-		double s, c;
-		sincos(joints(op.var) / 2.0, &s, &c);
-		if (op.flags & FK_INVERT) s = -s;
-		p.q = qmul(p.q, Q4{op.axis[0] * s, op.axis[1] * s, op.axis[2] * s, c});
-	}
-	return then(p, D3{op.post_t[0], op.post_t[1], op.post_t[2]}, Q4{op.post_q[0], op.post_q[1], op.post_q[2], op.post_q[3]},
-				op.flags & FK_POST_ROT_ID);
-}
-
-/// The culls a box goes through before it is worth a ring slot: scene bounds, clearance grid, the root record's children.
-__device__ __noinline__ bool box_may_touch_scene(const SceneDev &sc, D3 c, Q4 q, const double *half, const BoxDev *spheres) {
-	if (!sc.n_nodes) return false;  // empty scene
-	const CullBox cb = make_cull_box(sc, c, q, half);
-	if (!cull_overlap(cb, sc.root_c[0], sc.root_c[1], sc.root_c[2], sc.root_h[0], sc.root_h[1], sc.root_h[2])) return false;
-	if (sc.clear) {
-		bool free_of_scene = true;
-		if (spheres) {
-			const float need = spheres->sphere_r + sc.margin + 1e-4f;
-#pragma unroll
-			for (int k = 0; k < BOX_SPHERES; ++k) {
-				const float ox = spheres->sphere_c[k][0], oy = spheres->sphere_c[k][1], oz = spheres->sphere_c[k][2];
-				free_of_scene &= scene_clearance(sc, cb.cx + cb.r[0] * ox + cb.r[1] * oy + cb.r[2] * oz, cb.cy + cb.r[3] * ox + cb.r[4] * oy + cb.r[5] * oz,
-												 cb.cz + cb.r[6] * ox + cb.r[7] * oy + cb.r[8] * oz) > need;
-			}
-		} else {
-			free_of_scene = scene_clearance(sc, cb.cx, cb.cy, cb.cz) > sqrtf(cb.hx * cb.hx + cb.hy * cb.hy + cb.hz * cb.hz) + 1e-4f;
-		}
-		if (free_of_scene) return false;
-	} else if (sc.wide) {
-		bool any = false;
-#pragma unroll
-		for (int k = 0; k < 4; ++k)
-			any |= __float_as_int(sc.top[2 * k].w) != WIDE_EMPTY &&
-				   cull_overlap(cb, sc.top[2 * k].x, sc.top[2 * k].y, sc.top[2 * k].z, sc.top[2 * k + 1].x, sc.top[2 * k + 1].y, sc.top[2 * k + 1].z);
-		if (!any) return false;
-	}
-	return true;
-}
-
 /// Per-lane view of the warp's worker state.  Members marked (u) hold the same value in every lane.
 struct Worker {
 	WarpMem *wm;
@@ -180,44 +114,6 @@ struct Worker {
 		__syncwarp();
 	}
 };
-
-/// FK for the links that carry collision geometry, one `emit` per box (check_robot_collision, collision_detection.cpp:57-80;
-/// check_link_collision :16-55).  All 32 lanes run the same loop (the robot is the same for everyone) so that every
-/// emit is a convergent point; lanes whose candidate is dead (`alive` false) skip the arithmetic.  Only the boxes
-/// [box_lo, box_hi) are emitted (robots with more boxes than a lane owns ring slots are expanded in several groups).
-/// CHAIN: every collision op continues from the previous one, so the running pose stays in registers and no link table
-/// exists at all (every procedural drone; RobotDev::chain).
-template<bool CHAIN, class Joints>
-__device__ __forceinline__ void expand_boxes(const SceneDev &sc, const RobotDev &rb, Worker &w, bool alive, const Pose &base, const Joints &joints,
-											 unsigned owner, unsigned step, int box_lo, int box_hi) {
-	auto boxes_of = [&](const Pose &link, int lo, int hi) {
-		lo = max(lo, box_lo), hi = min(hi, box_hi);
-		for (int bi = lo; bi < hi; ++bi) {
-			bool want = false;
-			Pose p = link;
-			if (alive) {
-				const BoxDev &bx = rb.boxes[bi];
-				if (!bx.tf_identity) p = then(link, D3{bx.t[0], bx.t[1], bx.t[2]}, Q4{bx.q[0], bx.q[1], bx.q[2], bx.q[3]}, false);
-				want = box_may_touch_scene(sc, p.t, p.q, bx.half, &bx);
-			}
-			w.emit(want, p.t, p.q, owner, step, (unsigned) bi);
-		}
-	};
-	boxes_of(base, rb.root_box_begin, rb.root_box_end);
-	Pose cur = base;
-	Pose link_tf[CHAIN ? 1 : MGODPL_MAX_LINKS];
-	if (!CHAIN) link_tf[rb.root] = base;
-	for (int i = 0; i < rb.n_ops; ++i) {
-		const FkOp &op = rb.ops[i];
-		if (!(op.flags & FK_FOR_COLLISION)) continue;
-		if (op.box_begin >= box_hi && op.box_begin < op.box_end) break;  // boxes are sorted by op: nothing of this group is left
-		if (alive) {
-			cur = fk_apply_j(op, (CHAIN || (op.flags & FK_PARENT_IS_PREV)) ? cur : link_tf[op.parent], joints);
-			if (!CHAIN && (op.flags & FK_STORE)) link_tf[op.child] = cur;
-		}
-		boxes_of(cur, op.box_begin, op.box_end);
-	}
-}
 
 /// Exact phase of a leaf test with the pose passed by value (the pipeline's items live in shared memory).
 __device__ __noinline__ bool exact_leaf_test_pose(const SceneDev &sc, D3 c, Q4 q, const double *half, int ref, unsigned unknown, unsigned *n_tests) {
@@ -410,7 +306,7 @@ k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 							base = Pose{D3{r7[0], r7[1], r7[2]}, Q4{r7[3], r7[4], r7[5], r7[6]}};
 						}
 					}
-					expand_boxes<CHAIN>(sc, rb, w, alive, base, JointsFromRow{row + 7}, owner, 0u, box_lo, box_hi);  // (stage A1 counted the states)
+					expand_boxes<CHAIN, true>(sc, rb, w, alive, base, JointsFromRow{row + 7}, owner, 0u, box_lo, box_hi);  // (stage A1 counted the states)
 				} else if (KIND == SRC_MOTION_STEPS) {
 					JointsLerp jl{nullptr, nullptr, 0.0, false};
 					if (alive) {
@@ -420,76 +316,22 @@ k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 						if (alive) {
 							const uint2 e = __ldcg(&src.list[tail ? 1 : 0].entries[k]);
 							owner = e.x, step = e.y;
-							const unsigned first_hit = __ldcg(res.first_step + owner);  // travels with the endpoint rows: one round trip
-							const double *A = src.a + (size_t) owner * src.stride, *B = src.b + (size_t) owner * src.stride;
-							const unsigned ns = __ldg(src.n_steps + owner);
-							double a7[7], b7[7];
-#pragma unroll
-							for (int j = 0; j < 7; ++j) a7[j] = __ldg(A + j), b7[j] = __ldg(B + j);
-							alive = !(first_hit <= step);
-							if (alive) {
-								lc.states += box_lo == 0;
-								// for n_steps == 0 the reference evaluates t = 0/0; here the start state is checked once.
-								const double t = ns ? (double) step / (double) ns : 0.0;
-								const D3 tr{(1.0 - t) * a7[0] + t * b7[0], (1.0 - t) * a7[1] + t * b7[1], (1.0 - t) * a7[2] + t * b7[2]};
-								alive = !robot_out_of_reach(sc, rb, tr, false);
-								if (alive) {
-									base = Pose{tr, Q4{a7[3], a7[4], a7[5], a7[6]}};
-									if (ns) {  // Eigen slerp rule with the per-motion constants of stage A1
-										const SlerpConst sk = load_slerp(src.slerp + owner);
-										double w0, w1;
-										if (sk.theta < 0.0) {
-											w0 = 1.0 - t, w1 = t;
-										} else {
-											double s1, c1;
-											sincos(t * sk.theta, &s1, &c1);
-											w0 = c1 - sk.cot * s1;
-											w1 = s1 * fabs(sk.inv_sin);
-										}
-										if (signbit(sk.inv_sin)) w1 = -w1;
-										base.q = Q4{w0 * a7[3] + w1 * b7[3], w0 * a7[4] + w1 * b7[4], w0 * a7[5] + w1 * b7[5], w0 * a7[6] + w1 * b7[6]};
-									}
-									jl = JointsLerp{A + 7, B + 7, t, ns != 0};
-									alive = isfinite(base.q.x + base.q.y + base.q.z + base.q.w);
-								}
-							}
+							LocalCounters once;
+							alive = make_motion_step(sc, rb, src.a + (size_t) owner * src.stride, src.b + (size_t) owner * src.stride, __ldg(src.n_steps + owner),
+													 src.slerp + owner, step, res.first_step + owner, base, jl, once);
+							if (box_lo == 0) lc.states += once.states;
 						}
 					}
-					expand_boxes<CHAIN>(sc, rb, w, alive, base, jl, owner, step, box_lo, box_hi);
+					expand_boxes<CHAIN, true>(sc, rb, w, alive, base, jl, owner, step, box_lo, box_hi);
 				} else if (KIND == SRC_GOALS) {
 					JointsGoal jg{nullptr, rb.limits, src.seed, 0ull};
 					if (alive) {
-						const size_t row = (size_t) (cand / src.per_row), s = (size_t) (cand - row * src.per_row);
-						const int nv = rb.n_vars;
-						double yaw;
-						if (src.draws) {
-							jg.draw_row = src.draws + s * (size_t) (1 + nv);
-							yaw = __ldg(jg.draw_row);
-						} else {
-							jg.ctr = cand * (unsigned long long) (1 + nv);
-							yaw = -M_PI + 2.0 * M_PI * u01_from_bits(mix64(src.seed ^ mix64(jg.ctr)));
-						}
-						// genUprightState: base at the origin, rotation about z by yaw (Quaternion.h:53-62 with axis UnitZ); FK to the end
-						// effector along the op path that leads to it; base shifted so the end effector lands on the target
-						double sy, cy;
-						sincos(yaw / 2.0, &sy, &cy);
-						const Q4 yq{0 * sy, 0 * sy, 1 * sy, cy};
-						Pose ee{{0, 0, 0}, yq};
-						for (int k = 0; k < rb.n_ee_path; ++k) ee = fk_apply_j(rb.ops[rb.ee_path[k]], ee, jg);
-						D3 delta = D3{__ldg(src.targets + 3 * row), __ldg(src.targets + 3 * row + 1), __ldg(src.targets + 3 * row + 2)} - ee.t;
-						if (src.distance_from_target > 0.0) delta = delta + qrot(ee.q, D3{0.0, -src.distance_from_target, 0.0});
-						base = Pose{D3{0, 0, 0} + delta, yq};
-						if (src.states_out && box_lo == 0) {
-							double *o = src.states_out + cand * (size_t) (7 + nv);
-							o[0] = base.t.x, o[1] = base.t.y, o[2] = base.t.z;
-							o[3] = base.q.x, o[4] = base.q.y, o[5] = base.q.z, o[6] = base.q.w;
-							for (int k = 0; k < nv; ++k) o[7 + k] = jg(k);
-						}
-						lc.states += box_lo == 0;
-						owner = (unsigned) (row * (((src.per_row + 31) / 32) * 32) + s);
-						alive = !robot_out_of_reach(sc, rb, base.t);
+						LocalCounters once;
+						alive = make_goal_sample(sc, rb, src.targets, src.per_row, src.draws, src.seed, src.distance_from_target,
+												 box_lo == 0 ? src.states_out : nullptr, cand, base, jg, owner, once);
+						if (box_lo == 0) lc.states += once.states;
 					}
-					expand_boxes<CHAIN>(sc, rb, w, alive, base, jg, owner, 0u, box_lo, box_hi);
+					expand_boxes<CHAIN, true>(sc, rb, w, alive, base, jg, owner, 0u, box_lo, box_hi);
 				} else if (KIND == SRC_QUEUE) {  // a box queued by a stage A2 kernel: copy it on chip
 					bool want = alive && slot_filled(s_counts[0], (unsigned) cand);
 					unsigned step_box = 0;
@@ -508,7 +350,7 @@ k_pipeline(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 						for (int k = 0; k < 10; ++k) v[k] = __ldg(src.boxes + cand * 10 + k);
 						const double half[3] = {v[7] * 0.5, v[8] * 0.5, v[9] * 0.5};
 						base = Pose{D3{v[0], v[1], v[2]}, Q4{v[3], v[4], v[5], v[6]}};
-						want = finite7(v) && box_may_touch_scene(sc, base.t, base.q, half, nullptr);
+						want = finite7(v) && box_may_touch_scene_call(sc, base.t, base.q, half, nullptr);
 						owner = (unsigned) cand;
 					}
 					w.emit(want, base.t, base.q, owner, 0u, 0u);

@@ -27,6 +27,7 @@ namespace cg = cooperative_groups;
 namespace mgodpl_b200 {
 
 constexpr int BLOCK_A = 256;
+constexpr int BLOCK_C = 128;  // stage A2 for chain robots: 5 blocks x 4 warps per SM at <= 102 registers
 constexpr int BLOCK_B = 128;
 constexpr unsigned NO_HIT = 0xFFFFFFFFu;
 constexpr int ROW_MAX = 7 + MGODPL_MAX_JOINT_VALUES;
@@ -387,6 +388,30 @@ __device__ __forceinline__ void expand_state(const SceneDev &sc, const RobotDev 
 	}
 }
 
+__device__ __forceinline__ double u01_from_bits(unsigned long long x) { return (double) (x >> 11) * 0x1.0p-53; }
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // splitmix64 finaliser
+	z += 0x9E3779B97F4A7C15ull;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+
+/// Per-motion constants of the Eigen slerp rule (Quaternion.cpp:12-20), computed once in stage A1: with theta =
+/// acos(|dot|) the weights sin((1-t) theta) / sin(theta) and sin(t theta) / sin(theta) become, by the angle-difference
+/// identity, cos(t theta) - cot(theta) sin(t theta) and sin(t theta) / sin(theta): one sincos per step, no division.
+/// theta < 0 flags the linear-weights case; the sign of inv_sin carries "dot < 0" (second weight negated).
+struct __align__(16) SlerpConst {
+	double theta, inv_sin, cot, pad;
+};
+__device__ __forceinline__ SlerpConst load_slerp(const SlerpConst *p) {
+	const double2 lo = __ldg(reinterpret_cast<const double2 *>(p)), hi = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+	return SlerpConst{lo.x, lo.y, hi.x, 0.0};
+}
+
+}  // namespace mgodpl_b200
+#include "expand.cuh"
+namespace mgodpl_b200 {
+
 // ---------------------------------------------------------------------------------------------------------------
 // Stage A kernels
 // ---------------------------------------------------------------------------------------------------------------
@@ -453,23 +478,117 @@ k_cull_states(const __grid_constant__ SceneDev sc, const __grid_constant__ Robot
 	flush_counters(sc, lc);
 }
 
+// ---- the same stream through the bulk-copy engine (sm_90+ / sm_100a: cp.async.bulk + mbarrier) ---------------------------------
+// One elected lane per warp asks the copy engine for a whole 32-row span (32 * stride * 8 bytes, one descriptor-less bulk
+// copy global -> shared) and the warp keeps BULK_STAGES spans in flight; completion is signalled on an mbarrier by byte count,
+// so no thread spends load instructions or registers on the stream.  MGODPL_CULL_BULK=1 selects it.
+constexpr int BULK_STAGES = 3;
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+				 "r"(bytes), "r"(smem_addr(bar))
+				 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+	unsigned done = 0;
+	while (!done)
+		asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(BLOCK_A, 4)
+k_cull_states_bulk(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ states,
+				   size_t n, size_t stride, SurvivorsDev S, QueueDev Q, Results res) {
+	extern __shared__ __align__(128) unsigned char s_bulk[];
+	constexpr int WARPS = BLOCK_A / 32;
+	const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned span_bytes = 32u * (unsigned) stride * 8u, span_pad = (span_bytes + 127u) & ~127u;
+	unsigned long long *bars = reinterpret_cast<unsigned long long *>(s_bulk) + warp * BULK_STAGES;                 // WARPS x BULK_STAGES barriers
+	unsigned char *bufs = s_bulk + ((WARPS * BULK_STAGES * 8 + 127) & ~127) + (size_t) warp * BULK_STAGES * span_pad;  // this warp's stages
+	if (lane == 0)
+		for (int st = 0; st < BULK_STAGES; ++st) mbar_init(bars + st, 1);
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	__syncwarp();
+	unsigned n_states = 0;
+	const size_t full_spans = n / 32, warps_total = (size_t) gridDim.x * WARPS, first = (size_t) blockIdx.x * WARPS + warp;
+	auto issue = [&](size_t j) {  // span number j of this warp -> stage j % BULK_STAGES (lane 0 only)
+		const size_t span = first + j * warps_total;
+		if (span >= full_spans) return;
+		const int st = (int) (j % BULK_STAGES);
+		mbar_expect_tx(bars + st, span_bytes);
+		bulk_copy_g2s(bufs + (size_t) st * span_pad, states + span * 32 * stride, span_bytes, bars + st);
+	};
+	if (lane == 0)
+		for (int j = 0; j < BULK_STAGES; ++j) issue((size_t) j);
+	for (size_t j = 0; first + j * warps_total < full_spans; ++j) {
+		const int st = (int) (j % BULK_STAGES);
+		mbar_wait(bars + st, (unsigned) ((j / BULK_STAGES) & 1));
+		const double *r = reinterpret_cast<const double *>(bufs + (size_t) st * span_pad) + lane * stride;
+		const D3 t{r[0], r[1], r[2]};
+		const size_t i0 = (first + j * warps_total) * 32;
+		n_states++;
+		const bool keep = !robot_out_of_reach(sc, rb, t);
+		bool overflow = false;
+		unsigned pos = 0;
+		if (keep) {
+			cg::coalesced_group g = cg::coalesced_threads();
+			unsigned base = 0;
+			const unsigned shard = my_shard();
+			if (g.thread_rank() == 0) base = atomicAdd(S.counts + shard * COUNTER_STRIDE, g.size());
+			pos = shard_slot(shard, g.shfl(base, 0) + g.thread_rank());
+			if (pos < S.cap) S.entries[pos] = make_uint2((unsigned) (i0 + lane), 0u);
+			else overflow = true;
+		}
+		if (overflow) expand_state_now(sc, rb, Q, res, r, (unsigned) (i0 + lane));  // list full (badly skewed batch); reads the row before it is recycled
+		__syncwarp();  // every lane is done with this stage: hand it back to the copy engine
+		if (lane == 0) issue(j + BULK_STAGES);
+	}
+	// the ragged last span (n % 32 rows) goes through ordinary loads, by one warp of the grid
+	if (n % 32 && first == 0 && lane < n % 32) {
+		const size_t i = full_spans * 32 + lane;
+		const double *r = states + i * stride;
+		n_states++;
+		if (!robot_out_of_reach(sc, rb, D3{__ldg(r), __ldg(r + 1), __ldg(r + 2)})) {
+			cg::coalesced_group g = cg::coalesced_threads();
+			unsigned base = 0;
+			const unsigned shard = my_shard();
+			if (g.thread_rank() == 0) base = atomicAdd(S.counts + shard * COUNTER_STRIDE, g.size());
+			const unsigned pos = shard_slot(shard, g.shfl(base, 0) + g.thread_rank());
+			if (pos < S.cap) S.entries[pos] = make_uint2((unsigned) i, 0u);
+			else expand_state_now(sc, rb, Q, res, r, (unsigned) i);
+		}
+	}
+	LocalCounters lc;
+	lc.states = n_states;
+	flush_counters(sc, lc);
+}
+
 /// A2 for explicit states: FK + per-box cull + queue append, one thread per surviving state
-/// (check_robot_collision, collision_detection.cpp:57-80).
-__global__ void __launch_bounds__(BLOCK_A)
+/// (check_robot_collision, collision_detection.cpp:57-80).  CHAIN: the robot is a chain (every procedural drone), so no
+/// link table and no joint array exist — the running pose and the joint value an op needs are all that is live.
+template<bool CHAIN>
+__global__ void __launch_bounds__(CHAIN ? BLOCK_C : BLOCK_A, CHAIN ? 5 : 2)
 k_expand_states(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ states,
 				size_t stride, SurvivorsDev S, unsigned pass_lo, unsigned pass_hi, QueueDev Q, Results res) {
 	LocalCounters lc;
 	__shared__ unsigned s_counts[SHARDS];
 	load_shard_counts(s_counts, S.counts);
 	const unsigned n = min(slot_range(s_counts, S.cap), pass_hi);
-	for (unsigned k = pass_lo + blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
+	QueueSink sink{sc, Q, res, rb, lc};
+	for (unsigned k = pass_lo + blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
 		if (!slot_filled(s_counts, k)) continue;
 		const unsigned i = __ldcg(&S.entries[k]).x;
 		const double *r = states + (size_t) i * stride;
-		double row[ROW_MAX];
-		for (int j = 0; j < 7 + rb.n_vars; ++j) row[j] = __ldg(r + j);
-		if (!finite7(row)) continue;
-		expand_state(sc, rb, Q, res, Pose{D3{row[0], row[1], row[2]}, Q4{row[3], row[4], row[5], row[6]}}, row + 7, i, 0u, lc);
+		double r7[7];
+#pragma unroll
+		for (int j = 0; j < 7; ++j) r7[j] = __ldg(r + j);
+		if (!finite7(r7)) continue;
+		expand_boxes<CHAIN, false>(sc, rb, sink, true, Pose{D3{r7[0], r7[1], r7[2]}, Q4{r7[3], r7[4], r7[5], r7[6]}}, JointsFromRow{r + 7}, i, 0u, 0, MGODPL_MAX_BOXES);
 	}
 	flush_counters(sc, lc);
 }
@@ -489,72 +608,25 @@ k_expand_boxes(const __grid_constant__ SceneDev sc, const double *__restrict__ b
 	flush_counters(sc, lc);
 }
 
-__device__ __forceinline__ double u01_from_bits(unsigned long long x) { return (double) (x >> 11) * 0x1.0p-53; }
-__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {  // splitmix64 finaliser
-	z += 0x9E3779B97F4A7C15ull;
-	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-	return z ^ (z >> 31);
-}
-
-/// Goal samples: genGoalStateUniform (goal_sampling.cpp:51-79) for `rows` targets x `per_row` samples.  The upright
-/// state comes from caller-supplied draws (yaw, joint values — goal_sampling.cpp:13-49) or from a counter-based
-/// generator; FK to the end effector; base shifted so the end effector lands on the target; then the collision filter.
-/// Result bit index = row * (32 * words_per_row) + sample.
-__global__ void __launch_bounds__(BLOCK_A)
+/// Goal samples: genGoalStateUniform (goal_sampling.cpp:51-79) for `rows` targets x `per_row` samples, then the collision
+/// filter.  Result bit index = row * (32 * words_per_row) + sample.
+template<bool CHAIN>
+__global__ void __launch_bounds__(CHAIN ? BLOCK_C : BLOCK_A, CHAIN ? 5 : 2)
 k_expand_goals(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ targets,
 			   size_t rows, size_t per_row, const double *__restrict__ draws,
 			   unsigned long long seed, double distance_from_target, double *__restrict__ states_out, size_t pass_lo, size_t pass_hi,
 			   QueueDev Q, Results res) {
 	LocalCounters lc;
-	const int nv = rb.n_vars;
-	const size_t total = min(rows * per_row, pass_hi), bits_per_row = ((per_row + 31) / 32) * 32;
-	for (size_t i = pass_lo + (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < total; i += (size_t) gridDim.x * BLOCK_A) {
-		const size_t row = i / per_row, s = i - row * per_row;
-		double jv[MGODPL_MAX_JOINT_VALUES], yaw;
-		if (draws) {
-			const double *d = draws + s * (size_t) (1 + nv);
-			yaw = __ldg(d);
-			for (int k = 0; k < nv; ++k) jv[k] = __ldg(d + 1 + k);
-		} else {
-			unsigned long long ctr = i * (unsigned long long) (1 + nv);
-			yaw = -M_PI + 2.0 * M_PI * u01_from_bits(mix64(seed ^ mix64(ctr)));
-			for (int k = 0; k < nv; ++k)
-				jv[k] = rb.limits[2 * k] + (rb.limits[2 * k + 1] - rb.limits[2 * k]) * u01_from_bits(mix64(seed ^ mix64(ctr + 1 + k)));
-		}
-		// genUprightState: base at the origin, rotation about z by yaw (Quaternion.h:53-62 with axis UnitZ)
-		double sy, cy;
-		sincos(yaw / 2.0, &sy, &cy);
-		Pose tf[MGODPL_MAX_LINKS];
-		tf[rb.root] = Pose{{0, 0, 0}, {0 * sy, 0 * sy, 1 * sy, cy}};
-		for (int k = 0; k < rb.n_ops; ++k) tf[rb.ops[k].child] = fk_apply(rb.ops[k], tf[rb.ops[k].parent], jv);
-		const Pose ee = tf[rb.ee];
-		D3 delta = D3{__ldg(targets + 3 * row), __ldg(targets + 3 * row + 1), __ldg(targets + 3 * row + 2)} - ee.t;
-		if (distance_from_target > 0.0) delta = delta + qrot(ee.q, D3{0.0, -distance_from_target, 0.0});
-		const Pose base{D3{0, 0, 0} + delta, tf[rb.root].q};
-		if (states_out) {
-			double *o = states_out + i * (size_t) (7 + nv);
-			o[0] = base.t.x, o[1] = base.t.y, o[2] = base.t.z;
-			o[3] = base.q.x, o[4] = base.q.y, o[5] = base.q.z, o[6] = base.q.w;
-			for (int k = 0; k < nv; ++k) o[7 + k] = jv[k];
-		}
-		lc.states++;
-		if (robot_out_of_reach(sc, rb, base.t)) continue;
-		expand_state(sc, rb, Q, res, base, jv, (unsigned) (row * bits_per_row + s), 0u, lc);
+	QueueSink sink{sc, Q, res, rb, lc};
+	const size_t total = min(rows * per_row, pass_hi);
+	for (size_t i = pass_lo + (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		Pose base{};
+		JointsGoal jg{nullptr, rb.limits, seed, 0ull};
+		unsigned owner = 0;
+		if (!make_goal_sample(sc, rb, targets, per_row, draws, seed, distance_from_target, states_out, i, base, jg, owner, lc)) continue;
+		expand_boxes<CHAIN, false>(sc, rb, sink, true, base, jg, owner, 0u, 0, MGODPL_MAX_BOXES);
 	}
 	flush_counters(sc, lc);
-}
-
-/// Per-motion constants of the Eigen slerp rule (Quaternion.cpp:12-20), computed once in stage A1: with theta =
-/// acos(|dot|) the weights sin((1-t) theta) / sin(theta) and sin(t theta) / sin(theta) become, by the angle-difference
-/// identity, cos(t theta) - cot(theta) sin(t theta) and sin(t theta) / sin(theta): one sincos per step, no division.
-/// theta < 0 flags the linear-weights case; the sign of inv_sin carries "dot < 0" (second weight negated).
-struct __align__(16) SlerpConst {
-	double theta, inv_sin, cot, pad;
-};
-__device__ __forceinline__ SlerpConst load_slerp(const SlerpConst *p) {
-	const double2 lo = __ldg(reinterpret_cast<const double2 *>(p)), hi = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-	return SlerpConst{lo.x, lo.y, hi.x, 0.0};
 }
 
 /// One interpolation step of one motion: interpolate(a, b, t) (RobotState.cpp:14-24, Transform.h:69-78, Eigen slerp
@@ -622,7 +694,9 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 	const size_t m_pad = (m + 31) & ~(size_t) 31;
 	for (size_t i = (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < m_pad; i += (size_t) gridDim.x * BLOCK_A) {
 		unsigned s_lo = 0, len = 0, n_steps = 0, head = head_steps;
+		bool uncertain = false;
 		if (i < m) {
+			res.first_step[i] = NO_HIT;  // (this kernel initialises the per-motion result: no memset in front of it)
 			const double *A = a + i * stride, *B = b + i * stride;
 			double ar[7], br[7];
 #pragma unroll
@@ -637,7 +711,7 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 			const double trans = sqrt(dx * dx + dy * dy + dz * dz);
 			const double x = d / max_step;
 			double nd = ceil(x);
-			bool uncertain = fabs(x - rint(x)) < 1e-9 * fmax(1.0, x);
+			uncertain = fabs(x - rint(x)) < 1e-9 * fmax(1.0, x);
 			if (!(nd >= 0.0 && nd < 268435455.0)) nd = 0.0;  // non-finite / absurd distances: one check of the start state
 			n_steps = (unsigned) nd;
 			if (n_steps_override) {
@@ -658,7 +732,6 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 				if (dq < 0.0) k.inv_sin = -k.inv_sin;
 				slerp_out[i] = k;
 			}
-			if (uncertain && uncertain_bits) atomicOr(uncertain_bits + (i >> 5), 1u << (i & 31));
 			n_uncertain += uncertain;
 			n_motions++;
 			// slab clip of P(t) = A + t (B - A), t in [0, 1], against the scene bounds grown by the reach
@@ -728,7 +801,11 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 				if (!head_steps) head = (unsigned) fmin(fmax((rb.reach + 0.75) * (double) n_steps / fmax(trans, 1e-3 * (double) n_steps), 8.0), 256.0);
 			}
 		}
-		__syncwarp();  // slerp_out[] of this warp's motions is read by other lanes on the overflow path
+		{
+			const unsigned ub = __ballot_sync(0xffffffffu, uncertain);  // one whole word per warp iteration: no memset, no atomics
+			if (lane == 0 && uncertain_bits) uncertain_bits[i >> 5] = ub;
+		}
+		__syncwarp();  // slerp_out[] / first_step[] of this warp's motions are touched by other lanes on the overflow path
 		// cooperative append.  One allocation per warp and list: a prefix sum over the lanes' range lengths and a single
 		// atomicAdd of the total (a chain of per-motion atomics, each a dependent L2 round trip, used to be this kernel's
 		// critical path).  The first `head` steps of a range go to the head list, the rest to the tail list: the head is
@@ -778,8 +855,8 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 }
 
 /// A2 for motions: one thread per surviving (motion, step).
-template<int MIN_BLOCKS>
-__global__ void __launch_bounds__(BLOCK_A, MIN_BLOCKS)
+template<bool CHAIN>
+__global__ void __launch_bounds__(CHAIN ? BLOCK_C : BLOCK_A, CHAIN ? 5 : 2)
 k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
 					  const double *__restrict__ b, size_t stride, const uint32_t *__restrict__ n_steps,
 					  const SlerpConst *__restrict__ slerp_k, SurvivorsDev S, unsigned pass_lo, unsigned pass_hi, int skip_decided, QueueDev Q,
@@ -788,11 +865,16 @@ k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant
 	__shared__ unsigned s_counts[SHARDS];
 	load_shard_counts(s_counts, S.counts);
 	const unsigned n = min(slot_range(s_counts, S.cap), pass_hi);
-	for (unsigned k = pass_lo + blockIdx.x * BLOCK_A + threadIdx.x; k < n; k += gridDim.x * BLOCK_A) {
+	QueueSink sink{sc, Q, res, rb, lc};
+	for (unsigned k = pass_lo + blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
 		if (!slot_filled(s_counts, k)) continue;
 		const uint2 e = __ldcg(&S.entries[k]);
-		expand_motion_step(sc, rb, Q, res, a + (size_t) e.x * stride, b + (size_t) e.x * stride, __ldg(n_steps + e.x), load_slerp(slerp_k + e.x),
-						   e.x, e.y, lc, skip_decided ? res.first_step + e.x : nullptr);
+		Pose base{};
+		JointsLerp jl{nullptr, nullptr, 0.0, false};
+		if (!make_motion_step(sc, rb, a + (size_t) e.x * stride, b + (size_t) e.x * stride, __ldg(n_steps + e.x), slerp_k + e.x, e.y,
+							  skip_decided ? res.first_step + e.x : nullptr, base, jl, lc))
+			continue;
+		expand_boxes<CHAIN, false>(sc, rb, sink, true, base, jl, e.x, e.y, 0, MGODPL_MAX_BOXES);
 	}
 	flush_counters(sc, lc);
 }
@@ -1004,7 +1086,7 @@ static int sm_count() {  // of the current device (a process may drive several)
 
 /// Environment knobs, read once (thread-safe: function-local static of a struct initialised by one expression).
 struct Knobs {
-	int pipeline, pipe_refill_min, pipe_leaf_min, pipe_blocks, pipe_claim, no_prefilter, traverse_blocks, refill_min, leaf_min, trim;
+	int pipeline, pipe_refill_min, pipe_leaf_min, pipe_blocks, pipe_claim, cull_bulk, no_prefilter, traverse_blocks, refill_min, leaf_min, trim;
 	unsigned head_steps;
 	size_t queue_max_items, survivor_max_entries;
 	static int geti(const char *name, int dflt) {
@@ -1016,7 +1098,7 @@ struct Knobs {
 		return e && atoll(e) > 0 ? (size_t) atoll(e) : dflt;
 	}
 	Knobs()
-		: pipeline(geti("MGODPL_PIPELINE", 0)), pipe_refill_min(geti("MGODPL_PIPE_REFILL_MIN", 8)), pipe_leaf_min(geti("MGODPL_PIPE_LEAF_MIN", 32)), pipe_blocks(geti("MGODPL_PIPE_BLOCKS", 4)), pipe_claim(geti("MGODPL_PIPE_CLAIM", 0)),
+		: pipeline(geti("MGODPL_PIPELINE", 0)), pipe_refill_min(geti("MGODPL_PIPE_REFILL_MIN", 8)), pipe_leaf_min(geti("MGODPL_PIPE_LEAF_MIN", 32)), pipe_blocks(geti("MGODPL_PIPE_BLOCKS", 4)), pipe_claim(geti("MGODPL_PIPE_CLAIM", 0)), cull_bulk(geti("MGODPL_CULL_BULK", 0)),
 		  no_prefilter(geti("MGODPL_NO_PREFILTER", 0)), traverse_blocks(geti("MGODPL_TRAVERSE_BLOCKS", 4)), refill_min(geti("MGODPL_REFILL_MIN", 16)),
 		  leaf_min(geti("MGODPL_LEAF_MIN", 8)), trim(geti("MGODPL_TRIM", 16)),
 		  head_steps(geti("MGODPL_HEAD_STEPS", 0) > 0 ? (unsigned) geti("MGODPL_HEAD_STEPS", 0) : 0u),
@@ -1180,7 +1262,15 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
 	if (knobs().pipeline == 1) Q.cap = 0;  // the fused kernel keeps its boxes on chip; only stage A1's overflow path would queue, and traverses inline instead
-	k_cull_states<<<grid_for(n, BLOCK_A, 8), BLOCK_A, BLOCK_A * stride * sizeof(double), stream>>>(sc, rb, d_states, n, stride, S, Q, res);
+	if (knobs().cull_bulk && (reinterpret_cast<size_t>(d_states) & 15) == 0 && (32 * stride * 8) % 16 == 0) {
+		const size_t span_pad = (32 * stride * 8 + 127) & ~(size_t) 127;
+		const size_t smem = (((BLOCK_A / 32) * BULK_STAGES * 8 + 127) & ~(size_t) 127) + (BLOCK_A / 32) * BULK_STAGES * span_pad;
+		LQ_CHECK(cudaFuncSetAttribute(k_cull_states_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		const unsigned per_sm = (unsigned) std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / smem));
+		k_cull_states_bulk<<<grid_for(n, BLOCK_A, (int) per_sm), BLOCK_A, smem, stream>>>(sc, rb, d_states, n, stride, S, Q, res);
+	} else {
+		k_cull_states<<<grid_for(n, BLOCK_A, 8), BLOCK_A, BLOCK_A * stride * sizeof(double), stream>>>(sc, rb, d_states, n, stride, S, Q, res);
+	}
 	LQ_CHECK(cudaGetLastError());
 	if (knobs().pipeline == 1) {
 		SourceArgs src{};
@@ -1193,7 +1283,8 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 	for (size_t lo = 0; lo < end || lo == 0; lo += R) {
 		const size_t hi = lo + R < end ? lo + R : end;
 		if (lo) LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
-		k_expand_states<<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_states, stride, S, (unsigned) lo, (unsigned) hi, Q, res);
+		if (rb.chain) k_expand_states<true><<<grid_for(hi - lo, BLOCK_C, 5), BLOCK_C, 0, stream>>>(sc, rb, d_states, stride, S, (unsigned) lo, (unsigned) hi, Q, res);
+		else k_expand_states<false><<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_states, stride, S, (unsigned) lo, (unsigned) hi, Q, res);
 		LQ_CHECK(cudaGetLastError());
 		LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (hi - lo) * (size_t) rb.n_boxes, stream));
 	}
@@ -1236,8 +1327,6 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	carve(scratch, scratch_bytes, survivor_entries, &S, &Q, &S_tail, m * (size_t) (head_arg ? head_arg : 48u));
 	Results res{RESULT_FIRST_STEP, nullptr, d_first_step};
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
-	LQ_CHECK(cudaMemsetAsync(d_first_step, 0xff, m * sizeof(unsigned), stream));
-	if (d_uncertain) LQ_CHECK(cudaMemsetAsync(d_uncertain, 0, ((m + 31) / 32) * 4, stream));
 	if (knobs().pipeline == 1) Q.cap = 0;
 	k_motion_ranges<<<grid_for(m, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
 																	  d_n_steps, d_uncertain, (SlerpConst *) d_slerp, S, S_tail, head_arg, trim, Q, res);
@@ -1268,8 +1357,12 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 			// the first pass shares the queue with stage A1's own overflow path (a survivor list that ran full expands inline)
 			if (!first_pass) LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
 			first_pass = false;
-			k_expand_motion_steps<2><<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const SlerpConst *) d_slerp, L,
-																							 (unsigned) lo, (unsigned) hi, part, Q, res);
+			if (rb.chain)
+				k_expand_motion_steps<true><<<grid_for(hi - lo, BLOCK_C, 5), BLOCK_C, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const SlerpConst *) d_slerp, L,
+																									(unsigned) lo, (unsigned) hi, part, Q, res);
+			else
+				k_expand_motion_steps<false><<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const SlerpConst *) d_slerp, L,
+																									 (unsigned) lo, (unsigned) hi, part, Q, res);
 			LQ_CHECK(cudaGetLastError());
 			LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (hi - lo) * (size_t) rb.n_boxes, stream));
 		}
@@ -1303,8 +1396,10 @@ cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const do
 	for (size_t lo = 0; lo < total; lo += R) {
 		const size_t hi = lo + R < total ? lo + R : total;
 		LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
-		k_expand_goals<<<grid_for(hi - lo, BLOCK_A, 8), BLOCK_A, 0, stream>>>(sc, rb, d_targets, f, s, d_draws, seed, distance_from_target,
-																			  d_states_out, lo, hi, Q, res);
+		if (rb.chain)
+			k_expand_goals<true><<<grid_for(hi - lo, BLOCK_C, 5), BLOCK_C, 0, stream>>>(sc, rb, d_targets, f, s, d_draws, seed, distance_from_target, d_states_out, lo, hi, Q, res);
+		else
+			k_expand_goals<false><<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_targets, f, s, d_draws, seed, distance_from_target, d_states_out, lo, hi, Q, res);
 		LQ_CHECK(cudaGetLastError());
 		LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (hi - lo) * (size_t) rb.n_boxes, stream));
 	}

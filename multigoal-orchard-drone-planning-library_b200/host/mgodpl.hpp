@@ -3,6 +3,7 @@
 #include "mgodpl/collision_detection.hpp"
 #include "mgodpl/local_optimization.hpp"
 #include "mgodpl/math.hpp"
+#include "mgodpl/multi_gpu.hpp"
 #include "mgodpl/prm.hpp"
 #include "mgodpl/roadmap.hpp"
 #include "mgodpl/robot_model.hpp"

@@ -736,6 +736,41 @@ int main() {
 		std::printf("scanning motions: %zu arcs, %zu states kept, %zu arcs cut at a collision\n", arcs, states_total, cut_short);
 		CHECK(cut_short > 0 && cut_short < arcs);
 	}
+	// -- one process, several GPUs: a DeviceGroup shards every batch over its scene replicas (one per device; on a single-GPU
+	//    box the same device is listed twice, which exercises the same threads, shard bounds and in-place merging) -----------------
+	{
+		std::vector<int> devs;
+		for (int d = 0; d < std::min(mgodpl_device_count(), 4); ++d) devs.push_back(d);
+		if (devs.size() < 2) devs = {0, 0, 0};
+		const gpu::DeviceGroup group(tree, devs);
+		CHECK(group.size() == devs.size());
+		int dev = -1;
+		CHECK(mgodpl_scene_device(group.scene(group.size() - 1).handle(), &dev) == MGODPL_OK && dev == devs.back());
+		random_numbers::RandomNumberGenerator rng(2024);
+		std::vector<RobotState> st;
+		for (int i = 0; i < 5003; ++i) st.push_back(generateUniformRandomState(robot, rng, 2.5, 3.5));
+		CHECK(group.check_states(robot, st) == check_states(robot, scene, st));
+		const size_t m = 2001;
+		const MotionResults one = check_motions(robot, scene, st.data(), st.data() + m, m), many = group.check_motions(robot, st.data(), st.data() + m, m);
+		CHECK(one.hit_bits == many.hit_bits && one.n_steps == many.n_steps);
+		size_t toi_diff = 0;
+		for (size_t i = 0; i < m; ++i) toi_diff += !(one.toi[i] == many.toi[i] || (std::isnan(one.toi[i]) && std::isnan(many.toi[i])));
+		CHECK(toi_diff == 0);
+		// the motion shards are balanced by predicted state checks, and the prediction is the step count the device uses
+		std::vector<double> costs(m);
+		for (size_t i = 0; i < m; ++i) costs[i] = gpu::predicted_motion_cost(st[i], st[m + i]);
+		for (size_t i = 0; i < m; ++i) CHECK(costs[i] == (double) one.n_steps[i] + 1.0);
+		const auto bounds = gpu::balanced_bounds(costs, 3);
+		CHECK(bounds.front().first == 0 && bounds.back().second == m && bounds[0].second % 32 == 0 && bounds[0].second == bounds[1].first);
+		std::vector<math::Vec3d> targets;
+		for (int i = 0; i < 7; ++i) targets.push_back({0.5 * std::cos(i), 0.5 * std::sin(i), 1.2 + 0.1 * i});
+		const GoalSamples g1 = sample_goal_states(robot, scene, targets, 300, 42, 0.0, true), gn = group.sample_goal_states(robot, targets, 300, 42, 0.0, true);
+		CHECK(g1.hit_bits == gn.hit_bits && g1.collisions == gn.collisions && g1.states.size() == gn.states.size());
+		for (size_t i = 0; i < g1.states.size(); i += 97) CHECK(g1.states[i] == gn.states[i]);
+		std::printf("device group: %zu replicas on devices", group.size());
+		for (size_t r = 0; r < group.size(); ++r) std::printf(" %d", group.device(r));
+		std::printf("\n");
+	}
 	// -- error vocabulary -------------------------------------------------------------------------------------------------------
 	{
 		robot_model::RobotModel bad;
