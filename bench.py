@@ -37,7 +37,7 @@ M_MOTIONS = 100_000
 ARM, JOINTS = 0.75, (0,)
 TREE = dict(seed=42, trunk_triangles=50_000, leaf_triangles=150_000, n_fruit=500)
 MAX_STEP = 0.1
-GATHER_EVERY = 4  # N > 1: result words of this many consecutive batches share one all-gather
+GATHER_EVERY = int(os.environ.get("MGODPL_BENCH_GATHER_EVERY", "4"))  # N > 1: result words of this many consecutive batches share one all-gather
 # our kernels inside the device-timed region, per step
 LAUNCHES_PER_STEP = 6
 KERNEL_NOTE = ("check_motions pipeline: k_motion_ranges + 2 x (k_expand_motion_steps + k_traverse) + k_finish_motions; k_traverse is the "
@@ -183,6 +183,37 @@ def run_ours(args):
                 pending[i].wait()
                 pending[i] = None
 
+    if args.graph:
+        # replay the step's launches from CUDA graphs (one per result buffer): the host's share of a 0.3 ms step disappears
+        step(0)
+        drain(0)
+        torch.cuda.synchronize()
+        graphs = {}
+        cap = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(cap):  # the library keeps one scratch area per stream: let it allocate before the capture starts
+            mg.capi.check_motions_device(scene, robot, d_a, d_b, m, stride, js, hit_groups[0][0], MAX_STEP, d_toi, d_steps, d_unc, stream=cap.cuda_stream)
+        torch.cuda.synchronize()
+
+        def captured(k):
+            key = ((k // G) & 1, k % G)
+            if key not in graphs:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cap):
+                    mg.capi.check_motions_device(scene, robot, d_a, d_b, m, stride, js, hit_groups[key[0]][key[1]], MAX_STEP, d_toi, d_steps, d_unc,
+                                                 stream=torch.cuda.current_stream().cuda_stream)
+                graphs[key] = g
+            return graphs[key]
+        for k in range(2 * G):
+            captured(k)
+
+        def step(k=0):  # noqa: F811
+            group, slot = (k // G) & 1, k % G
+            if world > 1 and slot == 0 and pending[group] is not None:
+                pending[group].wait()
+                pending[group] = None
+            captured(k).replay()
+            if world > 1 and slot == G - 1:
+                pending[group] = dist.all_gather_into_tensor(gathered[group], hit_groups[group], async_op=True)
     sampler = ClockSampler(local)
     sampler.start()
     for k in range(args.warmup):
@@ -209,7 +240,13 @@ def run_ours(args):
     d_hit = hit_groups[((args.steps - 1) // G) & 1][(args.steps - 1) % G]
     step_ms = [s.elapsed_time(e) for s, e in ev]
     total_ms = torch.tensor([sum(step_ms) + ev[-1][1].elapsed_time(tail)], dtype=torch.float64, device=dev)
+    by_rank = None
     if world > 1:
+        # per rank: [whole timed region / steps, mean of the per-step events (what the rank's own kernels took)]
+        mine = torch.tensor([float(total_ms.item()) / args.steps, float(np.mean(step_ms))], dtype=torch.float64, device=dev)
+        all_ms = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(all_ms, mine)
+        by_rank = [[round(float(x[0].item()), 4), round(float(x[1].item()), 4)] for x in all_ms]
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
 
@@ -275,6 +312,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "motions_per_gpu": m, "triangles": int(info.n_triangles), "bvh_nodes": int(info.n_nodes),
                    "l2": "flushed before every timed step (256 MiB write)", "parallelism": f"replicated scene x{world}, batch sharded" + (f", result words all-gathered every {G} batches (async)" if world > 1 else "")},
+        "ms_per_step_by_rank": by_rank,
         "motions_per_sec": motions_all * args.steps / (total_ms * 1e-3),
         "states_checked_per_motion": states_all / motions_all, "collision_rate": float(hit.mean()),
         "e2e": {"value": e2e_value, "unit": "states/s", "h2d_bytes_per_step": int(2 * m * stride * 8),
@@ -743,6 +781,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the device-timed step from CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

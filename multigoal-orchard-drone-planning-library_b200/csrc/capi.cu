@@ -773,7 +773,8 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		const char *e = getenv("MGODPL_E2E_CHUNKS");
 		return e && atoi(e) > 0 ? std::min((size_t) atoi(e), Workspace::MAX_CHUNKS) : (size_t) 2;
 	}();
-	const size_t n_chunks = m >= 32768 ? chunk_pref : 1;
+	const bool use_side = m >= 32768;  // large batches run on the workspace's own non-blocking streams, in chunk_pref chunks
+	const size_t n_chunks = use_side ? chunk_pref : 1;
 	const size_t chunk_m = n_chunks == 1 ? m : ((m + n_chunks - 1) / n_chunks + 31) / 32 * 32;
 	const size_t in_b = m * stride * 8, words = (m + 31) / 32, qb = motion_scratch_bytes(chunk_m, robot->dev.n_boxes);
 	size_t o_a = c.take(in_b), o_b = c.take(in_b), o_first = c.take(m * 4), o_slerp = c.take(m * 32);
@@ -784,7 +785,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	size_t o_q = c.take(qb), o_q2 = c.take(n_chunks > 1 ? qb : 0);
 	CU(ws->reserve(c.off, host_hi - out_lo));
 	char *D = ws->dev, *H = ws->host - out_lo;  // host staging mirrors the device layout from out_lo onwards
-	if (n_chunks > 1) {
+	if (use_side) {
 		CU(ws->side_streams());
 		CU(cudaEventRecord(ws->ev_start, stream));
 		for (int s = 0; s < 2; ++s) CU(cudaStreamWaitEvent(ws->side[s], ws->ev_start, 0));
@@ -793,7 +794,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		const size_t lo = ci * chunk_m, hi = std::min(m, lo + chunk_m);
 		if (lo >= hi) break;
 		const size_t mc = hi - lo, w_lo = lo / 32, w_n = (mc + 31) / 32;
-		cudaStream_t s = n_chunks > 1 ? ws->side[ci & 1] : stream;
+		cudaStream_t s = use_side ? ws->side[ci & 1] : stream;
 		if (trace && ci < 2) {
 			for (int k = 0; k < 4; ++k)
 				if (!tev[ci][k]) CU(cudaEventCreate(&tev[ci][k]));
@@ -812,9 +813,9 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		CU(cudaMemcpyAsync(H + o_steps + lo * 4, D + o_steps + lo * 4, mc * 4, cudaMemcpyDeviceToHost, s));
 		if (toi) CU(cudaMemcpyAsync(H + o_toi + lo * 8, D + o_toi + lo * 8, mc * 8, cudaMemcpyDeviceToHost, s));
 		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][3], s));
-		if (n_chunks > 1) CU(cudaEventRecord(ws->ev_chunk[ci], s));
+		if (use_side) CU(cudaEventRecord(ws->ev_chunk[ci], s));
 	}
-	if (n_chunks > 1)
+	if (use_side)
 		for (int s = 0; s < 2; ++s) {
 			CU(cudaEventRecord(ws->ev_done[s], ws->side[s]));
 			CU(cudaStreamWaitEvent(stream, ws->ev_done[s], 0));
@@ -845,7 +846,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		if (toi) memcpy(toi + lo, H + o_toi + lo * 8, (hi - lo) * 8);
 		if (n_steps_out) memcpy(n_steps_out + lo, h_steps + lo, (hi - lo) * 4);
 	};
-	if (n_chunks > 1) {
+	if (use_side) {
 		// a chunk's results are handed over while the chunks behind it are still on the GPU
 		for (size_t ci = 0; ci < n_chunks && ci * chunk_m < m; ++ci) {
 			CU(cudaEventSynchronize(ws->ev_chunk[ci]));
@@ -853,7 +854,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		}
 	}
 	CU(cudaStreamSynchronize(stream));
-	if (n_chunks == 1) deliver(0, m);
+	if (!use_side) deliver(0, m);
 	const auto t_synced = now();
 	if (n_fix) {
 		// Rare path (the boundary set is normally empty for sampled states): re-run with the corrected counts pinned.

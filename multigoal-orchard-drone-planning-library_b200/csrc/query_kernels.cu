@@ -682,7 +682,8 @@ __device__ __noinline__ void expand_motion_step_now(const SceneDev &sc, const Ro
 /// and — instead of visiting every step — the contiguous range of steps whose base position can lie within the
 /// robot's reach of the scene bounds (slab clip of the translation segment, widened by one step either side).
 /// The surviving (motion, step) pairs go to the survivor list, written warp-cooperatively.
-__global__ void __launch_bounds__(BLOCK_A)
+template<int BLOCK, int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
 k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
 				const double *__restrict__ b, size_t m, size_t stride, int js, double max_step,
 				const uint32_t *__restrict__ n_steps_override, uint32_t *__restrict__ n_steps_out,
@@ -1086,7 +1087,7 @@ static int sm_count() {  // of the current device (a process may drive several)
 
 /// Environment knobs, read once (thread-safe: function-local static of a struct initialised by one expression).
 struct Knobs {
-	int pipeline, pipe_refill_min, pipe_leaf_min, pipe_blocks, pipe_claim, cull_bulk, no_prefilter, traverse_blocks, refill_min, leaf_min, trim;
+	int pipeline, pipe_refill_min, pipe_leaf_min, pipe_blocks, pipe_claim, cull_bulk, ranges_variant, no_prefilter, traverse_blocks, refill_min, leaf_min, trim;
 	unsigned head_steps;
 	size_t queue_max_items, survivor_max_entries;
 	static int geti(const char *name, int dflt) {
@@ -1098,7 +1099,7 @@ struct Knobs {
 		return e && atoll(e) > 0 ? (size_t) atoll(e) : dflt;
 	}
 	Knobs()
-		: pipeline(geti("MGODPL_PIPELINE", 0)), pipe_refill_min(geti("MGODPL_PIPE_REFILL_MIN", 8)), pipe_leaf_min(geti("MGODPL_PIPE_LEAF_MIN", 32)), pipe_blocks(geti("MGODPL_PIPE_BLOCKS", 4)), pipe_claim(geti("MGODPL_PIPE_CLAIM", 0)), cull_bulk(geti("MGODPL_CULL_BULK", 0)),
+		: pipeline(geti("MGODPL_PIPELINE", 0)), pipe_refill_min(geti("MGODPL_PIPE_REFILL_MIN", 8)), pipe_leaf_min(geti("MGODPL_PIPE_LEAF_MIN", 32)), pipe_blocks(geti("MGODPL_PIPE_BLOCKS", 4)), pipe_claim(geti("MGODPL_PIPE_CLAIM", 0)), cull_bulk(geti("MGODPL_CULL_BULK", 0)), ranges_variant(geti("MGODPL_RANGES_VARIANT", 0)),
 		  no_prefilter(geti("MGODPL_NO_PREFILTER", 0)), traverse_blocks(geti("MGODPL_TRAVERSE_BLOCKS", 4)), refill_min(geti("MGODPL_REFILL_MIN", 16)),
 		  leaf_min(geti("MGODPL_LEAF_MIN", 8)), trim(geti("MGODPL_TRIM", 16)),
 		  head_steps(geti("MGODPL_HEAD_STEPS", 0) > 0 ? (unsigned) geti("MGODPL_HEAD_STEPS", 0) : 0u),
@@ -1328,8 +1329,12 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	Results res{RESULT_FIRST_STEP, nullptr, d_first_step};
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	if (knobs().pipeline == 1) Q.cap = 0;
-	k_motion_ranges<<<grid_for(m, BLOCK_A, 4), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override,
-																	  d_n_steps, d_uncertain, (SlerpConst *) d_slerp, S, S_tail, head_arg, trim, Q, res);
+	if (knobs().ranges_variant == 1)  // one wave for 100 k motions: 6 blocks x 4 warps per SM at <= 85 registers
+		k_motion_ranges<128, 6><<<grid_for(m, 128, 6), 128, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override, d_n_steps, d_uncertain,
+																		  (SlerpConst *) d_slerp, S, S_tail, head_arg, trim, Q, res);
+	else
+		k_motion_ranges<BLOCK_A, 2><<<grid_for(m, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override, d_n_steps, d_uncertain,
+																					  (SlerpConst *) d_slerp, S, S_tail, head_arg, trim, Q, res);
 	LQ_CHECK(cudaGetLastError());
 	if (knobs().pipeline == 1) {
 		// one launch walks the head list, then the tail list: by the time a warp reaches a motion's tail steps, the head steps of
