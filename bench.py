@@ -224,11 +224,13 @@ def run_ours(args):
         dist.barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     torch.cuda.synchronize()
+    t_host = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(k)  # evict inputs and scene from L2 (outside the timed events)
         ev[k][0].record()
         step(k)
         ev[k][1].record()
+    host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps  # how long the host needs to enqueue one step (it runs ahead of the GPU)
     drain(args.steps - 1)  # the stream now waits for the gathers still in flight ...
     tail = torch.cuda.Event(enable_timing=True)
     tail.record()  # ... and this event closes the timed region after them
@@ -312,7 +314,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "motions_per_gpu": m, "triangles": int(info.n_triangles), "bvh_nodes": int(info.n_nodes),
                    "l2": "flushed before every timed step (256 MiB write)", "parallelism": f"replicated scene x{world}, batch sharded" + (f", result words all-gathered every {G} batches (async)" if world > 1 else "")},
-        "ms_per_step_by_rank": by_rank,
+        "ms_per_step_by_rank": by_rank, "host_enqueue_ms_per_step": host_enqueue_ms, "graph_replay": bool(args.graph),
         "motions_per_sec": motions_all * args.steps / (total_ms * 1e-3),
         "states_checked_per_motion": states_all / motions_all, "collision_rate": float(hit.mean()),
         "e2e": {"value": e2e_value, "unit": "states/s", "h2d_bytes_per_step": int(2 * m * stride * 8),

@@ -693,7 +693,7 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 	LocalCounters lc;
 	unsigned long long n_uncertain = 0, n_motions = 0;
 	const size_t m_pad = (m + 31) & ~(size_t) 31;
-	for (size_t i = (size_t) blockIdx.x * BLOCK_A + threadIdx.x; i < m_pad; i += (size_t) gridDim.x * BLOCK_A) {
+	for (size_t i = (size_t) blockIdx.x * BLOCK + threadIdx.x; i < m_pad; i += (size_t) gridDim.x * BLOCK) {
 		unsigned s_lo = 0, len = 0, n_steps = 0, head = head_steps;
 		bool uncertain = false;
 		if (i < m) {
@@ -1147,8 +1147,7 @@ static void carve(void *scratch, size_t scratch_bytes, size_t survivor_entries, 
 	if (S && S_tail) {  // split the entry region: [head | tail]
 		const size_t grain = (size_t) SHARDS * SHARD_BLOCK;
 		size_t hcap = head_entries < scap / 2 ? head_entries : scap / 2;
-		hcap = (hcap + grain - 1) / grain * grain;
-		if (hcap > scap) hcap = scap;
+		hcap = hcap >= grain ? hcap / grain * grain : std::min(grain, scap);  // (down: a queue sized for the list's worst case then takes it in one pass)
 		S->cap = (unsigned) hcap;
 		S_tail->counts = S->counts + SHARDS * COUNTER_STRIDE;
 		S_tail->entries = S->entries + hcap;
@@ -1278,7 +1277,10 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 		src.list[0] = S, src.n_lists = 1, src.states = d_states, src.stride = stride;
 		return launch_pipeline<SRC_STATES>(sc, rb, src, Q.cursor, res, std::min<size_t>(S.cap, n + SHARDS * SHARD_BLOCK) * (size_t) ((rb.n_boxes + SPL - 1) / SPL > 0 ? (rb.n_boxes + SPL - 1) / SPL : 1), stream);
 	}
-	const size_t R = pass_size(Q, rb.n_boxes);
+	// The list's slot range has holes (sharded appends) but at most n filled slots: a queue that holds n * n_boxes items takes the
+	// whole list in one pass, with no read-back (the call stays asynchronous and can be captured into a CUDA graph).
+	const bool one_pass = (size_t) Q.cap >= n * (size_t) std::max(rb.n_boxes, 1);
+	const size_t R = one_pass ? (size_t) S.cap : pass_size(Q, rb.n_boxes);
 	size_t end = S.cap;
 	if (end > R) LQ_CHECK(survivor_slot_ranges(&S, 1, stream, &end));
 	for (size_t lo = 0; lo < end || lo == 0; lo += R) {
