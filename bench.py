@@ -78,6 +78,12 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.sm, self.max_sm, self.mask, self.stop_flag, self.how = index, [], None, 0, threading.Event(), "nvml"
+        self.ready = threading.Event()  # set after the first sample: the caller starts its warm-up only then
+
+    def mark(self):
+        """Forget what was sampled so far (called right before the warm-up steps)."""
+        self.ready.wait(20.0)
+        self.sm, self.mask = [], 0
 
     def run(self):
         try:
@@ -91,7 +97,8 @@ class ClockSampler(threading.Thread):
             while not self.stop_flag.is_set():
                 self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                 self.mask |= int(reasons(h))
-                self.stop_flag.wait(0.003)
+                self.ready.set()
+                self.stop_flag.wait(0.0005)  # the timed region of a 20-step run lasts a few ms
             return
         except Exception:
             self.how = "nvidia-smi"
@@ -111,6 +118,7 @@ class ClockSampler(threading.Thread):
                             self.mask |= bit
             except Exception:
                 pass
+            self.ready.set()
             self.stop_flag.wait(0.05)
 
     def summary(self):
@@ -136,6 +144,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.current_stream().cuda_stream
 
+    sampler = ClockSampler(local)  # started early: NVML initialisation takes longer than a short timed region
+    sampler.start()
     tree = mg.scenes.make_tree(**TREE)
     mesh = tree.collision_mesh(True)
     scene = mg.Scene.from_mesh(mesh)
@@ -183,39 +193,43 @@ def run_ours(args):
                 pending[i].wait()
                 pending[i] = None
 
+    graph_note = "off (--no-graph)"
     if args.graph:
-        # replay the step's launches from CUDA graphs (one per result buffer): the host's share of a 0.3 ms step disappears
-        step(0)
-        drain(0)
-        torch.cuda.synchronize()
-        graphs = {}
-        cap = torch.cuda.Stream(device=dev)
-        with torch.cuda.stream(cap):  # the library keeps one scratch area per stream: let it allocate before the capture starts
-            mg.capi.check_motions_device(scene, robot, d_a, d_b, m, stride, js, hit_groups[0][0], MAX_STEP, d_toi, d_steps, d_unc, stream=cap.cuda_stream)
-        torch.cuda.synchronize()
-
-        def captured(k):
-            key = ((k // G) & 1, k % G)
-            if key not in graphs:
+        # The device-buffer call never blocks the host or allocates once its scratch exists, so it can be captured: the step's
+        # launches are replayed from CUDA graphs (one per result buffer), which takes the host out of a 0.3 ms step.  The timed
+        # work is the same C-ABI call, recorded once.  Falls back to plain launches if the capture fails.
+        plain_step = step
+        try:
+            step(0)
+            drain(0)
+            torch.cuda.synchronize()
+            graphs = {}
+            cap = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(cap):  # the library keeps one scratch area per stream: let it allocate before the capture starts
+                mg.capi.check_motions_device(scene, robot, d_a, d_b, m, stride, js, hit_groups[0][0], MAX_STEP, d_toi, d_steps, d_unc, stream=cap.cuda_stream)
+            torch.cuda.synchronize()
+            for key in [(g_, s_) for g_ in range(2) for s_ in range(G)]:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=cap):
+                with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
                     mg.capi.check_motions_device(scene, robot, d_a, d_b, m, stride, js, hit_groups[key[0]][key[1]], MAX_STEP, d_toi, d_steps, d_unc,
                                                  stream=torch.cuda.current_stream().cuda_stream)
                 graphs[key] = g
-            return graphs[key]
-        for k in range(2 * G):
-            captured(k)
+            torch.cuda.synchronize()
 
-        def step(k=0):  # noqa: F811
-            group, slot = (k // G) & 1, k % G
-            if world > 1 and slot == 0 and pending[group] is not None:
-                pending[group].wait()
-                pending[group] = None
-            captured(k).replay()
-            if world > 1 and slot == G - 1:
-                pending[group] = dist.all_gather_into_tensor(gathered[group], hit_groups[group], async_op=True)
-    sampler = ClockSampler(local)
-    sampler.start()
+            def step(k=0):  # noqa: F811
+                group, slot = (k // G) & 1, k % G
+                if world > 1 and slot == 0 and pending[group] is not None:
+                    pending[group].wait()
+                    pending[group] = None
+                graphs[(group, slot)].replay()
+                if world > 1 and slot == G - 1:
+                    pending[group] = dist.all_gather_into_tensor(gathered[group], hit_groups[group], async_op=True)
+            graph_note = "the step's C-ABI call captured once per result buffer and replayed (CUDA graph)"
+        except Exception as e:  # keep measuring with plain launches
+            torch.cuda.synchronize()
+            step = plain_step
+            graph_note = f"capture failed, plain launches: {e!r}"[:200]
+    sampler.mark()
     for k in range(args.warmup):
         step(k)
     drain(args.warmup - 1)
@@ -242,7 +256,7 @@ def run_ours(args):
     d_hit = hit_groups[((args.steps - 1) // G) & 1][(args.steps - 1) % G]
     step_ms = [s.elapsed_time(e) for s, e in ev]
     total_ms = torch.tensor([sum(step_ms) + ev[-1][1].elapsed_time(tail)], dtype=torch.float64, device=dev)
-    by_rank = None
+    by_rank, clocks_by_rank = None, None
     if world > 1:
         # per rank: [whole timed region / steps, mean of the per-step events (what the rank's own kernels took)]
         mine = torch.tensor([float(total_ms.item()) / args.steps, float(np.mean(step_ms))], dtype=torch.float64, device=dev)
@@ -250,6 +264,11 @@ def run_ours(args):
         dist.all_gather(all_ms, mine)
         by_rank = [[round(float(x[0].item()), 4), round(float(x[1].item()), 4)] for x in all_ms]
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        cs = sampler.summary()
+        mine = torch.tensor([float(cs.get("sm_mhz") or 0), float(cs.get("sm_mhz_min") or 0)], dtype=torch.float64, device=dev)
+        all_clk = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(all_clk, mine)
+        clocks_by_rank = [[int(x[0].item()), int(x[1].item())] for x in all_clk]
     total_ms = float(total_ms.item())
 
     hit = mg.capi.unpack_bits(d_hit.cpu().numpy().view(np.uint32), m)
@@ -314,7 +333,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "motions_per_gpu": m, "triangles": int(info.n_triangles), "bvh_nodes": int(info.n_nodes),
                    "l2": "flushed before every timed step (256 MiB write)", "parallelism": f"replicated scene x{world}, batch sharded" + (f", result words all-gathered every {G} batches (async)" if world > 1 else "")},
-        "ms_per_step_by_rank": by_rank, "host_enqueue_ms_per_step": host_enqueue_ms, "graph_replay": bool(args.graph),
+        "ms_per_step_by_rank": by_rank, "host_enqueue_ms_per_step": host_enqueue_ms, "launch_mode": graph_note,
         "motions_per_sec": motions_all * args.steps / (total_ms * 1e-3),
         "states_checked_per_motion": states_all / motions_all, "collision_rate": float(hit.mean()),
         "e2e": {"value": e2e_value, "unit": "states/s", "h2d_bytes_per_step": int(2 * m * stride * 8),
@@ -326,7 +345,7 @@ def run_ours(args):
                      "kernel": KERNEL_NOTE,
                      "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_bytes": "152.125 B x motions + 112 B x triangles (SURVEY 8d)",
                      "own_accounting_bytes_per_launch": own_bytes, "own_accounting_frac": own_bytes / (np.mean(step_ms) * 1e-3) / 1e9 / peak},
-        "clocks": sampler.summary(),
+        "clocks": dict(sampler.summary(), by_rank_median_min=clocks_by_rank),
         "scene": {"build_ms": info.build_ms, "sah_cost": info.sah_cost, "max_depth": int(info.max_depth),
                   "device_bytes": int(info.device_bytes)},
     }
@@ -783,7 +802,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay the device-timed step from CUDA graphs")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="plain launches instead of replaying the device-timed step from CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

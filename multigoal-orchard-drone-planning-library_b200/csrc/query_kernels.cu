@@ -1099,7 +1099,7 @@ struct Knobs {
 		return e && atoll(e) > 0 ? (size_t) atoll(e) : dflt;
 	}
 	Knobs()
-		: pipeline(geti("MGODPL_PIPELINE", 0)), pipe_refill_min(geti("MGODPL_PIPE_REFILL_MIN", 8)), pipe_leaf_min(geti("MGODPL_PIPE_LEAF_MIN", 32)), pipe_blocks(geti("MGODPL_PIPE_BLOCKS", 4)), pipe_claim(geti("MGODPL_PIPE_CLAIM", 0)), cull_bulk(geti("MGODPL_CULL_BULK", 0)), ranges_variant(geti("MGODPL_RANGES_VARIANT", 0)),
+		: pipeline(geti("MGODPL_PIPELINE", 0)), pipe_refill_min(geti("MGODPL_PIPE_REFILL_MIN", 8)), pipe_leaf_min(geti("MGODPL_PIPE_LEAF_MIN", 32)), pipe_blocks(geti("MGODPL_PIPE_BLOCKS", 4)), pipe_claim(geti("MGODPL_PIPE_CLAIM", 0)), cull_bulk(geti("MGODPL_CULL_BULK", 0)), ranges_variant(geti("MGODPL_RANGES_VARIANT", 1)),
 		  no_prefilter(geti("MGODPL_NO_PREFILTER", 0)), traverse_blocks(geti("MGODPL_TRAVERSE_BLOCKS", 4)), refill_min(geti("MGODPL_REFILL_MIN", 16)),
 		  leaf_min(geti("MGODPL_LEAF_MIN", 8)), trim(geti("MGODPL_TRIM", 16)),
 		  head_steps(geti("MGODPL_HEAD_STEPS", 0) > 0 ? (unsigned) geti("MGODPL_HEAD_STEPS", 0) : 0u),
