@@ -251,8 +251,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler.stop_flag.set()
-    sampler.join()
+    clocks_timed = sampler.summary()  # warm-up + timed region; the thread keeps sampling through the e2e calls below
     d_hit = hit_groups[((args.steps - 1) // G) & 1][(args.steps - 1) % G]
     step_ms = [s.elapsed_time(e) for s, e in ev]
     total_ms = torch.tensor([sum(step_ms) + ev[-1][1].elapsed_time(tail)], dtype=torch.float64, device=dev)
@@ -264,7 +263,7 @@ def run_ours(args):
         dist.all_gather(all_ms, mine)
         by_rank = [[round(float(x[0].item()), 4), round(float(x[1].item()), 4)] for x in all_ms]
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        cs = sampler.summary()
+        cs = clocks_timed
         mine = torch.tensor([float(cs.get("sm_mhz") or 0), float(cs.get("sm_mhz_min") or 0)], dtype=torch.float64, device=dev)
         all_clk = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(all_clk, mine)
@@ -291,15 +290,22 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     e2e_steps = max(3, min(args.steps, 10))
+    e2e_calls = []
+    sampler.sm, sampler.mask = [], 0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        mg.capi.check_motions(scene, robot, na, nb, MAX_STEP, True, stream=stream, out=res)
+        t1 = time.perf_counter()
+        mg.capi.check_motions(scene, robot, na, nb, MAX_STEP, True, stream=stream, out=res)  # returns with the results in host memory
+        e2e_calls.append((time.perf_counter() - t1) * 1e3)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     assert np.array_equal(mg.capi.unpack_bits(res["words"], m), hit), "host-buffer and device-buffer paths disagree"
     assert np.array_equal(res["n_steps"].astype(np.int64), n_steps) and np.array_equal(res["toi"], toi, equal_nan=True)
+    clocks_e2e = sampler.summary()
+    sampler.stop_flag.set()
+    sampler.join()
     e2e_value = states_all * e2e_steps / float(e2e_s.item())
 
     strong = None
@@ -337,7 +343,8 @@ def run_ours(args):
         "motions_per_sec": motions_all * args.steps / (total_ms * 1e-3),
         "states_checked_per_motion": states_all / motions_all, "collision_rate": float(hit.mean()),
         "e2e": {"value": e2e_value, "unit": "states/s", "h2d_bytes_per_step": int(2 * m * stride * 8),
-                "d2h_bytes_per_step": int(2 * words * 4 + m * 4 + m * 8), "steps": e2e_steps},
+                "d2h_bytes_per_step": int(2 * words * 4 + m * 4 + m * 8), "steps": e2e_steps,
+                "ms_per_call": [round(x, 4) for x in e2e_calls]},
         # our kernels inside the device-timed region, per step: k_motion_ranges, 2 x (k_expand_motion_steps, k_traverse), k_finish_motions
         "gpu_launches": LAUNCHES_PER_STEP * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -345,7 +352,7 @@ def run_ours(args):
                      "kernel": KERNEL_NOTE,
                      "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_bytes": "152.125 B x motions + 112 B x triangles (SURVEY 8d)",
                      "own_accounting_bytes_per_launch": own_bytes, "own_accounting_frac": own_bytes / (np.mean(step_ms) * 1e-3) / 1e9 / peak},
-        "clocks": dict(sampler.summary(), by_rank_median_min=clocks_by_rank),
+        "clocks": dict(clocks_timed, by_rank_median_min=clocks_by_rank, during_e2e=clocks_e2e),
         "scene": {"build_ms": info.build_ms, "sah_cost": info.sah_cost, "max_depth": int(info.max_depth),
                   "device_bytes": int(info.device_bytes)},
     }

@@ -66,21 +66,23 @@ struct DeviceGuard {
 struct Workspace {
 	char *dev = nullptr, *host = nullptr;
 	size_t dev_cap = 0, host_cap = 0;
-	// two side streams for copy/compute overlap inside one host-buffer call (created on first use)
-	cudaStream_t side[2] = {nullptr, nullptr};
-	cudaEvent_t ev_start = nullptr, ev_done[2] = {nullptr, nullptr};
+	// Streams of one host-buffer call (created on first use): every chunk's input copy goes through `copy_in`, back to back, so
+	// the PCIe link is busy from the first microsecond to the last input byte; chunk k's kernels and result copies run on
+	// side[k], which waits for "chunk k has arrived" (ev_in[k]) only.
 	static constexpr size_t MAX_CHUNKS = 8;
+	cudaStream_t copy_in = nullptr, side[MAX_CHUNKS] = {};
+	cudaEvent_t ev_start = nullptr, ev_in[MAX_CHUNKS] = {};
 	cudaEvent_t ev_chunk[MAX_CHUNKS] = {};  // "results of chunk k are in pinned memory"
 
 	cudaError_t side_streams() {
-		if (side[0]) return cudaSuccess;
-		cudaError_t e = cudaSuccess;
-		for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-			e = cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
-			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming);
-		}
+		if (copy_in) return cudaSuccess;
+		cudaError_t e = cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking);
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
-		for (size_t i = 0; i < MAX_CHUNKS && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ev_chunk[i], cudaEventDisableTiming);
+		for (size_t i = 0; i < MAX_CHUNKS && e == cudaSuccess; ++i) {
+			e = cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_chunk[i], cudaEventDisableTiming);
+		}
 		return e;
 	}
 	cudaError_t reserve(size_t dev_bytes, size_t host_bytes) {
@@ -105,13 +107,13 @@ struct Workspace {
 	~Workspace() {
 		if (dev) cudaFree(dev);
 		if (host) cudaFreeHost(host);
-		for (int i = 0; i < 2; ++i) {
-			if (side[i]) cudaStreamDestroy(side[i]);
-			if (ev_done[i]) cudaEventDestroy(ev_done[i]);
-		}
+		if (copy_in) cudaStreamDestroy(copy_in);
 		if (ev_start) cudaEventDestroy(ev_start);
-		for (auto ev: ev_chunk)
-			if (ev) cudaEventDestroy(ev);
+		for (size_t i = 0; i < MAX_CHUNKS; ++i) {
+			if (side[i]) cudaStreamDestroy(side[i]);
+			if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+			if (ev_chunk[i]) cudaEventDestroy(ev_chunk[i]);
+		}
 	}
 };
 
@@ -769,8 +771,11 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	static thread_local cudaEvent_t tev[2][4] = {};
 	Lease ws(scene->pool);
 	Carver c;
-	// Large batches are cut into chunks that alternate between two side streams, so chunk k+1's H2D copy and chunk
-	// k-1's D2H copy overlap chunk k's kernels.  Chunk boundaries are multiples of 32: result words never straddle.
+	// Large batches are cut into chunks.  All input copies go through one copy stream, back to back (the PCIe link carries input
+	// from the first microsecond to the last byte); chunk k's kernels and result copies run on a stream of their own that waits for
+	// "chunk k has arrived" only, so the kernels of the early chunks hide behind the input copies of the later ones.  Two chunks
+	// measure best for 100 k motions (0.74 ms; 1: 0.85, 4: 1.2): a chunk's kernels have a latency floor of ~0.15 ms however small
+	// it is, and concurrent chunks share the SMs.  Chunk boundaries are multiples of 32: result words never straddle.
 	static const size_t chunk_pref = [] {
 		const char *e = getenv("MGODPL_E2E_CHUNKS");
 		return e && atoi(e) > 0 ? std::min((size_t) atoi(e), Workspace::MAX_CHUNKS) : (size_t) 2;
@@ -784,44 +789,62 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	const size_t out_lo = o_hit, out_hi = c.off;
 	size_t o_ovr = c.take(m * 4);
 	const size_t host_hi = c.off;
-	size_t o_q = c.take(qb), o_q2 = c.take(n_chunks > 1 ? qb : 0);
+	size_t o_q[Workspace::MAX_CHUNKS];  // chunks run concurrently: a work queue each
+	for (size_t ci = 0; ci < n_chunks; ++ci) o_q[ci] = c.take(qb);
+	const size_t qb_all = c.off - o_q[0];  // (the rare whole-batch re-run uses the chunks' queues as one)
 	CU(ws->reserve(c.off, host_hi - out_lo));
 	char *D = ws->dev, *H = ws->host - out_lo;  // host staging mirrors the device layout from out_lo onwards
 	if (use_side) {
 		CU(ws->side_streams());
 		CU(cudaEventRecord(ws->ev_start, stream));
-		for (int s = 0; s < 2; ++s) CU(cudaStreamWaitEvent(ws->side[s], ws->ev_start, 0));
+		CU(cudaStreamWaitEvent(ws->copy_in, ws->ev_start, 0));
+		for (size_t ci = 0; ci < n_chunks; ++ci) {
+			const size_t lo = ci * chunk_m, hi = std::min(m, lo + chunk_m);
+			if (lo >= hi) break;
+			if (trace && ci < 2) {
+				for (int k = 0; k < 4; ++k)
+					if (!tev[ci][k]) CU(cudaEventCreate(&tev[ci][k]));
+				CU(cudaEventRecord(tev[ci][0], ws->copy_in));
+			}
+			CU(cudaMemcpyAsync(D + o_a + lo * stride * 8, a + lo * stride, (hi - lo) * stride * 8, cudaMemcpyHostToDevice, ws->copy_in));
+			CU(cudaMemcpyAsync(D + o_b + lo * stride * 8, b + lo * stride, (hi - lo) * stride * 8, cudaMemcpyHostToDevice, ws->copy_in));
+			CU(cudaEventRecord(ws->ev_in[ci], ws->copy_in));
+			if (trace && ci < 2) CU(cudaEventRecord(tev[ci][1], ws->copy_in));
+		}
 	}
 	for (size_t ci = 0; ci < n_chunks; ++ci) {
 		const size_t lo = ci * chunk_m, hi = std::min(m, lo + chunk_m);
 		if (lo >= hi) break;
 		const size_t mc = hi - lo, w_lo = lo / 32, w_n = (mc + 31) / 32;
-		cudaStream_t s = use_side ? ws->side[ci & 1] : stream;
-		if (trace && ci < 2) {
-			for (int k = 0; k < 4; ++k)
-				if (!tev[ci][k]) CU(cudaEventCreate(&tev[ci][k]));
-			CU(cudaEventRecord(tev[ci][0], s));
+		cudaStream_t s = use_side ? ws->side[ci] : stream;
+		if (use_side) {
+			CU(cudaStreamWaitEvent(s, ws->ev_in[ci], 0));
+		} else {
+			if (trace) {
+				for (int k = 0; k < 4; ++k)
+					if (!tev[ci][k]) CU(cudaEventCreate(&tev[ci][k]));
+				CU(cudaEventRecord(tev[ci][0], s));
+			}
+			CU(cudaMemcpyAsync(D + o_a, a, in_b, cudaMemcpyHostToDevice, s));
+			CU(cudaMemcpyAsync(D + o_b, b, in_b, cudaMemcpyHostToDevice, s));
+			if (trace) CU(cudaEventRecord(tev[ci][1], s));
 		}
-		CU(cudaMemcpyAsync(D + o_a + lo * stride * 8, a + lo * stride, mc * stride * 8, cudaMemcpyHostToDevice, s));
-		CU(cudaMemcpyAsync(D + o_b + lo * stride * 8, b + lo * stride, mc * stride * 8, cudaMemcpyHostToDevice, s));
-		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][1], s));
+		if (trace && use_side && ci < 2) CU(cudaEventRecord(tev[ci][1], s));  // (kernels start here: after the chunk has arrived)
 		CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a) + lo * stride, (const double *) (D + o_b) + lo * stride, mc,
 								stride, js, max_step, nullptr, (uint32_t *) (D + o_hit) + w_lo, toi ? (double *) (D + o_toi) + lo : nullptr,
 								(uint32_t *) (D + o_steps) + lo, (uint32_t *) (D + o_unc) + w_lo, (unsigned *) (D + o_first) + lo,
-								D + o_slerp + lo * 32, D + ((ci & 1) ? o_q2 : o_q), qb, motion_survivors(mc), s));
+								D + o_slerp + lo * 32, D + o_q[ci], qb, motion_survivors(mc), s));
 		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][2], s));
 		CU(cudaMemcpyAsync(H + o_hit + w_lo * 4, D + o_hit + w_lo * 4, w_n * 4, cudaMemcpyDeviceToHost, s));
 		CU(cudaMemcpyAsync(H + o_unc + w_lo * 4, D + o_unc + w_lo * 4, w_n * 4, cudaMemcpyDeviceToHost, s));
 		CU(cudaMemcpyAsync(H + o_steps + lo * 4, D + o_steps + lo * 4, mc * 4, cudaMemcpyDeviceToHost, s));
 		if (toi) CU(cudaMemcpyAsync(H + o_toi + lo * 8, D + o_toi + lo * 8, mc * 8, cudaMemcpyDeviceToHost, s));
 		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][3], s));
-		if (use_side) CU(cudaEventRecord(ws->ev_chunk[ci], s));
-	}
-	if (use_side)
-		for (int s = 0; s < 2; ++s) {
-			CU(cudaEventRecord(ws->ev_done[s], ws->side[s]));
-			CU(cudaStreamWaitEvent(stream, ws->ev_done[s], 0));
+		if (use_side) {
+			CU(cudaEventRecord(ws->ev_chunk[ci], s));
+			CU(cudaStreamWaitEvent(stream, ws->ev_chunk[ci], 0));  // the caller's stream continues after every chunk
 		}
+	}
 	const auto t_enqueued = now();
 	// Step-count fix-up: the device libm may differ from the host's by an ulp, which only matters when distance /
 	// max_step sits on an integer boundary.  Re-derive those on the host and re-run if any count disagrees.
@@ -864,7 +887,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a), (const double *) (D + o_b), m, stride, js,
 								max_step, (const uint32_t *) (D + o_ovr), (uint32_t *) (D + o_hit),
 								toi ? (double *) (D + o_toi) : nullptr, (uint32_t *) (D + o_steps), nullptr,
-								(unsigned *) (D + o_first), D + o_slerp, D + o_q, qb, motion_survivors(m), stream));
+								(unsigned *) (D + o_first), D + o_slerp, D + o_q[0], qb_all, motion_survivors(m), stream));
 		CU(cudaMemcpyAsync(H + out_lo, D + out_lo, out_hi - out_lo, cudaMemcpyDeviceToHost, stream));
 		CU(cudaStreamSynchronize(stream));
 		memcpy(hit_bits, H + o_hit, words * 4);

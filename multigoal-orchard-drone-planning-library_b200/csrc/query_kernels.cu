@@ -786,15 +786,19 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 					if (!(g > 0.f) || !(inv_step > 0.f)) return 1u;
 					return (unsigned) fminf(fmaxf(floorf(g * inv_step), 1.f), (float) max(room, 1u));
 				};
-				for (int guard = 0; guard < trim && s_lo < s_hi; ++guard) {
-					const float g = gap(s_lo);
-					if (g <= 0.f) break;
-					s_lo += steps_cleared(g, s_hi - s_lo);
-				}
-				for (int guard = 0; guard < trim && s_hi > s_lo; ++guard) {
-					const float g = gap(s_hi);
-					if (g <= 0.f) break;
-					s_hi -= steps_cleared(g, s_hi - s_lo);
+				// both ends walk inwards in the same loop: their look-ups are independent, so the two dependent chains of (cold)
+				// grid loads overlap instead of running one after the other
+				bool lo_open = true, hi_open = true;
+				for (int guard = 0; guard < trim && (lo_open || hi_open) && s_lo < s_hi; ++guard) {
+					const float g_lo = lo_open ? gap(s_lo) : 0.f, g_hi = hi_open ? gap(s_hi) : 0.f;
+					if (lo_open) {
+						if (g_lo <= 0.f) lo_open = false;
+						else s_lo += steps_cleared(g_lo, s_hi - s_lo);
+					}
+					if (hi_open && s_hi > s_lo) {
+						if (g_hi <= 0.f) hi_open = false;
+						else s_hi -= steps_cleared(g_hi, s_hi - s_lo);
+					}
 				}
 				len = (s_lo == s_hi && !(gap(s_lo) <= 0.f)) ? 0u : s_hi - s_lo + 1;
 				// head_steps == 0: adaptive head — the steps it takes to cross the reach shell around the scene bounds plus
