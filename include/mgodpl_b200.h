@@ -54,14 +54,20 @@ enum mgodpl_status {
 #define MGODPL_MAX_BOXES 12
 #define MGODPL_MAX_JOINT_VALUES 16
 
-enum mgodpl_shape_type { MGODPL_SHAPE_BOX = 0, MGODPL_SHAPE_MESH = 1 };    /* shapes.h:24-29 */
+/* BOX and MESH are the reference's Shape variant (shapes.h:24-29); it collides boxes only and so does a MESH link here (rejected
+ * with the reference's message).  CAPSULE and CONVEX_MESH are additions of this library (BASELINE north_star (3)): they walk the
+ * tree as their bounding box and get their own exact test at the triangle leaves. */
+enum mgodpl_shape_type { MGODPL_SHAPE_BOX = 0, MGODPL_SHAPE_MESH = 1, MGODPL_SHAPE_CAPSULE = 2, MGODPL_SHAPE_CONVEX_MESH = 3 };
+#define MGODPL_MAX_CONVEX_VERTICES 16
 enum mgodpl_joint_type { MGODPL_JOINT_REVOLUTE = 0, MGODPL_JOINT_FIXED = 1 }; /* RobotModel.h:48-62 variant order */
 
 /* PositionedShape (positioned_shape.h:12-30) attached to a link; only boxes can be collided (collision_detection.cpp:21-22). */
 typedef struct mgodpl_shape_desc {
 	int32_t link;
 	int32_t shape_type;  /* mgodpl_shape_type */
-	double size[3];      /* Box::size, full extents, centred (shapes.h:20-22) */
+	double size[3];      /* BOX: Box::size, full extents, centred (shapes.h:20-22).  CAPSULE: size[0] = radius, size[2] = length of
+	                      * the cylindrical part along the shape's z axis, centred (fcl::Capsule's convention); size[1] unused.
+	                      * CONVEX_MESH: unused (the vertices go to mgodpl_robot_create_ex). */
 	double transform[7]; /* relative to the link frame */
 } mgodpl_shape_desc;
 
@@ -135,6 +141,12 @@ int mgodpl_scene_get_counters(mgodpl_scene *scene, mgodpl_counters *out, int res
 int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_t n_shapes,
 						const mgodpl_joint_desc *joints, int32_t n_joints, int32_t root_link, int32_t end_effector_link,
 						mgodpl_robot **out);
+/* The same with convex-polytope links: shape i of type MGODPL_SHAPE_CONVEX_MESH is the convex hull of the vertices
+ * mesh_vertices[3 * mesh_vertex_offsets[i] .. 3 * mesh_vertex_offsets[i + 1]) (shape frame; 4 .. MGODPL_MAX_CONVEX_VERTICES points
+ * with non-zero volume); mesh_vertex_offsets has n_shapes + 1 entries.  Both arrays may be NULL when no shape needs them. */
+int mgodpl_robot_create_ex(int32_t n_links, const mgodpl_shape_desc *shapes, int32_t n_shapes,
+						   const mgodpl_joint_desc *joints, int32_t n_joints, int32_t root_link, int32_t end_effector_link,
+						   const double *mesh_vertices, const int32_t *mesh_vertex_offsets, mgodpl_robot **out);
 int mgodpl_robot_destroy(mgodpl_robot *robot);
 int mgodpl_robot_n_variables(const mgodpl_robot *robot); /* RobotModel::count_joint_variables, RobotModel.cpp:130-134 */
 

@@ -17,14 +17,14 @@ LIB_PATH = os.path.join(PKG_DIR, "libmgodpl_b200.so")
 MAX_LINKS, MAX_BOXES, MAX_JOINT_VALUES = 12, 12, 16
 SCENE_COUNTERS, SCENE_NO_REFINE, SCENE_NO_CLEARANCE_GRID = 1, 2, 4
 JOINT_REVOLUTE, JOINT_FIXED = 0, 1
-SHAPE_BOX, SHAPE_MESH = 0, 1
+SHAPE_BOX, SHAPE_MESH, SHAPE_CAPSULE, SHAPE_CONVEX_MESH = 0, 1, 2, 3
 
 STATUS = {0: "OK", 1: "INVALID_ARGUMENT", 2: "UNSUPPORTED_SHAPE", 3: "LINK_NOT_FOUND", 4: "UNKNOWN_JOINT_TYPE",
           5: "CUDA", 6: "NO_DEVICE", 7: "OUT_OF_MEMORY", 8: "UNSUPPORTED_ROBOT"}
 
 EXPORTS = [
     "mgodpl_last_error", "mgodpl_device_count", "mgodpl_set_device", "mgodpl_scene_device", "mgodpl_scene_create", "mgodpl_scene_create_u64",
-    "mgodpl_scene_destroy", "mgodpl_scene_get_info", "mgodpl_scene_get_counters", "mgodpl_robot_create",
+    "mgodpl_scene_destroy", "mgodpl_scene_get_info", "mgodpl_scene_get_counters", "mgodpl_robot_create", "mgodpl_robot_create_ex",
     "mgodpl_robot_destroy", "mgodpl_robot_n_variables", "mgodpl_forward_kinematics", "mgodpl_check_boxes",
     "mgodpl_check_states", "mgodpl_check_states_device", "mgodpl_check_motions", "mgodpl_check_motions_device",
     "mgodpl_check_path", "mgodpl_sample_goals", "mgodpl_sample_goals_device", "mgodpl_knn", "mgodpl_knn_device", "mgodpl_knn_query",
@@ -174,14 +174,19 @@ class Robot:
     """Flattened ``RobotModel``: links by index, box shapes, joints in insertion order."""
 
     def __init__(self, n_links: int, shapes, joints, root_link: int, end_effector_link: int = -1):
-        """shapes: iterable of (link, size3, tf7[, shape_type]); joints: iterable of
+        """shapes: iterable of (link, size3, tf7[, shape_type[, vertices]]) — size3 is the box size, or (radius, -, length) of
+        a SHAPE_CAPSULE; a SHAPE_CONVEX_MESH carries its vertices (k x 3) as the fifth element; joints: iterable of
         (link_a, link_b, attach_a7, attach_b7, joint_type, axis3, min, max)."""
         shapes, joints = list(shapes), list(joints)
         sd = (ShapeDesc * max(len(shapes), 1))()
+        mesh_verts, mesh_off = [], [0]
         for i, s in enumerate(shapes):
             sd[i].link, sd[i].shape_type = int(s[0]), int(s[3]) if len(s) > 3 else SHAPE_BOX
             sd[i].size[:] = [float(x) for x in s[1]]
             sd[i].transform[:] = [float(x) for x in s[2]]
+            if len(s) > 4 and s[4] is not None:
+                mesh_verts.append(_f64(s[4]).reshape(-1, 3))
+            mesh_off.append(mesh_off[-1] + (len(mesh_verts[-1]) if len(s) > 4 and s[4] is not None else 0))
         jd = (JointDesc * max(len(joints), 1))()
         for i, j in enumerate(joints):
             jd[i].link_a, jd[i].link_b, jd[i].joint_type = int(j[0]), int(j[1]), int(j[4])
@@ -190,8 +195,14 @@ class Robot:
             jd[i].axis[:] = [float(x) for x in j[5]]
             jd[i].min_angle, jd[i].max_angle = float(j[6]), float(j[7])
         self.h = C.c_void_p()
-        _check(lib().mgodpl_robot_create(n_links, sd, len(shapes), jd, len(joints), root_link, end_effector_link,
-                                         C.byref(self.h)))
+        if mesh_verts:
+            mv = np.ascontiguousarray(np.concatenate(mesh_verts))
+            mo = (C.c_int32 * len(mesh_off))(*mesh_off)
+            _check(lib().mgodpl_robot_create_ex(n_links, sd, len(shapes), jd, len(joints), root_link, end_effector_link,
+                                                _p(mv), mo, C.byref(self.h)))
+        else:
+            _check(lib().mgodpl_robot_create(n_links, sd, len(shapes), jd, len(joints), root_link, end_effector_link,
+                                             C.byref(self.h)))
         self.n_links, self.n_joints = n_links, len(joints)
         self.n_variables = lib().mgodpl_robot_n_variables(self.h)
         self.root_link, self.end_effector_link = root_link, end_effector_link

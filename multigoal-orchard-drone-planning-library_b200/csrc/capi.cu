@@ -1,6 +1,7 @@
 // C ABI of the collision-query path (include/mgodpl_b200.h): handle management, robot flattening, host-buffer
 // staging, and the host-side fix-up that keeps motion step counts bit-identical to the reference's libm.
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -214,7 +215,51 @@ struct mgodpl_scene {
 struct mgodpl_robot {
 	RobotDev dev{};
 	int n_joints = 0;
+	// Convex links only: the hulls (vertices, face planes, edge directions; convex_triangle_hit's layout) and their device copies,
+	// uploaded on first use per device.  Robots made of boxes and capsules hold no device memory at all.
+	std::vector<double> shape_data;
+	mutable std::mutex mu;
+	mutable std::map<int, double *> shape_data_on;
+	~mgodpl_robot() {
+		int cur = 0;
+		cudaGetDevice(&cur);
+		for (auto &kv: shape_data_on) {
+			cudaSetDevice(kv.first);
+			cudaFree(kv.second);
+		}
+		if (!shape_data_on.empty()) cudaSetDevice(cur);
+	}
 };
+
+namespace {
+/// The robot as the kernels of `device` (the current device) take it: robot->dev itself, or — for robots with convex links — a
+/// copy that points at this device's upload of the hull data.
+cudaError_t robot_for_device(const mgodpl_robot *robot, int device, RobotDev &patched, const RobotDev **out) {
+	*out = &robot->dev;
+	if (robot->shape_data.empty()) return cudaSuccess;
+	std::lock_guard<std::mutex> g(robot->mu);
+	double *&p = robot->shape_data_on[device];
+	if (!p) {
+		cudaError_t e = cudaMalloc((void **) &p, robot->shape_data.size() * sizeof(double));
+		if (e == cudaSuccess) e = cudaMemcpy(p, robot->shape_data.data(), robot->shape_data.size() * sizeof(double), cudaMemcpyHostToDevice);
+		if (e != cudaSuccess) {
+			cudaFree(p);
+			p = nullptr;
+			return e;
+		}
+	}
+	patched = robot->dev;
+	patched.shape_data = p;
+	*out = &patched;
+	return cudaSuccess;
+}
+}  // namespace
+/// `const RobotDev &RB` for the query entry points (after DeviceGuard has switched to the scene's device).
+#define ROBOT_ON_SCENE_DEVICE(RB)      \
+	RobotDev patched_robot_;           \
+	const RobotDev *robot_ptr_ = nullptr; \
+	CU(robot_for_device(robot, scene->device, patched_robot_, &robot_ptr_)); \
+	const RobotDev &RB = *robot_ptr_
 
 // =================================================================================================================
 extern "C" {
@@ -404,10 +449,92 @@ HTf inverse(const HTf &a) {
 }
 bool rot_is_identity(const double *q) { return q[0] == 0.0 && q[1] == 0.0 && q[2] == 0.0 && q[3] == 1.0; }
 double vnorm(const double *t) { return std::sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]); }
+
+/// Rotate v by the unit quaternion q (x, y, z, w).
+void hq_rot(const double *q, const double *v, double *o) {
+	const double tx = 2 * (q[1] * v[2] - q[2] * v[1]), ty = 2 * (q[2] * v[0] - q[0] * v[2]), tz = 2 * (q[0] * v[1] - q[1] * v[0]);
+	o[0] = v[0] + q[3] * tx + (q[1] * tz - q[2] * ty);
+	o[1] = v[1] + q[3] * ty + (q[2] * tx - q[0] * tz);
+	o[2] = v[2] + q[3] * tz + (q[0] * ty - q[1] * tx);
+}
+
+/// Hull of a small point set by exhaustive search (n <= MGODPL_MAX_CONVEX_VERTICES): every vertex triple whose plane has all
+/// points on one side is a face; every vertex pair that lies on two different faces is an edge.  Appends convex_triangle_hit's
+/// record to `out` (vertices relative to `centre`, the middle of their bounding box) and returns false for point sets without
+/// volume (a flat or collinear "hull" has no face normals to separate with).
+bool build_hull(const double *v, int n, const double *centre, std::vector<double> &out) {
+	std::vector<std::array<double, 3>> p(n);
+	double scale = 0.0;
+	for (int i = 0; i < n; ++i)
+		for (int a = 0; a < 3; ++a) p[i][a] = v[3 * i + a] - centre[a], scale = std::max(scale, std::fabs(p[i][a]));
+	if (!(scale > 0.0)) return false;
+	const double eps = 1e-10 * scale;
+	struct Face {
+		double n[3], d;
+		std::vector<int> on;
+	};
+	std::vector<Face> faces;
+	for (int i = 0; i < n; ++i)
+		for (int j = i + 1; j < n; ++j)
+			for (int k = j + 1; k < n; ++k) {
+				const double e0[3] = {p[j][0] - p[i][0], p[j][1] - p[i][1], p[j][2] - p[i][2]}, e1[3] = {p[k][0] - p[i][0], p[k][1] - p[i][1], p[k][2] - p[i][2]};
+				double nn[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+				const double len = vnorm(nn);
+				if (!(len > 1e-12 * scale * scale)) continue;
+				for (double &x: nn) x /= len;
+				double lo = 0.0, hi = 0.0;
+				for (int q = 0; q < n; ++q) {
+					const double s = nn[0] * (p[q][0] - p[i][0]) + nn[1] * (p[q][1] - p[i][1]) + nn[2] * (p[q][2] - p[i][2]);
+					lo = std::min(lo, s), hi = std::max(hi, s);
+				}
+				const bool above = hi > eps, below = lo < -eps;
+				if (above && below) continue;      // points on both sides: not a supporting plane
+				if (!above && !below) return false;  // every point lies in this plane: no volume
+				if (above)
+					for (double &x: nn) x = -x;  // everything lies on the positive side: the outward normal points the other way
+				bool dup = false;
+				for (auto &f: faces) dup |= f.n[0] * nn[0] + f.n[1] * nn[1] + f.n[2] * nn[2] > 1.0 - 1e-12;
+				if (dup) continue;
+				Face f;
+				memcpy(f.n, nn, sizeof(nn));
+				f.d = -1e300;
+				for (int q = 0; q < n; ++q) f.d = std::max(f.d, nn[0] * p[q][0] + nn[1] * p[q][1] + nn[2] * p[q][2]);
+				for (int q = 0; q < n; ++q)
+					if (nn[0] * p[q][0] + nn[1] * p[q][1] + nn[2] * p[q][2] > f.d - eps) f.on.push_back(q);
+				faces.push_back(f);
+			}
+	if (faces.size() < 4) return false;
+	std::vector<std::array<double, 3>> edges;
+	for (int i = 0; i < n; ++i)
+		for (int j = i + 1; j < n; ++j) {
+			int shared = 0;
+			for (auto &f: faces)
+				shared += std::find(f.on.begin(), f.on.end(), i) != f.on.end() && std::find(f.on.begin(), f.on.end(), j) != f.on.end();
+			if (shared < 2) continue;
+			double d[3] = {p[j][0] - p[i][0], p[j][1] - p[i][1], p[j][2] - p[i][2]};
+			const double len = vnorm(d);
+			if (!(len > eps)) continue;
+			for (double &x: d) x /= len;
+			bool dup = false;
+			for (auto &e: edges) dup |= std::fabs(e[0] * d[0] + e[1] * d[1] + e[2] * d[2]) > 1.0 - 1e-12;
+			if (!dup) edges.push_back({d[0], d[1], d[2]});
+		}
+	out.push_back((double) n), out.push_back((double) faces.size()), out.push_back((double) edges.size()), out.push_back(0.0);
+	for (auto &q: p) out.insert(out.end(), q.begin(), q.end());
+	for (auto &f: faces) out.insert(out.end(), {f.n[0], f.n[1], f.n[2], f.d});
+	for (auto &e: edges) out.insert(out.end(), e.begin(), e.end());
+	return true;
+}
 }  // namespace
 
 int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_t n_shapes, const mgodpl_joint_desc *joints,
 						int32_t n_joints, int32_t root_link, int32_t ee_link, mgodpl_robot **out) {
+	return mgodpl_robot_create_ex(n_links, shapes, n_shapes, joints, n_joints, root_link, ee_link, nullptr, nullptr, out);
+}
+
+int mgodpl_robot_create_ex(int32_t n_links, const mgodpl_shape_desc *shapes, int32_t n_shapes, const mgodpl_joint_desc *joints,
+						   int32_t n_joints, int32_t root_link, int32_t ee_link, const double *mesh_vertices,
+						   const int32_t *mesh_vertex_offsets, mgodpl_robot **out) {
 	if (!out) return fail(MGODPL_E_INVALID_ARGUMENT, "out is null");
 	*out = nullptr;
 	if (n_links <= 0 || n_shapes < 0 || n_joints < 0 || (n_shapes && !shapes) || (n_joints && !joints))
@@ -417,8 +544,19 @@ int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_
 	if (n_links > MGODPL_MAX_LINKS) return fail(MGODPL_E_UNSUPPORTED_ROBOT, "too many links");
 	if (n_shapes > MGODPL_MAX_BOXES) return fail(MGODPL_E_UNSUPPORTED_ROBOT, "too many collision shapes");
 	for (int i = 0; i < n_shapes; ++i) {
-		if (shapes[i].shape_type != MGODPL_SHAPE_BOX)
+		const int st = shapes[i].shape_type;
+		// the reference's own variant is Box | Mesh and it collides boxes only (collision_detection.cpp:21-22,49-51): a general
+		// Mesh link keeps failing the way it does there; capsules and convex polytopes are this library's additions
+		if (st != MGODPL_SHAPE_BOX && st != MGODPL_SHAPE_CAPSULE && st != MGODPL_SHAPE_CONVEX_MESH)
 			return fail(MGODPL_E_UNSUPPORTED_SHAPE, "Only boxes are implemented for collision geometry.");
+		if (st == MGODPL_SHAPE_CAPSULE && !(shapes[i].size[0] > 0.0 && shapes[i].size[2] >= 0.0))
+			return fail(MGODPL_E_INVALID_ARGUMENT, "capsule needs size[0] = radius > 0 and size[2] = length >= 0");
+		if (st == MGODPL_SHAPE_CONVEX_MESH) {
+			if (!mesh_vertices || !mesh_vertex_offsets) return fail(MGODPL_E_INVALID_ARGUMENT, "convex mesh shapes need mgodpl_robot_create_ex with their vertices");
+			const int nv = mesh_vertex_offsets[i + 1] - mesh_vertex_offsets[i];
+			if (mesh_vertex_offsets[i] < 0 || nv < 4 || nv > MGODPL_MAX_CONVEX_VERTICES)
+				return fail(MGODPL_E_UNSUPPORTED_SHAPE, "a convex mesh link needs 4 .. MGODPL_MAX_CONVEX_VERTICES vertices");
+		}
 		if (shapes[i].link < 0 || shapes[i].link >= n_links) return fail(MGODPL_E_LINK_NOT_FOUND, "Link not found: shape link index");
 	}
 	for (int i = 0; i < n_joints; ++i) {
@@ -502,8 +640,31 @@ int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_
 		const mgodpl_shape_desc &sh = shapes[order[i]];
 		BoxDev &b = d.boxes[i];
 		b.link = box_link[order[i]];
-		for (int a = 0; a < 3; ++a) b.half[a] = 0.5 * sh.size[a];
 		HTf tf = load_tf(sh.transform);
+		b.kind = SHAPE_KIND_BOX, b.data_off = 0;
+		if (sh.shape_type == MGODPL_SHAPE_CAPSULE) {
+			// fcl::Capsule's convention: the cylinder part of length size[2] runs along the shape's z axis, centred
+			b.kind = SHAPE_KIND_CAPSULE;
+			b.half[0] = b.half[1] = sh.size[0], b.half[2] = 0.5 * sh.size[2] + sh.size[0];
+		} else if (sh.shape_type == MGODPL_SHAPE_CONVEX_MESH) {
+			// travels as the bounding box of its vertices in the shape frame; the shape frame moves to that box's centre
+			const double *v = mesh_vertices + 3 * (size_t) mesh_vertex_offsets[order[i]];
+			const int nv = mesh_vertex_offsets[order[i] + 1] - mesh_vertex_offsets[order[i]];
+			double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+			for (int k = 0; k < nv; ++k)
+				for (int a = 0; a < 3; ++a) {
+					if (!std::isfinite(v[3 * k + a])) return fail(MGODPL_E_INVALID_ARGUMENT, "non-finite convex mesh vertex");
+					lo[a] = std::min(lo[a], v[3 * k + a]), hi[a] = std::max(hi[a], v[3 * k + a]);
+				}
+			double centre[3], shift[3];
+			for (int a = 0; a < 3; ++a) centre[a] = 0.5 * (lo[a] + hi[a]), b.half[a] = 0.5 * (hi[a] - lo[a]);
+			b.kind = SHAPE_KIND_CONVEX, b.data_off = (int32_t) rb->shape_data.size();
+			if (!build_hull(v, nv, centre, rb->shape_data)) return fail(MGODPL_E_UNSUPPORTED_SHAPE, "convex mesh link has no volume (flat or collinear vertices)");
+			hq_rot(tf.q, centre, shift);
+			for (int a = 0; a < 3; ++a) tf.t[a] += shift[a];
+		} else {
+			for (int a = 0; a < 3; ++a) b.half[a] = 0.5 * sh.size[a];
+		}
 		memcpy(b.t, tf.t, sizeof(tf.t)), memcpy(b.q, tf.q, sizeof(tf.q));
 		b.tf_identity = rot_is_identity(tf.q) && tf.t[0] == 0.0 && tf.t[1] == 0.0 && tf.t[2] == 0.0;
 		{
@@ -532,6 +693,8 @@ int mgodpl_robot_create(int32_t n_links, const mgodpl_shape_desc *shapes, int32_
 		reach = std::max(reach, depth_reach[b.link] + vnorm(tf.t) + vnorm(b.half));
 	}
 	d.reach = reach * (1.0 + 1e-9) + 1e-9;
+	d.all_boxes = 1, d.shape_data = nullptr;
+	for (int i = 0; i < n_shapes; ++i) d.all_boxes &= d.boxes[i].kind == SHAPE_KIND_BOX;
 	for (int k = d.n_ops - 1; k >= 0; --k) {
 		if (needed[d.ops[k].child]) {
 			d.ops[k].flags |= FK_FOR_COLLISION;
@@ -672,7 +835,8 @@ int mgodpl_check_states_device(mgodpl_scene *scene, const mgodpl_robot *robot, c
 	auto &slot = scene->stream_slot(stream);
 	std::lock_guard<std::mutex> enqueue(slot.mu);
 	CU(slot.ws.reserve(qb, 0));
-	CU(launch_check_states(scene->dev, robot->dev, d_states, n, stride, d_hit_bits, slot.ws.dev, qb, stream));
+	ROBOT_ON_SCENE_DEVICE(rdev);
+	CU(launch_check_states(scene->dev, rdev, d_states, n, stride, d_hit_bits, slot.ws.dev, qb, stream));
 	return MGODPL_OK;
 }
 
@@ -693,7 +857,8 @@ int mgodpl_check_states(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	CU(ws->reserve(c.off, words * 4));
 	// Caller memory goes straight to the device; only the (small) result is staged through pinned memory.
 	CU(cudaMemcpyAsync(ws->dev + o_in, states, in_b, cudaMemcpyHostToDevice, stream));
-	CU(launch_check_states(scene->dev, robot->dev, (const double *) (ws->dev + o_in), n, stride, (uint32_t *) (ws->dev + o_out),
+	ROBOT_ON_SCENE_DEVICE(rdev);
+	CU(launch_check_states(scene->dev, rdev, (const double *) (ws->dev + o_in), n, stride, (uint32_t *) (ws->dev + o_out),
 						   ws->dev + o_q, qb, stream));
 	CU(cudaMemcpyAsync(ws->host, ws->dev + o_out, words * 4, cudaMemcpyDeviceToHost, stream));
 	CU(cudaStreamSynchronize(stream));
@@ -732,7 +897,8 @@ int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, 
 	std::lock_guard<std::mutex> enqueue(slot.mu);
 	CU(slot.ws.reserve(c.off, 0));
 	char *scratch = slot.ws.dev;
-	CU(launch_check_motions(scene->dev, robot->dev, d_a, d_b, m, stride, js, max_step, d_override, d_hit_bits, d_toi,
+	ROBOT_ON_SCENE_DEVICE(rdev);
+	CU(launch_check_motions(scene->dev, rdev, d_a, d_b, m, stride, js, max_step, d_override, d_hit_bits, d_toi,
 							d_n_steps ? d_n_steps : (uint32_t *) (scratch + o_steps), d_uncertain, (unsigned *) (scratch + o_first),
 							scratch + o_slerp, scratch + o_q, qb, motion_survivors(m), stream));
 	return MGODPL_OK;
@@ -769,6 +935,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	auto now = [] { return std::chrono::steady_clock::now(); };
 	const auto t_begin = now();
 	static thread_local cudaEvent_t tev[2][4] = {};
+	ROBOT_ON_SCENE_DEVICE(rdev);
 	Lease ws(scene->pool);
 	Carver c;
 	// Large batches are cut into chunks.  All input copies go through one copy stream, back to back (the PCIe link carries input
@@ -830,7 +997,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 			if (trace) CU(cudaEventRecord(tev[ci][1], s));
 		}
 		if (trace && use_side && ci < 2) CU(cudaEventRecord(tev[ci][1], s));  // (kernels start here: after the chunk has arrived)
-		CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a) + lo * stride, (const double *) (D + o_b) + lo * stride, mc,
+		CU(launch_check_motions(scene->dev, rdev, (const double *) (D + o_a) + lo * stride, (const double *) (D + o_b) + lo * stride, mc,
 								stride, js, max_step, nullptr, (uint32_t *) (D + o_hit) + w_lo, toi ? (double *) (D + o_toi) + lo : nullptr,
 								(uint32_t *) (D + o_steps) + lo, (uint32_t *) (D + o_unc) + w_lo, (unsigned *) (D + o_first) + lo,
 								D + o_slerp + lo * 32, D + o_q[ci], qb, motion_survivors(mc), s));
@@ -884,7 +1051,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	if (n_fix) {
 		// Rare path (the boundary set is normally empty for sampled states): re-run with the corrected counts pinned.
 		CU(cudaMemcpyAsync(D + o_ovr, h_ovr, m * 4, cudaMemcpyHostToDevice, stream));
-		CU(launch_check_motions(scene->dev, robot->dev, (const double *) (D + o_a), (const double *) (D + o_b), m, stride, js,
+		CU(launch_check_motions(scene->dev, rdev, (const double *) (D + o_a), (const double *) (D + o_b), m, stride, js,
 								max_step, (const uint32_t *) (D + o_ovr), (uint32_t *) (D + o_hit),
 								toi ? (double *) (D + o_toi) : nullptr, (uint32_t *) (D + o_steps), nullptr,
 								(unsigned *) (D + o_first), D + o_slerp, D + o_q[0], qb_all, motion_survivors(m), stream));
@@ -951,7 +1118,8 @@ int mgodpl_sample_goals_device(mgodpl_scene *scene, const mgodpl_robot *robot, c
 	auto &slot = scene->stream_slot(stream);
 	std::lock_guard<std::mutex> enqueue(slot.mu);
 	CU(slot.ws.reserve(qb, 0));
-	CU(launch_sample_goals(scene->dev, robot->dev, d_targets, f, d_draws, s, seed, dist, d_hit_bits, d_collisions,
+	ROBOT_ON_SCENE_DEVICE(rdev);
+	CU(launch_sample_goals(scene->dev, rdev, d_targets, f, d_draws, s, seed, dist, d_hit_bits, d_collisions,
 						   d_states_out, slot.ws.dev, qb, stream));
 	return MGODPL_OK;
 }
@@ -976,7 +1144,8 @@ int mgodpl_sample_goals(mgodpl_scene *scene, const mgodpl_robot *robot, const do
 	char *D = ws->dev, *H = ws->host - o_hit;  // host staging mirrors the device layout of the two result arrays
 	CU(cudaMemcpyAsync(D + o_t, targets, f * 24, cudaMemcpyHostToDevice, stream));
 	if (draws) CU(cudaMemcpyAsync(D + o_d, draws, s * (1 + nv) * 8, cudaMemcpyHostToDevice, stream));
-	CU(launch_sample_goals(scene->dev, robot->dev, (const double *) (D + o_t), f, draws ? (const double *) (D + o_d) : nullptr,
+	ROBOT_ON_SCENE_DEVICE(rdev);
+	CU(launch_sample_goals(scene->dev, rdev, (const double *) (D + o_t), f, draws ? (const double *) (D + o_d) : nullptr,
 						   s, seed, dist, (uint32_t *) (D + o_hit), (uint32_t *) (D + o_cnt),
 						   states_out ? (double *) (D + o_st) : nullptr, D + o_q, qb, stream));
 	CU(cudaMemcpyAsync(H + o_hit, D + o_hit, small_hi - o_hit, cudaMemcpyDeviceToHost, stream));

@@ -90,6 +90,7 @@ enum : int32_t {
 	FK_STORE = 32         // a later, non-adjacent collision op uses this child as its parent: keep it in the link table
 };
 
+enum ShapeKind : int { SHAPE_KIND_BOX = 0, SHAPE_KIND_CAPSULE = 1, SHAPE_KIND_CONVEX = 2 };
 constexpr int BOX_SPHERES = 4;
 struct BoxDev {
 	int32_t link;
@@ -100,6 +101,11 @@ struct BoxDev {
 	// scene when every sphere is (clearance grid, SceneDev::clear)
 	float sphere_c[BOX_SPHERES][3];
 	float sphere_r;
+	// ShapeKind (geometry.cuh).  A capsule or convex polytope travels as its bounding box (half, t, q: the tree descent and every
+	// fp32 cull are a box link's) and differs in the exact leaf test only: capsule radius = half[0], segment half length =
+	// half[2] - half[0]; a convex polytope's hull lives at RobotDev::shape_data + data_off (doubles).
+	int32_t kind;
+	int32_t data_off;
 	int32_t pad_;
 };
 
@@ -108,6 +114,8 @@ struct RobotDev {
 	int32_t root, ee;
 	int32_t root_box_begin, root_box_end;  // boxes of the root link (boxes are sorted by the op that reaches their link)
 	int32_t chain;        // every collision op continues from the previous one: FK needs no link table
+	int32_t all_boxes;    // every collision shape is a box (the reference's robots): the fp32 pre-filter may answer "certain hit"
+	const double *shape_data;  // device copy of the convex hulls (per device, patched in by the C ABI), or nullptr
 	int32_t n_ee_path;    // ops on the way from the root to the end effector (ee_path), in execution order
 	double reach;         // radius around the root link origin that contains every box for every joint value
 	int8_t ee_path[MGODPL_MAX_LINKS];

@@ -219,7 +219,7 @@ struct QueueSink {
 			__stcg(dst + 3, make_double2(q.w, __hiloint2double((int) (step | box << 28), (int) owner)));
 		} else if (!already_decided(res, owner, step)) {
 			const CullBox cb = make_cull_box(sc, c, q, rb.boxes[box].half);
-			if (box_hits_scene(sc, cb, c, q, rb.boxes[box].half, lc)) report_hit(res, owner, step);
+			if (box_hits_scene(sc, cb, c, q, rb.boxes[box].half, lc, rb.boxes[box].kind, rb.shape_data + rb.boxes[box].data_off)) report_hit(res, owner, step);
 		}
 	}
 };

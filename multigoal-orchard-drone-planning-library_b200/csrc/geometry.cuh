@@ -236,4 +236,132 @@ static __device__ __noinline__ bool box_triangle_hit(const ExactBox &b, const do
 	return true;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Other link shapes (north_star (3); the reference itself only collides boxes, collision_detection.cpp:21-22,49-51).
+// Both walk the tree with their bounding box (the same fp32 culling as a box link) and differ at the leaves only.
+// ---------------------------------------------------------------------------------------------------------------
+
+/// Squared distance between the segments [p1, q1] and [p2, q2] (clamped closest-point parameters).
+__device__ __forceinline__ double segment_segment_dist2(D3 p1, D3 q1, D3 p2, D3 q2) {
+	const D3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+	const double a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), c = dot(d1, r), b = dot(d1, d2);
+	double s = 0.0, t = 0.0;
+	if (a > 1e-300 && e > 1e-300) {
+		const double den = a * e - b * b;
+		s = den > 1e-14 * a * e ? fmin(fmax((b * f - c * e) / den, 0.0), 1.0) : 0.0;
+		t = (b * s + f) / e;
+		if (t < 0.0) t = 0.0, s = fmin(fmax(-c / a, 0.0), 1.0);
+		else if (t > 1.0) t = 1.0, s = fmin(fmax((b - c) / a, 0.0), 1.0);
+	} else if (a > 1e-300) {
+		s = fmin(fmax(-c / a, 0.0), 1.0);
+	} else if (e > 1e-300) {
+		t = fmin(fmax(f / e, 0.0), 1.0);
+	}
+	const D3 dd = (p1 + d1 * s) - (p2 + d2 * t);
+	return dot(dd, dd);
+}
+
+/// Squared distance from point p to triangle (a, b, c): Voronoi-region classification of the closest point.
+__device__ __forceinline__ double point_triangle_dist2(D3 p, D3 a, D3 b, D3 c) {
+	const D3 ab = b - a, ac = c - a, ap = p - a;
+	const double d1 = dot(ab, ap), d2 = dot(ac, ap);
+	D3 cl = a;
+	do {
+		if (d1 <= 0.0 && d2 <= 0.0) break;
+		const D3 bp = p - b;
+		const double d3 = dot(ab, bp), d4 = dot(ac, bp);
+		if (d3 >= 0.0 && d4 <= d3) { cl = b; break; }
+		const double vc = d1 * d4 - d3 * d2;
+		if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) { cl = a + ab * (d1 / (d1 - d3)); break; }
+		const D3 cp = p - c;
+		const double d5 = dot(ab, cp), d6 = dot(ac, cp);
+		if (d6 >= 0.0 && d5 <= d6) { cl = c; break; }
+		const double vb = d5 * d2 - d1 * d6;
+		if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) { cl = a + ac * (d2 / (d2 - d6)); break; }
+		const double va = d3 * d6 - d5 * d4;
+		if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0) { cl = b + (c - b) * ((d4 - d3) / ((d4 - d3) + (d5 - d6))); break; }
+		const double den = va + vb + vc;
+		if (fabs(den) > 0.0) cl = a + ab * (vb / den) + ac * (vc / den);
+	} while (false);
+	const D3 d = p - cl;
+	return dot(d, d);
+}
+
+/// Capsule (the points within `radius` of the segment (0, 0, -+half_len) of the shape frame; fcl::Capsule's convention) vs
+/// closed triangle: contact iff the segment comes within `radius` of the triangle.  The segment either pierces the triangle
+/// (distance 0) or its closest approach is attained at a segment end point or on a triangle edge.
+static __device__ __noinline__ bool capsule_triangle_hit(const ExactBox &b, double radius, double half_len, const double *__restrict__ tri) {
+	D3 p[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const double dx = __ldg(tri + 3 * k) - b.cx, dy = __ldg(tri + 3 * k + 1) - b.cy, dz = __ldg(tri + 3 * k + 2) - b.cz;
+		p[k] = {b.r[0] * dx + b.r[3] * dy + b.r[6] * dz, b.r[1] * dx + b.r[4] * dy + b.r[7] * dz, b.r[2] * dx + b.r[5] * dy + b.r[8] * dz};
+	}
+	const D3 s0{0.0, 0.0, -half_len}, s1{0.0, 0.0, half_len};
+	const double r2 = radius * radius;
+	double best = fmin(point_triangle_dist2(s0, p[0], p[1], p[2]), point_triangle_dist2(s1, p[0], p[1], p[2]));
+	if (best <= r2) return true;
+#pragma unroll
+	for (int k = 0; k < 3; ++k) best = fmin(best, segment_segment_dist2(s0, s1, p[k], p[(k + 1) % 3]));
+	if (best <= r2) return true;
+	// piercing: the end points lie on opposite sides of the plane and the crossing point falls inside the triangle
+	const D3 e0 = p[1] - p[0], e1 = p[2] - p[0], n = cross(e0, e1);
+	const double h0 = dot(n, s0 - p[0]), h1 = dot(n, s1 - p[0]);
+	if ((h0 > 0.0 && h1 > 0.0) || (h0 < 0.0 && h1 < 0.0) || h0 == h1) return false;
+	const D3 x = s0 + (s1 - s0) * (h0 / (h0 - h1));
+	const D3 w = x - p[0];
+	const double d00 = dot(e0, e0), d01 = dot(e0, e1), d11 = dot(e1, e1), d20 = dot(w, e0), d21 = dot(w, e1);
+	const double den = d00 * d11 - d01 * d01;
+	if (!(den > 0.0)) return false;  // degenerate triangle: its edges were already measured
+	const double v = (d11 * d20 - d01 * d21) / den, u = (d00 * d21 - d01 * d20) / den;
+	return v >= 0.0 && u >= 0.0 && v + u <= 1.0;
+}
+
+/// Convex polytope vs closed triangle, separating-axis test in the shape frame.  `data` (mgodpl_robot_create_ex lays it out):
+/// [n_verts, n_faces, n_edges, -] [verts: 3 each] [faces: outward unit normal + support value, 4 each] [edge directions: 3 each].
+/// Axes: the polytope's face normals, the triangle normal, edge x edge.  Touching counts as contact; numerically null axes
+/// (parallel edges, degenerate triangle) carry no information and are skipped.
+static __device__ __noinline__ bool convex_triangle_hit(const ExactBox &b, const double *__restrict__ data, const double *__restrict__ tri) {
+	D3 p[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const double dx = __ldg(tri + 3 * k) - b.cx, dy = __ldg(tri + 3 * k + 1) - b.cy, dz = __ldg(tri + 3 * k + 2) - b.cz;
+		p[k] = {b.r[0] * dx + b.r[3] * dy + b.r[6] * dz, b.r[1] * dx + b.r[4] * dy + b.r[7] * dz, b.r[2] * dx + b.r[5] * dy + b.r[8] * dz};
+	}
+	const int nv = (int) __ldg(data), nf = (int) __ldg(data + 1), ne = (int) __ldg(data + 2);
+	const double *verts = data + 4, *faces = verts + 3 * nv, *edges = faces + 4 * nf;
+	for (int f = 0; f < nf; ++f) {
+		const D3 n{__ldg(faces + 4 * f), __ldg(faces + 4 * f + 1), __ldg(faces + 4 * f + 2)};
+		if (fmin(dot(n, p[0]), fmin(dot(n, p[1]), dot(n, p[2]))) > __ldg(faces + 4 * f + 3)) return false;
+	}
+	const D3 tf[3] = {p[1] - p[0], p[2] - p[1], p[0] - p[2]};
+	const double scale2 = fmax(dot(tf[0], tf[0]), fmax(dot(tf[1], tf[1]), dot(tf[2], tf[2])));
+	auto separates = [&](D3 a, double floor2) {
+		if (!(dot(a, a) > floor2)) return false;
+		double lo = 1e300, hi = -1e300;
+		for (int v = 0; v < nv; ++v) {
+			const double q = a.x * __ldg(verts + 3 * v) + a.y * __ldg(verts + 3 * v + 1) + a.z * __ldg(verts + 3 * v + 2);
+			lo = fmin(lo, q), hi = fmax(hi, q);
+		}
+		const double q0 = dot(a, p[0]), q1 = dot(a, p[1]), q2 = dot(a, p[2]);
+		return fmin(q0, fmin(q1, q2)) > hi || fmax(q0, fmax(q1, q2)) < lo;
+	};
+	if (separates(cross(tf[0], tf[1]), 1e-28 * scale2 * scale2)) return false;
+	for (int e = 0; e < ne; ++e) {
+		const D3 d{__ldg(edges + 3 * e), __ldg(edges + 3 * e + 1), __ldg(edges + 3 * e + 2)};  // unit length
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+			if (separates(cross(d, tf[k]), 1e-24 * dot(tf[k], tf[k]))) return false;
+	}
+	return true;
+}
+
+/// One exact shape/triangle test, by kind.  `half`: the box's half extents (capsule: radius = half[0], segment half length =
+/// half[2] - half[0]; convex: its bounding box, the vertices live in `data`).
+__device__ __forceinline__ bool shape_triangle_hit(int kind, const ExactBox &b, const double *data, const double *__restrict__ tri) {
+	if (kind == SHAPE_KIND_BOX) return box_triangle_hit(b, tri);
+	if (kind == SHAPE_KIND_CAPSULE) return capsule_triangle_hit(b, b.hx, b.hz - b.hx, tri);
+	return convex_triangle_hit(b, data, tri);
+}
+
 }  // namespace mgodpl_b200

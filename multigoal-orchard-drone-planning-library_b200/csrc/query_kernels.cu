@@ -96,14 +96,16 @@ __device__ __forceinline__ ExactBox make_exact_box(D3 c, Q4 q, const double *hal
 
 /// fp32 classification of a leaf's triangles against one box: returns TRI_HIT as soon as one triangle certainly
 /// touches, otherwise the set of triangles that still need the exact test (bit k of *unknown).
-__device__ __forceinline__ bool leaf_prefilter(const SceneDev &sc, const CullBox &cb, int ref, unsigned *unknown) {
+/// `is_box` false (capsule / convex link: `cb` is the shape's bounding box): a vertex inside the bounding box proves nothing,
+/// so "certain hit" is demoted to "needs the exact test".
+__device__ __forceinline__ bool leaf_prefilter(const SceneDev &sc, const CullBox &cb, int ref, unsigned *unknown, bool is_box = true) {
 	const unsigned info = (unsigned) (-1 - ref), first = info >> 4, cnt = (info & 15u) + 1u;
 	*unknown = 0;
 	for (unsigned k = 0; k < cnt; ++k) {
 		const float4 *t = sc.tris32 + 3ull * (first + k);
 		const int v = tri_classify(cb, sc.margin, __ldg(t), __ldg(t + 1), __ldg(t + 2));
-		if (v == TRI_HIT) return true;
-		if (v == TRI_UNKNOWN) *unknown |= 1u << k;
+		if (v == TRI_HIT && is_box) return true;
+		if (v != TRI_SEPARATED) *unknown |= 1u << k;
 	}
 	return false;
 }
@@ -112,7 +114,7 @@ __device__ __forceinline__ bool leaf_prefilter(const SceneDev &sc, const CullBox
 /// and test the triangles the pre-filter could not decide.  Rare and register-hungry (fp64): as a separate function its
 /// register demand does not shape the traversal loop.
 __device__ __noinline__ bool exact_leaf_test(const SceneDev &sc, const void *exact_pose, const double *half, int ref, unsigned unknown,
-											 unsigned *n_tests) {
+											 unsigned *n_tests, int kind = SHAPE_KIND_BOX, const double *shape_data = nullptr) {
 	const unsigned info = (unsigned) (-1 - ref), first = info >> 4, cnt = (info & 15u) + 1u;
 	const double2 *ex = reinterpret_cast<const double2 *>(exact_pose);
 	const double2 e0 = __ldcg(ex), e1 = __ldcg(ex + 1), e2 = __ldcg(ex + 2), e3 = __ldcg(ex + 3);
@@ -120,7 +122,7 @@ __device__ __noinline__ bool exact_leaf_test(const SceneDev &sc, const void *exa
 	for (unsigned k = 0; k < cnt; ++k) {
 		if (!(unknown >> k & 1u)) continue;
 		++*n_tests;
-		if (box_triangle_hit(eb, sc.tris + 9ull * (first + k))) return true;
+		if (shape_triangle_hit(kind, eb, shape_data, sc.tris + 9ull * (first + k))) return true;
 	}
 	return false;
 }
@@ -215,21 +217,22 @@ __device__ __forceinline__ int visit_wide(const SceneDev &sc, const CullBox &cb,
 }
 
 /// Exact test of the box against every triangle of one leaf reference.
-__device__ __forceinline__ bool leaf_hit(const SceneDev &sc, const CullBox &cb, const ExactBox &eb, int ref, LocalCounters &lc) {
+__device__ __forceinline__ bool leaf_hit(const SceneDev &sc, const CullBox &cb, const ExactBox &eb, int ref, LocalCounters &lc,
+										 int kind = SHAPE_KIND_BOX, const double *shape_data = nullptr) {
 	const unsigned info = (unsigned) (-1 - ref), first = info >> 4, cnt = (info & 15u) + 1u;
 	unsigned unknown;
-	if (leaf_prefilter(sc, cb, ref, &unknown)) return true;
+	if (leaf_prefilter(sc, cb, ref, &unknown, kind == SHAPE_KIND_BOX)) return true;
 	for (unsigned k = 0; k < cnt; ++k) {
 		if (!(unknown >> k & 1u)) continue;
 		lc.leaf++;
-		if (box_triangle_hit(eb, sc.tris + 9ull * (first + k))) return true;
+		if (shape_triangle_hit(kind, eb, shape_data, sc.tris + 9ull * (first + k))) return true;
 	}
 	return false;
 }
 
 /// Plain one-thread traversal (stage A's queue-overflow path): does the box touch any triangle of the scene?
 __device__ __noinline__ bool box_hits_scene(const SceneDev &sc, const CullBox &cb, D3 c, Q4 q, const double *half,
-											LocalCounters &lc) {
+											LocalCounters &lc, int kind = SHAPE_KIND_BOX, const double *shape_data = nullptr) {
 	if (!sc.n_nodes) return false;
 	const ExactBox eb = make_exact_box(c, q, half);
 	int stack[STACK_DEPTH], cur = 0;
@@ -240,7 +243,7 @@ __device__ __noinline__ bool box_hits_scene(const SceneDev &sc, const CullBox &c
 			lc.nodes++;
 			cur = visit_record(sc, cb, cur, st);
 		} else {
-			if (leaf_hit(sc, cb, eb, cur, lc)) return true;
+			if (leaf_hit(sc, cb, eb, cur, lc, kind, shape_data)) return true;
 			cur = st.sp > 0 ? st.pop() : REF_END;
 		}
 	}
@@ -291,7 +294,8 @@ struct QueueDev {
 
 /// Stage A tail: cull one box against the scene bounds and hand it to stage B (or traverse it here on overflow).
 __device__ __forceinline__ void emit_box(const SceneDev &sc, const QueueDev &Q, const Results &res, D3 c, Q4 q,
-										 const double *half, const BoxDev *spheres, unsigned owner, unsigned step, unsigned box, LocalCounters &lc) {
+										 const double *half, const BoxDev *spheres, unsigned owner, unsigned step, unsigned box, LocalCounters &lc,
+										 const double *shape_data = nullptr) {
 	const CullBox cb = make_cull_box(sc, c, q, half);
 	if (!cull_overlap(cb, sc.root_c[0], sc.root_c[1], sc.root_c[2], sc.root_h[0], sc.root_h[1], sc.root_h[2])) return;
 	if (sc.clear) {
@@ -331,7 +335,7 @@ __device__ __forceinline__ void emit_box(const SceneDev &sc, const QueueDev &Q, 
 		__stcg(dst + 2, make_double2(q.y, q.z));
 		__stcg(dst + 3, make_double2(q.w, __hiloint2double((int) (step | box << 28), (int) owner)));
 	} else if (!already_decided(res, owner, step)) {
-		if (box_hits_scene(sc, cb, c, q, half, lc)) report_hit(res, owner, step);
+		if (box_hits_scene(sc, cb, c, q, half, lc, spheres ? spheres->kind : SHAPE_KIND_BOX, shape_data)) report_hit(res, owner, step);
 	}
 }
 
@@ -369,7 +373,7 @@ __device__ __forceinline__ void emit_link_boxes(const SceneDev &sc, const RobotD
 	for (int bi = lo; bi < hi; ++bi) {
 		const BoxDev &bx = rb.boxes[bi];
 		const Pose w = bx.tf_identity ? link : then(link, D3{bx.t[0], bx.t[1], bx.t[2]}, Q4{bx.q[0], bx.q[1], bx.q[2], bx.q[3]}, false);
-		emit_box(sc, Q, res, w.t, w.q, bx.half, &bx, owner, step, (unsigned) bi, lc);
+		emit_box(sc, Q, res, w.t, w.q, bx.half, &bx, owner, step, (unsigned) bi, lc, rb.shape_data + bx.data_off);
 	}
 }
 __device__ __forceinline__ void expand_state(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
@@ -991,19 +995,21 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 					cur = REF_END;
 				} else {
 					unsigned unknown = 0xffffu;
-					bool hit = tune.no_prefilter ? false : leaf_prefilter(sc, cb, cur, &unknown);
+					const int kind = (explicit_boxes || rb.all_boxes) ? (int) SHAPE_KIND_BOX : rb.boxes[step_box >> 28].kind;
+					bool hit = tune.no_prefilter ? false : leaf_prefilter(sc, cb, cur, &unknown, kind == SHAPE_KIND_BOX);
 					if (!hit && unknown) {
 						double half_buf[3];
-						const double *half;
+						const double *half, *shape_data = nullptr;
 						if (explicit_boxes) {
 							const double *bx = explicit_boxes + (size_t) owner * 10;
 							half_buf[0] = __ldg(bx + 7) * 0.5, half_buf[1] = __ldg(bx + 8) * 0.5, half_buf[2] = __ldg(bx + 9) * 0.5;
 							half = half_buf;
 						} else {
 							half = rb.boxes[step_box >> 28].half;
+							if (kind == SHAPE_KIND_CONVEX) shape_data = rb.shape_data + rb.boxes[step_box >> 28].data_off;
 						}
 						unsigned n_exact = 0;
-						hit = exact_leaf_test(sc, reinterpret_cast<const char *>(Q.items + item), half, cur, unknown, &n_exact);
+						hit = exact_leaf_test(sc, reinterpret_cast<const char *>(Q.items + item), half, cur, unknown, &n_exact, kind, shape_data);
 						lc.leaf += n_exact;
 					}
 					if (hit) {
@@ -1113,6 +1119,8 @@ static const Knobs &knobs() {
 	static const Knobs k;
 	return k;
 }
+/// The experimental fused kernels (pipeline.cuh) only know box links: robots with capsules / convex links take the default path.
+static int pipeline_mode(const RobotDev &rb) { return rb.all_boxes ? knobs().pipeline : 0; }
 /// Grids are a multiple of the SM count (148 on B200) times the resident blocks per SM, or smaller for small inputs.
 static unsigned grid_for(size_t work_items, int block, int blocks_per_sm) {
 	size_t blocks = (work_items + block - 1) / block, cap = (size_t) sm_count() * blocks_per_sm;
@@ -1206,7 +1214,7 @@ static cudaError_t launch_pipeline(const SceneDev &sc, const RobotDev &rb, const
 static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const double *explicit_boxes, const QueueDev &Q,
 								const Results &res, size_t worst_case_items, cudaStream_t stream) {
 	size_t bound = worst_case_items < Q.cap ? worst_case_items : Q.cap;
-	if (knobs().pipeline == 2) {  // the pipeline kernel fed from the queue: warp-wide leaf batches and shared-memory stacks, expansion stays a kernel of its own
+	if (pipeline_mode(rb) == 2) {  // the pipeline kernel fed from the queue: warp-wide leaf batches and shared-memory stacks, expansion stays a kernel of its own
 		SourceArgs src{};
 		src.queue = Q, src.boxes = explicit_boxes;
 		return launch_pipeline<SRC_QUEUE>(sc, rb, src, Q.cursor, res, bound, stream);
@@ -1265,7 +1273,7 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
-	if (knobs().pipeline == 1) Q.cap = 0;  // the fused kernel keeps its boxes on chip; only stage A1's overflow path would queue, and traverses inline instead
+	if (pipeline_mode(rb) == 1) Q.cap = 0;  // the fused kernel keeps its boxes on chip; only stage A1's overflow path would queue, and traverses inline instead
 	if (knobs().cull_bulk && (reinterpret_cast<size_t>(d_states) & 15) == 0 && (32 * stride * 8) % 16 == 0) {
 		const size_t span_pad = (32 * stride * 8 + 127) & ~(size_t) 127;
 		const size_t smem = (((BLOCK_A / 32) * BULK_STAGES * 8 + 127) & ~(size_t) 127) + (BLOCK_A / 32) * BULK_STAGES * span_pad;
@@ -1276,7 +1284,7 @@ cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const do
 		k_cull_states<<<grid_for(n, BLOCK_A, 8), BLOCK_A, BLOCK_A * stride * sizeof(double), stream>>>(sc, rb, d_states, n, stride, S, Q, res);
 	}
 	LQ_CHECK(cudaGetLastError());
-	if (knobs().pipeline == 1) {
+	if (pipeline_mode(rb) == 1) {
 		SourceArgs src{};
 		src.list[0] = S, src.n_lists = 1, src.states = d_states, src.stride = stride;
 		return launch_pipeline<SRC_STATES>(sc, rb, src, Q.cursor, res, std::min<size_t>(S.cap, n + SHARDS * SHARD_BLOCK) * (size_t) ((rb.n_boxes + SPL - 1) / SPL > 0 ? (rb.n_boxes + SPL - 1) / SPL : 1), stream);
@@ -1304,6 +1312,7 @@ cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t
 	QueueDev Q = carve_queue(scratch, scratch_bytes);
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	RobotDev none{};
+	none.all_boxes = 1;
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, ((n + 31) / 32) * 4, stream));
 	if (knobs().pipeline == 1) {
 		LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
@@ -1334,7 +1343,7 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	carve(scratch, scratch_bytes, survivor_entries, &S, &Q, &S_tail, m * (size_t) (head_arg ? head_arg : 48u));
 	Results res{RESULT_FIRST_STEP, nullptr, d_first_step};
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
-	if (knobs().pipeline == 1) Q.cap = 0;
+	if (pipeline_mode(rb) == 1) Q.cap = 0;
 	if (knobs().ranges_variant == 1)  // one wave for 100 k motions: 6 blocks x 4 warps per SM at <= 85 registers
 		k_motion_ranges<128, 6><<<grid_for(m, 128, 6), 128, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override, d_n_steps, d_uncertain,
 																		  (SlerpConst *) d_slerp, S, S_tail, head_arg, trim, Q, res);
@@ -1342,7 +1351,7 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 		k_motion_ranges<BLOCK_A, 2><<<grid_for(m, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override, d_n_steps, d_uncertain,
 																					  (SlerpConst *) d_slerp, S, S_tail, head_arg, trim, Q, res);
 	LQ_CHECK(cudaGetLastError());
-	if (knobs().pipeline == 1) {
+	if (pipeline_mode(rb) == 1) {
 		// one launch walks the head list, then the tail list: by the time a warp reaches a motion's tail steps, the head steps of
 		// (almost) every motion have been decided, and tail steps behind a hit are dropped when they are claimed
 		SourceArgs src{};
@@ -1391,7 +1400,7 @@ cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const do
 	Results res{RESULT_BITS, d_hit_bits, nullptr};
 	const size_t wpr = (s + 31) / 32, total = f * s;
 	LQ_CHECK(cudaMemsetAsync(d_hit_bits, 0, f * wpr * 4, stream));
-	if (knobs().pipeline == 1) {
+	if (pipeline_mode(rb) == 1) {
 		LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
 		SourceArgs src{};
 		src.targets = d_targets, src.draws = d_draws, src.rows = f, src.per_row = s, src.seed = seed;

@@ -28,7 +28,17 @@ struct Mesh {
 struct Box {
 	math::Vec3d size;
 };
-using Shape = std::variant<Box, Mesh>;
+/// Additions of this library to the reference's Shape variant (Box | Mesh, shapes.h:24-29): link shapes the CUDA path collides
+/// beside boxes.  Capsule: the points within `radius` of a segment of `length` along the shape's z axis, centred (fcl::Capsule's
+/// convention).  ConvexMesh: the convex hull of 4 .. MGODPL_MAX_CONVEX_VERTICES points.  A general Mesh link still throws the
+/// reference's "Only boxes are implemented for collision geometry.".
+struct Capsule {
+	double radius, length;
+};
+struct ConvexMesh {
+	std::vector<math::Vec3d> vertices;
+};
+using Shape = std::variant<Box, Mesh, Capsule, ConvexMesh>;
 struct PositionedShape {
 	Shape shape;
 	math::Transformd transform;
@@ -167,6 +177,8 @@ public:
 		std::lock_guard<std::mutex> g(*device_mu);
 		if (!device) {
 			std::vector<mgodpl_shape_desc> sd;
+			std::vector<double> mesh_vertices;
+			std::vector<int32_t> mesh_offsets{0};
 			for (size_t l = 0; l < links.size(); ++l)
 				for (auto &g2: links[l].collision_geometry) {
 					mgodpl_shape_desc d{};
@@ -174,9 +186,16 @@ public:
 					if (auto *b = std::get_if<Box>(&g2.shape)) {
 						d.shape_type = MGODPL_SHAPE_BOX;
 						d.size[0] = b->size.x(), d.size[1] = b->size.y(), d.size[2] = b->size.z();
+					} else if (auto *c = std::get_if<Capsule>(&g2.shape)) {
+						d.shape_type = MGODPL_SHAPE_CAPSULE;
+						d.size[0] = d.size[1] = c->radius, d.size[2] = c->length;
+					} else if (auto *m = std::get_if<ConvexMesh>(&g2.shape)) {
+						d.shape_type = MGODPL_SHAPE_CONVEX_MESH;
+						for (auto &v: m->vertices) mesh_vertices.insert(mesh_vertices.end(), {v.x(), v.y(), v.z()});
 					} else {
 						d.shape_type = MGODPL_SHAPE_MESH;
 					}
+					mesh_offsets.push_back((int32_t) (mesh_vertices.size() / 3));
 					gpu::to7(g2.transform, d.transform);
 					sd.push_back(d);
 				}
@@ -199,8 +218,8 @@ public:
 			for (size_t i = 0; i < links.size(); ++i)
 				if (links[i].name == "end_effector") ee = (int32_t) i;
 			auto dr = std::make_shared<gpu::DeviceRobot>();
-			gpu::throw_status(mgodpl_robot_create((int32_t) links.size(), sd.data(), (int32_t) sd.size(), jd.data(), (int32_t) jd.size(),
-												   root, ee, &dr->handle));
+			gpu::throw_status(mgodpl_robot_create_ex((int32_t) links.size(), sd.data(), (int32_t) sd.size(), jd.data(), (int32_t) jd.size(),
+													  root, ee, mesh_vertices.data(), mesh_offsets.data(), &dr->handle));
 			device = dr;
 		}
 		return device->handle;

@@ -34,6 +34,16 @@ class RobotModel:
             self.shapes.append((len(self.link_names) - 1, tuple(box_size), capi.IDENTITY_TF))
         return len(self.link_names) - 1
 
+    def add_capsule(self, link: int, radius: float, length: float, tf=None):
+        """A capsule link shape (not in the reference): the points within ``radius`` of a segment of ``length`` along the
+        shape's z axis, centred (fcl::Capsule's convention)."""
+        self.shapes.append((link, (radius, radius, length), tuple(tf) if tf is not None else capi.IDENTITY_TF, capi.SHAPE_CAPSULE))
+
+    def add_convex_mesh(self, link: int, vertices, tf=None):
+        """A convex-polytope link shape (not in the reference): the hull of 4..16 points given in the shape frame."""
+        self.shapes.append((link, (0.0, 0.0, 0.0), tuple(tf) if tf is not None else capi.IDENTITY_TF, capi.SHAPE_CONVEX_MESH,
+                            np.asarray(vertices, dtype=np.float64).reshape(-1, 3)))
+
     def insert_joint(self, link_a, link_b, attach_a, attach_b, joint_type, axis=(1.0, 0.0, 0.0), lo=0.0, hi=0.0) -> int:
         self.joints.append((link_a, link_b, tuple(attach_a), tuple(attach_b), joint_type, tuple(axis), lo, hi))
         return len(self.joints) - 1

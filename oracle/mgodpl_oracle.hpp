@@ -122,9 +122,15 @@ inline Tf interpolate(const Tf &a, const Tf &b, double t) {
 // ---------------------------------------------------------------------------------------------------------
 enum JointKind : int { REVOLUTE = 0, FIXED = 1 };
 
+enum GeomKind : int { GEOM_BOX = 0, GEOM_CAPSULE = 1, GEOM_CONVEX = 2 };
 struct BoxGeom {  // src/experiment_utils/shapes.h:20-22 + positioned_shape.h:12-30
 	V3 size;      // full extents, centred
 	Tf tf;        // relative to the link frame
+	// Not in the reference (it collides boxes only, collision_detection.cpp:21-22,49-51): capsule and convex-polytope links of
+	// the CUDA library (BASELINE north_star (3)), defined here from first principles; parity for them is against this file only.
+	int kind = GEOM_BOX;
+	double radius = 0, length = 0;  // capsule: points within `radius` of the segment (0, 0, -+length / 2) of the shape frame
+	std::vector<V3> verts;          // convex: the hull of these points (shape frame)
 };
 struct Link {
 	std::string name;
@@ -378,6 +384,80 @@ inline double box_tri_clearance(const V3 &h, const V3 &p0, const V3 &p1, const V
 	return box_tri_distance_separated(h, p0, p1, p2);
 }
 
+/// Capsule vs triangle in the capsule's frame: signed clearance = (distance from the axis segment to the triangle) - radius.
+/// The closest approach of a segment and a triangle is 0 if the segment pierces the triangle, otherwise it is attained at a
+/// segment end point or on a triangle edge.
+inline double capsule_tri_clearance(double radius, double length, const V3 &p0, const V3 &p1, const V3 &p2) {
+	const V3 a{0, 0, -0.5 * length}, b{0, 0, 0.5 * length};
+	const V3 tri[3] = {p0, p1, p2};
+	double best = std::numeric_limits<double>::infinity();
+	for (const V3 &e: {a, b}) {
+		V3 d = e - closest_on_triangle(e, p0, p1, p2);
+		best = std::min(best, dot(d, d));
+	}
+	for (int k = 0; k < 3; ++k) best = std::min(best, seg_seg_dist2(a, b, tri[k], tri[(k + 1) % 3]));
+	// piercing: solve a + t (b - a) = p0 + u (p1 - p0) + v (p2 - p0) (Moeller-Trumbore form)
+	V3 dir = b - a, e1 = p1 - p0, e2 = p2 - p0, pv = cross(dir, e2);
+	double det = dot(e1, pv);
+	if (std::fabs(det) > 0) {
+		V3 tv = a - p0;
+		double u = dot(tv, pv) / det;
+		V3 qv = cross(tv, e1);
+		double v = dot(dir, qv) / det, t = dot(e2, qv) / det;
+		if (u >= 0 && v >= 0 && u + v <= 1 && t >= 0 && t <= 1) best = 0;
+	}
+	return std::sqrt(best) - radius;
+}
+
+/// Convex polytope (hull of `verts`, shape frame) vs triangle (same frame) by separating axes, with a deliberately generous
+/// axis set found by exhaustive search at every call: the normals of ALL supporting planes through three vertices, the triangle
+/// normal, and (v_i - v_j) x (triangle edge) for ALL vertex pairs — a superset of the hull's real edges, so nothing depends on
+/// a hull construction being right.  sat_gap: largest normalised separation (> 0 separated, a lower bound of the distance;
+/// <= 0 overlapping, minus the penetration depth along the best axis).
+inline SatResult convex_tri_sat(const std::vector<V3> &verts, const V3 &p0, const V3 &p1, const V3 &p2) {
+	const V3 p[3] = {p0, p1, p2};
+	const V3 f[3] = {p1 - p0, p2 - p1, p0 - p2};
+	double gap = -std::numeric_limits<double>::infinity();
+	double scale = 0;
+	for (auto &v: verts) scale = std::max({scale, std::fabs(v.x), std::fabs(v.y), std::fabs(v.z)});
+	auto axis = [&](const V3 &a, double len2_floor) {
+		double l2 = dot(a, a);
+		if (!(l2 > len2_floor)) return;
+		double lo = 1e300, hi = -1e300;
+		for (auto &v: verts) {
+			double q = dot(a, v);
+			lo = std::min(lo, q), hi = std::max(hi, q);
+		}
+		double q0 = dot(a, p[0]), q1 = dot(a, p[1]), q2 = dot(a, p[2]);
+		double tlo = std::min({q0, q1, q2}), thi = std::max({q0, q1, q2});
+		gap = std::max(gap, std::max(tlo - hi, lo - thi) / std::sqrt(l2));
+	};
+	const size_t n = verts.size();
+	for (size_t i = 0; i < n; ++i)
+		for (size_t j = i + 1; j < n; ++j)
+			for (size_t k = j + 1; k < n; ++k) {
+				V3 nn = cross(verts[j] - verts[i], verts[k] - verts[i]);
+				if (!(dot(nn, nn) > 1e-24 * scale * scale * scale * scale)) continue;
+				double lo = 0, hi = 0, len = std::sqrt(dot(nn, nn));
+				for (auto &v: verts) {
+					double sd = dot(nn, v - verts[i]) / len;
+					lo = std::min(lo, sd), hi = std::max(hi, sd);
+				}
+				if (hi > 1e-10 * scale && lo < -1e-10 * scale) continue;  // not a supporting plane
+				axis(nn, 0.0);
+			}
+	double scale2 = std::max({dot(f[0], f[0]), dot(f[1], f[1]), dot(f[2], f[2])});
+	axis(cross(f[0], f[1]), 1e-28 * scale2 * scale2);
+	for (size_t i = 0; i < n; ++i)
+		for (size_t j = i + 1; j < n; ++j) {
+			V3 d = verts[i] - verts[j];
+			double dl2 = dot(d, d);
+			if (!(dl2 > 0)) continue;
+			for (int k = 0; k < 3; ++k) axis(cross(d, f[k]), 1e-24 * dl2 * dot(f[k], f[k]));
+		}
+	return {gap <= 0.0, gap};
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Scene (stands where fcl::BVHModel<OBBd> stood): the triangle soup of Mesh (src/planning/Mesh.h:19-22) as
 // handed to meshToFclBVH (src/planning/fcl_utils.cpp:23-56), identity pose, surface only.
@@ -554,13 +634,80 @@ inline double obb_scene_clearance(const Scene &s, const Obb &b, double reach) {
 	return max_pen >= 0.0 ? -max_pen : min_dist;
 }
 
+/// The same two queries for any link shape.  Boxes go through the functions above; a capsule or convex polytope walks the tree
+/// with its bounding box (conservative) and runs its own exact test on the triangles of the leaves it reaches.
+inline Obb geom_bounding_box(const Tf &shape_tf, const BoxGeom &g) {
+	if (g.kind == GEOM_CAPSULE) return Obb(shape_tf, {2 * g.radius, 2 * g.radius, g.length + 2 * g.radius});
+	if (g.kind == GEOM_CONVEX) {
+		Aabb bb;
+		for (auto &v: g.verts) bb.grow(v);
+		return Obb(then(shape_tf, Tf{(bb.lo + bb.hi) * 0.5, {0, 0, 0, 1}}), bb.hi - bb.lo);
+	}
+	return Obb(shape_tf, g.size);
+}
+/// Signed clearance of one shape/triangle pair (triangle given in the world frame); > 0 separated, <= 0 in contact.
+inline double geom_tri_clearance(const Tf &shape_tf, const BoxGeom &g, const std::array<V3, 3> &t) {
+	const Obb fr(shape_tf, g.kind == GEOM_BOX ? g.size : V3{0, 0, 0});
+	const V3 p0 = fr.to_local(t[0]), p1 = fr.to_local(t[1]), p2 = fr.to_local(t[2]);
+	if (g.kind == GEOM_CAPSULE) return capsule_tri_clearance(g.radius, g.length, p0, p1, p2);
+	if (g.kind == GEOM_CONVEX) return convex_tri_sat(g.verts, p0, p1, p2).sat_gap;
+	return box_tri_clearance(fr.h, p0, p1, p2);
+}
+inline bool geom_hits_scene(const Scene &s, const Tf &shape_tf, const BoxGeom &g, Counters *cnt = nullptr) {
+	if (g.kind == GEOM_BOX) return obb_hits_scene(s, Obb(shape_tf, g.size), cnt);
+	if (s.nodes.empty()) return false;
+	const Obb b = geom_bounding_box(shape_tf, g);
+	int stack[128];
+	int sp = 0;
+	stack[sp++] = 0;
+	while (sp) {
+		const Scene::Node &n = s.nodes[stack[--sp]];
+		if (cnt) cnt->nodes_visited++;
+		if (!b.may_touch(n.box, 0.0)) continue;
+		if (n.leaf) {
+			for (int i = 0; i < n.right; ++i) {
+				if (cnt) cnt->leaf_tests++;
+				if (geom_tri_clearance(shape_tf, g, s.tris[s.order[n.left + i]]) <= 0.0) return true;
+			}
+		} else {
+			stack[sp++] = n.right;
+			stack[sp++] = n.left;
+		}
+	}
+	return false;
+}
+inline double geom_scene_clearance(const Scene &s, const Tf &shape_tf, const BoxGeom &g, double reach) {
+	if (g.kind == GEOM_BOX) return obb_scene_clearance(s, Obb(shape_tf, g.size), reach);
+	double min_dist = reach, max_pen = -1.0;
+	if (s.nodes.empty()) return reach;
+	const Obb b = geom_bounding_box(shape_tf, g);
+	int stack[128];
+	int sp = 0;
+	stack[sp++] = 0;
+	while (sp) {
+		const Scene::Node &n = s.nodes[stack[--sp]];
+		if (!b.may_touch(n.box, reach)) continue;
+		if (n.leaf) {
+			for (int i = 0; i < n.right; ++i) {
+				const double cl = geom_tri_clearance(shape_tf, g, s.tris[s.order[n.left + i]]);
+				if (cl <= 0.0) max_pen = std::max(max_pen, -cl);
+				else min_dist = std::min(min_dist, cl);
+			}
+		} else {
+			stack[sp++] = n.right;
+			stack[sp++] = n.left;
+		}
+	}
+	return max_pen >= 0.0 ? -max_pen : min_dist;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // The four check_* loops: src/planning/collision_detection.cpp:16-122
 // ---------------------------------------------------------------------------------------------------------
 /// collision_detection.cpp:16-55 — every box of the link, world pose = link_tf.then(shape_tf), OR with early break.
 inline bool check_link_collision(const Link &link, const Scene &scene, const Tf &link_tf, Counters *cnt = nullptr) {
 	for (auto &g: link.boxes)
-		if (obb_hits_scene(scene, Obb(then(link_tf, g.tf), g.size), cnt)) return true;
+		if (geom_hits_scene(scene, then(link_tf, g.tf), g, cnt)) return true;
 	return false;
 }
 /// collision_detection.cpp:57-80 — FK from "flying_base", links in index order, early break.
@@ -578,7 +725,7 @@ inline double robot_clearance(const Robot &robot, const Scene &scene, const Stat
 	double best = reach;
 	for (size_t i = 0; i < fk.size(); ++i)
 		for (auto &g: robot.links[i].boxes)
-			best = std::min(best, obb_scene_clearance(scene, Obb(then(fk[i], g.tf), g.size), reach));
+			best = std::min(best, geom_scene_clearance(scene, then(fk[i], g.tf), g, reach));
 	return best;
 }
 

@@ -101,6 +101,16 @@ class Robot:
     def add_box(self, link: int, size, tf=(0, 0, 0, 0, 0, 0, 1)):
         lib().orc_robot_add_box(self.h, link, _d(_arr(size)), _d(_arr(tf)))
 
+    # link shapes the reference does not have; `other_shapes` records them for helpers.device_robot_from_oracle
+    def add_capsule(self, link: int, radius: float, length: float, tf=(0, 0, 0, 0, 0, 0, 1)):
+        lib().orc_robot_add_capsule(self.h, link, C.c_double(radius), C.c_double(length), _d(_arr(tf)))
+        self.__dict__.setdefault("other_shapes", []).append((link, (radius, radius, length), tuple(tf), 2, None))
+
+    def add_convex(self, link: int, verts, tf=(0, 0, 0, 0, 0, 0, 1)):
+        v = _arr(verts).reshape(-1, 3)
+        lib().orc_robot_add_convex(self.h, link, _d(v), len(v), _d(_arr(tf)))
+        self.__dict__.setdefault("other_shapes", []).append((link, (0.0, 0.0, 0.0), tuple(tf), 3, v.copy()))
+
     def add_joint(self, link_a, link_b, attach_a, attach_b, kind=FIXED, axis=(1, 0, 0), lo=0.0, hi=0.0) -> int:
         return lib().orc_robot_add_joint(self.h, link_a, link_b, _d(_arr(attach_a)), _d(_arr(attach_b)), kind,
                                          _d(_arr(axis)), C.c_double(lo), C.c_double(hi))
@@ -180,6 +190,14 @@ def tf_inverse(a):
 
 def motion_steps(d: float, max_step: float = 0.1) -> int:
     return int(lib().orc_motion_steps(C.c_double(d), C.c_double(max_step)))
+
+
+def shape_tri(kind, tf7, tri9, radius=0.0, length=0.0, verts=None):
+    """(hit, signed clearance) of one capsule (kind 1) or convex polytope (kind 2) against one triangle (world frame)."""
+    cl = C.c_double()
+    v = _arr(verts).reshape(-1, 3) if verts is not None else np.zeros((0, 3))
+    hit = lib().orc_shape_tri(kind, _d(_arr(tf7)), C.c_double(radius), C.c_double(length), _d(v), len(v), _d(_arr(tri9).reshape(-1)), C.byref(cl))
+    return bool(hit), cl.value
 
 
 def box_tri(tf7, size3, tri9):

@@ -51,6 +51,29 @@ int orc_robot_add_link(void *r, const char *name) { return ((Robot *) r)->add_li
 void orc_robot_add_box(void *r, int link, const double *size3, const double *tf7) {
 	((Robot *) r)->links[link].boxes.push_back({{size3[0], size3[1], size3[2]}, load_tf(tf7)});
 }
+/// Link shapes the reference does not have (capsule: fcl::Capsule's convention, axis along the shape's z; convex: hull of the points).
+void orc_robot_add_capsule(void *r, int link, double radius, double length, const double *tf7) {
+	BoxGeom g{{2 * radius, 2 * radius, length + 2 * radius}, load_tf(tf7)};
+	g.kind = GEOM_CAPSULE, g.radius = radius, g.length = length;
+	((Robot *) r)->links[link].boxes.push_back(g);
+}
+void orc_robot_add_convex(void *r, int link, const double *verts, int n, const double *tf7) {
+	BoxGeom g{{0, 0, 0}, load_tf(tf7)};
+	g.kind = GEOM_CONVEX;
+	for (int i = 0; i < n; ++i) g.verts.push_back({verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]});
+	((Robot *) r)->links[link].boxes.push_back(g);
+}
+/// One shape against one triangle (world frame): kind 1 = capsule (params radius, length), 2 = convex (verts); returns hit,
+/// *clearance = signed clearance.
+int orc_shape_tri(int kind, const double *tf7, double radius, double length, const double *verts, int n, const double *tri9, double *clearance) {
+	BoxGeom g{{0, 0, 0}, tf_identity()};
+	g.kind = kind, g.radius = radius, g.length = length;
+	for (int i = 0; i < n; ++i) g.verts.push_back({verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]});
+	std::array<V3, 3> t{V3{tri9[0], tri9[1], tri9[2]}, V3{tri9[3], tri9[4], tri9[5]}, V3{tri9[6], tri9[7], tri9[8]}};
+	const double cl = geom_tri_clearance(load_tf(tf7), g, t);
+	if (clearance) *clearance = cl;
+	return cl <= 0.0;
+}
 int orc_robot_add_joint(void *r, int link_a, int link_b, const double *attach_a7, const double *attach_b7, int kind,
 						const double *axis3, double min_angle, double max_angle) {
 	Joint j;
@@ -80,6 +103,7 @@ int orc_robot_describe(void *rp, double *boxes, int max_boxes, double *joints, i
 	int nb = 0;
 	for (size_t l = 0; l < r.links.size(); ++l)
 		for (auto &g: r.links[l].boxes) {
+			if (g.kind != GEOM_BOX) continue;  // capsules / convex links: the Python wrapper keeps its own record of what it added
 			if (nb < max_boxes) {
 				double *o = boxes + 11 * nb;
 				o[0] = (double) l, o[1] = g.size.x, o[2] = g.size.y, o[3] = g.size.z;

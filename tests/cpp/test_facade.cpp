@@ -771,6 +771,45 @@ int main() {
 		for (size_t r = 0; r < group.size(); ++r) std::printf(" %d", group.device(r));
 		std::printf("\n");
 	}
+	// -- capsule and convex-polytope links (this library's additions to the Shape variant) against the oracle's definitions ---------
+	{
+		using RM = robot_model::RobotModel;
+		const std::vector<math::Vec3d> wedge{{-0.08, -0.1, -0.05}, {0.08, -0.1, -0.05}, {0.08, 0.1, -0.05}, {-0.08, 0.1, -0.05}, {0.0, 0.12, 0.09}, {0.0, -0.06, 0.07}};
+		const math::Transformd lying{{0, 0, 0}, math::Quaterniond::fromAxisAngle({1, 0, 0}, M_PI / 2)};  // capsule axis along the link's y
+		RM shaped;
+		auto base = shaped.insertLink(RM::Link::namedBox("flying_base", {0.8, 0.8, 0.2}));
+		auto arm = shaped.insertLink({"stick", {}, {PositionedShape{Capsule{0.04, 0.7}, lying}}, {}});
+		auto ee = shaped.insertLink({"end_effector", {}, {PositionedShape::untransformed(ConvexMesh{wedge})}, {}});
+		shaped.insertJoint({"j0", math::Transformd{{0, 0.4, 0}, {0, 0, 0, 1}}, math::Transformd{{0, -0.4, 0}, {0, 0, 0, 1}}, base, arm, RM::RevoluteJoint{{1, 0, 0}, -1.5, 1.5}});
+		shaped.insertJoint({"j1", math::Transformd{{0, 0.4, 0}, {0, 0, 0, 1}}, math::Transformd{{0, 0, 0}, {0, 0, 0, 1}}, arm, ee, RM::RevoluteJoint{{0, 0, 1}, -1.0, 1.0}});
+		orc::Robot oshaped;
+		oshaped.add_link({"flying_base", {}, {orc::BoxGeom{{0.8, 0.8, 0.2}, orc::tf_identity()}}});
+		orc::BoxGeom cap{{0, 0, 0}, {{0, 0, 0}, {lying.orientation.x, lying.orientation.y, lying.orientation.z, lying.orientation.w}}};
+		cap.kind = orc::GEOM_CAPSULE, cap.radius = 0.04, cap.length = 0.7;
+		oshaped.add_link({"stick", {}, {cap}});
+		orc::BoxGeom cvx{{0, 0, 0}, orc::tf_identity()};
+		cvx.kind = orc::GEOM_CONVEX;
+		for (auto &v: wedge) cvx.verts.push_back({v.x(), v.y(), v.z()});
+		oshaped.add_link({"end_effector", {}, {cvx}});
+		orc::Joint j0, j1;
+		j0.attach_a = {{0, 0.4, 0}, {0, 0, 0, 1}}, j0.attach_b = {{0, -0.4, 0}, {0, 0, 0, 1}}, j0.link_a = 0, j0.link_b = 1, j0.kind = orc::REVOLUTE, j0.axis = {1, 0, 0}, j0.min_angle = -1.5, j0.max_angle = 1.5;
+		j1.attach_a = {{0, 0.4, 0}, {0, 0, 0, 1}}, j1.attach_b = {{0, 0, 0}, {0, 0, 0, 1}}, j1.link_a = 1, j1.link_b = 2, j1.kind = orc::REVOLUTE, j1.axis = {0, 0, 1}, j1.min_angle = -1.0, j1.max_angle = 1.0;
+		oshaped.add_joint(j0), oshaped.add_joint(j1);
+		random_numbers::RandomNumberGenerator rng(7);
+		std::vector<RobotState> states;
+		for (int i = 0; i < 8000; ++i) states.push_back(generateUniformRandomState(shaped, rng, 2.0, 3.0));
+		auto bits = check_states(shaped, scene, states);
+		size_t mismatch_outside = 0, hits = 0;
+		for (size_t i = 0; i < states.size(); ++i) {
+			const orc::State os = to_orc(states[i]);
+			const bool want = orc::check_robot_collision(oshaped, oscene, os);
+			hits += want;
+			if (bit(bits, i) != want && std::fabs(orc::robot_clearance(oshaped, oscene, os, 1e-3)) > 1e-6) ++mismatch_outside;
+		}
+		std::printf("capsule + convex links: %zu / %zu collide, mismatches outside band %zu\n", hits, states.size(), mismatch_outside);
+		CHECK(mismatch_outside == 0);
+		CHECK(hits > 300 && hits < 7700);
+	}
 	// -- error vocabulary -------------------------------------------------------------------------------------------------------
 	{
 		robot_model::RobotModel bad;
