@@ -658,7 +658,7 @@ int mgodpl_robot_create_ex(int32_t n_links, const mgodpl_shape_desc *shapes, int
 				}
 			double centre[3], shift[3];
 			for (int a = 0; a < 3; ++a) centre[a] = 0.5 * (lo[a] + hi[a]), b.half[a] = 0.5 * (hi[a] - lo[a]);
-			b.kind = SHAPE_KIND_CONVEX, b.data_off = (int32_t) rb->shape_data.size();
+			b.kind = SHAPE_KIND_CONVEX, b.data_off = (int16_t) rb->shape_data.size();
 			if (!build_hull(v, nv, centre, rb->shape_data)) return fail(MGODPL_E_UNSUPPORTED_SHAPE, "convex mesh link has no volume (flat or collinear vertices)");
 			hq_rot(tf.q, centre, shift);
 			for (int a = 0; a < 3; ++a) tf.t[a] += shift[a];

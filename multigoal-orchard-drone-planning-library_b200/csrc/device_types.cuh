@@ -104,9 +104,9 @@ struct BoxDev {
 	// ShapeKind (geometry.cuh).  A capsule or convex polytope travels as its bounding box (half, t, q: the tree descent and every
 	// fp32 cull are a box link's) and differs in the exact leaf test only: capsule radius = half[0], segment half length =
 	// half[2] - half[0]; a convex polytope's hull lives at RobotDev::shape_data + data_off (doubles).
-	int32_t kind;
-	int32_t data_off;
-	int32_t pad_;
+	// (16-bit fields in the struct's old padding word: its size — and with it the kernels' register allocation — stays what it was)
+	int16_t kind;
+	int16_t data_off;
 };
 
 struct RobotDev {

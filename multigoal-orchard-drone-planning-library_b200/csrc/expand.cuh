@@ -196,14 +196,32 @@ __device__ __forceinline__ bool make_goal_sample(const SceneDev &sc, const Robot
 	return !robot_out_of_reach(sc, rb, base.t);
 }
 
-/// Sink of the two-kernel path: the sharded box queue in HBM (emit_box's append, without its culls).  If the queue is full
-/// the box is traversed on the spot.
+/// Queue-overflow path of the sink below, out of line (rare; its cull box and traversal state stay out of the expansion kernels).
+__device__ __noinline__ void traverse_box_now(const SceneDev &sc, const RobotDev &rb, const Results &res, D3 c, Q4 q, unsigned owner, unsigned step,
+											  unsigned box, LocalCounters &lc) {
+	if (already_decided(res, owner, step)) return;
+	const BoxDev &bx = rb.boxes[box];
+	const CullBox cb = make_cull_box(sc, c, q, bx.half);
+	if (box_hits_scene(sc, cb, c, q, bx.half, lc, &bx, rb.shape_data)) report_hit(res, owner, step);
+}
+
+/// Sink of the two-kernel path: the sharded box queue in HBM (emit_box's append, without its culls).  A box that finds the
+/// queue full is traversed on the spot — but not from inside the FK loop: it is parked in `deferred` (local memory, touched on
+/// that path only) and the kernel calls flush() once the candidate is done, where nothing but loop counters is live.  (The call
+/// sat inside emit() before; the callee tree of the exact tests then shaped the register allocation of the whole expansion.)
+struct DeferredBox {
+	D3 c;
+	Q4 q;
+	unsigned owner, step, box;
+};
 struct QueueSink {
 	const SceneDev &sc;
 	const QueueDev &Q;
 	const Results &res;
 	const RobotDev &rb;
 	LocalCounters &lc;
+	DeferredBox *deferred;  // MGODPL_MAX_BOXES entries
+	int n_deferred;
 	__device__ __forceinline__ void emit(bool want, D3 c, Q4 q, unsigned owner, unsigned step, unsigned box) {
 		if (!want) return;
 		cg::coalesced_group g = cg::coalesced_threads();
@@ -217,10 +235,14 @@ struct QueueSink {
 			__stcg(dst + 1, make_double2(c.z, q.x));
 			__stcg(dst + 2, make_double2(q.y, q.z));
 			__stcg(dst + 3, make_double2(q.w, __hiloint2double((int) (step | box << 28), (int) owner)));
-		} else if (!already_decided(res, owner, step)) {
-			const CullBox cb = make_cull_box(sc, c, q, rb.boxes[box].half);
-			if (box_hits_scene(sc, cb, c, q, rb.boxes[box].half, lc, rb.boxes[box].kind, rb.shape_data + rb.boxes[box].data_off)) report_hit(res, owner, step);
+		} else {
+			deferred[n_deferred++] = DeferredBox{c, q, owner, step, box};
 		}
+	}
+	__device__ __forceinline__ void flush() {
+		if (n_deferred == 0) return;
+		for (int i = 0; i < n_deferred; ++i) traverse_box_now(sc, rb, res, deferred[i].c, deferred[i].q, deferred[i].owner, deferred[i].step, deferred[i].box, lc);
+		n_deferred = 0;
 	}
 };
 

@@ -114,7 +114,9 @@ __device__ __forceinline__ bool leaf_prefilter(const SceneDev &sc, const CullBox
 /// and test the triangles the pre-filter could not decide.  Rare and register-hungry (fp64): as a separate function its
 /// register demand does not shape the traversal loop.
 __device__ __noinline__ bool exact_leaf_test(const SceneDev &sc, const void *exact_pose, const double *half, int ref, unsigned unknown,
-											 unsigned *n_tests, int kind = SHAPE_KIND_BOX, const double *shape_data = nullptr) {
+											 unsigned *n_tests, const BoxDev *shape = nullptr, const double *shape_data_base = nullptr) {
+	const int kind = shape ? shape->kind : (int) SHAPE_KIND_BOX;
+	const double *shape_data = kind == SHAPE_KIND_CONVEX ? shape_data_base + shape->data_off : nullptr;
 	const unsigned info = (unsigned) (-1 - ref), first = info >> 4, cnt = (info & 15u) + 1u;
 	const double2 *ex = reinterpret_cast<const double2 *>(exact_pose);
 	const double2 e0 = __ldcg(ex), e1 = __ldcg(ex + 1), e2 = __ldcg(ex + 2), e3 = __ldcg(ex + 3);
@@ -218,7 +220,7 @@ __device__ __forceinline__ int visit_wide(const SceneDev &sc, const CullBox &cb,
 
 /// Exact test of the box against every triangle of one leaf reference.
 __device__ __forceinline__ bool leaf_hit(const SceneDev &sc, const CullBox &cb, const ExactBox &eb, int ref, LocalCounters &lc,
-										 int kind = SHAPE_KIND_BOX, const double *shape_data = nullptr) {
+										 int kind, const double *shape_data) {
 	const unsigned info = (unsigned) (-1 - ref), first = info >> 4, cnt = (info & 15u) + 1u;
 	unsigned unknown;
 	if (leaf_prefilter(sc, cb, ref, &unknown, kind == SHAPE_KIND_BOX)) return true;
@@ -232,8 +234,10 @@ __device__ __forceinline__ bool leaf_hit(const SceneDev &sc, const CullBox &cb, 
 
 /// Plain one-thread traversal (stage A's queue-overflow path): does the box touch any triangle of the scene?
 __device__ __noinline__ bool box_hits_scene(const SceneDev &sc, const CullBox &cb, D3 c, Q4 q, const double *half,
-											LocalCounters &lc, int kind = SHAPE_KIND_BOX, const double *shape_data = nullptr) {
+											LocalCounters &lc, const BoxDev *shape = nullptr, const double *shape_data_base = nullptr) {
 	if (!sc.n_nodes) return false;
+	const int kind = shape ? shape->kind : (int) SHAPE_KIND_BOX;
+	const double *shape_data = kind == SHAPE_KIND_CONVEX ? shape_data_base + shape->data_off : nullptr;
 	const ExactBox eb = make_exact_box(c, q, half);
 	int stack[STACK_DEPTH], cur = 0;
 	LocalStack st{stack, 0};
@@ -335,7 +339,7 @@ __device__ __forceinline__ void emit_box(const SceneDev &sc, const QueueDev &Q, 
 		__stcg(dst + 2, make_double2(q.y, q.z));
 		__stcg(dst + 3, make_double2(q.w, __hiloint2double((int) (step | box << 28), (int) owner)));
 	} else if (!already_decided(res, owner, step)) {
-		if (box_hits_scene(sc, cb, c, q, half, lc, spheres ? spheres->kind : SHAPE_KIND_BOX, shape_data)) report_hit(res, owner, step);
+		if (box_hits_scene(sc, cb, c, q, half, lc, spheres, shape_data)) report_hit(res, owner, step);
 	}
 }
 
@@ -373,7 +377,7 @@ __device__ __forceinline__ void emit_link_boxes(const SceneDev &sc, const RobotD
 	for (int bi = lo; bi < hi; ++bi) {
 		const BoxDev &bx = rb.boxes[bi];
 		const Pose w = bx.tf_identity ? link : then(link, D3{bx.t[0], bx.t[1], bx.t[2]}, Q4{bx.q[0], bx.q[1], bx.q[2], bx.q[3]}, false);
-		emit_box(sc, Q, res, w.t, w.q, bx.half, &bx, owner, step, (unsigned) bi, lc, rb.shape_data + bx.data_off);
+		emit_box(sc, Q, res, w.t, w.q, bx.half, &bx, owner, step, (unsigned) bi, lc, rb.shape_data);
 	}
 }
 __device__ __forceinline__ void expand_state(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
@@ -583,7 +587,8 @@ k_expand_states(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 	__shared__ unsigned s_counts[SHARDS];
 	load_shard_counts(s_counts, S.counts);
 	const unsigned n = min(slot_range(s_counts, S.cap), pass_hi);
-	QueueSink sink{sc, Q, res, rb, lc};
+	DeferredBox deferred[MGODPL_MAX_BOXES];
+	QueueSink sink{sc, Q, res, rb, lc, deferred, 0};
 	for (unsigned k = pass_lo + blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
 		if (!slot_filled(s_counts, k)) continue;
 		const unsigned i = __ldcg(&S.entries[k]).x;
@@ -593,6 +598,7 @@ k_expand_states(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 		for (int j = 0; j < 7; ++j) r7[j] = __ldg(r + j);
 		if (!finite7(r7)) continue;
 		expand_boxes<CHAIN, false>(sc, rb, sink, true, Pose{D3{r7[0], r7[1], r7[2]}, Q4{r7[3], r7[4], r7[5], r7[6]}}, JointsFromRow{r + 7}, i, 0u, 0, MGODPL_MAX_BOXES);
+		sink.flush();
 	}
 	flush_counters(sc, lc);
 }
@@ -621,7 +627,8 @@ k_expand_goals(const __grid_constant__ SceneDev sc, const __grid_constant__ Robo
 			   unsigned long long seed, double distance_from_target, double *__restrict__ states_out, size_t pass_lo, size_t pass_hi,
 			   QueueDev Q, Results res) {
 	LocalCounters lc;
-	QueueSink sink{sc, Q, res, rb, lc};
+	DeferredBox deferred[MGODPL_MAX_BOXES];
+	QueueSink sink{sc, Q, res, rb, lc, deferred, 0};
 	const size_t total = min(rows * per_row, pass_hi);
 	for (size_t i = pass_lo + (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
 		Pose base{};
@@ -629,6 +636,7 @@ k_expand_goals(const __grid_constant__ SceneDev sc, const __grid_constant__ Robo
 		unsigned owner = 0;
 		if (!make_goal_sample(sc, rb, targets, per_row, draws, seed, distance_from_target, states_out, i, base, jg, owner, lc)) continue;
 		expand_boxes<CHAIN, false>(sc, rb, sink, true, base, jg, owner, 0u, 0, MGODPL_MAX_BOXES);
+		sink.flush();
 	}
 	flush_counters(sc, lc);
 }
@@ -874,7 +882,8 @@ k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant
 	__shared__ unsigned s_counts[SHARDS];
 	load_shard_counts(s_counts, S.counts);
 	const unsigned n = min(slot_range(s_counts, S.cap), pass_hi);
-	QueueSink sink{sc, Q, res, rb, lc};
+	DeferredBox deferred[MGODPL_MAX_BOXES];
+	QueueSink sink{sc, Q, res, rb, lc, deferred, 0};
 	for (unsigned k = pass_lo + blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
 		if (!slot_filled(s_counts, k)) continue;
 		const uint2 e = __ldcg(&S.entries[k]);
@@ -884,6 +893,7 @@ k_expand_motion_steps(const __grid_constant__ SceneDev sc, const __grid_constant
 							  skip_decided ? res.first_step + e.x : nullptr, base, jl, lc))
 			continue;
 		expand_boxes<CHAIN, false>(sc, rb, sink, true, base, jl, e.x, e.y, 0, MGODPL_MAX_BOXES);
+		sink.flush();
 	}
 	flush_counters(sc, lc);
 }
@@ -995,21 +1005,22 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 					cur = REF_END;
 				} else {
 					unsigned unknown = 0xffffu;
-					const int kind = (explicit_boxes || rb.all_boxes) ? (int) SHAPE_KIND_BOX : rb.boxes[step_box >> 28].kind;
-					bool hit = tune.no_prefilter ? false : leaf_prefilter(sc, cb, cur, &unknown, kind == SHAPE_KIND_BOX);
+					const bool is_box = explicit_boxes || rb.all_boxes || rb.boxes[step_box >> 28].kind == SHAPE_KIND_BOX;
+					bool hit = tune.no_prefilter ? false : leaf_prefilter(sc, cb, cur, &unknown, is_box);
 					if (!hit && unknown) {
 						double half_buf[3];
-						const double *half, *shape_data = nullptr;
+						const double *half;
+						const BoxDev *shape = nullptr;
 						if (explicit_boxes) {
 							const double *bx = explicit_boxes + (size_t) owner * 10;
 							half_buf[0] = __ldg(bx + 7) * 0.5, half_buf[1] = __ldg(bx + 8) * 0.5, half_buf[2] = __ldg(bx + 9) * 0.5;
 							half = half_buf;
 						} else {
-							half = rb.boxes[step_box >> 28].half;
-							if (kind == SHAPE_KIND_CONVEX) shape_data = rb.shape_data + rb.boxes[step_box >> 28].data_off;
+							shape = &rb.boxes[step_box >> 28];
+							half = shape->half;
 						}
 						unsigned n_exact = 0;
-						hit = exact_leaf_test(sc, reinterpret_cast<const char *>(Q.items + item), half, cur, unknown, &n_exact, kind, shape_data);
+						hit = exact_leaf_test(sc, reinterpret_cast<const char *>(Q.items + item), half, cur, unknown, &n_exact, shape, rb.shape_data);
 						lc.leaf += n_exact;
 					}
 					if (hit) {
