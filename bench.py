@@ -39,8 +39,8 @@ TREE = dict(seed=42, trunk_triangles=50_000, leaf_triangles=150_000, n_fruit=500
 MAX_STEP = 0.1
 GATHER_EVERY = int(os.environ.get("MGODPL_BENCH_GATHER_EVERY", "4"))  # N > 1: result words of this many consecutive batches share one all-gather
 # our kernels inside the device-timed region, per step
-LAUNCHES_PER_STEP = 6
-KERNEL_NOTE = ("check_motions pipeline: k_motion_ranges + 2 x (k_expand_motion_steps + k_traverse) + k_finish_motions; k_traverse is the "
+LAUNCHES_PER_STEP = 7
+KERNEL_NOTE = ("check_motions pipeline: k_motion_ranges + k_expand_overflow_ranges (idle unless a work list ran full) + 2 x (k_expand_motion_steps + k_traverse) + k_finish_motions; k_traverse is the "
                "dominant kernel (see profiles/)")
 B_MOTION = 2 * 8 * (7 + 2) + 1 / 8 + 8      # two fp64 states in, 1 result bit + toi out = 152.125 B per motion
 B_SCENE_PER_TRIANGLE = 48 + 64              # 3 x float4 vertices + ~2 nodes x 32 B per triangle

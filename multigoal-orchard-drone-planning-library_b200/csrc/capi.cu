@@ -875,7 +875,7 @@ static size_t motion_survivors(size_t m) { return m * 64; }
 static size_t motion_scratch_bytes(size_t m, int n_boxes) {
 	// head and tail list hold m * 32 entries each; two list grains (4096 slots) of slack so that a pass (a whole number of grains)
 	// covers a whole list: no survivor-count read-back, the call never blocks the host
-	return query_scratch_bytes((m * 32 + 4096) * (size_t) n_boxes, motion_survivors(m));
+	return query_scratch_bytes((m * 32 + 4096) * (size_t) n_boxes, motion_survivors(m)) + motion_overflow_bytes(m);
 }
 
 int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, const double *d_a, const double *d_b, size_t m,

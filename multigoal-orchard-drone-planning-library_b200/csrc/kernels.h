@@ -12,6 +12,7 @@ constexpr size_t QUEUE_MAX_ITEMS = 32u << 20;
 /// Upper bound on survivor-list entries (8 B each) between the broad cull and FK expansion.
 constexpr size_t SURVIVOR_MAX_ENTRIES = 64u << 20;
 size_t query_scratch_bytes(size_t worst_case_boxes, size_t survivor_entries = 0);
+size_t motion_overflow_bytes(size_t m);
 size_t state_survivor_slots(size_t n);
 
 cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const double *d_states, size_t n, size_t stride,

@@ -681,8 +681,17 @@ __device__ __forceinline__ void expand_motion_step(const SceneDev &sc, const Rob
 	expand_state(sc, rb, Q, res, base, jv, motion, step, lc);
 }
 
-/// Overflow path of the motion survivor lists (a list ran full: badly skewed batches only), kept out of line so that its
-/// register demand and code do not shape k_motion_ranges: expand one interpolation step on the spot.
+/// Steps that found their survivor list full (badly skewed batches only): k_motion_ranges records them as ranges — the slots
+/// a warp writes for one motion and list ascend, so what does not fit is a suffix — and k_expand_overflow_ranges, a kernel of its
+/// own right behind it, expands them.  (The expansion used to be an out-of-line call inside k_motion_ranges; a call anywhere in
+/// that kernel cost it 330 bytes of spills and 13 of its 45 us on every batch, used or not.)
+struct OverflowRanges {
+	uint4 *entries;   // (motion, first step, count, -): at most one per motion and list
+	unsigned *count;
+	unsigned cap;
+};
+
+/// Expand one interpolation step on the spot (out of line: rare paths only).
 __device__ __noinline__ void expand_motion_step_now(const SceneDev &sc, const RobotDev &rb, const QueueDev &Q, const Results &res,
 													const double *A, const double *B, unsigned n_steps, const SlerpConst *slerp_k, unsigned motion, unsigned step) {
 	LocalCounters lc;
@@ -700,7 +709,7 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 				const double *__restrict__ b, size_t m, size_t stride, int js, double max_step,
 				const uint32_t *__restrict__ n_steps_override, uint32_t *__restrict__ n_steps_out,
 				uint32_t *__restrict__ uncertain_bits, SlerpConst *__restrict__ slerp_out, SurvivorsDev S, SurvivorsDev S_tail,
-				unsigned head_steps, int trim, QueueDev Q, Results res) {
+				OverflowRanges O, unsigned head_steps, int trim, Results res) {
 	const unsigned lane = threadIdx.x & 31;
 	LocalCounters lc;
 	unsigned long long n_uncertain = 0, n_motions = 0;
@@ -849,16 +858,24 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 				const int src = __ffs(todo) - 1;
 				todo &= todo - 1;
 				const unsigned lo = __shfl_sync(0xffffffffu, s_lo, src), lh = __shfl_sync(0xffffffffu, l_head, src);
-				const unsigned mot = (unsigned) (i - lane + src), ns = __shfl_sync(0xffffffffu, n_steps, src);
+				const unsigned mot = (unsigned) (i - lane + src);
 				const unsigned cnts[2] = {lh, __shfl_sync(0xffffffffu, l_tail, src)};
 				const unsigned bases[2] = {__shfl_sync(0xffffffffu, base_h, src), __shfl_sync(0xffffffffu, base_t, src)};
 				for (int part = 0; part < 2; ++part) {
 					const SurvivorsDev &L = part ? S_tail : S;
 					const unsigned first = part ? lh : 0u;
+					unsigned k_full = cnts[part];  // first entry of this lane's share that found the list full
 					for (unsigned k = lane; k < cnts[part]; k += 32) {
-						const unsigned pos = shard_slot(shard, bases[part] + k), step = lo + first + k;
-						if (pos < L.cap) L.entries[pos] = make_uint2(mot, step);
-						else expand_motion_step_now(sc, rb, Q, res, a + (size_t) mot * stride, b + (size_t) mot * stride, ns, slerp_out + mot, mot, step);
+						const unsigned pos = shard_slot(shard, bases[part] + k);
+						if (pos < L.cap) L.entries[pos] = make_uint2(mot, lo + first + k);
+						else k_full = min(k_full, k);
+					}
+					if (__any_sync(0xffffffffu, k_full < cnts[part])) {  // list full: hand the rest of the range to k_expand_overflow_ranges
+						k_full = __reduce_min_sync(0xffffffffu, k_full);
+						if (lane == 0) {
+							const unsigned at = atomicAdd(O.count, 1u);
+							if (at < O.cap) O.entries[at] = make_uint4(mot, lo + first + k_full, cnts[part] - k_full, 0u);
+						}
 					}
 				}
 			}
@@ -868,6 +885,22 @@ k_motion_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ Rob
 	if (sc.counters) {
 		if (n_motions) atomicAdd(sc.counters + CNT_MOTIONS, n_motions);
 		if (n_uncertain) atomicAdd(sc.counters + CNT_UNCERTAIN, n_uncertain);
+	}
+}
+
+/// The ranges k_motion_ranges could not list (see OverflowRanges): one warp per range, expanded on the spot.  Launched behind
+/// every k_motion_ranges; without overflow it reads one counter and exits.
+__global__ void __launch_bounds__(128)
+k_expand_overflow_ranges(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev rb, const double *__restrict__ a,
+						 const double *__restrict__ b, size_t stride, const uint32_t *__restrict__ n_steps, const SlerpConst *__restrict__ slerp_k,
+						 OverflowRanges O, QueueDev Q, Results res) {
+	const unsigned n = min(__ldcg(O.count), O.cap);
+	if (!n) return;
+	const unsigned lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+	for (unsigned t = warp; t < n; t += n_warps) {
+		const uint4 e = __ldcg(O.entries + t);
+		for (unsigned k = lane; k < e.z; k += 32)
+			expand_motion_step_now(sc, rb, Q, res, a + (size_t) e.x * stride, b + (size_t) e.x * stride, __ldg(n_steps + e.x), slerp_k + e.x, e.x, e.y + k);
 	}
 }
 
@@ -1146,6 +1179,9 @@ size_t state_survivor_slots(size_t n) { return n + n / 4 + SHARDS * SHARD_BLOCK;
 static size_t queue_max_items() { return knobs().queue_max_items; }
 static size_t survivor_max_entries() { return knobs().survivor_max_entries; }
 
+/// Room for one overflow-range record per motion and list (launch_check_motions carves it off the end of its scratch).
+size_t motion_overflow_bytes(size_t m) { return ((2 * m + 64) * sizeof(uint4) + 255) & ~(size_t) 255; }
+
 size_t query_scratch_bytes(size_t worst_case_boxes, size_t survivor_entries) {
 	if (knobs().pipeline == 1) worst_case_boxes = 0;  // the fused kernel keeps its boxes in shared memory: no queue in HBM
 	size_t cap = worst_case_boxes < queue_max_items() ? worst_case_boxes : queue_max_items();
@@ -1351,16 +1387,23 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	QueueDev Q;
 	const unsigned head_arg = knobs().head_steps;  // 0: adaptive per motion
 	const int trim = knobs().trim;
+	// the overflow-range records sit behind the queue: [header][survivor lists][queue items][overflow ranges]
+	const size_t over_bytes = motion_overflow_bytes(m);
+	if (scratch_bytes < over_bytes + SCRATCH_HEADER) return cudaErrorInvalidValue;
+	scratch_bytes -= over_bytes;
 	carve(scratch, scratch_bytes, survivor_entries, &S, &Q, &S_tail, m * (size_t) (head_arg ? head_arg : 48u));
+	const OverflowRanges O{reinterpret_cast<uint4 *>(reinterpret_cast<char *>(scratch) + scratch_bytes), Q.cursor + 16, (unsigned) (2 * m + 64)};
 	Results res{RESULT_FIRST_STEP, nullptr, d_first_step};
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	if (pipeline_mode(rb) == 1) Q.cap = 0;
 	if (knobs().ranges_variant == 1)  // one wave for 100 k motions: 6 blocks x 4 warps per SM at <= 85 registers
 		k_motion_ranges<128, 6><<<grid_for(m, 128, 6), 128, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override, d_n_steps, d_uncertain,
-																		  (SlerpConst *) d_slerp, S, S_tail, head_arg, trim, Q, res);
+																		  (SlerpConst *) d_slerp, S, S_tail, O, head_arg, trim, res);
 	else
 		k_motion_ranges<BLOCK_A, 2><<<grid_for(m, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override, d_n_steps, d_uncertain,
-																					  (SlerpConst *) d_slerp, S, S_tail, head_arg, trim, Q, res);
+																					  (SlerpConst *) d_slerp, S, S_tail, O, head_arg, trim, res);
+	LQ_CHECK(cudaGetLastError());
+	k_expand_overflow_ranges<<<(unsigned) sm_count() * 2, 128, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const SlerpConst *) d_slerp, O, Q, res);
 	LQ_CHECK(cudaGetLastError());
 	if (pipeline_mode(rb) == 1) {
 		// one launch walks the head list, then the tail list: by the time a warp reaches a motion's tail steps, the head steps of
