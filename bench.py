@@ -326,11 +326,12 @@ def run_ours(args):
     # what this implementation actually has to touch once per launch: the same inputs/outputs + the step-count array, its own
     # traversal records and both triangle copies (mgodpl_scene_info.traversal_bytes) and the clearance grid
     own_bytes = m * (B_MOTION + 4) + int(info.traversal_bytes) + int(info.clearance_cells)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, traffic_kept = None, None, {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
             traffic, traffic_src = tj.get("k_check_motions_dram_bytes_per_launch"), tj.get("source")
+            traffic_kept = tj.get("l2_kept_between_kernels", {})
     except Exception:
         pass
     line = {
@@ -349,6 +350,8 @@ def run_ours(args):
         "gpu_launches": LAUNCHES_PER_STEP * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
+                     # the same step with L2 contents kept between its kernels (as in the timed run): what really comes from DRAM
+                     "traffic_reads_l2_kept_between_kernels": traffic_kept.get("dram_bytes_read_per_step"),
                      "kernel": KERNEL_NOTE,
                      "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_bytes": "152.125 B x motions + 112 B x triangles (SURVEY 8d)",
                      "own_accounting_bytes_per_launch": own_bytes, "own_accounting_frac": own_bytes / (np.mean(step_ms) * 1e-3) / 1e9 / peak},

@@ -1403,7 +1403,7 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 		k_motion_ranges<BLOCK_A, 2><<<grid_for(m, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, m, stride, js, max_step, d_override, d_n_steps, d_uncertain,
 																					  (SlerpConst *) d_slerp, S, S_tail, O, head_arg, trim, res);
 	LQ_CHECK(cudaGetLastError());
-	k_expand_overflow_ranges<<<(unsigned) sm_count() * 2, 128, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const SlerpConst *) d_slerp, O, Q, res);
+	k_expand_overflow_ranges<<<(unsigned) sm_count(), 128, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const SlerpConst *) d_slerp, O, Q, res);
 	LQ_CHECK(cudaGetLastError());
 	if (pipeline_mode(rb) == 1) {
 		// one launch walks the head list, then the tail list: by the time a warp reaches a motion's tail steps, the head steps of
