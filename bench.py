@@ -437,6 +437,8 @@ def orchard_strong_scaling(mg, torch, dist, dev, stream, rank, world, steps=6):
         pad_s = (pad_s + 1) // 2 * 2  # keep the fp64 toi block 8-byte aligned
         return sb, mb, pad_s, pad_m, pad_mw
 
+    launch_modes = []
+
     def run(w, r, gather):
         """Time `steps` batches on shard r of w; returns (ms per batch, the gathered staging buffers of the last batch, plan, n_steps)."""
         sb, mb, pad_s, pad_m, pad_mw = plan(w)
@@ -450,21 +452,50 @@ def orchard_strong_scaling(mg, torch, dist, dev, stream, rank, world, steps=6):
         d_states, a_sh, b_sh = st[slo:shi], d_ma[mlo:mhi], d_mb[mlo:mhi]
         pending = [None, None]
 
-        def batch(k):
-            buf = local[k & 1]
+        def kernels(buf):
             d_sw, d_mw, d_toi = buf[:pad_s], buf[pad_s:pad_s + pad_mw], buf[pad_s + pad_mw:].view(torch.float64)
-            if pending[k & 1] is not None:
-                pending[k & 1].wait()  # the gather that last read this staging buffer (two batches ago)
-                pending[k & 1] = None
             # the state half and the motion half of a batch are independent: they run on two streams (a small shard is bound by
             # the latency of its few launches, not by throughput), joined before the results travel
-            side.wait_stream(torch.cuda.current_stream())
+            cur = torch.cuda.current_stream()
+            side.wait_stream(cur)
             if shi > slo:
                 with torch.cuda.stream(side):
                     mg.capi.check_states_device(oscene, robot, d_states, shi - slo, 9, 2, d_sw, stream=side.cuda_stream)
             if mhi > mlo:
-                mg.capi.check_motions_device(oscene, robot, a_sh, b_sh, mhi - mlo, 9, 2, d_mw, MAX_STEP, d_toi, d_steps, stream=stream)
-            torch.cuda.current_stream().wait_stream(side)
+                mg.capi.check_motions_device(oscene, robot, a_sh, b_sh, mhi - mlo, 9, 2, d_mw, MAX_STEP, d_toi, d_steps, stream=cur.cuda_stream)
+            cur.wait_stream(side)
+
+        # both library calls of a batch (neither blocks the host nor allocates once its scratch exists) are captured into one CUDA
+        # graph per staging buffer and replayed; plain launches if the capture fails (e.g. a batch so large that it needs the
+        # survivor-count read-back)
+        graphs = [None, None]
+        try:
+            # (a shard whose worst case exceeds the library's 2^25-item box queue reads a survivor count back mid-call: not capturable)
+            if ((mhi - mlo) * 32 + 4096) * 4 > 2 ** 25 or (shi - slo) * 4 > 2 ** 25:
+                raise RuntimeError("shard too large to capture")
+            cap = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(cap):
+                kernels(local[0])
+            torch.cuda.synchronize()
+            for i in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
+                    kernels(local[i])
+                graphs[i] = g
+            torch.cuda.synchronize()
+        except Exception:
+            torch.cuda.synchronize()
+            graphs = [None, None]
+
+        def batch(k):
+            buf = local[k & 1]
+            if pending[k & 1] is not None:
+                pending[k & 1].wait()  # the gather that last read this staging buffer (two batches ago)
+                pending[k & 1] = None
+            if graphs[k & 1] is not None:
+                graphs[k & 1].replay()
+            else:
+                kernels(buf)
             if gather:
                 pending[k & 1] = dist.all_gather_into_tensor(everyone[k & 1], buf, async_op=True)
 
@@ -491,6 +522,7 @@ def orchard_strong_scaling(mg, torch, dist, dev, stream, rank, world, steps=6):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         last = (steps - 1) & 1
         full = everyone[last].view(w, words_total) if gather else local[last].view(1, words_total)
+        launch_modes.append("graph replay" if graphs[0] is not None else "plain launches")
         return float(ms.item()), full, (sb, mb, pad_s, pad_m, pad_mw), d_steps
 
     ms_n, full, (sb, mb, pad_s, pad_m, pad_mw), _ = run(world, rank, world > 1)
@@ -506,7 +538,7 @@ def orchard_strong_scaling(mg, torch, dist, dev, stream, rank, world, steps=6):
                        "one fixed batch sharded over the GPUs, scene replicated",
            "scaling": "strong", "n_gpus": world, "steps": steps, "triangles": int(oinfo.n_triangles), "scene_bytes": int(oinfo.device_bytes),
            "scene_build_ms": oinfo.build_ms, "clearance_grid_build_ms": oinfo.clearance_build_ms,
-           "ms_per_batch": ms_n, "states_per_sec": n / (ms_n * 1e-3), "motions_per_sec": mm / (ms_n * 1e-3),
+           "launch_mode": launch_modes[0], "ms_per_batch": ms_n, "states_per_sec": n / (ms_n * 1e-3), "motions_per_sec": mm / (ms_n * 1e-3),
            "state_collision_rate": float(s_hit.mean()), "motion_collision_rate": float(m_hit.mean()),
            "gathered_bytes_per_rank": int(4 * (pad_s + pad_mw + 2 * pad_m)),
            "motion_shards": {"balanced_by": "predicted ceil(d/0.1)+1 per motion", "sizes": [hi - lo for lo, hi in mb],
