@@ -940,12 +940,13 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	Carver c;
 	// Large batches are cut into chunks.  All input copies go through one copy stream, back to back (the PCIe link carries input
 	// from the first microsecond to the last byte); chunk k's kernels and result copies run on a stream of their own that waits for
-	// "chunk k has arrived" only, so the kernels of the early chunks hide behind the input copies of the later ones.  Two chunks
-	// measure best for 100 k motions (0.74 ms; 1: 0.85, 4: 1.2): a chunk's kernels have a latency floor of ~0.15 ms however small
-	// it is, and concurrent chunks share the SMs.  Chunk boundaries are multiples of 32: result words never straddle.
+	// "chunk k has arrived" only, so the kernels of the early chunks hide behind the input copies of the later ones.  Three chunks
+	// measure best for 100 k motions (0.58 ms; 1: 0.70, 2: 0.59, 4: 0.58, 6: 0.7): a chunk's kernels have a latency floor of
+	// ~0.15 ms however small it is, and concurrent chunks share the SMs.  Chunk boundaries are multiples of 32: result words never
+	// straddle.
 	static const size_t chunk_pref = [] {
 		const char *e = getenv("MGODPL_E2E_CHUNKS");
-		return e && atoi(e) > 0 ? std::min((size_t) atoi(e), Workspace::MAX_CHUNKS) : (size_t) 2;
+		return e && atoi(e) > 0 ? std::min((size_t) atoi(e), Workspace::MAX_CHUNKS) : (size_t) 3;
 	}();
 	const bool use_side = m >= 32768;  // large batches run on the workspace's own non-blocking streams, in chunk_pref chunks
 	const size_t n_chunks = use_side ? chunk_pref : 1;
