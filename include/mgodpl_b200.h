@@ -218,7 +218,9 @@ int mgodpl_knn_query(const double *database, size_t n_database, const double *qu
  *      n_vertices, source-major (distance_lookup[i][v], tsp_over_prm.h:90-97) — bit-identical to Dijkstra's labels, DBL_MAX
  *      where unreachable (boost's default infinity); pred (optional): same shape, the vertex before v on a shortest path,
  *      v itself for the source and for unreachable vertices.  Where several neighbours tie exactly, the one nearer the
- *      source, then the lower index, is reported (boost reports whichever its heap relaxed first).  sweeps_out (optional):
+ *      source, then the lower index, is reported (boost reports whichever its heap relaxed first).  With positive weights
+ *      the predecessors form a tree; three or more distinct vertices joined by ZERO-weight edges sit at the same distance and
+ *      may name each other (distances stay exact) — bound any walk over `pred` by n_vertices, as the facade does.  sweeps_out (optional):
  *      label-correcting sweeps enqueued.  The _device variant takes the graph in CSR form (row_offsets: n_vertices + 1,
  *      neighbours / weights: both directions of every edge) in device memory and synchronises the stream before returning. */
 int mgodpl_roadmap_shortest_paths(uint32_t n_vertices, const uint32_t *edges, const double *weights, size_t n_edges,

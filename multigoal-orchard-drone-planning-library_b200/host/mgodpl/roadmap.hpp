@@ -70,7 +70,10 @@ inline std::pair<std::vector<double>, std::vector<PRMGraph::vertex_descriptor>> 
 inline RobotPath retrace_path(const PRMGraph &graph, const std::vector<PRMGraph::vertex_descriptor> &predecessor_lookup,
 							  PRMGraph::vertex_descriptor goal_node) {
 	RobotPath path;
-	for (auto cur = goal_node; predecessor_lookup[cur] != cur; cur = predecessor_lookup[cur]) path.states.push_back(graph[cur]);
+	// (a predecessor map is a tree for positive edge weights; zero-weight edges between distinct vertices can tie — the walk is
+	// bounded by the vertex count so that such a map cannot hang the caller)
+	size_t guard = predecessor_lookup.size();
+	for (auto cur = goal_node; predecessor_lookup[cur] != cur && guard-- > 0; cur = predecessor_lookup[cur]) path.states.push_back(graph[cur]);
 	std::reverse(path.states.begin(), path.states.end());
 	return path;
 }
