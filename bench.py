@@ -375,14 +375,15 @@ def run_ours(args):
             "traversal_bytes_per_reference_state": rec_bytes * c["nodes_visited"] / (states_all / world),
             "traversal_bytes_per_box": rec_bytes * c["nodes_visited"] / max(c["boxes_traversed"], 1),
             "note": "L1/L2-level bytes (record size x records visited); ncu L2 hit rate, FMA-pipe and issue utilisation per kernel "
-                    "are in profiles/r01_ncu_full_final_motion_pipeline.txt"}
+                    "are in profiles/r02_final_ncu_full_motion_step.txt"}
         del cscene
     except Exception as e:  # never at the cost of the headline line
         line["secondary"] = {"error": repr(e)}
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(mesh, a, b, use_ref=False)
-        # one host thread: how a single reference call executes (collision_detection.cpp:57-105 is sequential)
-        line["cpu_baseline_1thread"] = cpu_baseline(mesh, a, b, use_ref=False, budget_s=6.0, cores=1)
+        if world == 1:  # the CPU baseline is timed on rank 0 at N = 1 only
+            line["cpu_baseline"] = cpu_baseline(mesh, a, b, use_ref=False)
+            # one host thread: how a single reference call executes (collision_detection.cpp:57-105 is sequential)
+            line["cpu_baseline_1thread"] = cpu_baseline(mesh, a, b, use_ref=False, budget_s=6.0, cores=1)
         try:
             line["parity"] = parity_sample(mesh, a, b, hit)
         except Exception as e:
@@ -390,7 +391,7 @@ def run_ours(args):
     if strong is not None:
         line["strong_scaling"] = strong
     if not args.no_extra:
-        line["extra"] = extra_workloads(mg, torch, scene, tree, dev, stream, cpu_leg=not args.no_cpu_baseline)
+        line["extra"] = extra_workloads(mg, torch, scene, tree, dev, stream, cpu_leg=not args.no_cpu_baseline and world == 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -614,6 +615,34 @@ def extra_workloads(mg, torch, scene, tree, dev, stream, cpu_leg=True):
         ms = e0.elapsed_time(e1) / 3
         out[name] = {"states_per_sec": n / (ms * 1e-3), "ms": ms, "hbm_frac": n * 72.125 / (ms * 1e-3) / 1e9 / peaks()[0],
                      "collision_rate": float(mg.capi.unpack_bits(d_hit.cpu().numpy().view(np.uint32), n).mean())}
+    # ---- the same 10 M states with a capsule arm and a convex-polytope end effector (north_star (3): link shapes beside boxes;
+    #      the reference has no such shapes, so this line has no CPU leg) --------------------------------------------------------
+    try:
+        shaped = mg.robots.RobotModel()
+        base = shaped.insert_link("flying_base", (0.8, 0.8, 0.2))
+        arm = shaped.insert_link("stick")
+        s45 = float(np.sin(np.pi / 4))
+        shaped.add_capsule(arm, 0.035, 0.93, (0.0, 0.0, 0.0, s45, 0.0, 0.0, s45))  # axis along the link's y, like the reference's 1 m stick
+        ee = shaped.insert_link("end_effector")
+        shaped.add_convex_mesh(ee, [[-0.08, -0.1, -0.05], [0.08, -0.1, -0.05], [0.08, 0.1, -0.05], [-0.08, 0.1, -0.05], [0.0, 0.12, 0.09], [0.0, -0.06, 0.07]])
+        ident = mg.capi.IDENTITY_TF
+        shaped.insert_joint(base, arm, (0, 0.4, 0, 0, 0, 0, 1), (0, -0.5, 0, 0, 0, 0, 1), mg.capi.JOINT_REVOLUTE, (1.0, 0.0, 0.0), -np.pi / 2, np.pi / 2)
+        shaped.insert_joint(arm, ee, (0, 0.5, 0, 0, 0, 0, 1), ident, mg.capi.JOINT_REVOLUTE, (0.0, 0.0, 1.0), -np.pi / 2, np.pi / 2)
+        srobot = shaped.to_device()
+        for _ in range(2):
+            mg.capi.check_states_device(scene, srobot, st, n, 9, 2, d_hit, stream=stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            mg.capi.check_states_device(scene, srobot, st, n, 9, 2, d_hit, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out["states_10M_capsule_arm_convex_end_effector"] = {
+            "states_per_sec": n / (ms * 1e-3), "ms": ms, "collision_rate": float(mg.capi.unpack_bits(d_hit.cpu().numpy().view(np.uint32), n).mean()),
+            "note": "box base + capsule arm (r 0.035, l 0.93) + 6-vertex convex end effector, two revolute joints; same states as the line above"}
+    except Exception as e:
+        out["states_10M_capsule_arm_convex_end_effector"] = {"error": repr(e)}
     # ---- config 1 as BASELINE.json words it: ONE call with 10 000 states (host buffers in, booleans out) — launch-latency scale ----
     st10k = mg.robots.generate_uniform_random_states(model, mg.robots.Mt19937(42), 10_000, h, float(lo[2] + 1.0))
     for _ in range(3):

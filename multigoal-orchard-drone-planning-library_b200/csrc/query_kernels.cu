@@ -110,6 +110,44 @@ __device__ __forceinline__ bool leaf_prefilter(const SceneDev &sc, const CullBox
 	return false;
 }
 
+/// The same for a capsule / convex link (`cb` is the shape's bounding box), out of line so that box robots pay nothing for it.
+/// "Certainly separated" carries over from the bounding box; "certainly hit" needs a test of its own — a triangle vertex inside
+/// the shape shrunk by the margin: within radius of the capsule's axis segment, or behind every face plane of the polytope.
+/// (Without it every contact went to the fp64 test at one active lane: 10 M states took 2.7 ms instead of 0.57 for boxes.)
+__device__ __noinline__ bool leaf_prefilter_shape(const SceneDev &sc, const CullBox &cb, int ref, unsigned *unknown, const BoxDev *shape,
+												 const double *shape_data_base) {
+	const unsigned info = (unsigned) (-1 - ref), first = info >> 4, cnt = (info & 15u) + 1u;
+	const float slack = 2.f * sc.margin + 1e-5f;
+	const bool capsule = shape->kind == SHAPE_KIND_CAPSULE;
+	// capsule: true radius = inflated hx - margin, the axis segment reaches +- (hz - hx) along the local z axis
+	const float rad = cb.hx - sc.margin - slack, half_len = cb.hz - cb.hx;
+	const double *hull = capsule ? nullptr : shape_data_base + shape->data_off;
+	const int n_faces = capsule ? 0 : (int) __ldg(hull + 1);
+	const double *faces = capsule ? nullptr : hull + 4 + 3 * (int) __ldg(hull);
+	*unknown = 0;
+	for (unsigned k = 0; k < cnt; ++k) {
+		const float4 *t = sc.tris32 + 3ull * (first + k);
+		const float4 v[3] = {__ldg(t), __ldg(t + 1), __ldg(t + 2)};
+		if (tri_classify(cb, sc.margin, v[0], v[1], v[2]) == TRI_SEPARATED) continue;
+		bool inside = false;
+		for (int c = 0; c < 3 && !inside; ++c) {
+			const float dx = v[c].x - cb.cx, dy = v[c].y - cb.cy, dz = v[c].z - cb.cz;
+			const float px = cb.r[0] * dx + cb.r[3] * dy + cb.r[6] * dz, py = cb.r[1] * dx + cb.r[4] * dy + cb.r[7] * dz, pz = cb.r[2] * dx + cb.r[5] * dy + cb.r[8] * dz;
+			if (capsule) {
+				const float ez = pz - fminf(fmaxf(pz, -half_len), half_len);
+				inside = rad > 0.f && px * px + py * py + ez * ez < rad * rad;
+			} else {
+				inside = true;
+				for (int f = 0; f < n_faces && inside; ++f)
+					inside = (float) __ldg(faces + 4 * f) * px + (float) __ldg(faces + 4 * f + 1) * py + (float) __ldg(faces + 4 * f + 2) * pz < (float) __ldg(faces + 4 * f + 3) - slack;
+			}
+		}
+		if (inside) return true;
+		*unknown |= 1u << k;
+	}
+	return false;
+}
+
 /// The exact phase of one parked lane, kept out of line: re-read the fp64 pose of the queued box, build the exact box
 /// and test the triangles the pre-filter could not decide.  Rare and register-hungry (fp64): as a separate function its
 /// register demand does not shape the traversal loop.
@@ -223,7 +261,7 @@ __device__ __forceinline__ bool leaf_hit(const SceneDev &sc, const CullBox &cb, 
 										 int kind, const double *shape_data) {
 	const unsigned info = (unsigned) (-1 - ref), first = info >> 4, cnt = (info & 15u) + 1u;
 	unsigned unknown;
-	if (leaf_prefilter(sc, cb, ref, &unknown, kind == SHAPE_KIND_BOX)) return true;
+	if (leaf_prefilter(sc, cb, ref, &unknown, kind == SHAPE_KIND_BOX)) return true;  // (overflow path: non-box shapes go straight to the exact test)
 	for (unsigned k = 0; k < cnt; ++k) {
 		if (!(unknown >> k & 1u)) continue;
 		lc.leaf++;
@@ -1039,7 +1077,8 @@ k_traverse(const __grid_constant__ SceneDev sc, const __grid_constant__ RobotDev
 				} else {
 					unsigned unknown = 0xffffu;
 					const bool is_box = explicit_boxes || rb.all_boxes || rb.boxes[step_box >> 28].kind == SHAPE_KIND_BOX;
-					bool hit = tune.no_prefilter ? false : leaf_prefilter(sc, cb, cur, &unknown, is_box);
+					bool hit = false;
+					if (!tune.no_prefilter) hit = is_box ? leaf_prefilter(sc, cb, cur, &unknown) : leaf_prefilter_shape(sc, cb, cur, &unknown, &rb.boxes[step_box >> 28], rb.shape_data);
 					if (!hit && unknown) {
 						double half_buf[3];
 						const double *half;
