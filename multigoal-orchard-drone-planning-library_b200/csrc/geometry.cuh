@@ -317,6 +317,82 @@ static __device__ __noinline__ bool capsule_triangle_hit(const ExactBox &b, doub
 	return v >= 0.0 && u >= 0.0 && v + u <= 1.0;
 }
 
+// ---- the same distance in fp32, as a pre-filter (the exact test above decides what this cannot) -----------------------------
+struct V3f {
+	float x, y, z;
+};
+__device__ __forceinline__ V3f operator+(V3f a, V3f b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ V3f operator-(V3f a, V3f b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3f operator*(V3f a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ float dot(V3f a, V3f b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3f cross(V3f a, V3f b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+
+__device__ __forceinline__ float segment_segment_dist2_f(V3f p1, V3f q1, V3f p2, V3f q2) {
+	const V3f d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+	const float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), c = dot(d1, r), b = dot(d1, d2);
+	float s = 0.f, t = 0.f;
+	if (a > 1e-20f && e > 1e-20f) {
+		const float den = a * e - b * b;
+		s = den > 1e-6f * a * e ? clamp01((b * f - c * e) / den) : 0.f;
+		t = (b * s + f) / e;
+		if (t < 0.f) t = 0.f, s = clamp01(-c / a);
+		else if (t > 1.f) t = 1.f, s = clamp01((b - c) / a);
+	} else if (a > 1e-20f) {
+		s = clamp01(-c / a);
+	} else if (e > 1e-20f) {
+		t = clamp01(f / e);
+	}
+	const V3f dd = (p1 + d1 * s) - (p2 + d2 * t);
+	return dot(dd, dd);  // the distance between two points ON the segments: never below the true minimum by more than rounding
+}
+__device__ __forceinline__ float point_triangle_dist2_f(V3f p, V3f a, V3f b, V3f c) {
+	const V3f ab = b - a, ac = c - a, ap = p - a;
+	const float d1 = dot(ab, ap), d2 = dot(ac, ap);
+	V3f cl = a;
+	do {
+		if (d1 <= 0.f && d2 <= 0.f) break;
+		const V3f bp = p - b;
+		const float d3 = dot(ab, bp), d4 = dot(ac, bp);
+		if (d3 >= 0.f && d4 <= d3) { cl = b; break; }
+		const float vc = d1 * d4 - d3 * d2;
+		if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) { cl = a + ab * (d1 / (d1 - d3)); break; }
+		const V3f cp = p - c;
+		const float d5 = dot(ab, cp), d6 = dot(ac, cp);
+		if (d6 >= 0.f && d5 <= d6) { cl = c; break; }
+		const float vb = d5 * d2 - d1 * d6;
+		if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) { cl = a + ac * (d2 / (d2 - d6)); break; }
+		const float va = d3 * d6 - d5 * d4;
+		if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) { cl = b + (c - b) * ((d4 - d3) / ((d4 - d3) + (d5 - d6))); break; }
+		const float den = va + vb + vc;
+		if (fabsf(den) > 0.f) cl = a + ab * (vb / den) + ac * (vc / den);
+	} while (false);
+	const V3f d = p - cl;
+	return dot(d, d);
+}
+
+/// fp32 verdict for a capsule (axis (0, 0, -+half_len) of the frame the triangle is given in, radius `rad`) against a triangle.
+/// Every candidate distance below is measured between a point of the segment and a point of the triangle, so the smallest of
+/// them can only OVERestimate the true distance: "smallest < rad - slack" is a certain hit.  "Certainly separated" needs the
+/// true minimum, which the candidates attain unless the segment pierces the triangle's interior — that case is told apart by
+/// the plane-side test, and left to the exact test whenever it is not clear-cut.  `slack` covers the fp32 error of the inputs.
+__device__ __forceinline__ int capsule_triangle_classify(float rad, float half_len, float slack, V3f p0, V3f p1, V3f p2) {
+	const V3f s0{0.f, 0.f, -half_len}, s1{0.f, 0.f, half_len};
+	float best = fminf(point_triangle_dist2_f(s0, p0, p1, p2), point_triangle_dist2_f(s1, p0, p1, p2));
+	best = fminf(best, fminf(segment_segment_dist2_f(s0, s1, p0, p1), fminf(segment_segment_dist2_f(s0, s1, p1, p2), segment_segment_dist2_f(s0, s1, p2, p0))));
+	const float d = sqrtf(best), tol = slack + 1e-5f * (d + rad);
+	if (d < rad - tol) return TRI_HIT;
+	if (!(d > rad + tol)) return TRI_UNKNOWN;
+	// far by every candidate: separated unless the axis passes through the triangle.  Both end points strictly on one side of the
+	// plane (by more than the tolerance, measured along the unit normal) rule that out.
+	const V3f n = cross(p1 - p0, p2 - p0);
+	const float nn = dot(n, n);
+	if (!(nn > 1e-20f)) return TRI_SEPARATED;  // no area: its edges were measured
+	const float inv = rsqrtf(nn), h0 = dot(n, s0 - p0) * inv, h1 = dot(n, s1 - p0) * inv;
+	if ((h0 > tol && h1 > tol) || (h0 < -tol && h1 < -tol)) return TRI_SEPARATED;
+	return TRI_UNKNOWN;
+}
+
 /// Convex polytope vs closed triangle, separating-axis test in the shape frame.  `data` (mgodpl_robot_create_ex lays it out):
 /// [n_verts, n_faces, n_edges, -] [verts: 3 each] [faces: outward unit normal + support value, 4 each] [edge directions: 3 each].
 /// Axes: the polytope's face normals, the triangle normal, edge x edge.  Touching counts as contact; numerically null axes

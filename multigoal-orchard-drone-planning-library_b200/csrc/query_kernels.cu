@@ -111,8 +111,9 @@ __device__ __forceinline__ bool leaf_prefilter(const SceneDev &sc, const CullBox
 }
 
 /// The same for a capsule / convex link (`cb` is the shape's bounding box), out of line so that box robots pay nothing for it.
-/// "Certainly separated" carries over from the bounding box; "certainly hit" needs a test of its own — a triangle vertex inside
-/// the shape shrunk by the margin: within radius of the capsule's axis segment, or behind every face plane of the polytope.
+/// "Certainly separated" carries over from the bounding box; beyond that a capsule gets an fp32 copy of its exact test (the
+/// axis-segment / triangle distance against the radius, with error bars: capsule_triangle_classify), a polytope a "certain
+/// hit" when a triangle vertex lies behind every face plane shrunk by the margin.
 /// (Without it every contact went to the fp64 test at one active lane: 10 M states took 2.7 ms instead of 0.57 for boxes.)
 __device__ __noinline__ bool leaf_prefilter_shape(const SceneDev &sc, const CullBox &cb, int ref, unsigned *unknown, const BoxDev *shape,
 												 const double *shape_data_base) {
@@ -120,7 +121,7 @@ __device__ __noinline__ bool leaf_prefilter_shape(const SceneDev &sc, const Cull
 	const float slack = 2.f * sc.margin + 1e-5f;
 	const bool capsule = shape->kind == SHAPE_KIND_CAPSULE;
 	// capsule: true radius = inflated hx - margin, the axis segment reaches +- (hz - hx) along the local z axis
-	const float rad = cb.hx - sc.margin - slack, half_len = cb.hz - cb.hx;
+	const float half_len = cb.hz - cb.hx;
 	const double *hull = capsule ? nullptr : shape_data_base + shape->data_off;
 	const int n_faces = capsule ? 0 : (int) __ldg(hull + 1);
 	const double *faces = capsule ? nullptr : hull + 4 + 3 * (int) __ldg(hull);
@@ -130,17 +131,34 @@ __device__ __noinline__ bool leaf_prefilter_shape(const SceneDev &sc, const Cull
 		const float4 v[3] = {__ldg(t), __ldg(t + 1), __ldg(t + 2)};
 		if (tri_classify(cb, sc.margin, v[0], v[1], v[2]) == TRI_SEPARATED) continue;
 		bool inside = false;
-		for (int c = 0; c < 3 && !inside; ++c) {
-			const float dx = v[c].x - cb.cx, dy = v[c].y - cb.cy, dz = v[c].z - cb.cz;
-			const float px = cb.r[0] * dx + cb.r[3] * dy + cb.r[6] * dz, py = cb.r[1] * dx + cb.r[4] * dy + cb.r[7] * dz, pz = cb.r[2] * dx + cb.r[5] * dy + cb.r[8] * dz;
-			if (capsule) {
-				const float ez = pz - fminf(fmaxf(pz, -half_len), half_len);
-				inside = rad > 0.f && px * px + py * py + ez * ez < rad * rad;
-			} else {
-				inside = true;
-				for (int f = 0; f < n_faces && inside; ++f)
-					inside = (float) __ldg(faces + 4 * f) * px + (float) __ldg(faces + 4 * f + 1) * py + (float) __ldg(faces + 4 * f + 2) * pz < (float) __ldg(faces + 4 * f + 3) - slack;
+		if (capsule) {
+			V3f p[3];
+#pragma unroll
+			for (int c = 0; c < 3; ++c) {
+				const float dx = v[c].x - cb.cx, dy = v[c].y - cb.cy, dz = v[c].z - cb.cz;
+				p[c] = V3f{cb.r[0] * dx + cb.r[3] * dy + cb.r[6] * dz, cb.r[1] * dx + cb.r[4] * dy + cb.r[7] * dz, cb.r[2] * dx + cb.r[5] * dy + cb.r[8] * dz};
 			}
+			const int verdict = capsule_triangle_classify(cb.hx - sc.margin, half_len, slack, p[0], p[1], p[2]);
+			if (verdict == TRI_SEPARATED) continue;
+			inside = verdict == TRI_HIT;
+		} else {
+			// polytope: one pass over its face planes settles both easy cases — all three vertices beyond one plane (separated), or
+			// one vertex behind every plane (hit); everything else goes to the exact test
+			float px[3], py[3], pz[3];
+#pragma unroll
+			for (int c = 0; c < 3; ++c) {
+				const float dx = v[c].x - cb.cx, dy = v[c].y - cb.cy, dz = v[c].z - cb.cz;
+				px[c] = cb.r[0] * dx + cb.r[3] * dy + cb.r[6] * dz, py[c] = cb.r[1] * dx + cb.r[4] * dy + cb.r[7] * dz, pz[c] = cb.r[2] * dx + cb.r[5] * dy + cb.r[8] * dz;
+			}
+			bool in0 = true, in1 = true, in2 = true, separated = false;
+			for (int f = 0; f < n_faces && !separated; ++f) {
+				const float nx = (float) __ldg(faces + 4 * f), ny = (float) __ldg(faces + 4 * f + 1), nz = (float) __ldg(faces + 4 * f + 2), off = (float) __ldg(faces + 4 * f + 3);
+				const float s0 = nx * px[0] + ny * py[0] + nz * pz[0] - off, s1 = nx * px[1] + ny * py[1] + nz * pz[1] - off, s2 = nx * px[2] + ny * py[2] + nz * pz[2] - off;
+				separated = fminf(s0, fminf(s1, s2)) > slack;
+				in0 &= s0 < -slack, in1 &= s1 < -slack, in2 &= s2 < -slack;
+			}
+			if (separated) continue;
+			inside = in0 | in1 | in2;
 		}
 		if (inside) return true;
 		*unknown |= 1u << k;
