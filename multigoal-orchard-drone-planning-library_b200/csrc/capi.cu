@@ -201,6 +201,19 @@ struct mgodpl_scene {
 	struct StreamSlot {
 		std::mutex mu;
 		Workspace ws;
+		MotionOverlap overlap;  // created on first use (motion batches): see launch_check_motions
+		cudaError_t overlap_streams() {
+			if (overlap.side) return cudaSuccess;
+			cudaError_t e = cudaStreamCreateWithFlags(&overlap.side, cudaStreamNonBlocking);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&overlap.ev_head, cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&overlap.ev_tail, cudaEventDisableTiming);
+			return e;
+		}
+		~StreamSlot() {
+			if (overlap.side) cudaStreamDestroy(overlap.side);
+			if (overlap.ev_head) cudaEventDestroy(overlap.ev_head);
+			if (overlap.ev_tail) cudaEventDestroy(overlap.ev_tail);
+		}
 	};
 	std::mutex stream_mu;
 	std::map<cudaStream_t, std::unique_ptr<StreamSlot>> stream_ws;
@@ -891,16 +904,17 @@ int mgodpl_check_motions_device(mgodpl_scene *scene, const mgodpl_robot *robot, 
 	if (!m) return MGODPL_OK;
 	cudaStream_t stream = (cudaStream_t) stream_;
 	Carver c;
-	const size_t qb = motion_scratch_bytes(m, robot->dev.n_boxes);
+	const size_t qb = motion_scratch_bytes(m, robot->dev.n_boxes) + motion_tail_queue_bytes(m, robot->dev.n_boxes);
 	size_t o_first = c.take(m * 4), o_steps = c.take(d_n_steps ? 0 : m * 4), o_slerp = c.take(m * 32), o_q = c.take(qb);
 	auto &slot = scene->stream_slot(stream);
 	std::lock_guard<std::mutex> enqueue(slot.mu);
 	CU(slot.ws.reserve(c.off, 0));
+	CU(slot.overlap_streams());
 	char *scratch = slot.ws.dev;
 	ROBOT_ON_SCENE_DEVICE(rdev);
 	CU(launch_check_motions(scene->dev, rdev, d_a, d_b, m, stride, js, max_step, d_override, d_hit_bits, d_toi,
 							d_n_steps ? d_n_steps : (uint32_t *) (scratch + o_steps), d_uncertain, (unsigned *) (scratch + o_first),
-							scratch + o_slerp, scratch + o_q, qb, motion_survivors(m), stream));
+							scratch + o_slerp, scratch + o_q, qb, motion_survivors(m), stream, &slot.overlap));
 	return MGODPL_OK;
 }
 

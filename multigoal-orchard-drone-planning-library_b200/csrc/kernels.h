@@ -13,6 +13,13 @@ constexpr size_t QUEUE_MAX_ITEMS = 32u << 20;
 constexpr size_t SURVIVOR_MAX_ENTRIES = 64u << 20;
 size_t query_scratch_bytes(size_t worst_case_boxes, size_t survivor_entries = 0);
 size_t motion_overflow_bytes(size_t m);
+size_t motion_tail_queue_bytes(size_t m, int n_boxes);
+/// What lets launch_check_motions overlap its two rounds (see there): a side stream and two events, owned by the caller's
+/// per-stream slot.
+struct MotionOverlap {
+	cudaStream_t side = nullptr;
+	cudaEvent_t ev_head = nullptr, ev_tail = nullptr;
+};
 size_t state_survivor_slots(size_t n);
 
 cudaError_t launch_check_states(const SceneDev &sc, const RobotDev &rb, const double *d_states, size_t n, size_t stride,
@@ -24,7 +31,7 @@ cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t
 cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const double *d_a, const double *d_b, size_t m,
 								 size_t stride, int js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,
 								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned *d_first_step, void *d_slerp,
-								 void *scratch, size_t scratch_bytes, size_t survivor_entries, cudaStream_t stream);
+								 void *scratch, size_t scratch_bytes, size_t survivor_entries, cudaStream_t stream, const MotionOverlap *overlap = nullptr);
 cudaError_t launch_sample_goals(const SceneDev &sc, const RobotDev &rb, const double *d_targets, size_t f,
 								const double *d_draws, size_t s, unsigned long long seed,
 								double distance_from_target, uint32_t *d_hit_bits, uint32_t *d_collisions,

@@ -1198,7 +1198,7 @@ static int sm_count() {  // of the current device (a process may drive several)
 
 /// Environment knobs, read once (thread-safe: function-local static of a struct initialised by one expression).
 struct Knobs {
-	int pipeline, pipe_refill_min, pipe_leaf_min, pipe_blocks, pipe_claim, cull_bulk, ranges_variant, no_prefilter, traverse_blocks, refill_min, leaf_min, trim;
+	int overlap, pipeline, pipe_refill_min, pipe_leaf_min, pipe_blocks, pipe_claim, cull_bulk, ranges_variant, no_prefilter, traverse_blocks, refill_min, leaf_min, trim;
 	unsigned head_steps;
 	size_t queue_max_items, survivor_max_entries;
 	static int geti(const char *name, int dflt) {
@@ -1210,7 +1210,7 @@ struct Knobs {
 		return e && atoll(e) > 0 ? (size_t) atoll(e) : dflt;
 	}
 	Knobs()
-		: pipeline(geti("MGODPL_PIPELINE", 0)), pipe_refill_min(geti("MGODPL_PIPE_REFILL_MIN", 8)), pipe_leaf_min(geti("MGODPL_PIPE_LEAF_MIN", 32)), pipe_blocks(geti("MGODPL_PIPE_BLOCKS", 4)), pipe_claim(geti("MGODPL_PIPE_CLAIM", 0)), cull_bulk(geti("MGODPL_CULL_BULK", 0)), ranges_variant(geti("MGODPL_RANGES_VARIANT", 1)),
+		: overlap(geti("MGODPL_OVERLAP", 1)), pipeline(geti("MGODPL_PIPELINE", 0)), pipe_refill_min(geti("MGODPL_PIPE_REFILL_MIN", 8)), pipe_leaf_min(geti("MGODPL_PIPE_LEAF_MIN", 32)), pipe_blocks(geti("MGODPL_PIPE_BLOCKS", 4)), pipe_claim(geti("MGODPL_PIPE_CLAIM", 0)), cull_bulk(geti("MGODPL_CULL_BULK", 0)), ranges_variant(geti("MGODPL_RANGES_VARIANT", 1)),
 		  no_prefilter(geti("MGODPL_NO_PREFILTER", 0)), traverse_blocks(geti("MGODPL_TRAVERSE_BLOCKS", 4)), refill_min(geti("MGODPL_REFILL_MIN", 16)),
 		  leaf_min(geti("MGODPL_LEAF_MIN", 8)), trim(geti("MGODPL_TRIM", 16)),
 		  head_steps(geti("MGODPL_HEAD_STEPS", 0) > 0 ? (unsigned) geti("MGODPL_HEAD_STEPS", 0) : 0u),
@@ -1235,6 +1235,9 @@ size_t state_survivor_slots(size_t n) { return n + n / 4 + SHARDS * SHARD_BLOCK;
 /// this to drive every query through the inline overflow paths).
 static size_t queue_max_items() { return knobs().queue_max_items; }
 static size_t survivor_max_entries() { return knobs().survivor_max_entries; }
+
+/// Room for the tail round's own queue (8 boxes per motion; launch_check_motions carves it off the end of its scratch).
+size_t motion_tail_queue_bytes(size_t m, int n_boxes) { return QUEUE_HEADER + (8 * m + 4096) * (size_t) std::max(n_boxes, 1) * sizeof(Item); }
 
 /// Room for one overflow-range record per motion and list (launch_check_motions carves it off the end of its scratch).
 size_t motion_overflow_bytes(size_t m) { return ((2 * m + 64) * sizeof(uint4) + 255) & ~(size_t) 255; }
@@ -1438,10 +1441,23 @@ cudaError_t launch_check_boxes(const SceneDev &sc, const double *d_boxes, size_t
 cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const double *d_a, const double *d_b, size_t m,
 								 size_t stride, int js, double max_step, const uint32_t *d_override, uint32_t *d_hit_bits,
 								 double *d_toi, uint32_t *d_n_steps, uint32_t *d_uncertain, unsigned *d_first_step, void *d_slerp,
-								 void *scratch, size_t scratch_bytes, size_t survivor_entries, cudaStream_t stream) {
+								 void *scratch, size_t scratch_bytes, size_t survivor_entries, cudaStream_t stream, const MotionOverlap *overlap) {
 	if (!m) return cudaSuccess;
 	SurvivorsDev S, S_tail;
 	QueueDev Q;
+	// (optional) a second, smaller queue for the tail round at the very end of the scratch: with it the tail expansion does not have
+	// to wait for the head traversal to hand the queue back
+	QueueDev Q2{};
+	if (overlap && knobs().overlap) {
+		const size_t tail_bytes = motion_tail_queue_bytes(m, rb.n_boxes);
+		if (scratch_bytes > tail_bytes + SCRATCH_HEADER) {
+			scratch_bytes -= tail_bytes;
+			char *p = reinterpret_cast<char *>(scratch) + scratch_bytes;
+			Q2.counts = reinterpret_cast<unsigned *>(p), Q2.cursor = Q2.counts + SHARDS * COUNTER_STRIDE;
+			Q2.items = reinterpret_cast<Item *>(p + QUEUE_HEADER);
+			Q2.cap = (unsigned) std::min<size_t>((tail_bytes - QUEUE_HEADER) / sizeof(Item), queue_max_items());
+		}
+	}
 	const unsigned head_arg = knobs().head_steps;  // 0: adaptive per motion
 	const int trim = knobs().trim;
 	// the overflow-range records sit behind the queue: [header][survivor lists][queue items][overflow ranges]
@@ -1451,6 +1467,13 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	carve(scratch, scratch_bytes, survivor_entries, &S, &Q, &S_tail, m * (size_t) (head_arg ? head_arg : 48u));
 	const OverflowRanges O{reinterpret_cast<uint4 *>(reinterpret_cast<char *>(scratch) + scratch_bytes), Q.cursor + 16, (unsigned) (2 * m + 64)};
 	Results res{RESULT_FIRST_STEP, nullptr, d_first_step};
+	// Overlapped rounds (see below) pay off when the launches are being recorded into a CUDA graph, where a cross-stream
+	// dependency is an edge; between plain launches each one costs several microseconds and the overlap loses (0.291 -> 0.313 ms
+	// per 100 k motions, against 0.277 -> 0.258 ms replayed).  MGODPL_OVERLAP=2 forces it on, 0 off.
+	const size_t R_all = pass_size(Q, rb.n_boxes);
+	cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+	if (Q2.items) LQ_CHECK(cudaStreamIsCapturing(stream, &capturing));
+	const bool overlapped = Q2.items && pipeline_mode(rb) == 0 && S.cap <= R_all && (capturing == cudaStreamCaptureStatusActive || knobs().overlap == 2);
 	LQ_CHECK(cudaMemsetAsync(Q.counts, 0, SCRATCH_HEADER, stream));
 	if (pipeline_mode(rb) == 1) Q.cap = 0;
 	if (knobs().ranges_variant == 1)  // one wave for 100 k motions: 6 blocks x 4 warps per SM at <= 85 registers
@@ -1479,23 +1502,47 @@ cudaError_t launch_check_motions(const SceneDev &sc, const RobotDev &rb, const d
 	bool first_pass = true;
 	const SurvivorsDev lists[2] = {S, S_tail};
 	size_t ends[2] = {S.cap, S_tail.cap};
-	if (ends[0] > R || ends[1] > R) LQ_CHECK(survivor_slot_ranges(lists, 2, stream, ends));
-	for (int part = 0; part < 2; ++part) {
-		const SurvivorsDev &L = lists[part];
-		const size_t end = ends[part];
-		for (size_t lo = 0; lo < end; lo += R) {
-			const size_t hi = lo + R < end ? lo + R : end;
-			// the first pass shares the queue with stage A1's own overflow path (a survivor list that ran full expands inline)
-			if (!first_pass) LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
-			first_pass = false;
-			if (rb.chain)
-				k_expand_motion_steps<true><<<grid_for(hi - lo, BLOCK_C, 5), BLOCK_C, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const SlerpConst *) d_slerp, L,
-																									(unsigned) lo, (unsigned) hi, part, Q, res);
-			else
-				k_expand_motion_steps<false><<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, stream>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const SlerpConst *) d_slerp, L,
-																									 (unsigned) lo, (unsigned) hi, part, Q, res);
-			LQ_CHECK(cudaGetLastError());
-			LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (hi - lo) * (size_t) rb.n_boxes, stream));
+	auto expand = [&](const SurvivorsDev &L, size_t lo, size_t hi, int part, const QueueDev &q, cudaStream_t st) {
+		if (rb.chain)
+			k_expand_motion_steps<true><<<grid_for(hi - lo, BLOCK_C, 5), BLOCK_C, 0, st>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const SlerpConst *) d_slerp, L,
+																						   (unsigned) lo, (unsigned) hi, part, q, res);
+		else
+			k_expand_motion_steps<false><<<grid_for(hi - lo, BLOCK_A, 2), BLOCK_A, 0, st>>>(sc, rb, d_a, d_b, stride, d_n_steps, (const SlerpConst *) d_slerp, L,
+																							(unsigned) lo, (unsigned) hi, part, q, res);
+		return cudaGetLastError();
+	};
+	if (overlapped) {
+		// Overlapped rounds (batches whose head list fits one pass).  The tail expansion runs on a side stream that waits for the
+		// head expansion only.  The head traversal follows the head expansion on the caller's stream, so it is runnable first and
+		// its persistent blocks fill every SM; the tail expansion's blocks — runnable a cross-stream hop later — get on as those
+		// retire, i.e. during the traversal's drawn-out end, when most first hits are known and the "already collided" skip works
+		// almost as well as after the kernel boundary.  A tail step expanded too early costs its FK, never a wrong answer: the
+		// traversal re-checks the first hit before it walks a box.  The tail queue is small (8 boxes per motion); what does not
+		// fit is traversed by its producer, as everywhere.  (Measured alternatives: the traversal on a high-priority side stream
+		// instead — the tail expansion then starts FIRST and expands every tail step blind: the orchard shard went 0.77 -> 1.14 ms;
+		// the whole pipeline on a high-priority stream — right order, but four cross-stream hops cost plain launches 8 %.)
+		LQ_CHECK(cudaMemsetAsync(Q2.counts, 0, QUEUE_HEADER, stream));
+		LQ_CHECK(expand(S, 0, ends[0], 0, Q, stream));
+		LQ_CHECK(cudaEventRecord(overlap->ev_head, stream));
+		LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, ends[0] * (size_t) rb.n_boxes, stream));
+		LQ_CHECK(cudaStreamWaitEvent(overlap->side, overlap->ev_head, 0));
+		LQ_CHECK(expand(S_tail, 0, ends[1], 1, Q2, overlap->side));
+		LQ_CHECK(cudaEventRecord(overlap->ev_tail, overlap->side));
+		LQ_CHECK(cudaStreamWaitEvent(stream, overlap->ev_tail, 0));
+		LQ_CHECK(run_traverse(sc, rb, nullptr, Q2, res, ends[1] * (size_t) rb.n_boxes, stream));
+	} else {
+		if (ends[0] > R || ends[1] > R) LQ_CHECK(survivor_slot_ranges(lists, 2, stream, ends));
+		for (int part = 0; part < 2; ++part) {
+			const SurvivorsDev &L = lists[part];
+			const size_t end = ends[part];
+			for (size_t lo = 0; lo < end; lo += R) {
+				const size_t hi = lo + R < end ? lo + R : end;
+				// the first pass shares the queue with stage A1's own overflow path (a survivor list that ran full expands inline)
+				if (!first_pass) LQ_CHECK(cudaMemsetAsync(Q.counts, 0, QUEUE_HEADER, stream));
+				first_pass = false;
+				LQ_CHECK(expand(L, lo, hi, part, Q, stream));
+				LQ_CHECK(run_traverse(sc, rb, nullptr, Q, res, (hi - lo) * (size_t) rb.n_boxes, stream));
+			}
 		}
 	}
 	k_finish_motions<<<(unsigned) ((m + 255) / 256), 256, 0, stream>>>(d_first_step, d_n_steps, m, d_hit_bits, d_toi);
