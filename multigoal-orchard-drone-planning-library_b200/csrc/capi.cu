@@ -974,8 +974,15 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	size_t o_q[Workspace::MAX_CHUNKS];  // chunks run concurrently: a work queue each
 	for (size_t ci = 0; ci < n_chunks; ++ci) o_q[ci] = c.take(qb);
 	const size_t qb_all = c.off - o_q[0];  // (the rare whole-batch re-run uses the chunks' queues as one)
-	CU(ws->reserve(c.off, host_hi - out_lo));
-	char *D = ws->dev, *H = ws->host - out_lo;  // host staging mirrors the device layout from out_lo onwards
+	// a chunk's results — hit words, boundary-case words, step counts, toi — sit in one block, so that they come back in ONE copy
+	auto up = [](size_t x) { return (x + 255) & ~(size_t) 255; };
+	const size_t cw = (chunk_m + 31) / 32;
+	const size_t b_unc = up(cw * 4), b_steps = b_unc + up(cw * 4), b_toi = b_steps + up(chunk_m * 4), b_size = b_toi + (toi ? up(chunk_m * 8) : 0);
+	size_t o_blk[Workspace::MAX_CHUNKS];
+	for (size_t ci = 0; ci < n_chunks; ++ci) o_blk[ci] = c.take(b_size);
+	CU(ws->reserve(c.off, (host_hi - out_lo) + n_chunks * b_size));
+	char *D = ws->dev, *H = ws->host - out_lo;  // host staging mirrors the device layout from out_lo onwards (whole-batch re-run) ...
+	char *HB = ws->host + (host_hi - out_lo);    // ... followed by the chunks' result blocks
 	if (use_side) {
 		CU(ws->side_streams());
 		CU(cudaEventRecord(ws->ev_start, stream));
@@ -1012,15 +1019,13 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 			if (trace) CU(cudaEventRecord(tev[ci][1], s));
 		}
 		if (trace && use_side && ci < 2) CU(cudaEventRecord(tev[ci][1], s));  // (kernels start here: after the chunk has arrived)
+		char *blk = D + o_blk[ci];
 		CU(launch_check_motions(scene->dev, rdev, (const double *) (D + o_a) + lo * stride, (const double *) (D + o_b) + lo * stride, mc,
-								stride, js, max_step, nullptr, (uint32_t *) (D + o_hit) + w_lo, toi ? (double *) (D + o_toi) + lo : nullptr,
-								(uint32_t *) (D + o_steps) + lo, (uint32_t *) (D + o_unc) + w_lo, (unsigned *) (D + o_first) + lo,
+								stride, js, max_step, nullptr, (uint32_t *) blk, toi ? (double *) (blk + b_toi) : nullptr,
+								(uint32_t *) (blk + b_steps), (uint32_t *) (blk + b_unc), (unsigned *) (D + o_first) + lo,
 								D + o_slerp + lo * 32, D + o_q[ci], qb, motion_survivors(mc), s));
 		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][2], s));
-		CU(cudaMemcpyAsync(H + o_hit + w_lo * 4, D + o_hit + w_lo * 4, w_n * 4, cudaMemcpyDeviceToHost, s));
-		CU(cudaMemcpyAsync(H + o_unc + w_lo * 4, D + o_unc + w_lo * 4, w_n * 4, cudaMemcpyDeviceToHost, s));
-		CU(cudaMemcpyAsync(H + o_steps + lo * 4, D + o_steps + lo * 4, mc * 4, cudaMemcpyDeviceToHost, s));
-		if (toi) CU(cudaMemcpyAsync(H + o_toi + lo * 8, D + o_toi + lo * 8, mc * 8, cudaMemcpyDeviceToHost, s));
+		CU(cudaMemcpyAsync(HB + ci * b_size, blk, b_size, cudaMemcpyDeviceToHost, s));
 		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][3], s));
 		if (use_side) {
 			CU(cudaEventRecord(ws->ev_chunk[ci], s));
@@ -1030,38 +1035,40 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	const auto t_enqueued = now();
 	// Step-count fix-up: the device libm may differ from the host's by an ulp, which only matters when distance /
 	// max_step sits on an integer boundary.  Re-derive those on the host and re-run if any count disagrees.
-	uint32_t *h_unc = (uint32_t *) (H + o_unc), *h_steps = (uint32_t *) (H + o_steps), *h_ovr = (uint32_t *) (H + o_ovr);
+	uint32_t *h_steps = (uint32_t *) (H + o_steps), *h_ovr = (uint32_t *) (H + o_ovr);
 	size_t n_fix = 0;
-	// Results of motions [lo, hi) are in pinned memory: look for step counts to fix up and hand the range to the caller.
-	auto deliver = [&](size_t lo, size_t hi) {
-		const size_t w_lo = lo / 32, w_hi = (hi + 31) / 32;
-		for (size_t w = w_lo; w < w_hi; ++w) {
-			uint32_t bits = h_unc[w];
+	// Results of chunk ci = motions [lo, hi) are in pinned memory: look for step counts to fix up and hand the range to the caller.
+	auto deliver = [&](size_t ci, size_t lo, size_t hi) {
+		const char *hb = HB + ci * b_size;
+		const uint32_t *c_hit = (const uint32_t *) hb, *c_unc = (const uint32_t *) (hb + b_unc), *c_steps = (const uint32_t *) (hb + b_steps);
+		const size_t w_lo = lo / 32, w_n = (hi - lo + 31) / 32;
+		for (size_t w = 0; w < w_n; ++w) {
+			uint32_t bits = c_unc[w];
 			while (bits) {
 				int k = __builtin_ctz(bits);
 				bits &= bits - 1;
-				size_t i = w * 32 + k;
+				size_t i = lo + w * 32 + k;
 				uint32_t want = host_n_steps(a + i * stride, b + i * stride, js, max_step);
-				if (want != h_steps[i]) {
+				if (want != c_steps[i - lo]) {
 					if (!n_fix) memset(h_ovr, 0xff, m * 4);
 					h_ovr[i] = want;
 					++n_fix;
 				}
 			}
 		}
-		memcpy(hit_bits + w_lo, H + o_hit + w_lo * 4, (w_hi - w_lo) * 4);
-		if (toi) memcpy(toi + lo, H + o_toi + lo * 8, (hi - lo) * 8);
-		if (n_steps_out) memcpy(n_steps_out + lo, h_steps + lo, (hi - lo) * 4);
+		memcpy(hit_bits + w_lo, c_hit, w_n * 4);
+		if (toi) memcpy(toi + lo, hb + b_toi, (hi - lo) * 8);
+		if (n_steps_out) memcpy(n_steps_out + lo, c_steps, (hi - lo) * 4);
 	};
 	if (use_side) {
 		// a chunk's results are handed over while the chunks behind it are still on the GPU
 		for (size_t ci = 0; ci < n_chunks && ci * chunk_m < m; ++ci) {
 			CU(cudaEventSynchronize(ws->ev_chunk[ci]));
-			deliver(ci * chunk_m, std::min(m, (ci + 1) * chunk_m));
+			deliver(ci, ci * chunk_m, std::min(m, (ci + 1) * chunk_m));
 		}
 	}
 	CU(cudaStreamSynchronize(stream));
-	if (!use_side) deliver(0, m);
+	if (!use_side) deliver(0, 0, m);
 	const auto t_synced = now();
 	if (n_fix) {
 		// Rare path (the boundary set is normally empty for sampled states): re-run with the corrected counts pinned.
