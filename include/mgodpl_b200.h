@@ -21,7 +21,10 @@
  *  - "_device" variants take device pointers and only enqueue work on `stream` (a cudaStream_t passed as void*);
  *    the others take host pointers, copy in, run, copy out and synchronise `stream` before returning.  (One exception:
  *    a device-variant batch whose worst case exceeds the internal box queue — more than 2^25 candidate boxes — reads one
- *    counter block back, i.e. synchronises `stream` once, to learn how many passes it needs.)
+ *    counter block back, i.e. synchronises `stream` once, to learn how many passes it needs.)  Batches below that size never
+ *    block the host and allocate nothing once the stream's scratch exists (after the first call of that size on the stream),
+ *    so they can be recorded into a CUDA graph; replays use the capture stream's scratch, so do not issue other calls on
+ *    that stream while a replay is in flight.
  *  - handles are immutable after creation and may be used from several host threads at once.
  *  - there is no CPU fallback: without a CUDA device every entry point returns MGODPL_E_NO_DEVICE.
  */
