@@ -124,8 +124,8 @@ enum JointKind : int { REVOLUTE = 0, FIXED = 1 };
 
 enum GeomKind : int { GEOM_BOX = 0, GEOM_CAPSULE = 1, GEOM_CONVEX = 2 };
 struct BoxGeom {  // src/experiment_utils/shapes.h:20-22 + positioned_shape.h:12-30
-	V3 size;      // full extents, centred
-	Tf tf;        // relative to the link frame
+	V3 size{0, 0, 0};      // full extents, centred
+	Tf tf = tf_identity(); // relative to the link frame
 	// Not in the reference (it collides boxes only, collision_detection.cpp:21-22,49-51): capsule and convex-polytope links of
 	// the CUDA library (BASELINE north_star (3)), defined here from first principles; parity for them is against this file only.
 	int kind = GEOM_BOX;
@@ -204,12 +204,16 @@ inline std::vector<Tf> forward_kinematics(const Robot &r, const double *joint_va
 inline Robot procedural_robot(double total_arm_length, const std::vector<int> &joint_types) {
 	Robot m;
 	double stick = total_arm_length / (double) joint_types.size();
-	int base = m.add_link({"flying_base", {}, {BoxGeom{{0.8, 0.8, 0.2}, tf_identity()}}});
+	BoxGeom base_box;
+	base_box.size = {0.8, 0.8, 0.2};
+	int base = m.add_link({"flying_base", {}, {base_box}});
 	int attach_to = base;
 	Tf attach_a{{0, 0.2, 0}, {0, 0, 0, 1}};
 	for (int jt: joint_types) {
 		Tf stick_tf{{0, -stick / 2, 0}, {0, 0, 0, 1}};
-		int link = m.add_link({"stick", {}, {BoxGeom{{0.05, stick, 0.05}, tf_identity()}}});
+		BoxGeom stick_box;
+		stick_box.size = {0.05, stick, 0.05};
+		int link = m.add_link({"stick", {}, {stick_box}});
 		Joint j;
 		j.attach_a = attach_a;
 		j.attach_b = stick_tf;

@@ -49,16 +49,20 @@ void *orc_robot_procedural(double arm_length, const int *joint_types, int n_join
 void *orc_robot_new() { return new Robot(); }
 int orc_robot_add_link(void *r, const char *name) { return ((Robot *) r)->add_link({name, {}, {}}); }
 void orc_robot_add_box(void *r, int link, const double *size3, const double *tf7) {
-	((Robot *) r)->links[link].boxes.push_back({{size3[0], size3[1], size3[2]}, load_tf(tf7)});
+	BoxGeom g;
+	g.size = {size3[0], size3[1], size3[2]}, g.tf = load_tf(tf7);
+	((Robot *) r)->links[link].boxes.push_back(g);
 }
 /// Link shapes the reference does not have (capsule: fcl::Capsule's convention, axis along the shape's z; convex: hull of the points).
 void orc_robot_add_capsule(void *r, int link, double radius, double length, const double *tf7) {
-	BoxGeom g{{2 * radius, 2 * radius, length + 2 * radius}, load_tf(tf7)};
+	BoxGeom g;
+	g.size = {2 * radius, 2 * radius, length + 2 * radius}, g.tf = load_tf(tf7);
 	g.kind = GEOM_CAPSULE, g.radius = radius, g.length = length;
 	((Robot *) r)->links[link].boxes.push_back(g);
 }
 void orc_robot_add_convex(void *r, int link, const double *verts, int n, const double *tf7) {
-	BoxGeom g{{0, 0, 0}, load_tf(tf7)};
+	BoxGeom g;
+	g.size = {0, 0, 0}, g.tf = load_tf(tf7);
 	g.kind = GEOM_CONVEX;
 	for (int i = 0; i < n; ++i) g.verts.push_back({verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]});
 	((Robot *) r)->links[link].boxes.push_back(g);
@@ -66,7 +70,8 @@ void orc_robot_add_convex(void *r, int link, const double *verts, int n, const d
 /// One shape against one triangle (world frame): kind 1 = capsule (params radius, length), 2 = convex (verts); returns hit,
 /// *clearance = signed clearance.
 int orc_shape_tri(int kind, const double *tf7, double radius, double length, const double *verts, int n, const double *tri9, double *clearance) {
-	BoxGeom g{{0, 0, 0}, tf_identity()};
+	BoxGeom g;
+	g.size = {0, 0, 0}, g.tf = tf_identity();
 	g.kind = kind, g.radius = radius, g.length = length;
 	for (int i = 0; i < n; ++i) g.verts.push_back({verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]});
 	std::array<V3, 3> t{V3{tri9[0], tri9[1], tri9[2]}, V3{tri9[3], tri9[4], tri9[5]}, V3{tri9[6], tri9[7], tri9[8]}};

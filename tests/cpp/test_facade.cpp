@@ -783,11 +783,15 @@ int main() {
 		shaped.insertJoint({"j0", math::Transformd{{0, 0.4, 0}, {0, 0, 0, 1}}, math::Transformd{{0, -0.4, 0}, {0, 0, 0, 1}}, base, arm, RM::RevoluteJoint{{1, 0, 0}, -1.5, 1.5}});
 		shaped.insertJoint({"j1", math::Transformd{{0, 0.4, 0}, {0, 0, 0, 1}}, math::Transformd{{0, 0, 0}, {0, 0, 0, 1}}, arm, ee, RM::RevoluteJoint{{0, 0, 1}, -1.0, 1.0}});
 		orc::Robot oshaped;
-		oshaped.add_link({"flying_base", {}, {orc::BoxGeom{{0.8, 0.8, 0.2}, orc::tf_identity()}}});
-		orc::BoxGeom cap{{0, 0, 0}, {{0, 0, 0}, {lying.orientation.x, lying.orientation.y, lying.orientation.z, lying.orientation.w}}};
+		orc::BoxGeom obase;
+		obase.size = {0.8, 0.8, 0.2}, obase.tf = orc::tf_identity();
+		oshaped.add_link({"flying_base", {}, {obase}});
+		orc::BoxGeom cap;
+		cap.size = {0, 0, 0}, cap.tf = {{0, 0, 0}, {lying.orientation.x, lying.orientation.y, lying.orientation.z, lying.orientation.w}};
 		cap.kind = orc::GEOM_CAPSULE, cap.radius = 0.04, cap.length = 0.7;
 		oshaped.add_link({"stick", {}, {cap}});
-		orc::BoxGeom cvx{{0, 0, 0}, orc::tf_identity()};
+		orc::BoxGeom cvx;
+		cvx.size = {0, 0, 0}, cvx.tf = orc::tf_identity();
 		cvx.kind = orc::GEOM_CONVEX;
 		for (auto &v: wedge) cvx.verts.push_back({v.x(), v.y(), v.z()});
 		oshaped.add_link({"end_effector", {}, {cvx}});
