@@ -1334,6 +1334,8 @@ static cudaError_t run_traverse(const SceneDev &sc, const RobotDev &rb, const do
 	else k_traverse<MB, false><<<grid_for(bound, BLOCK_B, MB), BLOCK_B, 0, stream>>>(sc, rb, explicit_boxes, Q, res, tune)
 	switch (min_blocks) {
 		case 8: MGODPL_LAUNCH_TRAVERSE(8); break;
+		case 3: MGODPL_LAUNCH_TRAVERSE(3); break;
+		case 2: MGODPL_LAUNCH_TRAVERSE(2); break;
 		case 6: MGODPL_LAUNCH_TRAVERSE(6); break;
 		case 5: MGODPL_LAUNCH_TRAVERSE(5); break;
 		default: MGODPL_LAUNCH_TRAVERSE(4); break;
