@@ -74,6 +74,22 @@ struct Workspace {
 	cudaStream_t copy_in = nullptr, side[MAX_CHUNKS] = {};
 	cudaEvent_t ev_start = nullptr, ev_in[MAX_CHUNKS] = {};
 	cudaEvent_t ev_chunk[MAX_CHUNKS] = {};  // "results of chunk k are in pinned memory"
+	// A chunk's kernels + result copy as an instantiated CUDA graph, re-used while the call's shape stays what it was (a planner
+	// validates batch after batch of one size): one graph launch instead of ~12 enqueues per chunk, and the pipeline records its
+	// two rounds overlapped (launch_check_motions), which only pays off inside a graph.
+	struct ChunkGraph {
+		cudaGraphExec_t exec = nullptr;
+		unsigned long long key[10] = {};
+	};
+	ChunkGraph chunk_graph[MAX_CHUNKS];
+	MotionOverlap overlap[MAX_CHUNKS];
+	bool graphs_failed = false;  // a capture went wrong once: plain launches from then on
+	void drop_graphs() {
+		for (auto &g: chunk_graph) {
+			if (g.exec) cudaGraphExecDestroy(g.exec);
+			g.exec = nullptr;
+		}
+	}
 
 	cudaError_t side_streams() {
 		if (copy_in) return cudaSuccess;
@@ -83,10 +99,14 @@ struct Workspace {
 			e = cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_chunk[i], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&overlap[i].side, cudaStreamNonBlocking);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&overlap[i].ev_head, cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&overlap[i].ev_tail, cudaEventDisableTiming);
 		}
 		return e;
 	}
 	cudaError_t reserve(size_t dev_bytes, size_t host_bytes) {
+		if (dev_bytes > dev_cap || host_bytes > host_cap) drop_graphs();  // they point into the buffers that are about to move
 		if (dev_bytes > dev_cap) {
 			if (dev) cudaFree(dev);
 			dev = nullptr, dev_cap = 0;
@@ -106,6 +126,12 @@ struct Workspace {
 		return cudaSuccess;
 	}
 	~Workspace() {
+		drop_graphs();
+		for (auto &o: overlap) {
+			if (o.side) cudaStreamDestroy(o.side);
+			if (o.ev_head) cudaEventDestroy(o.ev_head);
+			if (o.ev_tail) cudaEventDestroy(o.ev_tail);
+		}
 		if (dev) cudaFree(dev);
 		if (host) cudaFreeHost(host);
 		if (copy_in) cudaStreamDestroy(copy_in);
@@ -187,7 +213,10 @@ WorkspacePool &global_pool() {
 
 }  // namespace
 
+static std::atomic<unsigned long long> g_handle_uid{1};
+
 struct mgodpl_scene {
+	const unsigned long long uid = g_handle_uid++;  // (cached graphs are keyed by it: a pointer can be re-used after destroy)
 	int device = 0;  // the CUDA device that holds the BVH
 	SceneDev dev{};
 	BuiltScene built{};
@@ -226,6 +255,7 @@ struct mgodpl_scene {
 };
 
 struct mgodpl_robot {
+	const unsigned long long uid = g_handle_uid++;
 	RobotDev dev{};
 	int n_joints = 0;
 	// Convex links only: the hulls (vertices, face planes, edge directions; convex_triangle_hit's layout) and their device copies,
@@ -962,10 +992,15 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		const char *e = getenv("MGODPL_E2E_CHUNKS");
 		return e && atoi(e) > 0 ? std::min((size_t) atoi(e), Workspace::MAX_CHUNKS) : (size_t) 3;
 	}();
+	static const bool use_graphs = [] {
+		const char *e = getenv("MGODPL_E2E_GRAPHS");
+		return !(e && atoi(e) == 0);
+	}();
 	const bool use_side = m >= 32768;  // large batches run on the workspace's own non-blocking streams, in chunk_pref chunks
 	const size_t n_chunks = use_side ? chunk_pref : 1;
 	const size_t chunk_m = n_chunks == 1 ? m : ((m + n_chunks - 1) / n_chunks + 31) / 32 * 32;
-	const size_t in_b = m * stride * 8, words = (m + 31) / 32, qb = motion_scratch_bytes(chunk_m, robot->dev.n_boxes);
+	const size_t in_b = m * stride * 8, words = (m + 31) / 32;
+	const size_t qb = motion_scratch_bytes(chunk_m, robot->dev.n_boxes) + (use_side ? motion_tail_queue_bytes(chunk_m, robot->dev.n_boxes) : 0);
 	size_t o_a = c.take(in_b), o_b = c.take(in_b), o_first = c.take(m * 4), o_slerp = c.take(m * 32);
 	size_t o_hit = c.take(words * 4), o_unc = c.take(words * 4), o_steps = c.take(m * 4), o_toi = c.take(toi ? m * 8 : 0);
 	const size_t out_lo = o_hit, out_hi = c.off;
@@ -1020,13 +1055,48 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		}
 		if (trace && use_side && ci < 2) CU(cudaEventRecord(tev[ci][1], s));  // (kernels start here: after the chunk has arrived)
 		char *blk = D + o_blk[ci];
-		CU(launch_check_motions(scene->dev, rdev, (const double *) (D + o_a) + lo * stride, (const double *) (D + o_b) + lo * stride, mc,
-								stride, js, max_step, nullptr, (uint32_t *) blk, toi ? (double *) (blk + b_toi) : nullptr,
-								(uint32_t *) (blk + b_steps), (uint32_t *) (blk + b_unc), (unsigned *) (D + o_first) + lo,
-								D + o_slerp + lo * 32, D + o_q[ci], qb, motion_survivors(mc), s));
-		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][2], s));
-		CU(cudaMemcpyAsync(HB + ci * b_size, blk, b_size, cudaMemcpyDeviceToHost, s));
-		if (trace && ci < 2) CU(cudaEventRecord(tev[ci][3], s));
+		auto enqueue_chunk = [&](const MotionOverlap *ov) -> cudaError_t {
+			cudaError_t e = launch_check_motions(scene->dev, rdev, (const double *) (D + o_a) + lo * stride, (const double *) (D + o_b) + lo * stride, mc,
+												 stride, js, max_step, nullptr, (uint32_t *) blk, toi ? (double *) (blk + b_toi) : nullptr,
+												 (uint32_t *) (blk + b_steps), (uint32_t *) (blk + b_unc), (unsigned *) (D + o_first) + lo,
+												 D + o_slerp + lo * 32, D + o_q[ci], qb, motion_survivors(mc), s, ov);
+			if (e != cudaSuccess) return e;
+			if (trace && ci < 2 && !ov) cudaEventRecord(tev[ci][2], s);
+			return cudaMemcpyAsync(HB + ci * b_size, blk, b_size, cudaMemcpyDeviceToHost, s);
+		};
+		// Chunked calls replay the chunk's kernels + result copy from a cached CUDA graph when nothing about the call's shape has
+		// changed since it was recorded (MGODPL_E2E_GRAPHS=0: plain launches).
+		bool replayed = false;
+		if (use_side && use_graphs && !ws->graphs_failed && !trace && motion_batch_is_one_pass(mc, robot->dev.n_boxes)) {
+			const unsigned long long key[10] = {scene->uid, robot->uid, (unsigned long long) mc, (unsigned long long) lo, (unsigned long long) stride,
+											   (unsigned long long) js, (unsigned long long) __builtin_bit_cast(unsigned long long, max_step), toi ? 1ull : 0ull,
+											   (unsigned long long) (uintptr_t) blk ^ ((unsigned long long) (uintptr_t) (D + o_q[ci]) << 1), (unsigned long long) qb ^ ((unsigned long long) m << 32)};
+			Workspace::ChunkGraph &cg = ws->chunk_graph[ci];
+			if (!cg.exec || memcmp(cg.key, key, sizeof(key)) != 0) {
+				if (cg.exec) cudaGraphExecDestroy(cg.exec);
+				cg.exec = nullptr;
+				cudaGraph_t graph = nullptr;
+				cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+				if (e == cudaSuccess) {
+					e = enqueue_chunk(&ws->overlap[ci]);
+					const cudaError_t e_end = cudaStreamEndCapture(s, &graph);
+					if (e == cudaSuccess) e = e_end;
+				}
+				if (e == cudaSuccess) e = cudaGraphInstantiate(&cg.exec, graph, 0);
+				if (graph) cudaGraphDestroy(graph);
+				if (e != cudaSuccess) {
+					cudaGetLastError();
+					cg.exec = nullptr, ws->graphs_failed = true;
+				} else {
+					memcpy(cg.key, key, sizeof(key));
+				}
+			}
+			if (cg.exec) {
+				CU(cudaGraphLaunch(cg.exec, s));
+				replayed = true;
+			}
+		}
+		if (!replayed) CU(enqueue_chunk(nullptr));
 		if (use_side) {
 			CU(cudaEventRecord(ws->ev_chunk[ci], s));
 			CU(cudaStreamWaitEvent(stream, ws->ev_chunk[ci], 0));  // the caller's stream continues after every chunk

@@ -14,6 +14,8 @@ constexpr size_t SURVIVOR_MAX_ENTRIES = 64u << 20;
 size_t query_scratch_bytes(size_t worst_case_boxes, size_t survivor_entries = 0);
 size_t motion_overflow_bytes(size_t m);
 size_t motion_tail_queue_bytes(size_t m, int n_boxes);
+/// Does a motion batch of this size run without the survivor-count read-back (i.e. can its launches be recorded into a graph)?
+bool motion_batch_is_one_pass(size_t m, int n_boxes);
 /// What lets launch_check_motions overlap its two rounds (see there): a side stream and two events, owned by the caller's
 /// per-stream slot.
 struct MotionOverlap {

@@ -1236,6 +1236,10 @@ size_t state_survivor_slots(size_t n) { return n + n / 4 + SHARDS * SHARD_BLOCK;
 static size_t queue_max_items() { return knobs().queue_max_items; }
 static size_t survivor_max_entries() { return knobs().survivor_max_entries; }
 
+bool motion_batch_is_one_pass(size_t m, int n_boxes) {
+	return knobs().pipeline == 0 && (m * 32 + 4096) * (size_t) std::max(n_boxes, 1) <= queue_max_items() && m * 64 <= survivor_max_entries();
+}
+
 /// Room for the tail round's own queue (8 boxes per motion; launch_check_motions carves it off the end of its scratch).
 size_t motion_tail_queue_bytes(size_t m, int n_boxes) { return QUEUE_HEADER + (8 * m + 4096) * (size_t) std::max(n_boxes, 1) * sizeof(Item); }
 
