@@ -139,16 +139,19 @@ cudaError_t launch_roadmap_shortest_paths(const uint32_t *d_row, const uint32_t 
 	double *labels = (double *) scratch;
 	unsigned char *moved = (unsigned char *) (labels + group * n * 32);
 	unsigned *flags = (unsigned *) (((uintptr_t) (moved + 3 * group * n) + 255) & ~(uintptr_t) 255);
+	int sm_dev = 0, sms = 148;  // SM count of the current device (a process may drive several)
+	cudaGetDevice(&sm_dev);
+	if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sm_dev) != cudaSuccess || sms <= 0) sms = 148;
 	constexpr unsigned BATCH = 8;  // sweeps enqueued between two convergence read-backs
 	unsigned sweeps_total = 0;
 	cudaError_t err = cudaSuccess;
 	for (size_t b0 = 0; b0 < total_blocks; b0 += group) {
 		const unsigned nb = (unsigned) (b0 + group <= total_blocks ? group : total_blocks - b0);
 		const size_t first_source = b0 * 32;
-		k_sssp_init<<<148 * 8, SSSP_BLOCK, 0, stream>>>(labels, moved, n, nb);
+		k_sssp_init<<<(unsigned) sms * 8, SSSP_BLOCK, 0, stream>>>(labels, moved, n, nb);
 		k_sssp_seed<<<(nb * 32 + 127) / 128, 128, 0, stream>>>(labels, moved, n, nb, d_sources, first_source, n_sources);
 		// a few resident waves per source block: a sweep that finds the batch already converged costs microseconds, not a full grid
-		const unsigned per_block = (n + SSSP_BLOCK / 32 - 1) / (SSSP_BLOCK / 32), cap = (148u * 8u * 4u + nb - 1) / nb;
+		const unsigned per_block = (n + SSSP_BLOCK / 32 - 1) / (SSSP_BLOCK / 32), cap = ((unsigned) sms * 8u * 4u + nb - 1) / nb;
 		const dim3 grid(per_block < cap ? per_block : cap, nb);
 		unsigned t = 0;
 		for (;;) {
