@@ -286,16 +286,16 @@ def run_ours(args):
     pa, pb = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
     na, nb = pa.numpy(), pb.numpy()
     res = mg.capi.motion_result_buffers(m)  # caller-owned result arrays, reused across calls
-    # Warm-up of the host-buffer path: at least 40 calls, then on until the call time has settled (the last eight within 3 % of
-    # each other) or 200 calls / 0.4 s have passed.  On some hosts the first 50-100 calls after a process starts using the host
+    # Warm-up of the host-buffer path: at least 100 calls, then on until the call time has settled (the last eight within 3 % of
+    # each other) or 400 calls / 0.8 s have passed.  On some hosts the first 50-100 calls after a process starts using the host
     # link take up to 2.5x as long and speed up gradually (seen as 1.5 -> 0.6 ms over 70 ms with SM clocks at maximum
     # throughout; tools/gpu_e2e_trace.py): the timed calls measure the steady state, and every one of them is reported.
     e2e_warm, t_warm = [], time.perf_counter()
-    while len(e2e_warm) < 200 and (len(e2e_warm) < 3 or time.perf_counter() - t_warm < 0.4):
+    while len(e2e_warm) < 400 and (len(e2e_warm) < 3 or time.perf_counter() - t_warm < 0.8):
         t1 = time.perf_counter()
         mg.capi.check_motions(scene, robot, na, nb, MAX_STEP, True, stream=stream, out=res)
         e2e_warm.append((time.perf_counter() - t1) * 1e3)
-        if len(e2e_warm) >= 40 and max(e2e_warm[-8:]) <= 1.03 * min(e2e_warm[-8:]):
+        if len(e2e_warm) >= 100 and max(e2e_warm[-8:]) <= 1.03 * min(e2e_warm[-8:]):
             break
     torch.cuda.synchronize()
     if world > 1:
