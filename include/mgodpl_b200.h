@@ -222,8 +222,11 @@ int mgodpl_knn_query(const double *database, size_t n_database, const double *qu
  *      where unreachable (boost's default infinity); pred (optional): same shape, the vertex before v on a shortest path,
  *      v itself for the source and for unreachable vertices.  Where several neighbours tie exactly, the one nearer the
  *      source, then the lower index, is reported (boost reports whichever its heap relaxed first).  With positive weights
- *      the predecessors form a tree; three or more distinct vertices joined by ZERO-weight edges sit at the same distance and
- *      may name each other (distances stay exact) — bound any walk over `pred` by n_vertices, as the facade does.  sweeps_out (optional):
+ *      the predecessors form a tree.  Distinct vertices joined by edges that VANISH in the sum (zero weight, or below half an
+ *      ulp of the distance) sit at one distance: the host-buffer variant passes its result through
+ *      mgodpl_roadmap_repair_predecessors, so that it is a tree again; the _device variant leaves the predecessors as the
+ *      kernel picked them, and three or more such vertices may name each other (distances stay exact) — copy them to the host
+ *      and repair them there, or bound any walk over `pred` by n_vertices, as the facade does.  sweeps_out (optional):
  *      label-correcting sweeps enqueued.  The _device variant takes the graph in CSR form (row_offsets: n_vertices + 1,
  *      neighbours / weights: both directions of every edge) in device memory and synchronises the stream before returning. */
 int mgodpl_roadmap_shortest_paths(uint32_t n_vertices, const uint32_t *edges, const double *weights, size_t n_edges,
@@ -232,6 +235,14 @@ int mgodpl_roadmap_shortest_paths(uint32_t n_vertices, const uint32_t *edges, co
 int mgodpl_roadmap_shortest_paths_device(const uint32_t *d_row_offsets, const uint32_t *d_neighbours, const double *d_weights,
 										 uint32_t n_vertices, const uint32_t *d_sources, size_t n_sources, double *d_dist,
 										 uint32_t *d_pred, uint32_t *sweeps_out, void *stream);
+
+/* Host-side utility, no device involved: makes ONE source's predecessors a tree where vanishing edges let vertices at one
+ * distance name each other.  row_offsets / neighbours / weights: the CSR graph as the _device variant takes it, in host memory;
+ * dist / pred: one source's n_vertices labels and predecessors (pred is rewritten in place).  Vertices whose predecessor is
+ * strictly nearer the source are left alone; the others take a strictly nearer neighbour on a shortest path if they have one,
+ * and are otherwise reached breadth-first over the vanishing edges, so every walk over `pred` ends at the source. */
+int mgodpl_roadmap_repair_predecessors(uint32_t n_vertices, const uint32_t *row_offsets, const uint32_t *neighbours,
+									   const double *weights, const double *dist, uint32_t *pred);
 
 /* ---- connected components of a mesh's vertex graph: connected_vertex_components
  *      (src/experiment_utils/mesh_connected_components.cpp:25-74), which loadTreeMeshes uses to split a tree model's

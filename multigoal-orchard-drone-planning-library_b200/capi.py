@@ -28,7 +28,8 @@ EXPORTS = [
     "mgodpl_robot_destroy", "mgodpl_robot_n_variables", "mgodpl_forward_kinematics", "mgodpl_check_boxes",
     "mgodpl_check_states", "mgodpl_check_states_device", "mgodpl_check_motions", "mgodpl_check_motions_device",
     "mgodpl_check_path", "mgodpl_sample_goals", "mgodpl_sample_goals_device", "mgodpl_knn", "mgodpl_knn_device", "mgodpl_knn_query",
-    "mgodpl_roadmap_shortest_paths", "mgodpl_roadmap_shortest_paths_device", "mgodpl_mesh_components",
+    "mgodpl_roadmap_shortest_paths", "mgodpl_roadmap_shortest_paths_device", "mgodpl_roadmap_repair_predecessors",
+    "mgodpl_mesh_components",
     "mgodpl_mesh_components_u64",
 ]
 
@@ -358,6 +359,22 @@ def roadmap_shortest_paths(n_vertices: int, edges, weights, sources, want_pred: 
                                                _p(sources, C.c_uint32), C.c_size_t(len(sources)), _p(dist), _p(pred, C.c_uint32),
                                                C.byref(sweeps), _stream(stream)))
     return dict(dist=dist, pred=pred, sweeps=int(sweeps.value))
+
+
+def roadmap_repair_predecessors(row_offsets, neighbours, weights, dist, pred):
+    """Host-side: one source's predecessors made a tree again where vanishing (zero-weight) edges let vertices at one distance
+    name each other.  CSR graph with both directions of every edge; returns the repaired copy of `pred`."""
+    row = np.ascontiguousarray(row_offsets, dtype=np.uint32).reshape(-1)
+    col = np.ascontiguousarray(neighbours, dtype=np.uint32).reshape(-1)
+    w = _f64(weights).reshape(-1)
+    dist = _f64(dist).reshape(-1)
+    pred = np.array(pred, dtype=np.uint32).reshape(-1)
+    n = len(row) - 1
+    if n < 0 or len(dist) != n or len(pred) != n or len(col) != len(w) or (n >= 0 and len(col) != int(row[-1])):
+        raise MgodplError(-1, "row_offsets: n_vertices + 1 entries; dist / pred: n_vertices; neighbours / weights: row_offsets[-1]")
+    _check(lib().mgodpl_roadmap_repair_predecessors(C.c_uint32(n), _p(row, C.c_uint32), _p(col, C.c_uint32), _p(w), _p(dist),
+                                                    _p(pred, C.c_uint32)))
+    return pred
 
 
 def roadmap_shortest_paths_device(d_row_offsets, d_neighbours, d_weights, n_vertices: int, d_sources, n_sources: int, d_dist,

@@ -1342,6 +1342,46 @@ int mgodpl_roadmap_shortest_paths_device(const uint32_t *d_row_offsets, const ui
 	return MGODPL_OK;
 }
 
+int mgodpl_roadmap_repair_predecessors(uint32_t n_vertices, const uint32_t *row, const uint32_t *col, const double *w, const double *ds,
+									   uint32_t *ps) {
+	if (n_vertices && (!row || !ds || !ps)) return fail(MGODPL_E_INVALID_ARGUMENT, "null buffer");
+	if (n_vertices && row[n_vertices] && (!col || !w)) return fail(MGODPL_E_INVALID_ARGUMENT, "null adjacency");
+	for (uint32_t v = 0; v < n_vertices; ++v)
+		if (ps[v] >= n_vertices) return fail(MGODPL_E_INVALID_ARGUMENT, "predecessor out of range");
+	// members: vertices whose predecessor sits at the same distance (the edge between them vanished in the sum): decide those again
+	std::vector<uint32_t> frontier, members;
+	std::vector<char> settled(n_vertices, 1);
+	for (uint32_t v = 0; v < n_vertices; ++v)
+		if (ps[v] != v && ds[ps[v]] == ds[v]) settled[v] = 0, members.push_back(v);
+	if (members.empty()) return MGODPL_OK;
+	// a member with a strictly nearer neighbour on a shortest path takes that one (ties: nearer the source, then lower index)
+	for (uint32_t v: members) {
+		uint32_t best = v;
+		for (uint32_t k = row[v]; k < row[v + 1]; ++k) {
+			const uint32_t u = col[k];
+			if (u != v && ds[u] < ds[v] && ds[u] + w[k] == ds[v] && (best == v || ds[u] < ds[best] || (ds[u] == ds[best] && u < best))) best = u;
+		}
+		if (best != v) ps[v] = best, settled[v] = 1, frontier.push_back(v);
+	}
+	// every settled vertex that reaches a still-undecided member over a vanishing edge starts the breadth-first search as well
+	for (uint32_t v: members)
+		if (!settled[v])
+			for (uint32_t k = row[v]; k < row[v + 1]; ++k) {
+				const uint32_t u = col[k];
+				if (u != v && settled[u] && ds[u] == ds[v] && ds[u] + w[k] == ds[v]) frontier.push_back(u);
+			}
+	std::sort(frontier.begin(), frontier.end());
+	frontier.erase(std::unique(frontier.begin(), frontier.end()), frontier.end());
+	for (size_t head = 0; head < frontier.size(); ++head) {
+		const uint32_t u = frontier[head];
+		for (uint32_t k = row[u]; k < row[u + 1]; ++k) {
+			const uint32_t v = col[k];
+			if (!settled[v] && ds[v] == ds[u] && ds[u] + w[k] == ds[v]) ps[v] = u, settled[v] = 1, frontier.push_back(v);
+		}
+	}
+	return MGODPL_OK;
+}
+
 int mgodpl_roadmap_shortest_paths(uint32_t n_vertices, const uint32_t *edges, const double *weights, size_t n_edges,
 								  const uint32_t *sources, size_t n_sources, double *dist, uint32_t *pred, uint32_t *sweeps_out,
 								  void *stream_) {
@@ -1391,6 +1431,20 @@ int mgodpl_roadmap_shortest_paths(uint32_t n_vertices, const uint32_t *edges, co
 	if (pred) CU(cudaMemcpyAsync(pred, d_pred, cells * 4, cudaMemcpyDeviceToHost, stream));
 	CU(cudaStreamSynchronize(stream));
 	ws.settled = true;
+	// Edges so short that they vanish in the sum (zero weight, or below half an ulp of the distance) join vertices at ONE distance,
+	// and the device, which picks a predecessor per vertex on its own, may let such vertices name each other.  The distances are
+	// exact; mgodpl_roadmap_repair_predecessors makes the predecessors a tree again (what boost's Dijkstra always returns).
+	// No distance exceeds the sum of all weights, so an edge can only vanish if w <= 2^-53 * that sum: graphs without such an
+	// edge — every roadmap of distinct states — skip the pass.
+	if (pred) {
+		double total = 0.0;
+		for (size_t e = 0; e < n_edges; ++e) total += weights[e];
+		bool may_vanish = false;
+		for (size_t e = 0; e < n_edges && !may_vanish; ++e) may_vanish = edges[2 * e] != edges[2 * e + 1] && weights[e] <= total * 0x1p-52;
+		if (may_vanish)
+			for (size_t s = 0; s < n_sources; ++s)
+				mgodpl_roadmap_repair_predecessors(n_vertices, row.data(), col.data(), w.data(), dist + s * n_vertices, pred + s * n_vertices);
+	}
 	return MGODPL_OK;
 }
 

@@ -78,6 +78,87 @@ def test_abi_validates_graph_arguments(mg):
         mg.capi.roadmap_shortest_paths(3, [[0, 1]], [1.0], [5])
 
 
+def csr_of(n, edges, weights):
+    """Both directions of every edge, neighbours in edge-list order (what the library builds and the _device variant takes)."""
+    row = np.zeros(n + 1, np.uint32)
+    for a, b in edges.tolist():
+        row[a + 1] += 1
+        row[b + 1] += 1
+    row = np.cumsum(row, dtype=np.uint32)
+    cur, col, w = row[:-1].copy(), np.zeros(2 * len(edges), np.uint32), np.zeros(2 * len(edges))
+    for (a, b), x in zip(edges.tolist(), weights.tolist()):
+        col[cur[a]], w[cur[a]] = b, x
+        cur[a] += 1
+        col[cur[b]], w[cur[b]] = a, x
+        cur[b] += 1
+    return row, col, w
+
+
+def assert_predecessor_tree(src, dist, pred):
+    """Every reachable vertex walks to the source in fewer than n hops."""
+    n = len(pred)
+    for v in range(n):
+        if dist[v] == DBL_MAX:
+            assert pred[v] == v
+            continue
+        u, hops = v, 0
+        while u != src:
+            u, hops = int(pred[u]), hops + 1
+            assert hops < n, f"walk from {v} does not reach the source"
+
+
+def zero_weight_cluster_graph():
+    """Source 0 inside a zero-weight triangle (0, 1, 2); a second zero-weight clique (4, 5, 6, 7) one unit away behind vertex 3;
+    an edge far too short to register in the sum (8, behind 7); vertex 9 isolated."""
+    edges = np.array([[0, 1], [1, 2], [2, 0], [2, 3], [3, 4], [4, 5], [5, 6], [6, 7], [7, 4], [4, 6], [5, 7], [7, 8]], np.uint32)
+    w = np.array([0.0, 0.0, 0.0, 1.0, 0.5, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1e-30])
+    return 10, edges, w
+
+
+def test_repair_predecessors_breaks_cycles_between_tied_vertices(mg, oracle):
+    """The host-side pass of mgodpl_roadmap_shortest_paths (no device involved): predecessors that name each other inside
+    clusters joined by vanishing edges — what the per-vertex choice on the device may produce — become a tree; everything
+    else is left as it was."""
+    n, edges, w = zero_weight_cluster_graph()
+    row, col, cw = csr_of(n, edges, w)
+    dist, _ = oracle.roadmap_shortest_paths(n, edges, w, [0])
+    dist = dist[0]
+    assert dist.tolist() == [0.0, 0.0, 0.0, 1.0, 1.5, 1.5, 1.5, 1.5, 1.5, DBL_MAX]
+    # worst case the kernel's rule admits: 1 <-> 2 name each other, 4..7 form a ring, 8 hangs off 7
+    bad = np.array([0, 2, 1, 2, 5, 6, 7, 4, 7, 9], np.uint32)
+    got = mg.capi.roadmap_repair_predecessors(row, col, cw, dist, bad)
+    assert got[0] == 0 and got[9] == 9 and got[3] == 2
+    assert got[4] == 3                      # the only member with a strictly nearer neighbour on a shortest path
+    check_predecessors(n, edges, w, [0], dist[None], got[None])
+    assert_predecessor_tree(0, dist, got)
+    # an already valid tree is returned unchanged wherever the predecessor is strictly nearer, and stays a tree elsewhere
+    good = np.array([0, 0, 0, 2, 3, 4, 4, 4, 7, 9], np.uint32)
+    again = mg.capi.roadmap_repair_predecessors(row, col, cw, dist, good)
+    assert again[3] == 2 and again[4] == 3
+    assert_predecessor_tree(0, dist, again)
+    # random graphs with many zero-weight edges, predecessors scrambled inside each tied cluster
+    rng = np.random.default_rng(17)
+    for _ in range(20):
+        n = int(rng.integers(5, 60))
+        edges = rng.integers(0, n, (int(rng.integers(n, 4 * n)), 2)).astype(np.uint32)
+        w = rng.choice([0.0, 0.0, 1.0, 2.0, 1e-40], len(edges))
+        row, col, cw = csr_of(n, edges, w)
+        src = int(rng.integers(0, n))
+        dist, _ = oracle.roadmap_shortest_paths(n, edges, w, [src])
+        dist = dist[0]
+        pred = np.arange(n, dtype=np.uint32)
+        for v in range(n):  # any neighbour on a shortest path, chosen at random: cycles inside tied clusters are likely
+            if v == src or dist[v] == DBL_MAX:
+                continue
+            cands = [int(col[k]) for k in range(row[v], row[v + 1]) if col[k] != v and dist[col[k]] + cw[k] == dist[v]]
+            pred[v] = cands[int(rng.integers(0, len(cands)))]
+        got = mg.capi.roadmap_repair_predecessors(row, col, cw, dist, pred)
+        check_predecessors(n, edges, w, [src], dist[None], got[None])
+        assert_predecessor_tree(src, dist, got)
+    with pytest.raises(mg.capi.MgodplError, match="out of range"):
+        mg.capi.roadmap_repair_predecessors(row, col, cw, dist, np.full(n, n, np.uint32))
+
+
 # ---- GPU -------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,e,g", [(1, 0, 1), (2, 1, 2), (50, 60, 7), (400, 1500, 33), (3000, 12000, 100), (20000, 90000, 64)])
@@ -142,6 +223,14 @@ def test_gpu_ties_zero_weights_and_long_chains(gpu, oracle):
     want_d, _ = oracle.roadmap_shortest_paths(5, edges, w, [0, 0, 3])
     assert np.array_equal(got["dist"], want_d) and got["dist"][0].tolist() == [0.0, 1.5, 1.5, 2.5, DBL_MAX]
     assert got["pred"][0].tolist()[:2] == [0, 0] and got["pred"][0][4] == 4 and got["pred"][0][3] == 2
+    # zero-weight clusters, one of them around the source, and an edge too short to register: distances exact, predecessors a tree
+    n, edges, w = zero_weight_cluster_graph()
+    got = gpu.capi.roadmap_shortest_paths(n, edges, w, [0, 5, 8])
+    want_d, _ = oracle.roadmap_shortest_paths(n, edges, w, [0, 5, 8])
+    assert np.array_equal(got["dist"], want_d)
+    check_predecessors(n, edges, w, [0, 5, 8], got["dist"], got["pred"])
+    for i, src in enumerate([0, 5, 8]):
+        assert_predecessor_tree(src, got["dist"][i], got["pred"][i])
     # no sources / no vertices
     assert gpu.capi.roadmap_shortest_paths(5, edges, w, [])["dist"].shape == (0, 5)
 
