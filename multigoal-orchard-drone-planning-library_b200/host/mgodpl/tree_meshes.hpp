@@ -8,10 +8,12 @@
 // The reference reads COLLADA through assimp (aiProcess_Triangulate | JoinIdenticalVertices | SortByPType |
 // RemoveComponent with everything but positions removed) and then ignores the node hierarchy: it concatenates the raw
 // vertices of every aiMesh, applying one hard-coded unit/axis conversion.  assimp is absent here, so `from_dae` is a
-// small COLLADA 1.4 reader that produces the same kind of mesh: positions only, polygons fan-triangulated, identical
-// positions merged per primitive block in first-seen order, float32 coordinates (assimp's aiVector3D) converted exactly as
+// small COLLADA 1.4 reader that produces the same kind of mesh: positions only, geometries in the order the visual scene's
+// nodes first instantiate them (assimp's aiMesh order), polygons fan-triangulated, identical positions merged per primitive
+// block in first-seen order, float32 coordinates (assimp's aiVector3D) converted exactly as
 // mesh_from_dae.cpp:55-69 does.  Fruit separation runs on the GPU (mgodpl_mesh_components).
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstring>
 #include <filesystem>
@@ -187,6 +189,44 @@ inline Mesh from_dae(const std::string &dae_file) {
 	Mesh mesh;
 	std::vector<const Element *> geometries;
 	collect(root, "geometry", geometries);
+	// assimp's COLLADA loader creates its aiMeshes while it walks the node hierarchy of the instantiated visual scene (depth
+	// first, a node's own geometry instances before its children), one per geometry the first time a node instantiates it:
+	// scene->mMeshes — which mesh_from_dae.cpp:52 concatenates, ignoring the nodes' transforms — is in THAT order, and a
+	// geometry no node refers to is not in it at all.  A document without a visual scene (assimp refuses those) is read in
+	// library order.
+	{
+		std::vector<const Element *> scenes, nodes, ordered;
+		collect(root, "visual_scene", scenes);
+		collect(root, "node", nodes);
+		const Element *start = nullptr;
+		if (const Element *sc = root.child("scene"))
+			if (const Element *inst = sc->child("instance_visual_scene"))
+				for (const Element *vs: scenes)
+					if (vs->attribute("id") == strip_hash(inst->attribute("url"))) start = vs;
+		if (!start && !scenes.empty()) start = scenes.front();
+		std::vector<const Element *> active;  // guards against <instance_node> cycles
+		auto walk = [&](auto &&self, const Element &node) -> void {
+			if (std::find(active.begin(), active.end(), &node) != active.end()) return;
+			active.push_back(&node);
+			for (const auto &c: node.children)
+				if (c.name == "instance_geometry")
+					for (const Element *g: geometries)
+						if (g->attribute("id") == strip_hash(c.attribute("url")) && std::find(ordered.begin(), ordered.end(), g) == ordered.end())
+							ordered.push_back(g);
+			for (const auto &c: node.children) {
+				if (c.name == "node") self(self, c);
+				else if (c.name == "instance_node")
+					for (const Element *n: nodes)
+						if (n->attribute("id") == strip_hash(c.attribute("url"))) self(self, *n);
+			}
+			active.pop_back();
+		};
+		if (start) {
+			for (const auto &c: start->children)
+				if (c.name == "node") walk(walk, c);
+			geometries = ordered;
+		}
+	}
 	for (const Element *geometry: geometries) {
 		const Element *m = geometry->child("mesh");
 		if (!m) continue;

@@ -224,11 +224,11 @@ def test_gpu_ties_zero_weights_and_long_chains(gpu, oracle):
     assert np.array_equal(got["dist"], want_d) and got["dist"][0].tolist() == [0.0, 1.5, 1.5, 2.5, DBL_MAX]
     assert got["pred"][0].tolist()[:2] == [0, 0] and got["pred"][0][4] == 4 and got["pred"][0][3] == 2
     # zero-weight clusters, one of them around the source, and an edge too short to register: distances exact, predecessors a tree
-    n, edges, w = zero_weight_cluster_graph()
-    got = gpu.capi.roadmap_shortest_paths(n, edges, w, [0, 5, 8])
-    want_d, _ = oracle.roadmap_shortest_paths(n, edges, w, [0, 5, 8])
+    cn, cedges, cw = zero_weight_cluster_graph()
+    got = gpu.capi.roadmap_shortest_paths(cn, cedges, cw, [0, 5, 8])
+    want_d, _ = oracle.roadmap_shortest_paths(cn, cedges, cw, [0, 5, 8])
     assert np.array_equal(got["dist"], want_d)
-    check_predecessors(n, edges, w, [0, 5, 8], got["dist"], got["pred"])
+    check_predecessors(cn, cedges, cw, [0, 5, 8], got["dist"], got["pred"])
     for i, src in enumerate([0, 5, 8]):
         assert_predecessor_tree(src, got["dist"][i], got["pred"][i])
     # no sources / no vertices
