@@ -964,6 +964,8 @@ uint32_t host_n_steps(const double *a, const double *b, int js, double max_step)
 }
 }  // namespace
 
+/// Ratio of consecutive chunk sizes in the host-buffer motion call (see there); 1 = equal chunks.
+static constexpr double E2E_TAPER_DEFAULT = 0.7;
 int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const double *a, const double *b, size_t m, size_t stride,
 						 int32_t js, double max_step, uint32_t *hit_bits, double *toi, uint32_t *n_steps_out, void *stream_) {
 	if (!scene) return fail(MGODPL_E_INVALID_ARGUMENT, "scene is null");
@@ -984,21 +986,45 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	Carver c;
 	// Large batches are cut into chunks.  All input copies go through one copy stream, back to back (the PCIe link carries input
 	// from the first microsecond to the last byte); chunk k's kernels and result copies run on a stream of their own that waits for
-	// "chunk k has arrived" only, so the kernels of the early chunks hide behind the input copies of the later ones.  Three chunks
-	// measure best for 100 k motions (0.58 ms; 1: 0.70, 2: 0.59, 4: 0.58, 6: 0.7): a chunk's kernels have a latency floor of
-	// ~0.15 ms however small it is, and concurrent chunks share the SMs.  Chunk boundaries are multiples of 32: result words never
-	// straddle.
+	// "chunk k has arrived" only, so the kernels of the early chunks hide behind the input copies of the later ones.  A chunk's
+	// kernels have a latency floor of ~0.12-0.15 ms however small it is, and concurrent chunks share the SMs: for 100 k motions
+	// equal chunks measured 0.70 ms (1 chunk), 0.59 (2), 0.58 (3), 0.58 (4), 0.7 (6); four chunks whose sizes fall off by 0.7
+	// (below) are the default (0.522 against 0.543-0.554 for three equal ones in the same run; tools/gpu_e2e_taper.py).  Chunk
+	// boundaries are multiples of 32: result words never straddle.
 	static const size_t chunk_pref = [] {
 		const char *e = getenv("MGODPL_E2E_CHUNKS");
-		return e && atoi(e) > 0 ? std::min((size_t) atoi(e), Workspace::MAX_CHUNKS) : (size_t) 3;
+		return e && atoi(e) > 0 ? std::min((size_t) atoi(e), Workspace::MAX_CHUNKS) : (size_t) 4;
 	}();
 	static const bool use_graphs = [] {
 		const char *e = getenv("MGODPL_E2E_GRAPHS");
 		return !(e && atoi(e) == 0);
 	}();
+	// Chunk sizes fall off geometrically (chunk k+1 = taper x chunk k): what the call waits for in the end is the LAST chunk's
+	// kernels, which cannot start before the last input byte has arrived, so that chunk should be small — down to where a chunk's
+	// latency floor makes a smaller one pointless.  MGODPL_E2E_TAPER=1: equal chunks.
+	static const double chunk_taper = [] {
+		const char *e = getenv("MGODPL_E2E_TAPER");
+		const double r = e ? atof(e) : E2E_TAPER_DEFAULT;
+		return r > 0.05 && r <= 1.0 ? r : 1.0;
+	}();
 	const bool use_side = m >= 32768;  // large batches run on the workspace's own non-blocking streams, in chunk_pref chunks
-	const size_t n_chunks = use_side ? chunk_pref : 1;
-	const size_t chunk_m = n_chunks == 1 ? m : ((m + n_chunks - 1) / n_chunks + 31) / 32 * 32;
+	size_t n_chunks = use_side ? chunk_pref : 1;
+	size_t cb[Workspace::MAX_CHUNKS + 1] = {0};  // chunk ci = motions [cb[ci], cb[ci + 1]), boundaries multiples of 32
+	{
+		double total = 0.0, w = 1.0, acc = 0.0;
+		for (size_t ci = 0; ci < n_chunks; ++ci, w *= chunk_taper) total += w;
+		size_t made = 0;
+		w = 1.0;
+		for (size_t ci = 0; ci < n_chunks; ++ci, w *= chunk_taper) {
+			acc += w;
+			size_t hi = ci + 1 == n_chunks ? m : std::min(m, ((size_t) ((double) m * (acc / total)) + 31) / 32 * 32);
+			if (hi > cb[made]) cb[++made] = hi;
+		}
+		n_chunks = made ? made : 1;
+		cb[n_chunks] = m;
+	}
+	size_t chunk_m = 0;  // the largest chunk: scratch and result blocks are sized for it
+	for (size_t ci = 0; ci < n_chunks; ++ci) chunk_m = std::max(chunk_m, cb[ci + 1] - cb[ci]);
 	const size_t in_b = m * stride * 8, words = (m + 31) / 32;
 	const size_t qb = motion_scratch_bytes(chunk_m, robot->dev.n_boxes) + (use_side ? motion_tail_queue_bytes(chunk_m, robot->dev.n_boxes) : 0);
 	size_t o_a = c.take(in_b), o_b = c.take(in_b), o_first = c.take(m * 4), o_slerp = c.take(m * 32);
@@ -1011,8 +1037,16 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	const size_t qb_all = c.off - o_q[0];  // (the rare whole-batch re-run uses the chunks' queues as one)
 	// a chunk's results — hit words, boundary-case words, step counts, toi — sit in one block, so that they come back in ONE copy
 	auto up = [](size_t x) { return (x + 255) & ~(size_t) 255; };
-	const size_t cw = (chunk_m + 31) / 32;
-	const size_t b_unc = up(cw * 4), b_steps = b_unc + up(cw * 4), b_toi = b_steps + up(chunk_m * 4), b_size = b_toi + (toi ? up(chunk_m * 8) : 0);
+	struct BlockLayout {
+		size_t unc, steps, toi, size;
+	};
+	auto block_layout = [&](size_t mc) {  // of a chunk of mc motions: only what the chunk needs travels back
+		const size_t cw = (mc + 31) / 32;
+		BlockLayout l;
+		l.unc = up(cw * 4), l.steps = l.unc + up(cw * 4), l.toi = l.steps + up(mc * 4), l.size = l.toi + (toi ? up(mc * 8) : 0);
+		return l;
+	};
+	const size_t b_size = block_layout(chunk_m).size;  // blocks are spaced for the largest chunk
 	size_t o_blk[Workspace::MAX_CHUNKS];
 	for (size_t ci = 0; ci < n_chunks; ++ci) o_blk[ci] = c.take(b_size);
 	CU(ws->reserve(c.off, (host_hi - out_lo) + n_chunks * b_size));
@@ -1023,7 +1057,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		CU(cudaEventRecord(ws->ev_start, stream));
 		CU(cudaStreamWaitEvent(ws->copy_in, ws->ev_start, 0));
 		for (size_t ci = 0; ci < n_chunks; ++ci) {
-			const size_t lo = ci * chunk_m, hi = std::min(m, lo + chunk_m);
+			const size_t lo = cb[ci], hi = cb[ci + 1];
 			if (lo >= hi) break;
 			if (trace && ci < 2) {
 				for (int k = 0; k < 4; ++k)
@@ -1037,7 +1071,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		}
 	}
 	for (size_t ci = 0; ci < n_chunks; ++ci) {
-		const size_t lo = ci * chunk_m, hi = std::min(m, lo + chunk_m);
+		const size_t lo = cb[ci], hi = cb[ci + 1];
 		if (lo >= hi) break;
 		const size_t mc = hi - lo, w_lo = lo / 32, w_n = (mc + 31) / 32;
 		cudaStream_t s = use_side ? ws->side[ci] : stream;
@@ -1055,14 +1089,15 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		}
 		if (trace && use_side && ci < 2) CU(cudaEventRecord(tev[ci][1], s));  // (kernels start here: after the chunk has arrived)
 		char *blk = D + o_blk[ci];
+		const BlockLayout L = block_layout(mc);
 		auto enqueue_chunk = [&](const MotionOverlap *ov) -> cudaError_t {
 			cudaError_t e = launch_check_motions(scene->dev, rdev, (const double *) (D + o_a) + lo * stride, (const double *) (D + o_b) + lo * stride, mc,
-												 stride, js, max_step, nullptr, (uint32_t *) blk, toi ? (double *) (blk + b_toi) : nullptr,
-												 (uint32_t *) (blk + b_steps), (uint32_t *) (blk + b_unc), (unsigned *) (D + o_first) + lo,
+												 stride, js, max_step, nullptr, (uint32_t *) blk, toi ? (double *) (blk + L.toi) : nullptr,
+												 (uint32_t *) (blk + L.steps), (uint32_t *) (blk + L.unc), (unsigned *) (D + o_first) + lo,
 												 D + o_slerp + lo * 32, D + o_q[ci], qb, motion_survivors(mc), s, ov);
 			if (e != cudaSuccess) return e;
 			if (trace && ci < 2 && !ov) cudaEventRecord(tev[ci][2], s);
-			return cudaMemcpyAsync(HB + ci * b_size, blk, b_size, cudaMemcpyDeviceToHost, s);
+			return cudaMemcpyAsync(HB + ci * b_size, blk, L.size, cudaMemcpyDeviceToHost, s);
 		};
 		// Chunked calls replay the chunk's kernels + result copy from a cached CUDA graph when nothing about the call's shape has
 		// changed since it was recorded (MGODPL_E2E_GRAPHS=0: plain launches).
@@ -1110,6 +1145,8 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	// Results of chunk ci = motions [lo, hi) are in pinned memory: look for step counts to fix up and hand the range to the caller.
 	auto deliver = [&](size_t ci, size_t lo, size_t hi) {
 		const char *hb = HB + ci * b_size;
+		const BlockLayout L = block_layout(hi - lo);
+		const size_t b_unc = L.unc, b_steps = L.steps, b_toi = L.toi;
 		const uint32_t *c_hit = (const uint32_t *) hb, *c_unc = (const uint32_t *) (hb + b_unc), *c_steps = (const uint32_t *) (hb + b_steps);
 		const size_t w_lo = lo / 32, w_n = (hi - lo + 31) / 32;
 		for (size_t w = 0; w < w_n; ++w) {
@@ -1132,9 +1169,9 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	};
 	if (use_side) {
 		// a chunk's results are handed over while the chunks behind it are still on the GPU
-		for (size_t ci = 0; ci < n_chunks && ci * chunk_m < m; ++ci) {
+		for (size_t ci = 0; ci < n_chunks; ++ci) {
 			CU(cudaEventSynchronize(ws->ev_chunk[ci]));
-			deliver(ci, ci * chunk_m, std::min(m, (ci + 1) * chunk_m));
+			deliver(ci, cb[ci], cb[ci + 1]);
 		}
 	}
 	CU(cudaStreamSynchronize(stream));
