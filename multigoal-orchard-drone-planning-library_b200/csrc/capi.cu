@@ -63,6 +63,7 @@ struct DeviceGuard {
 	DeviceGuard &operator=(const DeviceGuard &) = delete;
 };
 
+static constexpr int E2E_PRIO_DEFAULT = 0;
 /// A growable device + pinned-host staging area, one per in-flight host-buffer call.
 struct Workspace {
 	char *dev = nullptr, *host = nullptr;
@@ -95,11 +96,19 @@ struct Workspace {
 		if (copy_in) return cudaSuccess;
 		cudaError_t e = cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking);
 		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
+		// MGODPL_E2E_PRIO (experiment): 1 = earlier chunks at higher stream priority (they retire first and leave the SMs to the
+		// chunks behind them), 2 = later chunks at higher priority (the chunk the call ends on is served first); 0 = all equal.
+		const char *pe = getenv("MGODPL_E2E_PRIO");
+		const int prio_mode = pe ? atoi(pe) : E2E_PRIO_DEFAULT;
+		int least = 0, greatest = 0;
+		if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&least, &greatest);  // numerically: greatest <= least
 		for (size_t i = 0; i < MAX_CHUNKS && e == cudaSuccess; ++i) {
-			e = cudaStreamCreateWithFlags(&side[i], cudaStreamNonBlocking);
+			const int levels = least - greatest, rank = (int) std::min<size_t>(i, (size_t) std::max(levels, 0));
+			const int prio = prio_mode == 1 ? std::min(least, greatest + rank) : prio_mode == 2 ? std::max(greatest, least - rank) : least;
+			e = cudaStreamCreateWithPriority(&side[i], cudaStreamNonBlocking, prio);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_chunk[i], cudaEventDisableTiming);
-			if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&overlap[i].side, cudaStreamNonBlocking);
+			if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&overlap[i].side, cudaStreamNonBlocking, prio);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&overlap[i].ev_head, cudaEventDisableTiming);
 			if (e == cudaSuccess) e = cudaEventCreateWithFlags(&overlap[i].ev_tail, cudaEventDisableTiming);
 		}
@@ -980,7 +989,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 	static const bool trace = getenv("MGODPL_TRACE_E2E") != nullptr;  // dev aid: where a host-buffer call spends its time
 	auto now = [] { return std::chrono::steady_clock::now(); };
 	const auto t_begin = now();
-	static thread_local cudaEvent_t tev[2][4] = {};
+	static thread_local cudaEvent_t tev[Workspace::MAX_CHUNKS][5] = {};  // trace only: copy start / end, kernels start / end, results on the host
 	ROBOT_ON_SCENE_DEVICE(rdev);
 	Lease ws(scene->pool);
 	Carver c;
@@ -1059,15 +1068,15 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		for (size_t ci = 0; ci < n_chunks; ++ci) {
 			const size_t lo = cb[ci], hi = cb[ci + 1];
 			if (lo >= hi) break;
-			if (trace && ci < 2) {
-				for (int k = 0; k < 4; ++k)
+			if (trace) {
+				for (int k = 0; k < 5; ++k)
 					if (!tev[ci][k]) CU(cudaEventCreate(&tev[ci][k]));
 				CU(cudaEventRecord(tev[ci][0], ws->copy_in));
 			}
 			CU(cudaMemcpyAsync(D + o_a + lo * stride * 8, a + lo * stride, (hi - lo) * stride * 8, cudaMemcpyHostToDevice, ws->copy_in));
 			CU(cudaMemcpyAsync(D + o_b + lo * stride * 8, b + lo * stride, (hi - lo) * stride * 8, cudaMemcpyHostToDevice, ws->copy_in));
 			CU(cudaEventRecord(ws->ev_in[ci], ws->copy_in));
-			if (trace && ci < 2) CU(cudaEventRecord(tev[ci][1], ws->copy_in));
+			if (trace) CU(cudaEventRecord(tev[ci][1], ws->copy_in));
 		}
 	}
 	for (size_t ci = 0; ci < n_chunks; ++ci) {
@@ -1079,7 +1088,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 			CU(cudaStreamWaitEvent(s, ws->ev_in[ci], 0));
 		} else {
 			if (trace) {
-				for (int k = 0; k < 4; ++k)
+				for (int k = 0; k < 5; ++k)
 					if (!tev[ci][k]) CU(cudaEventCreate(&tev[ci][k]));
 				CU(cudaEventRecord(tev[ci][0], s));
 			}
@@ -1087,7 +1096,7 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 			CU(cudaMemcpyAsync(D + o_b, b, in_b, cudaMemcpyHostToDevice, s));
 			if (trace) CU(cudaEventRecord(tev[ci][1], s));
 		}
-		if (trace && use_side && ci < 2) CU(cudaEventRecord(tev[ci][1], s));  // (kernels start here: after the chunk has arrived)
+		if (trace) CU(cudaEventRecord(tev[ci][2], s));  // (kernels may start here: the chunk has arrived)
 		char *blk = D + o_blk[ci];
 		const BlockLayout L = block_layout(mc);
 		auto enqueue_chunk = [&](const MotionOverlap *ov) -> cudaError_t {
@@ -1096,8 +1105,10 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 												 (uint32_t *) (blk + L.steps), (uint32_t *) (blk + L.unc), (unsigned *) (D + o_first) + lo,
 												 D + o_slerp + lo * 32, D + o_q[ci], qb, motion_survivors(mc), s, ov);
 			if (e != cudaSuccess) return e;
-			if (trace && ci < 2 && !ov) cudaEventRecord(tev[ci][2], s);
-			return cudaMemcpyAsync(HB + ci * b_size, blk, L.size, cudaMemcpyDeviceToHost, s);
+			if (trace && !ov) cudaEventRecord(tev[ci][3], s);
+			e = cudaMemcpyAsync(HB + ci * b_size, blk, L.size, cudaMemcpyDeviceToHost, s);
+			if (trace && !ov && e == cudaSuccess) e = cudaEventRecord(tev[ci][4], s);
+			return e;
 		};
 		// Chunked calls replay the chunk's kernels + result copy from a cached CUDA graph when nothing about the call's shape has
 		// changed since it was recorded (MGODPL_E2E_GRAPHS=0: plain launches).
@@ -1194,14 +1205,11 @@ int mgodpl_check_motions(mgodpl_scene *scene, const mgodpl_robot *robot, const d
 		auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
 		fprintf(stderr, "[mgodpl] check_motions m=%zu: enqueue %.0f us, wait + fix-up scan + copy-out %.0f us, re-run %.0f us (%zu re-derived)\n", m,
 				us(t_begin, t_enqueued), us(t_enqueued, t_synced), us(t_synced, now()), n_fix);
-		for (size_t ci = 0; ci < n_chunks && ci < 2; ++ci) {
-			float h2d = 0, ker = 0, d2h = 0, off = 0;
-			cudaEventElapsedTime(&h2d, tev[ci][0], tev[ci][1]);
-			cudaEventElapsedTime(&ker, tev[ci][1], tev[ci][2]);
-			cudaEventElapsedTime(&d2h, tev[ci][2], tev[ci][3]);
-			cudaEventElapsedTime(&off, tev[0][0], tev[ci][0]);
-			fprintf(stderr, "[mgodpl]   chunk %zu: starts +%.0f us, H2D %.0f us, kernels %.0f us, D2H %.0f us\n", ci, off * 1e3, h2d * 1e3,
-					ker * 1e3, d2h * 1e3);
+		for (size_t ci = 0; ci < n_chunks; ++ci) {  // device timeline, microseconds after the first input copy started
+			float t[5] = {};
+			for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&t[k], tev[0][0], tev[ci][k]);
+			fprintf(stderr, "[mgodpl]   chunk %zu (%zu motions): input copy %.0f-%.0f us, kernels %.0f-%.0f us, results on the host %.0f us\n", ci,
+					cb[ci + 1] - cb[ci], t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3);
 		}
 	}
 	ws.settled = true;

@@ -1,4 +1,4 @@
-"""Dev tool: host-buffer motion call (100 k motions) under different chunk layouts — MGODPL_E2E_CHUNKS x MGODPL_E2E_TAPER.
+"""Dev tool: host-buffer motion call (100 k motions) under different chunk layouts — MGODPL_E2E_CHUNKS x MGODPL_E2E_TAPER x MGODPL_E2E_PRIO (arguments: chunks:taper[:prio] ...).
 One subprocess per setting (the knobs are read once per process); every setting's result hash must equal the first one's."""
 import hashlib
 import os
@@ -42,13 +42,14 @@ settings = [(3, 1.0), (3, 0.7), (3, 0.5), (4, 0.7), (4, 0.55), (5, 0.6), (6, 0.6
 if len(sys.argv) > 1:
     settings = [tuple(float(x) for x in s.split(":")) for s in sys.argv[1:]]
 first = None
-for chunks, taper in settings:
-    env = dict(os.environ, MGODPL_E2E_CHUNKS=str(int(chunks)), MGODPL_E2E_TAPER=str(taper))
+for setting in settings:
+    chunks, taper, prio = (tuple(setting) + (0,))[:3]
+    env = dict(os.environ, MGODPL_E2E_CHUNKS=str(int(chunks)), MGODPL_E2E_TAPER=str(taper), MGODPL_E2E_PRIO=str(int(prio)))
     p = subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env, capture_output=True, text=True, timeout=120)
     line = [l for l in p.stdout.splitlines() if l.startswith("RESULT")]
     if not line:
-        print(f"chunks {int(chunks)} taper {taper}: FAILED rc {p.returncode}\n{p.stdout[-400:]}\n{p.stderr[-800:]}", flush=True)
+        print(f"chunks {int(chunks)} taper {taper} prio {int(prio)}: FAILED rc {p.returncode}\n{p.stdout[-400:]}\n{p.stderr[-800:]}", flush=True)
         continue
     hashes = line[0].split("hash ")[1]
     first = first or hashes
-    print(f"chunks {int(chunks)} taper {taper}: {line[0][7:]} {'' if hashes == first else '  <-- RESULTS DIFFER'}", flush=True)
+    print(f"chunks {int(chunks)} taper {taper} prio {int(prio)}: {line[0][7:]} {'' if hashes == first else '  <-- RESULTS DIFFER'}", flush=True)
