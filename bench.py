@@ -11,7 +11,8 @@ One step = one pass of the hot path over one batch of synthetic input:
   value     collision-checked robot states per second, counted the way the reference would count them
             (a motion that first collides at step k costs k+1 state checks, a free one n_steps+1), inputs resident in
             HBM, device time from CUDA events on the launching stream, L2 flushed before every timed step.
-  e2e       the same metric through the host-buffer C ABI call (pinned host inputs, H2D + kernel + D2H inside).
+  e2e       the same metric through the host-buffer C ABI call (pinned host inputs, H2D + kernel + D2H inside): the sum of the
+            synchronous calls' wall times; clocks are queried between the calls, from the calling thread.
 With N > 1 (torchrun) every rank holds a replica of the scene and validates its own 100 000 motions (weak scaling);
 the packed result words are all-gathered over NCCL inside the step.
 
@@ -80,6 +81,9 @@ class ClockSampler(threading.Thread):
         self.index, self.sm, self.max_sm, self.mask, self.stop_flag, self.how = index, [], None, 0, threading.Event(), "nvml"
         self.ready = threading.Event()  # set after the first sample: the caller starts its warm-up only then
         self.period = 0.0005            # the timed region of a 20-step run lasts a few ms
+        self.paused = threading.Event() # set: the thread stops polling; the owner samples with sample_now() instead
+        self.lock = threading.Lock()    # held around a query, so that pause() returns only when none is in flight
+        self._query = None
 
     def mark(self):
         """Forget what was sampled so far (called right before the warm-up steps)."""
@@ -95,9 +99,13 @@ class ClockSampler(threading.Thread):
             h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
             reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self._query = lambda: (pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), int(reasons(h)))
             while not self.stop_flag.is_set():
-                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-                self.mask |= int(reasons(h))
+                if not self.paused.is_set():
+                    with self.lock:
+                        sm, mask = self._query()
+                        self.sm.append(sm)
+                        self.mask |= mask
                 self.ready.set()
                 self.stop_flag.wait(self.period)
             return
@@ -107,6 +115,9 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         bits = [0x8, 0x40, 0x20, 0x4]
         while not self.stop_flag.is_set():
+            if self.paused.is_set():
+                self.stop_flag.wait(0.05)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -121,6 +132,24 @@ class ClockSampler(threading.Thread):
                 pass
             self.ready.set()
             self.stop_flag.wait(0.05)
+
+    def pause(self):
+        """No more polling from the thread (NVML queries take driver locks that CUDA calls of other threads wait for: polled
+        every 2 ms they made the host-buffer calls 15 % slower, every 0.5 ms 2.5x).  Returns once no query is in flight."""
+        self.paused.set()
+        with self.lock:
+            self.sm, self.mask = [], 0
+
+    def sample_now(self):
+        """One sample from the calling thread (between two host-buffer calls: it cannot hold up a CUDA call of this thread)."""
+        if self._query is None:
+            return
+        try:
+            sm, mask = self._query()
+            self.sm.append(sm)
+            self.mask |= mask
+        except Exception:
+            pass
 
     def summary(self):
         if not self.sm:
@@ -252,8 +281,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks_timed = sampler.summary()  # warm-up + timed region; the thread keeps sampling through the e2e calls below,
-    sampler.period = 0.002            # less often: NVML queries take driver locks the host-buffer calls also need
+    clocks_timed = sampler.summary()  # warm-up + timed region
+    sampler.pause()                   # the e2e calls below are sampled from this thread, between calls (see ClockSampler.pause)
     d_hit = hit_groups[((args.steps - 1) // G) & 1][(args.steps - 1) % G]
     step_ms = [s.elapsed_time(e) for s, e in ev]
     total_ms = torch.tensor([sum(step_ms) + ev[-1][1].elapsed_time(tail)], dtype=torch.float64, device=dev)
@@ -303,13 +332,18 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, 10))
     e2e_calls = []
     sampler.sm, sampler.mask = [], 0
+    sampler.sample_now()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         t1 = time.perf_counter()
         mg.capi.check_motions(scene, robot, na, nb, MAX_STEP, True, stream=stream, out=res)  # returns with the results in host memory
         e2e_calls.append((time.perf_counter() - t1) * 1e3)
+        sampler.sample_now()  # clocks + throttle reasons right after the call, outside its timer
     torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    # every call is synchronous (inputs from pinned host memory in, results in host memory when it returns): the e2e time is the
+    # sum of the calls' own wall times; the NVML queries between them are not part of any call
+    e2e_s = torch.tensor([sum(e2e_calls) * 1e-3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     assert np.array_equal(mg.capi.unpack_bits(res["words"], m), hit), "host-buffer and device-buffer paths disagree"
@@ -356,7 +390,8 @@ def run_ours(args):
         "states_checked_per_motion": states_all / motions_all, "collision_rate": float(hit.mean()),
         "e2e": {"value": e2e_value, "unit": "states/s", "h2d_bytes_per_step": int(2 * m * stride * 8),
                 "d2h_bytes_per_step": int(2 * words * 4 + m * 4 + m * 8), "steps": e2e_steps,
-                "ms_per_call": [round(x, 4) for x in e2e_calls], "warmup_calls": len(e2e_warm),
+                "ms_per_call": [round(x, 4) for x in e2e_calls], "timed": "sum of the synchronous calls' wall times, max over ranks",
+                "wall_ms_with_clock_queries_between_calls": round(e2e_wall_ms, 4), "warmup_calls": len(e2e_warm),
                 "warmup_first_last_ms": [round(e2e_warm[0], 4), round(e2e_warm[-1], 4)]},
         # our kernels inside the device-timed region, per step: k_motion_ranges, 2 x (k_expand_motion_steps, k_traverse), k_finish_motions
         "gpu_launches": LAUNCHES_PER_STEP * args.steps,
