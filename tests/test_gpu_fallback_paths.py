@@ -26,6 +26,9 @@ out = {}
 out["states"] = hashlib.sha1(mg.check_states(scene, robot, st, packed=True).tobytes()).hexdigest()
 m = mg.check_motions(scene, robot, st[:8000], st[8000:16000])
 out["motions"] = hashlib.sha1(m["words"].tobytes() + np.nan_to_num(m["toi"], nan=-1).tobytes()).hexdigest()
+# large enough (>= 32768) for the chunked host-buffer path, ragged so that the last chunk ends inside a result word
+mc = mg.check_motions(scene, robot, st[:40003], st[19997:60000])
+out["motions_chunked"] = hashlib.sha1(mc["words"].tobytes() + np.nan_to_num(mc["toi"], nan=-1).tobytes() + mc["n_steps"].tobytes()).hexdigest()
 g = mg.sample_goals(scene, robot, tree.fruit_centers, 512, draws=mg.robots.goal_draws(model, mg.robots.Mt19937(42), 512))
 out["goals"] = hashlib.sha1(g["words"].tobytes() + g["collisions"].tobytes()).hexdigest()
 rng = np.random.default_rng(1)
@@ -62,8 +65,11 @@ def test_overflow_and_no_prefilter_paths_agree_with_the_fast_path(gpu):
         "fixed head of 4 steps": {"MGODPL_HEAD_STEPS": "4"},
         "no clearance grid (bounds / root-record culls only)": {"MGODPL_CLEARANCE_GRID": "0"},
         "coarse clearance grid (4096 cells)": {"MGODPL_CLEARANCE_CELLS": "4096"},
+        "host-buffer call in one chunk": {"MGODPL_E2E_CHUNKS": "1"},
+        "host-buffer call in eight steeply tapered chunks, plain launches": {"MGODPL_E2E_CHUNKS": "8", "MGODPL_E2E_TAPER": "0.3", "MGODPL_E2E_GRAPHS": "0"},
+        "host-buffer call in three equal chunks on prioritised streams": {"MGODPL_E2E_CHUNKS": "3", "MGODPL_E2E_TAPER": "1", "MGODPL_E2E_PRIO": "1"},
     }
     for name, env in variants.items():
         got = run_variant(env)
-        for key in ("states", "motions", "goals", "boxes"):
+        for key in ("states", "motions", "motions_chunked", "goals", "boxes"):
             assert got[key] == base[key], f"{name}: {key} differs from the default configuration"
