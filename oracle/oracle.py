@@ -207,6 +207,25 @@ def box_tri(tf7, size3, tri9):
     return bool(hit), cl.value
 
 
+MPR_STAGES = ("portal discovery: apart", "portal discovery: centre on the origin ray", "refinement: origin enclosed",
+              "refinement: support plane short of the origin", "refinement: stopped at the tolerance", "iteration guard")
+
+
+def box_tri_batch(tf7, size3, tri9, tolerance: float = 1e-6):
+    """n box / triangle pairs: the exact answer (hit, signed clearance) and the libccd-style MPR second opinion
+    (mpr_second_opinion.hpp; mpr_stage indexes MPR_STAGES).  Never "FCL": a restatement of the published algorithm."""
+    tf7, size3 = _arr(tf7).reshape(-1, 7), _arr(size3).reshape(-1, 3)
+    tri9 = _arr(tri9).reshape(-1, 9)
+    n = len(tf7)
+    assert len(size3) == n and len(tri9) == n
+    hit, mpr_hit = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    cl, it, st = np.zeros(n), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    i32p = C.POINTER(C.c_int32)
+    lib().orc_box_tri_batch(C.c_size_t(n), _d(tf7), _d(size3), _d(tri9), C.c_double(tolerance), hit.ctypes.data_as(_u8p), _d(cl),
+                            mpr_hit.ctypes.data_as(_u8p), it.ctypes.data_as(i32p), st.ctypes.data_as(i32p))
+    return dict(hit=hit.astype(bool), clearance=cl, mpr_hit=mpr_hit.astype(bool), mpr_iterations=it, mpr_stage=st)
+
+
 class Scene:
     def __init__(self, verts, tris):
         self.verts = _arr(verts).reshape(-1, 3)

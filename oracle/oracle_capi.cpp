@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see mgodpl_oracle.hpp).  Plain C entry points over the fp64 restatement so
 // that tests/ and bench.py's cpu_baseline leg can drive it through ctypes.  Nothing in the product links this.
 #include "mgodpl_oracle.hpp"
+#include "mpr_second_opinion.hpp"
 
 #include <atomic>
 #include <cstring>
@@ -173,6 +174,28 @@ int orc_box_tri(const double *tf7, const double *size3, const double *tri9, doub
 	   p2 = b.to_local({tri9[6], tri9[7], tri9[8]});
 	if (clearance_or_null) *clearance_or_null = box_tri_clearance(b.h, p0, p1, p2);
 	return box_tri_sat(b.h, p0, p1, p2).hit;
+}
+
+/// n box / triangle pairs at once: the exact answer (hit, signed clearance) and the libccd-style MPR second opinion
+/// (mpr_second_opinion.hpp: contact reported, refinement rounds, stage at which it decided).  Any output may be null.
+void orc_box_tri_batch(size_t n, const double *tf7, const double *size3, const double *tri9, double tolerance, uint8_t *hit, double *clearance,
+					   uint8_t *mpr_hit, int32_t *mpr_iterations, int32_t *mpr_stage) {
+	for (size_t i = 0; i < n; ++i) {
+		const Tf tf = load_tf(tf7 + 7 * i);
+		const V3 size{size3[3 * i], size3[3 * i + 1], size3[3 * i + 2]};
+		const double *t = tri9 + 9 * i;
+		const V3 a{t[0], t[1], t[2]}, b{t[3], t[4], t[5]}, c{t[6], t[7], t[8]};
+		Obb o(tf, size);
+		const V3 p0 = o.to_local(a), p1 = o.to_local(b), p2 = o.to_local(c);
+		if (hit) hit[i] = box_tri_sat(o.h, p0, p1, p2).hit;
+		if (clearance) clearance[i] = box_tri_clearance(o.h, p0, p1, p2);
+		if (mpr_hit || mpr_iterations || mpr_stage) {
+			const mpr::Outcome r = mpr::box_triangle(tf, size, a, b, c, tolerance);
+			if (mpr_hit) mpr_hit[i] = (uint8_t) r.intersect;
+			if (mpr_iterations) mpr_iterations[i] = r.iterations;
+			if (mpr_stage) mpr_stage[i] = r.stage;
+		}
+	}
 }
 
 // ---- scene -------------------------------------------------------------------------------------------------

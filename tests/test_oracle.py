@@ -129,6 +129,97 @@ def test_sat_against_brute_force_distance(oracle):
         assert (cl <= 0) == hit
 
 
+# ---- "libccd-style" second opinion (last row): how an MPR intersection query answers the same pairs ---------
+def _random_pairs(rng, n):
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    tf = np.concatenate([rng.uniform(-1, 1, (n, 3)), q], axis=1)
+    size = rng.uniform(0.05, 1.0, (n, 3))
+    tri = rng.uniform(-1.2, 1.2, (n, 1, 3)) + rng.normal(scale=0.4, size=(n, 3, 3))
+    return tf, size, tri
+
+
+def test_mpr_second_opinion_known_answers(oracle):
+    unit = [0, 0, 0, 0, 0, 0, 1]
+    tris = np.array([[[2, 0, 0], [2, 1, 0], [2, 0, 1]],                    # well clear of the +x face
+                     [[-2, 0, 0], [2, 0.1, 0], [0, 0, 2]],                  # piercing the box
+                     [[0.1, 0.1, 0.1], [0.2, 0.1, 0.1], [0.1, 0.2, 0.1]],   # entirely inside
+                     [[0.6, 0.6, 0.6], [1.6, 0.6, 0.6], [0.6, 1.6, 0.6]],   # vertex 0.1 beyond the corner
+                     [[0.4, 0.4, 0.4], [1.6, 0.6, 0.6], [0.6, 1.6, 0.6]]], float)  # vertex inside the corner
+    r = oracle.box_tri_batch([unit] * 5, [[1, 1, 1]] * 5, tris)
+    assert r["hit"].tolist() == [False, True, True, False, True]
+    assert r["mpr_hit"].tolist() == r["hit"].tolist()
+    assert r["mpr_stage"][0] in (0, 3) and r["mpr_stage"][1] in (1, 2)
+    assert all(0 <= st < len(oracle.MPR_STAGES) for st in r["mpr_stage"])
+
+
+def test_mpr_second_opinion_agrees_with_the_exact_test_on_random_pairs(oracle):
+    tf, size, tri = _random_pairs(np.random.default_rng(0), 100000)
+    r = oracle.box_tri_batch(tf, size, tri)
+    assert 0.02 < r["hit"].mean() < 0.2
+    assert np.array_equal(r["hit"], r["mpr_hit"])
+    assert r["mpr_iterations"].max() < 50 and not (r["mpr_stage"] == 5).any()
+
+
+@pytest.mark.parametrize("target", [1e-3, 1e-5, 1e-7, 1e-9, -1e-9, -1e-7, -1e-5, -1e-3])
+def test_mpr_second_opinion_near_contact_in_general_position(oracle, target):
+    """Pairs pushed along a random direction until the exact signed clearance equals `target` (bisection): vertex / face and
+    edge / edge contacts in general position.  The MPR query decides them by the sign of a support-plane offset, not by its
+    1e-6 tolerance, so it agrees with the exact test far inside the band of BASELINE.json's north_star."""
+    rng = np.random.default_rng(3)
+    tf, size, tri = _random_pairs(rng, 1500)
+    d = rng.normal(size=(len(tf), 1, 3))
+    d /= np.linalg.norm(d, axis=2, keepdims=True)
+
+    def clearance(s):
+        return oracle.box_tri_batch(tf, size, tri + d * s[:, None, None])["clearance"]
+    grid = np.linspace(-4, 4, 81)
+    cls = np.stack([clearance(np.full(len(tf), g)) for g in grid])
+    lo, hi = grid[cls.argmin(axis=0)], np.full(len(tf), 8.0)     # lo: the deepest point of the sweep, hi: far away
+    usable = cls.min(axis=0) < target
+    for _ in range(70):
+        mid = 0.5 * (lo + hi)
+        below = clearance(mid) < target
+        lo, hi = np.where(below, mid, lo), np.where(below, hi, mid)
+    r = oracle.box_tri_batch(tf, size, tri + d * (0.5 * (lo + hi))[:, None, None])
+    ok = usable & (np.abs(r["clearance"] - target) <= 1e-3 * abs(target))
+    assert ok.sum() > 150
+    assert (r["hit"][ok] == (target < 0)).all()
+    assert np.array_equal(r["mpr_hit"][ok], r["hit"][ok])
+
+
+@pytest.mark.parametrize("rotated", [False, True])
+def test_mpr_second_opinion_face_parallel_triangles(oracle, rotated):
+    """The degenerate case: a triangle parallel to a box face (support directions with components that are exactly zero in the box
+    frame).  Agreement down to 1e-9 m either side; at exactly zero clearance rounding decides both tests, and they may differ —
+    that, not 1e-6 m, is the width of the band this second opinion sees."""
+    rng = np.random.default_rng(4)
+    n = 1500
+    size = rng.uniform(0.1, 1.0, (n, 3))
+    h = size / 2
+    xy = rng.uniform(-0.8, 0.8, (n, 1, 2)) * h[:, None, :2] + rng.normal(scale=0.3, size=(n, 3, 2))
+    q = rng.normal(size=(n, 4)) if rotated else np.tile([0, 0, 0, 1.0], (n, 1))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    t = rng.uniform(-1, 1, (n, 3))
+    tf = np.concatenate([t, q], axis=1)
+    for target in (1e-5, 1e-7, 1e-9, -1e-9, -1e-7, -1e-5):
+        local = np.concatenate([xy, (h[:, 2] + target)[:, None, None] * np.ones((n, 3, 1))], axis=2)
+        world = np.stack([[oracle.tf_then(tf[i], np.concatenate([p, [0, 0, 0, 1]]))[:3] for p in local[i]] for i in range(0, n, 5)])
+        r = oracle.box_tri_batch(tf[::5], size[::5], world)
+        assert np.array_equal(r["mpr_hit"], r["hit"]), target
+        if target > 0:
+            assert not r["hit"].any()
+        else:
+            assert r["hit"].mean() > 0.5                           # (some triangles lie beside the face, not over it)
+    local = np.concatenate([xy, h[:, 2][:, None, None] * np.ones((n, 3, 1))], axis=2)   # exactly touching
+    world = np.stack([[oracle.tf_then(tf[i], np.concatenate([p, [0, 0, 0, 1]]))[:3] for p in local[i]] for i in range(0, n, 5)])
+    r = oracle.box_tri_batch(tf[::5], size[::5], world)
+    touching = np.abs(r["clearance"]) < 1e-12                      # over the face: clearance is rounding noise around zero
+    assert touching.sum() > 100
+    assert np.array_equal(r["mpr_hit"][~touching], r["hit"][~touching])   # beside the face: clearly apart, both say so
+    assert (r["mpr_hit"][touching] == r["hit"][touching]).mean() > 0.5    # on the face: either answer is defensible
+
+
 # ---- golden fixtures generated from the reference's own sources ------------------------------------------------------
 @pytest.fixture(scope="module")
 def golden():
