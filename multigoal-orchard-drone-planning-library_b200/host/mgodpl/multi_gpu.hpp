@@ -17,7 +17,8 @@
 
 namespace mgodpl::gpu {
 
-/// [lo, hi) of shard `rank` of n queries; lo is a multiple of `align`, shard sizes differ by at most `align`.
+/// [lo, hi) of shard `rank` of n queries; lo is a multiple of `align`; shards differ by one block of `align` at most, and the last
+/// non-empty shard may additionally end inside a block (so sizes differ by less than 2 x align).
 inline std::pair<size_t, size_t> shard_range(size_t n, size_t rank, size_t world, size_t align = 32) {
 	if (!world || rank >= world) throw std::invalid_argument("bad rank / world size");
 	const size_t blocks = (n + align - 1) / align, per = blocks / world, extra = blocks % world;

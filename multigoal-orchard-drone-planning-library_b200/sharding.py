@@ -13,7 +13,8 @@ import numpy as np
 
 
 def shard_range(n: int, rank: int, world_size: int, align: int = 32) -> tuple[int, int]:
-    """[lo, hi) of `rank`'s share of n queries; lo is a multiple of `align`, shares differ by at most `align`."""
+    """[lo, hi) of `rank`'s share of n queries; lo is a multiple of `align`; shares differ by one block of `align`
+    at most, and the last non-empty share may additionally end inside a block (so sizes differ by less than 2 x align)."""
     if world_size <= 0 or not (0 <= rank < world_size):
         raise ValueError("bad rank / world_size")
     blocks = (n + align - 1) // align

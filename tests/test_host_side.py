@@ -185,3 +185,14 @@ def test_two_rank_gloo_shard_and_gather(tmp_path):
     for p, out in zip(procs, outs):
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+def test_cpp_facade_host_logic_against_the_oracle(mg):
+    """tests/cpp/test_host.cpp: the C++ facade's device-free parts (FK, distance, interpolation, state tools, goal projection,
+    closure-taking shortcutting over the oracle's motion check, sharding arithmetic, roadmap walking, ABI argument errors)."""
+    mg.capi.lib()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "cpp")])
+    p = subprocess.run([os.path.join(ROOT, "tests", "cpp", "test_host")], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    m = re.search(r"(\d+) checks, 0 failed", p.stdout)
+    assert m and int(m.group(1)) > 4000
