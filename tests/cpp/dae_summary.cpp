@@ -3,6 +3,7 @@
 // independent reading of the same file that follows assimp's documented behaviour (mesh_from_dae.cpp:17-85).
 #include <cinttypes>
 #include <cstdio>
+#include <string>
 
 #include "../../multigoal-orchard-drone-planning-library_b200/host/mgodpl/tree_meshes.hpp"
 
@@ -13,7 +14,8 @@ int main(int argc, char **argv) {
 	}
 	try {
 		const mgodpl::Mesh mesh = mgodpl::from_dae(argv[1]);
-		const auto box = mgodpl::mesh_aabb(mesh);
+		auto box = mgodpl::mesh_aabb(mesh);
+		if (mesh.vertices.empty()) box._min = box._max = {0, 0, 0};  // (an empty mesh has infinite bounds: not JSON)
 		// position-weighted sums: sensitive to the order of vertices and triangles, exactly reproducible in numpy (fp64, sequential)
 		double vsum = 0.0;
 		for (size_t i = 0; i < mesh.vertices.size(); ++i) {
@@ -28,7 +30,10 @@ int main(int argc, char **argv) {
 					mesh.vertices.size(), mesh.triangles.size(), box._min.x(), box._min.y(), box._min.z(), box._max.x(), box._max.y(), box._max.z(),
 					vsum, tsum);
 	} catch (const std::exception &e) {
-		std::printf("{\"error\": \"%s\"}\n", e.what());
+		std::string what = e.what();
+		for (char &c: what)
+			if (c == '"' || c == '\\' || (unsigned char) c < 32) c = '\'';
+		std::printf("{\"error\": \"%s\"}\n", what.c_str());
 		return 1;
 	}
 	return 0;

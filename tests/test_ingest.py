@@ -141,3 +141,28 @@ def test_from_dae_reads_the_reference_drone_model(dae_summary):
     assert rc == 0
     same(got, dae_reader.summary(*dae_reader.read(DRONE)))
     same(got, json.load(open(os.path.join(ROOT, "tests", "golden", "drone_dae_summary.json"))))
+
+
+def test_from_dae_survives_damaged_documents(dae_summary, tmp_path):
+    """Truncated, corrupted and spliced documents end in a mesh or in an exception — never in a crash (exit codes 0 / 1 only)."""
+    import random
+    doc = document(GEOMS, SCENE).encode()
+    rnd = random.Random(1)
+    splices = [b"<p>1 2 99999999999999999999</p>", b"<node>", b"</mesh>", b"-5 ", b"<![CDATA[", b"<!--", b'<instance_node url="#n1"/>', b"1e400 ", b"nan "]
+    f = tmp_path / "damaged.dae"
+    for i in range(120):
+        b = bytearray(doc)
+        if i % 4 == 0:
+            b = b[:rnd.randrange(len(b))]
+        elif i % 4 == 1:
+            for _ in range(rnd.randrange(1, 6)):
+                b[rnd.randrange(len(b))] = rnd.choice(b'<>/"= 0-9ae\n')
+        elif i % 4 == 2:
+            a = rnd.randrange(len(b))
+            del b[a:rnd.randrange(a, min(len(b), a + 200))]
+        else:
+            a = rnd.randrange(len(b))
+            b[a:a] = rnd.choice(splices)
+        f.write_bytes(bytes(b))
+        rc, out = dae_summary(f)
+        assert rc in (0, 1) and (("error" in out) == (rc == 1)), (i, rc, out)
