@@ -203,7 +203,9 @@ int mgodpl_sample_goals_device(mgodpl_scene *scene, const mgodpl_robot *robot, c
  *      query issued before every batch of PRM edge checks (src/planning/tsp_over_prm.cpp:44-45, 383-386), for all n
  *      states at once.  causal != 0: state i only sees states j < i, i.e. the roadmap as it stood when the reference
  *      inserted node i.  idx: n x k indices ascending by distance (-1 pads when fewer than k candidates exist);
- *      dist (optional): n x k distances (NaN pads).  1 <= k <= 32. ------------------------------------------------------- */
+ *      dist (optional): n x k distances (NaN pads).  1 <= k <= 32.  The k neighbours are DISTINCT; the reference's GNAT can list
+ *      one neighbour twice (its Node::split never finds a point's closest pivot, NearestNeighborsGNAT.h:398-405): with the
+ *      duplicates removed its list is the leading part of this one. ---------------------------------------------------------- */
 int mgodpl_knn(const double *states, size_t n, size_t stride, int32_t n_joint_values, int32_t k, int32_t causal, int32_t *idx,
 			   double *dist, void *stream);
 int mgodpl_knn_device(const double *d_states, size_t n, size_t stride, int32_t n_joint_values, int32_t k, int32_t causal,

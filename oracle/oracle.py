@@ -438,6 +438,18 @@ class RefRobot:
             pass
 
 
+def ref_gnat_causal_knn(states, k: int, seed: int = 42):
+    """The reference's own NearestNeighborsGNAT (greedy-k-centres pivots, equal_weights_distance) used as
+    add_and_connect_roadmap_node uses it: nearestK among the states added before, then add.  Returns (idx, dist), n x k."""
+    states = _arr(states)
+    n, stride = states.shape
+    idx = np.zeros((n, k), np.int32)
+    dist = np.zeros((n, k))
+    ref().ref_gnat_causal_knn(_d(states), C.c_size_t(n), C.c_size_t(stride), stride - 7, k, C.c_uint(seed),
+                              idx.ctypes.data_as(C.POINTER(C.c_int32)), _d(dist))
+    return idx, dist
+
+
 def ref_distance(a, b):
     a, b = _arr(a), _arr(b)
     return ref().ref_distance(_d(a), _d(b), len(a) - 7)

@@ -2,7 +2,8 @@
 // lie under /root/reference/src by oracle/Makefile (target `ref`) into oracle/_ref/libmgodpl_ref.so.  The
 // reference's planning-layer code runs unmodified: forwardKinematics, interpolate, equal_weights_distance,
 // check_robot_collision, check_motion_collides, check_path_collides, generateUniformRandomState,
-// genGoalStateUniform, fromEndEffectorAndVector, createProceduralRobotModel, meshToFclBVH.  Its two absent
+// genGoalStateUniform, fromEndEffectorAndVector, createProceduralRobotModel, meshToFclBVH, and its nearest-neighbour structure
+// (NearestNeighborsGNAT.h + GreedyKCenters.h, header-only, standard library only).  Its two absent
 // third-party dependencies (FCL, Eigen) are satisfied by oracle/shim/, which forwards to the oracle's restated
 // narrow phase and slerp; so this library pins everything ABOVE the fcl::collide call, not FCL itself.
 //
@@ -24,6 +25,8 @@
 #include "planning/fcl_utils.h"
 #include "planning/goal_sampling.h"
 #include "planning/local_optimization.h"
+#include "planning/nearest_neighbours/GreedyKCenters.h"
+#include "planning/nearest_neighbours/NearestNeighborsGNAT.h"
 #include "planning/state_tools.h"
 
 #include <fcl/narrowphase/collision_object.h>
@@ -207,6 +210,32 @@ size_t ref_mesh_components(const uint32_t *tris, size_t nt, size_t nv, uint32_t 
 		for (size_t v: c) labels[v] = (uint32_t) lo;
 	}
 	return cc.size();
+}
+
+/// The reference's OWN nearest-neighbour structure (nearest_neighbours/NearestNeighborsGNAT.h with greedy_k_centers pivots, set up
+/// as init_empty_spatial_index does, tsp_over_prm.cpp:357-390) driven the way add_and_connect_roadmap_node drives it
+/// (tsp_over_prm.cpp:33-66): for every state in turn, nearestK among the states added BEFORE it, then add it.  idx: n x k, -1
+/// padded; dist: n x k (NaN padded), in the order nearestK returns them.
+void ref_gnat_causal_knn(const double *states, size_t n, size_t stride, int js, int k, unsigned seed, int32_t *idx, double *dist) {
+	using Point = std::pair<RobotState, size_t>;
+	random_numbers::RandomNumberGenerator rng(seed);
+	const std::function<double(const Point &, const Point &)> d = [](const Point &a, const Point &b) { return equal_weights_distance(a.first, b.first); };
+	ompl::NearestNeighborsGNAT<Point>::SelectPivotFn pivots = [d, &rng](const std::vector<Point> &data, unsigned int kk) {
+		return greedy_k_centers<Point>(data, kk, d, rng, std::nullopt);
+	};
+	ompl::NearestNeighborsGNAT<Point> gnat(pivots);
+	gnat.setDistanceFunction(d);
+	std::vector<Point> near;
+	for (size_t i = 0; i < n; ++i) {
+		const RobotState s = load_state(states + i * stride, js);
+		gnat.nearestK({s, 0}, (size_t) k, near);
+		for (int j = 0; j < k; ++j) {
+			const bool have = (size_t) j < near.size();
+			idx[i * k + j] = have ? (int32_t) near[j].second : -1;
+			dist[i * k + j] = have ? equal_weights_distance(s, near[j].first) : std::nan("");
+		}
+		gnat.add({s, i});
+	}
 }
 
 }  // extern "C"

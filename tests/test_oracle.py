@@ -419,3 +419,52 @@ def test_degenerate_motion_checks_start_state_once(oracle, mg):
     inside = np.array([[0, 0, 1, 0, 0, 0, 1, 0, 0.0]])
     res = s.check_motions(r, inside, inside)
     assert res["n_steps"][0] == 0 and res["states_checked"][0] == 1 and res["hit"][0] and res["toi"][0] == 0.0
+
+
+# ---- k-NN: the oracle's causal k-NN against the reference's OWN nearest-neighbour structure ----------------
+def _distinct_prefix_equal(gnat_row, oracle_row):
+    g = [x for x in gnat_row if x >= 0]
+    distinct = list(dict.fromkeys(g))                      # order kept: ascending by distance
+    return distinct == [x for x in oracle_row if x >= 0][:len(distinct)], len(g) - len(distinct)
+
+
+def test_causal_knn_equals_the_references_gnat_golden(oracle):
+    """tests/golden/gnat_knn.json holds what the reference's NearestNeighborsGNAT returned, driven as add_and_connect_roadmap_node
+    drives it (nearestK among the nodes inserted before, then add; tsp_over_prm.cpp:33-66).  The structure answers exactly —
+    except that it can list one neighbour TWICE: Node::split (NearestNeighborsGNAT.h:380-440; the comparator at :398-405) compares d(i, j) with d(j, i) when it
+    looks for a point's closest pivot, which is never true, so every point — the other pivots included — lands in the first child
+    while those pivots also stay pivots, and nearestK then meets them twice.  With the duplicates removed, every row is the
+    leading part of the oracle's exact causal k-NN, in the same order; the library returns k DISTINCT neighbours."""
+    with open(os.path.join(os.path.dirname(GOLDEN), "gnat_knn.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) == 3
+    for c in cases:
+        robot = oracle.Robot(c["arm_length"], tuple(c["joint_types"]))
+        states = oracle.gen_uniform_states(robot, c["n"], seed=c["seed"], h_range=c["h_range"], v_range=c["v_range"])
+        idx, dist = oracle.knn(states, c["k"], causal=True)
+        dup_rows = 0
+        for i, (grow, drow) in enumerate(zip(c["gnat_idx"], c["gnat_dist"])):
+            ok, dups = _distinct_prefix_equal(grow, idx[i].tolist())
+            assert ok, (c["n"], i, grow, idx[i].tolist())
+            dup_rows += dups > 0
+            # distances bit-equal where the lists agree entry for entry (no duplicate before that entry)
+            for j, (g, h) in enumerate(zip(grow, drow)):
+                if g < 0 or g != idx[i, j]:
+                    break
+                assert float.fromhex(h) == dist[i, j]
+        assert dup_rows > 0                                   # the quirk is real and frequent (a fifth to a third of the rows)
+        assert (idx[:c["k"]] < np.arange(c["k"])[:, None]).all()   # row i only ever names nodes before i (-1 pads included)
+
+
+def test_causal_knn_equals_the_references_gnat_live(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref is only built where /root/reference exists")
+    robot = oracle.Robot(0.75, (0,))
+    states = oracle.gen_uniform_states(robot, 2500, seed=21, h_range=5.0, v_range=10.0)
+    gi, gd = oracle.ref_gnat_causal_knn(states, 10)
+    oi, _ = oracle.knn(states, 10, causal=True)
+    assert all(_distinct_prefix_equal(g, o)[0] for g, o in zip(gi.tolist(), oi.tolist()))
+    assert (np.diff(np.nan_to_num(gd, nan=1e300), axis=1) >= 0).all()    # nearestK lists nearest first (NaN pads last)
+    # a different pivot-selection seed changes the tree, never the answer
+    gi2, _ = oracle.ref_gnat_causal_knn(states, 10, seed=5)
+    assert all(_distinct_prefix_equal(g, o)[0] for g, o in zip(gi2.tolist(), oi.tolist()))
