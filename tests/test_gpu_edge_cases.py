@@ -278,6 +278,22 @@ def test_knn_matches_exhaustive_oracle(gpu, oracle, env, causal):
         assert (idx < np.arange(700)[:, None]).all()
 
 
+def test_knn_against_the_references_own_gnat(gpu, oracle):
+    """tests/golden/gnat_knn.json: what the reference's NearestNeighborsGNAT returned, driven as its PRM builder drives it
+    (tests/test_oracle.py explains the duplicates it lists): with duplicates removed, every row is the leading part of the
+    library's causal k-NN row, in the same order."""
+    with open(os.path.join(os.path.dirname(GOLDEN), "gnat_knn.json")) as f:
+        case = json.load(f)["cases"][0]            # the default 0.75 m arm, 400 nodes from the PRM sampler, k = 10
+    robot = oracle.Robot(case["arm_length"], tuple(case["joint_types"]))
+    st = oracle.gen_uniform_states(robot, case["n"], seed=case["seed"], h_range=case["h_range"], v_range=case["v_range"])
+    idx, _ = gpu.capi.knn(st, case["k"], causal=True)
+    agree = 0
+    for i, row in enumerate(case["gnat_idx"]):
+        distinct = list(dict.fromkeys(x for x in row if x >= 0))
+        agree += distinct == [x for x in idx[i].tolist() if x >= 0][:len(distinct)]
+    assert agree >= case["n"] - 2                  # (a 1-ulp near-tie may be ordered differently by the device libm)
+
+
 def test_knn_query_against_a_separate_database(gpu, oracle, env):
     """Goal samples / the start state look up their nearest *infrastructure* nodes without being part of the index
     (tsp_over_prm.cpp:297-344): exhaustive search with the oracle's equal_weights_distance."""
